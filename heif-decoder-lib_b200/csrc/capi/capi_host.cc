@@ -1,6 +1,9 @@
 // capi_host.cc — C ABI over the host front-end (include/heifcuda.h, section "host front-end").
 #include "../../../include/heifcuda.h"
 #include "../host/hevc_parse.h"
+#include "../host/heif_reader.h"
+#include <cstdlib>
+#include <cstring>
 #include <string>
 
 namespace {
@@ -13,6 +16,9 @@ void set_last_error(const std::string& s) { g_last_error = s; }
 
 struct hc_parser {
   hc::HevcIntraParser parser;
+};
+struct hc_heif {
+  hc::HeifFile file;
 };
 struct hc_records {
   std::unique_ptr<hc::PictureRecords> rec;
@@ -93,5 +99,68 @@ hc_records* hc_parse_picture(const uint8_t* data, size_t size, int stream_format
   if (hc_parser_push(&p, data, size, stream_format) != HC_OK) return nullptr;
   return hc_parser_take_picture(&p);
 }
+
+hc_heif* hc_heif_open(const uint8_t* data, size_t size) {
+  if (!data) { g_last_error = "hc_heif_open: null data"; return nullptr; }
+  hc_heif* f = new (std::nothrow) hc_heif;
+  if (!f) { g_last_error = "out of memory"; return nullptr; }
+  std::string e = f->file.parse(data, size);
+  if (!e.empty()) { g_last_error = e; delete f; return nullptr; }
+  return f;
+}
+void hc_heif_close(hc_heif* f) { delete f; }
+uint32_t hc_heif_primary_id(const hc_heif* f) { return f->file.primary_id(); }
+int hc_heif_top_level_ids(const hc_heif* f, uint32_t* ids, int max) {
+  std::vector<uint32_t> v = f->file.top_level_images();
+  for (int i = 0; i < (int)v.size() && i < max; i++) ids[i] = v[i];
+  return (int)v.size();
+}
+int hc_heif_get_image_info(const hc_heif* f, uint32_t id, hc_heif_image_info* info) {
+  const hc::HeifItem* it = f->file.item(id);
+  if (!it || !info) { g_last_error = "hc_heif_get_image_info: no such item"; return HC_ERR_ARGUMENT; }
+  memset(info, 0, sizeof(*info));
+  info->id = id;
+  info->rows = info->cols = 1;
+  info->width = it->ispe_w;
+  info->height = it->ispe_h;
+  if (f->file.is_grid(id)) {
+    hc::HeifGrid g;
+    std::string e = f->file.grid(id, g);
+    if (!e.empty()) { g_last_error = e; return HC_ERR_BITSTREAM; }
+    info->is_grid = 1;
+    info->rows = g.rows;
+    info->cols = g.cols;
+    info->width = g.out_w;
+    info->height = g.out_h;
+  }
+  info->alpha_id = f->file.alpha_item(id);
+  info->rot = it->rot;
+  info->mirror = it->mirror;
+  info->nclx_present = it->nclx.present;
+  info->primaries = it->nclx.primaries;
+  info->transfer = it->nclx.transfer;
+  info->matrix = it->nclx.matrix;
+  info->full_range = it->nclx.full_range;
+  return HC_OK;
+}
+int hc_heif_grid_tiles(const hc_heif* f, uint32_t id, uint32_t* tiles, int max) {
+  hc::HeifGrid g;
+  std::string e = f->file.grid(id, g);
+  if (!e.empty()) { g_last_error = e; return HC_ERR_BITSTREAM; }
+  for (int i = 0; i < (int)g.tiles.size() && i < max; i++) tiles[i] = g.tiles[i];
+  return (int)g.tiles.size();
+}
+int hc_heif_coded_stream(const hc_heif* f, uint32_t id, uint8_t** out, size_t* size) {
+  std::vector<uint8_t> v;
+  std::string e = f->file.coded_stream(id, v);
+  if (!e.empty()) { g_last_error = e; return HC_ERR_BITSTREAM; }
+  uint8_t* p = (uint8_t*)malloc(v.size() ? v.size() : 1);
+  if (!p) { g_last_error = "out of memory"; return HC_ERR_MEMORY; }
+  memcpy(p, v.data(), v.size());
+  *out = p;
+  *size = v.size();
+  return HC_OK;
+}
+void hc_free(void* p) { free(p); }
 
 }  // extern "C"

@@ -75,6 +75,38 @@ size_t hc_records_upload_bytes(const hc_records* r);
 /* One-call convenience: parse one coded picture (parameter sets + slice NALs). */
 hc_records* hc_parse_picture(const uint8_t* data, size_t size, int stream_format);
 
+/* ------------------------------------------------------------------ HEIF container -------- */
+/* Minimal ISO-BMFF/HEIF item resolver used by the batch decode API (the plugin path gets NAL
+ * units from libheif instead). Mirrors what libheif resolves before it calls the decoder plugin:
+ * libheif/file.cc:1246-1536, libheif/context.cc:172-221,710-1240. */
+typedef struct hc_heif hc_heif;
+
+typedef struct hc_heif_image_info {
+  uint32_t id;
+  int32_t is_grid;
+  int32_t width, height;       /* output size: grid output size or ispe of a single image       */
+  int32_t rows, cols;          /* grid layout (1,1 for a single image)                          */
+  uint32_t alpha_id;           /* alpha auxiliary image item, 0 if none                         */
+  int32_t rot;                 /* irot: anti-clockwise quarter turns                            */
+  int32_t mirror;              /* imir: -1 none, 0 vertical axis, 1 horizontal axis             */
+  int32_t nclx_present;        /* container colr(nclx) overrides the bitstream VUI              */
+  int32_t primaries, transfer, matrix, full_range;
+} hc_heif_image_info;
+
+/* `data` must stay valid until hc_heif_close. NULL + error text on malformed files. */
+hc_heif* hc_heif_open(const uint8_t* data, size_t size);
+void hc_heif_close(hc_heif* f);
+uint32_t hc_heif_primary_id(const hc_heif* f);
+/* writes up to `max` ids, returns the total number of top-level images */
+int hc_heif_top_level_ids(const hc_heif* f, uint32_t* ids, int max);
+int hc_heif_get_image_info(const hc_heif* f, uint32_t id, hc_heif_image_info* info);
+/* row-major tile item ids of a grid; returns rows*cols or a negative error */
+int hc_heif_grid_tiles(const hc_heif* f, uint32_t id, uint32_t* tiles, int max);
+/* hvcC parameter sets + item data as 4-byte-length-prefixed NAL units (what libheif gives
+ * heif_decoder_plugin::push_data). *out is malloc'ed; release with hc_free. */
+int hc_heif_coded_stream(const hc_heif* f, uint32_t id, uint8_t** out, size_t* size);
+void hc_free(void* p);
+
 #ifdef __cplusplus
 }
 #endif
