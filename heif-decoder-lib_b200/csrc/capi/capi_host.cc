@@ -1,10 +1,9 @@
 // capi_host.cc — C ABI over the host front-end (include/heifcuda.h, section "host front-end").
-#include "../../../include/heifcuda.h"
-#include "../host/hevc_parse.h"
-#include "../host/heif_reader.h"
+#include "capi_internal.h"
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <vector>
 
 namespace {
 thread_local std::string g_last_error;
@@ -14,15 +13,6 @@ namespace hc {
 void set_last_error(const std::string& s) { g_last_error = s; }
 }  // namespace hc
 
-struct hc_parser {
-  hc::HevcIntraParser parser;
-};
-struct hc_heif {
-  hc::HeifFile file;
-};
-struct hc_records {
-  std::unique_ptr<hc::PictureRecords> rec;
-};
 
 extern "C" {
 

@@ -1,0 +1,25 @@
+// no_engine.cc — hc_engine_* entry points of the host-only library (libheifcuda_host.so).
+// There is NO CPU implementation of the reconstruction path: every call fails loudly.
+#include "capi_internal.h"
+
+#define NO_ENGINE() (hc::set_last_error("this build has no CUDA engine and there is no CPU fallback"), HC_ERR_NO_DEVICE)
+
+extern "C" {
+int hc_has_cuda_engine(void) { return 0; }
+hc_engine* hc_engine_create(int) { NO_ENGINE(); return nullptr; }
+void hc_engine_destroy(hc_engine*) {}
+hc_batch* hc_batch_create(hc_engine*) { NO_ENGINE(); return nullptr; }
+void hc_batch_destroy(hc_batch*) {}
+int hc_batch_add_canvas(hc_batch*, int, int, int, int, int) { return NO_ENGINE(); }
+int hc_batch_add_picture(hc_batch*, const hc_records*, int, int, int, int, int) { return NO_ENGINE(); }
+int hc_batch_upload(hc_batch*) { return NO_ENGINE(); }
+int hc_batch_reconstruct(hc_batch*, int) { return NO_ENGINE(); }
+int hc_batch_convert(hc_batch*, int, const hc_csc_params*) { return NO_ENGINE(); }
+int hc_batch_sync(hc_batch*) { return NO_ENGINE(); }
+int hc_batch_read_plane(hc_batch*, int, int, void*, size_t) { return NO_ENGINE(); }
+int hc_batch_read_rgb(hc_batch*, int, void*, size_t) { return NO_ENGINE(); }
+int hc_batch_read_residual(hc_batch*, int, int16_t*, size_t) { return NO_ENGINE(); }
+int hc_batch_stage_ms(hc_batch*, float*) { return NO_ENGINE(); }
+int hc_batch_launch_count(const hc_batch*) { return 0; }
+size_t hc_batch_upload_bytes(const hc_batch*) { return 0; }
+}

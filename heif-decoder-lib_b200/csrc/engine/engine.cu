@@ -1,0 +1,558 @@
+// engine.cu — device engine behind include/heifcuda.h ("device engine" section): places parsed
+// pictures in HBM, launches K1..K5 on a CUDA stream and reads results back.
+//
+// HBM layout of one batch (all offsets 256-byte aligned):
+//   record arena   : [hc_pic[]][hc_ctu[]][hc_blk[]][hc_tb[]][hc_coeff[]][edge_map][qp_map][scaling]
+//                    [tb index lists by size][K2 row tasks]        -- ONE pinned->device copy
+//   residual buffer: int16, one contiguous nT*nT tile per coded transform block (K1 -> K2)
+//   plane pool     : per picture the reconstruction planes (K2 writes, K3 filters in place, K4 reads),
+//                    per canvas the final Y/Cb/Cr(/A) planes (K4 writes, K5 reads)
+//   rgb buffer     : interleaved output of K5, rows padded to 256 bytes
+// Device blocks come from a per-engine free list so that the plugin's one-decoder-per-tile call
+// pattern (context.cc:1799-1835) does not pay a cudaMalloc per tile.
+#include <cuda_runtime.h>
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+#include "../capi/capi_internal.h"
+#include "../kernels/launch.h"
+
+namespace {
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+bool cuda_ok(cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return true;
+  hc::set_last_error(std::string(what) + ": " + cudaGetErrorString(e));
+  return false;
+}
+
+struct Block {
+  void* p = nullptr;
+  size_t cap = 0;
+};
+
+}  // namespace
+
+struct hc_engine {
+  int device = 0;
+  std::mutex mu;
+  std::vector<Block> free_dev, free_pin;
+  std::vector<cudaStream_t> free_streams;
+
+  Block take(std::vector<Block>& list, size_t size, bool pinned) {
+    std::lock_guard<std::mutex> lk(mu);
+    int best = -1;
+    for (int i = 0; i < (int)list.size(); i++)
+      if (list[i].cap >= size && (best < 0 || list[i].cap < list[best].cap)) best = i;
+    if (best >= 0) {
+      Block b = list[best];
+      list.erase(list.begin() + best);
+      return b;
+    }
+    Block b;
+    size_t cap = align_up(size + size / 4, 1 << 20);
+    cudaError_t e = pinned ? cudaMallocHost(&b.p, cap) : cudaMalloc(&b.p, cap);
+    if (e != cudaSuccess) {
+      // try the exact size before giving up
+      cap = align_up(size, 4096);
+      e = pinned ? cudaMallocHost(&b.p, cap) : cudaMalloc(&b.p, cap);
+    }
+    if (e != cudaSuccess) {
+      cuda_ok(e, pinned ? "cudaMallocHost" : "cudaMalloc");
+      b.p = nullptr;
+      cap = 0;
+    }
+    b.cap = cap;
+    return b;
+  }
+  void give(std::vector<Block>& list, Block b) {
+    if (!b.p) return;
+    std::lock_guard<std::mutex> lk(mu);
+    list.push_back(b);
+  }
+};
+
+namespace {
+
+struct Canvas {
+  int w = 0, h = 0, chroma = 1, bit_depth = 8;
+  bool alpha = false;
+  size_t off[4] = {0, 0, 0, 0};     // byte offsets in the plane pool
+  int stride[4] = {0, 0, 0, 0};     // samples
+  int pw[4] = {0, 0, 0, 0}, ph[4] = {0, 0, 0, 0};
+  // rgb output of the last convert
+  size_t rgb_off = 0;
+  size_t rgb_stride = 0;
+  int rgb_bpp = 0;
+  bool converted = false;
+};
+
+struct Placement {
+  const hc::PictureRecords* rec;
+  int canvas, x, y, role, rescale;
+};
+
+}  // namespace
+
+struct hc_batch {
+  hc_engine* eng = nullptr;
+  cudaStream_t stream = nullptr;
+  std::vector<Canvas> canvases;
+  std::vector<Placement> pics;
+  std::vector<hc_pic> hpics;  // host copy with bases / placement filled
+  Block d_arena, h_arena, d_resid, d_planes, d_rgb, d_progress;
+  size_t arena_bytes = 0, resid_elems = 0, planes_bytes = 0, rgb_bytes = 0;
+  hc::BatchView view{};
+  const uint32_t* d_tb_index[4] = {nullptr, nullptr, nullptr, nullptr};
+  int tb_counts[4] = {0, 0, 0, 0};
+  const hc::RowTask* d_tasks = nullptr;
+  int ntasks = 0;
+  long long max_dbk_units = 0, max_sao_quads = 0;
+  int max_planes = 1;
+  bool uploaded = false;
+  cudaEvent_t ev[8] = {};
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> csc_events;
+  int launches = 0;
+  float last_d2h_ms = 0.f;
+};
+
+namespace {
+
+int plane_w(int w, int chroma, int c) { return (c == 0 || c == 3 || chroma == 3) ? w : (chroma == 0 ? 0 : (w + 1) / 2); }
+int plane_h(int h, int chroma, int c) { return (c == 0 || c == 3 || chroma != 1) ? (chroma == 0 && c != 0 && c != 3 ? 0 : h) : (h + 1) / 2; }
+
+void release_blocks(hc_batch* b) {
+  hc_engine* e = b->eng;
+  e->give(e->free_dev, b->d_arena);
+  e->give(e->free_pin, b->h_arena);
+  e->give(e->free_dev, b->d_resid);
+  e->give(e->free_dev, b->d_planes);
+  e->give(e->free_dev, b->d_rgb);
+  e->give(e->free_dev, b->d_progress);
+  b->d_arena = b->h_arena = b->d_resid = b->d_planes = b->d_rgb = b->d_progress = Block();
+}
+
+}  // namespace
+
+extern "C" {
+
+int hc_has_cuda_engine(void) { return 1; }
+
+hc_engine* hc_engine_create(int device) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    hc::set_last_error(std::string("no CUDA device available (") + (e != cudaSuccess ? cudaGetErrorString(e) : "0 devices") +
+                       "); this engine has no CPU fallback");
+    return nullptr;
+  }
+  if (device < 0 || device >= n) {
+    hc::set_last_error("hc_engine_create: device ordinal out of range");
+    return nullptr;
+  }
+  if (!cuda_ok(cudaSetDevice(device), "cudaSetDevice")) return nullptr;
+  hc_engine* eng = new (std::nothrow) hc_engine;
+  if (!eng) return nullptr;
+  eng->device = device;
+  return eng;
+}
+
+void hc_engine_destroy(hc_engine* e) {
+  if (!e) return;
+  cudaSetDevice(e->device);
+  for (auto& b : e->free_dev) cudaFree(b.p);
+  for (auto& b : e->free_pin) cudaFreeHost(b.p);
+  for (auto s : e->free_streams) cudaStreamDestroy(s);
+  delete e;
+}
+
+hc_batch* hc_batch_create(hc_engine* e) {
+  if (!e) { hc::set_last_error("hc_batch_create: null engine"); return nullptr; }
+  if (!cuda_ok(cudaSetDevice(e->device), "cudaSetDevice")) return nullptr;
+  hc_batch* b = new (std::nothrow) hc_batch;
+  if (!b) return nullptr;
+  b->eng = e;
+  {
+    std::lock_guard<std::mutex> lk(e->mu);
+    if (!e->free_streams.empty()) { b->stream = e->free_streams.back(); e->free_streams.pop_back(); }
+  }
+  if (!b->stream && !cuda_ok(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking), "cudaStreamCreate")) {
+    delete b;
+    return nullptr;
+  }
+  for (auto& ev : b->ev)
+    if (!cuda_ok(cudaEventCreate(&ev), "cudaEventCreate")) { delete b; return nullptr; }
+  return b;
+}
+
+void hc_batch_destroy(hc_batch* b) {
+  if (!b) return;
+  cudaSetDevice(b->eng->device);
+  cudaStreamSynchronize(b->stream);
+  release_blocks(b);
+  for (auto& ev : b->ev) if (ev) cudaEventDestroy(ev);
+  for (auto& p : b->csc_events) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
+  {
+    std::lock_guard<std::mutex> lk(b->eng->mu);
+    b->eng->free_streams.push_back(b->stream);
+  }
+  delete b;
+}
+
+int hc_batch_add_canvas(hc_batch* b, int width, int height, int chroma_format, int bit_depth, int with_alpha) {
+  if (!b || width <= 0 || height <= 0 || chroma_format < 0 || chroma_format > 3 || bit_depth < 8 || bit_depth > 16) {
+    hc::set_last_error("hc_batch_add_canvas: bad argument");
+    return HC_ERR_ARGUMENT;
+  }
+  Canvas c;
+  c.w = width; c.h = height; c.chroma = chroma_format; c.bit_depth = bit_depth; c.alpha = with_alpha != 0;
+  b->canvases.push_back(c);
+  return (int)b->canvases.size() - 1;
+}
+
+int hc_batch_add_picture(hc_batch* b, const hc_records* rec, int canvas, int x, int y, int role, int rescale_limited) {
+  if (!b || !rec || canvas < 0 || canvas >= (int)b->canvases.size() || x < 0 || y < 0) {
+    hc::set_last_error("hc_batch_add_picture: bad argument");
+    return HC_ERR_ARGUMENT;
+  }
+  const Canvas& c = b->canvases[canvas];
+  const hc_pic& p = rec->rec->pic;
+  if (b->pics.size() >= 65535) { hc::set_last_error("too many pictures in one batch"); return HC_ERR_ARGUMENT; }
+  if (role == HC_ROLE_COLOUR) {
+    if (p.chroma_format != c.chroma) { hc::set_last_error("picture has a different chroma format than its canvas"); return HC_ERR_BITSTREAM; }
+    if (p.bit_depth_y != c.bit_depth || (p.chroma_format && p.bit_depth_c != c.bit_depth)) {
+      hc::set_last_error("picture has a different bit depth than its canvas");
+      return HC_ERR_BITSTREAM;
+    }
+  } else {
+    if (!c.alpha) { hc::set_last_error("canvas has no alpha plane"); return HC_ERR_ARGUMENT; }
+    if ((p.bit_depth_y == 8) != (c.bit_depth == 8)) { hc::set_last_error("alpha image sample size differs from the colour image"); return HC_ERR_UNSUPPORTED; }
+  }
+  if (x >= c.w || y >= c.h) { hc::set_last_error("picture placed outside its canvas"); return HC_ERR_BITSTREAM; }
+  b->pics.push_back({rec->rec.get(), canvas, x, y, role, rescale_limited});
+  b->uploaded = false;
+  return (int)b->pics.size() - 1;
+}
+
+int hc_batch_upload(hc_batch* b) {
+  if (!b) return HC_ERR_ARGUMENT;
+  if (!cuda_ok(cudaSetDevice(b->eng->device), "cudaSetDevice")) return HC_ERR_CUDA;
+  const int np = (int)b->pics.size();
+  if (np == 0) { hc::set_last_error("hc_batch_upload: empty batch"); return HC_ERR_ARGUMENT; }
+
+  // ---- plane pool layout ----
+  size_t pool = 0;
+  b->hpics.resize(np);
+  for (auto& c : b->canvases) {
+    const int ps = c.bit_depth == 8 ? 1 : 2;
+    for (int k = 0; k < 4; k++) {
+      if (k == 3 && !c.alpha) continue;
+      c.pw[k] = plane_w(c.w, c.chroma, k);
+      c.ph[k] = plane_h(c.h, c.chroma, k);
+      if (c.pw[k] == 0) continue;
+      c.stride[k] = (int)(align_up((size_t)(c.pw[k] + 4) * ps, 128) / ps);
+      c.off[k] = pool;
+      pool += align_up((size_t)c.stride[k] * c.ph[k] * ps, 256);
+    }
+    c.converted = false;
+  }
+  // ---- record bases ----
+  size_t n_ctu = 0, n_blk = 0, n_tb = 0, n_coeff = 0, n_edge = 0, n_qp = 0, n_scal = 0;
+  uint64_t n_resid = 0;
+  int counts[4] = {0, 0, 0, 0};
+  int max_rows = 0;
+  size_t n_tasks = 0;
+  b->max_dbk_units = b->max_sao_quads = 0;
+  b->max_planes = 1;
+  for (int i = 0; i < np; i++) {
+    const hc::PictureRecords& r = *b->pics[i].rec;
+    hc_pic& p = b->hpics[i];
+    p = r.pic;
+    p.ctu_base = (uint32_t)n_ctu;   n_ctu += r.ctus.size();
+    p.blk_base = (uint32_t)n_blk;   n_blk += r.blks.size();
+    p.tb_base = (uint32_t)n_tb;     n_tb += r.tbs.size();
+    p.coeff_base = (uint32_t)n_coeff; n_coeff += r.coeffs.size();
+    p.edge_base = (uint32_t)n_edge; n_edge += r.edge_map.size();
+    p.qp_base = (uint32_t)n_qp;     n_qp += r.qp_map.size();
+    p.scaling_base = (uint32_t)n_scal; n_scal += r.scaling.size();
+    p.resid_base = n_resid;         n_resid += align_up(r.resid_count, 8);
+    if (n_blk > 0xFFFFFFFFull || n_coeff > 0xFFFFFFFFull) { hc::set_last_error("batch too large"); return HC_ERR_ARGUMENT; }
+    for (auto& t : r.tbs) counts[t.log2 - 2]++;
+    const int ncomp = p.chroma_format ? 3 : 1;
+    max_rows = std::max(max_rows, (int)p.ctbs_h);
+    n_tasks += (size_t)ncomp * p.ctbs_h;
+    b->max_planes = std::max(b->max_planes, ncomp);
+    b->max_dbk_units = std::max(b->max_dbk_units, (long long)(p.width >> 3) * (p.height >> 2));
+    b->max_sao_quads = std::max(b->max_sao_quads, (long long)((p.width + 3) >> 2) * p.height);
+    // reconstruction planes
+    const int ps = (p.bit_depth_y == 8 && p.bit_depth_c == 8) ? 1 : 2;
+    const int SubW = (p.chroma_format == 1 || p.chroma_format == 2) ? 2 : 1, SubH = p.chroma_format == 1 ? 2 : 1;
+    for (int c = 0; c < ncomp; c++) {
+      const int w = c ? p.width / SubW : p.width, h = c ? p.height / SubH : p.height;
+      p.rec_stride[c] = (uint32_t)(align_up((size_t)w * ps, 128) / ps);
+      p.rec_off[c] = pool;
+      pool += align_up((size_t)p.rec_stride[c] * h * ps, 256);
+    }
+    // destination
+    const Canvas& cv = b->canvases[b->pics[i].canvas];
+    p.dst_x = b->pics[i].x; p.dst_y = b->pics[i].y; p.dst_w = cv.w; p.dst_h = cv.h;
+    p.dst_flags = 0;
+    if (b->pics[i].rescale) p.dst_flags |= HC_DST_RESCALE_LIMITED;
+    if (b->pics[i].role == HC_ROLE_ALPHA) {
+      p.dst_off[0] = cv.off[3]; p.dst_stride[0] = (uint32_t)cv.stride[3];
+      p.dst_flags |= HC_DST_SKIP_CB | HC_DST_SKIP_CR;
+    } else {
+      for (int c = 0; c < ncomp; c++) { p.dst_off[c] = cv.off[c]; p.dst_stride[c] = (uint32_t)cv.stride[c]; }
+    }
+  }
+
+  // ---- arena layout ----
+  size_t o = 0;
+  auto place = [&](size_t bytes) { size_t at = o; o += align_up(bytes ? bytes : 1, 256); return at; };
+  const size_t o_pics = place(sizeof(hc_pic) * np), o_ctus = place(sizeof(hc_ctu) * n_ctu), o_blks = place(sizeof(hc_blk) * n_blk);
+  const size_t o_tbs = place(sizeof(hc_tb) * n_tb), o_coeffs = place(sizeof(hc_coeff) * n_coeff);
+  const size_t o_edge = place(n_edge), o_qp = place(n_qp), o_scal = place(n_scal);
+  size_t o_idx[4];
+  for (int l = 0; l < 4; l++) o_idx[l] = place(sizeof(uint32_t) * counts[l]);
+  const size_t o_tasks = place(sizeof(hc::RowTask) * n_tasks);
+  b->arena_bytes = o;
+
+  release_blocks(b);
+  b->h_arena = b->eng->take(b->eng->free_pin, o, true);
+  b->d_arena = b->eng->take(b->eng->free_dev, o, false);
+  b->d_resid = b->eng->take(b->eng->free_dev, std::max<size_t>(n_resid * 2, 256), false);
+  b->d_planes = b->eng->take(b->eng->free_dev, std::max<size_t>(pool, 256), false);
+  b->d_progress = b->eng->take(b->eng->free_dev, std::max<size_t>(n_tasks * sizeof(int), 256), false);
+  if (!b->h_arena.p || !b->d_arena.p || !b->d_resid.p || !b->d_planes.p || !b->d_progress.p) return HC_ERR_MEMORY;
+  b->resid_elems = n_resid;
+  b->planes_bytes = pool;
+
+  // ---- pack ----
+  uint8_t* H = (uint8_t*)b->h_arena.p;
+  memcpy(H + o_pics, b->hpics.data(), sizeof(hc_pic) * np);
+  uint32_t* idx[4];
+  int fill[4] = {0, 0, 0, 0};
+  for (int l = 0; l < 4; l++) idx[l] = (uint32_t*)(H + o_idx[l]);
+  for (int i = 0; i < np; i++) {
+    const hc::PictureRecords& r = *b->pics[i].rec;
+    const hc_pic& p = b->hpics[i];
+    memcpy(H + o_ctus + sizeof(hc_ctu) * p.ctu_base, r.ctus.data(), sizeof(hc_ctu) * r.ctus.size());
+    memcpy(H + o_blks + sizeof(hc_blk) * p.blk_base, r.blks.data(), sizeof(hc_blk) * r.blks.size());
+    hc_tb* tb = (hc_tb*)(H + o_tbs) + p.tb_base;
+    memcpy(tb, r.tbs.data(), sizeof(hc_tb) * r.tbs.size());
+    for (size_t k = 0; k < r.tbs.size(); k++) {
+      tb[k].pic = (uint16_t)i;
+      const int l = tb[k].log2 - 2;
+      idx[l][fill[l]++] = (uint32_t)(p.tb_base + k);
+    }
+    memcpy(H + o_coeffs + sizeof(hc_coeff) * p.coeff_base, r.coeffs.data(), sizeof(hc_coeff) * r.coeffs.size());
+    memcpy(H + o_edge + p.edge_base, r.edge_map.data(), r.edge_map.size());
+    memcpy(H + o_qp + p.qp_base, r.qp_map.data(), r.qp_map.size());
+    if (!r.scaling.empty()) memcpy(H + o_scal + p.scaling_base, r.scaling.data(), r.scaling.size());
+  }
+  // K2 tasks: row-major across all pictures so that every wavefront advances together and a task
+  // only depends on a task with a smaller index
+  {
+    hc::RowTask* tasks = (hc::RowTask*)(H + o_tasks);
+    std::vector<int> first_of_row((size_t)np * 3, -1), prev((size_t)np * 3, -1);
+    int t = 0;
+    for (int row = 0; row < max_rows; row++)
+      for (int i = 0; i < np; i++) {
+        const hc_pic& p = b->hpics[i];
+        if (row >= p.ctbs_h) continue;
+        const int ncomp = p.chroma_format ? 3 : 1;
+        for (int c = 0; c < ncomp; c++) {
+          hc::RowTask& k = tasks[t];
+          k.pic = (uint32_t)i; k.row = (uint16_t)row; k.comp = (uint8_t)c; k.pad = 0;
+          k.dep = prev[(size_t)i * 3 + c];
+          prev[(size_t)i * 3 + c] = t;
+          t++;
+        }
+      }
+    b->ntasks = t;
+  }
+
+  // ---- device view ----
+  uint8_t* D = (uint8_t*)b->d_arena.p;
+  b->view.pics = (const hc_pic*)(D + o_pics);
+  b->view.ctus = (const hc_ctu*)(D + o_ctus);
+  b->view.blks = (const hc_blk*)(D + o_blks);
+  b->view.tbs = (const hc_tb*)(D + o_tbs);
+  b->view.coeffs = (const hc_coeff*)(D + o_coeffs);
+  b->view.edge_map = D + o_edge;
+  b->view.qp_map = (const int8_t*)(D + o_qp);
+  b->view.scaling = D + o_scal;
+  b->view.resid = (int16_t*)b->d_resid.p;
+  b->view.planes = (uint8_t*)b->d_planes.p;
+  b->view.npics = np;
+  for (int l = 0; l < 4; l++) { b->d_tb_index[l] = (const uint32_t*)(D + o_idx[l]); b->tb_counts[l] = counts[l]; }
+  b->d_tasks = (const hc::RowTask*)(D + o_tasks);
+
+  cudaEventRecord(b->ev[0], b->stream);
+  if (!cuda_ok(cudaMemcpyAsync(D, H, o, cudaMemcpyHostToDevice, b->stream), "cudaMemcpyAsync(H2D records)")) return HC_ERR_CUDA;
+  cudaEventRecord(b->ev[1], b->stream);
+  b->uploaded = true;
+  return HC_OK;
+}
+
+int hc_batch_reconstruct(hc_batch* b, int stages) {
+  if (!b || !b->uploaded) { hc::set_last_error("hc_batch_reconstruct: batch not uploaded"); return HC_ERR_ARGUMENT; }
+  if (!cuda_ok(cudaSetDevice(b->eng->device), "cudaSetDevice")) return HC_ERR_CUDA;
+  cudaStream_t s = b->stream;
+  b->launches = 0;
+  cudaMemsetAsync(b->d_progress.p, 0, std::max<size_t>((size_t)b->ntasks * sizeof(int), 4), s);
+  cudaEventRecord(b->ev[2], s);
+  hc::launch_k1(b->view, b->d_tb_index, b->tb_counts, s);
+  for (int l = 0; l < 4; l++) b->launches += b->tb_counts[l] > 0;
+  cudaEventRecord(b->ev[3], s);
+  hc::launch_k2(b->view, b->d_tasks, b->ntasks, (int*)b->d_progress.p, s);
+  b->launches += 1;
+  cudaEventRecord(b->ev[4], s);
+  if (stages & HC_STAGE_DEBLOCK) {
+    hc::launch_k3(b->view, b->max_dbk_units, b->max_planes, s);
+    b->launches += 2;
+  }
+  cudaEventRecord(b->ev[5], s);
+  // K4 always runs: it is also the crop + paste pass; SAO parameters are ignored when disabled
+  hc::BatchView v = b->view;
+  v.flags = (stages & HC_STAGE_SAO) ? 0 : hc::HC_VIEW_NO_SAO;
+  hc::launch_k4(v, b->max_sao_quads, b->max_planes, s);
+  b->launches += 1;
+  cudaEventRecord(b->ev[6], s);
+  if (!cuda_ok(cudaGetLastError(), "kernel launch")) return HC_ERR_CUDA;
+  return HC_OK;
+}
+
+int hc_batch_convert(hc_batch* b, int canvas, const hc_csc_params* params) {
+  if (!b || !params || canvas < 0 || canvas >= (int)b->canvases.size() || !b->uploaded) {
+    hc::set_last_error("hc_batch_convert: bad argument");
+    return HC_ERR_ARGUMENT;
+  }
+  if (!cuda_ok(cudaSetDevice(b->eng->device), "cudaSetDevice")) return HC_ERR_CUDA;
+  Canvas& c = b->canvases[canvas];
+  static const int bpp_of[6] = {3, 4, 6, 8, 6, 8};
+  if (params->out_format < 0 || params->out_format > 5) { hc::set_last_error("bad output format"); return HC_ERR_ARGUMENT; }
+  if ((params->out_format <= HC_OUT_RGBA) != (c.bit_depth == 8)) {
+    hc::set_last_error("8-bit images convert to RGB/RGBA, deeper images to RRGGBB(AA)");
+    return HC_ERR_UNSUPPORTED;
+  }
+  c.rgb_bpp = bpp_of[params->out_format];
+  c.rgb_stride = align_up((size_t)((c.w + 3) & ~3) * c.rgb_bpp, 256);
+  // lay all canvases' rgb buffers out in one block (grow if needed)
+  size_t total = 0;
+  for (auto& cv : b->canvases) {
+    const int bp = &cv == &c ? c.rgb_bpp : (cv.rgb_bpp ? cv.rgb_bpp : (cv.bit_depth == 8 ? 4 : 8));
+    cv.rgb_off = total;
+    total += align_up(align_up((size_t)((cv.w + 3) & ~3) * bp, 256) * cv.h, 256);
+  }
+  if (b->d_rgb.cap < total) {
+    bool any = false;
+    for (auto& cv : b->canvases) any |= cv.converted;
+    if (any) { hc::set_last_error("hc_batch_convert: convert all canvases with the same format class"); return HC_ERR_ARGUMENT; }
+    b->eng->give(b->eng->free_dev, b->d_rgb);
+    b->d_rgb = b->eng->take(b->eng->free_dev, total, false);
+    if (!b->d_rgb.p) return HC_ERR_MEMORY;
+  }
+  hc::CscArgs a;
+  const uint8_t* P = (const uint8_t*)b->d_planes.p;
+  a.y = P + c.off[0];
+  a.cb = c.chroma ? P + c.off[1] : nullptr;
+  a.cr = c.chroma ? P + c.off[2] : nullptr;
+  a.a = c.alpha ? P + c.off[3] : nullptr;
+  a.y_stride = c.stride[0]; a.c_stride = c.stride[1]; a.a_stride = c.stride[3];
+  a.width = c.w; a.height = c.h; a.chroma_format = c.chroma;
+  a.out = (uint8_t*)b->d_rgb.p + c.rgb_off;
+  a.out_stride = (long long)c.rgb_stride;
+  a.p = *params;
+  a.p.bit_depth = c.bit_depth;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  cudaEventRecord(e0, b->stream);
+  hc::launch_k5(a, c.bit_depth != 8, b->stream);
+  cudaEventRecord(e1, b->stream);
+  b->csc_events.push_back({e0, e1});
+  b->launches += 1;
+  c.converted = true;
+  if (!cuda_ok(cudaGetLastError(), "kernel launch (K5)")) return HC_ERR_CUDA;
+  return HC_OK;
+}
+
+int hc_batch_sync(hc_batch* b) {
+  if (!b) return HC_ERR_ARGUMENT;
+  if (!cuda_ok(cudaStreamSynchronize(b->stream), "cudaStreamSynchronize")) return HC_ERR_CUDA;
+  return HC_OK;
+}
+
+int hc_batch_read_plane(hc_batch* b, int canvas, int plane, void* dst, size_t dst_stride) {
+  if (!b || !dst || canvas < 0 || canvas >= (int)b->canvases.size() || plane < 0 || plane > 3) {
+    hc::set_last_error("hc_batch_read_plane: bad argument");
+    return HC_ERR_ARGUMENT;
+  }
+  const Canvas& c = b->canvases[canvas];
+  if (c.pw[plane] == 0 || (plane == 3 && !c.alpha)) { hc::set_last_error("canvas has no such plane"); return HC_ERR_ARGUMENT; }
+  const int ps = c.bit_depth == 8 ? 1 : 2;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  cudaEventRecord(e0, b->stream);
+  cudaError_t e = cudaMemcpy2DAsync(dst, dst_stride, (const uint8_t*)b->d_planes.p + c.off[plane], (size_t)c.stride[plane] * ps,
+                                    (size_t)c.pw[plane] * ps, c.ph[plane], cudaMemcpyDeviceToHost, b->stream);
+  cudaEventRecord(e1, b->stream);
+  if (!cuda_ok(e, "cudaMemcpy2DAsync(D2H plane)")) return HC_ERR_CUDA;
+  if (!cuda_ok(cudaStreamSynchronize(b->stream), "cudaStreamSynchronize")) return HC_ERR_CUDA;
+  cudaEventElapsedTime(&b->last_d2h_ms, e0, e1);
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  return HC_OK;
+}
+
+int hc_batch_read_rgb(hc_batch* b, int canvas, void* dst, size_t dst_stride) {
+  if (!b || !dst || canvas < 0 || canvas >= (int)b->canvases.size()) { hc::set_last_error("hc_batch_read_rgb: bad argument"); return HC_ERR_ARGUMENT; }
+  const Canvas& c = b->canvases[canvas];
+  if (!c.converted) { hc::set_last_error("canvas was not converted"); return HC_ERR_ARGUMENT; }
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  cudaEventRecord(e0, b->stream);
+  cudaError_t e = cudaMemcpy2DAsync(dst, dst_stride, (const uint8_t*)b->d_rgb.p + c.rgb_off, c.rgb_stride, (size_t)c.w * c.rgb_bpp, c.h,
+                                    cudaMemcpyDeviceToHost, b->stream);
+  cudaEventRecord(e1, b->stream);
+  if (!cuda_ok(e, "cudaMemcpy2DAsync(D2H rgb)")) return HC_ERR_CUDA;
+  if (!cuda_ok(cudaStreamSynchronize(b->stream), "cudaStreamSynchronize")) return HC_ERR_CUDA;
+  cudaEventElapsedTime(&b->last_d2h_ms, e0, e1);
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  return HC_OK;
+}
+
+int hc_batch_read_residual(hc_batch* b, int pic, int16_t* dst, size_t count) {
+  if (!b || !dst || pic < 0 || pic >= (int)b->hpics.size()) { hc::set_last_error("hc_batch_read_residual: bad argument"); return HC_ERR_ARGUMENT; }
+  const hc_pic& p = b->hpics[pic];
+  if (count > p.resid_count) count = p.resid_count;
+  if (!cuda_ok(cudaMemcpyAsync(dst, (const int16_t*)b->d_resid.p + p.resid_base, count * 2, cudaMemcpyDeviceToHost, b->stream), "D2H residual"))
+    return HC_ERR_CUDA;
+  if (!cuda_ok(cudaStreamSynchronize(b->stream), "cudaStreamSynchronize")) return HC_ERR_CUDA;
+  return HC_OK;
+}
+
+int hc_batch_stage_ms(hc_batch* b, float ms[8]) {
+  if (!b || !ms) return HC_ERR_ARGUMENT;
+  if (!cuda_ok(cudaStreamSynchronize(b->stream), "cudaStreamSynchronize")) return HC_ERR_CUDA;
+  for (int i = 0; i < 8; i++) ms[i] = 0.f;
+  cudaEventElapsedTime(&ms[0], b->ev[0], b->ev[1]);
+  for (int k = 0; k < 4; k++) cudaEventElapsedTime(&ms[1 + k], b->ev[2 + k], b->ev[3 + k]);
+  for (auto& p : b->csc_events) {
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, p.first, p.second) == cudaSuccess) ms[5] += t;
+    cudaEventDestroy(p.first); cudaEventDestroy(p.second);
+  }
+  b->csc_events.clear();
+  ms[6] = b->last_d2h_ms;
+  cudaGetLastError();
+  return HC_OK;
+}
+
+int hc_batch_launch_count(const hc_batch* b) { return b ? b->launches : 0; }
+size_t hc_batch_upload_bytes(const hc_batch* b) { return b ? b->arena_bytes : 0; }
+
+}  // extern "C"

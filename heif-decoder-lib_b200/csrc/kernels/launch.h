@@ -1,0 +1,25 @@
+// launch.h — host-callable launchers of the sm_100a kernels (defined in the k*.cu files).
+#pragma once
+#include <cuda_runtime.h>
+#include "common.cuh"
+#include "../../../include/heifcuda.h"
+
+namespace hc {
+
+struct CscArgs {
+  const uint8_t* y;  const uint8_t* cb;  const uint8_t* cr;  const uint8_t* a;   // plane bases (bytes)
+  int y_stride, c_stride, a_stride;   // in samples
+  int width, height;
+  int chroma_format;                  // 0..3
+  uint8_t* out;
+  long long out_stride;               // bytes
+  hc_csc_params p;
+};
+
+void launch_k1(const BatchView& bv, const uint32_t* const tb_index[4], const int counts[4], cudaStream_t stream);
+void launch_k2(const BatchView& bv, const RowTask* tasks, int ntasks, int* progress, cudaStream_t stream);
+void launch_k3(const BatchView& bv, long long max_units, int planes, cudaStream_t stream);
+void launch_k4(const BatchView& bv, long long max_quads, int planes, cudaStream_t stream);
+void launch_k5(const CscArgs& a, bool sixteen_bit, cudaStream_t stream);
+
+}  // namespace hc

@@ -107,6 +107,83 @@ int hc_heif_grid_tiles(const hc_heif* f, uint32_t id, uint32_t* tiles, int max);
 int hc_heif_coded_stream(const hc_heif* f, uint32_t id, uint8_t** out, size_t* size);
 void hc_free(void* p);
 
+/* ------------------------------------------------------------------ colour conversion ----- */
+/* output layouts == heif_chroma_interleaved_* (libheif/api/libheif/heif.h heif_chroma) */
+#define HC_OUT_RGB 0
+#define HC_OUT_RGBA 1
+#define HC_OUT_RRGGBB_BE 2
+#define HC_OUT_RRGGBBAA_BE 3
+#define HC_OUT_RRGGBB_LE 4
+#define HC_OUT_RRGGBBAA_LE 5
+
+#define HC_CSC_INT420 0 /* Op_YCbCr420_to_RGB24 / _RGB32: 8-bit fixed point      yuv2rgb.cc:260-495 */
+#define HC_CSC_FLOAT 1  /* Op_YCbCr_to_RGB<> / Op_YCbCr420_to_RRGGBBaa: fp32     yuv2rgb.cc:28-254,498-643 */
+#define HC_CSC_GBR 2    /* matrix_coefficients == 0                               yuv2rgb.cc:197-211 */
+#define HC_CSC_YCGCO 3  /* matrix_coefficients == 8                               yuv2rgb.cc:212-226 */
+
+typedef struct hc_csc_params {
+  int32_t mode;          /* HC_CSC_*                                                             */
+  int32_t out_format;    /* HC_OUT_*                                                             */
+  int32_t full_range;
+  int32_t bit_depth;
+  int32_t r_cr_i, g_cb_i, g_cr_i, b_cb_i; /* lround(256*coefficient), INT420 mode                */
+  float r_cr, g_cb, g_cr, b_cb;           /* nclx.cc:151-171                                     */
+} hc_csc_params;
+
+/* Chooses the conversion the reference's pipeline would run with default decoding options
+ * (colorconversion.cc:266-420, table in SURVEY.md 3.5) and fills the coefficients exactly as
+ * nclx.cc:82-171 computes them. `matrix`/`primaries`/`full_range` are the image's nclx values
+ * (pass matrix=2 for "unspecified": replaced by BT.601 like nclx.cc:346-359). Returns
+ * HC_ERR_UNSUPPORTED for combinations the reference cannot convert either (matrix 11/14) or that
+ * depend on colour-primaries tables not implemented here (matrix 12/13). */
+int hc_csc_select(int matrix, int primaries, int full_range, int chroma_format, int bit_depth,
+                  int has_alpha, int out_format, hc_csc_params* out);
+
+/* ------------------------------------------------------------------ device engine ---------- */
+typedef struct hc_engine hc_engine;
+typedef struct hc_batch hc_batch;
+
+/* Creates the engine on CUDA device `device`. NULL + HC_ERR_NO_DEVICE text when no usable GPU is
+ * present: there is deliberately no CPU fallback. */
+hc_engine* hc_engine_create(int device);
+void hc_engine_destroy(hc_engine* e);
+
+/* A batch = a set of parsed pictures placed on destination canvases (one canvas per output
+ * image: a single picture, or a HEIF grid whose tiles are pasted at their offsets). */
+hc_batch* hc_batch_create(hc_engine* e);
+void hc_batch_destroy(hc_batch* b);
+/* returns the canvas index (>= 0) */
+int hc_batch_add_canvas(hc_batch* b, int width, int height, int chroma_format, int bit_depth, int with_alpha);
+#define HC_ROLE_COLOUR 0
+#define HC_ROLE_ALPHA 1 /* the picture's luma becomes the canvas' alpha plane (context.cc:2029-2078) */
+/* `rec` must stay alive until hc_batch_upload returns. (x,y): paste position of the picture's
+ * conformance window on the canvas, luma samples. rescale_limited: apply the reference's
+ * limited->full range rescale while pasting (grid tiles whose nclx is limited range). */
+int hc_batch_add_picture(hc_batch* b, const hc_records* rec, int canvas, int x, int y, int role, int rescale_limited);
+/* packs all records into one pinned arena and copies it to the device (async on the engine stream) */
+int hc_batch_upload(hc_batch* b);
+#define HC_STAGE_DEBLOCK 1
+#define HC_STAGE_SAO 2
+#define HC_STAGE_ALL 3
+/* K1 (dequant+transform) -> K2 (intra wavefront) -> K3 (deblock) -> K4 (SAO+crop+paste), async */
+int hc_batch_reconstruct(hc_batch* b, int stages);
+/* K5 for one canvas into the engine's device RGB buffer, async */
+int hc_batch_convert(hc_batch* b, int canvas, const hc_csc_params* params);
+int hc_batch_sync(hc_batch* b);
+/* D2H reads (synchronous). plane: 0 Y, 1 Cb, 2 Cr, 3 alpha. Samples are 1 byte for 8-bit canvases,
+ * 2 bytes little-endian otherwise. */
+int hc_batch_read_plane(hc_batch* b, int canvas, int plane, void* dst, size_t dst_stride_bytes);
+int hc_batch_read_rgb(hc_batch* b, int canvas, void* dst, size_t dst_stride_bytes);
+/* residuals of picture `pic` as produced by K1 (resid_count int16) — used by the parity tests */
+int hc_batch_read_residual(hc_batch* b, int pic, int16_t* dst, size_t count);
+/* device time of the last run's stages in ms (CUDA events on the engine stream):
+ * [0] H2D upload, [1] K1, [2] K2, [3] K3, [4] K4, [5] K5 (sum over canvases), [6] D2H of the last read */
+int hc_batch_stage_ms(hc_batch* b, float ms[8]);
+/* number of kernel launches issued by the last reconstruct + convert calls */
+int hc_batch_launch_count(const hc_batch* b);
+/* bytes of the packed record arena uploaded by hc_batch_upload */
+size_t hc_batch_upload_bytes(const hc_batch* b);
+
 #ifdef __cplusplus
 }
 #endif

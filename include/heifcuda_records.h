@@ -113,6 +113,11 @@ typedef struct hc_ctu {
 #define HC_PIC_SCALING_LIST      0x0010u /* scaling_list_enabled: hc_pic.scaling_off is valid    */
 #define HC_PIC_LIMITED_RANGE     0x0020u /* VUI video_full_range_flag == 0 (or VUI absent)       */
 
+#define HC_DST_RESCALE_LIMITED 0x01u /* limited->full range rescale while pasting (context.cc:2504-2528) */
+#define HC_DST_SKIP_Y  0x02u          /* component not written to the destination                  */
+#define HC_DST_SKIP_CB 0x04u
+#define HC_DST_SKIP_CR 0x08u
+
 /* Per-picture header. All *_base are batch-global indices of this picture's first element;
  * record-internal offsets are relative to them. Plane/destination fields are filled by the
  * engine when it places the picture in device memory (host parser leaves them zero). */
@@ -128,7 +133,8 @@ typedef struct hc_pic {
   int8_t   pps_cb_qp_offset, pps_cr_qp_offset;   /* deblock chroma cQpPicOffset (deblock.cc:1652) */
   /* VUI colour description (defaults 2/2/2 when absent: vui.cc:93-97) */
   uint8_t  colour_primaries, transfer_characteristics, matrix_coeffs, full_range;
-  uint8_t  pad0[2];
+  uint8_t  dst_flags;            /* HC_DST_* (engine-filled)                                     */
+  uint8_t  pad0;
   /* batch-global bases */
   uint32_t ctu_base;             /* hc_ctu[] : ctbs_w*ctbs_h entries                            */
   uint32_t blk_base;             /* hc_blk[]                                                    */
