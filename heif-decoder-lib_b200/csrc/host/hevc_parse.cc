@@ -1263,45 +1263,64 @@ void HevcIntraParser::Impl::finish_picture() {
     if (e & (HC_EDGE_V | HC_EDGE_H)) { any_edge = true; break; }
   if (any_edge) p.flags |= HC_PIC_HAS_DEBLOCK;
 
-  // pcm (with pcm_loop_filter_disabled) / transquant-bypass samples are left untouched by the
-  // in-loop filters (deblock.cc:755-783, sao.cc:349-356)
-  bool nofilt_possible = (S->pcm_enabled && S->pcm_loop_filter_disabled) || P->transquant_bypass_enabled;
-  if (nofilt_possible) {
+  // pcm / transquant-bypass units: needed by SAO (sao.cc:349-356) and by the reference's special
+  // deblocking path for such streams (deblock.cc:755-790)
+  if ((S->pcm_enabled && S->pcm_loop_filter_disabled) || P->transquant_bypass_enabled) p.flags |= HC_PIC_PCMF;
+  if (S->pcm_enabled && S->pcm_loop_filter_disabled) p.flags |= HC_PIC_PCM_LF_DISABLED;
+  if (S->pcm_enabled || P->transquant_bypass_enabled) {
     for (int y8 = 0; y8 < h8; y8++)
       for (int x8 = 0; x8 < w8; x8++) {
         uint8_t f = cu_flags[x8 + (size_t)y8 * w8];
-        bool nf = ((f & 1) && S->pcm_loop_filter_disabled) || (f & 2);
-        if (!nf) continue;
+        if (!f) continue;
+        uint8_t bits = (uint8_t)(((f & 1) ? HC_EDGE_PCM : 0) | ((f & 2) ? HC_EDGE_BYPASS : 0));
         for (int dy = 0; dy < 2; dy++)
-          for (int dx = 0; dx < 2; dx++) rec->edge_map[(x8 * 2 + dx) + (size_t)(y8 * 2 + dy) * w4] |= HC_EDGE_NOFILT;
+          for (int dx = 0; dx < 2; dx++) rec->edge_map[(x8 * 2 + dx) + (size_t)(y8 * 2 + dy) * w4] |= bits;
         rec->ctus[ctb_of(x8 << 3, y8 << 3)].flags |= HC_CTU_HAS_NOFILTER;
       }
   }
 
+  // SAO neighbour masks, mirroring apply_sao_internal (sao.cc:323-423) including two quirks of the
+  // reference: (a) its fast path ignores slice-level loop_filter_across_slices flags altogether,
+  // (b) for chroma its "current slice address" is looked up at chroma coordinates taken as luma.
   bool any_sao = false;
   const int cw = S->ctbs_w, chh = S->ctbs_h;
+  static const int dx[8] = {-1, 1, 0, 0, -1, 1, -1, 1};
+  static const int dy[8] = {0, 0, -1, 1, -1, -1, 1, 1};
   for (int cy = 0; cy < chh; cy++)
     for (int cx = 0; cx < cw; cx++) {
-      int a = cx + cy * cw;
+      const int a = cx + cy * cw;
       hc_ctu& ctu = rec->ctus[a];
       if (ctu.sao_type[0] | ctu.sao_type[1] | ctu.sao_type[2]) any_sao = true;
-      uint8_t m = 0;
-      static const int dx[8] = {-1, 1, 0, 0, -1, 1, -1, 1};
-      static const int dy[8] = {0, 0, -1, 1, -1, -1, 1, 1};
-      for (int k = 0; k < 8; k++) {
-        int nx = cx + dx[k], ny = cy + dy[k];
-        if (nx < 0 || ny < 0 || nx >= cw || ny >= chh) continue;
-        int n = nx + ny * cw;
-        if (ctb_slice_idx[n] < 0 || ctb_slice_idx[a] < 0) continue;
-        bool ok = true;
-        // sao.cc:377-395
-        int sa = ctb_slice_addr[a], sn = ctb_slice_addr[n];
-        if (sn < sa && !slices[ctb_slice_idx[a]].loop_filter_across_slices) ok = false;
-        if (sn > sa && !slices[ctb_slice_idx[n]].loop_filter_across_slices) ok = false;
-        if (!P->loop_filter_across_tiles && P->tile_id_rs[n] != P->tile_id_rs[a]) ok = false;
-        if (ok) m |= (uint8_t)(1u << k);
+      const bool fast = P->loop_filter_across_slices && !P->tiles_enabled && !(ctu.flags & HC_CTU_HAS_NOFILTER);
+      for (int comp = 0; comp < 2; comp++) {
+        // slice address the reference compares against
+        int sa = ctb_slice_addr[a];
+        if (comp == 1 && S->ChromaArrayType != 0 && S->ChromaArrayType != 3) {
+          int qx = (cx << S->log2_ctb) / S->SubWidthC, qy = (cy << S->log2_ctb) / S->SubHeightC;
+          sa = ctb_slice_addr[ctb_of(qx, qy)];
+        }
+        uint8_t m = 0;
+        for (int k = 0; k < 8; k++) {
+          int nx = cx + dx[k], ny = cy + dy[k];
+          if (nx < 0 || ny < 0 || nx >= cw || ny >= chh) continue;
+          int n = nx + ny * cw;
+          if (ctb_slice_idx[n] < 0 || ctb_slice_idx[a] < 0) continue;
+          bool ok = true;
+          if (!fast) {
+            int sn = ctb_slice_addr[n];
+            if (sn < sa && !slices[ctb_slice_idx[a]].loop_filter_across_slices) ok = false;
+            if (sn > sa && !slices[ctb_slice_idx[n]].loop_filter_across_slices) ok = false;
+            if (!P->loop_filter_across_tiles && P->tile_id_rs[n] != P->tile_id_rs[a]) ok = false;
+          }
+          if (ok) m |= (uint8_t)(1u << k);
+        }
+        if (comp == 0) ctu.sao_nb = m;
+        else {
+          ctu.sao_nb_c = m;
+          if (!fast && ctb_slice_addr[a] != sa && !slices[ctb_slice_idx[a]].loop_filter_across_slices)
+            ctu.flags |= HC_CTU_SAO_C_SELF;
+        }
       }
-      ctu.sao_nb = m;
     }
   if (any_sao) p.flags |= HC_PIC_HAS_SAO;
 

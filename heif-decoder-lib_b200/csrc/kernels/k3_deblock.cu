@@ -29,8 +29,9 @@ HC_D int qpc_from_qpi_420(int qPi) {
   // H.265 Table 8-10
   if (qPi < 30) return qPi;
   if (qPi >= 44) return qPi - 6;
-  const int t[14] = {29, 30, 31, 32, 33, 33, 34, 34, 35, 35, 36, 36, 37, 37};
-  return t[qPi - 30];
+  // 30..43 -> 29,30,31,32,33,33,34,34,35,35,36,36,37,37
+  const int d = qPi - 30;
+  return d < 4 ? 29 + d : 33 + ((d - 4) >> 1);
 }
 
 // Luma: 4 lines x 8 samples (p3 p2 p1 p0 | q0 q1 q2 q3) held in registers.
@@ -135,9 +136,22 @@ __device__ void deblock_picture(const BatchView& bv, const hc_pic& pic, int plan
     const int bd = pic.bit_depth_y;
     const int beta = c_beta_tab[clip3i(0, 51, qPL + ctu.beta_offset)] * (1 << (bd - 8));
     const int tc = c_tc_tab[clip3i(0, 53, qPL + 2 + ctu.tc_offset)] * (1 << (bd - 8));
-    const int px = vertical ? x - 1 : x, py = vertical ? y : y - 1;
-    const bool no_p = edge[(px >> 2) + (size_t)(py >> 2) * w4] & HC_EDGE_NOFILT;
-    const bool no_q = e & HC_EDGE_NOFILT;
+    // Streams with pcm(+loop filter disabled) / transquant bypass: mirror of the reference's
+    // special path as its default build behaves (deblock.cc:755-790, see oracle/hevc_recon_oracle.c)
+    bool no_p = false, no_q = false;
+    if (pic.flags & HC_PIC_PCMF) {
+      bool normal[2][2];
+#pragma unroll
+      for (int u = 0; u < 2; u++) {
+        const int qx = vertical ? sx : sx + 4 * u, qy = vertical ? sy + 4 * u : sy;
+        const int px = vertical ? qx - 1 : qx, py = vertical ? qy : qy - 1;
+        normal[u][0] = !(edge[(px >> 2) + (size_t)(py >> 2) * w4] & (HC_EDGE_PCM | HC_EDGE_BYPASS));
+        normal[u][1] = !(edge[(qx >> 2) + (size_t)(qy >> 2) * w4] & (HC_EDGE_PCM | HC_EDGE_BYPASS));
+      }
+      const int j = vertical ? ((y >> 2) & 1) : ((x >> 2) & 1);
+      if (normal[0][0] && normal[0][1] && normal[1][0] && normal[1][1]) no_p = no_q = bd > 8;
+      else { no_p = normal[j][0]; no_q = normal[j][1]; }
+    }
     Pixel* pix = plane + x + (size_t)y * stride;
     if (vertical) deblock_luma_unit<Pixel>(pix, 1, stride, beta, tc, no_p, no_q, bd);
     else deblock_luma_unit<Pixel>(pix, stride, 1, beta, tc, no_p, no_q, bd);
@@ -181,12 +195,29 @@ __device__ void deblock_picture(const BatchView& bv, const hc_pic& pic, int plan
   const int maxv = (1 << bd) - 1;
   Pixel* pix = plane + xc + (size_t)yc * stride;
   const ptrdiff_t xs = vertical ? 1 : stride, ys = vertical ? stride : 1;
+  bool no_p = false, no_q = false;
+  if (pic.flags & HC_PIC_PCMF) {
+    // deblock.cc:1716-1755 + loop_filter_chroma_c (fallback-postfilter.h:138-179)
+    bool normal[2][2];
+    const bool lfd = pic.flags & HC_PIC_PCM_LF_DISABLED;
+    const int slx = sxc * SubW, sly = syc * SubH;  // luma position of the segment start
+#pragma unroll
+    for (int u = 0; u < 2; u++) {
+      const int ux = vertical ? slx : slx + 4 * u * SubW, uy = vertical ? sly + 4 * u * SubH : sly;
+      if (ux >= W || uy >= H) { normal[u][0] = normal[u][1] = true; continue; }
+      const int upx = vertical ? ux - 1 : ux, upy = vertical ? uy : uy - 1;
+      const int ep = edge[(upx >> 2) + (size_t)(upy >> 2) * w4], eq = edge[(ux >> 2) + (size_t)(uy >> 2) * w4];
+      normal[u][0] = !((lfd && (ep & HC_EDGE_PCM)) || (ep & HC_EDGE_BYPASS));
+      normal[u][1] = !((lfd && (eq & HC_EDGE_PCM)) || (eq & HC_EDGE_BYPASS));
+    }
+    if (!(normal[0][0] && normal[0][1] && normal[1][0] && normal[1][1])) {
+      const int j = vertical ? ((yc >> 2) & 1) : ((xc >> 2) & 1);
+      no_p = !normal[j][0];
+      no_q = vertical ? !normal[j][0] : !normal[j][1];
+    }
+  }
 #pragma unroll
   for (int k = 0; k < 4; k++) {
-    const int lqx = vertical ? lx : lx + k * SubW, lqy = vertical ? ly + k * SubH : ly;
-    const int lpx = vertical ? lx - 1 : lqx, lpy = vertical ? lqy : ly - 1;
-    const bool no_q = edge[(lqx >> 2) + (size_t)(lqy >> 2) * w4] & HC_EDGE_NOFILT;
-    const bool no_p = edge[(lpx >> 2) + (size_t)(lpy >> 2) * w4] & HC_EDGE_NOFILT;
     Pixel* l = pix + (ptrdiff_t)k * ys;
     const int p1 = l[-2 * xs], p0 = l[-1 * xs], q0 = l[0], q1 = l[xs];
     const int delta = clip3i(-tc, tc, (((q0 - p0) * 4) + p1 - q1 + 4) >> 3);

@@ -64,8 +64,10 @@ __device__ void sao_picture(const BatchView& bv, const hc_pic& pic, int c, long 
     const int type = (bv.flags & HC_VIEW_NO_SAO) ? 0 : ctu.sao_type[c];
     if (type) {
       bool skip = false;
-      if (ctu.flags & HC_CTU_HAS_NOFILTER)
-        skip = edge[((x * SubW) >> 2) + (size_t)((y * SubH) >> 2) * w4] & HC_EDGE_NOFILT;
+      if (ctu.flags & HC_CTU_HAS_NOFILTER) {
+        const int e = edge[((x * SubW) >> 2) + (size_t)((y * SubH) >> 2) * w4];
+        skip = ((pic.flags & HC_PIC_PCM_LF_DISABLED) && (e & HC_EDGE_PCM)) || (e & HC_EDGE_BYPASS);
+      }
       if (!skip) {
         if (type == 1) {
           // bandShift >= 8 leaves the sample untouched in the reference (sao.cc:461)
@@ -91,7 +93,12 @@ __device__ void sao_picture(const BatchView& bv, const hc_pic& pic, int c, long 
               else if (dxc == 0) bit = dyc < 0 ? HC_NB_T : HC_NB_B;
               else if (dyc < 0) bit = dxc < 0 ? HC_NB_TL : HC_NB_TR;
               else bit = dxc < 0 ? HC_NB_BL : HC_NB_BR;
-              if (!(ctu.sao_nb & bit)) ok = false;
+              if (!((c ? ctu.sao_nb_c : ctu.sao_nb) & bit)) ok = false;
+            } else if (c && (ctu.flags & HC_CTU_SAO_C_SELF)) {
+              // reference quirk (sao.cc:283): border samples of this CTB also lose their in-CTB neighbours
+              const int lx = x & ((1 << log2w) - 1), ly = y & ((1 << log2h) - 1);
+              const int cwid = min(1 << log2w, width - (ctbx << log2w)), chei = min(1 << log2h, height - (ctby << log2h));
+              if (lx == 0 || ly == 0 || lx == cwid - 1 || ly == chei - 1) ok = false;
             }
           }
           if (ok) {

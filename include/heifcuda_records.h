@@ -85,8 +85,11 @@ typedef struct hc_blk {
 #define HC_NB_BL 0x40u
 #define HC_NB_BR 0x80u
 
-#define HC_CTU_HAS_NOFILTER 0x01u  /* CTB contains pcm(+loop filter off) or transquant-bypass CUs */
+#define HC_CTU_HAS_NOFILTER 0x01u  /* CTB contains pcm or transquant-bypass CUs                    */
 #define HC_CTU_DEBLOCK_OFF  0x02u  /* slice_deblocking_filter_disabled_flag for this CTB's slice  */
+#define HC_CTU_SAO_C_SELF   0x04u  /* chroma SAO: neighbours inside this CTB count as unavailable for
+                                      samples on the CTB border (reference quirk, sao.cc:283,377-389:
+                                      the "current" slice is looked up at chroma coordinates)      */
 
 /* Per-CTB record, indexed by raster CTB address inside the picture. */
 typedef struct hc_ctu {
@@ -97,14 +100,17 @@ typedef struct hc_ctu {
   int8_t   sao_offset[3][4];     /* SaoOffsetVal (already << log2OffsetScale)                  */
   int8_t   beta_offset;    /* slice_beta_offset_div2*2 of the slice covering this CTB          */
   int8_t   tc_offset;      /* slice_tc_offset_div2*2                                           */
-  uint8_t  sao_nb;         /* HC_NB_* */
+  uint8_t  sao_nb;         /* HC_NB_* for luma                                                 */
   uint8_t  flags;          /* HC_CTU_* */
+  uint8_t  sao_nb_c;       /* HC_NB_* for chroma (differs from sao_nb only through the quirk above) */
+  uint8_t  pad[3];
 } hc_ctu;
 
 /* hc_pic.edge_map byte per 4x4 luma unit */
 #define HC_EDGE_V       0x01u  /* filter the vertical edge at the left of this unit (bS=2)      */
 #define HC_EDGE_H       0x02u  /* filter the horizontal edge at the top of this unit (bS=2)     */
-#define HC_EDGE_NOFILT  0x04u  /* samples of this unit are pcm/bypass: deblock + SAO leave them */
+#define HC_EDGE_PCM     0x04u  /* unit belongs to a pcm coding unit                             */
+#define HC_EDGE_BYPASS  0x08u  /* unit belongs to a cu_transquant_bypass coding unit            */
 
 #define HC_PIC_STRONG_INTRA      0x0001u /* sps strong_intra_smoothing_enabled_flag              */
 #define HC_PIC_NO_INTRA_SMOOTH   0x0002u /* sps range-ext intra_smoothing_disabled_flag          */
@@ -112,6 +118,9 @@ typedef struct hc_ctu {
 #define HC_PIC_HAS_SAO           0x0008u /* at least one CTB component has sao_type != 0         */
 #define HC_PIC_SCALING_LIST      0x0010u /* scaling_list_enabled: hc_pic.scaling_off is valid    */
 #define HC_PIC_LIMITED_RANGE     0x0020u /* VUI video_full_range_flag == 0 (or VUI absent)       */
+#define HC_PIC_PCMF              0x0040u /* (pcm_enabled && pcm_loop_filter_disabled) || transquant_bypass_enabled:
+                                            the reference's special deblocking path (deblock.cc:724,755-790) */
+#define HC_PIC_PCM_LF_DISABLED   0x0080u /* pcm_loop_filter_disabled_flag                         */
 
 #define HC_DST_RESCALE_LIMITED 0x01u /* limited->full range rescale while pasting (context.cc:2504-2528) */
 #define HC_DST_SKIP_Y  0x02u          /* component not written to the destination                  */

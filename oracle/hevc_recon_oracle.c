@@ -337,9 +337,12 @@ static inline const hc_ctu* ctu_at(const dbk_ctx* d, int x, int y) {
 }
 
 /* deblock.cc:708-792 edge_filtering_luma_internal + fallback-postfilter.h:31-135 loop_filter_luma.
- * The pcm/bypass "no filter" handling follows the spec (samples of such CUs are not modified);
- * the reference's own handling of that corner is inconsistent between its scalar and SSE code
- * (SURVEY.md §8a hazard 2) and is outside the pinned parity set. */
+ * Streams with (pcm && pcm_loop_filter_disabled) or transquant_bypass_enabled take the reference's
+ * special path (deblock.cc:755-790), restated here exactly as its default (SIMD) build behaves, which
+ * is NOT what the standard says: an 8-sample segment touching no pcm/bypass CU is filtered normally
+ * for 8-bit pictures (SIMD kernel ignores the flags) and not at all for deeper ones (the scalar
+ * template tests "!no_p" while the caller passes true for "filter"); in a segment that does touch
+ * one, only the pcm/bypass sides are modified. */
 static void oracle_deblock_luma(const dbk_ctx* d, uint16_t* plane, int stride, int vertical) {
   const hc_pic* pic = d->pic;
   const int bd = pic->bit_depth_y;
@@ -361,11 +364,18 @@ static void oracle_deblock_luma(const dbk_ctx* d, uint16_t* plane, int stride, i
       uint16_t* pix = plane + x + (size_t)y * stride;
       for (int j = 0; j < 2; j++, pix += 4 * ys) {
         const int tc = tcs[j];
-        /* spec 8.7.2.5.7: pcm+pcm_loop_filter_disabled / cu_transquant_bypass sides stay untouched */
-        int px = vertical ? x - 1 : x + 4 * j, py = vertical ? y + 4 * j : y - 1;
-        int qx = vertical ? x : x + 4 * j, qy = vertical ? y + 4 * j : y;
-        const int no_p = (edge_at(d, px, py) & HC_EDGE_NOFILT) != 0;
-        const int no_q = (edge_at(d, qx, qy) & HC_EDGE_NOFILT) != 0;
+        int no_p = 0, no_q = 0; /* 1 = leave that side untouched */
+        if (pic->flags & HC_PIC_PCMF) {
+          int normal[2][2];
+          for (int u = 0; u < 2; u++) {
+            int px = vertical ? x - 1 : x + 4 * u, py = vertical ? y + 4 * u : y - 1;
+            int qx = vertical ? x : x + 4 * u, qy = vertical ? y + 4 * u : y;
+            normal[u][0] = !(edge_at(d, px, py) & (HC_EDGE_PCM | HC_EDGE_BYPASS));
+            normal[u][1] = !(edge_at(d, qx, qy) & (HC_EDGE_PCM | HC_EDGE_BYPASS));
+          }
+          if (normal[0][0] && normal[0][1] && normal[1][0] && normal[1][1]) no_p = no_q = (bd > 8);
+          else { no_p = normal[j][0]; no_q = normal[j][1]; }
+        }
 #define PX(i, k) pix[(ptrdiff_t)(i) * xs + (ptrdiff_t)(k) * ys]
         const int dp0 = iabs(PX(-3, 0) - 2 * PX(-2, 0) + PX(-1, 0)), dq0 = iabs(PX(2, 0) - 2 * PX(1, 0) + PX(0, 0));
         const int dp3 = iabs(PX(-3, 3) - 2 * PX(-2, 3) + PX(-1, 3)), dq3 = iabs(PX(2, 3) - 2 * PX(1, 3) + PX(0, 3));
@@ -447,9 +457,26 @@ static void oracle_deblock_chroma(const dbk_ctx* d, uint16_t* plane, int stride,
         const int tc = tcv[j];
         int lqx = vertical ? lx : lx + k * SubW, lqy = vertical ? ly + k * SubH : ly;
         if (lqx >= pic->width || lqy >= pic->height) continue;
-        int lpx = vertical ? lx - 1 : lqx, lpy = vertical ? lqy : ly - 1;
-        const int no_p = (edge_at(d, lpx, lpy) & HC_EDGE_NOFILT) != 0;
-        const int no_q = (edge_at(d, lqx, lqy) & HC_EDGE_NOFILT) != 0;
+        int no_p = 0, no_q = 0;
+        if (pic->flags & HC_PIC_PCMF) {
+          /* deblock.cc:1716-1755: flags of the two 4-line units of this 8-sample segment */
+          int normal[2][2];
+          const int lfd = (pic->flags & HC_PIC_PCM_LF_DISABLED) != 0;
+          for (int u = 0; u < 2; u++) {
+            int ux = vertical ? lx : lx + 4 * u * SubW, uy = vertical ? ly + 4 * u * SubH : ly;
+            int upx = vertical ? lx - 1 : ux, upy = vertical ? uy : ly - 1;
+            if (ux >= pic->width || uy >= pic->height) { normal[u][0] = normal[u][1] = 1; continue; }
+            int ep = edge_at(d, upx, upy), eq = edge_at(d, ux, uy);
+            normal[u][0] = !((lfd && (ep & HC_EDGE_PCM)) || (ep & HC_EDGE_BYPASS));
+            normal[u][1] = !((lfd && (eq & HC_EDGE_PCM)) || (eq & HC_EDGE_BYPASS));
+          }
+          if (!(normal[0][0] && normal[0][1] && normal[1][0] && normal[1][1])) {
+            /* loop_filter_chroma_c (fallback-postfilter.h:138-179): the vertical branch tests the P
+             * flag for both sides */
+            no_p = !normal[j][0];
+            no_q = vertical ? !normal[j][0] : !normal[j][1];
+          }
+        }
         uint16_t *q0p, *q1p, *p0p, *p1p;
         if (vertical) { q0p = ptr + (size_t)k * stride; q1p = q0p + 1; p0p = q0p - 1; p1p = q0p - 2; }
         else { q0p = ptr + k; q1p = q0p + stride; p0p = q0p - stride; p1p = q0p - 2 * stride; }
@@ -459,6 +486,11 @@ static void oracle_deblock_chroma(const dbk_ctx* d, uint16_t* plane, int stride,
         if (!no_q) *q0p = (uint16_t)nq;
       }
     }
+}
+
+/* sao.cc:349-356,441-445: pcm samples (when pcm_loop_filter_disabled) and bypass samples keep their value */
+static int sao_sample_skipped(const hc_pic* pic, int e) {
+  return ((pic->flags & HC_PIC_PCM_LF_DISABLED) && (e & HC_EDGE_PCM)) || (e & HC_EDGE_BYPASS);
 }
 
 /* sao.cc:261-488 apply_sao_internal, :552-625 driver. in = deblocked copy, out = picture. */
@@ -493,8 +525,9 @@ static void oracle_sao_plane(const hc_pic* pic, const hc_ctu* ctus, const uint8_
         for (int j = 0; j < ctbH; j++)
           for (int i = 0; i < ctbW; i++) {
             const int x = xC + i, y = yC + j;
-            if (nofilt && (edge[((x * SubW) >> 2) + (size_t)((y * SubH) >> 2) * w4] & HC_EDGE_NOFILT)) continue;
+            if (nofilt && sao_sample_skipped(pic, edge[((x * SubW) >> 2) + (size_t)((y * SubH) >> 2) * w4])) continue;
             int skip = 0;
+            const int on_border = (i == 0 || j == 0 || i == ctbW - 1 || j == ctbH - 1);
             for (int k = 0; k < 2 && !skip; k++) {
               int xS = x + hPos[k], yS = y + vPos[k];
               if (xS < 0 || yS < 0 || xS >= width || yS >= height) { skip = 1; break; }
@@ -506,7 +539,9 @@ static void oracle_sao_plane(const hc_pic* pic, const hc_ctu* ctus, const uint8_
                 else if (dx == 0) bit = dy < 0 ? HC_NB_T : HC_NB_B;
                 else if (dy < 0) bit = dx < 0 ? HC_NB_TL : HC_NB_TR;
                 else bit = dx < 0 ? HC_NB_BL : HC_NB_BR;
-                if (!(ctu->sao_nb & bit)) skip = 1;
+                if (!((cIdx ? ctu->sao_nb_c : ctu->sao_nb) & bit)) skip = 1;
+              } else if (cIdx && on_border && (ctu->flags & HC_CTU_SAO_C_SELF)) {
+                skip = 1; /* reference quirk: see HC_CTU_SAO_C_SELF */
               }
             }
             if (skip) continue;
@@ -523,7 +558,7 @@ static void oracle_sao_plane(const hc_pic* pic, const hc_ctu* ctus, const uint8_
         for (int j = 0; j < ctbH; j++)
           for (int i = 0; i < ctbW; i++) {
             const int x = xC + i, y = yC + j;
-            if (nofilt && (edge[((x * SubW) >> 2) + (size_t)((y * SubH) >> 2) * w4] & HC_EDGE_NOFILT)) continue;
+            if (nofilt && sao_sample_skipped(pic, edge[((x * SubW) >> 2) + (size_t)((y * SubH) >> 2) * w4])) continue;
             const int c = in[x + (size_t)y * stride];
             const int bandIdx = bandTable[c >> bandShift];
             if (bandIdx > 0) out[x + (size_t)y * stride] = (uint16_t)clip3i(0, maxv, c + ctu->sao_offset[cIdx][bandIdx - 1]);
@@ -612,4 +647,15 @@ int hc_oracle_reconstruct(const hc_pic* pic, const hc_ctu* ctus, const hc_blk* b
     }
   }
   return 0;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* Block-level entry points used by the test-content generator (tools/hevc_enc) to keep its
+ * encoding loop closed (its reconstruction is by construction what a conforming decoder yields). */
+void hc_oracle_predict_block(const hc_pic* pic, const hc_blk* b, uint16_t* plane, int stride, uint16_t* dst) {
+  oracle_predict(pic, b, plane, stride, dst);
+}
+void hc_oracle_residual_block(const hc_pic* pic, const hc_tb* tb, const hc_coeff* coeffs, const uint8_t* scaling,
+                              int32_t* res) {
+  oracle_tb_residual(pic, tb, coeffs, scaling, res);
 }
