@@ -63,7 +63,8 @@ CASES = {
     "chroma_qp_offsets": (264, 200, dict(cb_qp_offset=5, cr_qp_offset=-4)),
     "plain":             (264, 200, dict(strong_intra=0, sao=0, sign_hiding=0)),
     "novui":             (264, 200, dict(vui=0)),
-    "odd_size":          (250, 131, dict(seed=3)),
+    "odd_size":          (250, 130, dict(seed=3)),
+    "odd_size_444":      (251, 131, dict(seed=3, chroma_format=3)),
     "tiny":              (8, 8, dict(seed=4)),
     "one_ctb_wide":      (40, 300, dict(wpp=1, seed=5)),
     "deep_rqt_520":      (520, 520, dict(max_th_depth=3, seed=7)),
