@@ -552,6 +552,13 @@ int hc_batch_stage_ms(hc_batch* b, float ms[8]) {
   return HC_OK;
 }
 
+void* hc_host_alloc(size_t bytes) {
+  void* p = nullptr;
+  if (!cuda_ok(cudaMallocHost(&p, bytes ? bytes : 1), "cudaMallocHost")) return nullptr;
+  return p;
+}
+void hc_host_free(void* p) { if (p) cudaFreeHost(p); }
+
 int hc_batch_launch_count(const hc_batch* b) { return b ? b->launches : 0; }
 size_t hc_batch_upload_bytes(const hc_batch* b) { return b ? b->arena_bytes : 0; }
 

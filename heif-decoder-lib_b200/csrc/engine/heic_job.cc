@@ -1,0 +1,240 @@
+// heic_job.cc — HEIC files -> interleaved RGB for many files at once (include/heifcuda.h,
+// "HEIC batch decode"). Host-side orchestration only: container resolution, threaded CABAC parse,
+// batch placement; every pixel is produced by the device engine (no CPU reconstruction exists).
+//
+// Mirrors, per file, what HeifContext::decode_image_user does in the reference
+// (libheif/context.cc:1516-1600): decode_image_planar (:1729) for hvc1 items, decode_full_grid_image
+// (:2120-2404) + decode_and_paste_tile_image (:2407-2539) for grids, the alpha auxiliary image
+// (:2029-2078), the nclx precedence (:1844-1847) and convert_colorspace (colorconversion.cc:487).
+#include <atomic>
+#include <chrono>
+#include <thread>
+#include <vector>
+#include "../capi/capi_internal.h"
+
+namespace {
+
+struct CodedItem {
+  int file;
+  uint32_t item_id;
+  std::vector<uint8_t> stream;
+  hc_records rec;
+  std::string error;
+};
+
+struct ImagePlan {
+  int file = 0;
+  hc_heif_image_info info{};
+  std::vector<int> tiles;   // indices into items (1 for a single image)
+  int alpha = -1;           // index into items
+  int canvas = -1;
+  hc_image_desc desc{};
+  hc_csc_params csc{};
+};
+
+}  // namespace
+
+struct hc_heic_job {
+  hc_engine* eng = nullptr;
+  hc_batch* batch = nullptr;
+  std::vector<std::unique_ptr<hc::HeifFile>> files;
+  std::vector<CodedItem> items;
+  std::vector<ImagePlan> images;
+  double parse_seconds = 0;
+  bool want_alpha = false;
+};
+
+extern "C" {
+
+void hc_heic_job_destroy(hc_heic_job* j) {
+  if (!j) return;
+  if (j->batch) hc_batch_destroy(j->batch);
+  delete j;
+}
+
+hc_heic_job* hc_heic_job_create(hc_engine* e, int nfiles, const uint8_t* const* data, const size_t* sizes,
+                                int want_alpha, int threads) {
+  if (!e || nfiles <= 0 || !data || !sizes) {
+    hc::set_last_error("hc_heic_job_create: bad argument");
+    return nullptr;
+  }
+  std::unique_ptr<hc_heic_job> j(new hc_heic_job);
+  j->eng = e;
+  j->want_alpha = want_alpha != 0;
+  const auto t0 = std::chrono::steady_clock::now();
+
+  // ---- containers: which coded items does every image need? ----
+  j->files.resize(nfiles);
+  j->images.resize(nfiles);
+  for (int f = 0; f < nfiles; f++) {
+    j->files[f].reset(new hc::HeifFile);
+    std::string err = j->files[f]->parse(data[f], sizes[f]);
+    if (!err.empty()) { hc::set_last_error("file " + std::to_string(f) + ": " + err); return nullptr; }
+    hc::HeifFile& hf = *j->files[f];
+    ImagePlan& im = j->images[f];
+    im.file = f;
+    const uint32_t id = hf.primary_id();
+    const hc::HeifItem* it = hf.item(id);
+    if (!it) { hc::set_last_error("file " + std::to_string(f) + ": no primary item"); return nullptr; }
+    im.info.id = id;
+    im.info.rows = im.info.cols = 1;
+    im.info.width = it->ispe_w;
+    im.info.height = it->ispe_h;
+    im.info.nclx_present = it->nclx.present;
+    im.info.primaries = it->nclx.primaries;
+    im.info.transfer = it->nclx.transfer;
+    im.info.matrix = it->nclx.matrix;
+    im.info.full_range = it->nclx.full_range;
+    im.info.alpha_id = hf.alpha_item(id);
+    std::vector<uint32_t> ids;
+    if (hf.is_grid(id)) {
+      hc::HeifGrid g;
+      err = hf.grid(id, g);
+      if (!err.empty()) { hc::set_last_error("file " + std::to_string(f) + ": " + err); return nullptr; }
+      im.info.is_grid = 1;
+      im.info.rows = g.rows; im.info.cols = g.cols; im.info.width = g.out_w; im.info.height = g.out_h;
+      ids = g.tiles;
+    } else {
+      ids.push_back(id);
+    }
+    for (uint32_t t : ids) {
+      im.tiles.push_back((int)j->items.size());
+      j->items.emplace_back();
+      j->items.back().file = f;
+      j->items.back().item_id = t;
+    }
+    if (im.info.alpha_id) {
+      if (hf.is_grid(im.info.alpha_id)) { hc::set_last_error("grid-coded alpha images are not supported"); return nullptr; }
+      im.alpha = (int)j->items.size();
+      j->items.emplace_back();
+      j->items.back().file = f;
+      j->items.back().item_id = im.info.alpha_id;
+    }
+  }
+
+  // ---- serial CABAC parse of every coded item, in parallel across items ----
+  int nthreads = threads > 0 ? threads : (int)std::thread::hardware_concurrency();
+  if (nthreads < 1) nthreads = 1;
+  nthreads = std::min<int>(nthreads, (int)j->items.size());
+  std::atomic<size_t> next{0};
+  auto worker = [&]() {
+    for (;;) {
+      size_t i = next.fetch_add(1);
+      if (i >= j->items.size()) return;
+      CodedItem& ci = j->items[i];
+      std::string err = j->files[ci.file]->coded_stream(ci.item_id, ci.stream);
+      if (!err.empty()) { ci.error = err; continue; }
+      hc::HevcIntraParser parser;
+      err = parser.push_length_prefixed(ci.stream.data(), ci.stream.size());
+      if (!err.empty()) { ci.error = err; continue; }
+      ci.rec.rec = parser.take_picture(&err);
+      if (!ci.rec.rec) ci.error = err;
+      std::vector<uint8_t>().swap(ci.stream);
+    }
+  };
+  if (nthreads == 1) worker();
+  else {
+    std::vector<std::thread> pool;
+    for (int t = 0; t < nthreads; t++) pool.emplace_back(worker);
+    for (auto& t : pool) t.join();
+  }
+  for (auto& ci : j->items)
+    if (!ci.error.empty()) {
+      hc::set_last_error("file " + std::to_string(ci.file) + " item " + std::to_string(ci.item_id) + ": " + ci.error);
+      return nullptr;
+    }
+  j->parse_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+
+  // ---- batch placement ----
+  j->batch = hc_batch_create(e);
+  if (!j->batch) return nullptr;
+  for (ImagePlan& im : j->images) {
+    const hc_pic& p0 = j->items[im.tiles[0]].rec.rec->pic;
+    const bool has_alpha = im.alpha >= 0;
+    int W = im.info.width, H = im.info.height;
+    if (!im.info.is_grid) { W = p0.crop_w; H = p0.crop_h; }   // decoded size, like the reference
+    im.canvas = hc_batch_add_canvas(j->batch, W, H, p0.chroma_format, p0.bit_depth_y, has_alpha);
+    if (im.canvas < 0) return nullptr;
+    int matrix, primaries, full;
+    if (im.info.is_grid) {
+      const int tw = p0.crop_w, th = p0.crop_h;
+      for (size_t k = 0; k < im.tiles.size(); k++) {
+        CodedItem& ci = j->items[im.tiles[k]];
+        const hc_pic& p = ci.rec.rec->pic;
+        const hc::HeifItem* tit = j->files[im.file]->item(ci.item_id);
+        const int tfull = tit && tit->nclx.present ? tit->nclx.full_range : p.full_range;
+        const int tmatrix = tit && tit->nclx.present ? tit->nclx.matrix : p.matrix_coeffs;
+        const int x0 = (int)(k % im.info.cols) * tw, y0 = (int)(k / im.info.cols) * th;
+        if (x0 >= W || y0 >= H) { hc::set_last_error("grid tile lies outside the output image"); return nullptr; }
+        // context.cc:2504: limited-range tiles (matrix != 0) are expanded to full range while pasting
+        if (hc_batch_add_picture(j->batch, &ci.rec, im.canvas, x0, y0, HC_ROLE_COLOUR, (!tfull && tmatrix != 0) ? 1 : 0) < 0)
+          return nullptr;
+      }
+      // the canvas only has an nclx if the grid item itself carries one (context.cc:1841-1844)
+      matrix = im.info.nclx_present ? im.info.matrix : 2;
+      primaries = im.info.nclx_present ? im.info.primaries : 2;
+      full = im.info.nclx_present ? im.info.full_range : 1;
+    } else {
+      if (hc_batch_add_picture(j->batch, &j->items[im.tiles[0]].rec, im.canvas, 0, 0, HC_ROLE_COLOUR, 0) < 0) return nullptr;
+      matrix = im.info.nclx_present ? im.info.matrix : p0.matrix_coeffs;
+      primaries = im.info.nclx_present ? im.info.primaries : p0.colour_primaries;
+      full = im.info.nclx_present ? im.info.full_range : p0.full_range;
+    }
+    if (has_alpha) {
+      const hc_pic& pa = j->items[im.alpha].rec.rec->pic;
+      if (pa.crop_w != W || pa.crop_h != H) {
+        hc::set_last_error("alpha image of a different size than the colour image (nearest-neighbour rescale) is not supported");
+        return nullptr;
+      }
+      if (hc_batch_add_picture(j->batch, &j->items[im.alpha].rec, im.canvas, 0, 0, HC_ROLE_ALPHA, 0) < 0) return nullptr;
+    }
+    const bool hdr = p0.bit_depth_y != 8;
+    const int fmt = hdr ? (j->want_alpha ? HC_OUT_RRGGBBAA_LE : HC_OUT_RRGGBB_LE) : (j->want_alpha ? HC_OUT_RGBA : HC_OUT_RGB);
+    if (hc_csc_select(matrix, primaries, full, p0.chroma_format, p0.bit_depth_y, has_alpha, fmt, &im.csc) != HC_OK) return nullptr;
+    static const int bpp_of[6] = {3, 4, 6, 8, 6, 8};
+    im.desc.width = W; im.desc.height = H; im.desc.chroma_format = p0.chroma_format; im.desc.bit_depth = p0.bit_depth_y;
+    im.desc.has_alpha = has_alpha; im.desc.out_format = fmt; im.desc.bytes_per_pixel = bpp_of[fmt];
+    im.desc.coded_pictures = (int)im.tiles.size() + (has_alpha ? 1 : 0);
+  }
+  return j.release();
+}
+
+int hc_heic_job_image_count(const hc_heic_job* j) { return j ? (int)j->images.size() : 0; }
+
+int hc_heic_job_image_desc(const hc_heic_job* j, int image, hc_image_desc* desc) {
+  if (!j || !desc || image < 0 || image >= (int)j->images.size()) { hc::set_last_error("hc_heic_job_image_desc: bad argument"); return HC_ERR_ARGUMENT; }
+  *desc = j->images[image].desc;
+  return HC_OK;
+}
+
+int hc_heic_job_upload(hc_heic_job* j) { return j ? hc_batch_upload(j->batch) : HC_ERR_ARGUMENT; }
+
+int hc_heic_job_run(hc_heic_job* j) {
+  if (!j) return HC_ERR_ARGUMENT;
+  int rc = hc_batch_reconstruct(j->batch, HC_STAGE_ALL);
+  if (rc != HC_OK) return rc;
+  for (ImagePlan& im : j->images) {
+    rc = hc_batch_convert(j->batch, im.canvas, &im.csc);
+    if (rc != HC_OK) return rc;
+  }
+  return HC_OK;
+}
+
+int hc_heic_job_sync(hc_heic_job* j) { return j ? hc_batch_sync(j->batch) : HC_ERR_ARGUMENT; }
+
+int hc_heic_job_read_rgb(hc_heic_job* j, int image, void* dst, size_t stride) {
+  if (!j || image < 0 || image >= (int)j->images.size()) { hc::set_last_error("hc_heic_job_read_rgb: bad argument"); return HC_ERR_ARGUMENT; }
+  return hc_batch_read_rgb(j->batch, j->images[image].canvas, dst, stride);
+}
+
+int hc_heic_job_read_plane(hc_heic_job* j, int image, int plane, void* dst, size_t stride) {
+  if (!j || image < 0 || image >= (int)j->images.size()) { hc::set_last_error("hc_heic_job_read_plane: bad argument"); return HC_ERR_ARGUMENT; }
+  return hc_batch_read_plane(j->batch, j->images[image].canvas, plane, dst, stride);
+}
+
+int hc_heic_job_stage_ms(hc_heic_job* j, float ms[8]) { return j ? hc_batch_stage_ms(j->batch, ms) : HC_ERR_ARGUMENT; }
+int hc_heic_job_launch_count(const hc_heic_job* j) { return j ? hc_batch_launch_count(j->batch) : 0; }
+size_t hc_heic_job_upload_bytes(const hc_heic_job* j) { return j ? hc_batch_upload_bytes(j->batch) : 0; }
+double hc_heic_job_parse_seconds(const hc_heic_job* j) { return j ? j->parse_seconds : 0.0; }
+
+}  // extern "C"

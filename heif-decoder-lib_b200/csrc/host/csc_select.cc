@@ -33,6 +33,7 @@ KrKb kr_kb(int matrix) {
 extern "C" int hc_csc_select(int matrix, int primaries, int full_range, int chroma_format, int bit_depth,
                              int has_alpha, int out_format, hc_csc_params* out) {
   (void)primaries;
+  (void)has_alpha;
   if (!out || out_format < HC_OUT_RGB || out_format > HC_OUT_RRGGBBAA_LE || bit_depth < 8 || bit_depth > 16) {
     hc::set_last_error("hc_csc_select: bad argument");
     return HC_ERR_ARGUMENT;
@@ -77,10 +78,9 @@ extern "C" int hc_csc_select(int matrix, int primaries, int full_range, int chro
   p.g_cb_i = (int)std::lround(256 * p.g_cb);
   p.b_cb_i = (int)std::lround(256 * p.b_cb);
 
-  const bool to_alpha = out_format == HC_OUT_RGBA || out_format == HC_OUT_RRGGBBAA_BE || out_format == HC_OUT_RRGGBBAA_LE;
   if (matrix == 0) p.mode = HC_CSC_GBR;
   else if (matrix == 8) p.mode = HC_CSC_YCGCO;
-  else if (bit_depth == 8 && chroma_format == 1 && full_range && (to_alpha || !has_alpha)) p.mode = HC_CSC_INT420;
+  else if (bit_depth == 8 && chroma_format == 1 && full_range) p.mode = HC_CSC_INT420;  // with or without alpha
   else p.mode = HC_CSC_FLOAT;
   *out = p;
   return HC_OK;

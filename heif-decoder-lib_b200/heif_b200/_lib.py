@@ -38,6 +38,12 @@ class CscParams(C.Structure):
                 ("r_cr", C.c_float), ("g_cb", C.c_float), ("g_cr", C.c_float), ("b_cb", C.c_float)]
 
 
+class ImageDesc(C.Structure):
+    """hc_image_desc"""
+    _fields_ = [(n, C.c_int32) for n in ("width", "height", "chroma_format", "bit_depth", "has_alpha", "out_format",
+                                           "bytes_per_pixel", "coded_pictures")]
+
+
 class HeifImageInfo(C.Structure):
     """hc_heif_image_info"""
     _fields_ = [("id", C.c_uint32), ("is_grid", C.c_int32), ("width", C.c_int32), ("height", C.c_int32),
@@ -91,6 +97,21 @@ SYMBOLS = [
     ("hc_batch_stage_ms", _i, [_vp, C.POINTER(C.c_float)]),
     ("hc_batch_launch_count", _i, [_vp]),
     ("hc_batch_upload_bytes", _sz, [_vp]),
+    ("hc_heic_job_create", _vp, [_vp, _i, C.POINTER(C.c_char_p), C.POINTER(_sz), _i, _i]),
+    ("hc_heic_job_destroy", None, [_vp]),
+    ("hc_heic_job_image_count", _i, [_vp]),
+    ("hc_heic_job_image_desc", _i, [_vp, _i, C.POINTER(ImageDesc)]),
+    ("hc_heic_job_upload", _i, [_vp]),
+    ("hc_heic_job_run", _i, [_vp]),
+    ("hc_heic_job_sync", _i, [_vp]),
+    ("hc_heic_job_read_rgb", _i, [_vp, _i, _vp, _sz]),
+    ("hc_heic_job_read_plane", _i, [_vp, _i, _i, _vp, _sz]),
+    ("hc_heic_job_stage_ms", _i, [_vp, C.POINTER(C.c_float)]),
+    ("hc_heic_job_launch_count", _i, [_vp]),
+    ("hc_heic_job_upload_bytes", _sz, [_vp]),
+    ("hc_heic_job_parse_seconds", C.c_double, [_vp]),
+    ("hc_host_alloc", _vp, [_sz]),
+    ("hc_host_free", None, [_vp]),
 ]
 
 _libs = {}

@@ -256,3 +256,77 @@ def decode_heic(engine, data, out_format=OUT_RGB, item_id=None):
     finally:
         batch.close()
         hf.close()
+
+
+class HeicJob:
+    """Many HEIC files -> interleaved RGB through the native batch path (hc_heic_job): host threads
+    parse every coded item, the GPU reconstructs all of them as one batch."""
+
+    def __init__(self, engine, files, want_alpha=False, threads=0):
+        from ._lib import ImageDesc
+        self._L, self._eng = engine._L, engine
+        self._bufs = [C.create_string_buffer(f, len(f)) for f in files]
+        n = len(files)
+        ptrs = (C.c_char_p * n)(*[C.cast(b, C.c_char_p) for b in self._bufs])
+        sizes = (C.c_size_t * n)(*[len(f) for f in files])
+        self._h = self._L.hc_heic_job_create(engine._h, n, ptrs, sizes, int(want_alpha), threads)
+        if not self._h:
+            raise HeifCudaError("heic job: " + (self._L.hc_last_error() or b"").decode())
+        self.descs = []
+        for i in range(self._L.hc_heic_job_image_count(self._h)):
+            d = ImageDesc()
+            check(self._L, self._L.hc_heic_job_image_desc(self._h, i, C.byref(d)), "image_desc")
+            self.descs.append(d)
+
+    def upload(self):
+        check(self._L, self._L.hc_heic_job_upload(self._h), "upload")
+
+    def run(self):
+        check(self._L, self._L.hc_heic_job_run(self._h), "run")
+
+    def sync(self):
+        check(self._L, self._L.hc_heic_job_sync(self._h), "sync")
+
+    def read_rgb(self, image, out=None):
+        d = self.descs[image]
+        if out is None:
+            out = np.empty((d.height, d.width * d.bytes_per_pixel), np.uint8)
+        check(self._L, self._L.hc_heic_job_read_rgb(self._h, image, out.ctypes.data, out.strides[0]), "read_rgb")
+        return out
+
+    def read_plane(self, image, plane):
+        d = self.descs[image]
+        w, h = d.width, d.height
+        if plane in (1, 2):
+            if d.chroma_format in (1, 2):
+                w = (w + 1) // 2
+            if d.chroma_format == 1:
+                h = (h + 1) // 2
+        out = np.empty((h, w), np.uint8 if d.bit_depth == 8 else np.uint16)
+        check(self._L, self._L.hc_heic_job_read_plane(self._h, image, plane, out.ctypes.data, out.strides[0]), "read_plane")
+        return out
+
+    def stage_ms(self):
+        ms = (C.c_float * 8)()
+        check(self._L, self._L.hc_heic_job_stage_ms(self._h, ms), "stage_ms")
+        return dict(zip(("h2d", "k1_transform", "k2_intra", "k3_deblock", "k4_sao", "k5_csc", "d2h"), list(ms)[:7]))
+
+    @property
+    def launch_count(self):
+        return self._L.hc_heic_job_launch_count(self._h)
+
+    @property
+    def upload_bytes(self):
+        return self._L.hc_heic_job_upload_bytes(self._h)
+
+    @property
+    def parse_seconds(self):
+        return self._L.hc_heic_job_parse_seconds(self._h)
+
+    def close(self):
+        if self._h:
+            self._L.hc_heic_job_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        self.close()

@@ -184,6 +184,51 @@ int hc_batch_launch_count(const hc_batch* b);
 /* bytes of the packed record arena uploaded by hc_batch_upload */
 size_t hc_batch_upload_bytes(const hc_batch* b);
 
+/* ------------------------------------------------------------------ HEIC batch decode ------ */
+/* The call a user of the reference makes is heif_decode_image(handle, &img, heif_colorspace_RGB,
+ * heif_chroma_interleaved_*, opts) per file (libheif/api/libheif/heif.cc:1150), which walks
+ * HeifContext::decode_image_user (context.cc:1516): container -> one decoder instance per coded
+ * item -> paste -> colour conversion. hc_heic_job is the same walk for MANY files at once: all
+ * coded items (single images, every grid tile, alpha auxiliary images) of all files are parsed by
+ * a pool of host threads and reconstructed on the GPU as one batch. */
+typedef struct hc_heic_job hc_heic_job;
+
+typedef struct hc_image_desc {
+  int32_t width, height;     /* output size in pixels                                             */
+  int32_t chroma_format;     /* of the decoded YCbCr image                                        */
+  int32_t bit_depth;
+  int32_t has_alpha;
+  int32_t out_format;        /* HC_OUT_* chosen for this image (8-bit -> RGB/RGBA, else RRGGBB(AA)) */
+  int32_t bytes_per_pixel;
+  int32_t coded_pictures;    /* HEVC pictures decoded for this image (tiles + alpha)              */
+} hc_image_desc;
+
+/* Parses `nfiles` HEIC files held in host memory (the primary image of each) with `threads` host
+ * threads (<=0: hardware concurrency). The buffers must stay valid until hc_heic_job_destroy.
+ * want_alpha: 0 -> interleaved RGB / RRGGBB_LE, 1 -> RGBA / RRGGBBAA_LE. */
+hc_heic_job* hc_heic_job_create(hc_engine* e, int nfiles, const uint8_t* const* data, const size_t* sizes,
+                                int want_alpha, int threads);
+void hc_heic_job_destroy(hc_heic_job* j);
+int hc_heic_job_image_count(const hc_heic_job* j);
+int hc_heic_job_image_desc(const hc_heic_job* j, int image, hc_image_desc* desc);
+/* H2D upload of the packed records (async). */
+int hc_heic_job_upload(hc_heic_job* j);
+/* K1..K4 for all pictures + K5 for every image (async; may be called repeatedly after one upload). */
+int hc_heic_job_run(hc_heic_job* j);
+int hc_heic_job_sync(hc_heic_job* j);
+/* copies image `image` to host memory (dst_stride_bytes >= width*bytes_per_pixel), synchronous */
+int hc_heic_job_read_rgb(hc_heic_job* j, int image, void* dst, size_t dst_stride_bytes);
+/* decoded planes of an image (0 Y, 1 Cb, 2 Cr, 3 alpha), as the plugin ABI would return them */
+int hc_heic_job_read_plane(hc_heic_job* j, int image, int plane, void* dst, size_t dst_stride_bytes);
+/* stage timings of the last run (see hc_batch_stage_ms), launches, uploaded bytes, host parse seconds */
+int hc_heic_job_stage_ms(hc_heic_job* j, float ms[8]);
+int hc_heic_job_launch_count(const hc_heic_job* j);
+size_t hc_heic_job_upload_bytes(const hc_heic_job* j);
+double hc_heic_job_parse_seconds(const hc_heic_job* j);
+/* pinned host memory for fast H2D/D2H in the caller (NULL when no CUDA engine) */
+void* hc_host_alloc(size_t bytes);
+void hc_host_free(void* p);
+
 #ifdef __cplusplus
 }
 #endif

@@ -69,8 +69,9 @@ int hc_oracle_csc(const uint16_t* y, const uint16_t* cb, const uint16_t* cr, con
   const int maxv = (1 << bit_depth) - 1;
   const int half = 1 << (bit_depth - 1);
   /* the fixed-point ops win only for 8-bit 4:2:0 full-range input */
-  const int use_int = bit_depth == 8 && chroma_format == 1 && full_range && matrix != 0 && matrix != 8 &&
-                      (to_alpha || !has_alpha);
+  /* (also when an alpha plane is present but not wanted: the pipeline drops it and still takes the
+   * fixed-point op — checked against the reference with tests/golden/heic/alpha_420_8.heic) */
+  const int use_int = bit_depth == 8 && chroma_format == 1 && full_range && matrix != 0 && matrix != 8;
   const int r_cr = (int)lround(256 * k.r_cr), g_cr = (int)lround(256 * k.g_cr);
   const int g_cb = (int)lround(256 * k.g_cb), b_cb = (int)lround(256 * k.b_cb);
   const float lro = (float)(16 << (bit_depth - 8));

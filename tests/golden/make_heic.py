@@ -1,0 +1,86 @@
+#!/usr/bin/env python
+"""Generates the HEIC file fixtures under tests/golden/heic/ (tools/heif_writer + tools/hevc_enc) and
+records what the UNMODIFIED reference (oracle/_ref/libheifref.so, heif_decode_image) returns for them.
+
+  python tests/golden/make_heic.py
+"""
+import hashlib
+import json
+import os
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+from tools import heif_writer, hevcenc  # noqa: E402
+import refheif as R  # noqa: E402
+
+OUT = os.path.join(HERE, "heic")
+
+
+def md5(b):
+    return hashlib.md5(b).hexdigest()
+
+
+def enc(w, h, cf, bd, seed, **kw):
+    return hevcenc.encode(hevcenc.synth_image(w, h, cf, bd, seed), chroma_format=cf, bit_depth=bd, seed=seed, **kw)
+
+
+def build():
+    files = {}
+    # grids (BASELINE config C2 in miniature): full-range tiles paste by memcpy, integer CSC
+    files["grid_300x200_t128"] = heif_writer.synth_grid_heic(300, 200, tile=128, seed=3)
+    files["grid_640x384_t128_wpp"] = heif_writer.synth_grid_heic(640, 384, tile=128, seed=4, wpp=1, log2_ctb=5)
+    # tiles without VUI are limited range for the reference: float rescale while pasting (context.cc:2504)
+    files["grid_limited_260x130_t64"] = heif_writer.synth_grid_heic(260, 130, tile=64, seed=5, vui=0)
+    files["grid_709_limited"] = heif_writer.synth_grid_heic(256, 128, tile=64, seed=6, vui=1, full_range=0, matrix=1)
+    files["grid_444"] = heif_writer.synth_grid_heic(200, 120, tile=64, seed=7, chroma_format=3)
+    files["grid_422_10"] = heif_writer.synth_grid_heic(200, 120, tile=64, seed=8, chroma_format=2, bit_depth=10)
+    # single images
+    files["single_420_8_full601"] = heif_writer.single_image(enc(264, 200, 1, 8, 9), 264, 200, 1, 8)
+    files["single_420_8_limited709"] = heif_writer.single_image(enc(264, 200, 1, 8, 10, full_range=0, matrix=1), 264, 200, 1, 8)
+    files["single_420_8_novui"] = heif_writer.single_image(enc(264, 200, 1, 8, 11, vui=0), 264, 200, 1, 8)
+    files["single_420_8_colr_override"] = heif_writer.single_image(enc(264, 200, 1, 8, 12, vui=0), 264, 200, 1, 8, nclx=(1, 13, 1, 1))
+    files["single_422_8"] = heif_writer.single_image(enc(200, 120, 2, 8, 13), 200, 120, 2, 8)
+    files["single_444_8_bt2020"] = heif_writer.single_image(enc(200, 120, 3, 8, 14, matrix=9, primaries=9), 200, 120, 3, 8)
+    files["single_mono_8"] = heif_writer.single_image(enc(200, 120, 0, 8, 15), 200, 120, 0, 8)
+    files["single_420_10"] = heif_writer.single_image(enc(200, 120, 1, 10, 16), 200, 120, 1, 10)
+    files["single_420_12_limited"] = heif_writer.single_image(enc(200, 120, 1, 12, 17, full_range=0, matrix=9), 200, 120, 1, 12)
+    # alpha auxiliary images (BASELINE config C3 in miniature)
+    files["alpha_420_8"] = heif_writer.single_image(enc(200, 120, 1, 8, 18), 200, 120, 1, 8, alpha_stream=enc(200, 120, 0, 8, 19))
+    files["alpha_422_10"] = heif_writer.single_image(enc(200, 120, 2, 10, 20), 200, 120, 2, 10, alpha_stream=enc(200, 120, 0, 10, 21))
+    files["alpha_422_12"] = heif_writer.single_image(enc(200, 120, 2, 12, 22), 200, 120, 2, 12, alpha_stream=enc(200, 120, 0, 12, 23))
+    files["alpha_444_8_limited"] = heif_writer.single_image(enc(200, 120, 3, 8, 24, full_range=0), 200, 120, 3, 8,
+                                                            alpha_stream=enc(200, 120, 1, 8, 25), alpha_chroma_format=1)
+    return files
+
+
+def reference_outputs(data):
+    planes = R.decode(data, R.COLORSPACE_UNDEFINED, R.CHROMA_UNDEFINED)
+    bpp = planes["bpp"]
+    out = {"bit_depth": bpp, "planes_md5": md5(b"".join(planes[k][0] for k in ("Y", "Cb", "Cr", "A") if k in planes)),
+           "width": planes["Y"][1], "height": planes["Y"][2], "has_alpha": "A" in planes}
+    targets = {"rgb": R.CHROMA_RGB, "rgba": R.CHROMA_RGBA} if bpp == 8 else {"rrggbb_le": R.CHROMA_RRGGBB_LE, "rrggbbaa_le": R.CHROMA_RRGGBBAA_LE}
+    for name, chroma in targets.items():
+        try:
+            r = R.decode(data, R.COLORSPACE_RGB, chroma)
+            out[name + "_md5"] = md5(r["interleaved"][0])
+        except RuntimeError as e:
+            out[name + "_error"] = str(e)
+    return out
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    meta = {}
+    for name, data in sorted(build().items()):
+        open(os.path.join(OUT, name + ".heic"), "wb").write(data)
+        meta[name] = reference_outputs(data)
+        meta[name]["bytes"] = len(data)
+        print(name, meta[name])
+    json.dump(meta, open(os.path.join(HERE, "heic.json"), "w"), indent=1, sort_keys=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,84 @@
+"""Oracle-side HEIC decode: product container reader + host parser feed the CPU oracle; grid paste,
+alpha attach and colour conversion are restated here following libheif/context.cc:1729-2539.
+Test infrastructure (the checker)."""
+import ctypes as C
+
+import numpy as np
+
+import heif_b200 as hb
+import oracle_lib
+
+OUT_BPP = {0: 3, 1: 4, 2: 6, 3: 8, 4: 6, 5: 8}
+
+
+def csc(planes, chroma_format, bit_depth, matrix, full_range, out_format, alpha=None):
+    O = oracle_lib.lib()
+    h, w = planes[0].shape
+    out = np.zeros((h, w * OUT_BPP[out_format]), np.uint8)
+    pl = [np.ascontiguousarray(p, np.uint16) for p in planes]
+    a = np.ascontiguousarray(alpha, np.uint16) if alpha is not None else None
+    rc = O.hc_oracle_csc(C.c_void_p(pl[0].ctypes.data), C.c_void_p(pl[1].ctypes.data if len(pl) > 1 else None),
+                         C.c_void_p(pl[2].ctypes.data if len(pl) > 2 else None), C.c_void_p(a.ctypes.data if a is not None else None),
+                         pl[0].shape[1], pl[1].shape[1] if len(pl) > 1 else 0, a.shape[1] if a is not None else 0,
+                         w, h, chroma_format, bit_depth, matrix, int(full_range), out_format,
+                         C.c_void_p(out.ctypes.data), C.c_size_t(out.strides[0]))
+    if rc != 0:
+        raise RuntimeError("oracle csc cannot convert this combination")
+    return out
+
+
+def _rescale_limited(plane, chroma, bit_depth):
+    """context.cc:2504-2528: clip_f_u8((v - 16<<(bpp-8)) * ratio), byte-wise (8-bit tiles)"""
+    ratio = np.float32(1.1429 if chroma else 1.1689)
+    full = (plane.astype(np.float32) - np.float32(16 << (bit_depth - 8))) * ratio
+    x = (full + np.float32(0.5)).astype(np.int64)  # (long)(fx + 0.5f): truncation toward zero
+    return np.clip(x, 0, 255).astype(np.uint16)
+
+
+def decode_planes(data, item_id=None):
+    """Returns (planes[list], alpha or None, chroma_format, bit_depth, (matrix, full_range))"""
+    hf = hb.HeifFile(data, host_only=True)
+    iid = item_id or hf.primary_id
+    info = hf.image_info(iid)
+    if info.is_grid:
+        ids = hf.grid_tiles(iid)
+        recs = [hb.parse_picture(hf.coded_stream(t), host_only=True) for t in ids]
+        p0 = recs[0].pic
+        cf, bd = p0.chroma_format, p0.bit_depth_y
+        W, H = info.width, info.height
+        sw = 2 if cf in (1, 2) else 1
+        sh = 2 if cf == 1 else 1
+        canvas = [np.zeros((H, W), np.uint16)]
+        if cf:
+            canvas += [np.zeros(((H + sh - 1) // sh, (W + sw - 1) // sw), np.uint16) for _ in range(2)]
+        tw, th = p0.crop_w, p0.crop_h
+        for i, (t, r) in enumerate(zip(ids, recs)):
+            pl, _ = oracle_lib.reconstruct(r)
+            tinfo = hf.image_info(t)
+            full = tinfo.full_range if tinfo.nclx_present else r.pic.full_range
+            matrix = tinfo.matrix if tinfo.nclx_present else r.pic.matrix_coeffs
+            x0, y0 = (i % info.cols) * tw, (i // info.cols) * th
+            for k, p in enumerate(pl):
+                if (not full) and matrix != 0:
+                    p = _rescale_limited(p, k > 0, bd)
+                xx, yy = (x0, y0) if k == 0 else ((x0 + sw - 1) // sw, (y0 + sh - 1) // sh)
+                hh, ww = min(p.shape[0], canvas[k].shape[0] - yy), min(p.shape[1], canvas[k].shape[1] - xx)
+                canvas[k][yy:yy + hh, xx:xx + ww] = p[:hh, :ww]
+        nclx = (info.matrix, info.full_range) if info.nclx_present else (2, 1)
+        planes = canvas
+    else:
+        r = hb.parse_picture(hf.coded_stream(iid), host_only=True)
+        planes, _ = oracle_lib.reconstruct(r)
+        cf, bd = r.pic.chroma_format, r.pic.bit_depth_y
+        nclx = (info.matrix, info.full_range) if info.nclx_present else (r.pic.matrix_coeffs, r.pic.full_range)
+    alpha = None
+    if info.alpha_id:
+        a = hb.parse_picture(hf.coded_stream(info.alpha_id), host_only=True)
+        apl, _ = oracle_lib.reconstruct(a)
+        alpha = apl[0]
+    return planes, alpha, cf, bd, nclx
+
+
+def decode_rgb(data, out_format, item_id=None):
+    planes, alpha, cf, bd, (matrix, full) = decode_planes(data, item_id)
+    return csc(planes, cf, bd, matrix, full, out_format, alpha)

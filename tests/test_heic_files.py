@@ -1,0 +1,75 @@
+"""HEIC file fixtures (tests/golden/heic/, made by tests/golden/make_heic.py and decoded by the
+unmodified reference's heif_decode_image): grids, limited-range tiles, colr override, 4:2:2/4:4:4,
+10/12 bit, alpha auxiliary images -> interleaved RGB / RGBA / RRGGBB(AA)_LE.
+CPU test: container reader + host parser + oracle reproduce the reference's MD5s.
+GPU test: the native batch path (hc_heic_job) reproduces them too."""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+import heif_b200 as hb
+import heic_oracle
+from conftest import ROOT
+
+DIR = os.path.join(ROOT, "tests", "golden", "heic")
+META = json.load(open(os.path.join(ROOT, "tests", "golden", "heic.json")))
+NAMES = sorted(META)
+FORMATS = {"rgb": hb.OUT_RGB, "rgba": hb.OUT_RGBA, "rrggbb_le": hb.OUT_RRGGBB_LE, "rrggbbaa_le": hb.OUT_RRGGBBAA_LE}
+
+
+def load(name):
+    return open(os.path.join(DIR, name + ".heic"), "rb").read()
+
+
+def md5(b):
+    return hashlib.md5(b).hexdigest()
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_oracle_reproduces_reference(name):
+    m = META[name]
+    planes, alpha, cf, bd, _ = heic_oracle.decode_planes(load(name))
+    dt = np.uint8 if bd == 8 else np.dtype("<u2")
+    allp = planes + ([alpha] if alpha is not None else [])
+    assert md5(b"".join(p.astype(dt).tobytes() for p in allp)) == m["planes_md5"]
+    for key, fmt in FORMATS.items():
+        if key + "_md5" in m:
+            assert md5(heic_oracle.decode_rgb(load(name), fmt).tobytes()) == m[key + "_md5"], key
+
+
+@pytest.fixture(scope="module")
+def engine():
+    e = hb.Engine(0)
+    yield e
+    e.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("want_alpha", [False, True])
+def test_gpu_heic_job_matches_reference(engine, want_alpha):
+    """All fixture files in ONE job (one upload, one launch sequence for every tile of every file)."""
+    job = hb.HeicJob(engine, [load(n) for n in NAMES], want_alpha=want_alpha, threads=4)
+    job.upload()
+    job.run()
+    for i, name in enumerate(NAMES):
+        m, d = META[name], job.descs[i]
+        assert (d.width, d.height, d.bit_depth, bool(d.has_alpha)) == (m["width"], m["height"], m["bit_depth"], m["has_alpha"])
+        key = {hb.OUT_RGB: "rgb", hb.OUT_RGBA: "rgba", hb.OUT_RRGGBB_LE: "rrggbb_le", hb.OUT_RRGGBBAA_LE: "rrggbbaa_le"}[d.out_format]
+        assert md5(job.read_rgb(i).tobytes()) == m[key + "_md5"], (name, key)
+        dt = np.uint8 if d.bit_depth == 8 else np.dtype("<u2")
+        planes = [job.read_plane(i, k) for k in range(3 if d.chroma_format else 1)]
+        if d.has_alpha:
+            planes.append(job.read_plane(i, 3))
+        assert md5(b"".join(p.astype(dt).tobytes() for p in planes)) == m["planes_md5"], name
+    assert job.launch_count >= 6
+    job.close()
+
+
+@pytest.mark.gpu
+def test_gpu_decode_heic_python_path(engine):
+    for name in ("grid_300x200_t128", "single_420_8_novui", "alpha_420_8"):
+        rgb = hb.decode_heic(engine, load(name), hb.OUT_RGB)
+        assert md5(rgb.tobytes()) == META[name]["rgb_md5"], name
