@@ -1,0 +1,311 @@
+#!/usr/bin/env python
+"""bench.py — decoded MP/s HEIC -> RGB on B200 (BASELINE.json metric), one JSON line on stdout.
+
+Workload (config.workload): BASELINE config C2 — 4032x3024 "iPhone-style" grid of 48 (8x6) 512x512
+HEVC intra tiles, 8-bit 4:2:0, CTB 64, WPP, SAO + deblocking, QP 26, full-range BT.601 VUI -> interleaved
+RGB. Content is synthetic (tools/hevc_enc closed-loop encoder + tools/heif_writer), generated untimed
+at start-up. One step = one batch of `--images` such files (default 8 = 384 coded pictures in flight).
+
+  value : device time of K steps of K1..K5 with the packed records already resident in HBM
+          (CUDA events on the engine's stream), whole-job MP/s over all ranks
+  e2e   : the same metric through the C ABI from HEIC bytes in host memory to RGB bytes in pinned host
+          memory: host CABAC parse (all host threads) + H2D + kernels + D2H inside the timed region
+  roofline     : the dominant kernel's algorithmic bytes / its CUDA-event duration vs MEASURED_PEAKS.json
+  cpu_baseline : the unmodified reference (oracle/_ref: libheif + libde265, heif_decode_image -> RGB) on
+                 the host cores, bounded sample of the same file
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+Launched under torchrun for N > 1 (one rank per GPU, NCCL only for the barrier / max-over-ranks).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (os.path.join(ROOT, "heif-decoder-lib_b200"), os.path.join(ROOT, "tests"), ROOT):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+WORKLOAD = "C2: 4032x3024 grid of 48 512x512 HEVC-intra tiles, 8-bit 4:2:0, CTB64 WPP SAO+deblock QP26 -> RGB24"
+GRID_W, GRID_H, TILE = 4032, 3024, 512
+METRIC = "decoded MP/s HEIC->RGB (device-timed)"
+UNIT = "MP/s"
+
+
+def make_content(n_distinct, cache_dir):
+    """n_distinct synthetic 12 MP grid HEICs (cached on disk between runs of the same box)."""
+    from tools import heif_writer
+    os.makedirs(cache_dir, exist_ok=True)
+    files = []
+    for i in range(n_distinct):
+        path = os.path.join(cache_dir, "c2_%dx%d_t%d_seed%d.heic" % (GRID_W, GRID_H, TILE, i))
+        if not os.path.exists(path):
+            data = heif_writer.synth_grid_heic(GRID_W, GRID_H, tile=TILE, seed=100 + i, qp=26, wpp=1, sao=1, log2_ctb=6)
+            with open(path + ".tmp", "wb") as f:
+                f.write(data)
+            os.replace(path + ".tmp", path)
+        files.append(open(path, "rb").read())
+    return files
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region."""
+
+    def __init__(self, index):
+        self.index, self.lines, self.proc = index, [], None
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def reference_arm(files, steps, warmup, threads):
+    """The reference's own CPU implementation: heif_decode_image(..., RGB, interleaved_RGB) per file with
+    heif_context_set_threads(ctx, handle, all cores) (grid -> tile threads, heif.cc:499-514)."""
+    import refheif as R
+    if not R.available():
+        return None
+    mp = GRID_W * GRID_H / 1e6
+    sample = files[:1]
+    for _ in range(warmup):
+        R.decode(sample[0], R.COLORSPACE_RGB, R.CHROMA_RGB, threads=threads)
+    t0 = time.perf_counter()
+    n = 0
+    for _ in range(steps):
+        for f in sample:
+            R.decode(f, R.COLORSPACE_RGB, R.CHROMA_RGB, threads=threads)
+            n += 1
+    dt = time.perf_counter() - t0
+    return {"value": n * mp / dt, "ms_per_step": dt / steps * 1e3, "sample": "%d x one 12.19 MP grid file per step" % len(sample)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--images", type=int, default=8, help="12 MP files per step and GPU")
+    ap.add_argument("--distinct", type=int, default=2, help="distinct synthetic files (replicated to --images)")
+    ap.add_argument("--threads", type=int, default=0, help="host parse threads (0 = all cores)")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    cores = os.cpu_count() or 1
+    cache = os.path.join(ROOT, "gpurun_out", "bench_content")
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        files = make_content(1, cache)
+        r = reference_arm(files, max(1, min(args.steps, 5)), 1, cores)
+        if r is None:
+            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref (reference build) is missing"}))
+            return 0
+        line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "u8", "data": "synthetic", "config": {"workload": WORKLOAD},
+                "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": cores, "kind": "reference", "sample": r["sample"]},
+                "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return 0
+
+    import numpy as np
+    import torch
+    import heif_b200 as hb
+
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the reconstruction path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- content (untimed; rank 0 generates, the others read the cache) ----
+    if rank == 0:
+        distinct = make_content(args.distinct, cache)
+    barrier()
+    if rank != 0:
+        distinct = make_content(args.distinct, cache)
+    files = [distinct[(i + rank) % len(distinct)] for i in range(args.images)]
+    mp_per_step = args.images * GRID_W * GRID_H / 1e6
+
+    eng = hb.Engine(local_rank)
+    threads = args.threads or cores // max(1, world)
+
+    # ---- device-resident arm: records in HBM, K1..K5 timed with CUDA events on the engine stream ----
+    job = hb.HeicJob(eng, files, want_alpha=False, threads=threads)
+    job.upload()
+    for _ in range(args.warmup):
+        job.run()
+    job.sync()
+    stage = job.stage_ms()   # per-kernel split of the last warm-up step
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    job.timer_start()
+    for _ in range(args.steps):
+        job.run()
+    dev_ms = job.timer_stop_ms()
+    barrier()
+    clocks = sampler.stop()
+    dev_ms = max_over_ranks(dev_ms)
+    launches = job.launch_count * args.steps
+    upload_bytes = job.upload_bytes
+    rgb_bytes = sum(d.width * d.height * d.bytes_per_pixel for d in job.descs)
+    stage_last = job.stage_ms()
+
+    # ---- parity guard: the timed configuration still produces the reference's pixels ----
+    check = None
+    try:
+        import hashlib
+        import heic_oracle
+        got = job.read_rgb(0)
+        want = heic_oracle.decode_rgb(files[0], hb.OUT_RGB)
+        check = bool(np.array_equal(got, want))
+    except Exception as e:  # the oracle is only the checker; never fail the measurement on it
+        check = "unchecked: %s" % e
+    job.close()
+
+    # ---- end-to-end arm: HEIC bytes (host) -> RGB bytes (pinned host), everything inside the timed region ----
+    L = eng._L
+    out_bufs = []
+    for d in [None] * args.images:
+        pass
+    e2e_steps = max(2, min(args.steps, 4))
+    pinned = None
+    barrier()
+    e2e_t = []
+    for it in range(1 + e2e_steps):
+        t0 = time.perf_counter()
+        j2 = hb.HeicJob(eng, files, want_alpha=False, threads=threads)
+        if pinned is None:
+            import ctypes as C
+            pinned = []
+            for d in j2.descs:
+                nbytes = d.width * d.height * d.bytes_per_pixel
+                ptr = L.hc_host_alloc(nbytes)
+                arr = np.ctypeslib.as_array((C.c_uint8 * nbytes).from_address(ptr)).reshape(d.height, d.width * d.bytes_per_pixel)
+                pinned.append((ptr, arr))
+        j2.upload()
+        j2.run()
+        for i in range(len(j2.descs)):
+            j2.read_rgb(i, pinned[i][1])
+        parse_s = j2.parse_seconds
+        j2.close()
+        dt = time.perf_counter() - t0
+        if it > 0:
+            e2e_t.append((dt, parse_s))
+    barrier()
+    e2e_dt = max_over_ranks(sum(t for t, _ in e2e_t) / len(e2e_t))
+    parse_s = sum(p for _, p in e2e_t) / len(e2e_t)
+    for ptr, _ in pinned:
+        L.hc_host_free(ptr)
+
+    # ---- roofline of the dominant kernel ----
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "measured (MEASURED_PEAKS.json)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    px = args.images * GRID_W * GRID_H
+    coded_px = args.images * 48 * TILE * TILE
+    # algorithmic bytes per kernel for 8-bit 4:2:0 (DESIGN.md "kernels")
+    alg = {"k1_transform": upload_bytes + 3.0 * coded_px, "k2_intra": 4.5 * coded_px, "k3_deblock": 2 * 3.0 * coded_px,
+           "k4_sao": 1.5 * coded_px + 1.5 * px, "k5_csc": 4.5 * px}
+    kernels = {k: stage_last[k] for k in alg}
+    dom = max(kernels, key=kernels.get)
+    achieved = alg[dom] / (kernels[dom] * 1e-3) / 1e9 if kernels[dom] > 0 else 0.0
+    roofline = {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "peak_source": peak_src,
+                "all_kernels": {k: {"ms": round(kernels[k], 4), "algorithmic_GBps": round(alg[k] / (kernels[k] * 1e-3) / 1e9, 1) if kernels[k] > 0 else None}
+                                for k in alg},
+                "note": "k2_intra is a dependency-latency-bound CTB wavefront, not a streaming kernel (DESIGN.md)"}
+
+    # ---- CPU baseline on the box's cores (rank 0, N = 1 only) ----
+    cpu = None
+    if rank == 0 and world == 1:
+        r = reference_arm(distinct, 2, 1, cores)
+        if r is not None:
+            cpu = {"value": r["value"], "unit": UNIT, "cores": cores, "kind": "reference", "sample": "2 x " + r["sample"]}
+        else:
+            cpu = {"value": None, "unit": UNIT, "cores": cores, "kind": "reference", "sample": "oracle/_ref missing on this box"}
+
+    if rank == 0:
+        ms_per_step = dev_ms / args.steps
+        line = {
+            "metric": METRIC, "value": world * mp_per_step / (ms_per_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u8", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "images_per_step_per_gpu": args.images, "coded_pictures_per_step_per_gpu": args.images * 48,
+                       "l2": "working set per step (planes + residuals + RGB, ~%d MB) exceeds the 126 MB L2; no explicit flush" % (
+                           args.images * (18 + 18 + 37 + 38)),
+                       "host_parse_threads": threads, "parity_vs_oracle": check},
+            "e2e": {"value": world * mp_per_step / e2e_dt, "unit": UNIT, "h2d_bytes_per_step": upload_bytes, "d2h_bytes_per_step": rgb_bytes,
+                    "ms_per_step": e2e_dt * 1e3, "host_parse_ms_per_step": parse_s * 1e3},
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "stage_ms_last_step": {k: round(v, 4) for k, v in stage_last.items()},
+            "record_bytes_per_px": upload_bytes / px,
+            "roofline": roofline,
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line))
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -20,6 +20,8 @@ int hc_batch_read_plane(hc_batch*, int, int, void*, size_t) { return NO_ENGINE()
 int hc_batch_read_rgb(hc_batch*, int, void*, size_t) { return NO_ENGINE(); }
 int hc_batch_read_residual(hc_batch*, int, int16_t*, size_t) { return NO_ENGINE(); }
 int hc_batch_stage_ms(hc_batch*, float*) { return NO_ENGINE(); }
+int hc_batch_timer_start(hc_batch*) { return NO_ENGINE(); }
+int hc_batch_timer_stop_ms(hc_batch*, float*) { return NO_ENGINE(); }
 int hc_batch_launch_count(const hc_batch*) { return 0; }
 size_t hc_batch_upload_bytes(const hc_batch*) { return 0; }
 void* hc_host_alloc(size_t) { NO_ENGINE(); return nullptr; }

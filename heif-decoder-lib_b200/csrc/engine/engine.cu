@@ -115,6 +115,7 @@ struct hc_batch {
   int max_planes = 1;
   bool uploaded = false;
   cudaEvent_t ev[8] = {};
+  cudaEvent_t timer[2] = {};
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> csc_events;
   int launches = 0;
   float last_d2h_ms = 0.f;
@@ -186,6 +187,8 @@ hc_batch* hc_batch_create(hc_engine* e) {
   }
   for (auto& ev : b->ev)
     if (!cuda_ok(cudaEventCreate(&ev), "cudaEventCreate")) { delete b; return nullptr; }
+  for (auto& ev : b->timer)
+    if (!cuda_ok(cudaEventCreate(&ev), "cudaEventCreate")) { delete b; return nullptr; }
   return b;
 }
 
@@ -195,6 +198,7 @@ void hc_batch_destroy(hc_batch* b) {
   cudaStreamSynchronize(b->stream);
   release_blocks(b);
   for (auto& ev : b->ev) if (ev) cudaEventDestroy(ev);
+  for (auto& ev : b->timer) if (ev) cudaEventDestroy(ev);
   for (auto& p : b->csc_events) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
   {
     std::lock_guard<std::mutex> lk(b->eng->mu);
@@ -404,6 +408,8 @@ int hc_batch_reconstruct(hc_batch* b, int stages) {
   if (!cuda_ok(cudaSetDevice(b->eng->device), "cudaSetDevice")) return HC_ERR_CUDA;
   cudaStream_t s = b->stream;
   b->launches = 0;
+  for (auto& p : b->csc_events) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
+  b->csc_events.clear();
   cudaMemsetAsync(b->d_progress.p, 0, std::max<size_t>((size_t)b->ntasks * sizeof(int), 4), s);
   cudaEventRecord(b->ev[2], s);
   hc::launch_k1(b->view, b->d_tb_index, b->tb_counts, s);
@@ -559,6 +565,16 @@ void* hc_host_alloc(size_t bytes) {
 }
 void hc_host_free(void* p) { if (p) cudaFreeHost(p); }
 
+int hc_batch_timer_start(hc_batch* b) {
+  if (!b) return HC_ERR_ARGUMENT;
+  return cuda_ok(cudaEventRecord(b->timer[0], b->stream), "cudaEventRecord") ? HC_OK : HC_ERR_CUDA;
+}
+int hc_batch_timer_stop_ms(hc_batch* b, float* ms) {
+  if (!b || !ms) return HC_ERR_ARGUMENT;
+  if (!cuda_ok(cudaEventRecord(b->timer[1], b->stream), "cudaEventRecord")) return HC_ERR_CUDA;
+  if (!cuda_ok(cudaEventSynchronize(b->timer[1]), "cudaEventSynchronize")) return HC_ERR_CUDA;
+  return cuda_ok(cudaEventElapsedTime(ms, b->timer[0], b->timer[1]), "cudaEventElapsedTime") ? HC_OK : HC_ERR_CUDA;
+}
 int hc_batch_launch_count(const hc_batch* b) { return b ? b->launches : 0; }
 size_t hc_batch_upload_bytes(const hc_batch* b) { return b ? b->arena_bytes : 0; }
 

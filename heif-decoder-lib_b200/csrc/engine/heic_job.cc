@@ -233,6 +233,8 @@ int hc_heic_job_read_plane(hc_heic_job* j, int image, int plane, void* dst, size
 }
 
 int hc_heic_job_stage_ms(hc_heic_job* j, float ms[8]) { return j ? hc_batch_stage_ms(j->batch, ms) : HC_ERR_ARGUMENT; }
+int hc_heic_job_timer_start(hc_heic_job* j) { return j ? hc_batch_timer_start(j->batch) : HC_ERR_ARGUMENT; }
+int hc_heic_job_timer_stop_ms(hc_heic_job* j, float* ms) { return j ? hc_batch_timer_stop_ms(j->batch, ms) : HC_ERR_ARGUMENT; }
 int hc_heic_job_launch_count(const hc_heic_job* j) { return j ? hc_batch_launch_count(j->batch) : 0; }
 size_t hc_heic_job_upload_bytes(const hc_heic_job* j) { return j ? hc_batch_upload_bytes(j->batch) : 0; }
 double hc_heic_job_parse_seconds(const hc_heic_job* j) { return j ? j->parse_seconds : 0.0; }

@@ -95,6 +95,8 @@ SYMBOLS = [
     ("hc_batch_read_rgb", _i, [_vp, _i, _vp, _sz]),
     ("hc_batch_read_residual", _i, [_vp, _i, _vp, _sz]),
     ("hc_batch_stage_ms", _i, [_vp, C.POINTER(C.c_float)]),
+    ("hc_batch_timer_start", _i, [_vp]),
+    ("hc_batch_timer_stop_ms", _i, [_vp, C.POINTER(C.c_float)]),
     ("hc_batch_launch_count", _i, [_vp]),
     ("hc_batch_upload_bytes", _sz, [_vp]),
     ("hc_heic_job_create", _vp, [_vp, _i, C.POINTER(C.c_char_p), C.POINTER(_sz), _i, _i]),
@@ -107,6 +109,8 @@ SYMBOLS = [
     ("hc_heic_job_read_rgb", _i, [_vp, _i, _vp, _sz]),
     ("hc_heic_job_read_plane", _i, [_vp, _i, _i, _vp, _sz]),
     ("hc_heic_job_stage_ms", _i, [_vp, C.POINTER(C.c_float)]),
+    ("hc_heic_job_timer_start", _i, [_vp]),
+    ("hc_heic_job_timer_stop_ms", _i, [_vp, C.POINTER(C.c_float)]),
     ("hc_heic_job_launch_count", _i, [_vp]),
     ("hc_heic_job_upload_bytes", _sz, [_vp]),
     ("hc_heic_job_parse_seconds", C.c_double, [_vp]),

@@ -311,6 +311,14 @@ class HeicJob:
         check(self._L, self._L.hc_heic_job_stage_ms(self._h, ms), "stage_ms")
         return dict(zip(("h2d", "k1_transform", "k2_intra", "k3_deblock", "k4_sao", "k5_csc", "d2h"), list(ms)[:7]))
 
+    def timer_start(self):
+        check(self._L, self._L.hc_heic_job_timer_start(self._h), "timer_start")
+
+    def timer_stop_ms(self):
+        ms = C.c_float()
+        check(self._L, self._L.hc_heic_job_timer_stop_ms(self._h, C.byref(ms)), "timer_stop_ms")
+        return ms.value
+
     @property
     def launch_count(self):
         return self._L.hc_heic_job_launch_count(self._h)

@@ -179,6 +179,11 @@ int hc_batch_read_residual(hc_batch* b, int pic, int16_t* dst, size_t count);
 /* device time of the last run's stages in ms (CUDA events on the engine stream):
  * [0] H2D upload, [1] K1, [2] K2, [3] K3, [4] K4, [5] K5 (sum over canvases), [6] D2H of the last read */
 int hc_batch_stage_ms(hc_batch* b, float ms[8]);
+/* CUDA-event stopwatch on the batch's stream: start records an event; stop records a second one,
+ * waits for it and returns the device time between the two in ms (used by bench.py to time K
+ * steps on the stream the kernels are launched on). */
+int hc_batch_timer_start(hc_batch* b);
+int hc_batch_timer_stop_ms(hc_batch* b, float* ms);
 /* number of kernel launches issued by the last reconstruct + convert calls */
 int hc_batch_launch_count(const hc_batch* b);
 /* bytes of the packed record arena uploaded by hc_batch_upload */
@@ -222,6 +227,8 @@ int hc_heic_job_read_rgb(hc_heic_job* j, int image, void* dst, size_t dst_stride
 int hc_heic_job_read_plane(hc_heic_job* j, int image, int plane, void* dst, size_t dst_stride_bytes);
 /* stage timings of the last run (see hc_batch_stage_ms), launches, uploaded bytes, host parse seconds */
 int hc_heic_job_stage_ms(hc_heic_job* j, float ms[8]);
+int hc_heic_job_timer_start(hc_heic_job* j);
+int hc_heic_job_timer_stop_ms(hc_heic_job* j, float* ms);
 int hc_heic_job_launch_count(const hc_heic_job* j);
 size_t hc_heic_job_upload_bytes(const hc_heic_job* j);
 double hc_heic_job_parse_seconds(const hc_heic_job* j);
