@@ -22,6 +22,9 @@ class HeifError(C.Structure):
 
 
 _lib = None
+# set by tests/test_plugin.py once libheif-cuda.so is registered in this process: from then on a
+# plain decode() must name the reference's own decoder explicitly to stay the reference
+FOREIGN_PLUGIN_LOADED = False
 
 
 def available():
@@ -89,8 +92,13 @@ def plane_bytes(img, channel, bytes_per_px):
 
 
 def decode(data, colorspace, chroma, item_id=None, threads=None, decoder_id=None):
-    """heif_decode_image on an in-memory HEIC. Returns dict of channel -> (bytes, w, h) plus bpp."""
+    """heif_decode_image on an in-memory HEIC. Returns dict of channel -> (bytes, w, h) plus bpp.
+    decoder_id: None = the reference's libde265 plugin; "" = let libheif choose by priority."""
     L = lib()
+    if decoder_id is None and FOREIGN_PLUGIN_LOADED:
+        decoder_id = "libde265"
+    if decoder_id == "":
+        decoder_id = None
     ctx = L.heif_context_alloc()
     buf = C.create_string_buffer(data, len(data))
     try:
