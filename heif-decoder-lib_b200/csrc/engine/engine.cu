@@ -111,6 +111,7 @@ struct hc_batch {
   int tb_counts[4] = {0, 0, 0, 0};
   const hc::RowTask* d_tasks = nullptr;
   int ntasks = 0;
+  int k2_smem = 0;   // dynamic shared memory per K2 CTA
   long long max_dbk_units = 0, max_sao_quads = 0;
   int max_planes = 1;
   bool uploaded = false;
@@ -363,7 +364,8 @@ int hc_batch_upload(hc_batch* b) {
   {
     hc::RowTask* tasks = (hc::RowTask*)(H + o_tasks);
     std::vector<int> first_of_row((size_t)np * 3, -1), prev((size_t)np * 3, -1);
-    int t = 0;
+    int t = 0, cta_smem = 0;
+    b->k2_smem = 0;
     for (int row = 0; row < max_rows; row++)
       for (int i = 0; i < np; i++) {
         const hc_pic& p = b->hpics[i];
@@ -374,6 +376,14 @@ int hc_batch_upload(hc_batch* b) {
           k.pic = (uint32_t)i; k.row = (uint16_t)row; k.comp = (uint8_t)c; k.pad = 0;
           k.dep = prev[(size_t)i * 3 + c];
           prev[(size_t)i * 3 + c] = t;
+          // this warp's slice of its CTA's shared memory
+          const int ps = (p.bit_depth_y == 8 && p.bit_depth_c == 8) ? 1 : 2;
+          const int cw = (1 << p.log2_ctb) >> ((c && (p.chroma_format == 1 || p.chroma_format == 2)) ? 1 : 0);
+          const int ch = (1 << p.log2_ctb) >> ((c && p.chroma_format == 1) ? 1 : 0);
+          if (t % hc::K2_WARPS == 0) cta_smem = 0;
+          k.smem_off = (uint32_t)cta_smem;
+          cta_smem += hc::k2_task_smem_bytes(cw, ch, ps);
+          b->k2_smem = std::max(b->k2_smem, cta_smem);
           t++;
         }
       }
@@ -415,7 +425,7 @@ int hc_batch_reconstruct(hc_batch* b, int stages) {
   hc::launch_k1(b->view, b->d_tb_index, b->tb_counts, s);
   for (int l = 0; l < 4; l++) b->launches += b->tb_counts[l] > 0;
   cudaEventRecord(b->ev[3], s);
-  hc::launch_k2(b->view, b->d_tasks, b->ntasks, (int*)b->d_progress.p, s);
+  hc::launch_k2(b->view, b->d_tasks, b->ntasks, b->k2_smem, (int*)b->d_progress.p, s);
   b->launches += 1;
   cudaEventRecord(b->ev[4], s);
   if (stages & HC_STAGE_DEBLOCK) {

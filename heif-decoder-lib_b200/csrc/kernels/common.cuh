@@ -42,7 +42,9 @@ struct RowTask {
   uint8_t comp;
   uint8_t pad;
   int32_t dep;   // task index of the row above (same picture / component), -1 for row 0
+  uint32_t smem_off;  // byte offset of this warp's slice of the CTA's dynamic shared memory
 };
+constexpr int K2_WARPS = 6;   // row tasks per CTA (two Y/Cb/Cr triples of a 4:2:0 picture)
 
 #if defined(__CUDACC__)
 // L2-coherent loads: neighbour samples and progress counters are produced by other SMs while

@@ -223,7 +223,7 @@ hcp_error cuda_decode_image(void* raw, void** out_img) {
 
 extern "C" {
 
-__attribute__((visibility("default"))) const hcp_decoder_plugin heifcuda_decoder_plugin = {
+const hcp_decoder_plugin heifcuda_decoder_plugin = {
     3,
     cuda_plugin_name,
     cuda_init_plugin,
@@ -237,6 +237,6 @@ __attribute__((visibility("default"))) const hcp_decoder_plugin heifcuda_decoder
     "cuda",
 };
 
-__attribute__((visibility("default"))) hcp_plugin_info plugin_info = {1, HCP_PLUGIN_TYPE_DECODER, &heifcuda_decoder_plugin, nullptr};
+hcp_plugin_info plugin_info = {1, HCP_PLUGIN_TYPE_DECODER, &heifcuda_decoder_plugin, nullptr};
 
 }  // extern "C"
