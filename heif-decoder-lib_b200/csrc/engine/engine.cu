@@ -292,7 +292,7 @@ int hc_batch_upload(hc_batch* b) {
     n_tasks += (size_t)ncomp * p.ctbs_h;
     b->max_planes = std::max(b->max_planes, ncomp);
     b->max_dbk_units = std::max(b->max_dbk_units, (long long)(p.width >> 3) * (p.height >> 2));
-    b->max_sao_quads = std::max(b->max_sao_quads, (long long)((p.width + 3) >> 2) * p.height);
+    b->max_sao_quads = std::max(b->max_sao_quads, (long long)((p.width + 7) >> 3) * p.height);
     // reconstruction planes
     const int ps = (p.bit_depth_y == 8 && p.bit_depth_c == 8) ? 1 : 2;
     const int SubW = (p.chroma_format == 1 || p.chroma_format == 2) ? 2 : 1, SubH = p.chroma_format == 1 ? 2 : 1;

@@ -105,9 +105,9 @@ struct Geo {
 // parallel) and broadcast by shuffle in the block loop:
 //   w0 : left_off | top_off << 16     byte offsets of ref sample (-1, 0) resp. corner (-1,-1) of the block
 //   w1 : store_off | mode << 16 | (log2-2) << 22 | BP_* bits
-//   w2 : lo & 0xff | (hi & 0xff) << 8 | inv_angle << 16     clamp range of the contiguous available run
+//   w2 : lo & 0xff | (hi & 0xff) << 8 | staged residual byte offset << 16     (lo..hi: the available run)
 //   w3 : avail_left | avail_top << 16                        (general substitution only)
-//   w4 : residual location: staged -> byte offset in shared memory, else int16 index in the residual buffer
+//   w4 : int16 index in the residual buffer                  (16x16 / 32x32 blocks only)
 constexpr uint32_t BP_HAS_RES = 1u << 24, BP_PCM = 1u << 25, BP_FILT = 1u << 26, BP_EDGE = 1u << 27, BP_NOEDGEFLT = 1u << 28,
                    BP_NONE_AVAIL = 1u << 29, BP_GENERAL = 1u << 30, BP_TL = 1u << 31;
 
@@ -118,19 +118,28 @@ HC_D int ld_px(const uint8_t* sm, int off) { return (int)*reinterpret_cast<const
 HC_D int slot_first(int s, int nu) { return s < nu ? -(4 * (nu - 1 - s) + 4) : (s == nu ? 0 : 4 * (s - nu - 1) + 1); }
 HC_D int slot_last(int s, int nu) { return s < nu ? -(4 * (nu - 1 - s) + 1) : (s == nu ? 0 : 4 * (s - nu - 1) + 4); }
 
+// One prediction block. All 32 lanes run every statement (no divergent lane guards): lanes beyond
+// the block's sample count recompute a sample another lane owns and store the identical value.
 template <typename Pixel, int LOG2>
 __device__ __forceinline__ void process_block(const Geo& g, uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, const int16_t* __restrict__ res,
                                               int lane) {
   constexpr int PS = (int)sizeof(Pixel);
   constexpr int nT = 1 << LOG2, nref = 4 * nT + 1, nu = nT >> 1;
+  constexpr int NS = nT * nT;                       // samples
+  constexpr int ITER = NS >= 32 ? NS / 32 : 1;      // sample passes of the warp
+  constexpr int RPI = 32 >> LOG2;                   // block rows covered per pass (8x8: 4, 16x16: 2, 32x32: 1)
+  constexpr int GIT = (nref + 31) / 32;             // gather passes
   const int store_off = w1 & 0xffff, mode = (w1 >> 16) & 63;
   const int pitch = g.pitch;
   const int maxv = (1 << g.bit_depth) - 1;
+  // this lane's sample of pass 0: s0 = lane (4x4: lane & 15), x = s0 % nT, y = s0 / nT
+  const int s0 = NS >= 32 ? lane : (lane & (NS - 1));
+  const int x = s0 & (nT - 1), yb = s0 >> LOG2;
+  uint8_t* out = g.sm + store_off + yb * pitch + x * PS;
 
   if (w1 & BP_PCM) {
-#pragma unroll
-    for (int s = lane; s < nT * nT; s += 32)
-      *reinterpret_cast<Pixel*>(g.sm + store_off + (s >> LOG2) * pitch + (s & (nT - 1)) * PS) = (Pixel)(uint16_t)res[s];
+#pragma unroll 4
+    for (int j = 0; j < ITER; j++) *reinterpret_cast<Pixel*>(out + j * RPI * pitch) = (Pixel)(uint16_t)res[s0 + 32 * j];
     __syncwarp();
     return;
   }
@@ -141,15 +150,16 @@ __device__ __forceinline__ void process_block(const Geo& g, uint32_t w0, uint32_
     // the available units form one run in scan order: unavailable samples take the nearest end of it
     const int lo = (int)(int8_t)(w2 & 0xff), hi = (int)(int8_t)((w2 >> 8) & 0xff);
 #pragma unroll
-    for (int idx = lane; idx < nref; idx += 32) {
+    for (int j = 0; j < GIT; j++) {
+      const int idx = min(lane + 32 * j, nref - 1);
       const int i = idx - 2 * nT;
       const int src = min(max(i, lo), hi);
-      const int off = src < 0 ? left_off + (-src - 1) * pitch : top_off + src * PS;
+      const int off = src < 0 ? left_off - (src + 1) * pitch : top_off + src * PS;
       g.refA[REF_OFF + i] = (int16_t)ld_px<Pixel>(g.sm, off);
     }
   } else if (w1 & BP_NONE_AVAIL) {
 #pragma unroll
-    for (int idx = lane; idx < nref; idx += 32) g.refA[REF_OFF + idx - 2 * nT] = (int16_t)(1 << (g.bit_depth - 1));
+    for (int j = 0; j < GIT; j++) g.refA[REF_OFF + min(lane + 32 * j, nref - 1) - 2 * nT] = (int16_t)(1 << (g.bit_depth - 1));
   } else {
     // general case (slice / tile corners): nearest available unit before, else the first available
     const unsigned availL = w3 & 0xffff, availT = w3 >> 16;
@@ -166,7 +176,7 @@ __device__ __forceinline__ void process_block(const Geo& g, uint32_t w0, uint32_
         if (below) src = slot_last(63 - __clzll((long long)below), nu);
         else src = slot_first(__ffsll((long long)A) - 1, nu);
       }
-      const int off = src < 0 ? left_off + (-src - 1) * pitch : top_off + src * PS;
+      const int off = src < 0 ? left_off - (src + 1) * pitch : top_off + src * PS;
       g.refA[REF_OFF + i] = (int16_t)ld_px<Pixel>(g.sm, off);
     }
   }
@@ -182,7 +192,8 @@ __device__ __forceinline__ void process_block(const Geo& g, uint32_t w0, uint32_
     }
     int16_t* q = g.refB + REF_OFF;
 #pragma unroll
-    for (int idx = lane; idx < nref; idx += 32) {
+    for (int j = 0; j < GIT; j++) {
+      const int idx = min(lane + 32 * j, nref - 1);
       const int i = idx - 2 * nT;
       int v;
       if (i == -2 * nT || i == 2 * nT) v = p[i];
@@ -202,55 +213,80 @@ __device__ __forceinline__ void process_block(const Geo& g, uint32_t w0, uint32_
   // ---- 3. prediction + residual + store into the tile --------------------------------------------
   const bool has_res = w1 & BP_HAS_RES;
   const bool edge_ok = w1 & BP_EDGE;
-  uint8_t* out = g.sm + store_off;
   if (mode == 0) {
     const int tr = p[1 + nT], bl = p[-1 - nT];
-#pragma unroll
-    for (int s = lane; s < nT * nT; s += 32) {
-      const int x = s & (nT - 1), y = s >> LOG2;
-      int v = ((nT - 1 - x) * p[-1 - y] + (x + 1) * tr + (nT - 1 - y) * p[1 + x] + (y + 1) * bl + nT) >> (LOG2 + 1);
-      if (has_res) v = clip3i(0, maxv, v + res[s]);
-      *reinterpret_cast<Pixel*>(out + y * pitch + x * PS) = (Pixel)v;
+    const int top = p[1 + x], hx = (x + 1) * tr + nT;
+#pragma unroll 4
+    for (int j = 0; j < ITER; j++) {
+      const int y = yb + j * RPI;
+      int v = ((nT - 1 - x) * p[-1 - y] + hx + (nT - 1 - y) * top + (y + 1) * bl) >> (LOG2 + 1);
+      if (has_res) v = clip3i(0, maxv, v + res[s0 + 32 * j]);
+      *reinterpret_cast<Pixel*>(out + j * RPI * pitch) = (Pixel)v;
     }
   } else if (mode == 1) {
-    int sum = 0;
-    if (lane < nT) sum = p[lane + 1] + p[-lane - 1];
+    const int ln = lane & (nT - 1);
+    int sum = p[ln + 1] + p[-ln - 1];
 #pragma unroll
     for (int o = nT >> 1; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-    const int dc = (__shfl_sync(0xffffffffu, sum, 0) + nT) >> (LOG2 + 1);
-#pragma unroll
-    for (int s = lane; s < nT * nT; s += 32) {
-      const int x = s & (nT - 1), y = s >> LOG2;
+    const int dc = (sum + nT) >> (LOG2 + 1);
+    const int top = (p[x + 1] + 3 * dc + 2) >> 2;
+#pragma unroll 4
+    for (int j = 0; j < ITER; j++) {
+      const int y = yb + j * RPI;
       int v = dc;
       if (edge_ok) {
-        if (x == 0 && y == 0) v = (p[-1] + 2 * dc + p[1] + 2) >> 2;
-        else if (y == 0) v = (p[x + 1] + 3 * dc + 2) >> 2;
+        if (y == 0) v = x == 0 ? (p[-1] + 2 * dc + p[1] + 2) >> 2 : top;
         else if (x == 0) v = (p[-y - 1] + 3 * dc + 2) >> 2;
       }
-      if (has_res) v = clip3i(0, maxv, v + res[s]);
-      *reinterpret_cast<Pixel*>(out + y * pitch + x * PS) = (Pixel)v;
+      if (has_res) v = clip3i(0, maxv, v + res[s0 + 32 * j]);
+      *reinterpret_cast<Pixel*>(out + j * RPI * pitch) = (Pixel)v;
     }
   } else {
-    const int angle = c_intra_angle[mode];
-    const int inv = (int)(int16_t)(w2 >> 16);
-    const bool vertical = mode >= 18;
     // vertical modes walk the top row (ref[k] = p[k]); horizontal modes the left column (ref[k] = p[-k]);
-    // negative k projects onto the other side through the inverse angle
+    // u runs along the reference, w away from it
+    const int angle = c_intra_angle[mode];
+    const bool vertical = mode >= 18;
     const int sgn = vertical ? 1 : -1;
-    const bool edge_flt = edge_ok && !(w1 & BP_NOEDGEFLT) && (mode == 26 || mode == 10);
-#pragma unroll
-    for (int s = lane; s < nT * nT; s += 32) {
-      const int x = s & (nT - 1), y = s >> LOG2;
-      const int u = vertical ? x : y, w = vertical ? y : x;   // u along the reference, w away from it
-      const int t = (w + 1) * angle;
-      const int iIdx = t >> 5, iFact = t & 31;
-      const int k0 = u + iIdx + 1, k1 = k0 + 1;
-      const int a = k0 >= 0 ? p[sgn * k0] : p[-sgn * ((k0 * inv + 128) >> 8)];
-      const int b = k1 >= 0 ? p[sgn * k1] : p[-sgn * ((k1 * inv + 128) >> 8)];
-      int v = iFact ? ((32 - iFact) * a + iFact * b + 16) >> 5 : a;
-      if (edge_flt && u == 0) v = clip3i(0, maxv, p[sgn] + ((p[-sgn * (1 + w)] - p[0]) >> 1));
-      if (has_res) v = clip3i(0, maxv, v + res[s]);
-      *reinterpret_cast<Pixel*>(out + y * pitch + x * PS) = (Pixel)v;
+    if (angle == 0) {
+      // modes 10 / 26: copy the reference, optional boundary filter on the first row / column
+      const bool edge_flt = edge_ok && !(w1 & BP_NOEDGEFLT);
+      const int p0 = p[0], p1 = p[sgn];
+#pragma unroll 4
+      for (int j = 0; j < ITER; j++) {
+        const int y = yb + j * RPI;
+        const int u = vertical ? x : y, w = vertical ? y : x;
+        int v = p[sgn * (u + 1)];
+        if (edge_flt && u == 0) v = clip3i(0, maxv, p1 + ((p[-sgn * (1 + w)] - p0) >> 1));
+        if (has_res) v = clip3i(0, maxv, v + res[s0 + 32 * j]);
+        *reinterpret_cast<Pixel*>(out + j * RPI * pitch) = (Pixel)v;
+      }
+    } else if (angle > 0) {
+      // the reference index never goes negative; (32a + 16) >> 5 == a covers iFact == 0
+#pragma unroll 4
+      for (int j = 0; j < ITER; j++) {
+        const int y = yb + j * RPI;
+        const int u = vertical ? x : y, w = vertical ? y : x;
+        const int t = (w + 1) * angle;
+        const int k0 = u + (t >> 5) + 1, f = t & 31;
+        int v = ((32 - f) * p[sgn * k0] + f * p[sgn * (k0 + 1)] + 16) >> 5;
+        if (has_res) v = clip3i(0, maxv, v + res[s0 + 32 * j]);
+        *reinterpret_cast<Pixel*>(out + j * RPI * pitch) = (Pixel)v;
+      }
+    } else {
+      // negative angles: indices below zero project onto the other reference through the inverse angle
+      const int inv = c_inv_angle[mode - 11];
+#pragma unroll 4
+      for (int j = 0; j < ITER; j++) {
+        const int y = yb + j * RPI;
+        const int u = vertical ? x : y, w = vertical ? y : x;
+        const int t = (w + 1) * angle;
+        const int k0 = u + (t >> 5) + 1, k1 = k0 + 1, f = t & 31;
+        const int i0 = k0 >= 0 ? sgn * k0 : -sgn * ((k0 * inv + 128) >> 8);
+        const int i1 = k1 >= 0 ? sgn * k1 : -sgn * ((k1 * inv + 128) >> 8);
+        int v = ((32 - f) * p[i0] + f * p[i1] + 16) >> 5;
+        if (has_res) v = clip3i(0, maxv, v + res[s0 + 32 * j]);
+        *reinterpret_cast<Pixel*>(out + j * RPI * pitch) = (Pixel)v;
+      }
     }
   }
   // make the block visible to the lanes that gather the next block's references
@@ -419,9 +455,8 @@ __device__ void run_row(const BatchView& bv, const hc_pic& pic, const RowTask ta
       hi = slot_last(ls, nu);
     }
     w1 = (uint32_t)store_off | ((uint32_t)mode << 16) | ((uint32_t)(log2 - 2) << 22) | bits;
-    const int inv = (mode >= 11 && mode <= 25) ? c_inv_angle[mode - 11] : 0;
-    w2 = (uint32_t)(lo & 0xff) | ((uint32_t)(hi & 0xff) << 8) | ((uint32_t)(uint16_t)inv << 16);
-    w4 = log2 <= 3 ? (uint32_t)(stage_off + off_elems * 2) : r.w;
+    w2 = (uint32_t)(lo & 0xff) | ((uint32_t)(hi & 0xff) << 8) | ((uint32_t)(stage_off + off_elems * 2) << 16);
+    w4 = r.w;
   };
 
   // ---- software pipeline: records two batches ahead, staged residuals one batch ahead ----
@@ -471,16 +506,21 @@ __device__ void run_row(const BatchView& bv, const hc_pic& pic, const RowTask ta
       mbar_wait(buf ? bar1 : bar0, buf ? phase1 : phase0);
       if (buf) phase1 ^= 1; else phase0 ^= 1;
     }
+    // the parameter words of block k+1 are broadcast while block k is being predicted
+    uint32_t n0 = __shfl_sync(0xffffffffu, w0, 0), n1 = __shfl_sync(0xffffffffu, w1, 0), n2 = __shfl_sync(0xffffffffu, w2, 0);
     for (int k = 0; k < cur.n; k++) {
-      const uint32_t b0 = __shfl_sync(0xffffffffu, w0, k), b1 = __shfl_sync(0xffffffffu, w1, k), b2 = __shfl_sync(0xffffffffu, w2, k);
-      const uint32_t b4 = __shfl_sync(0xffffffffu, w4, k);
+      const uint32_t b0 = n0, b1 = n1, b2 = n2;
+      const int kn = k + 1 < cur.n ? k + 1 : k;
+      n0 = __shfl_sync(0xffffffffu, w0, kn); n1 = __shfl_sync(0xffffffffu, w1, kn); n2 = __shfl_sync(0xffffffffu, w2, kn);
       uint32_t b3 = 0;
       if (b1 & BP_GENERAL) b3 = __shfl_sync(0xffffffffu, w3, k);   // warp-uniform branch
-      switch ((b1 >> 22) & 3) {
-        case 0: process_block<Pixel, 2>(g, b0, b1, b2, b3, reinterpret_cast<const int16_t*>(smem + b4), lane); break;
-        case 1: process_block<Pixel, 3>(g, b0, b1, b2, b3, reinterpret_cast<const int16_t*>(smem + b4), lane); break;
-        case 2: process_block<Pixel, 4>(g, b0, b1, b2, b3, resid + b4, lane); break;
-        default: process_block<Pixel, 5>(g, b0, b1, b2, b3, resid + b4, lane); break;
+      const int lg = (b1 >> 22) & 3;
+      if (lg == 0) process_block<Pixel, 2>(g, b0, b1, b2, b3, reinterpret_cast<const int16_t*>(smem + (b2 >> 16)), lane);
+      else if (lg == 1) process_block<Pixel, 3>(g, b0, b1, b2, b3, reinterpret_cast<const int16_t*>(smem + (b2 >> 16)), lane);
+      else {
+        const uint32_t b4 = __shfl_sync(0xffffffffu, w4, k);
+        if (lg == 2) process_block<Pixel, 4>(g, b0, b1, b2, b3, resid + b4, lane);
+        else process_block<Pixel, 5>(g, b0, b1, b2, b3, resid + b4, lane);
       }
     }
 

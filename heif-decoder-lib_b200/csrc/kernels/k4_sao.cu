@@ -11,8 +11,11 @@
 // deblocked reconstruction planes are read-only input and the result is written straight to its
 // final position, so the copy, the crop and the paste cost no extra memory pass.
 //
-// Mapping: one thread per 4 horizontally adjacent samples; a warp covers 128 consecutive samples
-// of one row. Algorithmic bytes: read s + write s per sample (neighbour rows hit L1/L2).
+// Mapping: one thread per 8 horizontally adjacent samples (8-aligned, so a unit never straddles a
+// CTB: CTBs are >= 8 samples wide in every component); the unit's row and, for the edge classes,
+// the rows above / below are fetched with one 8- or 16-byte load each, the per-CTB parameters once
+// per thread. A warp covers 256 consecutive samples of a row.
+// Algorithmic bytes: read s + write s per sample (neighbour rows hit L1/L2).
 #include "launch.h"
 
 namespace hc {
@@ -20,13 +23,39 @@ namespace hc {
 HC_D int sign3(int v) { return (v > 0) - (v < 0); }
 
 template <typename Pixel>
+HC_D void load8(const Pixel* p, int v[8]);
+template <>
+HC_D void load8<uint8_t>(const uint8_t* p, int v[8]) {
+  const uint2 w = *reinterpret_cast<const uint2*>(p);
+#pragma unroll
+  for (int k = 0; k < 4; k++) { v[k] = (w.x >> (8 * k)) & 0xff; v[4 + k] = (w.y >> (8 * k)) & 0xff; }
+}
+template <>
+HC_D void load8<uint16_t>(const uint16_t* p, int v[8]) {
+  const uint4 w = *reinterpret_cast<const uint4*>(p);
+  v[0] = w.x & 0xffff; v[1] = w.x >> 16; v[2] = w.y & 0xffff; v[3] = w.y >> 16;
+  v[4] = w.z & 0xffff; v[5] = w.z >> 16; v[6] = w.w & 0xffff; v[7] = w.w >> 16;
+}
+HC_D void store8(uint8_t* p, const int v[8]) {
+  uint2 w;
+  w.x = v[0] | (v[1] << 8) | (v[2] << 16) | (v[3] << 24);
+  w.y = v[4] | (v[5] << 8) | (v[6] << 16) | (v[7] << 24);
+  *reinterpret_cast<uint2*>(p) = w;
+}
+HC_D void store8(uint16_t* p, const int v[8]) {
+  uint4 w;
+  w.x = v[0] | (v[1] << 16); w.y = v[2] | (v[3] << 16); w.z = v[4] | (v[5] << 16); w.w = v[6] | (v[7] << 16);
+  *reinterpret_cast<uint4*>(p) = w;
+}
+
+template <typename Pixel>
 __device__ void sao_picture(const BatchView& bv, const hc_pic& pic, int c, long long tid) {
   const int SubW = (c && (pic.chroma_format == 1 || pic.chroma_format == 2)) ? 2 : 1;
   const int SubH = (c && pic.chroma_format == 1) ? 2 : 1;
-  const int width = pic.width / SubW, height = pic.height / SubH;  // coded plane size
-  const int nq = (width + 3) >> 2;
-  if (tid >= (long long)nq * height) return;
-  const int y = (int)(tid / nq), xq = (int)(tid % nq) << 2;
+  const int width = pic.width / SubW, height = pic.height / SubH;  // coded plane size (multiples of 4)
+  const int nu = (width + 7) >> 3;
+  if (tid >= (long long)nu * height) return;
+  const int y = (int)(tid / nu), x0 = (int)(tid - (long long)y * nu) << 3;
 
   // crop window and destination clip, in samples of this plane (context.cc:2467-2497)
   const int cx0 = pic.crop_x / SubW, cy0 = pic.crop_y / SubH;
@@ -36,6 +65,8 @@ __device__ void sao_picture(const BatchView& bv, const hc_pic& pic, int c, long 
   const int copy_w = min(cw, dw - dx0), copy_h = min(ch, dh - dy0);
   const int oy = y - cy0;
   if (oy < 0 || oy >= copy_h) return;
+  const int ox0 = x0 - cx0;                         // destination column of sample 0 of the unit
+  if (ox0 + 8 <= 0 || ox0 >= copy_w) return;
 
   const Pixel* __restrict__ src = reinterpret_cast<const Pixel*>(bv.planes + pic.rec_off[c]);
   const int sstride = (int)pic.rec_stride[c];
@@ -43,82 +74,128 @@ __device__ void sao_picture(const BatchView& bv, const hc_pic& pic, int c, long 
   const int dstride = (int)pic.dst_stride[c];
   const int bit_depth = c == 0 ? pic.bit_depth_y : pic.bit_depth_c;
   const int maxv = (1 << bit_depth) - 1;
-  const int ctb_w = (1 << pic.log2_ctb) / SubW, ctb_h = (1 << pic.log2_ctb) / SubH;
   const int log2w = pic.log2_ctb - (SubW == 2), log2h = pic.log2_ctb - (SubH == 2);
-  const hc_ctu* __restrict__ ctus = bv.ctus + pic.ctu_base;
-  const uint8_t* __restrict__ edge = bv.edge_map + pic.edge_base;
-  const int w4 = pic.width >> 2;
-  const bool rescale = pic.dst_flags & HC_DST_RESCALE_LIMITED;
-  (void)ctb_w; (void)ctb_h;
+  const int ctbx = x0 >> log2w, ctby = y >> log2h;
+  const hc_ctu& ctu = bv.ctus[pic.ctu_base + ctbx + ctby * pic.ctbs_w];
+  const int nvalid = min(8, width - x0);            // 4 or 8
 
-  const Pixel* row = src + (size_t)y * sstride;
+  const Pixel* row = src + (size_t)y * sstride + x0;
+  int v[8];
+  if (nvalid == 8) load8<Pixel>(row, v);
+  else {
 #pragma unroll
-  for (int k = 0; k < 4; k++) {
-    const int x = xq + k;
-    const int ox = x - cx0;
-    if (x >= width || ox < 0 || ox >= copy_w) continue;
-    const int v0 = row[x];
-    int v = v0;
-    const int ctbx = x >> log2w, ctby = y >> log2h;
-    const hc_ctu& ctu = ctus[ctbx + ctby * pic.ctbs_w];
-    const int type = (bv.flags & HC_VIEW_NO_SAO) ? 0 : ctu.sao_type[c];
-    if (type) {
-      bool skip = false;
-      if (ctu.flags & HC_CTU_HAS_NOFILTER) {
-        const int e = edge[((x * SubW) >> 2) + (size_t)((y * SubH) >> 2) * w4];
-        skip = ((pic.flags & HC_PIC_PCM_LF_DISABLED) && (e & HC_EDGE_PCM)) || (e & HC_EDGE_BYPASS);
+    for (int k = 0; k < 8; k++) v[k] = k < nvalid ? (int)row[k] : 0;
+  }
+
+  const int type = (bv.flags & HC_VIEW_NO_SAO) ? 0 : ctu.sao_type[c];
+  if (type) {
+    // samples of pcm (with pcm_loop_filter_disabled) / transquant-bypass CUs are left alone (sao.cc:288-300)
+    unsigned skip = 0;
+    if (ctu.flags & HC_CTU_HAS_NOFILTER) {
+      const uint8_t* __restrict__ edge = bv.edge_map + pic.edge_base;
+      const int w4 = pic.width >> 2;
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        if (k >= nvalid) continue;
+        const int e = edge[(((x0 + k) * SubW) >> 2) + (size_t)((y * SubH) >> 2) * w4];
+        if (((pic.flags & HC_PIC_PCM_LF_DISABLED) && (e & HC_EDGE_PCM)) || (e & HC_EDGE_BYPASS)) skip |= 1u << k;
       }
-      if (!skip) {
-        if (type == 1) {
-          // bandShift >= 8 leaves the sample untouched in the reference (sao.cc:461)
-          if (bit_depth - 5 < 8) {
-            const int band = v0 >> (bit_depth - 5);
-            const int k4 = (band - ctu.sao_band_or_class[c]) & 31;
-            if (k4 < 4) v = clip3i(0, maxv, v0 + ctu.sao_offset[c][k4]);
-          }
-        } else {
-          const int cls = ctu.sao_band_or_class[c];
-          const int hx = cls == 1 ? 0 : (cls == 3 ? 1 : -1);   // first neighbour
-          const int vy = cls == 0 ? 0 : -1;
-          // neighbours: (x+hx, y+vy) and (x-hx, y-vy)
-          bool ok = true;
+    }
+    const int8_t* offs = ctu.sao_offset[c];
+    const int o0 = offs[0], o1 = offs[1], o2 = offs[2], o3 = offs[3];
+    if (type == 1) {
+      // bandShift >= 8 leaves the sample untouched in the reference (sao.cc:461)
+      if (bit_depth - 5 < 8) {
+        const int pos = ctu.sao_band_or_class[c];
 #pragma unroll
-          for (int n = 0; n < 2; n++) {
-            const int xs = n == 0 ? x + hx : x - hx, ys = n == 0 ? y + vy : y - vy;
-            if (xs < 0 || ys < 0 || xs >= width || ys >= height) { ok = false; continue; }
-            const int dxc = (xs >> log2w) - ctbx, dyc = (ys >> log2h) - ctby;
-            if (dxc | dyc) {
-              int bit;
-              if (dyc == 0) bit = dxc < 0 ? HC_NB_L : HC_NB_R;
-              else if (dxc == 0) bit = dyc < 0 ? HC_NB_T : HC_NB_B;
-              else if (dyc < 0) bit = dxc < 0 ? HC_NB_TL : HC_NB_TR;
-              else bit = dxc < 0 ? HC_NB_BL : HC_NB_BR;
-              if (!((c ? ctu.sao_nb_c : ctu.sao_nb) & bit)) ok = false;
-            } else if (c && (ctu.flags & HC_CTU_SAO_C_SELF)) {
-              // reference quirk (sao.cc:283): border samples of this CTB also lose their in-CTB neighbours
-              const int lx = x & ((1 << log2w) - 1), ly = y & ((1 << log2h) - 1);
-              const int cwid = min(1 << log2w, width - (ctbx << log2w)), chei = min(1 << log2h, height - (ctby << log2h));
-              if (lx == 0 || ly == 0 || lx == cwid - 1 || ly == chei - 1) ok = false;
-            }
-          }
-          if (ok) {
-            const int a = src[(size_t)(y + vy) * sstride + x + hx];
-            const int b = src[(size_t)(y - vy) * sstride + x - hx];
-            const int e = sign3(v0 - a) + sign3(v0 - b);   // -2..2
-            // edgeIdx -2,-1,1,2 -> offsets 0,1,2,3 (sao.cc:312-317)
-            if (e) v = clip3i(0, maxv, v0 + ctu.sao_offset[c][e < 0 ? e + 2 : e + 1]);
-          }
+        for (int k = 0; k < 8; k++) {
+          const int k4 = ((v[k] >> (bit_depth - 5)) - pos) & 31;
+          if (k4 < 4 && !((skip >> k) & 1)) v[k] = clip3i(0, maxv, v[k] + (k4 == 0 ? o0 : k4 == 1 ? o1 : k4 == 2 ? o2 : o3));
         }
       }
+    } else {
+      const int cls = ctu.sao_band_or_class[c];
+      const int hx = cls == 1 ? 0 : (cls == 3 ? 1 : -1);   // first neighbour (x+hx, y+vy), second (x-hx, y-vy)
+      const int vy = cls == 0 ? 0 : -1;
+      // rows of the two neighbours, columns x0-1 .. x0+8 (index + 1)
+      int ra[10], rb[10];
+      const bool have_up = y > 0, have_dn = y + 1 < height;
+      const Pixel* rowa = vy ? row - sstride : row;
+      const Pixel* rowb = vy ? row + sstride : row;
+      const bool oka = vy ? have_up : true, okb = vy ? have_dn : true;
+#pragma unroll
+      for (int k = 0; k < 10; k++) { ra[k] = 0; rb[k] = 0; }
+      if (vy == 0) {
+#pragma unroll
+        for (int k = 0; k < 8; k++) { ra[k + 1] = v[k]; rb[k + 1] = v[k]; }
+      } else {
+        if (oka) {
+          if (nvalid == 8) load8<Pixel>(rowa, ra + 1);
+          else for (int k = 0; k < nvalid; k++) ra[k + 1] = rowa[k];
+        }
+        if (okb) {
+          if (nvalid == 8) load8<Pixel>(rowb, rb + 1);
+          else for (int k = 0; k < nvalid; k++) rb[k + 1] = rowb[k];
+        }
+      }
+      if (hx) {
+        if (x0 > 0) { if (oka) ra[0] = rowa[-1]; if (okb) rb[0] = rowb[-1]; }
+        if (x0 + 8 < width) { if (oka) ra[9] = rowa[8]; if (okb) rb[9] = rowb[8]; }   // nvalid == 8 here
+      }
+      const unsigned nb = c ? ctu.sao_nb_c : ctu.sao_nb;
+      const bool self_quirk = c && (ctu.flags & HC_CTU_SAO_C_SELF);
+      const int lwid = min(1 << log2w, width - (ctbx << log2w)), lhei = min(1 << log2h, height - (ctby << log2h));
+      const int ly = y & ((1 << log2h) - 1);
+      const int orig[8] = {v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]};
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        if (k >= nvalid || ((skip >> k) & 1)) continue;
+        const int x = x0 + k;
+        bool ok = true;
+#pragma unroll
+        for (int n = 0; n < 2; n++) {
+          const int xs = n == 0 ? x + hx : x - hx, ys = n == 0 ? y + vy : y - vy;
+          if (xs < 0 || ys < 0 || xs >= width || ys >= height) { ok = false; continue; }
+          const int dxc = (xs >> log2w) - ctbx, dyc = (ys >> log2h) - ctby;
+          if (dxc | dyc) {
+            int bit;
+            if (dyc == 0) bit = dxc < 0 ? HC_NB_L : HC_NB_R;
+            else if (dxc == 0) bit = dyc < 0 ? HC_NB_T : HC_NB_B;
+            else if (dyc < 0) bit = dxc < 0 ? HC_NB_TL : HC_NB_TR;
+            else bit = dxc < 0 ? HC_NB_BL : HC_NB_BR;
+            if (!(nb & bit)) ok = false;
+          } else if (self_quirk) {
+            // reference quirk (sao.cc:283): border samples of this CTB also lose their in-CTB neighbours
+            const int lx = x & ((1 << log2w) - 1);
+            if (lx == 0 || ly == 0 || lx == lwid - 1 || ly == lhei - 1) ok = false;
+          }
+        }
+        if (!ok) continue;
+        const int a = hx < 0 ? ra[k] : (hx == 0 ? ra[k + 1] : ra[k + 2]);
+        const int b = hx < 0 ? rb[k + 2] : (hx == 0 ? rb[k + 1] : rb[k]);
+        const int e = sign3(orig[k] - a) + sign3(orig[k] - b);   // -2..2
+        // edgeIdx -2,-1,1,2 -> offsets 0,1,2,3 (sao.cc:312-317)
+        if (e) v[k] = clip3i(0, maxv, orig[k] + (e == -2 ? o0 : e == -1 ? o1 : e == 1 ? o2 : o3));
+      }
     }
-    if (rescale) {
-      // context.cc:2504-2528: bytewise float rescale of limited-range tiles, no FMA contraction
-      const float ratio = c == 0 ? 1.1689f : 1.1429f;
-      const float full = __fmul_rn(__fsub_rn((float)v, (float)(16 << (bit_depth - 8))), ratio);
+  }
+  if (pic.dst_flags & HC_DST_RESCALE_LIMITED) {
+    // context.cc:2504-2528: bytewise float rescale of limited-range tiles, no FMA contraction
+    const float ratio = c == 0 ? 1.1689f : 1.1429f;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      const float full = __fmul_rn(__fsub_rn((float)v[k], (float)(16 << (bit_depth - 8))), ratio);
       const long r = (long)__fadd_rn(full, 0.5f);
-      v = r < 0 ? 0 : (r > 255 ? 255 : (int)r);
+      v[k] = r < 0 ? 0 : (r > 255 ? 255 : (int)r);
     }
-    dst[(size_t)(dy0 + oy) * dstride + dx0 + ox] = (Pixel)v;
+  }
+  Pixel* out = dst + (size_t)(dy0 + oy) * dstride + dx0 + ox0;
+  if (nvalid == 8 && ox0 >= 0 && ox0 + 8 <= copy_w && ((dx0 + ox0) & 7) == 0) {
+    store8(out, v);
+  } else {
+#pragma unroll
+    for (int k = 0; k < 8; k++)
+      if (k < nvalid && ox0 + k >= 0 && ox0 + k < copy_w) out[k] = (Pixel)v[k];
   }
 }
 
@@ -132,10 +209,10 @@ __global__ void __launch_bounds__(256) k4_sao_kernel(BatchView bv) {
   else sao_picture<uint16_t>(bv, pic, c, tid);
 }
 
-// max_quads = max over pictures of ceil(width/4)*height
-void launch_k4(const BatchView& bv, long long max_quads, int planes, cudaStream_t stream) {
-  if (max_quads <= 0 || bv.npics <= 0) return;
-  dim3 grid((unsigned)((max_quads + 255) / 256), (unsigned)bv.npics, (unsigned)planes);
+// max_units = max over pictures of ceil(width/8)*height
+void launch_k4(const BatchView& bv, long long max_units, int planes, cudaStream_t stream) {
+  if (max_units <= 0 || bv.npics <= 0) return;
+  dim3 grid((unsigned)((max_units + 255) / 256), (unsigned)bv.npics, (unsigned)planes);
   k4_sao_kernel<<<grid, 256, 0, stream>>>(bv);
 }
 
