@@ -1,5 +1,7 @@
 // hevc_cabac.h — CABAC arithmetic decoding engine + I-slice context set (H.265 §9.3).
-// New implementation (byte-wise refill with a scaled offset register); tables 9-5..9-37 (context
+// New implementation: the 9-bit arithmetic offset and up to 47 look-ahead bits share one 64-bit
+// register, so renormalisation is a counter decrement and the input is refilled 32 bits at a time;
+// fixed-length bypass strings are decoded by one division. Tables 9-5..9-37 (context
 // initialisation, initType 0 only: this front-end decodes I slices) and 9-46/9-47 (state
 // transition, LPS range) are normative data.
 // Reference counterpart: third-party/libde265/libde265/cabac.cc:181-655, contextmodel.cc:234-354.
@@ -61,30 +63,24 @@ static const uint8_t kRangeLps[64][4] = {
     {10, 12, 14, 16},     {9, 11, 13, 15},      {9, 11, 12, 14},      {8, 10, 12, 14},
     {8, 9, 11, 13},       {7, 9, 11, 12},       {7, 9, 10, 12},       {7, 8, 10, 11},
     {6, 8, 9, 11},        {6, 7, 9, 10},        {6, 7, 8, 9},         {2, 2, 2, 2}};
-static const uint8_t kNextMps[64] = {1,  2,  3,  4,  5,  6,  7,  8,  9,  10, 11, 12, 13, 14, 15, 16,
-                                     17, 18, 19, 20, 21, 22, 23, 24, 25, 26, 27, 28, 29, 30, 31, 32,
-                                     33, 34, 35, 36, 37, 38, 39, 40, 41, 42, 43, 44, 45, 46, 47, 48,
-                                     49, 50, 51, 52, 53, 54, 55, 56, 57, 58, 59, 60, 61, 62, 62, 63};
-static const uint8_t kNextLps[64] = {0,  0,  1,  2,  2,  4,  4,  5,  6,  7,  8,  9,  9,  11, 11, 12,
-                                     13, 13, 15, 15, 16, 16, 18, 18, 19, 19, 21, 21, 22, 22, 23, 24,
-                                     24, 25, 26, 26, 27, 27, 28, 29, 29, 30, 30, 30, 31, 32, 32, 33,
-                                     33, 33, 34, 34, 35, 35, 35, 36, 36, 36, 37, 37, 37, 38, 38, 63};
-
 struct Transitions {
   uint8_t mps[128], lps[128];
-  Transitions() {
+  constexpr Transitions() : mps(), lps() {
+    constexpr uint8_t next_mps[64] = {1,  2,  3,  4,  5,  6,  7,  8,  9,  10, 11, 12, 13, 14, 15, 16, 17, 18, 19, 20, 21, 22,
+                                      23, 24, 25, 26, 27, 28, 29, 30, 31, 32, 33, 34, 35, 36, 37, 38, 39, 40, 41, 42, 43, 44,
+                                      45, 46, 47, 48, 49, 50, 51, 52, 53, 54, 55, 56, 57, 58, 59, 60, 61, 62, 62, 63};
+    constexpr uint8_t next_lps[64] = {0,  0,  1,  2,  2,  4,  4,  5,  6,  7,  8,  9,  9,  11, 11, 12, 13, 13, 15, 15, 16, 16,
+                                      18, 18, 19, 19, 21, 21, 22, 22, 23, 24, 24, 25, 26, 26, 27, 27, 28, 29, 29, 30, 30, 30,
+                                      31, 32, 32, 33, 33, 33, 34, 34, 35, 35, 35, 36, 36, 36, 37, 37, 37, 38, 38, 63};
     for (int st = 0; st < 64; st++)
       for (int m = 0; m < 2; m++) {
-        mps[(st << 1) | m] = (uint8_t)((kNextMps[st] << 1) | m);
+        mps[(st << 1) | m] = (uint8_t)((next_mps[st] << 1) | m);
         int nm = (st == 0) ? 1 - m : m;
-        lps[(st << 1) | m] = (uint8_t)((kNextLps[st] << 1) | nm);
+        lps[(st << 1) | m] = (uint8_t)((next_lps[st] << 1) | nm);
       }
   }
 };
-inline const Transitions& transitions() {
-  static const Transitions t;
-  return t;
-}
+static constexpr Transitions kTransitions{};
 }  // namespace detail
 
 inline uint8_t ctx_init_state(int init_value, int slice_qp) {
@@ -139,105 +135,115 @@ inline void ctx_init_all(CtxSet& c, int slice_qp) {
   set(CTX_RES_SCALE_SIGN, c154, 2);
 }
 
-// Arithmetic decoder. `value` holds the offset scaled by 2^7 plus up to 8 look-ahead bits;
-// `bits_needed` counts (negative) how many more shifts fit before the next byte is fetched.
+// Arithmetic decoder. `value` = (ivlOffset << avail) | the next `avail` bits of the stream, so
+// "ivlOffset < ivlCurrRange" is `value < (range << avail)` and a renormalisation shift by n is
+// `avail -= n`. Invariant between calls: 16 <= avail <= 47 (every call may consume up to 16 bits).
+// The input must be readable for 8 bytes past `end` (the parser pads its RBSP buffer).
 struct Cabac {
-  const uint8_t* cur = nullptr;
+  const uint8_t* start = nullptr;
+  const uint8_t* cur = nullptr;   // next byte to load
   const uint8_t* end = nullptr;
+  uint64_t value = 0;
   uint32_t range = 510;
-  uint32_t value = 0;
-  int bits_needed = -8;
-  bool overrun = false;
+  int avail = 0;
 
-  inline uint32_t next_byte() {
-    if (cur < end) return *cur++;
-    cur++;  // keep counting so that position arithmetic stays monotonic
-    overrun = true;
-    return 0;
+  static inline uint32_t load_be32(const uint8_t* p) {
+    uint32_t v;
+    memcpy(&v, p, 4);
+    return __builtin_bswap32(v);
+  }
+  inline void refill() {
+    if (avail < 16) {
+      value = (value << 32) | load_be32(cur);
+      cur += 4;
+      avail += 32;
+    }
   }
 
-  // 16 bits are loaded: the top 9 are the arithmetic offset, the low 7 are look-ahead; after
-  // 8 single-bit shifts the next byte is fetched (bits_needed counts up from -8).
   void init(const uint8_t* p, const uint8_t* e) {
-    cur = p;
+    start = p;
     end = e;
-    overrun = false;
     range = 510;
-    bits_needed = -8;
-    value = next_byte() << 8;
-    value |= next_byte();
+    value = load_be32(p);
+    cur = p + 4;
+    avail = 32 - 9;
   }
+
+  // Byte position "after the last byte fetched" of a decoder that loads 2 bytes at start-up and
+  // one more every 8 renormalisation shifts: where the next substream / the PCM samples begin
+  // (H.265 9.3.2.5; the reference uses its fetch pointer the same way, slice.cc:5306-5312).
+  inline const uint8_t* position() const {
+    const long shifts = (long)(cur - start) * 8 - 9 - avail;
+    return start + 2 + (shifts >> 3);
+  }
+  inline bool overrun() const { return position() > end; }
 
   inline int decode_bin(uint8_t& state) {
-    const detail::Transitions& tr = detail::transitions();
-    uint32_t st = state;
-    uint32_t lps = detail::kRangeLps[st >> 1][(range >> 6) & 3];
+    const uint32_t st = state;
+    const uint32_t lps = detail::kRangeLps[st >> 1][(range >> 6) & 3];
     range -= lps;
-    uint32_t scaled = range << 7;
+    const uint64_t scaled = (uint64_t)range << avail;
     int bin;
     if (value < scaled) {
-      bin = st & 1;
-      state = tr.mps[st];
-      if (scaled < (256u << 7)) {
-        range = scaled >> 6;
-        value <<= 1;
-        if (++bits_needed == 0) {
-          bits_needed = -8;
-          value |= next_byte();
-        }
+      bin = (int)(st & 1);
+      state = detail::kTransitions.mps[st];
+      if (range < 256) {
+        range <<= 1;
+        avail--;
       }
     } else {
-      bin = (st & 1) ^ 1;
-      state = tr.lps[st];
-      int num_bits = 0;
-      {
-        uint32_t l = lps;
-        // renorm shift: lps in [6..255] after table (2..240): shift until >= 256
-        while (l < 256) { l <<= 1; num_bits++; }
-      }
-      value = (value - scaled) << num_bits;
-      range = lps << num_bits;
-      bits_needed += num_bits;
-      if (bits_needed >= 0) {
-        value |= next_byte() << bits_needed;
-        bits_needed -= 8;
-      }
+      value -= scaled;
+      const int n = __builtin_clz(lps) - 23;   // lps in [2,240]: shift until >= 256
+      range = lps << n;
+      avail -= n;
+      bin = (int)((st & 1) ^ 1);
+      state = detail::kTransitions.lps[st];
     }
+    refill();
     return bin;
   }
 
   inline int decode_bypass() {
-    value <<= 1;
-    if (++bits_needed >= 0) {
-      bits_needed = -8;
-      value |= next_byte();
-    }
-    uint32_t scaled = range << 7;
+    avail--;
+    const uint64_t scaled = (uint64_t)range << avail;
+    int bin = 0;
     if (value >= scaled) {
       value -= scaled;
-      return 1;
+      bin = 1;
     }
-    return 0;
+    refill();
+    return bin;
   }
 
+  // n bypass bins at once: the repeated compare/subtract is a division by the scaled range
   inline uint32_t decode_bypass_bits(int n) {
-    uint32_t v = 0;
-    for (int i = 0; i < n; i++) v = (v << 1) | (uint32_t)decode_bypass();
-    return v;
+    uint32_t out = 0;
+    while (n > 0) {
+      const int k = n > 16 ? 16 : n;
+      if (k <= 2) {
+        for (int i = 0; i < k; i++) out = (out << 1) | (uint32_t)decode_bypass();
+      } else {
+        avail -= k;
+        const uint64_t scaled = (uint64_t)range << avail;
+        const uint64_t q = value / scaled;
+        value -= q * scaled;
+        out = (out << k) | (uint32_t)q;
+        refill();
+      }
+      n -= k;
+    }
+    return out;
   }
 
   inline int decode_terminate() {
     range -= 2;
-    uint32_t scaled = range << 7;
+    const uint64_t scaled = (uint64_t)range << avail;
     if (value >= scaled) return 1;
-    if (scaled < (256u << 7)) {
-      range = scaled >> 6;
-      value <<= 1;
-      if (++bits_needed == 0) {
-        bits_needed = -8;
-        value |= next_byte();
-      }
+    if (range < 256) {
+      range <<= 1;
+      avail--;
     }
+    refill();
     return 0;
   }
 };

@@ -216,17 +216,19 @@ std::string HevcIntraParser::push_nal(const uint8_t* nal, size_t size) {
   std::vector<uint8_t> rbsp;
   std::vector<uint32_t> skipped;
   nal_unescape(nal, size, rbsp, &skipped);
+  const size_t rbsp_size = rbsp.size();
+  rbsp.resize(rbsp_size + 16, 0);   // the CABAC engine refills 4 bytes at a time (hevc_cabac.h)
 
   if (nal_type == NAL_SPS) {
     Sps s;
-    std::string e = parse_sps(rbsp.data() + 2, rbsp.size() - 2, s);
+    std::string e = parse_sps(rbsp.data() + 2, rbsp_size - 2, s);
     if (!e.empty()) return e;
     d.sps_tab[s.sps_id] = s;
     return "";
   }
   if (nal_type == NAL_PPS) {
     Pps p;
-    std::string e = parse_pps(rbsp.data() + 2, rbsp.size() - 2, d.sps_tab, p);
+    std::string e = parse_pps(rbsp.data() + 2, rbsp_size - 2, d.sps_tab, p);
     if (!e.empty()) return e;
     d.pps_tab[p.pps_id] = std::move(p);
     return "";
@@ -236,7 +238,7 @@ std::string HevcIntraParser::push_nal(const uint8_t* nal, size_t size) {
 
   // ---- slice segment ----
   SliceHeader hdr;
-  std::string e = parse_slice_header(rbsp.data(), rbsp.size(), nal_type, d.sps_tab, d.pps_tab,
+  std::string e = parse_slice_header(rbsp.data(), rbsp_size, nal_type, d.sps_tab, d.pps_tab,
                                      d.have_prev_independent ? &d.prev_independent : nullptr, skipped, hdr);
   if (!e.empty()) return e;
   if (hdr.first_slice_segment_in_pic) {
@@ -250,7 +252,7 @@ std::string HevcIntraParser::push_nal(const uint8_t* nal, size_t size) {
     d.prev_independent = hdr;
     d.have_prev_independent = true;
   }
-  return d.decode_slice_segment(rbsp.data(), rbsp.size(), hdr);
+  return d.decode_slice_segment(rbsp.data(), rbsp_size, hdr);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -393,7 +395,7 @@ std::string HevcIntraParser::Impl::decode_slice_segment(const uint8_t* data, siz
 
     decode_ctu();
     if (!error.empty()) return error;
-    if (cabac.overrun) return "slice data truncated";
+    if (cabac.overrun()) return "slice data truncated";
     ctbs_done++;
 
     if (P->entropy_coding_sync_enabled && ctbx == 1 && ctby < S->ctbs_h - 1) {
@@ -420,7 +422,7 @@ std::string HevcIntraParser::Impl::decode_slice_segment(const uint8_t* data, siz
     if (end_of_substream) {
       if (!cabac.decode_terminate()) return "end_of_subset_one_bit is not set";
       // the next substream starts at the byte after the last one fetched by the engine
-      const uint8_t* p = cabac.cur;
+      const uint8_t* p = cabac.position();
       if (p >= cabac.end) return "slice data truncated at a substream boundary";
       cabac.init(p, cabac.end);
       first_substream_of_independent = false;
@@ -521,7 +523,7 @@ void HevcIntraParser::Impl::read_sao(int rx, int ry, hc_ctu& ctu) {
 
 // §7.3.8.4
 void HevcIntraParser::Impl::coding_quadtree(int x0, int y0, int log2, int depth) {
-  if (!error.empty() || cabac.overrun) return;
+  if (!error.empty() || cabac.overrun()) return;
   int size = 1 << log2;
   bool split;
   if (x0 + size <= W && y0 + size <= H && log2 > S->log2_min_cb) {
@@ -772,7 +774,7 @@ void HevcIntraParser::Impl::coding_unit(int x0, int y0, int log2, int depth) {
 // needs no special input channel.
 void HevcIntraParser::Impl::pcm_sample(int x0, int y0, int log2) {
   // PCM data starts at the byte after the last one fetched by the arithmetic decoder
-  const uint8_t* p = cabac.cur;
+  const uint8_t* p = cabac.position();
   BitReader br(p, (size_t)(cabac.end > p ? cabac.end - p : 0));
   int ncomp = S->ChromaArrayType != 0 ? 3 : 1;
   for (int c = 0; c < ncomp; c++) {
@@ -838,7 +840,7 @@ void HevcIntraParser::Impl::mark_tu_edges(int x0, int y0, int log2) {
 void HevcIntraParser::Impl::transform_tree(int x0, int y0, int xBase, int yBase, int log2, int depth,
                                            int blkIdx, int max_depth, int intra_split,
                                            int parent_cbf_cb, int parent_cbf_cr) {
-  if (!error.empty() || cabac.overrun) return;
+  if (!error.empty() || cabac.overrun()) return;
   int split;
   if (log2 <= S->log2_max_tb && log2 > S->log2_min_tb && depth < max_depth && !(intra_split && depth == 0)) {
     split = bin(CTX_SPLIT_TRANSFORM + 5 - log2);
@@ -1033,6 +1035,50 @@ void HevcIntraParser::Impl::transform_unit(int x0, int y0, int xBase, int yBase,
 }
 
 // §7.3.8.11 residual_coding + §9.3.4.2.4-9.3.4.2.7 context selection
+// sig_coeff_flag ctxInc (9.3.4.2.5) for every scan position, built once:
+//   b4[chroma][scanIdx][k]                                   4x4 blocks (Table 9-50 ctxIdxMap)
+//   sb[chroma][size class][sub-block != (0,0)][prevCsbf][scanIdx][k]   size class 0: 8x8 diagonal, 1: 8x8 hor/ver, 2: 16/32
+//   ts[chroma][k]                                            transform_skip_context_enabled blocks
+// (the DC position of sub-block (0,0) of blocks > 4x4 is context 0 and handled by the caller)
+struct SigCtxTables {
+  uint8_t b4[2][3][16];
+  uint8_t sb[2][3][2][4][3][16];
+  uint8_t ts[2][16];
+  SigCtxTables() {
+    const ScanTables& st = scan_tables();
+    for (int c = 0; c < 2; c++) {
+      for (int k = 0; k < 16; k++) ts[c][k] = (uint8_t)(c == 0 ? 42 : 43);
+      for (int s = 0; s < 3; s++)
+        for (int k = 0; k < 16; k++) {
+          const int xP = st.order[2][s][k].x, yP = st.order[2][s][k].y;
+          b4[c][s][k] = (uint8_t)((c ? 27 : 0) + kSigCtx4x4[(yP << 2) + xP]);
+          for (int cls = 0; cls < 3; cls++)
+            for (int nz = 0; nz < 2; nz++)
+              for (int prev = 0; prev < 4; prev++) {
+                int v;
+                switch (prev) {
+                  case 0: v = (xP + yP >= 3) ? 0 : (xP + yP > 0) ? 1 : 2; break;
+                  case 1: v = (yP == 0) ? 2 : (yP == 1) ? 1 : 0; break;
+                  case 2: v = (xP == 0) ? 2 : (xP == 1) ? 1 : 0; break;
+                  default: v = 2; break;
+                }
+                if (c == 0) {
+                  if (nz) v += 3;
+                  v += cls == 0 ? 9 : (cls == 1 ? 15 : 21);
+                } else {
+                  v += cls == 2 ? 12 : 9;
+                }
+                sb[c][cls][nz][prev][s][k] = (uint8_t)((c ? 27 : 0) + v);
+              }
+        }
+    }
+  }
+};
+static const SigCtxTables& sig_ctx_tables() {
+  static const SigCtxTables t;
+  return t;
+}
+
 uint32_t HevcIntraParser::Impl::residual_coding(int x0, int y0, int log2, int cIdx, int pred_mode) {
   (void)x0; (void)y0;
   const ScanTables& st = scan_tables();
@@ -1079,16 +1125,8 @@ uint32_t HevcIntraParser::Impl::residual_coding(int x0, int y0, int log2, int cI
   const int sbW = 1 << (log2 - 2);
 
   // locate the last sub-block / position
-  int lastSubBlock, lastScanPos;
-  {
-    int sx = LastX >> 2, sy = LastY >> 2, pxx = LastX & 3, pyy = LastY & 3;
-    lastSubBlock = 0;
-    for (int i = 0; i < sbW * sbW; i++)
-      if (scanSub[i].x == sx && scanSub[i].y == sy) { lastSubBlock = i; break; }
-    lastScanPos = 0;
-    for (int i = 0; i < 16; i++)
-      if (scanPos[i].x == pxx && scanPos[i].y == pyy) { lastScanPos = i; break; }
-  }
+  const int lastSubBlock = st.inverse[log2 - 2][scanIdx][(LastX >> 2) + ((LastY >> 2) << (log2 - 2))];
+  const int lastScanPos = st.inverse[2][scanIdx][(LastX & 3) + ((LastY & 3) << 2)];
 
   uint8_t csbf_nb[64];
   memset(csbf_nb, 0, (size_t)sbW * sbW);
@@ -1115,6 +1153,8 @@ uint32_t HevcIntraParser::Impl::residual_coding(int x0, int y0, int log2, int cI
                                (S->implicit_rdpcm_enabled && tskip && (pred_mode == 10 || pred_mode == 26)));
   int c1 = 1;
   int ncoeff_total = 0;
+  hc_coeff cbuf[1024];
+  const SigCtxTables& sig = sig_ctx_tables();
 
   for (int i = lastSubBlock; i >= 0; i--) {
     const int Sx = scanSub[i].x, Sy = scanSub[i].y;
@@ -1140,41 +1180,23 @@ uint32_t HevcIntraParser::Impl::residual_coding(int x0, int y0, int log2, int cI
     const int prevCsbf = csbf_nb[Sx + Sy * sbW];
     const int xS0 = Sx << 2, yS0 = Sy << 2;
 
-    auto sig_ctx = [&](int xC, int yC) -> int {
-      int sigCtx;
-      if (ts_ctx) return cIdx == 0 ? 42 : 43;
-      if (log2 == 2) sigCtx = kSigCtx4x4[(yC << 2) + xC];
-      else if (xC + yC == 0) sigCtx = 0;
-      else {
-        int xP = xC & 3, yP = yC & 3;
-        switch (prevCsbf) {
-          case 0: sigCtx = (xP + yP >= 3) ? 0 : (xP + yP > 0) ? 1 : 2; break;
-          case 1: sigCtx = (yP == 0) ? 2 : (yP == 1) ? 1 : 0; break;
-          case 2: sigCtx = (xP == 0) ? 2 : (xP == 1) ? 1 : 0; break;
-          default: sigCtx = 2; break;
-        }
-        if (cIdx == 0) {
-          if ((xC >> 2) + (yC >> 2) > 0) sigCtx += 3;
-          sigCtx += (log2 == 3) ? (scanIdx == 0 ? 9 : 15) : 21;
-        } else {
-          sigCtx += (log2 == 3) ? 9 : 12;
-        }
-      }
-      return cIdx == 0 ? sigCtx : 27 + sigCtx;
-    };
+    // sig_coeff_flag context per scan position of this sub-block (9.3.4.2.5), table driven
+    const uint8_t* sigtab = ts_ctx ? sig.ts[cIdx ? 1 : 0]
+                          : log2 == 2 ? sig.b4[cIdx ? 1 : 0][scanIdx]
+                                      : sig.sb[cIdx ? 1 : 0][log2 == 3 ? (scanIdx == 0 ? 0 : 1) : 2][(Sx | Sy) ? 1 : 0][prevCsbf][scanIdx];
+    const int dc_ctx = (ts_ctx || log2 == 2 || i > 0) ? sigtab[0] : (cIdx ? 27 : 0);
 
     int last_coeff = (i == lastSubBlock) ? lastScanPos - 1 : 15;
     if (i == lastSubBlock) { value[n] = 1; maxbase[n] = 1; spos[n] = (int8_t)lastScanPos; n++; }
     for (int k = last_coeff; k > 0; k--) {
-      int xC = xS0 + scanPos[k].x, yC = yS0 + scanPos[k].y;
-      if (bin(CTX_SIG + sig_ctx(xC, yC))) {
+      if (bin(CTX_SIG + sigtab[k])) {
         value[n] = 1; maxbase[n] = 1; spos[n] = (int8_t)k; n++;
         inferSbDc = 0;
       }
     }
     if (last_coeff >= 0) {
       if (!inferSbDc) {
-        if (bin(CTX_SIG + sig_ctx(xS0, yS0))) { value[n] = 1; maxbase[n] = 1; spos[n] = 0; n++; }
+        if (bin(CTX_SIG + dc_ctx)) { value[n] = 1; maxbase[n] = 1; spos[n] = 0; n++; }
       } else {
         value[n] = 1; maxbase[n] = 1; spos[n] = 0; n++;
       }
@@ -1242,10 +1264,10 @@ uint32_t HevcIntraParser::Impl::residual_coding(int x0, int y0, int log2, int cI
       hc_coeff co;
       co.pos = (uint16_t)((xS0 + scanPos[p].x) + (yS0 + scanPos[p].y) * nT);
       co.level = level;
-      rec->coeffs.push_back(co);
-      ncoeff_total++;
+      cbuf[ncoeff_total++] = co;
     }
   }
+  rec->coeffs.insert(rec->coeffs.end(), cbuf, cbuf + ncoeff_total);
   tb.ncoeff = (uint16_t)ncoeff_total;
   rec->tbs.push_back(tb);
   rec->resid_count += (uint64_t)nT * nT;

@@ -11,6 +11,8 @@ struct ScanTables {
   // [log2BlockSize 0..5][scanIdx 0 diag,1 horizontal,2 vertical] -> positions (blk*blk entries)
   ScanPos* order[6][3];
   ScanPos storage[3 * (1 + 4 + 16 + 64 + 256 + 1024)];
+  // inverse[log2][scanIdx][x + (y << log2)] -> scan index, for log2 0..3 (sub-block grids and the 4x4 positions)
+  uint8_t inverse[4][3][64];
   ScanTables() {
     ScanPos* p = storage;
     for (int l = 0; l <= 5; l++) {
@@ -39,6 +41,9 @@ struct ScanTables {
         for (int y = 0; y < n; y++, i++) { p[i].x = (uint8_t)x; p[i].y = (uint8_t)y; }
       p += n * n;
     }
+    for (int l = 0; l <= 3; l++)
+      for (int s = 0; s < 3; s++)
+        for (int i = 0; i < (1 << (2 * l)); i++) inverse[l][s][order[l][s][i].x + (order[l][s][i].y << l)] = (uint8_t)i;
   }
 };
 
