@@ -12,6 +12,8 @@
 // pattern (context.cc:1799-1835) does not pay a cudaMalloc per tile.
 #include <cuda_runtime.h>
 #include <algorithm>
+#include <atomic>
+#include <thread>
 #include <cstdio>
 #include <cstring>
 #include <mutex>
@@ -269,6 +271,7 @@ int hc_batch_upload(hc_batch* b) {
   size_t n_ctu = 0, n_blk = 0, n_tb = 0, n_coeff = 0, n_edge = 0, n_qp = 0, n_scal = 0;
   uint64_t n_resid = 0;
   int counts[4] = {0, 0, 0, 0};
+  std::vector<int> idx_base((size_t)np * 4);   // first slot of picture i in the size-l launch list
   int max_rows = 0;
   size_t n_tasks = 0;
   b->max_dbk_units = b->max_sao_quads = 0;
@@ -286,7 +289,7 @@ int hc_batch_upload(hc_batch* b) {
     p.scaling_base = (uint32_t)n_scal; n_scal += r.scaling.size();
     p.resid_base = n_resid;         n_resid += align_up(r.resid_count, 8);
     if (n_blk > 0xFFFFFFFFull || n_coeff > 0xFFFFFFFFull) { hc::set_last_error("batch too large"); return HC_ERR_ARGUMENT; }
-    for (auto& t : r.tbs) counts[t.log2 - 2]++;
+    for (int l = 0; l < 4; l++) { idx_base[(size_t)i * 4 + l] = counts[l]; counts[l] += (int)r.tbs_by_size[l]; }
     const int ncomp = p.chroma_format ? 3 : 1;
     max_rows = std::max(max_rows, (int)p.ctbs_h);
     n_tasks += (size_t)ncomp * p.ctbs_h;
@@ -336,20 +339,21 @@ int hc_batch_upload(hc_batch* b) {
   b->resid_elems = n_resid;
   b->planes_bytes = pool;
 
-  // ---- pack ----
+  // ---- pack: every picture's records go to disjoint slices of the pinned arena, in parallel ----
   uint8_t* H = (uint8_t*)b->h_arena.p;
   memcpy(H + o_pics, b->hpics.data(), sizeof(hc_pic) * np);
   uint32_t* idx[4];
-  int fill[4] = {0, 0, 0, 0};
   for (int l = 0; l < 4; l++) idx[l] = (uint32_t*)(H + o_idx[l]);
-  for (int i = 0; i < np; i++) {
+  auto pack_picture = [&](int i) {
     const hc::PictureRecords& r = *b->pics[i].rec;
     const hc_pic& p = b->hpics[i];
     memcpy(H + o_ctus + sizeof(hc_ctu) * p.ctu_base, r.ctus.data(), sizeof(hc_ctu) * r.ctus.size());
     memcpy(H + o_blks + sizeof(hc_blk) * p.blk_base, r.blks.data(), sizeof(hc_blk) * r.blks.size());
     hc_tb* tb = (hc_tb*)(H + o_tbs) + p.tb_base;
-    memcpy(tb, r.tbs.data(), sizeof(hc_tb) * r.tbs.size());
+    int fill[4];
+    for (int l = 0; l < 4; l++) fill[l] = idx_base[(size_t)i * 4 + l];
     for (size_t k = 0; k < r.tbs.size(); k++) {
+      tb[k] = r.tbs[k];
       tb[k].pic = (uint16_t)i;
       const int l = tb[k].log2 - 2;
       idx[l][fill[l]++] = (uint32_t)(p.tb_base + k);
@@ -358,6 +362,19 @@ int hc_batch_upload(hc_batch* b) {
     memcpy(H + o_edge + p.edge_base, r.edge_map.data(), r.edge_map.size());
     memcpy(H + o_qp + p.qp_base, r.qp_map.data(), r.qp_map.size());
     if (!r.scaling.empty()) memcpy(H + o_scal + p.scaling_base, r.scaling.data(), r.scaling.size());
+  };
+  {
+    int nthreads = (int)std::thread::hardware_concurrency();
+    nthreads = std::max(1, std::min(nthreads, std::min(np, (int)(o >> 22) + 1)));   // ~4 MB of records per thread at least
+    if (nthreads == 1) {
+      for (int i = 0; i < np; i++) pack_picture(i);
+    } else {
+      std::atomic<int> next{0};
+      std::vector<std::thread> pool;
+      for (int t = 0; t < nthreads; t++)
+        pool.emplace_back([&]() { for (int i; (i = next.fetch_add(1)) < np;) pack_picture(i); });
+      for (auto& t : pool) t.join();
+    }
   }
   // K2 tasks: row-major across all pictures so that every wavefront advances together and a task
   // only depends on a task with a smaller index
@@ -539,6 +556,15 @@ int hc_batch_read_rgb(hc_batch* b, int canvas, void* dst, size_t dst_stride) {
   cudaEventElapsedTime(&b->last_d2h_ms, e0, e1);
   cudaEventDestroy(e0); cudaEventDestroy(e1);
   return HC_OK;
+}
+
+int hc_batch_read_rgb_async(hc_batch* b, int canvas, void* dst, size_t dst_stride) {
+  if (!b || !dst || canvas < 0 || canvas >= (int)b->canvases.size()) { hc::set_last_error("hc_batch_read_rgb_async: bad argument"); return HC_ERR_ARGUMENT; }
+  const Canvas& c = b->canvases[canvas];
+  if (!c.converted) { hc::set_last_error("canvas was not converted"); return HC_ERR_ARGUMENT; }
+  cudaError_t e = cudaMemcpy2DAsync(dst, dst_stride, (const uint8_t*)b->d_rgb.p + c.rgb_off, c.rgb_stride, (size_t)c.w * c.rgb_bpp, c.h,
+                                    cudaMemcpyDeviceToHost, b->stream);
+  return cuda_ok(e, "cudaMemcpy2DAsync(D2H rgb)") ? HC_OK : HC_ERR_CUDA;
 }
 
 int hc_batch_read_residual(hc_batch* b, int pic, int16_t* dst, size_t count) {

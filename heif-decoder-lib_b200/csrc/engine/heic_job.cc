@@ -7,7 +7,9 @@
 // (:2120-2404) + decode_and_paste_tile_image (:2407-2539) for grids, the alpha auxiliary image
 // (:2029-2078), the nclx precedence (:1844-1847) and convert_colorspace (colorconversion.cc:487).
 #include <atomic>
+#include <algorithm>
 #include <chrono>
+#include <future>
 #include <thread>
 #include <vector>
 #include "../capi/capi_internal.h"
@@ -238,5 +240,90 @@ int hc_heic_job_timer_stop_ms(hc_heic_job* j, float* ms) { return j ? hc_batch_t
 int hc_heic_job_launch_count(const hc_heic_job* j) { return j ? hc_batch_launch_count(j->batch) : 0; }
 size_t hc_heic_job_upload_bytes(const hc_heic_job* j) { return j ? hc_batch_upload_bytes(j->batch) : 0; }
 double hc_heic_job_parse_seconds(const hc_heic_job* j) { return j ? j->parse_seconds : 0.0; }
+
+int hc_heic_decode_stream(hc_engine* e, int nfiles, const uint8_t* const* data, const size_t* sizes, int want_alpha,
+                          int threads, int files_per_batch, hc_image_callback on_image, void* user,
+                          hc_stream_stats* stats) {
+  if (!e || nfiles <= 0 || !data || !sizes || files_per_batch <= 0) {
+    hc::set_last_error("hc_heic_decode_stream: bad argument");
+    return HC_ERR_ARGUMENT;
+  }
+  using clock = std::chrono::steady_clock;
+  auto secs = [](clock::time_point a, clock::time_point b) { return std::chrono::duration<double>(b - a).count(); };
+  hc_stream_stats st{};
+  const auto t_begin = clock::now();
+  const int nbatches = (nfiles + files_per_batch - 1) / files_per_batch;
+
+  // stage 1 (host threads): container + CABAC parse of one batch; runs one batch ahead of stage 2
+  struct Parsed { hc_heic_job* job = nullptr; std::string error; double seconds = 0; };
+  auto parse_batch = [&](int b) -> Parsed {
+    Parsed p;
+    const int first = b * files_per_batch, n = std::min(files_per_batch, nfiles - first);
+    const auto t0 = clock::now();
+    p.job = hc_heic_job_create(e, n, data + first, sizes + first, want_alpha, threads);
+    if (!p.job) p.error = hc_last_error();   // thread-local: fetch on the parsing thread
+    p.seconds = secs(t0, clock::now());
+    return p;
+  };
+
+  void* pinned = nullptr;
+  size_t pinned_cap = 0;
+  int rc = HC_OK;
+  std::string err;
+  std::future<Parsed> ahead = std::async(std::launch::async, parse_batch, 0);
+  for (int b = 0; b < nbatches; b++) {
+    Parsed cur = ahead.get();
+    if (b + 1 < nbatches) ahead = std::async(std::launch::async, parse_batch, b + 1);
+    st.seconds_parse += cur.seconds;
+    if (!cur.job) {
+      if (rc == HC_OK) { rc = HC_ERR_BITSTREAM; err = "batch " + std::to_string(b) + ": " + cur.error; }
+      continue;   // keep draining the pipeline
+    }
+    if (rc != HC_OK) { hc_heic_job_destroy(cur.job); continue; }
+    // stage 2 (this thread): upload, K1..K5, read-back into pinned memory, hand out
+    const auto t0 = clock::now();
+    hc_heic_job* j = cur.job;
+    size_t need = 0;
+    std::vector<size_t> offs(j->images.size());
+    for (size_t i = 0; i < j->images.size(); i++) {
+      offs[i] = need;
+      need += ((size_t)j->images[i].desc.width * j->images[i].desc.bytes_per_pixel * j->images[i].desc.height + 255) & ~(size_t)255;
+    }
+    if (need > pinned_cap) {
+      if (pinned) hc_host_free(pinned);
+      pinned = hc_host_alloc(need + need / 8);
+      pinned_cap = pinned ? need + need / 8 : 0;
+    }
+    int r = pinned ? hc_heic_job_upload(j) : HC_ERR_MEMORY;
+    if (r == HC_OK) r = hc_heic_job_run(j);
+    for (size_t i = 0; r == HC_OK && i < j->images.size(); i++)
+      r = hc_batch_read_rgb_async(j->batch, j->images[i].canvas, (uint8_t*)pinned + offs[i],
+                                  (size_t)j->images[i].desc.width * j->images[i].desc.bytes_per_pixel);
+    if (r == HC_OK) r = hc_heic_job_sync(j);
+    if (r == HC_OK) {
+      float ms[8];
+      if (hc_heic_job_stage_ms(j, ms) == HC_OK) st.device_ms += ms[1] + ms[2] + ms[3] + ms[4] + ms[5];
+      st.bytes_h2d += hc_heic_job_upload_bytes(j);
+      st.launches += hc_heic_job_launch_count(j);
+      for (size_t i = 0; i < j->images.size(); i++) {
+        const hc_image_desc& d = j->images[i].desc;
+        st.bytes_d2h += (uint64_t)d.width * d.bytes_per_pixel * d.height;
+        st.pixels += (int64_t)d.width * d.height;
+        if (on_image) on_image(user, b * files_per_batch + (int)i, &d, (const uint8_t*)pinned + offs[i], (size_t)d.width * d.bytes_per_pixel);
+      }
+    } else if (rc == HC_OK) {
+      rc = r;
+      err = hc_last_error();
+    }
+    hc_heic_job_destroy(j);
+    st.seconds_gpu_phase += secs(t0, clock::now());
+    st.batches++;
+  }
+  if (pinned) hc_host_free(pinned);
+  st.seconds_total = secs(t_begin, clock::now());
+  if (stats) *stats = st;
+  if (rc != HC_OK) hc::set_last_error(err);
+  return rc;
+}
 
 }  // extern "C"

@@ -812,6 +812,7 @@ void HevcIntraParser::Impl::pcm_sample(int x0, int y0, int log2) {
         }
       tb.ncoeff = (uint16_t)n;
       rec->tbs.push_back(tb);
+      rec->tbs_by_size[tb.log2 - 2]++;
       rec->resid_count += (uint64_t)w * w;
       int xB = c == 0 ? x0 : x0 / S->SubWidthC;
       int yB = (c == 0 ? y0 : y0 / S->SubHeightC) + s * w;
@@ -1270,6 +1271,7 @@ uint32_t HevcIntraParser::Impl::residual_coding(int x0, int y0, int log2, int cI
   rec->coeffs.insert(rec->coeffs.end(), cbuf, cbuf + ncoeff_total);
   tb.ncoeff = (uint16_t)ncoeff_total;
   rec->tbs.push_back(tb);
+  rec->tbs_by_size[log2 - 2]++;
   rec->resid_count += (uint64_t)nT * nT;
   return tb.resid_off;
 }

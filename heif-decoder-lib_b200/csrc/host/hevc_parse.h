@@ -26,6 +26,7 @@ struct PictureRecords {
   std::vector<int8_t> qp_map;      // (width/8)*(height/8)
   std::vector<uint8_t> scaling;    // HC_SCALING_BLOB_BYTES or empty
   uint64_t resid_count = 0;        // int16 elements needed in the residual buffer
+  uint32_t tbs_by_size[4] = {0, 0, 0, 0};   // coded transform blocks per log2 size 2..5 (K1 launch lists)
   std::vector<std::string> warnings;
 };
 

@@ -52,6 +52,15 @@ class HeifImageInfo(C.Structure):
                 ("transfer", C.c_int32), ("matrix", C.c_int32), ("full_range", C.c_int32)]
 
 
+class StreamStats(C.Structure):
+    """hc_stream_stats"""
+    _fields_ = [("seconds_total", C.c_double), ("seconds_parse", C.c_double), ("seconds_gpu_phase", C.c_double),
+                ("device_ms", C.c_double), ("bytes_h2d", C.c_uint64), ("bytes_d2h", C.c_uint64), ("pixels", C.c_int64),
+                ("batches", C.c_int32), ("launches", C.c_int32)]
+
+
+IMAGE_CALLBACK = C.CFUNCTYPE(None, C.c_void_p, C.c_int, C.POINTER(ImageDesc), C.c_void_p, C.c_size_t)
+
 # every symbol include/heifcuda.h declares: (name, restype, argtypes)
 _vp, _sz, _i, _u32 = C.c_void_p, C.c_size_t, C.c_int, C.c_uint32
 SYMBOLS = [
@@ -93,6 +102,7 @@ SYMBOLS = [
     ("hc_batch_sync", _i, [_vp]),
     ("hc_batch_read_plane", _i, [_vp, _i, _i, _vp, _sz]),
     ("hc_batch_read_rgb", _i, [_vp, _i, _vp, _sz]),
+    ("hc_batch_read_rgb_async", _i, [_vp, _i, _vp, _sz]),
     ("hc_batch_read_residual", _i, [_vp, _i, _vp, _sz]),
     ("hc_batch_stage_ms", _i, [_vp, C.POINTER(C.c_float)]),
     ("hc_batch_timer_start", _i, [_vp]),
@@ -114,6 +124,8 @@ SYMBOLS = [
     ("hc_heic_job_launch_count", _i, [_vp]),
     ("hc_heic_job_upload_bytes", _sz, [_vp]),
     ("hc_heic_job_parse_seconds", C.c_double, [_vp]),
+    ("hc_heic_decode_stream", _i, [_vp, _i, C.POINTER(C.c_char_p), C.POINTER(_sz), _i, _i, _i, IMAGE_CALLBACK, _vp,
+                               C.POINTER(StreamStats)]),
     ("hc_host_alloc", _vp, [_sz]),
     ("hc_host_free", None, [_vp]),
 ]

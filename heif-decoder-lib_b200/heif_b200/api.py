@@ -338,3 +338,32 @@ class HeicJob:
 
     def __del__(self):
         self.close()
+
+
+def decode_stream(engine, files, on_image=None, want_alpha=False, threads=0, files_per_batch=8):
+    """Long file lists (hc_heic_decode_stream): host parse of batch b+1 overlaps upload + kernels + read-back of
+    batch b. on_image(file_index, desc, rows) gets every image as a numpy view [h, w*bytes_per_pixel] of PINNED
+    host memory that is only valid inside the callback. Returns the hc_stream_stats as a dict."""
+    from ._lib import IMAGE_CALLBACK, StreamStats
+    L = engine._L
+    bufs = {}
+    ptr_list = []
+    for f in files:                         # identical bytes objects share one buffer
+        if id(f) not in bufs:
+            bufs[id(f)] = C.create_string_buffer(f, len(f))
+        ptr_list.append(C.cast(bufs[id(f)], C.c_char_p))
+    n = len(files)
+    ptrs = (C.c_char_p * n)(*ptr_list)
+    sizes = (C.c_size_t * n)(*[len(f) for f in files])
+
+    def _cb(_user, index, desc, pixels, stride):
+        if on_image is not None:
+            d = desc.contents
+            rows = np.ctypeslib.as_array((C.c_uint8 * (stride * d.height)).from_address(pixels)).reshape(d.height, stride)
+            on_image(index, d, rows)
+
+    cb = IMAGE_CALLBACK(_cb)
+    st = StreamStats()
+    check(L, L.hc_heic_decode_stream(engine._h, n, ptrs, sizes, int(want_alpha), threads, files_per_batch, cb, None, C.byref(st)),
+          "hc_heic_decode_stream")
+    return {k: getattr(st, k) for k, _ in StreamStats._fields_}

@@ -31,6 +31,11 @@
 #ifdef __cplusplus
 extern "C" {
 #endif
+/* the libraries are built with -fvisibility=hidden -fno-gnu-unique: only this C ABI is exported, so that
+ * no C++ symbol of the engine can bind to (or be bound by) another library of the host process */
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)
+#endif
 
 #define HC_OK 0
 #define HC_ERR_BITSTREAM (-1)   /* malformed / unsupported bitstream                           */
@@ -174,6 +179,8 @@ int hc_batch_sync(hc_batch* b);
  * 2 bytes little-endian otherwise. */
 int hc_batch_read_plane(hc_batch* b, int canvas, int plane, void* dst, size_t dst_stride_bytes);
 int hc_batch_read_rgb(hc_batch* b, int canvas, void* dst, size_t dst_stride_bytes);
+/* same copy without the final synchronisation (dst should be pinned); pair with hc_batch_sync */
+int hc_batch_read_rgb_async(hc_batch* b, int canvas, void* dst, size_t dst_stride_bytes);
 /* residuals of picture `pic` as produced by K1 (resid_count int16) — used by the parity tests */
 int hc_batch_read_residual(hc_batch* b, int pic, int16_t* dst, size_t count);
 /* device time of the last run's stages in ms (CUDA events on the engine stream):
@@ -232,10 +239,33 @@ int hc_heic_job_timer_stop_ms(hc_heic_job* j, float* ms);
 int hc_heic_job_launch_count(const hc_heic_job* j);
 size_t hc_heic_job_upload_bytes(const hc_heic_job* j);
 double hc_heic_job_parse_seconds(const hc_heic_job* j);
+
+/* Streaming form for long file lists (BASELINE config C4: thousands of files): the files are cut
+ * into batches of `files_per_batch`; while batch b is uploaded, reconstructed, converted and read
+ * back, the host threads already parse batch b+1. Every finished image is handed to `on_image`
+ * (called on the calling thread, in file order) as tightly strided rows in PINNED host memory that
+ * stays valid until the callback returns. Returns HC_OK or the first error (hc_last_error). */
+typedef void (*hc_image_callback)(void* user, int file_index, const hc_image_desc* desc, const void* pixels,
+                                  size_t stride_bytes);
+typedef struct hc_stream_stats {
+  double seconds_total;      /* wall time of the call                                             */
+  double seconds_parse;      /* sum over batches of the host parse phase (overlaps the GPU phase) */
+  double seconds_gpu_phase;  /* sum over batches of upload + kernels + read-back (host wall time) */
+  double device_ms;          /* sum over batches of K1..K5 device time                            */
+  uint64_t bytes_h2d, bytes_d2h;
+  int64_t pixels;            /* output pixels delivered                                           */
+  int32_t batches, launches;
+} hc_stream_stats;
+int hc_heic_decode_stream(hc_engine* e, int nfiles, const uint8_t* const* data, const size_t* sizes, int want_alpha,
+                          int threads, int files_per_batch, hc_image_callback on_image, void* user,
+                          hc_stream_stats* stats);
 /* pinned host memory for fast H2D/D2H in the caller (NULL when no CUDA engine) */
 void* hc_host_alloc(size_t bytes);
 void hc_host_free(void* p);
 
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
 #ifdef __cplusplus
 }
 #endif

@@ -24,6 +24,11 @@
 #ifdef __cplusplus
 extern "C" {
 #endif
+/* the libraries are built with -fvisibility=hidden -fno-gnu-unique: only this C ABI is exported, so that
+ * no C++ symbol of the engine can bind to (or be bound by) another library of the host process */
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)
+#endif
 
 /* struct heif_error                                   libheif/api/libheif/heif.h:373-384 */
 typedef struct hcp_error {
@@ -87,6 +92,9 @@ extern const hcp_decoder_plugin heifcuda_decoder_plugin;
  *   HEIFCUDA_LIBHEIF  path of the libheif shared object to call back into, for hosts that loaded
  *                     libheif with RTLD_LOCAL (default: symbols already visible in the process) */
 
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
 #ifdef __cplusplus
 }
 #endif

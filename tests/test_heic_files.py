@@ -73,3 +73,29 @@ def test_gpu_decode_heic_python_path(engine):
     for name in ("grid_300x200_t128", "single_420_8_novui", "alpha_420_8"):
         rgb = hb.decode_heic(engine, load(name), hb.OUT_RGB)
         assert md5(rgb.tobytes()) == META[name]["rgb_md5"], name
+
+
+@pytest.mark.gpu
+def test_gpu_decode_stream_pipelined_batches(engine):
+    """hc_heic_decode_stream: batches of 4 files, parse of batch b+1 overlapping the GPU phase of batch b;
+    every image arrives once, in order, bit-exact."""
+    files = [load(n) for n in NAMES] * 2
+    seen = []
+
+    def on_image(index, desc, rows):
+        name = NAMES[index % len(NAMES)]
+        key = {hb.OUT_RGB: "rgb", hb.OUT_RGBA: "rgba", hb.OUT_RRGGBB_LE: "rrggbb_le", hb.OUT_RRGGBBAA_LE: "rrggbbaa_le"}[desc.out_format]
+        seen.append((index, md5(rows.tobytes()) == META[name][key + "_md5"]))
+
+    st = hb.decode_stream(engine, files, on_image, want_alpha=False, threads=4, files_per_batch=4)
+    assert [i for i, _ in seen] == list(range(len(files)))
+    assert all(ok for _, ok in seen)
+    assert st["batches"] == (len(files) + 3) // 4 and st["pixels"] == 2 * sum(META[n]["width"] * META[n]["height"] for n in NAMES)
+    assert st["launches"] > 0 and st["bytes_d2h"] > 0
+
+
+@pytest.mark.gpu
+def test_gpu_decode_stream_reports_bad_file(engine):
+    files = [load(NAMES[0]), b"not a heic file at all", load(NAMES[1])]
+    with pytest.raises(hb.HeifCudaError):
+        hb.decode_stream(engine, files, None, files_per_batch=1)
