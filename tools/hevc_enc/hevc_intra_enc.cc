@@ -149,7 +149,7 @@ struct CabacEnc {
   }
   void test_write() { if (bits_left < 12) write_out(); }
   void bin(uint8_t& state, int v) {
-    const detail::Transitions& tr = detail::transitions();
+    const detail::Transitions& tr = detail::kTransitions;
     uint32_t st = state;
     uint32_t lps = detail::kRangeLps[st >> 1][(range >> 6) & 3];
     range -= lps;
