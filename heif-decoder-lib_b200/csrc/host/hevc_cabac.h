@@ -65,7 +65,8 @@ static const uint8_t kRangeLps[64][4] = {
     {6, 8, 9, 11},        {6, 7, 9, 10},        {6, 7, 8, 9},         {2, 2, 2, 2}};
 struct Transitions {
   uint8_t mps[128], lps[128];
-  constexpr Transitions() : mps(), lps() {
+  uint8_t next[128][2];   // [state][is_lps]
+  constexpr Transitions() : mps(), lps(), next() {
     constexpr uint8_t next_mps[64] = {1,  2,  3,  4,  5,  6,  7,  8,  9,  10, 11, 12, 13, 14, 15, 16, 17, 18, 19, 20, 21, 22,
                                       23, 24, 25, 26, 27, 28, 29, 30, 31, 32, 33, 34, 35, 36, 37, 38, 39, 40, 41, 42, 43, 44,
                                       45, 46, 47, 48, 49, 50, 51, 52, 53, 54, 55, 56, 57, 58, 59, 60, 61, 62, 62, 63};
@@ -77,6 +78,8 @@ struct Transitions {
         mps[(st << 1) | m] = (uint8_t)((next_mps[st] << 1) | m);
         int nm = (st == 0) ? 1 - m : m;
         lps[(st << 1) | m] = (uint8_t)((next_lps[st] << 1) | nm);
+        next[(st << 1) | m][0] = mps[(st << 1) | m];
+        next[(st << 1) | m][1] = lps[(st << 1) | m];
       }
   }
 };
@@ -178,29 +181,24 @@ struct Cabac {
   }
   inline bool overrun() const { return position() > end; }
 
+  // Branch-free bin decode: the MPS/LPS outcome of a well-used context is close to a coin flip, so
+  // it is turned into a mask instead of a (mispredicted) branch. Both paths renormalise by
+  // clz(range) - 23 (MPS: range >= 128 after the subtraction, i.e. 0 or 1 shifts).
   inline int decode_bin(uint8_t& state) {
     const uint32_t st = state;
     const uint32_t lps = detail::kRangeLps[st >> 1][(range >> 6) & 3];
-    range -= lps;
-    const uint64_t scaled = (uint64_t)range << avail;
-    int bin;
-    if (value < scaled) {
-      bin = (int)(st & 1);
-      state = detail::kTransitions.mps[st];
-      if (range < 256) {
-        range <<= 1;
-        avail--;
-      }
-    } else {
-      value -= scaled;
-      const int n = __builtin_clz(lps) - 23;   // lps in [2,240]: shift until >= 256
-      range = lps << n;
-      avail -= n;
-      bin = (int)((st & 1) ^ 1);
-      state = detail::kTransitions.lps[st];
-    }
+    const uint32_t rmps = range - lps;
+    const uint64_t scaled = (uint64_t)rmps << avail;
+    const uint32_t is_lps = value >= scaled;                 // 0 / 1
+    const uint32_t mask = 0u - is_lps;
+    value -= scaled & (uint64_t)(int64_t)(int32_t)mask;
+    const uint32_t r = rmps + ((lps - rmps) & mask);
+    const int n = __builtin_clz(r) - 23;
+    range = r << n;
+    avail -= n;
+    state = detail::kTransitions.next[st][is_lps];
     refill();
-    return bin;
+    return (int)((st & 1) ^ is_lps);
   }
 
   inline int decode_bypass() {
@@ -215,24 +213,28 @@ struct Cabac {
     return bin;
   }
 
-  // n bypass bins at once: the repeated compare/subtract is a division by the scaled range
+  // n <= 16 bypass bins at once: the repeated compare/subtract of n bypass decodes is the long division
+  // of the top (9 + n) bits of `value` by the range (a 32-bit division); the quotient bits are the bins
   inline uint32_t decode_bypass_bits(int n) {
     uint32_t out = 0;
     while (n > 0) {
       const int k = n > 16 ? 16 : n;
-      if (k <= 2) {
-        for (int i = 0; i < k; i++) out = (out << 1) | (uint32_t)decode_bypass();
-      } else {
-        avail -= k;
-        const uint64_t scaled = (uint64_t)range << avail;
-        const uint64_t q = value / scaled;
-        value -= q * scaled;
-        out = (out << k) | (uint32_t)q;
-        refill();
-      }
+      avail -= k;
+      const uint32_t q = (uint32_t)(value >> avail) / range;
+      value -= (uint64_t)(q * range) << avail;
+      out = (out << k) | q;
+      refill();
       n -= k;
     }
     return out;
+  }
+  // The next 16 bypass bins without consuming them (bit 15 = first bin) ...
+  inline uint32_t peek_bypass16() const { return (uint32_t)(value >> (avail - 16)) / range; }
+  // ... and the commit of the first `n` of them (`bins` = peek >> (16 - n))
+  inline void consume_bypass(int n, uint32_t bins) {
+    avail -= n;
+    value -= (uint64_t)(bins * range) << avail;
+    refill();
   }
 
   inline int decode_terminate() {

@@ -1187,40 +1187,44 @@ uint32_t HevcIntraParser::Impl::residual_coding(int x0, int y0, int log2, int cI
                                       : sig.sb[cIdx ? 1 : 0][log2 == 3 ? (scanIdx == 0 ? 0 : 1) : 2][(Sx | Sy) ? 1 : 0][prevCsbf][scanIdx];
     const int dc_ctx = (ts_ctx || log2 == 2 || i > 0) ? sigtab[0] : (cIdx ? 27 : 0);
 
+    // significant-coefficient flags: positions are written unconditionally and the count advances by the
+    // decoded bin, so the (unpredictable) flag never steers a branch
     int last_coeff = (i == lastSubBlock) ? lastScanPos - 1 : 15;
-    if (i == lastSubBlock) { value[n] = 1; maxbase[n] = 1; spos[n] = (int8_t)lastScanPos; n++; }
+    if (i == lastSubBlock) spos[n++] = (int8_t)lastScanPos;
     for (int k = last_coeff; k > 0; k--) {
-      if (bin(CTX_SIG + sigtab[k])) {
-        value[n] = 1; maxbase[n] = 1; spos[n] = (int8_t)k; n++;
-        inferSbDc = 0;
-      }
+      const int b = bin(CTX_SIG + sigtab[k]);
+      spos[n] = (int8_t)k;
+      n += b;
     }
     if (last_coeff >= 0) {
-      if (!inferSbDc) {
-        if (bin(CTX_SIG + dc_ctx)) { value[n] = 1; maxbase[n] = 1; spos[n] = 0; n++; }
+      if (n > 0 || !inferSbDc) {      // a significant flag was seen (or nothing can be inferred): DC flag is coded
+        const int b = bin(CTX_SIG + dc_ctx);
+        spos[n] = 0;
+        n += b;
       } else {
-        value[n] = 1; maxbase[n] = 1; spos[n] = 0; n++;
+        spos[n++] = 0;                // inferred: the only coefficient of a coded sub-block
       }
     }
     if (n == 0) continue;
 
+    // greater1 / greater2 flags. base[c] = 1 + g1 (+ g2); a coefficient carries coeff_abs_level_remaining when its
+    // base reached what the flags can express: 2 without g2, 3 for the one coefficient that had a g2 flag, 1 past the 8th
     int ctxSet = (i == 0 || cIdx > 0) ? 0 : 2;
     if (c1 == 0) ctxSet++;
     c1 = 1;
-    int firstG1 = -1;
-    int ng1 = std::min(8, n);
+    int firstG1 = 16;
+    const int ng1 = std::min(8, n);
+    const int g1base = CTX_G1 + ctxSet * 4 + (cIdx > 0 ? 16 : 0);
+    static const uint8_t c1next[8] = {0, 0, 2, 0, 3, 0, 3, 0};   // [c1 * 2 + bin]
     for (int c = 0; c < ng1; c++) {
-      int inc = ctxSet * 4 + c1 + (cIdx > 0 ? 16 : 0);
-      if (bin(CTX_G1 + inc)) {
-        value[c]++;
-        c1 = 0;
-        if (firstG1 < 0) firstG1 = c;
-      } else {
-        maxbase[c] = 0;
-        if (c1 < 3 && c1 > 0) c1++;
-      }
+      const int b = bin(g1base + c1);
+      value[c] = (int16_t)(1 + b);
+      maxbase[c] = (uint8_t)b;
+      firstG1 = (b && c < firstG1) ? c : firstG1;
+      c1 = c1next[c1 * 2 + b];
     }
-    if (firstG1 >= 0) {
+    for (int c = ng1; c < n; c++) { value[c] = 1; maxbase[c] = 1; }
+    if (firstG1 < 16) {
       int f = bin(CTX_G2 + ctxSet + (cIdx > 0 ? 4 : 0));
       value[firstG1] += f;
       maxbase[firstG1] = (uint8_t)f;
@@ -1239,11 +1243,23 @@ uint32_t HevcIntraParser::Impl::residual_coding(int x0, int y0, int log2, int cI
       int rem = 0;
       if (maxbase[c]) {
         // coeff_abs_level_remaining (§9.3.3.11): prefix of ones, TR / EGk suffix
-        int prefix = 0;
-        while (prefix < 32 && cabac.decode_bypass()) prefix++;
-        if (prefix >= 32) { error = "coeff_abs_level_remaining prefix too long"; return 0; }
-        if (prefix <= 3) rem = (prefix << rice) + (int)cabac.decode_bypass_bits(rice);
-        else rem = (((1 << (prefix - 3)) + 3 - 1) << rice) + (int)cabac.decode_bypass_bits(prefix - 3 + rice);
+        // fast path: prefix (ones + terminating zero) and suffix inside the next 16 bypass bins
+        const uint32_t q16 = cabac.peek_bypass16();
+        const int ones = q16 == 0xffffu ? 16 : __builtin_clz(~(q16 << 16));
+        const int suffix_len = ones <= 3 ? rice : ones - 3 + rice;
+        const int len = ones + 1 + suffix_len;
+        if (len <= 16) {
+          const uint32_t bins = q16 >> (16 - len);
+          const int suffix = (int)(bins & ((1u << suffix_len) - 1u));
+          rem = ones <= 3 ? (ones << rice) + suffix : (((1 << (ones - 3)) + 3 - 1) << rice) + suffix;
+          cabac.consume_bypass(len, bins);
+        } else {
+          int prefix = 0;
+          while (prefix < 32 && cabac.decode_bypass()) prefix++;
+          if (prefix >= 32) { error = "coeff_abs_level_remaining prefix too long"; return 0; }
+          if (prefix <= 3) rem = (prefix << rice) + (int)cabac.decode_bypass_bits(rice);
+          else rem = (((1 << (prefix - 3)) + 3 - 1) << rice) + (int)cabac.decode_bypass_bits(prefix - 3 + rice);
+        }
         if (base + rem > 3 * (1 << rice)) {
           rice++;
           if (!S->persistent_rice_adaptation_enabled && rice > 4) rice = 4;
