@@ -93,23 +93,34 @@ class ClockSampler:
 
 
 def reference_arm(files, steps, warmup, threads):
-    """The reference's own CPU implementation: heif_decode_image(..., RGB, interleaved_RGB) per file with
-    heif_context_set_threads(ctx, handle, all cores) (grid -> tile threads, heif.cc:499-514)."""
+    """The reference's own CPU implementation on all host cores, two ways, the better one is the value:
+      (a) its own policy: heif_decode_image(..., RGB, interleaved_RGB) per file with
+          heif_context_set_threads(ctx, handle, cores) (grid -> one thread per tile, heif.cc:499-514);
+      (b) process-level data parallelism: `cores` files decoded concurrently, one thread each."""
+    import concurrent.futures as cf
     import refheif as R
     if not R.available():
         return None
     mp = GRID_W * GRID_H / 1e6
-    sample = files[:1]
+    f0 = files[0]
     for _ in range(warmup):
-        R.decode(sample[0], R.COLORSPACE_RGB, R.CHROMA_RGB, threads=threads)
+        R.decode(f0, R.COLORSPACE_RGB, R.CHROMA_RGB, threads=threads)
     t0 = time.perf_counter()
-    n = 0
     for _ in range(steps):
-        for f in sample:
-            R.decode(f, R.COLORSPACE_RGB, R.CHROMA_RGB, threads=threads)
-            n += 1
-    dt = time.perf_counter() - t0
-    return {"value": n * mp / dt, "ms_per_step": dt / steps * 1e3, "sample": "%d x one 12.19 MP grid file per step" % len(sample)}
+        R.decode(f0, R.COLORSPACE_RGB, R.CHROMA_RGB, threads=threads)
+    dt_a = (time.perf_counter() - t0) / steps
+    with cf.ThreadPoolExecutor(max_workers=threads) as pool:   # ctypes releases the GIL inside heif_decode_image
+        def one(_):
+            R.decode(f0, R.COLORSPACE_RGB, R.CHROMA_RGB, threads=1)
+        list(pool.map(one, range(threads)))                    # warm-up
+        t0 = time.perf_counter()
+        n = threads * max(1, min(steps, 2))
+        list(pool.map(one, range(n)))
+        dt_b = (time.perf_counter() - t0) / n
+    best = min(dt_a, dt_b)
+    return {"value": mp / best, "ms_per_step": best * 1e3,
+            "sample": "one 12.19 MP grid file: (a) %d tile threads %.1f MP/s, (b) %d concurrent single-thread decodes %.1f MP/s" % (
+                threads, mp / dt_a, threads, mp / dt_b)}
 
 
 def main():
@@ -272,7 +283,7 @@ def main():
     if rank == 0 and world == 1:
         r = reference_arm(distinct, 2, 1, cores)
         if r is not None:
-            cpu = {"value": r["value"], "unit": UNIT, "cores": cores, "kind": "reference", "sample": "2 x " + r["sample"]}
+            cpu = {"value": r["value"], "unit": UNIT, "cores": cores, "kind": "reference", "sample": r["sample"]}
         else:
             cpu = {"value": None, "unit": UNIT, "cores": cores, "kind": "reference", "sample": "oracle/_ref missing on this box"}
 
