@@ -295,7 +295,7 @@ int hc_batch_upload(hc_batch* b) {
     n_tasks += (size_t)ncomp * p.ctbs_h;
     b->max_planes = std::max(b->max_planes, ncomp);
     b->max_dbk_units = std::max(b->max_dbk_units, (long long)(p.width >> 3) * (p.height >> 2));
-    b->max_sao_quads = std::max(b->max_sao_quads, (long long)((p.width + 7) >> 3) * p.height);
+    b->max_sao_quads = std::max(b->max_sao_quads, ((long long)p.ctbs_w * p.ctbs_h) << std::max(0, 2 * p.log2_ctb - 8));
     // reconstruction planes
     const int ps = (p.bit_depth_y == 8 && p.bit_depth_c == 8) ? 1 : 2;
     const int SubW = (p.chroma_format == 1 || p.chroma_format == 2) ? 2 : 1, SubH = p.chroma_format == 1 ? 2 : 1;
@@ -474,13 +474,13 @@ int hc_batch_convert(hc_batch* b, int canvas, const hc_csc_params* params) {
     return HC_ERR_UNSUPPORTED;
   }
   c.rgb_bpp = bpp_of[params->out_format];
-  c.rgb_stride = align_up((size_t)((c.w + 3) & ~3) * c.rgb_bpp, 256);
+  c.rgb_stride = align_up((size_t)((c.w + 7) & ~7) * c.rgb_bpp, 256);
   // lay all canvases' rgb buffers out in one block (grow if needed)
   size_t total = 0;
   for (auto& cv : b->canvases) {
     const int bp = &cv == &c ? c.rgb_bpp : (cv.rgb_bpp ? cv.rgb_bpp : (cv.bit_depth == 8 ? 4 : 8));
     cv.rgb_off = total;
-    total += align_up(align_up((size_t)((cv.w + 3) & ~3) * bp, 256) * cv.h, 256);
+    total += align_up(align_up((size_t)((cv.w + 7) & ~7) * bp, 256) * cv.h, 256);
   }
   if (b->d_rgb.cap < total) {
     bool any = false;

@@ -13,8 +13,8 @@
 //
 // Mapping: one thread per 8 horizontally adjacent samples (8-aligned, so a unit never straddles a
 // CTB: CTBs are >= 8 samples wide in every component); the unit's row and, for the edge classes,
-// the rows above / below are fetched with one 8- or 16-byte load each, the per-CTB parameters once
-// per thread. A warp covers 256 consecutive samples of a row.
+// the rows above / below are fetched with one 8- or 16-byte load each. A warp covers a
+// (CTB width) x (256 / CTB width) patch of ONE CTB, so SAO type, class and offsets are warp-uniform.
 // Algorithmic bytes: read s + write s per sample (neighbour rows hit L1/L2).
 #include "launch.h"
 
@@ -49,19 +49,29 @@ HC_D void store8(uint16_t* p, const int v[8]) {
 }
 
 template <typename Pixel>
-__device__ void sao_picture(const BatchView& bv, const hc_pic& pic, int c, long long tid) {
-  const int SubW = (c && (pic.chroma_format == 1 || pic.chroma_format == 2)) ? 2 : 1;
-  const int SubH = (c && pic.chroma_format == 1) ? 2 : 1;
-  const int width = pic.width / SubW, height = pic.height / SubH;  // coded plane size (multiples of 4)
-  const int nu = (width + 7) >> 3;
-  if (tid >= (long long)nu * height) return;
-  const int y = (int)(tid / nu), x0 = (int)(tid - (long long)y * nu) << 3;
+__device__ void sao_picture(const BatchView& bv, const hc_pic& pic, int c, unsigned warp_index, int lane) {
+  const int sw = (c && (pic.chroma_format == 1 || pic.chroma_format == 2)) ? 1 : 0;   // log2 subsampling
+  const int sh = (c && pic.chroma_format == 1) ? 1 : 0;
+  const int SubW = 1 << sw, SubH = 1 << sh;
+  const int width = pic.width >> sw, height = pic.height >> sh;  // coded plane size (multiples of 4)
+  const int log2w = pic.log2_ctb - sw, log2h = pic.log2_ctb - sh;
+  // a warp covers (CTB width / 8) units x (256 / CTB width) rows of ONE CTB, so the SAO type / class /
+  // offsets are warp-uniform and only the CTB-border handling differs between lanes
+  const int lu = log2w - 3;                          // log2 units per CTB row (0..3)
+  const int rows = 32 >> lu;                         // rows per warp
+  const unsigned wpc = (unsigned)((1 << log2h) + rows - 1) / (unsigned)rows;   // warps per CTB
+  const unsigned ctb = warp_index / wpc, part = warp_index - ctb * wpc;
+  if (ctb >= (unsigned)pic.ctbs_w * pic.ctbs_h) return;
+  const int ctby = (int)(ctb / pic.ctbs_w), ctbx = (int)(ctb - (unsigned)ctby * pic.ctbs_w);
+  const int x0 = (ctbx << log2w) + ((lane & ((1 << lu) - 1)) << 3);
+  const int y = (ctby << log2h) + (int)part * rows + (lane >> lu);
+  if (x0 >= width || y >= height || (y >> log2h) != ctby) return;
 
   // crop window and destination clip, in samples of this plane (context.cc:2467-2497)
-  const int cx0 = pic.crop_x / SubW, cy0 = pic.crop_y / SubH;
-  const int cw = (pic.crop_w + SubW - 1) / SubW, ch = (pic.crop_h + SubH - 1) / SubH;
-  const int dx0 = (pic.dst_x + SubW - 1) / SubW, dy0 = (pic.dst_y + SubH - 1) / SubH;
-  const int dw = (pic.dst_w + SubW - 1) / SubW, dh = (pic.dst_h + SubH - 1) / SubH;
+  const int cx0 = pic.crop_x >> sw, cy0 = pic.crop_y >> sh;
+  const int cw = (pic.crop_w + SubW - 1) >> sw, ch = (pic.crop_h + SubH - 1) >> sh;
+  const int dx0 = (pic.dst_x + SubW - 1) >> sw, dy0 = (pic.dst_y + SubH - 1) >> sh;
+  const int dw = (pic.dst_w + SubW - 1) >> sw, dh = (pic.dst_h + SubH - 1) >> sh;
   const int copy_w = min(cw, dw - dx0), copy_h = min(ch, dh - dy0);
   const int oy = y - cy0;
   if (oy < 0 || oy >= copy_h) return;
@@ -74,8 +84,6 @@ __device__ void sao_picture(const BatchView& bv, const hc_pic& pic, int c, long 
   const int dstride = (int)pic.dst_stride[c];
   const int bit_depth = c == 0 ? pic.bit_depth_y : pic.bit_depth_c;
   const int maxv = (1 << bit_depth) - 1;
-  const int log2w = pic.log2_ctb - (SubW == 2), log2h = pic.log2_ctb - (SubH == 2);
-  const int ctbx = x0 >> log2w, ctby = y >> log2h;
   const hc_ctu& ctu = bv.ctus[pic.ctu_base + ctbx + ctby * pic.ctbs_w];
   const int nvalid = min(8, width - x0);            // 4 or 8
 
@@ -144,38 +152,55 @@ __device__ void sao_picture(const BatchView& bv, const hc_pic& pic, int c, long 
       }
       const unsigned nb = c ? ctu.sao_nb_c : ctu.sao_nb;
       const bool self_quirk = c && (ctu.flags & HC_CTU_SAO_C_SELF);
-      const int lwid = min(1 << log2w, width - (ctbx << log2w)), lhei = min(1 << log2h, height - (ctby << log2h));
-      const int ly = y & ((1 << log2h) - 1);
+      const int mw = (1 << log2w) - 1, mh = (1 << log2h) - 1;
       const int orig[8] = {v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]};
+      // offsets for edgeIdx -2,-1,(0),1,2 packed as bytes (sao.cc:312-317)
+      const unsigned long long packed = (unsigned long long)(uint8_t)o0 | ((unsigned long long)(uint8_t)o1 << 8) |
+                                        ((unsigned long long)(uint8_t)o2 << 24) | ((unsigned long long)(uint8_t)o3 << 32);
+      // interior unit: no sample's neighbour leaves the CTB (or the picture) in the direction of this class
+      const bool in_x = hx == 0 || ((x0 & mw) != 0 && ((x0 + 8) & mw) != 0 && x0 + 8 < width);
+      const bool in_y = vy == 0 || ((y & mh) != 0 && ((y + 1) & mh) != 0 && y + 1 < height);
+      if (nvalid == 8 && skip == 0 && in_x && in_y && !self_quirk) {
 #pragma unroll
-      for (int k = 0; k < 8; k++) {
-        if (k >= nvalid || ((skip >> k) & 1)) continue;
-        const int x = x0 + k;
-        bool ok = true;
-#pragma unroll
-        for (int n = 0; n < 2; n++) {
-          const int xs = n == 0 ? x + hx : x - hx, ys = n == 0 ? y + vy : y - vy;
-          if (xs < 0 || ys < 0 || xs >= width || ys >= height) { ok = false; continue; }
-          const int dxc = (xs >> log2w) - ctbx, dyc = (ys >> log2h) - ctby;
-          if (dxc | dyc) {
-            int bit;
-            if (dyc == 0) bit = dxc < 0 ? HC_NB_L : HC_NB_R;
-            else if (dxc == 0) bit = dyc < 0 ? HC_NB_T : HC_NB_B;
-            else if (dyc < 0) bit = dxc < 0 ? HC_NB_TL : HC_NB_TR;
-            else bit = dxc < 0 ? HC_NB_BL : HC_NB_BR;
-            if (!(nb & bit)) ok = false;
-          } else if (self_quirk) {
-            // reference quirk (sao.cc:283): border samples of this CTB also lose their in-CTB neighbours
-            const int lx = x & ((1 << log2w) - 1);
-            if (lx == 0 || ly == 0 || lx == lwid - 1 || ly == lhei - 1) ok = false;
-          }
+        for (int k = 0; k < 8; k++) {
+          const int a = hx < 0 ? ra[k] : (hx == 0 ? ra[k + 1] : ra[k + 2]);
+          const int b = hx < 0 ? rb[k + 2] : (hx == 0 ? rb[k + 1] : rb[k]);
+          const int e = sign3(orig[k] - a) + sign3(orig[k] - b);
+          const int off = (int)(int8_t)(packed >> (8 * (e + 2)));
+          v[k] = clip3i(0, maxv, orig[k] + off);
         }
-        if (!ok) continue;
-        const int a = hx < 0 ? ra[k] : (hx == 0 ? ra[k + 1] : ra[k + 2]);
-        const int b = hx < 0 ? rb[k + 2] : (hx == 0 ? rb[k + 1] : rb[k]);
-        const int e = sign3(orig[k] - a) + sign3(orig[k] - b);   // -2..2
-        // edgeIdx -2,-1,1,2 -> offsets 0,1,2,3 (sao.cc:312-317)
-        if (e) v[k] = clip3i(0, maxv, orig[k] + (e == -2 ? o0 : e == -1 ? o1 : e == 1 ? o2 : o3));
+      } else {
+        const int lwid = min(1 << log2w, width - (ctbx << log2w)), lhei = min(1 << log2h, height - (ctby << log2h));
+        const int ly = y & mh;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+          if (k >= nvalid || ((skip >> k) & 1)) continue;
+          const int x = x0 + k;
+          bool ok = true;
+#pragma unroll
+          for (int n = 0; n < 2; n++) {
+            const int xs = n == 0 ? x + hx : x - hx, ys = n == 0 ? y + vy : y - vy;
+            if (xs < 0 || ys < 0 || xs >= width || ys >= height) { ok = false; continue; }
+            const int dxc = (xs >> log2w) - ctbx, dyc = (ys >> log2h) - ctby;
+            if (dxc | dyc) {
+              int bit;
+              if (dyc == 0) bit = dxc < 0 ? HC_NB_L : HC_NB_R;
+              else if (dxc == 0) bit = dyc < 0 ? HC_NB_T : HC_NB_B;
+              else if (dyc < 0) bit = dxc < 0 ? HC_NB_TL : HC_NB_TR;
+              else bit = dxc < 0 ? HC_NB_BL : HC_NB_BR;
+              if (!(nb & bit)) ok = false;
+            } else if (self_quirk) {
+              // reference quirk (sao.cc:283): border samples of this CTB also lose their in-CTB neighbours
+              const int lx = x & mw;
+              if (lx == 0 || ly == 0 || lx == lwid - 1 || ly == lhei - 1) ok = false;
+            }
+          }
+          if (!ok) continue;
+          const int a = hx < 0 ? ra[k] : (hx == 0 ? ra[k + 1] : ra[k + 2]);
+          const int b = hx < 0 ? rb[k + 2] : (hx == 0 ? rb[k + 1] : rb[k]);
+          const int e = sign3(orig[k] - a) + sign3(orig[k] - b);   // -2..2
+          if (e) v[k] = clip3i(0, maxv, orig[k] + (e == -2 ? o0 : e == -1 ? o1 : e == 1 ? o2 : o3));
+        }
       }
     }
   }
@@ -204,15 +229,16 @@ __global__ void __launch_bounds__(256) k4_sao_kernel(BatchView bv) {
   const int c = blockIdx.z;
   if (c > 0 && pic.chroma_format == 0) return;
   if (pic.dst_flags & (HC_DST_SKIP_Y << c)) return;   // component not wanted at the destination
-  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (pic.bit_depth_y == 8 && pic.bit_depth_c == 8) sao_picture<uint8_t>(bv, pic, c, tid);
-  else sao_picture<uint16_t>(bv, pic, c, tid);
+  const unsigned warp_index = blockIdx.x * 8u + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (pic.bit_depth_y == 8 && pic.bit_depth_c == 8) sao_picture<uint8_t>(bv, pic, c, warp_index, lane);
+  else sao_picture<uint16_t>(bv, pic, c, warp_index, lane);
 }
 
-// max_units = max over pictures of ceil(width/8)*height
-void launch_k4(const BatchView& bv, long long max_units, int planes, cudaStream_t stream) {
-  if (max_units <= 0 || bv.npics <= 0) return;
-  dim3 grid((unsigned)((max_units + 255) / 256), (unsigned)bv.npics, (unsigned)planes);
+// max_warps = max over pictures of (number of CTBs) * (CTB area / 256): one warp per 256 luma samples of a CTB
+void launch_k4(const BatchView& bv, long long max_warps, int planes, cudaStream_t stream) {
+  if (max_warps <= 0 || bv.npics <= 0) return;
+  dim3 grid((unsigned)((max_warps + 7) / 8), (unsigned)bv.npics, (unsigned)planes);
   k4_sao_kernel<<<grid, 256, 0, stream>>>(bv);
 }
 

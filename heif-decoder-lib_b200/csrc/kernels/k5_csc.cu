@@ -13,8 +13,8 @@
 // Float arithmetic uses explicit round-to-nearest mul/add (no FMA contraction) and the
 // reference's (long)(x + 0.5f) rounding (common_utils.h:64-70) so results are bit-exact.
 //
-// Mapping: one thread converts 4 horizontally adjacent pixels and writes them with 32-bit / 128-bit
-// stores; a warp writes 384 (RGB) .. 1024 (RRGGBBAA) contiguous bytes. Pure streaming:
+// Mapping: one thread converts 8 horizontally adjacent pixels (8/16-byte plane loads) and writes them
+// with 64-bit / 128-bit stores; a warp writes 768 (RGB) .. 2048 (RRGGBBAA) contiguous bytes. Pure streaming:
 // algorithmic bytes = s*c (+s alpha) read + bytes-per-pixel written.
 #include "launch.h"
 
@@ -62,47 +62,117 @@ __device__ void convert_px(const CscArgs& a, int yv, int cbv, int crv, int& r, i
 }
 
 template <typename Pixel>
+HC_D void load_px8(const Pixel* p, int n, int v[8]);
+template <>
+HC_D void load_px8<uint8_t>(const uint8_t* p, int n, int v[8]) {
+  if (n == 8 && (reinterpret_cast<uintptr_t>(p) & 7) == 0) {
+    const uint2 w = *reinterpret_cast<const uint2*>(p);
+#pragma unroll
+    for (int k = 0; k < 4; k++) { v[k] = (w.x >> (8 * k)) & 0xff; v[4 + k] = (w.y >> (8 * k)) & 0xff; }
+  } else {
+#pragma unroll
+    for (int k = 0; k < 8; k++) v[k] = k < n ? (int)p[k] : 0;
+  }
+}
+template <>
+HC_D void load_px8<uint16_t>(const uint16_t* p, int n, int v[8]) {
+  if (n == 8 && (reinterpret_cast<uintptr_t>(p) & 15) == 0) {
+    const uint4 w = *reinterpret_cast<const uint4*>(p);
+    v[0] = w.x & 0xffff; v[1] = w.x >> 16; v[2] = w.y & 0xffff; v[3] = w.y >> 16;
+    v[4] = w.z & 0xffff; v[5] = w.z >> 16; v[6] = w.w & 0xffff; v[7] = w.w >> 16;
+  } else {
+#pragma unroll
+    for (int k = 0; k < 8; k++) v[k] = k < n ? (int)p[k] : 0;
+  }
+}
+
+template <typename Pixel>
+HC_D void load_px4(const Pixel* p, int n, int fill, int v[8]) {
+  constexpr int PS = (int)sizeof(Pixel);
+  if (n == 4 && (reinterpret_cast<uintptr_t>(p) & (4 * PS - 1)) == 0) {
+    if (PS == 1) {
+      const uint32_t w = *reinterpret_cast<const uint32_t*>(p);
+#pragma unroll
+      for (int k = 0; k < 4; k++) v[k] = (w >> (8 * k)) & 0xff;
+    } else {
+      const uint2 w = *reinterpret_cast<const uint2*>(p);
+      v[0] = w.x & 0xffff; v[1] = w.x >> 16; v[2] = w.y & 0xffff; v[3] = w.y >> 16;
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < 4; k++) v[k] = k < n ? (int)p[k] : fill;
+  }
+}
+
+// One thread converts 8 horizontally adjacent pixels: 8/16-byte plane loads, 8/16-byte interleaved stores
+// (24 .. 64 bytes per thread, contiguous across the warp). Output rows are padded to a multiple of 8 pixels.
+template <typename Pixel>
 __global__ void __launch_bounds__(256) k5_csc_kernel(CscArgs a) {
-  const int nq = (a.width + 3) >> 2;
-  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (tid >= (long long)nq * a.height) return;
-  const int y = (int)(tid / nq), x0 = (int)(tid % nq) << 2;
+  const unsigned nq = (unsigned)(a.width + 7) >> 3;
+  const unsigned tid = blockIdx.x * blockDim.x + threadIdx.x;
+  if (tid >= nq * (unsigned)a.height) return;
+  const int y = (int)(tid / nq), x0 = (int)(tid - (unsigned)y * nq) << 3;
+  const int n = min(8, a.width - x0);
   const int shiftH = (a.chroma_format == 1 || a.chroma_format == 2) ? 1 : 0;
   const int shiftV = a.chroma_format == 1 ? 1 : 0;
-  const Pixel* __restrict__ py = reinterpret_cast<const Pixel*>(a.y) + (size_t)y * a.y_stride;
-  const Pixel* __restrict__ pcb = a.chroma_format ? reinterpret_cast<const Pixel*>(a.cb) + (size_t)(y >> shiftV) * a.c_stride : nullptr;
-  const Pixel* __restrict__ pcr = a.chroma_format ? reinterpret_cast<const Pixel*>(a.cr) + (size_t)(y >> shiftV) * a.c_stride : nullptr;
-  const Pixel* __restrict__ pa = a.a ? reinterpret_cast<const Pixel*>(a.a) + (size_t)y * a.a_stride : nullptr;
   const int bpp = a.p.bit_depth;
   const int fmt = a.p.out_format;
   const int half = 1 << (bpp - 1);
 
-  int R[4], G[4], B[4], A[4];
+  int Y[8], Cb[8], Cr[8], A[8];
+  load_px8<Pixel>(reinterpret_cast<const Pixel*>(a.y) + (size_t)y * a.y_stride + x0, n, Y);
+  if (a.chroma_format) {
+    const size_t coff = (size_t)(y >> shiftV) * a.c_stride + (x0 >> shiftH);
+    int cb[8], cr[8];
+    const int nc = shiftH ? (n + 1) >> 1 : n;
+    if (shiftH) {
+      // 4 (or fewer) chroma samples cover the 8 pixels: nearest neighbour, cx = x >> 1 (yuv2rgb.cc:173-174)
+      load_px4<Pixel>(reinterpret_cast<const Pixel*>(a.cb) + coff, nc, half, cb);
+      load_px4<Pixel>(reinterpret_cast<const Pixel*>(a.cr) + coff, nc, half, cr);
 #pragma unroll
-  for (int k = 0; k < 4; k++) {
-    const int x = x0 + k;
-    const int yv = py[x];
-    int cbv = half, crv = half;
-    if (a.chroma_format) { cbv = pcb[x >> shiftH]; crv = pcr[x >> shiftH]; }
-    if (a.chroma_format) convert_px<Pixel>(a, yv, cbv, crv, R[k], G[k], B[k]);
-    else { R[k] = G[k] = B[k] = yv; }
-    A[k] = pa ? (int)pa[x] : ((1 << bpp) - 1);
+      for (int k = 0; k < 8; k++) { Cb[k] = cb[k >> 1]; Cr[k] = cr[k >> 1]; }
+    } else {
+      load_px8<Pixel>(reinterpret_cast<const Pixel*>(a.cb) + coff, n, Cb);
+      load_px8<Pixel>(reinterpret_cast<const Pixel*>(a.cr) + coff, n, Cr);
+    }
+  }
+  if (a.a) load_px8<Pixel>(reinterpret_cast<const Pixel*>(a.a) + (size_t)y * a.a_stride + x0, n, A);
+  else {
+#pragma unroll
+    for (int k = 0; k < 8; k++) A[k] = (1 << bpp) - 1;
+  }
+
+  int R[8], G[8], B[8];
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    if (a.chroma_format) convert_px<Pixel>(a, Y[k], Cb[k], Cr[k], R[k], G[k], B[k]);
+    else { R[k] = G[k] = B[k] = Y[k]; }
   }
 
   uint8_t* orow = a.out + (size_t)y * a.out_stride;
   if (fmt == HC_OUT_RGB) {
-    uint32_t w0 = R[0] | (G[0] << 8) | (B[0] << 16) | (R[1] << 24);
-    uint32_t w1 = G[1] | (B[1] << 8) | (R[2] << 16) | (G[2] << 24);
-    uint32_t w2 = B[2] | (R[3] << 8) | (G[3] << 16) | (B[3] << 24);
-    uint32_t* o = reinterpret_cast<uint32_t*>(orow + (size_t)x0 * 3);
-    o[0] = w0; o[1] = w1; o[2] = w2;
+    uint32_t w[6];
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+      const int k = 4 * h;
+      w[3 * h + 0] = R[k] | (G[k] << 8) | (B[k] << 16) | (R[k + 1] << 24);
+      w[3 * h + 1] = G[k + 1] | (B[k + 1] << 8) | (R[k + 2] << 16) | (G[k + 2] << 24);
+      w[3 * h + 2] = B[k + 2] | (R[k + 3] << 8) | (G[k + 3] << 16) | (B[k + 3] << 24);
+    }
+    uint2* o = reinterpret_cast<uint2*>(orow + (size_t)x0 * 3);   // x0 * 3 is a multiple of 8
+    o[0] = make_uint2(w[0], w[1]); o[1] = make_uint2(w[2], w[3]); o[2] = make_uint2(w[4], w[5]);
   } else if (fmt == HC_OUT_RGBA) {
-    uint4 v;
-    v.x = R[0] | (G[0] << 8) | (B[0] << 16) | ((uint32_t)A[0] << 24);
-    v.y = R[1] | (G[1] << 8) | (B[1] << 16) | ((uint32_t)A[1] << 24);
-    v.z = R[2] | (G[2] << 8) | (B[2] << 16) | ((uint32_t)A[2] << 24);
-    v.w = R[3] | (G[3] << 8) | (B[3] << 16) | ((uint32_t)A[3] << 24);
-    *reinterpret_cast<uint4*>(orow + (size_t)x0 * 4) = v;
+    uint4* o = reinterpret_cast<uint4*>(orow + (size_t)x0 * 4);
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+      const int k = 4 * h;
+      uint4 v;
+      v.x = R[k] | (G[k] << 8) | (B[k] << 16) | ((uint32_t)A[k] << 24);
+      v.y = R[k + 1] | (G[k + 1] << 8) | (B[k + 1] << 16) | ((uint32_t)A[k + 1] << 24);
+      v.z = R[k + 2] | (G[k + 2] << 8) | (B[k + 2] << 16) | ((uint32_t)A[k + 2] << 24);
+      v.w = R[k + 3] | (G[k + 3] << 8) | (B[k + 3] << 16) | ((uint32_t)A[k + 3] << 24);
+      o[h] = v;
+    }
   } else {
     const bool le = (fmt == HC_OUT_RRGGBB_LE || fmt == HC_OUT_RRGGBBAA_LE);
     const bool alpha = (fmt == HC_OUT_RRGGBBAA_BE || fmt == HC_OUT_RRGGBBAA_LE);
@@ -110,7 +180,7 @@ __global__ void __launch_bounds__(256) k5_csc_kernel(CscArgs a) {
     if (alpha) {
       uint4* o = reinterpret_cast<uint4*>(orow + (size_t)x0 * 8);
 #pragma unroll
-      for (int k = 0; k < 2; k++) {
+      for (int k = 0; k < 4; k++) {
         uint4 v;
         v.x = h16(R[2 * k]) | (h16(G[2 * k]) << 16);
         v.y = h16(B[2 * k]) | (h16(A[2 * k]) << 16);
@@ -119,19 +189,22 @@ __global__ void __launch_bounds__(256) k5_csc_kernel(CscArgs a) {
         o[k] = v;
       }
     } else {
-      uint32_t* o = reinterpret_cast<uint32_t*>(orow + (size_t)x0 * 6);
-      o[0] = h16(R[0]) | (h16(G[0]) << 16);
-      o[1] = h16(B[0]) | (h16(R[1]) << 16);
-      o[2] = h16(G[1]) | (h16(B[1]) << 16);
-      o[3] = h16(R[2]) | (h16(G[2]) << 16);
-      o[4] = h16(B[2]) | (h16(R[3]) << 16);
-      o[5] = h16(G[3]) | (h16(B[3]) << 16);
+      uint32_t w[12];
+#pragma unroll
+      for (int h = 0; h < 4; h++) {
+        const int k = 2 * h;
+        w[3 * h + 0] = h16(R[k]) | (h16(G[k]) << 16);
+        w[3 * h + 1] = h16(B[k]) | (h16(R[k + 1]) << 16);
+        w[3 * h + 2] = h16(G[k + 1]) | (h16(B[k + 1]) << 16);
+      }
+      uint4* o = reinterpret_cast<uint4*>(orow + (size_t)x0 * 6);   // x0 * 6 is a multiple of 16
+      o[0] = make_uint4(w[0], w[1], w[2], w[3]); o[1] = make_uint4(w[4], w[5], w[6], w[7]); o[2] = make_uint4(w[8], w[9], w[10], w[11]);
     }
   }
 }
 
 void launch_k5(const CscArgs& a, bool sixteen_bit, cudaStream_t stream) {
-  const long long n = (long long)((a.width + 3) >> 2) * a.height;
+  const long long n = (long long)((a.width + 7) >> 3) * a.height;
   if (n <= 0) return;
   const unsigned grid = (unsigned)((n + 255) / 256);
   if (sixteen_bit) k5_csc_kernel<uint16_t><<<grid, 256, 0, stream>>>(a);
