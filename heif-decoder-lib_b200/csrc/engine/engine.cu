@@ -558,6 +558,16 @@ int hc_batch_read_rgb(hc_batch* b, int canvas, void* dst, size_t dst_stride) {
   return HC_OK;
 }
 
+int hc_batch_copy_rgb_device(hc_batch* b, int canvas, void* dst, size_t dst_stride) {
+  if (!b || !dst || canvas < 0 || canvas >= (int)b->canvases.size()) { hc::set_last_error("hc_batch_copy_rgb_device: bad argument"); return HC_ERR_ARGUMENT; }
+  const Canvas& c = b->canvases[canvas];
+  if (!c.converted) { hc::set_last_error("canvas was not converted"); return HC_ERR_ARGUMENT; }
+  cudaError_t e = cudaMemcpy2DAsync(dst, dst_stride, (const uint8_t*)b->d_rgb.p + c.rgb_off, c.rgb_stride, (size_t)c.w * c.rgb_bpp, c.h,
+                                    cudaMemcpyDeviceToDevice, b->stream);
+  if (!cuda_ok(e, "cudaMemcpy2DAsync(D2D rgb)")) return HC_ERR_CUDA;
+  return cuda_ok(cudaStreamSynchronize(b->stream), "cudaStreamSynchronize") ? HC_OK : HC_ERR_CUDA;
+}
+
 int hc_batch_read_rgb_async(hc_batch* b, int canvas, void* dst, size_t dst_stride) {
   if (!b || !dst || canvas < 0 || canvas >= (int)b->canvases.size()) { hc::set_last_error("hc_batch_read_rgb_async: bad argument"); return HC_ERR_ARGUMENT; }
   const Canvas& c = b->canvases[canvas];

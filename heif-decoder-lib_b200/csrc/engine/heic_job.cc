@@ -29,6 +29,9 @@ struct ImagePlan {
   hc_heif_image_info info{};
   std::vector<int> tiles;   // indices into items (1 for a single image)
   int alpha = -1;           // index into items
+  int band_first_row = 0;   // first tile row of a banded grid decode (multi-GPU, config C5)
+  int band_y0 = 0;          // first output row of the band
+  int full_height = 0;      // height of the whole image
   int canvas = -1;
   hc_image_desc desc{};
   hc_csc_params csc{};
@@ -54,8 +57,11 @@ void hc_heic_job_destroy(hc_heic_job* j) {
   delete j;
 }
 
-hc_heic_job* hc_heic_job_create(hc_engine* e, int nfiles, const uint8_t* const* data, const size_t* sizes,
-                                int want_alpha, int threads) {
+}  // extern "C"
+
+// band_begin/band_end: tile rows [begin, end) of a grid image to decode (band_end < 0: everything)
+static hc_heic_job* job_create(hc_engine* e, int nfiles, const uint8_t* const* data, const size_t* sizes,
+                               int want_alpha, int threads, int band_begin, int band_end) {
   if (!e || nfiles <= 0 || !data || !sizes) {
     hc::set_last_error("hc_heic_job_create: bad argument");
     return nullptr;
@@ -96,9 +102,17 @@ hc_heic_job* hc_heic_job_create(hc_engine* e, int nfiles, const uint8_t* const* 
       im.info.is_grid = 1;
       im.info.rows = g.rows; im.info.cols = g.cols; im.info.width = g.out_w; im.info.height = g.out_h;
       ids = g.tiles;
+      if (band_end >= 0) {
+        if (band_begin < 0 || band_begin >= band_end || band_end > g.rows) { hc::set_last_error("tile row band outside the grid"); return nullptr; }
+        ids.assign(g.tiles.begin() + (size_t)band_begin * g.cols, g.tiles.begin() + (size_t)band_end * g.cols);
+        im.band_first_row = band_begin;
+        im.info.rows = band_end - band_begin;
+      }
     } else {
+      if (band_end >= 0) { hc::set_last_error("a tile row band needs a grid image"); return nullptr; }
       ids.push_back(id);
     }
+    if (band_end >= 0 && im.info.alpha_id) { hc::set_last_error("banded decode of images with an alpha plane is not supported"); return nullptr; }
     for (uint32_t t : ids) {
       im.tiles.push_back((int)j->items.size());
       j->items.emplace_back();
@@ -155,6 +169,12 @@ hc_heic_job* hc_heic_job_create(hc_engine* e, int nfiles, const uint8_t* const* 
     const bool has_alpha = im.alpha >= 0;
     int W = im.info.width, H = im.info.height;
     if (!im.info.is_grid) { W = p0.crop_w; H = p0.crop_h; }   // decoded size, like the reference
+    im.full_height = H;
+    if (im.info.is_grid && band_end >= 0) {                     // this job owns output rows [y0, y0 + H)
+      im.band_y0 = im.band_first_row * p0.crop_h;
+      if (im.band_y0 >= H) { hc::set_last_error("tile row band lies below the output image"); return nullptr; }
+      H = std::min(H, band_end * p0.crop_h) - im.band_y0;
+    }
     im.canvas = hc_batch_add_canvas(j->batch, W, H, p0.chroma_format, p0.bit_depth_y, has_alpha);
     if (im.canvas < 0) return nullptr;
     int matrix, primaries, full;
@@ -199,6 +219,27 @@ hc_heic_job* hc_heic_job_create(hc_engine* e, int nfiles, const uint8_t* const* 
     im.desc.coded_pictures = (int)im.tiles.size() + (has_alpha ? 1 : 0);
   }
   return j.release();
+}
+
+extern "C" {
+
+hc_heic_job* hc_heic_job_create(hc_engine* e, int nfiles, const uint8_t* const* data, const size_t* sizes,
+                                int want_alpha, int threads) {
+  return job_create(e, nfiles, data, sizes, want_alpha, threads, 0, -1);
+}
+
+hc_heic_job* hc_heic_job_create_band(hc_engine* e, const uint8_t* data, size_t size, int want_alpha, int threads,
+                                     int tile_row_begin, int tile_row_end, int* first_output_row, int* full_height) {
+  if (tile_row_end < 0) { hc::set_last_error("hc_heic_job_create_band: bad band"); return nullptr; }
+  hc_heic_job* j = job_create(e, 1, &data, &size, want_alpha, threads, tile_row_begin, tile_row_end);
+  if (j && first_output_row) *first_output_row = j->images[0].band_y0;
+  if (j && full_height) *full_height = j->images[0].full_height;
+  return j;
+}
+
+int hc_heic_job_copy_rgb_device(hc_heic_job* j, int image, void* device_dst, size_t dst_stride_bytes) {
+  if (!j || image < 0 || image >= (int)j->images.size()) { hc::set_last_error("hc_heic_job_copy_rgb_device: bad argument"); return HC_ERR_ARGUMENT; }
+  return hc_batch_copy_rgb_device(j->batch, j->images[image].canvas, device_dst, dst_stride_bytes);
 }
 
 int hc_heic_job_image_count(const hc_heic_job* j) { return j ? (int)j->images.size() : 0; }

@@ -103,6 +103,7 @@ SYMBOLS = [
     ("hc_batch_read_plane", _i, [_vp, _i, _i, _vp, _sz]),
     ("hc_batch_read_rgb", _i, [_vp, _i, _vp, _sz]),
     ("hc_batch_read_rgb_async", _i, [_vp, _i, _vp, _sz]),
+    ("hc_batch_copy_rgb_device", _i, [_vp, _i, _vp, _sz]),
     ("hc_batch_read_residual", _i, [_vp, _i, _vp, _sz]),
     ("hc_batch_stage_ms", _i, [_vp, C.POINTER(C.c_float)]),
     ("hc_batch_timer_start", _i, [_vp]),
@@ -110,6 +111,8 @@ SYMBOLS = [
     ("hc_batch_launch_count", _i, [_vp]),
     ("hc_batch_upload_bytes", _sz, [_vp]),
     ("hc_heic_job_create", _vp, [_vp, _i, C.POINTER(C.c_char_p), C.POINTER(_sz), _i, _i]),
+    ("hc_heic_job_create_band", _vp, [_vp, C.c_char_p, _sz, _i, _i, _i, _i, C.POINTER(_i), C.POINTER(_i)]),
+    ("hc_heic_job_copy_rgb_device", _i, [_vp, _i, _vp, _sz]),
     ("hc_heic_job_destroy", None, [_vp]),
     ("hc_heic_job_image_count", _i, [_vp]),
     ("hc_heic_job_image_desc", _i, [_vp, _i, C.POINTER(ImageDesc)]),

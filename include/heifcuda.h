@@ -179,6 +179,7 @@ int hc_batch_sync(hc_batch* b);
  * 2 bytes little-endian otherwise. */
 int hc_batch_read_plane(hc_batch* b, int canvas, int plane, void* dst, size_t dst_stride_bytes);
 int hc_batch_read_rgb(hc_batch* b, int canvas, void* dst, size_t dst_stride_bytes);
+int hc_batch_copy_rgb_device(hc_batch* b, int canvas, void* device_dst, size_t dst_stride_bytes);
 /* same copy without the final synchronisation (dst should be pinned); pair with hc_batch_sync */
 int hc_batch_read_rgb_async(hc_batch* b, int canvas, void* dst, size_t dst_stride_bytes);
 /* residuals of picture `pic` as produced by K1 (resid_count int16) — used by the parity tests */
@@ -220,6 +221,16 @@ typedef struct hc_image_desc {
  * want_alpha: 0 -> interleaved RGB / RRGGBB_LE, 1 -> RGBA / RRGGBBAA_LE. */
 hc_heic_job* hc_heic_job_create(hc_engine* e, int nfiles, const uint8_t* const* data, const size_t* sizes,
                                 int want_alpha, int threads);
+/* Multi-GPU decode of ONE huge grid image (BASELINE config C5): every GPU decodes a band of tile rows
+ * [tile_row_begin, tile_row_end) of the primary grid image; the job's single output image is that band
+ * (desc.height = band height). *first_output_row / *full_height place the band in the whole picture; the
+ * caller stitches the bands into the owner GPU's buffer with peer copies (hc_heic_job_copy_rgb_device +
+ * NCCL send/recv or cudaMemcpyPeer). HEIF grid tiles are independent pictures (context.cc:2407-2415), so no
+ * data crosses GPUs before the stitch. */
+hc_heic_job* hc_heic_job_create_band(hc_engine* e, const uint8_t* data, size_t size, int want_alpha, int threads,
+                                     int tile_row_begin, int tile_row_end, int* first_output_row, int* full_height);
+/* device-to-device copy of a converted image into caller-owned device memory (same device), synchronous */
+int hc_heic_job_copy_rgb_device(hc_heic_job* j, int image, void* device_dst, size_t dst_stride_bytes);
 void hc_heic_job_destroy(hc_heic_job* j);
 int hc_heic_job_image_count(const hc_heic_job* j);
 int hc_heic_job_image_desc(const hc_heic_job* j, int image, hc_image_desc* desc);
