@@ -47,7 +47,7 @@ std::string g_engine_error;
 void resolve_api() {
   void* h = RTLD_DEFAULT;
   if (const char* path = getenv("HEIFCUDA_LIBHEIF")) {
-    void* lib = dlopen(path, RTLD_NOW | RTLD_GLOBAL);
+    void* lib = dlopen(path, RTLD_NOW | RTLD_LOCAL);   // usually already loaded: this only fetches its handle
     if (lib) h = lib;
   }
   auto sym = [&](const char* name) -> void* {

@@ -34,7 +34,8 @@ def available():
 def lib():
     global _lib
     if _lib is None:
-        C.CDLL(os.path.join(REF_DIR, "libde265ref.so"), mode=C.RTLD_GLOBAL)
+        # RTLD_LOCAL on purpose (libde265ref.so comes in through libheifref.so's $ORIGIN rpath): the reference's
+        # generic C++ symbol names must not interpose other libraries of the test process (torch crashed on import)
         L = C.CDLL(os.path.join(REF_DIR, "libheifref.so"))
         L.heif_context_alloc.restype = C.c_void_p
         L.heif_context_free.argtypes = [C.c_void_p]
