@@ -1,5 +1,6 @@
 // capi_host.cc — C ABI over the host front-end (include/heifcuda.h, section "host front-end").
 #include "capi_internal.h"
+#include "../host/k0_host.h"
 #include <cstdlib>
 #include <cstring>
 #include <string>
@@ -152,5 +153,50 @@ int hc_heif_coded_stream(const hc_heif* f, uint32_t id, uint8_t** out, size_t* s
   return HC_OK;
 }
 void hc_free(void* p) { free(p); }
+
+}  // extern "C"
+
+extern "C" {
+
+hc_k0_picture* hc_k0_prepare(const uint8_t* data, size_t size, int stream_format) {
+  if (!data || !size) { g_last_error = "hc_k0_prepare: null argument"; return nullptr; }
+  try {
+    std::unique_ptr<hc_k0_picture> k(new hc_k0_picture);
+    std::string e = hc::k0_prepare(data, size, stream_format, k->hp);
+    if (!e.empty()) { g_last_error = e; return nullptr; }
+    return k.release();
+  } catch (const std::bad_alloc&) {
+    g_last_error = "out of memory";
+    return nullptr;
+  }
+}
+void hc_k0_free(hc_k0_picture* k) { delete k; }
+int hc_k0_eligible(const hc_k0_picture* k) { return k && k->hp.eligible; }
+const char* hc_k0_why_not(const hc_k0_picture* k) { return k ? k->hp.why_not.c_str() : ""; }
+const hc_pic* hc_k0_pic(const hc_k0_picture* k) { return k ? &k->hp.hpic : nullptr; }
+size_t hc_k0_upload_bytes(const hc_k0_picture* k) {
+  return k ? k->hp.bytes.size() + k->hp.slices.size() * sizeof(hc::k0::Slice) + k->hp.ctb_slice.size() * 8 + k->hp.subs.size() * sizeof(hc::k0::Sub) : 0;
+}
+
+// Test scaffold: parses one picture with the K0 core (the device CABAC parser, kernels/k0_core.cuh) executed
+// on the CPU and returns its records in the host parser's form. NULL when the picture is not eligible for K0
+// (hc_last_error starts with "not eligible") or malformed.
+hc_records* hc_parse_picture_k0(const uint8_t* data, size_t size, int stream_format) {
+  hc::K0HostPicture hp;
+  std::string e;
+  try {
+    e = hc::k0_prepare(data, size, stream_format, hp);
+    if (e.empty() && !hp.eligible) e = "not eligible for K0: " + hp.why_not;
+    if (!e.empty()) { g_last_error = e; return nullptr; }
+    std::unique_ptr<hc::PictureRecords> rec = hc::k0_parse_on_cpu(hp, &e);
+    if (!rec) { g_last_error = e; return nullptr; }
+    hc_records* r = new hc_records;
+    r->rec = std::move(rec);
+    return r;
+  } catch (const std::bad_alloc&) {
+    g_last_error = "out of memory";
+    return nullptr;
+  }
+}
 
 }  // extern "C"

@@ -5,12 +5,16 @@
 #include "../../../include/heifcuda.h"
 #include "../host/hevc_parse.h"
 #include "../host/heif_reader.h"
+#include "../host/k0_host.h"
 
 struct hc_parser {
   hc::HevcIntraParser parser;
 };
 struct hc_records {
   std::unique_ptr<hc::PictureRecords> rec;
+};
+struct hc_k0_picture {
+  hc::K0HostPicture hp;
 };
 struct hc_heif {
   hc::HeifFile file;

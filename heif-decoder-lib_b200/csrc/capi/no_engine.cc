@@ -12,6 +12,8 @@ hc_batch* hc_batch_create(hc_engine*) { NO_ENGINE(); return nullptr; }
 void hc_batch_destroy(hc_batch*) {}
 int hc_batch_add_canvas(hc_batch*, int, int, int, int, int) { return NO_ENGINE(); }
 int hc_batch_add_picture(hc_batch*, const hc_records*, int, int, int, int, int) { return NO_ENGINE(); }
+int hc_batch_add_k0_picture(hc_batch*, const hc_k0_picture*, int, int, int, int, int) { return NO_ENGINE(); }
+int hc_batch_k0_pictures(const hc_batch*) { return 0; }
 int hc_batch_upload(hc_batch*) { return NO_ENGINE(); }
 int hc_batch_reconstruct(hc_batch*, int) { return NO_ENGINE(); }
 int hc_batch_convert(hc_batch*, int, const hc_csc_params*) { return NO_ENGINE(); }

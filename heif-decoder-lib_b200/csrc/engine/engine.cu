@@ -21,6 +21,7 @@
 #include <vector>
 #include "../capi/capi_internal.h"
 #include "../kernels/launch.h"
+#include "../host/k0_host.h"
 
 namespace {
 
@@ -44,6 +45,7 @@ struct hc_engine {
   std::mutex mu;
   std::vector<Block> free_dev, free_pin;
   std::vector<cudaStream_t> free_streams;
+  hc::k0::Tables* d_k0_tables = nullptr;   // read-only tables of the device parser
 
   Block take(std::vector<Block>& list, size_t size, bool pinned) {
     std::lock_guard<std::mutex> lk(mu);
@@ -94,8 +96,9 @@ struct Canvas {
 };
 
 struct Placement {
-  const hc::PictureRecords* rec;
+  const hc::PictureRecords* rec;     // host-parsed picture, or
   int canvas, x, y, role, rescale;
+  const hc::K0HostPicture* k0 = nullptr;   // picture whose slice data K0 parses on the device
 };
 
 }  // namespace
@@ -114,6 +117,21 @@ struct hc_batch {
   const hc::RowTask* d_tasks = nullptr;
   int ntasks = 0;
   int k2_smem = 0;   // dynamic shared memory per K2 CTA
+  // K0 (device CABAC parse) of the pictures added as bitstreams
+  int nk0 = 0, nchains = 0;
+  bool k0_done = false;
+  const hc::k0::Pic* d_k0_pics = nullptr;
+  const hc::k0::Sub* d_k0_subs = nullptr;
+  const hc::k0::Chain* d_k0_chains = nullptr;
+  size_t k0_zero_off = 0, k0_zero_bytes = 0;      // device-only zone: cleared to 0 before K0 (edge maps, progress, errors, counters)
+  size_t k0_ones_off = 0, k0_ones_bytes = 0;      // cleared to 1 (intra mode maps: DC)
+  size_t k0_status_off = 0;                        // [int error per K0 picture][4 list counters]
+  const uint32_t* d_k0_tb_index[4] = {nullptr, nullptr, nullptr, nullptr};
+  int k0_tb_counts[4] = {0, 0, 0, 0};
+  std::vector<int> k0_pic_of;                      // K0 picture -> batch picture index
+  Block h_status;
+  cudaEvent_t ev_k0[2] = {};
+  size_t k0_input_bytes = 0;
   long long max_dbk_units = 0, max_sao_quads = 0;
   int max_planes = 1;
   bool uploaded = false;
@@ -137,7 +155,8 @@ void release_blocks(hc_batch* b) {
   e->give(e->free_dev, b->d_planes);
   e->give(e->free_dev, b->d_rgb);
   e->give(e->free_dev, b->d_progress);
-  b->d_arena = b->h_arena = b->d_resid = b->d_planes = b->d_rgb = b->d_progress = Block();
+  e->give(e->free_pin, b->h_status);
+  b->d_arena = b->h_arena = b->d_resid = b->d_planes = b->d_rgb = b->d_progress = b->h_status = Block();
 }
 
 }  // namespace
@@ -162,6 +181,11 @@ hc_engine* hc_engine_create(int device) {
   hc_engine* eng = new (std::nothrow) hc_engine;
   if (!eng) return nullptr;
   eng->device = device;
+  if (!cuda_ok(cudaMalloc(&eng->d_k0_tables, sizeof(hc::k0::Tables)), "cudaMalloc(K0 tables)") ||
+      !cuda_ok(cudaMemcpy(eng->d_k0_tables, &hc::k0_tables(), sizeof(hc::k0::Tables), cudaMemcpyHostToDevice), "cudaMemcpy(K0 tables)")) {
+    delete eng;
+    return nullptr;
+  }
   return eng;
 }
 
@@ -171,6 +195,7 @@ void hc_engine_destroy(hc_engine* e) {
   for (auto& b : e->free_dev) cudaFree(b.p);
   for (auto& b : e->free_pin) cudaFreeHost(b.p);
   for (auto s : e->free_streams) cudaStreamDestroy(s);
+  if (e->d_k0_tables) cudaFree(e->d_k0_tables);
   delete e;
 }
 
@@ -192,6 +217,8 @@ hc_batch* hc_batch_create(hc_engine* e) {
     if (!cuda_ok(cudaEventCreate(&ev), "cudaEventCreate")) { delete b; return nullptr; }
   for (auto& ev : b->timer)
     if (!cuda_ok(cudaEventCreate(&ev), "cudaEventCreate")) { delete b; return nullptr; }
+  for (auto& ev : b->ev_k0)
+    if (!cuda_ok(cudaEventCreate(&ev), "cudaEventCreate")) { delete b; return nullptr; }
   return b;
 }
 
@@ -202,6 +229,7 @@ void hc_batch_destroy(hc_batch* b) {
   release_blocks(b);
   for (auto& ev : b->ev) if (ev) cudaEventDestroy(ev);
   for (auto& ev : b->timer) if (ev) cudaEventDestroy(ev);
+  for (auto& ev : b->ev_k0) if (ev) cudaEventDestroy(ev);
   for (auto& p : b->csc_events) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
   {
     std::lock_guard<std::mutex> lk(b->eng->mu);
@@ -221,13 +249,14 @@ int hc_batch_add_canvas(hc_batch* b, int width, int height, int chroma_format, i
   return (int)b->canvases.size() - 1;
 }
 
-int hc_batch_add_picture(hc_batch* b, const hc_records* rec, int canvas, int x, int y, int role, int rescale_limited) {
-  if (!b || !rec || canvas < 0 || canvas >= (int)b->canvases.size() || x < 0 || y < 0) {
+static int add_picture(hc_batch* b, const hc::PictureRecords* rec, const hc::K0HostPicture* k0, int canvas, int x, int y, int role,
+                       int rescale_limited) {
+  if (!b || (!rec && !k0) || canvas < 0 || canvas >= (int)b->canvases.size() || x < 0 || y < 0) {
     hc::set_last_error("hc_batch_add_picture: bad argument");
     return HC_ERR_ARGUMENT;
   }
   const Canvas& c = b->canvases[canvas];
-  const hc_pic& p = rec->rec->pic;
+  const hc_pic& p = rec ? rec->pic : k0->hpic;
   if (b->pics.size() >= 65535) { hc::set_last_error("too many pictures in one batch"); return HC_ERR_ARGUMENT; }
   if (role == HC_ROLE_COLOUR) {
     if (p.chroma_format != c.chroma) { hc::set_last_error("picture has a different chroma format than its canvas"); return HC_ERR_BITSTREAM; }
@@ -240,9 +269,18 @@ int hc_batch_add_picture(hc_batch* b, const hc_records* rec, int canvas, int x, 
     if ((p.bit_depth_y == 8) != (c.bit_depth == 8)) { hc::set_last_error("alpha image sample size differs from the colour image"); return HC_ERR_UNSUPPORTED; }
   }
   if (x >= c.w || y >= c.h) { hc::set_last_error("picture placed outside its canvas"); return HC_ERR_BITSTREAM; }
-  b->pics.push_back({rec->rec.get(), canvas, x, y, role, rescale_limited});
+  b->pics.push_back({rec, canvas, x, y, role, rescale_limited, k0});
   b->uploaded = false;
   return (int)b->pics.size() - 1;
+}
+
+int hc_batch_add_picture(hc_batch* b, const hc_records* rec, int canvas, int x, int y, int role, int rescale_limited) {
+  return add_picture(b, rec ? rec->rec.get() : nullptr, nullptr, canvas, x, y, role, rescale_limited);
+}
+
+int hc_batch_add_k0_picture(hc_batch* b, const hc_k0_picture* k, int canvas, int x, int y, int role, int rescale_limited) {
+  if (k && !k->hp.eligible) { hc::set_last_error("picture is not eligible for the device parser: " + k->hp.why_not); return HC_ERR_UNSUPPORTED; }
+  return add_picture(b, nullptr, k ? &k->hp : nullptr, canvas, x, y, role, rescale_limited);
 }
 
 int hc_batch_upload(hc_batch* b) {
@@ -276,20 +314,33 @@ int hc_batch_upload(hc_batch* b) {
   size_t n_tasks = 0;
   b->max_dbk_units = b->max_sao_quads = 0;
   b->max_planes = 1;
+  b->nk0 = 0;
+  b->k0_pic_of.clear();
   for (int i = 0; i < np; i++) {
-    const hc::PictureRecords& r = *b->pics[i].rec;
     hc_pic& p = b->hpics[i];
-    p = r.pic;
-    p.ctu_base = (uint32_t)n_ctu;   n_ctu += r.ctus.size();
-    p.blk_base = (uint32_t)n_blk;   n_blk += r.blks.size();
-    p.tb_base = (uint32_t)n_tb;     n_tb += r.tbs.size();
-    p.coeff_base = (uint32_t)n_coeff; n_coeff += r.coeffs.size();
-    p.edge_base = (uint32_t)n_edge; n_edge += r.edge_map.size();
-    p.qp_base = (uint32_t)n_qp;     n_qp += r.qp_map.size();
-    p.scaling_base = (uint32_t)n_scal; n_scal += r.scaling.size();
-    p.resid_base = n_resid;         n_resid += align_up(r.resid_count, 8);
-    if (n_blk > 0xFFFFFFFFull || n_coeff > 0xFFFFFFFFull) { hc::set_last_error("batch too large"); return HC_ERR_ARGUMENT; }
-    for (int l = 0; l < 4; l++) { idx_base[(size_t)i * 4 + l] = counts[l]; counts[l] += (int)r.tbs_by_size[l]; }
+    if (const hc::K0HostPicture* k = b->pics[i].k0) {
+      // device-parsed picture: its record regions live in the device-only zone behind the uploaded arena (bases below)
+      p = k->hpic;
+      const uint64_t nctb = (uint64_t)k->pic.ctbs_w * k->pic.ctbs_h;
+      p.scaling_base = (uint32_t)n_scal; n_scal += k->scaling.size();
+      p.resid_count = nctb * k->pic.resid_cap_ctb;
+      p.resid_base = n_resid;         n_resid += align_up(p.resid_count, 8);
+      b->k0_pic_of.push_back(i);
+      b->nk0++;
+    } else {
+      const hc::PictureRecords& r = *b->pics[i].rec;
+      p = r.pic;
+      p.ctu_base = (uint32_t)n_ctu;   n_ctu += r.ctus.size();
+      p.blk_base = (uint32_t)n_blk;   n_blk += r.blks.size();
+      p.tb_base = (uint32_t)n_tb;     n_tb += r.tbs.size();
+      p.coeff_base = (uint32_t)n_coeff; n_coeff += r.coeffs.size();
+      p.edge_base = (uint32_t)n_edge; n_edge += r.edge_map.size();
+      p.qp_base = (uint32_t)n_qp;     n_qp += r.qp_map.size();
+      p.scaling_base = (uint32_t)n_scal; n_scal += r.scaling.size();
+      p.resid_base = n_resid;         n_resid += align_up(r.resid_count, 8);
+      if (n_blk > 0xFFFFFFFFull || n_coeff > 0xFFFFFFFFull) { hc::set_last_error("batch too large"); return HC_ERR_ARGUMENT; }
+      for (int l = 0; l < 4; l++) { idx_base[(size_t)i * 4 + l] = counts[l]; counts[l] += (int)r.tbs_by_size[l]; }
+    }
     const int ncomp = p.chroma_format ? 3 : 1;
     max_rows = std::max(max_rows, (int)p.ctbs_h);
     n_tasks += (size_t)ncomp * p.ctbs_h;
@@ -327,11 +378,61 @@ int hc_batch_upload(hc_batch* b) {
   size_t o_idx[4];
   for (int l = 0; l < 4; l++) o_idx[l] = place(sizeof(uint32_t) * counts[l]);
   const size_t o_tasks = place(sizeof(hc::RowTask) * n_tasks);
+  // K0 inputs (uploaded): picture descriptors, slices, per-CTB tables, substreams, chains, RBSP bytes
+  const int nk0 = b->nk0;
+  size_t k_slices = 0, k_ctbs = 0, k_subs = 0, k_chains = 0, k_bytes = 0;
+  for (int q = 0; q < nk0; q++) {
+    const hc::K0HostPicture& k = *b->pics[b->k0_pic_of[q]].k0;
+    k_slices += k.slices.size(); k_ctbs += k.ctb_slice.size(); k_subs += k.subs.size(); k_chains += k.chains.size();
+    k_bytes += align_up(k.bytes.size(), 16);
+  }
+  const size_t o_kpics = place(sizeof(hc::k0::Pic) * nk0), o_kslices = place(sizeof(hc::k0::Slice) * k_slices);
+  const size_t o_kctbslice = place(4 * k_ctbs), o_kstatic = place(4 * k_ctbs), o_ksubs = place(sizeof(hc::k0::Sub) * k_subs);
+  const size_t o_kchains = place(sizeof(hc::k0::Chain) * k_chains), o_kbytes = place(k_bytes + 64);
   b->arena_bytes = o;
+  b->k0_input_bytes = nk0 ? o - o_kpics : 0;
+  b->nchains = (int)k_chains;
+
+  // device-only zone behind the uploaded arena: the fixed-capacity record regions K0 fills, its scratch maps,
+  // status words and K1 launch lists. Laid out by category so that each clear is one memset.
+  size_t z = align_up(o, 256);
+  auto zplace = [&](size_t bytes, size_t align) { z = align_up(z, align); size_t at = z; z += bytes; return at; };
+  struct K0Off { size_t ctus, blks, tbs, coeffs, edge, qp, ct_depth, ipm, ipm_c, wpp, progress; };
+  std::vector<K0Off> koff(nk0);
+  size_t z_lists[4] = {0, 0, 0, 0}, list_cap[4] = {0, 0, 0, 0};
+  if (nk0) {
+    for (int q = 0; q < nk0; q++) {   // ctu regions must sit at a multiple of sizeof(hc_ctu) from the ctu array base
+      const hc::k0::Pic& kp = b->pics[b->k0_pic_of[q]].k0->pic;
+      z = o_ctus + align_up(z - o_ctus, sizeof(hc_ctu));
+      koff[q].ctus = z; z += sizeof(hc_ctu) * (size_t)kp.ctbs_w * kp.ctbs_h;
+    }
+    for (int q = 0; q < nk0; q++) { const hc::k0::Pic& kp = b->pics[b->k0_pic_of[q]].k0->pic; koff[q].blks = zplace(sizeof(hc_blk) * (size_t)kp.ctbs_w * kp.ctbs_h * kp.blk_cap_ctb, 16); }
+    for (int q = 0; q < nk0; q++) { const hc::k0::Pic& kp = b->pics[b->k0_pic_of[q]].k0->pic; koff[q].tbs = zplace(sizeof(hc_tb) * (size_t)kp.ctbs_w * kp.ctbs_h * kp.tb_cap_ctb, 16); }
+    for (int q = 0; q < nk0; q++) { const hc::k0::Pic& kp = b->pics[b->k0_pic_of[q]].k0->pic; koff[q].coeffs = zplace(sizeof(hc_coeff) * (size_t)kp.ctbs_w * kp.ctbs_h * kp.coeff_cap_ctb, 16); }
+    for (int q = 0; q < nk0; q++) { const hc::k0::Pic& kp = b->pics[b->k0_pic_of[q]].k0->pic; koff[q].qp = zplace((size_t)kp.w8 * kp.h8, 1); }
+    for (int q = 0; q < nk0; q++) { const hc::k0::Pic& kp = b->pics[b->k0_pic_of[q]].k0->pic; koff[q].ct_depth = zplace((size_t)kp.w8 * kp.h8, 1); }
+    for (int q = 0; q < nk0; q++) { const hc::k0::Pic& kp = b->pics[b->k0_pic_of[q]].k0->pic; koff[q].wpp = zplace((size_t)kp.ctbs_h * hc::k0::CTX_BYTES, 16); }
+    for (int l = 0; l < 4; l++) {
+      for (int q = 0; q < nk0; q++) { const hc::k0::Pic& kp = b->pics[b->k0_pic_of[q]].k0->pic; list_cap[l] += ((size_t)kp.ctbs_w * kp.ctbs_h * kp.tb_cap_ctb >> (2 * l)) + 64; }
+      z_lists[l] = zplace(4 * list_cap[l], 16);
+    }
+    // cleared to 1: intra prediction mode maps (DC)
+    b->k0_ones_off = zplace(0, 256);
+    for (int q = 0; q < nk0; q++) { const hc::k0::Pic& kp = b->pics[b->k0_pic_of[q]].k0->pic; koff[q].ipm = zplace((size_t)kp.w4 * kp.h4, 1); koff[q].ipm_c = zplace((size_t)kp.w4 * kp.h4, 1); }
+    b->k0_ones_bytes = z - b->k0_ones_off;
+    // cleared to 0: edge maps, row progress, status
+    b->k0_zero_off = zplace(0, 256);
+    for (int q = 0; q < nk0; q++) { const hc::k0::Pic& kp = b->pics[b->k0_pic_of[q]].k0->pic; koff[q].edge = zplace((size_t)kp.w4 * kp.h4, 1); }
+    for (int q = 0; q < nk0; q++) { const hc::k0::Pic& kp = b->pics[b->k0_pic_of[q]].k0->pic; koff[q].progress = zplace(4 * (size_t)kp.ctbs_h, 4); }
+    b->k0_status_off = zplace(4 * ((size_t)nk0 + 4), 16);
+    b->k0_zero_bytes = z - b->k0_zero_off;
+  }
+  const size_t arena_total = align_up(z, 256);
 
   release_blocks(b);
   b->h_arena = b->eng->take(b->eng->free_pin, o, true);
-  b->d_arena = b->eng->take(b->eng->free_dev, o, false);
+  b->d_arena = b->eng->take(b->eng->free_dev, arena_total, false);
+  if (nk0) b->h_status = b->eng->take(b->eng->free_pin, 4 * ((size_t)nk0 + 4), true);
   b->d_resid = b->eng->take(b->eng->free_dev, std::max<size_t>(n_resid * 2, 256), false);
   b->d_planes = b->eng->take(b->eng->free_dev, std::max<size_t>(pool, 256), false);
   b->d_progress = b->eng->take(b->eng->free_dev, std::max<size_t>(n_tasks * sizeof(int), 256), false);
@@ -339,14 +440,77 @@ int hc_batch_upload(hc_batch* b) {
   b->resid_elems = n_resid;
   b->planes_bytes = pool;
 
-  // ---- pack: every picture's records go to disjoint slices of the pinned arena, in parallel ----
+  if (nk0 && !b->h_status.p) return HC_ERR_MEMORY;
   uint8_t* H = (uint8_t*)b->h_arena.p;
+  uint8_t* Dk = (uint8_t*)b->d_arena.p;
+  // ---- K0 pictures: record bases (element offsets from the uploaded array bases into the device-only zone) + inputs ----
+  if (nk0) {
+    hc::k0::Pic* kp_out = (hc::k0::Pic*)(H + o_kpics);
+    hc::k0::Slice* ks_out = (hc::k0::Slice*)(H + o_kslices);
+    int32_t* kc_out = (int32_t*)(H + o_kctbslice);
+    uint8_t* kst_out = H + o_kstatic;
+    hc::k0::Sub* ksub_out = (hc::k0::Sub*)(H + o_ksubs);
+    size_t is = 0, ic = 0, isub = 0, ib = 0;
+    std::vector<std::pair<int, hc::k0::Chain>> chains;   // (row of the first substream, chain)
+    for (int q = 0; q < nk0; q++) {
+      const int i = b->k0_pic_of[q];
+      const hc::K0HostPicture& k = *b->pics[i].k0;
+      hc_pic& p = b->hpics[i];
+      p.ctu_base = (uint32_t)((koff[q].ctus - o_ctus) / sizeof(hc_ctu));
+      p.blk_base = (uint32_t)((koff[q].blks - o_blks) / sizeof(hc_blk));
+      p.tb_base = (uint32_t)((koff[q].tbs - o_tbs) / sizeof(hc_tb));
+      p.coeff_base = (uint32_t)((koff[q].coeffs - o_coeffs) / sizeof(hc_coeff));
+      p.edge_base = (uint32_t)(koff[q].edge - o_edge);
+      p.qp_base = (uint32_t)(koff[q].qp - o_qp);
+      if ((koff[q].blks - o_blks) / sizeof(hc_blk) > 0xFFFFFFFFull || (koff[q].coeffs - o_coeffs) / sizeof(hc_coeff) > 0xFFFFFFFFull ||
+          koff[q].edge - o_edge > 0xFFFFFFFFull) { hc::set_last_error("batch too large for the device parser"); return HC_ERR_ARGUMENT; }
+      hc::k0::Pic kp = k.pic;
+      kp.pic_index = (uint32_t)i;
+      kp.tb_global_base = p.tb_base;
+      kp.bytes = Dk + o_kbytes + ib;
+      kp.slices = (const hc::k0::Slice*)(Dk + o_kslices) + is;
+      kp.ctb_slice = (const int32_t*)(Dk + o_kctbslice) + ic;
+      kp.ctu_static = Dk + o_kstatic + 4 * ic;
+      kp.ct_depth = Dk + koff[q].ct_depth; kp.ipm = Dk + koff[q].ipm; kp.ipm_c = Dk + koff[q].ipm_c; kp.wpp_ctx = Dk + koff[q].wpp;
+      kp.progress = (int*)(Dk + koff[q].progress);
+      kp.error = (int*)(Dk + b->k0_status_off) + q;
+      kp.qp_map = (int8_t*)(Dk + koff[q].qp); kp.edge_map = Dk + koff[q].edge;
+      kp.ctus = (hc_ctu*)(Dk + koff[q].ctus); kp.blks = (hc_blk*)(Dk + koff[q].blks); kp.tbs = (hc_tb*)(Dk + koff[q].tbs);
+      kp.coeffs = (hc_coeff*)(Dk + koff[q].coeffs);
+      for (int l = 0; l < 4; l++) kp.tb_lists[l] = (uint32_t*)(Dk + z_lists[l]);
+      kp.tb_counts = (unsigned int*)(Dk + b->k0_status_off) + nk0;
+      kp_out[q] = kp;
+      memcpy(ks_out + is, k.slices.data(), sizeof(hc::k0::Slice) * k.slices.size());
+      memcpy(kc_out + ic, k.ctb_slice.data(), 4 * k.ctb_slice.size());
+      memcpy(kst_out + 4 * ic, k.ctu_static.data(), k.ctu_static.size());
+      memcpy(H + o_kbytes + ib, k.bytes.data(), k.bytes.size());
+      for (size_t t = 0; t < k.subs.size(); t++) { ksub_out[isub + t] = k.subs[t]; ksub_out[isub + t].pic = (uint32_t)q; }
+      for (const hc::k0::Chain& c : k.chains) chains.push_back({k.subs[c.first_sub].first_ctb / k.pic.ctbs_w, {(uint32_t)(isub + c.first_sub), c.nsubs}});
+      is += k.slices.size(); ic += k.ctb_slice.size(); isub += k.subs.size(); ib += align_up(k.bytes.size(), 16);
+    }
+    memset(H + o_kbytes + ib, 0, 64);
+    // rows of all pictures interleaved: a chain only ever waits for a chain with a smaller index
+    std::stable_sort(chains.begin(), chains.end(), [](const std::pair<int, hc::k0::Chain>& a, const std::pair<int, hc::k0::Chain>& c) { return a.first < c.first; });
+    hc::k0::Chain* kch_out = (hc::k0::Chain*)(H + o_kchains);
+    for (size_t t = 0; t < chains.size(); t++) kch_out[t] = chains[t].second;
+    b->d_k0_pics = (const hc::k0::Pic*)(Dk + o_kpics);
+    b->d_k0_subs = (const hc::k0::Sub*)(Dk + o_ksubs);
+    b->d_k0_chains = (const hc::k0::Chain*)(Dk + o_kchains);
+    for (int l = 0; l < 4; l++) b->d_k0_tb_index[l] = (const uint32_t*)(Dk + z_lists[l]);
+  }
+  b->k0_done = false;
+
+  // ---- pack: every picture's records go to disjoint slices of the pinned arena, in parallel ----
   memcpy(H + o_pics, b->hpics.data(), sizeof(hc_pic) * np);
   uint32_t* idx[4];
   for (int l = 0; l < 4; l++) idx[l] = (uint32_t*)(H + o_idx[l]);
   auto pack_picture = [&](int i) {
-    const hc::PictureRecords& r = *b->pics[i].rec;
     const hc_pic& p = b->hpics[i];
+    if (const hc::K0HostPicture* k = b->pics[i].k0) {
+      if (!k->scaling.empty()) memcpy(H + o_scal + p.scaling_base, k->scaling.data(), k->scaling.size());
+      return;
+    }
+    const hc::PictureRecords& r = *b->pics[i].rec;
     memcpy(H + o_ctus + sizeof(hc_ctu) * p.ctu_base, r.ctus.data(), sizeof(hc_ctu) * r.ctus.size());
     memcpy(H + o_blks + sizeof(hc_blk) * p.blk_base, r.blks.data(), sizeof(hc_blk) * r.blks.size());
     hc_tb* tb = (hc_tb*)(H + o_tbs) + p.tb_base;
@@ -438,9 +602,37 @@ int hc_batch_reconstruct(hc_batch* b, int stages) {
   for (auto& p : b->csc_events) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
   b->csc_events.clear();
   cudaMemsetAsync(b->d_progress.p, 0, std::max<size_t>((size_t)b->ntasks * sizeof(int), 4), s);
+  if (b->nk0 && !b->k0_done) {
+    // K0: the slice data of the pictures added as bitstreams is parsed on the device, straight into their record
+    // regions; afterwards the records stay resident (a second hc_batch_reconstruct re-uses them)
+    uint8_t* D = (uint8_t*)b->d_arena.p;
+    cudaEventRecord(b->ev_k0[0], s);
+    cudaMemsetAsync(D + b->k0_ones_off, 1, b->k0_ones_bytes, s);
+    cudaMemsetAsync(D + b->k0_zero_off, 0, b->k0_zero_bytes, s);
+    hc::launch_k0(b->eng->d_k0_tables, b->d_k0_pics, b->d_k0_subs, b->d_k0_chains, b->nchains, s);
+    cudaEventRecord(b->ev_k0[1], s);
+    const size_t status_bytes = 4 * ((size_t)b->nk0 + 4);
+    if (!cuda_ok(cudaMemcpyAsync(b->h_status.p, D + b->k0_status_off, status_bytes, cudaMemcpyDeviceToHost, s), "cudaMemcpyAsync(K0 status)") ||
+        !cuda_ok(cudaStreamSynchronize(s), "K0 (device CABAC parse)"))
+      return HC_ERR_CUDA;
+    const int* status = (const int*)b->h_status.p;
+    for (int q = 0; q < b->nk0; q++)
+      if (status[q]) {
+        hc::set_last_error("picture " + std::to_string(b->k0_pic_of[q]) + (status[q] == hc::k0::ERR_CAPACITY ? ": device parser capacity exceeded"
+                                                                                                             : ": malformed slice data (device parser)"));
+        return HC_ERR_BITSTREAM;
+      }
+    for (int l = 0; l < 4; l++) b->k0_tb_counts[l] = status[b->nk0 + l];
+    b->k0_done = true;
+    b->launches += 1;
+  }
   cudaEventRecord(b->ev[2], s);
   hc::launch_k1(b->view, b->d_tb_index, b->tb_counts, s);
   for (int l = 0; l < 4; l++) b->launches += b->tb_counts[l] > 0;
+  if (b->nk0) {
+    hc::launch_k1(b->view, b->d_k0_tb_index, b->k0_tb_counts, s);
+    for (int l = 0; l < 4; l++) b->launches += b->k0_tb_counts[l] > 0;
+  }
   cudaEventRecord(b->ev[3], s);
   hc::launch_k2(b->view, b->d_tasks, b->ntasks, b->k2_smem, (int*)b->d_progress.p, s);
   b->launches += 1;
@@ -600,6 +792,7 @@ int hc_batch_stage_ms(hc_batch* b, float ms[8]) {
   }
   b->csc_events.clear();
   ms[6] = b->last_d2h_ms;
+  if (b->nk0 && b->k0_done) cudaEventElapsedTime(&ms[7], b->ev_k0[0], b->ev_k0[1]);
   cudaGetLastError();
   return HC_OK;
 }
@@ -623,5 +816,6 @@ int hc_batch_timer_stop_ms(hc_batch* b, float* ms) {
 }
 int hc_batch_launch_count(const hc_batch* b) { return b ? b->launches : 0; }
 size_t hc_batch_upload_bytes(const hc_batch* b) { return b ? b->arena_bytes : 0; }
+int hc_batch_k0_pictures(const hc_batch* b) { return b ? b->nk0 : 0; }
 
 }  // extern "C"

@@ -97,9 +97,10 @@ inline uint8_t ctx_init_state(int init_value, int slice_qp) {
   return (uint8_t)((st << 1) | mps);
 }
 
-inline void ctx_init_all(CtxSet& c, int slice_qp) {
-  auto set = [&](int first, const int* v, int n) {
-    for (int i = 0; i < n; i++) c.s[first + i] = ctx_init_state(v[i], slice_qp);
+// initValue of every context (Tables 9-5..9-37, initType 0)
+inline void ctx_init_values(uint8_t v[CTX_COUNT]) {
+  auto set = [&](int first, const int* src, int n) {
+    for (int i = 0; i < n; i++) v[first + i] = (uint8_t)src[i];
   };
   static const int sao_merge[1] = {153}, sao_type[1] = {200}, split_cu[3] = {139, 141, 157};
   static const int bypass[1] = {154}, part_mode[1] = {184}, prev_luma[1] = {184}, chroma_mode[1] = {63};
@@ -136,6 +137,12 @@ inline void ctx_init_all(CtxSet& c, int slice_qp) {
   set(CTX_CHROMA_QP_OFFSET_IDX, c154, 1);
   set(CTX_RES_SCALE_ABS, c154, 8);
   set(CTX_RES_SCALE_SIGN, c154, 2);
+}
+
+inline void ctx_init_all(CtxSet& c, int slice_qp) {
+  uint8_t v[CTX_COUNT];
+  ctx_init_values(v);
+  for (int i = 0; i < CTX_COUNT; i++) c.s[i] = ctx_init_state(v[i], slice_qp);
 }
 
 // Arithmetic decoder. `value` = (ivlOffset << avail) | the next `avail` bits of the stream, so

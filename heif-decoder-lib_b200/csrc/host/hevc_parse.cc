@@ -14,6 +14,7 @@
 //   - coefficient levels wrap to int16                                 slice.cc:3671
 //   - deblock slice/tile edge tests only at CTB boundaries             deblock.cc:180-215
 #include "hevc_parse.h"
+#include "k0_host.h"
 #include "hevc_cabac.h"
 #include "hevc_scan.h"
 #include <algorithm>
@@ -92,6 +93,11 @@ struct HevcIntraParser::Impl {
   int cu_x0 = 0, cu_y0 = 0, cu_log2 = 0;
   int filterLeftCbEdge = 0, filterTopCbEdge = 0;
   std::string error;
+
+  // ---- K0 preparation (collect-only mode) ----
+  bool collect_only = false;
+  std::vector<std::vector<uint8_t>> k0_rbsp;   // padded RBSP of every slice segment NAL
+  std::vector<size_t> k0_rbsp_size;
 
   // =========================================================================================
   std::string start_picture(const SliceHeader& first);
@@ -252,7 +258,165 @@ std::string HevcIntraParser::push_nal(const uint8_t* nal, size_t size) {
     d.prev_independent = hdr;
     d.have_prev_independent = true;
   }
+  if (d.collect_only) {
+    if (d.pps_tab[hdr.pps_id].pps_id != d.P->pps_id) return "slice segments of one picture refer to different PPSs";
+    d.slices.push_back(hdr);
+    d.k0_rbsp_size.push_back(rbsp_size);
+    d.k0_rbsp.push_back(std::move(rbsp));
+    return "";
+  }
   return d.decode_slice_segment(rbsp.data(), rbsp_size, hdr);
+}
+
+void HevcIntraParser::set_collect_only(bool on) { impl_->collect_only = on; }
+
+// Builds the K0 inputs from the collected slice segments (see kernels/k0_core.cuh for what K0 accepts).
+std::string HevcIntraParser::take_k0(K0HostPicture& out) {
+  Impl& d = *impl_;
+  if (!d.started || d.slices.empty()) return "no picture in the bitstream";
+  const Sps& S = *d.S;
+  const Pps& P = *d.P;
+  out = K0HostPicture();
+  out.hpic = d.rec->pic;
+  out.scaling = d.rec->scaling;
+  const int nctb = S.pic_size_in_ctbs, cw = S.ctbs_w, chh = S.ctbs_h;
+  auto no = [&](const char* why) { out.eligible = false; out.why_not = why; d.started = false; d.rec.reset(); d.slices.clear(); d.k0_rbsp.clear(); d.k0_rbsp_size.clear(); return std::string(); };
+  if (P.tiles_enabled) return no("HEVC tiles");
+  if (S.pcm_enabled) return no("pcm");
+  if (P.transquant_bypass_enabled) return no("transquant bypass");
+  if (S.persistent_rice_adaptation_enabled) return no("persistent_rice_adaptation");
+  if (P.chroma_qp_offset_list_enabled) return no("cu_chroma_qp_offset");
+  if (S.log2_ctb < 4 || S.log2_ctb > 6 || S.log2_min_cb < 3) return no("coding block sizes");
+  for (auto& h : d.slices)
+    if (h.cu_chroma_qp_offset_enabled) return no("cu_chroma_qp_offset");
+  // coverage: segments in increasing address order, together covering the picture
+  for (size_t k = 0; k < d.slices.size(); k++) {
+    const int a = d.slices[k].segment_address, b = k + 1 < d.slices.size() ? d.slices[k + 1].segment_address : nctb;
+    if ((k == 0 && a != 0) || b <= a || b > nctb) return no("slice segments do not cover the picture in order");
+    if (d.slices[k].dependent && k == 0) return no("dependent first slice segment");
+  }
+
+  k0::Pic& p = out.pic;
+  memset(&p, 0, sizeof(p));
+  p.W = S.width; p.H = S.height; p.w8 = p.W >> 3; p.h8 = p.H >> 3; p.w4 = p.W >> 2; p.h4 = p.H >> 2;
+  p.ctbs_w = cw; p.ctbs_h = chh;
+  p.log2_ctb = S.log2_ctb; p.log2_min_cb = S.log2_min_cb; p.log2_min_tb = S.log2_min_tb; p.log2_max_tb = S.log2_max_tb;
+  p.max_th_depth_intra = S.max_th_depth_intra;
+  p.chroma_array_type = S.ChromaArrayType; p.sub_w = S.SubWidthC; p.sub_h = S.SubHeightC;
+  p.bit_depth_y = S.bit_depth_y; p.bit_depth_c = S.bit_depth_c; p.qp_bd_offset_y = S.qp_bd_offset_y; p.qp_bd_offset_c = S.qp_bd_offset_c;
+  p.log2_max_transform_skip_size = P.log2_max_transform_skip_size;
+  p.log2_min_cu_qp_delta_size = P.log2_min_cu_qp_delta_size;
+  p.pps_cb_qp_offset = P.cb_qp_offset; p.pps_cr_qp_offset = P.cr_qp_offset;
+  p.log2_sao_offset_scale_luma = P.log2_sao_offset_scale_luma; p.log2_sao_offset_scale_chroma = P.log2_sao_offset_scale_chroma;
+  p.transform_skip_enabled = P.transform_skip_enabled; p.sign_data_hiding = P.sign_data_hiding;
+  p.cu_qp_delta_enabled = P.cu_qp_delta_enabled; p.entropy_coding_sync = P.entropy_coding_sync_enabled;
+  p.implicit_rdpcm = S.implicit_rdpcm_enabled; p.tskip_rotation = S.transform_skip_rotation_enabled;
+  p.tskip_context = S.transform_skip_context_enabled; p.pps_loop_filter_across_slices = P.loop_filter_across_slices;
+  const int ctb = 1 << S.log2_ctb;
+  const int ccw = S.ChromaArrayType ? ctb / S.SubWidthC : 0, cch = S.ChromaArrayType ? ctb / S.SubHeightC : 0;
+  p.blk_cap[0] = (uint32_t)(ctb / 4) * (ctb / 4);
+  p.blk_cap[1] = p.blk_cap[2] = (uint32_t)(ccw * cch) / 16;
+  p.blk_cap_ctb = p.tb_cap_ctb = p.blk_cap[0] + p.blk_cap[1] + p.blk_cap[2];
+  p.coeff_cap_ctb = p.resid_cap_ctb = (uint32_t)(ctb * ctb + 2 * ccw * cch);
+
+  // slices, bytes, per-CTB slice index
+  out.ctb_slice.assign(nctb, 0);
+  bool any_deblock = false, any_sao = false;
+  for (size_t k = 0; k < d.slices.size(); k++) {
+    const SliceHeader& h = d.slices[k];
+    k0::Slice s;
+    memset(&s, 0, sizeof(s));
+    s.segment_address = h.segment_address; s.slice_addr_rs = h.slice_addr_rs; s.slice_qp_y = h.slice_qp_y;
+    if (h.data_byte_offset >= d.k0_rbsp_size[k]) return "slice segment has no data";
+    s.data_begin = (uint32_t)(out.bytes.size() + h.data_byte_offset);
+    s.data_end = (uint32_t)(out.bytes.size() + d.k0_rbsp_size[k]);
+    s.cb_qp_offset = (int8_t)h.cb_qp_offset; s.cr_qp_offset = (int8_t)h.cr_qp_offset;
+    s.beta_offset = (int8_t)h.beta_offset; s.tc_offset = (int8_t)h.tc_offset;
+    s.dependent = h.dependent; s.sao_luma = h.sao_luma; s.sao_chroma = h.sao_chroma;
+    s.deblocking_disabled = h.deblocking_disabled; s.loop_filter_across_slices = h.loop_filter_across_slices;
+    out.slices.push_back(s);
+    out.bytes.insert(out.bytes.end(), d.k0_rbsp[k].begin(), d.k0_rbsp[k].end());
+    const int b = k + 1 < d.slices.size() ? d.slices[k + 1].segment_address : nctb;
+    for (int a = h.segment_address; a < b; a++) out.ctb_slice[a] = (int32_t)k;
+    any_deblock |= !h.deblocking_disabled;
+    any_sao |= h.sao_luma || h.sao_chroma;
+  }
+  if (any_deblock) out.hpic.flags |= HC_PIC_HAS_DEBLOCK;   // conservative: K3 / K4 look at the per-unit data anyway
+  if (any_sao) out.hpic.flags |= HC_PIC_HAS_SAO;
+
+  // SAO neighbour masks (the static part of finish_picture: no tiles, no pcm / bypass units)
+  out.ctu_static.assign((size_t)nctb * 4, 0);
+  {
+    auto sa_of = [&](int n) { return d.slices[out.ctb_slice[n]].slice_addr_rs; };
+    static const int dx[8] = {-1, 1, 0, 0, -1, 1, -1, 1};
+    static const int dy[8] = {0, 0, -1, 1, -1, -1, 1, 1};
+    const bool fast = P.loop_filter_across_slices;
+    for (int cy = 0; cy < chh; cy++)
+      for (int cx = 0; cx < cw; cx++) {
+        const int a = cx + cy * cw;
+        for (int comp = 0; comp < 2; comp++) {
+          int sa = sa_of(a);
+          if (comp == 1 && S.ChromaArrayType != 0 && S.ChromaArrayType != 3) {
+            const int qx = (cx << S.log2_ctb) / S.SubWidthC, qy = (cy << S.log2_ctb) / S.SubHeightC;
+            sa = sa_of((qx >> S.log2_ctb) + (qy >> S.log2_ctb) * cw);
+          }
+          uint8_t m = 0;
+          for (int k = 0; k < 8; k++) {
+            const int nx = cx + dx[k], ny = cy + dy[k];
+            if (nx < 0 || ny < 0 || nx >= cw || ny >= chh) continue;
+            const int n = nx + ny * cw;
+            bool ok = true;
+            if (!fast) {
+              const int sn = sa_of(n);
+              if (sn < sa && !d.slices[out.ctb_slice[a]].loop_filter_across_slices) ok = false;
+              if (sn > sa && !d.slices[out.ctb_slice[n]].loop_filter_across_slices) ok = false;
+            }
+            if (ok) m |= (uint8_t)(1u << k);
+          }
+          out.ctu_static[(size_t)a * 4 + comp] = m;
+          if (comp == 1 && !fast && sa_of(a) != sa && !d.slices[out.ctb_slice[a]].loop_filter_across_slices)
+            out.ctu_static[(size_t)a * 4 + 2] |= HC_CTU_SAO_C_SELF;
+        }
+      }
+  }
+
+  // chains: one per CTB row when every segment starts a row and carries all its entry points, else one per picture
+  bool rows = P.entropy_coding_sync_enabled;
+  for (size_t k = 0; rows && k < d.slices.size(); k++) {
+    const int a = d.slices[k].segment_address, b = k + 1 < d.slices.size() ? d.slices[k + 1].segment_address : nctb;
+    if (a % cw) rows = false;
+    else if ((int)d.slices[k].entry_points.size() != (b - 1) / cw - a / cw) rows = false;
+  }
+  for (size_t k = 0; k < d.slices.size(); k++) {
+    const SliceHeader& h = d.slices[k];
+    const int a = h.segment_address, b = k + 1 < d.slices.size() ? d.slices[k + 1].segment_address : nctb;
+    if (rows) {
+      for (int r = a / cw; r <= (b - 1) / cw; r++) {
+        k0::Sub s;
+        s.pic = 0; s.slice = (uint32_t)k; s.first_ctb = r * cw; s.end_ctb = (r + 1) * cw < b ? (r + 1) * cw : b;
+        const int i = r - a / cw;
+        s.byte_begin = out.slices[k].data_begin + (i == 0 ? 0u : h.entry_points[i - 1]);
+        if (s.byte_begin >= out.slices[k].data_end) return "entry point outside the slice segment";
+        s.flags = k0::SUB_ROW_CHAIN;
+        out.chains.push_back({(uint32_t)out.subs.size(), 1u});
+        out.subs.push_back(s);
+      }
+    } else {
+      k0::Sub s;
+      s.pic = 0; s.slice = (uint32_t)k; s.first_ctb = a; s.end_ctb = b;
+      s.byte_begin = out.slices[k].data_begin;
+      s.flags = 0;
+      out.subs.push_back(s);
+    }
+  }
+  if (!rows) out.chains.push_back({0u, (uint32_t)out.subs.size()});
+  out.eligible = true;
+  d.started = false;
+  d.rec.reset();
+  d.slices.clear();
+  d.k0_rbsp.clear();
+  d.k0_rbsp_size.clear();
+  return "";
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -46,6 +46,11 @@ class HevcIntraParser {
   // Feeds an Annex-B byte stream (00 00 01 start codes), e.g. the *.265 test files.
   std::string push_annexb(const uint8_t* data, size_t size);
 
+  // K0 (device parser) preparation: with collect-only set, slice segments are NOT parsed; their headers and
+  // RBSP bytes are kept and take_k0() turns them into the inputs of kernels/k0_core.cuh.
+  void set_collect_only(bool on);
+  std::string take_k0(struct K0HostPicture& out);
+
   // True when every CTB of the current picture has been parsed.
   bool picture_complete() const;
   // True when at least one slice of a picture has been seen.

@@ -1,0 +1,934 @@
+// k0_core.cuh — K0: CABAC slice-data parse of HEVC intra pictures as host/device code.
+//
+// The same statements compile for the GPU (k0_parse.cu: one warp per substream chain, lane 0 walks the
+// syntax) and for the CPU (capi: hc_parse_picture_k0, used by the tests to check this parser record by
+// record against the reconstruction oracle before it ever runs on a GPU). It emits the records of
+// include/heifcuda_records.h directly into device memory, so a picture parsed here needs no record upload at all:
+// only its RBSP bytes (~0.2 B/px) cross PCIe.
+//
+// It replaces the same reference code as host/hevc_parse.cc — read_coding_tree_unit slice.cc:3026, read_sao :2886,
+// read_coding_quadtree :4905, read_coding_unit :4568, read_transform_tree :4139, read_transform_unit :3867,
+// residual_coding :3118, decode_quantization_parameters transform.cc:31 — and is written from the same text
+// (H.265 7.3.8, 9.3, 8.4.2, 8.6.1, 6.4.1). Parallel structure the reference does not have:
+//   * WPP pictures: one chain per CTB row; a row may parse CTB x once the row above has parsed CTB x+1
+//     (context hand-over after the 2nd CTB, 9.3.2.2, plus the split/SAO-merge neighbours), tracked by the same
+//     acquire/release counters K2 uses; all rows of all pictures of a batch are in flight;
+//   * other pictures: one chain per picture (every slice segment in order).
+// Not handled here (the host parser takes such pictures): HEVC tiles, pcm, transquant bypass,
+// cu_chroma_qp_offset, persistent_rice_adaptation, slice segments that start inside a CTB row of a WPP picture.
+//
+// Layout of a K0 picture: every CTB owns fixed-capacity slices of the picture's blk / tb / coeff / residual
+// regions (worst case of a CTB), so chains never allocate.
+#pragma once
+#include "common.cuh"
+
+// functions that must stay real calls: the syntax tree recursion is unrolled by templates and would otherwise
+// be inlined 4^depth times
+#if defined(__CUDACC__)
+#define K0_FN __host__ __device__ __noinline__
+#else
+#define K0_FN __attribute__((noinline))
+#endif
+
+namespace hc {
+namespace k0 {
+
+// ---- context table layout: identical to host/hevc_cabac.h (CtxIdx) -------------------------------------------
+enum : int {
+  CX_SAO_MERGE = 0, CX_SAO_TYPE = 1, CX_SPLIT_CU = 2, CX_TQ_BYPASS = 5, CX_PART_MODE = 6, CX_PREV_INTRA_LUMA = 7,
+  CX_INTRA_CHROMA = 8, CX_CBF_LUMA = 9, CX_CBF_CHROMA = 11, CX_SPLIT_TRANSFORM = 15, CX_CU_QP_DELTA = 18,
+  CX_TSKIP = 20, CX_LAST_X = 22, CX_LAST_Y = 40, CX_CSBF = 58, CX_SIG = 62, CX_G1 = 106, CX_G2 = 130,
+  CX_COUNT = 136   // the range-extension contexts behind G2 are never touched by the streams K0 accepts
+};
+constexpr int CTX_BYTES = 160;   // padded
+
+// All read-only tables of the parser in one block (constant memory on the device).
+struct Tables {
+  uint8_t range_lps[64][4];
+  uint8_t next_state[128][2];      // [state][is_lps]
+  uint8_t ctx_init[CX_COUNT];      // initValue per context (initType 0)
+  uint8_t sig_b4[2][3][16];        // [chroma][scanIdx][k]
+  uint8_t sig_sb[2][3][2][4][3][16];
+  uint8_t scan_pos[3][16];         // 4x4 scan: x | y << 2
+  uint8_t scan_sub[4][3][64];      // sub-block scan for log2 (0..3) grids: x | y << 3
+  uint8_t inv_sub[4][3][64];       // [log2][scanIdx][x + (y << log2)] -> scan index
+  uint8_t inv_pos[3][16];
+  uint8_t mode422[35];
+  int8_t qpc420[14];
+};
+
+struct Slice {
+  int32_t segment_address, slice_addr_rs, slice_qp_y;
+  uint32_t data_begin, data_end;     // slice_segment_data bytes inside Pic::bytes (data_end excludes the padding)
+  int8_t cb_qp_offset, cr_qp_offset, beta_offset, tc_offset;
+  uint8_t dependent, sao_luma, sao_chroma, deblocking_disabled, loop_filter_across_slices, pad[3];
+};
+
+struct Pic {
+  // geometry / parameter sets (flattened Sps / Pps, host/hevc_params.h)
+  int32_t W, H, w8, h8, w4, h4, ctbs_w, ctbs_h;
+  int32_t log2_ctb, log2_min_cb, log2_min_tb, log2_max_tb, max_th_depth_intra;
+  int32_t chroma_array_type, sub_w, sub_h, bit_depth_y, bit_depth_c, qp_bd_offset_y, qp_bd_offset_c;
+  int32_t log2_max_transform_skip_size, log2_min_cu_qp_delta_size, pps_cb_qp_offset, pps_cr_qp_offset;
+  int32_t log2_sao_offset_scale_luma, log2_sao_offset_scale_chroma;
+  uint8_t transform_skip_enabled, sign_data_hiding, cu_qp_delta_enabled, entropy_coding_sync;
+  uint8_t implicit_rdpcm, tskip_rotation, tskip_context, pps_loop_filter_across_slices;
+  uint32_t pic_index;                // picture index in the batch (hc_tb::pic)
+  uint32_t tb_global_base;           // index of this picture's first hc_tb in the batch array
+  // per-CTB capacities
+  uint32_t blk_cap[3], blk_cap_ctb, tb_cap_ctb, coeff_cap_ctb, resid_cap_ctb;
+  // inputs
+  const uint8_t* bytes;
+  const Slice* slices;
+  const int32_t* ctb_slice;          // per CTB (RS): index into slices
+  const uint8_t* ctu_static;         // per CTB: sao_nb, sao_nb_c, flags, 0
+  // scratch maps
+  uint8_t* ct_depth;                 // per 8x8
+  uint8_t* ipm;                      // per 4x4
+  uint8_t* ipm_c;
+  uint8_t* wpp_ctx;                  // ctbs_h * CTX_BYTES
+  int* progress;                     // per CTB row: CTBs parsed
+  int* error;
+  // outputs
+  int8_t* qp_map;                    // per 8x8 (is QP_Y while parsing)
+  uint8_t* edge_map;                 // per 4x4
+  hc_ctu* ctus;
+  hc_blk* blks;
+  hc_tb* tbs;
+  hc_coeff* coeffs;
+  uint32_t* tb_lists[4];             // batch-global K1 launch lists
+  unsigned int* tb_counts;           // 4 counters
+};
+
+// One substream: CTBs [first_ctb, end_ctb) of one slice segment, starting at byte `byte_begin` of Pic::bytes
+// (byte_begin == 0xffffffff: continue where the previous substream of the chain stopped).
+struct Sub {
+  uint32_t pic, slice;
+  int32_t first_ctb, end_ctb;
+  uint32_t byte_begin;
+  uint32_t flags;                    // SUB_*
+};
+constexpr uint32_t SUB_ROW_CHAIN = 1;   // parallel mode: this substream is one CTB row, synchronised with the row above
+struct Chain { uint32_t first_sub, nsubs; };
+
+constexpr int ERR_NONE = 0, ERR_BITSTREAM = 1, ERR_CAPACITY = 2;
+
+// ---- platform glue ------------------------------------------------------------------------------------------
+#if defined(__CUDA_ARCH__)
+HC_D int k0_clz(unsigned v) { return __clz((int)v); }
+HC_D int progress_load(const int* p) { return ld_acquire_s32(p); }
+HC_D void progress_store(int* p, int v) { __threadfence(); st_release_s32(p, v); }
+HC_D unsigned list_append(unsigned int* counter) { return atomicAdd(counter, 1u); }
+HC_D void backoff() { __nanosleep(200); }
+#else
+HC_HD int k0_clz(unsigned v) { return __builtin_clz(v); }
+HC_HD int progress_load(const int* p) { return *p; }
+HC_HD void progress_store(int* p, int v) { *p = v; }
+HC_HD unsigned list_append(unsigned int* counter) { return (*counter)++; }
+HC_HD void backoff() {}
+#endif
+
+// ---- arithmetic decoder: same design as host/hevc_cabac.h (offset + look-ahead in one 64-bit register) --------
+struct Cabac {
+  const uint8_t* start;
+  const uint8_t* cur;
+  const uint8_t* end;
+  unsigned long long value;
+  uint32_t range;
+  int avail;
+  const Tables* T;
+
+  HC_HD static uint32_t be32(const uint8_t* p) { return ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | p[3]; }
+  HC_HD void refill() {
+    if (avail < 16) {
+      value = (value << 32) | be32(cur);
+      cur += 4;
+      avail += 32;
+    }
+  }
+  HC_HD void init(const uint8_t* p, const uint8_t* e) {
+    start = p; end = e;
+    range = 510;
+    value = be32(p);
+    cur = p + 4;
+    avail = 32 - 9;
+  }
+  HC_HD const uint8_t* position() const {
+    const long long shifts = (long long)(cur - start) * 8 - 9 - avail;
+    return start + 2 + (shifts >> 3);
+  }
+  HC_HD bool overrun() const { return position() > end; }
+  HC_HD int bin(uint8_t& state) {
+    const uint32_t st = state;
+    const uint32_t lps = T->range_lps[st >> 1][(range >> 6) & 3];
+    const uint32_t rmps = range - lps;
+    const unsigned long long scaled = (unsigned long long)rmps << avail;
+    const uint32_t is_lps = value >= scaled;
+    if (is_lps) value -= scaled;
+    const uint32_t r = is_lps ? lps : rmps;
+    const int n = k0_clz(r) - 23;
+    range = r << n;
+    avail -= n;
+    state = T->next_state[st][is_lps];
+    refill();
+    return (int)((st & 1) ^ is_lps);
+  }
+  HC_HD int bypass() {
+    avail--;
+    const unsigned long long scaled = (unsigned long long)range << avail;
+    int b = 0;
+    if (value >= scaled) { value -= scaled; b = 1; }
+    refill();
+    return b;
+  }
+  HC_HD uint32_t bypass_bits(int n) {
+    uint32_t out = 0;
+    while (n > 0) {
+      const int k = n > 16 ? 16 : n;
+      avail -= k;
+      const uint32_t q = (uint32_t)(value >> avail) / range;
+      value -= (unsigned long long)(q * range) << avail;
+      out = (out << k) | q;
+      refill();
+      n -= k;
+    }
+    return out;
+  }
+  HC_HD uint32_t peek16() const { return (uint32_t)(value >> (avail - 16)) / range; }
+  HC_HD void consume(int n, uint32_t bins) {
+    avail -= n;
+    value -= (unsigned long long)(bins * range) << avail;
+    refill();
+  }
+  HC_HD int terminate() {
+    range -= 2;
+    const unsigned long long scaled = (unsigned long long)range << avail;
+    if (value >= scaled) return 1;
+    if (range < 256) { range <<= 1; avail--; }
+    refill();
+    return 0;
+  }
+};
+
+HC_HD uint8_t ctx_init_state(int init_value, int slice_qp) {
+  const int slope = init_value >> 4, offs = init_value & 15;
+  const int m = slope * 5 - 45, n = (offs << 3) - 16;
+  const int q = slice_qp < 0 ? 0 : (slice_qp > 51 ? 51 : slice_qp);
+  int pre = ((m * q) >> 4) + n;
+  pre = pre < 1 ? 1 : (pre > 126 ? 126 : pre);
+  const int mps = pre <= 63 ? 0 : 1;
+  const int st = mps ? pre - 64 : 63 - pre;
+  return (uint8_t)((st << 1) | mps);
+}
+
+HC_HD int morton4(int x, int y) {   // interleave up to 4 bits of x (even positions) and y (odd positions)
+  int r = 0;
+
+  for (int b = 0; b < 4; b++) r |= (((x >> b) & 1) << (2 * b)) | (((y >> b) & 1) << (2 * b + 1));
+  return r;
+}
+
+// ---- the parser of one chain ---------------------------------------------------------------------------------
+struct Parser {
+  const Tables* T;
+  const Pic* P;
+  const Slice* sh;
+  uint8_t* ctx;            // CTX_BYTES context states (shared memory on the device)
+  Cabac cabac;
+  int err;
+  // CTB state
+  int ctb_rs, ctb_x, ctb_y;
+  uint32_t nblk[3], ntb, ncoeff, nresid;       // used inside the current CTB
+  // CU / QG state
+  bool IsCuQpDeltaCoded;
+  int CuQpDeltaVal;
+  int currentQG_x, currentQG_y, lastQPYinPreviousQG, currentQPY;
+  int qPYPrime, qPCbPrime, qPCrPrime;
+  int cu_x0, cu_y0, cu_log2;
+  int filterLeftCbEdge, filterTopCbEdge;
+
+  HC_HD int bin(int c) { return cabac.bin(ctx[c]); }
+  HC_HD void fail(int code) { if (!err) err = code; }
+  HC_HD void init_contexts() {
+    for (int i = 0; i < CX_COUNT; i++) ctx[i] = ctx_init_state(T->ctx_init[i], sh->slice_qp_y);
+  }
+
+  // ---- availability (no tiles: TS == RS) ----
+  HC_HD int ctb_of(int x, int y) const { return (x >> P->log2_ctb) + (y >> P->log2_ctb) * P->ctbs_w; }
+  HC_HD int slice_addr_of_ctb(int n) const { return P->slices[P->ctb_slice[n]].slice_addr_rs; }
+  HC_HD bool ctb_available(int xC, int yC, int xN, int yN) const {
+    if (xN < 0 || yN < 0 || xN >= P->W || yN >= P->H) return false;
+    return slice_addr_of_ctb(ctb_of(xN, yN)) == slice_addr_of_ctb(ctb_of(xC, yC));
+  }
+  HC_HD int zs_addr(int x, int y) const {
+    const int sh2 = P->log2_ctb - P->log2_min_tb, mask = (1 << P->log2_ctb) - 1;
+    return (ctb_of(x, y) << (2 * sh2)) + morton4((x & mask) >> P->log2_min_tb, (y & mask) >> P->log2_min_tb);
+  }
+  HC_HD bool available_zscan(int xC, int yC, int xN, int yN) const {
+    if (xN < 0 || yN < 0 || xN >= P->W || yN >= P->H) return false;
+    if (zs_addr(xN, yN) > zs_addr(xC, yC)) return false;
+    return ctb_available(xC, yC, xN, yN);
+  }
+
+  // ---- 7.3.8.3 SAO ----
+  K0_FN void read_sao(hc_ctu& ctu) {
+    const Pic& p = *P;
+    bool merge_left = false, merge_up = false;
+    if (ctb_x > 0 && slice_addr_of_ctb(ctb_rs - 1) == sh->slice_addr_rs) merge_left = bin(CX_SAO_MERGE);
+    if (ctb_y > 0 && !merge_left && slice_addr_of_ctb(ctb_rs - p.ctbs_w) == sh->slice_addr_rs) merge_up = bin(CX_SAO_MERGE);
+    if (merge_left || merge_up) {
+      const hc_ctu& src = p.ctus[merge_left ? ctb_rs - 1 : ctb_rs - p.ctbs_w];
+      for (int c = 0; c < 3; c++) {
+        ctu.sao_type[c] = src.sao_type[c];
+        ctu.sao_band_or_class[c] = src.sao_band_or_class[c];
+        for (int i = 0; i < 4; i++) ctu.sao_offset[c][i] = src.sao_offset[c][i];
+      }
+      if (!sh->sao_luma) ctu.sao_type[0] = 0;
+      if (!sh->sao_chroma) ctu.sao_type[1] = ctu.sao_type[2] = 0;
+      return;
+    }
+    const int ncomp = p.chroma_array_type != 0 ? 3 : 1;
+    for (int c = 0; c < ncomp; c++) {
+      if (!((sh->sao_luma && c == 0) || (sh->sao_chroma && c > 0))) { ctu.sao_type[c] = 0; continue; }
+      if (c < 2) {
+        int t = 0;
+        if (bin(CX_SAO_TYPE)) t = cabac.bypass() ? 2 : 1;
+        ctu.sao_type[c] = (uint8_t)t;
+      } else {
+        ctu.sao_type[2] = ctu.sao_type[1];
+      }
+      if (ctu.sao_type[c] == 0) continue;
+      const int bitDepth = c == 0 ? p.bit_depth_y : p.bit_depth_c;
+      const int cMax = (1 << ((bitDepth < 10 ? bitDepth : 10) - 5)) - 1;
+      int absv[4];
+      for (int i = 0; i < 4; i++) {
+        int v = 0;
+        while (v < cMax && cabac.bypass()) v++;
+        absv[i] = v;
+      }
+      const int scale = c == 0 ? p.log2_sao_offset_scale_luma : p.log2_sao_offset_scale_chroma;
+      if (ctu.sao_type[c] == 1) {
+        int sign[4] = {0, 0, 0, 0};
+        for (int i = 0; i < 4; i++)
+          if (absv[i]) sign[i] = cabac.bypass();
+        ctu.sao_band_or_class[c] = (uint8_t)cabac.bypass_bits(5);
+        for (int i = 0; i < 4; i++) ctu.sao_offset[c][i] = (int8_t)((sign[i] ? -absv[i] : absv[i]) * (1 << scale));
+      } else {
+        if (c < 2) ctu.sao_band_or_class[c] = (uint8_t)cabac.bypass_bits(2);
+        else ctu.sao_band_or_class[2] = ctu.sao_band_or_class[1];
+        ctu.sao_offset[c][0] = (int8_t)(absv[0] * (1 << scale));
+        ctu.sao_offset[c][1] = (int8_t)(absv[1] * (1 << scale));
+        ctu.sao_offset[c][2] = (int8_t)(-absv[2] * (1 << scale));
+        ctu.sao_offset[c][3] = (int8_t)(-absv[3] * (1 << scale));
+      }
+    }
+  }
+
+  // ---- 8.6.1 QP derivation (transform.cc:31-210 bookkeeping) ----
+  K0_FN void derive_qp(int xCU, int yCU) {
+    const Pic& p = *P;
+    const int qgmask = (1 << p.log2_min_cu_qp_delta_size) - 1;
+    const int xQG = xCU - (xCU & qgmask), yQG = yCU - (yCU & qgmask);
+    if (xQG != currentQG_x || yQG != currentQG_y) {
+      lastQPYinPreviousQG = currentQPY;
+      currentQG_x = xQG;
+      currentQG_y = yQG;
+    }
+    const int ctbmask = (1 << p.log2_ctb) - 1;
+    const bool firstInCTBRow = (xQG == 0 && (yQG & ctbmask) == 0);
+    const int sx = (sh->slice_addr_rs % p.ctbs_w) << p.log2_ctb, sy = (sh->slice_addr_rs / p.ctbs_w) << p.log2_ctb;
+    const bool firstQGInSlice = (sx == xQG && sy == yQG);
+    int pred = (firstQGInSlice || (firstInCTBRow && p.entropy_coding_sync)) ? sh->slice_qp_y : lastQPYinPreviousQG;
+    int qA = pred, qB = pred;
+    if (available_zscan(xQG, yQG, xQG - 1, yQG) && ctb_of(xQG - 1, yQG) == ctb_rs) qA = p.qp_map[((xQG - 1) >> 3) + (yQG >> 3) * p.w8];
+    if (available_zscan(xQG, yQG, xQG, yQG - 1) && ctb_of(xQG, yQG - 1) == ctb_rs) qB = p.qp_map[(xQG >> 3) + ((yQG - 1) >> 3) * p.w8];
+    pred = (qA + qB + 1) >> 1;
+    const int QPY = ((pred + CuQpDeltaVal + 52 + 2 * p.qp_bd_offset_y) % (52 + p.qp_bd_offset_y)) - p.qp_bd_offset_y;
+    qPYPrime = QPY + p.qp_bd_offset_y < 0 ? 0 : QPY + p.qp_bd_offset_y;
+    const int qPiCb = clip3i(-p.qp_bd_offset_c, 57, QPY + p.pps_cb_qp_offset + sh->cb_qp_offset);
+    const int qPiCr = clip3i(-p.qp_bd_offset_c, 57, QPY + p.pps_cr_qp_offset + sh->cr_qp_offset);
+    int qPCb = qPiCb, qPCr = qPiCr;   // the reference does not cap non-4:2:0 at 51 (transform.cc:175-178)
+    if (p.chroma_array_type == 1) {
+      qPCb = qPiCb < 30 ? qPiCb : (qPiCb >= 44 ? qPiCb - 6 : T->qpc420[qPiCb - 30]);
+      qPCr = qPiCr < 30 ? qPiCr : (qPiCr >= 44 ? qPiCr - 6 : T->qpc420[qPiCr - 30]);
+    }
+    qPCbPrime = qPCb + p.qp_bd_offset_c < 0 ? 0 : qPCb + p.qp_bd_offset_c;
+    qPCrPrime = qPCr + p.qp_bd_offset_c < 0 ? 0 : qPCr + p.qp_bd_offset_c;
+    const int n8 = ((1 << cu_log2) >> 3) < 1 ? 1 : ((1 << cu_log2) >> 3);
+    for (int y = 0; y < n8; y++)
+      for (int x = 0; x < n8; x++) {
+        const int xx = (cu_x0 >> 3) + x, yy = (cu_y0 >> 3) + y;
+        if (xx < p.w8 && yy < p.h8) p.qp_map[xx + yy * p.w8] = (int8_t)QPY;
+      }
+    currentQPY = QPY;
+  }
+
+  HC_HD void mark_tu_edges(int x0, int y0, int log2) {
+    if (sh->deblocking_disabled) return;
+    const Pic& p = *P;
+    const int n4 = (1 << log2) >> 2;
+    const int left = (x0 == cu_x0) ? filterLeftCbEdge : 1, top = (y0 == cu_y0) ? filterTopCbEdge : 1;
+    if (left)
+      for (int k = 0; k < n4; k++) p.edge_map[(x0 >> 2) + ((y0 >> 2) + k) * p.w4] |= HC_EDGE_V;
+    if (top)
+      for (int k = 0; k < n4; k++) p.edge_map[((x0 >> 2) + k) + (y0 >> 2) * p.w4] |= HC_EDGE_H;
+  }
+
+  // neighbour availability of one prediction block (intrapred.h:443-543, :838-940)
+  K0_FN void emit_blk(int cIdx, int xB, int yB, int log2, int mode, bool has_resid, uint32_t resid_off) {
+    const Pic& p = *P;
+    const int nT = 1 << log2;
+    const int SubW = cIdx == 0 ? 1 : p.sub_w, SubH = cIdx == 0 ? 1 : p.sub_h;
+    const int xBL = xB * SubW, yBL = yB * SubH;
+    bool aL = true, aT = true, aTR = true, aTL = true;
+    if (xBL == 0) { aL = false; aTL = false; }
+    if (yBL == 0) { aT = false; aTL = false; aTR = false; }
+    if (xBL + nT * SubW >= p.W) aTR = false;
+    const int l2c = p.log2_ctb, cw = p.ctbs_w;
+    const int xCur = xBL >> l2c, yCur = yBL >> l2c;
+    const int xLeft = (xBL - 1) >> l2c, xRight = (xBL + nT * SubW) >> l2c, yTop = (yBL - 1) >> l2c;
+    const int sa = slice_addr_of_ctb(xCur + yCur * cw);
+    if (aL && slice_addr_of_ctb(xLeft + yCur * cw) != sa) aL = false;
+    if (aT && slice_addr_of_ctb(xCur + yTop * cw) != sa) aT = false;
+    if (aTL && slice_addr_of_ctb(xLeft + yTop * cw) != sa) aTL = false;
+    if (aTR && slice_addr_of_ctb(xRight + yTop * cw) != sa) aTR = false;
+    int nBottom = (p.H - yBL + SubH - 1) / SubH;
+    if (nBottom > 2 * nT) nBottom = 2 * nT;
+    int nRight = (p.W - xBL + SubW - 1) / SubW;
+    if (nRight > 2 * nT) nRight = 2 * nT;
+    const int currAddr = zs_addr(xBL, yBL);
+    unsigned left = 0, top = 0;
+    if (aL)
+      for (int y = nBottom - 1; y >= 0; y -= 4)
+        if (zs_addr((xB - 1) * SubW, (yB + y) * SubH) <= currAddr) left |= 1u << (y >> 2);
+    bool tl = false;
+    if (aTL) tl = zs_addr((xB - 1) * SubW, (yB - 1) * SubH) <= currAddr;
+    for (int x = 0; x < nRight; x += 4) {
+      const bool ba = x < nT ? aT : aTR;
+      if (ba && zs_addr((xB + x) * SubW, (yB - 1) * SubH) <= currAddr) top |= 1u << (x >> 2);
+    }
+    if (nblk[cIdx] >= p.blk_cap[cIdx]) { fail(ERR_CAPACITY); return; }
+    uint32_t base = (uint32_t)ctb_rs * p.blk_cap_ctb;
+    for (int c = 0; c < cIdx; c++) base += p.blk_cap[c];
+    hc_blk b;
+    b.x = (uint16_t)xB;
+    b.y = (uint16_t)yB;
+    b.log2 = (uint8_t)log2;
+    b.mode = (uint8_t)mode;
+    b.flags = (uint8_t)((tl ? HC_BLK_AVAIL_TL : 0) | (has_resid ? HC_BLK_HAS_RESID : 0));
+    b.cidx = (uint8_t)cIdx;
+    b.avail_left = (uint16_t)left;
+    b.avail_top = (uint16_t)top;
+    b.resid_off = has_resid ? resid_off : 0;
+    p.blks[base + nblk[cIdx]++] = b;
+  }
+
+  // ---- 7.3.8.11 residual_coding ----
+  K0_FN uint32_t residual_coding(int log2, int cIdx, int pred_mode) {
+    const Pic& p = *P;
+    bool tskip = false;
+    if (p.transform_skip_enabled && log2 <= p.log2_max_transform_skip_size) tskip = bin(CX_TSKIP + (cIdx ? 1 : 0));
+
+    // last significant coefficient position
+    int last[2];
+    for (int d = 0; d < 2; d++) {
+      const int cMax = (log2 << 1) - 1;
+      int offset, shift;
+      if (cIdx == 0) { offset = 3 * (log2 - 2) + ((log2 - 1) >> 2); shift = (log2 + 1) >> 2; }
+      else { offset = 15; shift = log2 - 2; }
+      int v = 0;
+      const int base = d ? CX_LAST_Y : CX_LAST_X;
+      while (v < cMax && bin(base + offset + (v >> shift))) v++;
+      last[d] = v;
+    }
+    int LastX = last[0], LastY = last[1];
+    if (last[0] > 3) { const int nb = (last[0] >> 1) - 1; LastX = ((2 + (last[0] & 1)) << nb) + (int)cabac.bypass_bits(nb); }
+    if (last[1] > 3) { const int nb = (last[1] >> 1) - 1; LastY = ((2 + (last[1] & 1)) << nb) + (int)cabac.bypass_bits(nb); }
+
+    int scanIdx = 0;
+    if (log2 == 2 || (log2 == 3 && (cIdx == 0 || p.chroma_array_type == 3))) {
+      if (pred_mode >= 6 && pred_mode <= 14) scanIdx = 2;
+      else if (pred_mode >= 22 && pred_mode <= 30) scanIdx = 1;
+    }
+    if (scanIdx == 2) { const int t = LastX; LastX = LastY; LastY = t; }
+    const int nT = 1 << log2;
+    if (LastX >= nT || LastY >= nT) { fail(ERR_BITSTREAM); return 0; }
+
+    const int lsb = log2 - 2;
+    const uint8_t* scanSub = T->scan_sub[lsb][scanIdx];
+    const uint8_t* scanPos = T->scan_pos[scanIdx];
+    const int sbW = 1 << lsb;
+    const int lastSubBlock = T->inv_sub[lsb][scanIdx][(LastX >> 2) + ((LastY >> 2) << lsb)];
+    const int lastScanPos = T->inv_pos[scanIdx][(LastX & 3) + ((LastY & 3) << 2)];
+
+    uint8_t csbf_nb[64];
+    for (int i = 0; i < sbW * sbW; i++) csbf_nb[i] = 0;
+
+    if (ntb >= p.tb_cap_ctb || nresid + (uint32_t)(nT * nT) > p.resid_cap_ctb) { fail(ERR_CAPACITY); return 0; }
+    const uint32_t coeff_first = (uint32_t)ctb_rs * p.coeff_cap_ctb + ncoeff;
+    hc_coeff* out = p.coeffs + coeff_first;
+    const uint32_t coeff_room = p.coeff_cap_ctb - ncoeff;
+
+    hc_tb tb;
+    tb.coeff_off = coeff_first;
+    tb.resid_off = (uint32_t)ctb_rs * p.resid_cap_ctb + nresid;
+    tb.pic = (uint16_t)p.pic_index;
+    tb.log2 = (uint8_t)log2;
+    tb.qp = (uint8_t)(cIdx == 0 ? qPYPrime : (cIdx == 1 ? qPCbPrime : qPCrPrime));
+    tb.matrix_id = (uint8_t)(log2 == 5 ? 0 : cIdx);
+    uint8_t type = (uint8_t)cIdx;
+    if (tskip) type |= HC_TB_TSKIP;
+    else if (log2 == 2 && cIdx == 0) type |= HC_TB_DST;
+    if (p.implicit_rdpcm && tskip && (pred_mode == 10 || pred_mode == 26)) type |= (pred_mode == 26) ? HC_TB_RDPCM_V : HC_TB_RDPCM_H;
+    if (p.tskip_rotation && log2 == 2 && tskip) type |= HC_TB_ROTATE;
+    tb.type = type;
+
+    const bool ts_ctx = p.tskip_context && tskip;
+    const bool sign_hiding_possible = p.sign_data_hiding && !(p.implicit_rdpcm && tskip && (pred_mode == 10 || pred_mode == 26));
+    int c1 = 1;
+    uint32_t ncoeff_total = 0;
+    const int chroma = cIdx ? 1 : 0;
+
+    for (int i = lastSubBlock; i >= 0; i--) {
+      const int Sx = scanSub[i] & 7, Sy = scanSub[i] >> 3;
+      int inferSbDc = 0, coded = 1;
+      if (i < lastSubBlock && i > 0) {
+        coded = bin(CX_CSBF + (csbf_nb[Sx + Sy * sbW] ? 1 : 0) + (cIdx ? 2 : 0));
+        inferSbDc = 1;
+      }
+      if (!coded) continue;
+      if (Sx > 0) csbf_nb[Sx - 1 + Sy * sbW] |= 1;
+      if (Sy > 0) csbf_nb[Sx + (Sy - 1) * sbW] |= 2;
+
+      int16_t value[16];
+      int8_t spos[16];
+      uint8_t maxbase[16];
+      int n = 0;
+      const int prevCsbf = csbf_nb[Sx + Sy * sbW];
+      const int xS0 = Sx << 2, yS0 = Sy << 2;
+      const uint8_t* sigtab = log2 == 2 ? T->sig_b4[chroma][scanIdx]
+                                        : T->sig_sb[chroma][log2 == 3 ? (scanIdx == 0 ? 0 : 1) : 2][(Sx | Sy) ? 1 : 0][prevCsbf][scanIdx];
+      const int ts_c = chroma ? 43 : 42;
+      const int dc_ctx = ts_ctx ? ts_c : ((log2 == 2 || i > 0) ? sigtab[0] : (chroma ? 27 : 0));
+
+      const int last_coeff = (i == lastSubBlock) ? lastScanPos - 1 : 15;
+      if (i == lastSubBlock) spos[n++] = (int8_t)lastScanPos;
+      for (int k = last_coeff; k > 0; k--) {
+        const int b = bin(CX_SIG + (ts_ctx ? ts_c : sigtab[k]));
+        spos[n] = (int8_t)k;
+        n += b;
+      }
+      if (last_coeff >= 0) {
+        if (n > 0 || !inferSbDc) {
+          const int b = bin(CX_SIG + dc_ctx);
+          spos[n] = 0;
+          n += b;
+        } else {
+          spos[n++] = 0;
+        }
+      }
+      if (n == 0) continue;
+
+      int ctxSet = (i == 0 || cIdx > 0) ? 0 : 2;
+      if (c1 == 0) ctxSet++;
+      c1 = 1;
+      int firstG1 = 16;
+      const int ng1 = n < 8 ? n : 8;
+      const int g1base = CX_G1 + ctxSet * 4 + (cIdx > 0 ? 16 : 0);
+      for (int c = 0; c < ng1; c++) {
+        const int b = bin(g1base + c1);
+        value[c] = (int16_t)(1 + b);
+        maxbase[c] = (uint8_t)b;
+        if (b && c < firstG1) firstG1 = c;
+        c1 = b ? 0 : ((c1 > 0 && c1 < 3) ? c1 + 1 : c1);
+      }
+      for (int c = ng1; c < n; c++) { value[c] = 1; maxbase[c] = 1; }
+      if (firstG1 < 16) {
+        const int f = bin(CX_G2 + ctxSet + (cIdx > 0 ? 4 : 0));
+        value[firstG1] = (int16_t)(value[firstG1] + f);
+        maxbase[firstG1] = (uint8_t)f;
+      }
+
+      const bool signHidden = sign_hiding_possible && (spos[0] - spos[n - 1] > 3);
+      const int nsign = signHidden ? n - 1 : n;
+      const uint32_t signs = cabac.bypass_bits(nsign) << (16 - nsign);
+
+      if (ncoeff_total + (uint32_t)n > coeff_room) { fail(ERR_CAPACITY); return 0; }
+      int sumAbs = 0, rice = 0;
+      for (int c = 0; c < n; c++) {
+        const int base = value[c];
+        int rem = 0;
+        if (maxbase[c]) {
+          const uint32_t q16 = cabac.peek16();
+          const int ones = q16 == 0xffffu ? 16 : k0_clz(~(q16 << 16));
+          const int suffix_len = ones <= 3 ? rice : ones - 3 + rice;
+          const int len = ones + 1 + suffix_len;
+          if (len <= 16) {
+            const uint32_t bins = q16 >> (16 - len);
+            const int suffix = (int)(bins & ((1u << suffix_len) - 1u));
+            rem = ones <= 3 ? (ones << rice) + suffix : (((1 << (ones - 3)) + 3 - 1) << rice) + suffix;
+            cabac.consume(len, bins);
+          } else {
+            int prefix = 0;
+            while (prefix < 32 && cabac.bypass()) prefix++;
+            if (prefix >= 32) { fail(ERR_BITSTREAM); return 0; }
+            if (prefix <= 3) rem = (prefix << rice) + (int)cabac.bypass_bits(rice);
+            else rem = (((1 << (prefix - 3)) + 3 - 1) << rice) + (int)cabac.bypass_bits(prefix - 3 + rice);
+          }
+          if (base + rem > 3 * (1 << rice)) { rice++; if (rice > 4) rice = 4; }
+        }
+        int16_t level = (int16_t)(base + rem);
+        const bool neg = (c < nsign) ? ((signs >> (15 - c)) & 1) : false;
+        if (neg) level = (int16_t)-level;
+        if (signHidden) {
+          sumAbs += base + rem;
+          if (c == n - 1 && (sumAbs & 1)) level = (int16_t)-level;
+        }
+        const int sp = scanPos[spos[c]];
+        hc_coeff co;
+        co.pos = (uint16_t)((xS0 + (sp & 3)) + (yS0 + (sp >> 2)) * nT);
+        co.level = level;
+        out[ncoeff_total++] = co;
+      }
+    }
+    tb.ncoeff = (uint16_t)ncoeff_total;
+    const uint32_t tb_local = (uint32_t)ctb_rs * p.tb_cap_ctb + ntb;
+    p.tbs[tb_local] = tb;
+    ntb++;
+    ncoeff += ncoeff_total;
+    nresid += (uint32_t)(nT * nT);
+    const unsigned slot = list_append(p.tb_counts + (log2 - 2));
+    p.tb_lists[log2 - 2][slot] = p.tb_global_base + tb_local;
+    return tb.resid_off;
+  }
+
+  // ---- 7.3.8.10 transform_unit (record emission in the reference's reconstruction order, slice.cc:3979-4118) ----
+  K0_FN void transform_unit(int x0, int y0, int xBase, int yBase, int log2, int blkIdx, int cbf_luma, int cbf_cb, int cbf_cr) {
+    const Pic& p = *P;
+    const int cat = p.chroma_array_type;
+    const int log2C = cat == 3 ? log2 : (log2 - 1 < 2 ? 2 : log2 - 1);
+    if ((cbf_luma || cbf_cb || cbf_cr) && p.cu_qp_delta_enabled && !IsCuQpDeltaCoded) {
+      int v = 0;
+      if (bin(CX_CU_QP_DELTA)) {
+        v = 1;
+        while (v < 5 && bin(CX_CU_QP_DELTA + 1)) v++;
+        if (v == 5) {
+          int k = 0;
+          while (k < 32 && cabac.bypass()) k++;
+          if (k >= 32) { fail(ERR_BITSTREAM); return; }
+          v += ((1 << k) - 1) + (int)cabac.bypass_bits(k);
+        }
+      }
+      int sign = 0;
+      if (v) sign = cabac.bypass();
+      IsCuQpDeltaCoded = true;
+      CuQpDeltaVal = sign ? -v : v;
+      derive_qp(cu_x0, cu_y0);
+    }
+    mark_tu_edges(x0, y0, log2);
+
+    const int modeY = p.ipm[(x0 >> 2) + (y0 >> 2) * p.w4];
+    uint32_t roff = 0;
+    if (cbf_luma) roff = residual_coding(log2, 0, modeY);
+    if (err) return;
+    emit_blk(0, x0, y0, log2, modeY, cbf_luma != 0, roff);
+    if (cat == 0) return;
+    const int SubW = p.sub_w, SubH = p.sub_h;
+    const bool own = log2 > 2 || cat == 3;     // chroma of this TU; else the parent's chroma with the 4th 4x4 luma block
+    if (!own && blkIdx != 3) return;
+    const int bx = own ? x0 : xBase, by = own ? y0 : yBase;
+    const int l2 = own ? log2C : 2, nTC = 1 << l2;
+    for (int c = 1; c <= 2; c++) {
+      const int cbf = c == 1 ? cbf_cb : cbf_cr;
+      const int nblk2 = cat == 2 ? 2 : 1;
+      for (int t = 0; t < nblk2; t++) {
+        const int xB = bx / SubW, yB = by / SubH + t * nTC;
+        const int lx = xB * SubW, ly = yB * SubH;   // mode lookup position of the reference (slice.cc:3760-3763)
+        const int m = p.ipm_c[((lx < p.W - 1 ? lx : p.W - 1) >> 2) + ((ly < p.H - 1 ? ly : p.H - 1) >> 2) * p.w4];
+        uint32_t ro = 0;
+        const bool coded = (cbf >> t) & 1;
+        if (coded) ro = residual_coding(l2, c, m);
+        if (err) return;
+        emit_blk(c, xB, yB, l2, m, coded, ro);
+      }
+    }
+  }
+
+  // ---- 7.3.8.8 transform_tree: compile-time recursion over the block size ----
+  template <int LOG2>
+  K0_FN void transform_tree(int x0, int y0, int xBase, int yBase, int depth, int blkIdx, int max_depth, int intra_split,
+                            int parent_cbf_cb, int parent_cbf_cr) {
+    const Pic& p = *P;
+    if (err || cabac.overrun()) { fail(ERR_BITSTREAM); return; }
+    int split;
+    if (LOG2 <= p.log2_max_tb && LOG2 > p.log2_min_tb && depth < max_depth && !(intra_split && depth == 0)) split = bin(CX_SPLIT_TRANSFORM + 5 - LOG2);
+    else split = (LOG2 > p.log2_max_tb || (intra_split && depth == 0)) ? 1 : 0;
+    int cbf_cb = -1, cbf_cr = -1;
+    if ((LOG2 > 2 && p.chroma_array_type != 0) || p.chroma_array_type == 3) {
+      if (parent_cbf_cb) {
+        cbf_cb = bin(CX_CBF_CHROMA + depth);
+        if (p.chroma_array_type == 2 && (!split || LOG2 == 3)) cbf_cb |= bin(CX_CBF_CHROMA + depth) << 1;
+      }
+      if (parent_cbf_cr) {
+        cbf_cr = bin(CX_CBF_CHROMA + depth);
+        if (p.chroma_array_type == 2 && (!split || LOG2 == 3)) cbf_cr |= bin(CX_CBF_CHROMA + depth) << 1;
+      }
+    }
+    if (cbf_cb < 0) cbf_cb = (depth > 0 && LOG2 == 2) ? parent_cbf_cb : 0;
+    if (cbf_cr < 0) cbf_cr = (depth > 0 && LOG2 == 2) ? parent_cbf_cr : 0;
+    if (split) {
+      if (LOG2 > 2) {
+        constexpr int L = LOG2 > 2 ? LOG2 - 1 : 2;
+        constexpr int h = 1 << L;
+        transform_tree<L>(x0, y0, x0, y0, depth + 1, 0, max_depth, intra_split, cbf_cb, cbf_cr);
+        transform_tree<L>(x0 + h, y0, x0, y0, depth + 1, 1, max_depth, intra_split, cbf_cb, cbf_cr);
+        transform_tree<L>(x0, y0 + h, x0, y0, depth + 1, 2, max_depth, intra_split, cbf_cb, cbf_cr);
+        transform_tree<L>(x0 + h, y0 + h, x0, y0, depth + 1, 3, max_depth, intra_split, cbf_cb, cbf_cr);
+      } else {
+        fail(ERR_BITSTREAM);
+      }
+    } else {
+      const int cbf_luma = bin(CX_CBF_LUMA + (depth == 0 ? 1 : 0));
+      transform_unit(x0, y0, xBase, yBase, LOG2, blkIdx, cbf_luma, cbf_cb, cbf_cr);
+    }
+  }
+
+  // ---- 7.3.8.5 coding_unit (I slices) ----
+  template <int LOG2>
+  K0_FN void coding_unit(int x0, int y0, int depth) {
+    const Pic& p = *P;
+    constexpr int nCbS = 1 << LOG2;
+    cu_x0 = x0; cu_y0 = y0; cu_log2 = LOG2;
+    {
+      constexpr int n8 = nCbS >> 3;
+      for (int y = 0; y < n8; y++)
+        for (int x = 0; x < n8; x++) p.ct_depth[((x0 >> 3) + x) + ((y0 >> 3) + y) * p.w8] = (uint8_t)depth;
+    }
+    // deblocking: which CU edges may be filtered (deblock.cc:165-215)
+    filterLeftCbEdge = x0 != 0;
+    filterTopCbEdge = y0 != 0;
+    {
+      const int ctbmask = (1 << p.log2_ctb) - 1;
+      if (x0 && (x0 & ctbmask) == 0 && !sh->loop_filter_across_slices && slice_addr_of_ctb(ctb_of(x0 - 1, y0)) != sh->slice_addr_rs) filterLeftCbEdge = 0;
+      if (y0 && (y0 & ctbmask) == 0 && !sh->loop_filter_across_slices && slice_addr_of_ctb(ctb_of(x0, y0 - 1)) != sh->slice_addr_rs) filterTopCbEdge = 0;
+    }
+    derive_qp(x0, y0);
+
+    bool nxn = false;
+    if (LOG2 == p.log2_min_cb) {
+      nxn = !bin(CX_PART_MODE);
+      if (nxn && LOG2 <= p.log2_min_tb) { fail(ERR_BITSTREAM); return; }
+    }
+    // ---- intra prediction modes ----
+    const int pbOffset = nxn ? nCbS / 2 : nCbS;
+    const int nparts = nxn ? 4 : 1;
+    int prev_flag[4], mpm_idx[4] = {0, 0, 0, 0}, rem[4] = {0, 0, 0, 0};
+    for (int i = 0; i < nparts; i++) prev_flag[i] = bin(CX_PREV_INTRA_LUMA);
+    for (int i = 0; i < nparts; i++) {
+      if (prev_flag[i]) {
+        int v = 0;
+        while (v < 2 && cabac.bypass()) v++;
+        mpm_idx[i] = v;
+      } else {
+        rem[i] = (int)cabac.bypass_bits(5);
+      }
+    }
+    const bool availA0 = ctb_available(x0, y0, x0 - 1, y0), availB0 = ctb_available(x0, y0, x0, y0 - 1);
+    int luma_modes[4];
+    for (int idx = 0; idx < nparts; idx++) {
+      const int i = (idx & 1) * pbOffset, j = (idx >> 1) * pbOffset;
+      const int x = x0 + i, y = y0 + j;
+      const bool availA = availA0 || i > 0, availB = availB0 || j > 0;
+      int candA = 1, candB = 1;
+      if (availA) candA = p.ipm[((x - 1) >> 2) + (y >> 2) * p.w4];
+      if (availB && !(y - 1 < ((y >> p.log2_ctb) << p.log2_ctb))) candB = p.ipm[(x >> 2) + ((y - 1) >> 2) * p.w4];
+      int cand[3];
+      if (candA == candB) {
+        if (candA < 2) { cand[0] = 0; cand[1] = 1; cand[2] = 26; }
+        else { cand[0] = candA; cand[1] = 2 + ((candA - 2 - 1 + 32) % 32); cand[2] = 2 + ((candA - 2 + 1) % 32); }
+      } else {
+        cand[0] = candA; cand[1] = candB;
+        if (candA != 0 && candB != 0) cand[2] = 0;
+        else if (candA != 1 && candB != 1) cand[2] = 1;
+        else cand[2] = 26;
+      }
+      int mode;
+      if (prev_flag[idx]) {
+        mode = cand[mpm_idx[idx]];
+      } else {
+        int t;
+        if (cand[0] > cand[1]) { t = cand[0]; cand[0] = cand[1]; cand[1] = t; }
+        if (cand[0] > cand[2]) { t = cand[0]; cand[0] = cand[2]; cand[2] = t; }
+        if (cand[1] > cand[2]) { t = cand[1]; cand[1] = cand[2]; cand[2] = t; }
+        mode = rem[idx];
+        for (int n = 0; n < 3; n++)
+          if (mode >= cand[n]) mode++;
+      }
+      luma_modes[idx] = mode;
+      const int n4 = pbOffset >> 2;
+      for (int yy = 0; yy < n4; yy++)
+        for (int xx = 0; xx < n4; xx++) p.ipm[((x >> 2) + xx) + ((y >> 2) + yy) * p.w4] = (uint8_t)mode;
+    }
+    const int cat = p.chroma_array_type;
+    if (cat != 0) {
+      const int nchroma = cat == 3 ? nparts : 1;
+      for (int idx = 0; idx < nchroma; idx++) {
+        int icpm = 4;
+        if (bin(CX_INTRA_CHROMA)) icpm = (int)cabac.bypass_bits(2);
+        const int luma = luma_modes[idx];
+        int m = luma;
+        if (icpm != 4) {
+          m = icpm == 0 ? 0 : (icpm == 1 ? 26 : (icpm == 2 ? 10 : 1));
+          if (m == luma) m = 34;
+        }
+        if (cat == 2) m = T->mode422[m];
+        const int i = cat == 3 ? (idx & 1) * pbOffset : 0, j = cat == 3 ? (idx >> 1) * pbOffset : 0;
+        const int n4 = (cat == 3 ? pbOffset : nCbS) >> 2;
+        for (int yy = 0; yy < n4; yy++)
+          for (int xx = 0; xx < n4; xx++) p.ipm_c[(((x0 + i) >> 2) + xx) + (((y0 + j) >> 2) + yy) * p.w4] = (uint8_t)m;
+      }
+    }
+    const int max_depth = p.max_th_depth_intra + (nxn ? 1 : 0);
+    transform_tree<LOG2>(x0, y0, x0, y0, 0, 0, max_depth, nxn ? 1 : 0, 1, 1);
+  }
+
+  // ---- 7.3.8.4 coding_quadtree ----
+  template <int LOG2>
+  K0_FN void coding_quadtree(int x0, int y0, int depth) {
+    const Pic& p = *P;
+    if (err || cabac.overrun()) { fail(ERR_BITSTREAM); return; }
+    constexpr int size = 1 << LOG2;
+    bool split;
+    if (x0 + size <= p.W && y0 + size <= p.H && LOG2 > p.log2_min_cb) {
+      int condL = 0, condA = 0;
+      if (ctb_available(x0, y0, x0 - 1, y0) && p.ct_depth[((x0 - 1) >> 3) + (y0 >> 3) * p.w8] > depth) condL = 1;
+      if (ctb_available(x0, y0, x0, y0 - 1) && p.ct_depth[(x0 >> 3) + ((y0 - 1) >> 3) * p.w8] > depth) condA = 1;
+      split = bin(CX_SPLIT_CU + condL + condA);
+    } else {
+      split = LOG2 > p.log2_min_cb;
+    }
+    if (p.cu_qp_delta_enabled && LOG2 >= p.log2_min_cu_qp_delta_size) { IsCuQpDeltaCoded = false; CuQpDeltaVal = 0; }
+    if (split) {
+      if (LOG2 > 3) {
+        constexpr int L = LOG2 > 3 ? LOG2 - 1 : 3;
+        constexpr int h = 1 << L;
+        const int x1 = x0 + h, y1 = y0 + h;
+        coding_quadtree<L>(x0, y0, depth + 1);
+        if (x1 < p.W) coding_quadtree<L>(x1, y0, depth + 1);
+        if (y1 < p.H) coding_quadtree<L>(x0, y1, depth + 1);
+        if (x1 < p.W && y1 < p.H) coding_quadtree<L>(x1, y1, depth + 1);
+      } else {
+        fail(ERR_BITSTREAM);
+      }
+    } else {
+      coding_unit<LOG2>(x0, y0, depth);
+    }
+  }
+
+  // ---- one CTU ----
+  K0_FN void decode_ctu() {
+    const Pic& p = *P;
+    hc_ctu& ctu = p.ctus[ctb_rs];
+    nblk[0] = nblk[1] = nblk[2] = 0;
+    ntb = ncoeff = nresid = 0;
+    for (int c = 0; c < 3; c++) { ctu.sao_type[c] = 0; ctu.sao_band_or_class[c] = 0; for (int i = 0; i < 4; i++) ctu.sao_offset[c][i] = 0; }
+    if (sh->sao_luma || sh->sao_chroma) read_sao(ctu);
+    const int x0 = ctb_x << p.log2_ctb, y0 = ctb_y << p.log2_ctb;
+    if (p.log2_ctb == 6) coding_quadtree<6>(x0, y0, 0);
+    else if (p.log2_ctb == 5) coding_quadtree<5>(x0, y0, 0);
+    else if (p.log2_ctb == 4) coding_quadtree<4>(x0, y0, 0);
+    else coding_quadtree<3>(x0, y0, 0);
+    uint32_t base = (uint32_t)ctb_rs * p.blk_cap_ctb;
+    for (int c = 0; c < 3; c++) {
+      ctu.blk_first[c] = base;
+      ctu.blk_count[c] = (uint16_t)nblk[c];
+      base += p.blk_cap[c];
+    }
+    ctu.beta_offset = sh->beta_offset;
+    ctu.tc_offset = sh->tc_offset;
+    const uint8_t* st = p.ctu_static + 4 * ctb_rs;
+    ctu.sao_nb = st[0];
+    ctu.sao_nb_c = st[1];
+    ctu.flags = (uint8_t)(st[2] | (sh->deblocking_disabled ? HC_CTU_DEBLOCK_OFF : 0));
+    ctu.pad[0] = ctu.pad[1] = ctu.pad[2] = 0;
+  }
+
+  // ---- a chain of substreams (decode_slice_segment loop of the host parser) ----
+  K0_FN void run_chain(const Pic* pics, const Sub* subs, uint32_t first_sub, uint32_t nsubs) {
+    err = ERR_NONE;
+    const Pic* first_pic = pics + subs[first_sub].pic;
+    for (uint32_t s = 0; s < nsubs && !err; s++) {
+      const Sub& sub = subs[first_sub + s];
+      P = pics + sub.pic;
+      const Pic& p = *P;
+      sh = p.slices + sub.slice;
+      const uint8_t* seg_end = p.bytes + sh->data_end;
+      if (sub.byte_begin != 0xffffffffu) cabac.init(p.bytes + sub.byte_begin, seg_end);
+      const bool row_chain = sub.flags & SUB_ROW_CHAIN;
+      ctb_rs = sub.first_ctb;
+      currentQG_x = currentQG_y = -1;
+      currentQPY = 0;
+      if (!row_chain && sub.first_ctb == sh->segment_address && sh->segment_address > 0) {
+        // thread-context initialisation of the reference (decctx.cc:467-506)
+        const int prev = sh->segment_address - 1;
+        int x = (((prev % p.ctbs_w) + 1) << p.log2_ctb) - 1, y = (((prev / p.ctbs_w) + 1) << p.log2_ctb) - 1;
+        if (x > p.W - 1) x = p.W - 1;
+        if (y > p.H - 1) y = p.H - 1;
+        currentQPY = p.qp_map[(x >> 3) + (y >> 3) * p.w8];
+      }
+      // 9.3.1: context initialisation at the start of the slice segment (dependent segments of a serial chain keep
+      // the table of the previous segment; rows of a WPP picture synchronise below)
+      const bool segment_start = sub.first_ctb == sh->segment_address;
+      if (segment_start && !sh->dependent) init_contexts();
+      bool first_of_independent = segment_start && !sh->dependent;
+
+      while (ctb_rs < sub.end_ctb && !err) {
+        ctb_x = ctb_rs % p.ctbs_w;
+        ctb_y = ctb_rs / p.ctbs_w;
+        if (row_chain && ctb_y > 0) {
+          // wavefront: the row above must be two CTBs ahead (its context table, split depths and SAO parameters)
+          const int need = ctb_x + 2 < p.ctbs_w ? ctb_x + 2 : p.ctbs_w;
+          while (progress_load(p.progress + ctb_y - 1) < need) backoff();
+        }
+        if (p.entropy_coding_sync && ctb_x == 0 && ctb_y >= 1 && !(first_of_independent && ctb_rs == sh->segment_address)) {
+          if (p.ctbs_w > 1) {
+            const uint8_t* src = p.wpp_ctx + (size_t)(ctb_y - 1) * CTX_BYTES;
+            for (int i = 0; i < CX_COUNT; i++) ctx[i] = src[i];
+          } else {
+            init_contexts();
+          }
+        }
+        decode_ctu();
+        if (err) break;
+        if (cabac.overrun()) { fail(ERR_BITSTREAM); break; }
+        if (p.entropy_coding_sync && ctb_x == 1 && ctb_y < p.ctbs_h - 1) {
+          uint8_t* dst = p.wpp_ctx + (size_t)ctb_y * CTX_BYTES;
+          for (int i = 0; i < CX_COUNT; i++) dst[i] = ctx[i];
+        }
+        if (row_chain) progress_store(p.progress + ctb_y, ctb_x + 1);
+        const int end_of_slice_segment = cabac.terminate();
+        ctb_rs++;
+        if (end_of_slice_segment) break;
+        if (ctb_rs >= p.ctbs_w * p.ctbs_h) { fail(ERR_BITSTREAM); break; }
+        if (p.entropy_coding_sync && (ctb_rs % p.ctbs_w) == 0) {
+          if (!cabac.terminate()) { fail(ERR_BITSTREAM); break; }   // end_of_subset_one_bit
+          if (row_chain) break;                                       // the next row is another chain
+          const uint8_t* np = cabac.position();
+          if (np >= seg_end) { fail(ERR_BITSTREAM); break; }
+          cabac.init(np, seg_end);
+          first_of_independent = false;
+        }
+      }
+      if (!err && row_chain && ctb_rs != sub.end_ctb) fail(ERR_BITSTREAM);
+    }
+    if (err) {
+      // unblock every waiter of this picture, then report
+      const Pic& p = *(P ? P : first_pic);
+      for (int r = 0; r < p.ctbs_h; r++) progress_store(p.progress + r, 1 << 30);
+      *p.error = err;
+    }
+  }
+};
+
+}  // namespace k0
+}  // namespace hc

@@ -16,6 +16,10 @@ struct CscArgs {
   hc_csc_params p;
 };
 
+namespace k0 { struct Tables; struct Pic; struct Sub; struct Chain; }
+// K0: device CABAC parse of the pictures added as bitstreams (one CTA per substream chain)
+void launch_k0(const k0::Tables* tables, const k0::Pic* pics, const k0::Sub* subs, const k0::Chain* chains, int nchains,
+               cudaStream_t stream);
 void launch_k1(const BatchView& bv, const uint32_t* const tb_index[4], const int counts[4], cudaStream_t stream);
 // shared-memory bytes one K2 row task needs (CTB of ctb_w x ctb_h samples of this component)
 int k2_task_smem_bytes(int ctb_w, int ctb_h, int pixel_bytes);

@@ -81,6 +81,13 @@ SYMBOLS = [
     ("hc_records_scaling", _vp, [_vp, C.POINTER(_sz)]),
     ("hc_records_upload_bytes", _sz, [_vp]),
     ("hc_parse_picture", _vp, [C.c_char_p, _sz, _i]),
+    ("hc_parse_picture_k0", _vp, [C.c_char_p, _sz, _i]),
+    ("hc_k0_prepare", _vp, [C.c_char_p, _sz, _i]),
+    ("hc_k0_free", None, [_vp]),
+    ("hc_k0_eligible", _i, [_vp]),
+    ("hc_k0_why_not", C.c_char_p, [_vp]),
+    ("hc_k0_pic", C.POINTER(Pic), [_vp]),
+    ("hc_k0_upload_bytes", _sz, [_vp]),
     ("hc_heif_open", _vp, [C.c_char_p, _sz]),
     ("hc_heif_close", None, [_vp]),
     ("hc_heif_primary_id", _u32, [_vp]),
@@ -96,6 +103,8 @@ SYMBOLS = [
     ("hc_batch_destroy", None, [_vp]),
     ("hc_batch_add_canvas", _i, [_vp, _i, _i, _i, _i, _i]),
     ("hc_batch_add_picture", _i, [_vp, _vp, _i, _i, _i, _i, _i]),
+    ("hc_batch_add_k0_picture", _i, [_vp, _vp, _i, _i, _i, _i, _i]),
+    ("hc_batch_k0_pictures", _i, [_vp]),
     ("hc_batch_upload", _i, [_vp]),
     ("hc_batch_reconstruct", _i, [_vp, _i]),
     ("hc_batch_convert", _i, [_vp, _i, C.POINTER(CscParams)]),

@@ -52,6 +52,50 @@ def parse_picture(data, stream_format=STREAM_LENGTH_PREFIXED, host_only=False):
     return Records(L, h)
 
 
+def parse_picture_k0(data, stream_format=STREAM_LENGTH_PREFIXED, host_only=False):
+    """The K0 core (device CABAC parser) executed on the CPU -> Records in the host parser's form.
+    Raises HeifCudaError("not eligible ...") for pictures K0 leaves to the host parser."""
+    L = _lib.load(host_only)
+    h = L.hc_parse_picture_k0(data, len(data), stream_format)
+    if not h:
+        raise HeifCudaError((L.hc_last_error() or b"").decode())
+    return Records(L, h)
+
+
+class K0Picture:
+    """Headers of one picture prepared for K0, the device CABAC parser (hc_k0_picture)."""
+
+    def __init__(self, data, stream_format=STREAM_LENGTH_PREFIXED, host_only=False):
+        self._L = _lib.load(host_only)
+        self._h = self._L.hc_k0_prepare(data, len(data), stream_format)
+        if not self._h:
+            raise HeifCudaError("bitstream: " + (self._L.hc_last_error() or b"").decode())
+
+    @property
+    def eligible(self):
+        return bool(self._L.hc_k0_eligible(self._h))
+
+    @property
+    def why_not(self):
+        return (self._L.hc_k0_why_not(self._h) or b"").decode()
+
+    @property
+    def pic(self):
+        return self._L.hc_k0_pic(self._h).contents
+
+    @property
+    def upload_bytes(self):
+        return self._L.hc_k0_upload_bytes(self._h)
+
+    def close(self):
+        if self._h:
+            self._L.hc_k0_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        self.close()
+
+
 class HeifFile:
     """ISO-BMFF/HEIF item resolver (hc_heif)."""
 
@@ -143,6 +187,11 @@ class Batch:
         self._keep.append(rec)
         return check(self._L, self._L.hc_batch_add_picture(self._h, rec._h, canvas, x, y, role, int(rescale_limited)), "add_picture")
 
+    def add_k0_picture(self, k0pic, canvas, x=0, y=0, role=ROLE_COLOUR, rescale_limited=False):
+        """a picture whose slice data the GPU parses (K0)"""
+        self._keep.append(k0pic)
+        return check(self._L, self._L.hc_batch_add_k0_picture(self._h, k0pic._h, canvas, x, y, role, int(rescale_limited)), "add_k0_picture")
+
     def upload(self):
         check(self._L, self._L.hc_batch_upload(self._h), "upload")
 
@@ -185,7 +234,7 @@ class Batch:
     def stage_ms(self):
         ms = (C.c_float * 8)()
         check(self._L, self._L.hc_batch_stage_ms(self._h, ms), "stage_ms")
-        return dict(zip(("h2d", "k1_transform", "k2_intra", "k3_deblock", "k4_sao", "k5_csc", "d2h"), list(ms)[:7]))
+        return dict(zip(("h2d", "k1_transform", "k2_intra", "k3_deblock", "k4_sao", "k5_csc", "d2h", "k0_parse"), list(ms)[:8]))
 
     @property
     def launch_count(self):
@@ -309,7 +358,7 @@ class HeicJob:
     def stage_ms(self):
         ms = (C.c_float * 8)()
         check(self._L, self._L.hc_heic_job_stage_ms(self._h, ms), "stage_ms")
-        return dict(zip(("h2d", "k1_transform", "k2_intra", "k3_deblock", "k4_sao", "k5_csc", "d2h"), list(ms)[:7]))
+        return dict(zip(("h2d", "k1_transform", "k2_intra", "k3_deblock", "k4_sao", "k5_csc", "d2h", "k0_parse"), list(ms)[:8]))
 
     def timer_start(self):
         check(self._L, self._L.hc_heic_job_timer_start(self._h), "timer_start")

@@ -77,6 +77,23 @@ const uint8_t* hc_records_scaling(const hc_records* r, size_t* bytes); /* NULL i
 /* total bytes of all record arrays (the `R` term of the roofline: bytes uploaded per picture) */
 size_t hc_records_upload_bytes(const hc_records* r);
 
+/* ---- K0: CABAC parse on the device --------------------------------------------------------------------
+ * For pictures K0 accepts (no HEVC tiles / pcm / transquant bypass ...; csrc/kernels/k0_core.cuh) only the
+ * parameter sets and slice headers are parsed on the host; the slice data is unescaped and handed to the engine as
+ * bytes, and kernel K0 (one warp per WPP row / per picture, wavefront-synchronised) writes the records straight
+ * into HBM. hc_k0_prepare never fails for a well-formed picture: check hc_k0_eligible and fall back to
+ * hc_parse_picture + hc_batch_add_picture otherwise. */
+typedef struct hc_k0_picture hc_k0_picture;
+hc_k0_picture* hc_k0_prepare(const uint8_t* data, size_t size, int stream_format);
+void hc_k0_free(hc_k0_picture* k);
+int hc_k0_eligible(const hc_k0_picture* k);
+const char* hc_k0_why_not(const hc_k0_picture* k);
+const hc_pic* hc_k0_pic(const hc_k0_picture* k);          /* header fields only (sizes, formats, VUI) */
+size_t hc_k0_upload_bytes(const hc_k0_picture* k);        /* bytes this picture adds to the H2D copy */
+/* Same result through the K0 core — the DEVICE CABAC parser (csrc/kernels/k0_core.cuh) — executed on the CPU:
+ * the scaffold the tests use to validate K0 record by record. NULL + "not eligible for K0: ..." for pictures K0
+ * leaves to the host parser (HEVC tiles, pcm, transquant bypass, ...). */
+hc_records* hc_parse_picture_k0(const uint8_t* data, size_t size, int stream_format);
 /* One-call convenience: parse one coded picture (parameter sets + slice NALs). */
 hc_records* hc_parse_picture(const uint8_t* data, size_t size, int stream_format);
 
@@ -165,6 +182,9 @@ int hc_batch_add_canvas(hc_batch* b, int width, int height, int chroma_format, i
  * conformance window on the canvas, luma samples. rescale_limited: apply the reference's
  * limited->full range rescale while pasting (grid tiles whose nclx is limited range). */
 int hc_batch_add_picture(hc_batch* b, const hc_records* rec, int canvas, int x, int y, int role, int rescale_limited);
+/* Adds a picture whose slice data is parsed by K0 on the device. `k` must stay alive until hc_batch_upload returns. */
+int hc_batch_add_k0_picture(hc_batch* b, const hc_k0_picture* k, int canvas, int x, int y, int role, int rescale_limited);
+int hc_batch_k0_pictures(const hc_batch* b);              /* pictures of the batch that K0 parses */
 /* packs all records into one pinned arena and copies it to the device (async on the engine stream) */
 int hc_batch_upload(hc_batch* b);
 #define HC_STAGE_DEBLOCK 1
@@ -185,7 +205,8 @@ int hc_batch_read_rgb_async(hc_batch* b, int canvas, void* dst, size_t dst_strid
 /* residuals of picture `pic` as produced by K1 (resid_count int16) — used by the parity tests */
 int hc_batch_read_residual(hc_batch* b, int pic, int16_t* dst, size_t count);
 /* device time of the last run's stages in ms (CUDA events on the engine stream):
- * [0] H2D upload, [1] K1, [2] K2, [3] K3, [4] K4, [5] K5 (sum over canvases), [6] D2H of the last read */
+ * [0] H2D upload, [1] K1, [2] K2, [3] K3, [4] K4, [5] K5 (sum over canvases), [6] D2H of the last read,
+ * [7] K0 (device CABAC parse; runs once per upload, the records then stay resident) */
 int hc_batch_stage_ms(hc_batch* b, float ms[8]);
 /* CUDA-event stopwatch on the batch's stream: start records an event; stop records a second one,
  * waits for it and returns the device time between the two in ms (used by bench.py to time K
