@@ -8,6 +8,8 @@ extern "C" {
 int hc_has_cuda_engine(void) { return 0; }
 hc_engine* hc_engine_create(int) { NO_ENGINE(); return nullptr; }
 void hc_engine_destroy(hc_engine*) {}
+int hc_engine_set_option(hc_engine*, const char*, int) { return NO_ENGINE(); }
+int hc_engine_get_option(const hc_engine*, const char*) { return 0; }
 hc_batch* hc_batch_create(hc_engine*) { NO_ENGINE(); return nullptr; }
 void hc_batch_destroy(hc_batch*) {}
 int hc_batch_add_canvas(hc_batch*, int, int, int, int, int) { return NO_ENGINE(); }

@@ -15,6 +15,7 @@
 #include <atomic>
 #include <thread>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -46,6 +47,7 @@ struct hc_engine {
   std::vector<Block> free_dev, free_pin;
   std::vector<cudaStream_t> free_streams;
   hc::k0::Tables* d_k0_tables = nullptr;   // read-only tables of the device parser
+  int device_parse = 1;                    // hc_heic_job: let K0 parse every picture it accepts
 
   Block take(std::vector<Block>& list, size_t size, bool pinned) {
     std::lock_guard<std::mutex> lk(mu);
@@ -181,6 +183,7 @@ hc_engine* hc_engine_create(int device) {
   hc_engine* eng = new (std::nothrow) hc_engine;
   if (!eng) return nullptr;
   eng->device = device;
+  if (const char* m = getenv("HEIFCUDA_PARSER")) eng->device_parse = strcmp(m, "host") != 0;
   if (!cuda_ok(cudaMalloc(&eng->d_k0_tables, sizeof(hc::k0::Tables)), "cudaMalloc(K0 tables)") ||
       !cuda_ok(cudaMemcpy(eng->d_k0_tables, &hc::k0_tables(), sizeof(hc::k0::Tables), cudaMemcpyHostToDevice), "cudaMemcpy(K0 tables)")) {
     delete eng;
@@ -197,6 +200,18 @@ void hc_engine_destroy(hc_engine* e) {
   for (auto s : e->free_streams) cudaStreamDestroy(s);
   if (e->d_k0_tables) cudaFree(e->d_k0_tables);
   delete e;
+}
+
+int hc_engine_set_option(hc_engine* e, const char* name, int value) {
+  if (!e || !name) return HC_ERR_ARGUMENT;
+  if (!strcmp(name, "device_parse")) { e->device_parse = value; return HC_OK; }
+  hc::set_last_error(std::string("unknown engine option ") + name);
+  return HC_ERR_ARGUMENT;
+}
+int hc_engine_get_option(const hc_engine* e, const char* name) {
+  if (!e || !name) return 0;
+  if (!strcmp(name, "device_parse")) return e->device_parse;
+  return 0;
 }
 
 hc_batch* hc_batch_create(hc_engine* e) {

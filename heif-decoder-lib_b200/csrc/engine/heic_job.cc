@@ -20,8 +20,10 @@ struct CodedItem {
   int file;
   uint32_t item_id;
   std::vector<uint8_t> stream;
-  hc_records rec;
+  hc_records rec;                          // host-parsed records, or
+  std::unique_ptr<hc_k0_picture> k0;       // headers + slice bytes for the device parser (K0)
   std::string error;
+  const hc_pic& pic() const { return k0 ? k0->hp.hpic : rec.rec->pic; }
 };
 
 struct ImagePlan {
@@ -36,6 +38,10 @@ struct ImagePlan {
   hc_image_desc desc{};
   hc_csc_params csc{};
 };
+
+int add_item(hc_batch* b, const CodedItem& ci, int canvas, int x, int y, int role, int rescale) {
+  return ci.k0 ? hc_batch_add_k0_picture(b, ci.k0.get(), canvas, x, y, role, rescale) : hc_batch_add_picture(b, &ci.rec, canvas, x, y, role, rescale);
+}
 
 }  // namespace
 
@@ -132,6 +138,7 @@ static hc_heic_job* job_create(hc_engine* e, int nfiles, const uint8_t* const* d
   int nthreads = threads > 0 ? threads : (int)std::thread::hardware_concurrency();
   if (nthreads < 1) nthreads = 1;
   nthreads = std::min<int>(nthreads, (int)j->items.size());
+  const bool device_parse = hc_engine_get_option(e, "device_parse") != 0;
   std::atomic<size_t> next{0};
   auto worker = [&]() {
     for (;;) {
@@ -140,6 +147,17 @@ static hc_heic_job* job_create(hc_engine* e, int nfiles, const uint8_t* const* d
       CodedItem& ci = j->items[i];
       std::string err = j->files[ci.file]->coded_stream(ci.item_id, ci.stream);
       if (!err.empty()) { ci.error = err; continue; }
+      if (device_parse) {
+        // K0: only parameter sets and slice headers are read here; the GPU parses the slice data
+        std::unique_ptr<hc_k0_picture> k(new hc_k0_picture);
+        err = hc::k0_prepare(ci.stream.data(), ci.stream.size(), HC_STREAM_LENGTH_PREFIXED, k->hp);
+        if (!err.empty()) { ci.error = err; continue; }
+        if (k->hp.eligible) {
+          ci.k0 = std::move(k);
+          std::vector<uint8_t>().swap(ci.stream);
+          continue;
+        }
+      }
       hc::HevcIntraParser parser;
       err = parser.push_length_prefixed(ci.stream.data(), ci.stream.size());
       if (!err.empty()) { ci.error = err; continue; }
@@ -165,7 +183,7 @@ static hc_heic_job* job_create(hc_engine* e, int nfiles, const uint8_t* const* d
   j->batch = hc_batch_create(e);
   if (!j->batch) return nullptr;
   for (ImagePlan& im : j->images) {
-    const hc_pic& p0 = j->items[im.tiles[0]].rec.rec->pic;
+    const hc_pic& p0 = j->items[im.tiles[0]].pic();
     const bool has_alpha = im.alpha >= 0;
     int W = im.info.width, H = im.info.height;
     if (!im.info.is_grid) { W = p0.crop_w; H = p0.crop_h; }   // decoded size, like the reference
@@ -182,33 +200,32 @@ static hc_heic_job* job_create(hc_engine* e, int nfiles, const uint8_t* const* d
       const int tw = p0.crop_w, th = p0.crop_h;
       for (size_t k = 0; k < im.tiles.size(); k++) {
         CodedItem& ci = j->items[im.tiles[k]];
-        const hc_pic& p = ci.rec.rec->pic;
+        const hc_pic& p = ci.pic();
         const hc::HeifItem* tit = j->files[im.file]->item(ci.item_id);
         const int tfull = tit && tit->nclx.present ? tit->nclx.full_range : p.full_range;
         const int tmatrix = tit && tit->nclx.present ? tit->nclx.matrix : p.matrix_coeffs;
         const int x0 = (int)(k % im.info.cols) * tw, y0 = (int)(k / im.info.cols) * th;
         if (x0 >= W || y0 >= H) { hc::set_last_error("grid tile lies outside the output image"); return nullptr; }
         // context.cc:2504: limited-range tiles (matrix != 0) are expanded to full range while pasting
-        if (hc_batch_add_picture(j->batch, &ci.rec, im.canvas, x0, y0, HC_ROLE_COLOUR, (!tfull && tmatrix != 0) ? 1 : 0) < 0)
-          return nullptr;
+        if (add_item(j->batch, ci, im.canvas, x0, y0, HC_ROLE_COLOUR, (!tfull && tmatrix != 0) ? 1 : 0) < 0) return nullptr;
       }
       // the canvas only has an nclx if the grid item itself carries one (context.cc:1841-1844)
       matrix = im.info.nclx_present ? im.info.matrix : 2;
       primaries = im.info.nclx_present ? im.info.primaries : 2;
       full = im.info.nclx_present ? im.info.full_range : 1;
     } else {
-      if (hc_batch_add_picture(j->batch, &j->items[im.tiles[0]].rec, im.canvas, 0, 0, HC_ROLE_COLOUR, 0) < 0) return nullptr;
+      if (add_item(j->batch, j->items[im.tiles[0]], im.canvas, 0, 0, HC_ROLE_COLOUR, 0) < 0) return nullptr;
       matrix = im.info.nclx_present ? im.info.matrix : p0.matrix_coeffs;
       primaries = im.info.nclx_present ? im.info.primaries : p0.colour_primaries;
       full = im.info.nclx_present ? im.info.full_range : p0.full_range;
     }
     if (has_alpha) {
-      const hc_pic& pa = j->items[im.alpha].rec.rec->pic;
+      const hc_pic& pa = j->items[im.alpha].pic();
       if (pa.crop_w != W || pa.crop_h != H) {
         hc::set_last_error("alpha image of a different size than the colour image (nearest-neighbour rescale) is not supported");
         return nullptr;
       }
-      if (hc_batch_add_picture(j->batch, &j->items[im.alpha].rec, im.canvas, 0, 0, HC_ROLE_ALPHA, 0) < 0) return nullptr;
+      if (add_item(j->batch, j->items[im.alpha], im.canvas, 0, 0, HC_ROLE_ALPHA, 0) < 0) return nullptr;
     }
     const bool hdr = p0.bit_depth_y != 8;
     const int fmt = hdr ? (j->want_alpha ? HC_OUT_RRGGBBAA_LE : HC_OUT_RRGGBB_LE) : (j->want_alpha ? HC_OUT_RGBA : HC_OUT_RGB);

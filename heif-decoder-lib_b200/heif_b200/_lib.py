@@ -99,6 +99,8 @@ SYMBOLS = [
     ("hc_csc_select", _i, [_i, _i, _i, _i, _i, _i, _i, C.POINTER(CscParams)]),
     ("hc_engine_create", _vp, [_i]),
     ("hc_engine_destroy", None, [_vp]),
+    ("hc_engine_set_option", _i, [_vp, C.c_char_p, _i]),
+    ("hc_engine_get_option", _i, [_vp, C.c_char_p]),
     ("hc_batch_create", _vp, [_vp]),
     ("hc_batch_destroy", None, [_vp]),
     ("hc_batch_add_canvas", _i, [_vp, _i, _i, _i, _i, _i]),

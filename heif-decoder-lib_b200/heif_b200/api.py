@@ -161,6 +161,13 @@ class Engine:
     def batch(self):
         return Batch(self)
 
+    def set_option(self, name, value):
+        """"device_parse": 1 = K0 parses the slice data on the GPU (default), 0 = host CABAC parser"""
+        check(self._L, self._L.hc_engine_set_option(self._h, name.encode(), int(value)), "set_option")
+
+    def get_option(self, name):
+        return self._L.hc_engine_get_option(self._h, name.encode())
+
     def close(self):
         if self._h:
             self._L.hc_engine_destroy(self._h)

@@ -169,6 +169,10 @@ typedef struct hc_batch hc_batch;
  * present: there is deliberately no CPU fallback. */
 hc_engine* hc_engine_create(int device);
 void hc_engine_destroy(hc_engine* e);
+/* Options: "device_parse" (default 1; environment HEIFCUDA_PARSER=host sets 0): hc_heic_job / hc_heic_decode_stream
+ * let kernel K0 parse the slice data of every picture it accepts instead of the host CABAC parser. */
+int hc_engine_set_option(hc_engine* e, const char* name, int value);
+int hc_engine_get_option(const hc_engine* e, const char* name);
 
 /* A batch = a set of parsed pictures placed on destination canvases (one canvas per output
  * image: a single picture, or a HEIF grid whose tiles are pasted at their offsets). */
