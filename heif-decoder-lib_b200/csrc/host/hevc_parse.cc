@@ -312,6 +312,7 @@ std::string HevcIntraParser::take_k0(K0HostPicture& out) {
   p.cu_qp_delta_enabled = P.cu_qp_delta_enabled; p.entropy_coding_sync = P.entropy_coding_sync_enabled;
   p.implicit_rdpcm = S.implicit_rdpcm_enabled; p.tskip_rotation = S.transform_skip_rotation_enabled;
   p.tskip_context = S.transform_skip_context_enabled; p.pps_loop_filter_across_slices = P.loop_filter_across_slices;
+  p.nslices = (int32_t)d.slices.size();
   const int ctb = 1 << S.log2_ctb;
   const int ccw = S.ChromaArrayType ? ctb / S.SubWidthC : 0, cch = S.ChromaArrayType ? ctb / S.SubHeightC : 0;
   p.blk_cap[0] = (uint32_t)(ctb / 4) * (ctb / 4);

@@ -108,13 +108,13 @@ std::unique_ptr<PictureRecords> k0_parse_on_cpu(const K0HostPicture& hp, std::st
   p.tb_counts = counts;
   p.pic_index = 0; p.tb_global_base = 0;
 
-  uint8_t ctx[k0::CTX_BYTES];
+  std::unique_ptr<k0::Scratch> scratch(new k0::Scratch);
+  memset(scratch.get(), 0, sizeof(k0::Scratch));
   for (const k0::Chain& ch : hp.chains) {      // row order satisfies every wavefront dependency
     k0::Parser ps;
     memset(&ps, 0, sizeof(ps));
     ps.T = &k0_tables();
-    ps.cabac.T = ps.T;
-    ps.ctx = ctx;
+    ps.S = scratch.get();
     ps.run_chain(&p, hp.subs.data(), ch.first_sub, ch.nsubs);
     if (error) break;
   }

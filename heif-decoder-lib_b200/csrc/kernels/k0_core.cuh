@@ -43,7 +43,7 @@ enum : int {
 constexpr int CTX_BYTES = 160;   // padded
 
 // All read-only tables of the parser in one block (constant memory on the device).
-struct Tables {
+struct alignas(16) Tables {
   uint8_t range_lps[64][4];
   uint8_t next_state[128][2];      // [state][is_lps]
   uint8_t ctx_init[CX_COUNT];      // initValue per context (initType 0)
@@ -73,6 +73,7 @@ struct Pic {
   int32_t log2_sao_offset_scale_luma, log2_sao_offset_scale_chroma;
   uint8_t transform_skip_enabled, sign_data_hiding, cu_qp_delta_enabled, entropy_coding_sync;
   uint8_t implicit_rdpcm, tskip_rotation, tskip_context, pps_loop_filter_across_slices;
+  int32_t nslices;                   // slice segments of the picture (1: no per-CTB slice lookups)
   uint32_t pic_index;                // picture index in the batch (hc_tb::pic)
   uint32_t tb_global_base;           // index of this picture's first hc_tb in the batch array
   // per-CTB capacities
@@ -118,49 +119,91 @@ constexpr int ERR_NONE = 0, ERR_BITSTREAM = 1, ERR_CAPACITY = 2;
 HC_D int k0_clz(unsigned v) { return __clz((int)v); }
 HC_D int progress_load(const int* p) { return ld_acquire_s32(p); }
 HC_D void progress_store(int* p, int v) { __threadfence(); st_release_s32(p, v); }
-HC_D unsigned list_append(unsigned int* counter) { return atomicAdd(counter, 1u); }
-HC_D void backoff() { __nanosleep(200); }
+HC_D unsigned list_reserve(unsigned int* counter, unsigned n) { return atomicAdd(counter, n); }
+HC_D void backoff() { __nanosleep(400); }
 #else
 HC_HD int k0_clz(unsigned v) { return __builtin_clz(v); }
 HC_HD int progress_load(const int* p) { return *p; }
 HC_HD void progress_store(int* p, int v) { *p = v; }
-HC_HD unsigned list_append(unsigned int* counter) { return (*counter)++; }
+HC_HD unsigned list_reserve(unsigned int* counter, unsigned n) { const unsigned r = *counter; *counter += n; return r; }
 HC_HD void backoff() {}
 #endif
 
+// Per-chain scratch. On the device it lives in shared memory next to ONE copy of the tables per CTA (k0_parse.cu),
+// so every table lookup, context-state access and parameter read of the hot loops is an LDS / STS with a
+// compile-time-known address space; on the host it is a member of the parser.
+constexpr int TB_CAP_MAX = 768;      // transform blocks of one CTB: 64x64 4:4:4 in 4x4 blocks
+struct Scratch {
+  uint8_t ctx[CTX_BYTES];            // CABAC context states
+  Pic pic;                           // copy of the picture descriptor
+  Slice slice;                       // copy of the current slice segment descriptor
+  uint8_t tb_size[TB_CAP_MAX];       // log2 - 2 of every transform block of the current CTB (K1 list flush, decode_ctu)
+};
+constexpr int TABLE_BYTES = (int)((sizeof(Tables) + 15) & ~(size_t)15);
+constexpr int SCRATCH_BYTES = (int)((sizeof(Scratch) + 15) & ~(size_t)15);
+#if defined(__CUDACC__)
+extern __shared__ __align__(16) uint8_t k0_smem[];   // [Tables][Scratch x warps of the CTA]
+#endif
+
 // ---- arithmetic decoder: same design as host/hevc_cabac.h (offset + look-ahead in one 64-bit register) --------
+// The hot functions copy this struct into a local (registers), decode, and write it back (see Parser).
 struct Cabac {
   const uint8_t* start;
-  const uint8_t* cur;
   const uint8_t* end;
   unsigned long long value;
   uint32_t range;
   int avail;
-  const Tables* T;
+  uint32_t pos;                      // bytes of the substream already moved into `value`
+  // device: the bitstream is read as aligned 32-bit words, one word ahead of its use, so that a refill never waits
+  // for memory (w_hi holds the word the next byte comes from, w_lo the one after)
+  const uint32_t* wp;
+  uint32_t w_hi, w_lo, wshift;
 
   HC_HD static uint32_t be32(const uint8_t* p) { return ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | p[3]; }
+  HC_HD uint32_t next32() {
+#if defined(__CUDA_ARCH__)
+    const uint32_t r = __funnelshift_l(w_lo, w_hi, wshift);
+    w_hi = w_lo;
+    w_lo = __byte_perm(__ldg(wp), 0, 0x0123);
+    wp++;
+#else
+    const uint32_t r = be32(start + pos);
+#endif
+    pos += 4;
+    return r;
+  }
   HC_HD void refill() {
     if (avail < 16) {
-      value = (value << 32) | be32(cur);
-      cur += 4;
+      value = (value << 32) | next32();
       avail += 32;
     }
   }
   HC_HD void init(const uint8_t* p, const uint8_t* e) {
     start = p; end = e;
     range = 510;
-    value = be32(p);
-    cur = p + 4;
+    pos = 0;
+#if defined(__CUDA_ARCH__)
+    const unsigned a = (unsigned)(reinterpret_cast<uintptr_t>(p) & 3);
+    wp = reinterpret_cast<const uint32_t*>(p - a);
+    wshift = 8 * a;
+    w_hi = __byte_perm(__ldg(wp), 0, 0x0123);
+    w_lo = __byte_perm(__ldg(wp + 1), 0, 0x0123);
+    wp += 2;
+#else
+    wp = nullptr; w_hi = w_lo = wshift = 0;
+#endif
+    value = next32();
     avail = 32 - 9;
   }
   HC_HD const uint8_t* position() const {
-    const long long shifts = (long long)(cur - start) * 8 - 9 - avail;
+    const long long shifts = (long long)pos * 8 - 9 - avail;
     return start + 2 + (shifts >> 3);
   }
   HC_HD bool overrun() const { return position() > end; }
-  HC_HD int bin(uint8_t& state) {
+  HC_HD int bin(const Tables& t, uint8_t& state) {
     const uint32_t st = state;
-    const uint32_t lps = T->range_lps[st >> 1][(range >> 6) & 3];
+    const uint32_t lps = t.range_lps[st >> 1][(range >> 6) & 3];
+    const uint32_t nxt = *reinterpret_cast<const uint16_t*>(t.next_state[st]);   // both successors; picked below
     const uint32_t rmps = range - lps;
     const unsigned long long scaled = (unsigned long long)rmps << avail;
     const uint32_t is_lps = value >= scaled;
@@ -169,7 +212,7 @@ struct Cabac {
     const int n = k0_clz(r) - 23;
     range = r << n;
     avail -= n;
-    state = T->next_state[st][is_lps];
+    state = (uint8_t)(is_lps ? nxt >> 8 : nxt);
     refill();
     return (int)((st & 1) ^ is_lps);
   }
@@ -221,23 +264,27 @@ HC_HD uint8_t ctx_init_state(int init_value, int slice_qp) {
   return (uint8_t)((st << 1) | mps);
 }
 
-HC_HD int morton4(int x, int y) {   // interleave up to 4 bits of x (even positions) and y (odd positions)
-  int r = 0;
-
-  for (int b = 0; b < 4; b++) r |= (((x >> b) & 1) << (2 * b)) | (((y >> b) & 1) << (2 * b + 1));
-  return r;
+HC_HD int morton4(int x, int y) {   // interleave 4 bits of x (even positions) and 4 bits of y (odd positions)
+  unsigned v = (unsigned)(x & 15) | ((unsigned)(y & 15) << 8);
+  v = (v | (v << 2)) & 0x3333u;
+  v = (v | (v << 1)) & 0x5555u;
+  return (int)((v & 0xffu) | (v >> 7));
 }
 
 // ---- the parser of one chain ---------------------------------------------------------------------------------
 struct Parser {
+  // host build: the tables, picture, slice segment and scratch are reached through these pointers; the device build
+  // reaches its copies in shared memory through `wbase` (tab() / pic() / slice() / scratch() below)
   const Tables* T;
   const Pic* P;
   const Slice* sh;
-  uint8_t* ctx;            // CTX_BYTES context states (shared memory on the device)
+  Scratch* S;
+  uint32_t wbase;          // device: byte offset of this chain's Scratch in k0_smem
   Cabac cabac;
   int err;
   // CTB state
   int ctb_rs, ctb_x, ctb_y;
+  int slice_addr;          // slice_addr_rs of the current slice
   uint32_t nblk[3], ntb, ncoeff, nresid;       // used inside the current CTB
   // CU / QG state
   bool IsCuQpDeltaCoded;
@@ -247,35 +294,57 @@ struct Parser {
   int cu_x0, cu_y0, cu_log2;
   int filterLeftCbEdge, filterTopCbEdge;
 
-  HC_HD int bin(int c) { return cabac.bin(ctx[c]); }
+#if defined(__CUDA_ARCH__)
+  HC_HD const Tables& tab() const { return *reinterpret_cast<const Tables*>(k0_smem); }
+  HC_HD Scratch& scratch() const { return *reinterpret_cast<Scratch*>(k0_smem + wbase); }
+#else
+  HC_HD const Tables& tab() const { return *T; }
+  HC_HD Scratch& scratch() const { return *S; }
+#endif
+  HC_HD const Pic& pic() const { return scratch().pic; }
+  HC_HD const Slice& slice() const { return scratch().slice; }
+  HC_HD uint8_t* ctxs() const { return scratch().ctx; }
+
+  HC_HD int bin(int c) { return cabac.bin(tab(), ctxs()[c]); }
   HC_HD void fail(int code) { if (!err) err = code; }
   HC_HD void init_contexts() {
-    for (int i = 0; i < CX_COUNT; i++) ctx[i] = ctx_init_state(T->ctx_init[i], sh->slice_qp_y);
+    const Tables& t = tab();
+    uint8_t* ctx = ctxs();
+    const int qp = slice().slice_qp_y;
+    for (int i = 0; i < CX_COUNT; i++) ctx[i] = ctx_init_state(t.ctx_init[i], qp);
   }
 
   // ---- availability (no tiles: TS == RS) ----
-  HC_HD int ctb_of(int x, int y) const { return (x >> P->log2_ctb) + (y >> P->log2_ctb) * P->ctbs_w; }
-  HC_HD int slice_addr_of_ctb(int n) const { return P->slices[P->ctb_slice[n]].slice_addr_rs; }
+  HC_HD int ctb_of(int x, int y) const { const Pic& p = pic(); return (x >> p.log2_ctb) + (y >> p.log2_ctb) * p.ctbs_w; }
+  // pictures with one slice (the usual case) never look at the per-CTB slice table
+  HC_HD int slice_addr_of_ctb(int n) const { const Pic& p = pic(); return p.nslices == 1 ? 0 : p.slices[p.ctb_slice[n]].slice_addr_rs; }
   HC_HD bool ctb_available(int xC, int yC, int xN, int yN) const {
-    if (xN < 0 || yN < 0 || xN >= P->W || yN >= P->H) return false;
+    const Pic& p = pic();
+    if (xN < 0 || yN < 0 || xN >= p.W || yN >= p.H) return false;
+    if (p.nslices == 1) return true;
     return slice_addr_of_ctb(ctb_of(xN, yN)) == slice_addr_of_ctb(ctb_of(xC, yC));
   }
   HC_HD int zs_addr(int x, int y) const {
-    const int sh2 = P->log2_ctb - P->log2_min_tb, mask = (1 << P->log2_ctb) - 1;
-    return (ctb_of(x, y) << (2 * sh2)) + morton4((x & mask) >> P->log2_min_tb, (y & mask) >> P->log2_min_tb);
+    const Pic& p = pic();
+    const int sh2 = p.log2_ctb - p.log2_min_tb, mask = (1 << p.log2_ctb) - 1;
+    return (ctb_of(x, y) << (2 * sh2)) + morton4((x & mask) >> p.log2_min_tb, (y & mask) >> p.log2_min_tb);
   }
   HC_HD bool available_zscan(int xC, int yC, int xN, int yN) const {
-    if (xN < 0 || yN < 0 || xN >= P->W || yN >= P->H) return false;
+    const Pic& p = pic();
+    if (xN < 0 || yN < 0 || xN >= p.W || yN >= p.H) return false;
     if (zs_addr(xN, yN) > zs_addr(xC, yC)) return false;
     return ctb_available(xC, yC, xN, yN);
   }
 
   // ---- 7.3.8.3 SAO ----
   K0_FN void read_sao(hc_ctu& ctu) {
-    const Pic& p = *P;
+    const Pic& p = pic();
+    const Tables& t = tab();
+    uint8_t* const ctx = ctxs();
+    Cabac cb = cabac;
     bool merge_left = false, merge_up = false;
-    if (ctb_x > 0 && slice_addr_of_ctb(ctb_rs - 1) == sh->slice_addr_rs) merge_left = bin(CX_SAO_MERGE);
-    if (ctb_y > 0 && !merge_left && slice_addr_of_ctb(ctb_rs - p.ctbs_w) == sh->slice_addr_rs) merge_up = bin(CX_SAO_MERGE);
+    if (ctb_x > 0 && slice_addr_of_ctb(ctb_rs - 1) == slice().slice_addr_rs) merge_left = cb.bin(t, ctx[CX_SAO_MERGE]);
+    if (ctb_y > 0 && !merge_left && slice_addr_of_ctb(ctb_rs - p.ctbs_w) == slice().slice_addr_rs) merge_up = cb.bin(t, ctx[CX_SAO_MERGE]);
     if (merge_left || merge_up) {
       const hc_ctu& src = p.ctus[merge_left ? ctb_rs - 1 : ctb_rs - p.ctbs_w];
       for (int c = 0; c < 3; c++) {
@@ -283,17 +352,18 @@ struct Parser {
         ctu.sao_band_or_class[c] = src.sao_band_or_class[c];
         for (int i = 0; i < 4; i++) ctu.sao_offset[c][i] = src.sao_offset[c][i];
       }
-      if (!sh->sao_luma) ctu.sao_type[0] = 0;
-      if (!sh->sao_chroma) ctu.sao_type[1] = ctu.sao_type[2] = 0;
+      if (!slice().sao_luma) ctu.sao_type[0] = 0;
+      if (!slice().sao_chroma) ctu.sao_type[1] = ctu.sao_type[2] = 0;
+      cabac = cb;
       return;
     }
     const int ncomp = p.chroma_array_type != 0 ? 3 : 1;
     for (int c = 0; c < ncomp; c++) {
-      if (!((sh->sao_luma && c == 0) || (sh->sao_chroma && c > 0))) { ctu.sao_type[c] = 0; continue; }
+      if (!((slice().sao_luma && c == 0) || (slice().sao_chroma && c > 0))) { ctu.sao_type[c] = 0; continue; }
       if (c < 2) {
-        int t = 0;
-        if (bin(CX_SAO_TYPE)) t = cabac.bypass() ? 2 : 1;
-        ctu.sao_type[c] = (uint8_t)t;
+        int ty = 0;
+        if (cb.bin(t, ctx[CX_SAO_TYPE])) ty = cb.bypass() ? 2 : 1;
+        ctu.sao_type[c] = (uint8_t)ty;
       } else {
         ctu.sao_type[2] = ctu.sao_type[1];
       }
@@ -303,18 +373,18 @@ struct Parser {
       int absv[4];
       for (int i = 0; i < 4; i++) {
         int v = 0;
-        while (v < cMax && cabac.bypass()) v++;
+        while (v < cMax && cb.bypass()) v++;
         absv[i] = v;
       }
       const int scale = c == 0 ? p.log2_sao_offset_scale_luma : p.log2_sao_offset_scale_chroma;
       if (ctu.sao_type[c] == 1) {
         int sign[4] = {0, 0, 0, 0};
         for (int i = 0; i < 4; i++)
-          if (absv[i]) sign[i] = cabac.bypass();
-        ctu.sao_band_or_class[c] = (uint8_t)cabac.bypass_bits(5);
+          if (absv[i]) sign[i] = cb.bypass();
+        ctu.sao_band_or_class[c] = (uint8_t)cb.bypass_bits(5);
         for (int i = 0; i < 4; i++) ctu.sao_offset[c][i] = (int8_t)((sign[i] ? -absv[i] : absv[i]) * (1 << scale));
       } else {
-        if (c < 2) ctu.sao_band_or_class[c] = (uint8_t)cabac.bypass_bits(2);
+        if (c < 2) ctu.sao_band_or_class[c] = (uint8_t)cb.bypass_bits(2);
         else ctu.sao_band_or_class[2] = ctu.sao_band_or_class[1];
         ctu.sao_offset[c][0] = (int8_t)(absv[0] * (1 << scale));
         ctu.sao_offset[c][1] = (int8_t)(absv[1] * (1 << scale));
@@ -322,11 +392,12 @@ struct Parser {
         ctu.sao_offset[c][3] = (int8_t)(-absv[3] * (1 << scale));
       }
     }
+    cabac = cb;
   }
 
   // ---- 8.6.1 QP derivation (transform.cc:31-210 bookkeeping) ----
   K0_FN void derive_qp(int xCU, int yCU) {
-    const Pic& p = *P;
+    const Pic& p = pic();
     const int qgmask = (1 << p.log2_min_cu_qp_delta_size) - 1;
     const int xQG = xCU - (xCU & qgmask), yQG = yCU - (yCU & qgmask);
     if (xQG != currentQG_x || yQG != currentQG_y) {
@@ -336,21 +407,21 @@ struct Parser {
     }
     const int ctbmask = (1 << p.log2_ctb) - 1;
     const bool firstInCTBRow = (xQG == 0 && (yQG & ctbmask) == 0);
-    const int sx = (sh->slice_addr_rs % p.ctbs_w) << p.log2_ctb, sy = (sh->slice_addr_rs / p.ctbs_w) << p.log2_ctb;
+    const int sx = (slice().slice_addr_rs % p.ctbs_w) << p.log2_ctb, sy = (slice().slice_addr_rs / p.ctbs_w) << p.log2_ctb;
     const bool firstQGInSlice = (sx == xQG && sy == yQG);
-    int pred = (firstQGInSlice || (firstInCTBRow && p.entropy_coding_sync)) ? sh->slice_qp_y : lastQPYinPreviousQG;
+    int pred = (firstQGInSlice || (firstInCTBRow && p.entropy_coding_sync)) ? slice().slice_qp_y : lastQPYinPreviousQG;
     int qA = pred, qB = pred;
     if (available_zscan(xQG, yQG, xQG - 1, yQG) && ctb_of(xQG - 1, yQG) == ctb_rs) qA = p.qp_map[((xQG - 1) >> 3) + (yQG >> 3) * p.w8];
     if (available_zscan(xQG, yQG, xQG, yQG - 1) && ctb_of(xQG, yQG - 1) == ctb_rs) qB = p.qp_map[(xQG >> 3) + ((yQG - 1) >> 3) * p.w8];
     pred = (qA + qB + 1) >> 1;
     const int QPY = ((pred + CuQpDeltaVal + 52 + 2 * p.qp_bd_offset_y) % (52 + p.qp_bd_offset_y)) - p.qp_bd_offset_y;
     qPYPrime = QPY + p.qp_bd_offset_y < 0 ? 0 : QPY + p.qp_bd_offset_y;
-    const int qPiCb = clip3i(-p.qp_bd_offset_c, 57, QPY + p.pps_cb_qp_offset + sh->cb_qp_offset);
-    const int qPiCr = clip3i(-p.qp_bd_offset_c, 57, QPY + p.pps_cr_qp_offset + sh->cr_qp_offset);
+    const int qPiCb = clip3i(-p.qp_bd_offset_c, 57, QPY + p.pps_cb_qp_offset + slice().cb_qp_offset);
+    const int qPiCr = clip3i(-p.qp_bd_offset_c, 57, QPY + p.pps_cr_qp_offset + slice().cr_qp_offset);
     int qPCb = qPiCb, qPCr = qPiCr;   // the reference does not cap non-4:2:0 at 51 (transform.cc:175-178)
     if (p.chroma_array_type == 1) {
-      qPCb = qPiCb < 30 ? qPiCb : (qPiCb >= 44 ? qPiCb - 6 : T->qpc420[qPiCb - 30]);
-      qPCr = qPiCr < 30 ? qPiCr : (qPiCr >= 44 ? qPiCr - 6 : T->qpc420[qPiCr - 30]);
+      qPCb = qPiCb < 30 ? qPiCb : (qPiCb >= 44 ? qPiCb - 6 : tab().qpc420[qPiCb - 30]);
+      qPCr = qPiCr < 30 ? qPiCr : (qPiCr >= 44 ? qPiCr - 6 : tab().qpc420[qPiCr - 30]);
     }
     qPCbPrime = qPCb + p.qp_bd_offset_c < 0 ? 0 : qPCb + p.qp_bd_offset_c;
     qPCrPrime = qPCr + p.qp_bd_offset_c < 0 ? 0 : qPCr + p.qp_bd_offset_c;
@@ -363,20 +434,24 @@ struct Parser {
     currentQPY = QPY;
   }
 
+  // every 4x4 unit belongs to exactly one transform unit and the map starts zeroed, so plain stores suffice
   HC_HD void mark_tu_edges(int x0, int y0, int log2) {
-    if (sh->deblocking_disabled) return;
-    const Pic& p = *P;
+    if (slice().deblocking_disabled) return;
+    const Pic& p = pic();
     const int n4 = (1 << log2) >> 2;
     const int left = (x0 == cu_x0) ? filterLeftCbEdge : 1, top = (y0 == cu_y0) ? filterTopCbEdge : 1;
+    uint8_t* e = p.edge_map + (x0 >> 2) + (y0 >> 2) * p.w4;
+    const uint8_t fl = left ? HC_EDGE_V : 0, ft = top ? HC_EDGE_H : 0;
+    if (fl | ft) e[0] = (uint8_t)(fl | ft);
     if (left)
-      for (int k = 0; k < n4; k++) p.edge_map[(x0 >> 2) + ((y0 >> 2) + k) * p.w4] |= HC_EDGE_V;
+      for (int k = 1; k < n4; k++) e[k * p.w4] = HC_EDGE_V;
     if (top)
-      for (int k = 0; k < n4; k++) p.edge_map[((x0 >> 2) + k) + (y0 >> 2) * p.w4] |= HC_EDGE_H;
+      for (int k = 1; k < n4; k++) e[k] = HC_EDGE_H;
   }
 
   // neighbour availability of one prediction block (intrapred.h:443-543, :838-940)
   K0_FN void emit_blk(int cIdx, int xB, int yB, int log2, int mode, bool has_resid, uint32_t resid_off) {
-    const Pic& p = *P;
+    const Pic& p = pic();
     const int nT = 1 << log2;
     const int SubW = cIdx == 0 ? 1 : p.sub_w, SubH = cIdx == 0 ? 1 : p.sub_h;
     const int xBL = xB * SubW, yBL = yB * SubH;
@@ -387,11 +462,13 @@ struct Parser {
     const int l2c = p.log2_ctb, cw = p.ctbs_w;
     const int xCur = xBL >> l2c, yCur = yBL >> l2c;
     const int xLeft = (xBL - 1) >> l2c, xRight = (xBL + nT * SubW) >> l2c, yTop = (yBL - 1) >> l2c;
-    const int sa = slice_addr_of_ctb(xCur + yCur * cw);
-    if (aL && slice_addr_of_ctb(xLeft + yCur * cw) != sa) aL = false;
-    if (aT && slice_addr_of_ctb(xCur + yTop * cw) != sa) aT = false;
-    if (aTL && slice_addr_of_ctb(xLeft + yTop * cw) != sa) aTL = false;
-    if (aTR && slice_addr_of_ctb(xRight + yTop * cw) != sa) aTR = false;
+    if (p.nslices != 1) {
+      const int sa = slice_addr_of_ctb(xCur + yCur * cw);
+      if (aL && slice_addr_of_ctb(xLeft + yCur * cw) != sa) aL = false;
+      if (aT && slice_addr_of_ctb(xCur + yTop * cw) != sa) aT = false;
+      if (aTL && slice_addr_of_ctb(xLeft + yTop * cw) != sa) aTL = false;
+      if (aTR && slice_addr_of_ctb(xRight + yTop * cw) != sa) aTR = false;
+    }
     int nBottom = (p.H - yBL + SubH - 1) / SubH;
     if (nBottom > 2 * nT) nBottom = 2 * nT;
     int nRight = (p.W - xBL + SubW - 1) / SubW;
@@ -424,45 +501,52 @@ struct Parser {
   }
 
   // ---- 7.3.8.11 residual_coding ----
+  // The arithmetic decoder state is copied into a local for the duration of the call, and the per-sub-block lists
+  // (scan positions, base levels, "escape possible" flags, coded-sub-block neighbours) are bit-packed scalars, so the
+  // whole loop nest runs out of registers and shared memory.
   K0_FN uint32_t residual_coding(int log2, int cIdx, int pred_mode) {
-    const Pic& p = *P;
+    const Pic& p = pic();
+    const Tables& t = tab();
+    uint8_t* const ctx = ctxs();
+    Cabac cb = cabac;
     bool tskip = false;
-    if (p.transform_skip_enabled && log2 <= p.log2_max_transform_skip_size) tskip = bin(CX_TSKIP + (cIdx ? 1 : 0));
+    if (p.transform_skip_enabled && log2 <= p.log2_max_transform_skip_size) tskip = cb.bin(t, ctx[CX_TSKIP + (cIdx ? 1 : 0)]);
 
     // last significant coefficient position
     int last[2];
-    for (int d = 0; d < 2; d++) {
+    {
       const int cMax = (log2 << 1) - 1;
       int offset, shift;
       if (cIdx == 0) { offset = 3 * (log2 - 2) + ((log2 - 1) >> 2); shift = (log2 + 1) >> 2; }
       else { offset = 15; shift = log2 - 2; }
-      int v = 0;
-      const int base = d ? CX_LAST_Y : CX_LAST_X;
-      while (v < cMax && bin(base + offset + (v >> shift))) v++;
-      last[d] = v;
+      for (int d = 0; d < 2; d++) {
+        int v = 0;
+        const int base = (d ? CX_LAST_Y : CX_LAST_X) + offset;
+        while (v < cMax && cb.bin(t, ctx[base + (v >> shift)])) v++;
+        last[d] = v;
+      }
     }
     int LastX = last[0], LastY = last[1];
-    if (last[0] > 3) { const int nb = (last[0] >> 1) - 1; LastX = ((2 + (last[0] & 1)) << nb) + (int)cabac.bypass_bits(nb); }
-    if (last[1] > 3) { const int nb = (last[1] >> 1) - 1; LastY = ((2 + (last[1] & 1)) << nb) + (int)cabac.bypass_bits(nb); }
+    if (last[0] > 3) { const int nb = (last[0] >> 1) - 1; LastX = ((2 + (last[0] & 1)) << nb) + (int)cb.bypass_bits(nb); }
+    if (last[1] > 3) { const int nb = (last[1] >> 1) - 1; LastY = ((2 + (last[1] & 1)) << nb) + (int)cb.bypass_bits(nb); }
 
     int scanIdx = 0;
     if (log2 == 2 || (log2 == 3 && (cIdx == 0 || p.chroma_array_type == 3))) {
       if (pred_mode >= 6 && pred_mode <= 14) scanIdx = 2;
       else if (pred_mode >= 22 && pred_mode <= 30) scanIdx = 1;
     }
-    if (scanIdx == 2) { const int t = LastX; LastX = LastY; LastY = t; }
+    if (scanIdx == 2) { const int tmp = LastX; LastX = LastY; LastY = tmp; }
     const int nT = 1 << log2;
     if (LastX >= nT || LastY >= nT) { fail(ERR_BITSTREAM); return 0; }
 
     const int lsb = log2 - 2;
-    const uint8_t* scanSub = T->scan_sub[lsb][scanIdx];
-    const uint8_t* scanPos = T->scan_pos[scanIdx];
-    const int sbW = 1 << lsb;
-    const int lastSubBlock = T->inv_sub[lsb][scanIdx][(LastX >> 2) + ((LastY >> 2) << lsb)];
-    const int lastScanPos = T->inv_pos[scanIdx][(LastX & 3) + ((LastY & 3) << 2)];
+    const uint8_t* scanSub = t.scan_sub[lsb][scanIdx];
+    const uint8_t* scanPos = t.scan_pos[scanIdx];
+    const int lastSubBlock = t.inv_sub[lsb][scanIdx][(LastX >> 2) + ((LastY >> 2) << lsb)];
+    const int lastScanPos = t.inv_pos[scanIdx][(LastX & 3) + ((LastY & 3) << 2)];
 
-    uint8_t csbf_nb[64];
-    for (int i = 0; i < sbW * sbW; i++) csbf_nb[i] = 0;
+    // coded_sub_block_flag of the right / lower neighbour, one bit per sub-block at Sx + 8 * Sy
+    unsigned long long csbf_right = 0, csbf_below = 0;
 
     if (ntb >= p.tb_cap_ctb || nresid + (uint32_t)(nT * nT) > p.resid_cap_ctb) { fail(ERR_CAPACITY); return 0; }
     const uint32_t coeff_first = (uint32_t)ctb_rs * p.coeff_cap_ctb + ncoeff;
@@ -488,44 +572,45 @@ struct Parser {
     int c1 = 1;
     uint32_t ncoeff_total = 0;
     const int chroma = cIdx ? 1 : 0;
+    const int ts_c = chroma ? 43 : 42;
+    const int sig_size = log2 == 3 ? (scanIdx == 0 ? 0 : 1) : 2;
 
     for (int i = lastSubBlock; i >= 0; i--) {
-      const int Sx = scanSub[i] & 7, Sy = scanSub[i] >> 3;
+      const int sxy = scanSub[i];
+      const int Sx = sxy & 7, Sy = sxy >> 3;
+      const int prevCsbf = (int)((csbf_right >> sxy) & 1) | ((int)((csbf_below >> sxy) & 1) << 1);
       int inferSbDc = 0, coded = 1;
       if (i < lastSubBlock && i > 0) {
-        coded = bin(CX_CSBF + (csbf_nb[Sx + Sy * sbW] ? 1 : 0) + (cIdx ? 2 : 0));
+        coded = cb.bin(t, ctx[CX_CSBF + (prevCsbf ? 1 : 0) + (cIdx ? 2 : 0)]);
         inferSbDc = 1;
       }
       if (!coded) continue;
-      if (Sx > 0) csbf_nb[Sx - 1 + Sy * sbW] |= 1;
-      if (Sy > 0) csbf_nb[Sx + (Sy - 1) * sbW] |= 2;
+      if (Sx > 0) csbf_right |= 1ull << (sxy - 1);
+      if (Sy > 0) csbf_below |= 1ull << (sxy - 8);
 
-      int16_t value[16];
-      int8_t spos[16];
-      uint8_t maxbase[16];
+      // significant positions of this sub-block in decoding order: 4 bits each, entry c at bits [4c, 4c + 4)
+      unsigned long long spos = 0;
       int n = 0;
-      const int prevCsbf = csbf_nb[Sx + Sy * sbW];
       const int xS0 = Sx << 2, yS0 = Sy << 2;
-      const uint8_t* sigtab = log2 == 2 ? T->sig_b4[chroma][scanIdx]
-                                        : T->sig_sb[chroma][log2 == 3 ? (scanIdx == 0 ? 0 : 1) : 2][(Sx | Sy) ? 1 : 0][prevCsbf][scanIdx];
-      const int ts_c = chroma ? 43 : 42;
+      const uint8_t* sigtab = log2 == 2 ? t.sig_b4[chroma][scanIdx] : t.sig_sb[chroma][sig_size][(Sx | Sy) ? 1 : 0][prevCsbf][scanIdx];
       const int dc_ctx = ts_ctx ? ts_c : ((log2 == 2 || i > 0) ? sigtab[0] : (chroma ? 27 : 0));
 
       const int last_coeff = (i == lastSubBlock) ? lastScanPos - 1 : 15;
-      if (i == lastSubBlock) spos[n++] = (int8_t)lastScanPos;
-      for (int k = last_coeff; k > 0; k--) {
-        const int b = bin(CX_SIG + (ts_ctx ? ts_c : sigtab[k]));
-        spos[n] = (int8_t)k;
-        n += b;
+      if (i == lastSubBlock) { spos = (unsigned long long)lastScanPos; n = 1; }
+      if (ts_ctx) {
+        for (int k = last_coeff; k > 0; k--) {
+          const int b = cb.bin(t, ctx[CX_SIG + ts_c]);
+          if (b) { spos |= (unsigned long long)k << (4 * n); n++; }
+        }
+      } else {
+        for (int k = last_coeff; k > 0; k--) {
+          const int b = cb.bin(t, ctx[CX_SIG + sigtab[k]]);
+          if (b) { spos |= (unsigned long long)k << (4 * n); n++; }
+        }
       }
       if (last_coeff >= 0) {
-        if (n > 0 || !inferSbDc) {
-          const int b = bin(CX_SIG + dc_ctx);
-          spos[n] = 0;
-          n += b;
-        } else {
-          spos[n++] = 0;
-        }
+        if (n > 0 || !inferSbDc) n += cb.bin(t, ctx[CX_SIG + dc_ctx]);   // position 0: nothing to OR into spos
+        else n++;
       }
       if (n == 0) continue;
 
@@ -535,31 +620,34 @@ struct Parser {
       int firstG1 = 16;
       const int ng1 = n < 8 ? n : 8;
       const int g1base = CX_G1 + ctxSet * 4 + (cIdx > 0 ? 16 : 0);
+      uint32_t g1mask = 0;              // coefficient c has abs level >= 2
       for (int c = 0; c < ng1; c++) {
-        const int b = bin(g1base + c1);
-        value[c] = (int16_t)(1 + b);
-        maxbase[c] = (uint8_t)b;
+        const int b = cb.bin(t, ctx[g1base + c1]);
+        g1mask |= (uint32_t)b << c;
         if (b && c < firstG1) firstG1 = c;
         c1 = b ? 0 : ((c1 > 0 && c1 < 3) ? c1 + 1 : c1);
       }
-      for (int c = ng1; c < n; c++) { value[c] = 1; maxbase[c] = 1; }
+      // escape (coeff_abs_level_remaining) follows when the base level is at its maximum: 3 for the first "greater 1"
+      // coefficient with greater2 set, 2 for the other greater-1 coefficients of the first eight, 1 beyond them
+      uint32_t escmask = (g1mask | ~((1u << ng1) - 1u)) & ((1u << n) - 1u);
+      int g2 = 0;
       if (firstG1 < 16) {
-        const int f = bin(CX_G2 + ctxSet + (cIdx > 0 ? 4 : 0));
-        value[firstG1] = (int16_t)(value[firstG1] + f);
-        maxbase[firstG1] = (uint8_t)f;
+        g2 = cb.bin(t, ctx[CX_G2 + ctxSet + (cIdx > 0 ? 4 : 0)]);
+        if (!g2) escmask &= ~(1u << firstG1);
       }
 
-      const bool signHidden = sign_hiding_possible && (spos[0] - spos[n - 1] > 3);
+      const int pos_first = (int)(spos & 15), pos_last = (int)((spos >> (4 * (n - 1))) & 15);
+      const bool signHidden = sign_hiding_possible && (pos_first - pos_last > 3);
       const int nsign = signHidden ? n - 1 : n;
-      const uint32_t signs = cabac.bypass_bits(nsign) << (16 - nsign);
+      const uint32_t signs = cb.bypass_bits(nsign) << (16 - nsign);
 
       if (ncoeff_total + (uint32_t)n > coeff_room) { fail(ERR_CAPACITY); return 0; }
       int sumAbs = 0, rice = 0;
       for (int c = 0; c < n; c++) {
-        const int base = value[c];
+        const int base = 1 + (int)((g1mask >> c) & 1) + ((c == firstG1) ? g2 : 0);
         int rem = 0;
-        if (maxbase[c]) {
-          const uint32_t q16 = cabac.peek16();
+        if ((escmask >> c) & 1) {
+          const uint32_t q16 = cb.peek16();
           const int ones = q16 == 0xffffu ? 16 : k0_clz(~(q16 << 16));
           const int suffix_len = ones <= 3 ? rice : ones - 3 + rice;
           const int len = ones + 1 + suffix_len;
@@ -567,44 +655,44 @@ struct Parser {
             const uint32_t bins = q16 >> (16 - len);
             const int suffix = (int)(bins & ((1u << suffix_len) - 1u));
             rem = ones <= 3 ? (ones << rice) + suffix : (((1 << (ones - 3)) + 3 - 1) << rice) + suffix;
-            cabac.consume(len, bins);
+            cb.consume(len, bins);
           } else {
             int prefix = 0;
-            while (prefix < 32 && cabac.bypass()) prefix++;
+            while (prefix < 32 && cb.bypass()) prefix++;
             if (prefix >= 32) { fail(ERR_BITSTREAM); return 0; }
-            if (prefix <= 3) rem = (prefix << rice) + (int)cabac.bypass_bits(rice);
-            else rem = (((1 << (prefix - 3)) + 3 - 1) << rice) + (int)cabac.bypass_bits(prefix - 3 + rice);
+            if (prefix <= 3) rem = (prefix << rice) + (int)cb.bypass_bits(rice);
+            else rem = (((1 << (prefix - 3)) + 3 - 1) << rice) + (int)cb.bypass_bits(prefix - 3 + rice);
           }
           if (base + rem > 3 * (1 << rice)) { rice++; if (rice > 4) rice = 4; }
         }
-        int16_t level = (int16_t)(base + rem);
+        int level = base + rem;
         const bool neg = (c < nsign) ? ((signs >> (15 - c)) & 1) : false;
-        if (neg) level = (int16_t)-level;
+        if (neg) level = -level;
         if (signHidden) {
           sumAbs += base + rem;
-          if (c == n - 1 && (sumAbs & 1)) level = (int16_t)-level;
+          if (c == n - 1 && (sumAbs & 1)) level = -level;
         }
-        const int sp = scanPos[spos[c]];
+        const int sp = scanPos[(int)((spos >> (4 * c)) & 15)];
         hc_coeff co;
-        co.pos = (uint16_t)((xS0 + (sp & 3)) + (yS0 + (sp >> 2)) * nT);
-        co.level = level;
+        co.pos = (uint16_t)((xS0 + (sp & 3)) + ((yS0 + (sp >> 2)) << log2));
+        co.level = (int16_t)level;
         out[ncoeff_total++] = co;
       }
     }
+    cabac = cb;
     tb.ncoeff = (uint16_t)ncoeff_total;
     const uint32_t tb_local = (uint32_t)ctb_rs * p.tb_cap_ctb + ntb;
     p.tbs[tb_local] = tb;
+    scratch().tb_size[ntb] = (uint8_t)(log2 - 2);
     ntb++;
     ncoeff += ncoeff_total;
     nresid += (uint32_t)(nT * nT);
-    const unsigned slot = list_append(p.tb_counts + (log2 - 2));
-    p.tb_lists[log2 - 2][slot] = p.tb_global_base + tb_local;
     return tb.resid_off;
   }
 
   // ---- 7.3.8.10 transform_unit (record emission in the reference's reconstruction order, slice.cc:3979-4118) ----
   K0_FN void transform_unit(int x0, int y0, int xBase, int yBase, int log2, int blkIdx, int cbf_luma, int cbf_cb, int cbf_cr) {
-    const Pic& p = *P;
+    const Pic& p = pic();
     const int cat = p.chroma_array_type;
     const int log2C = cat == 3 ? log2 : (log2 - 1 < 2 ? 2 : log2 - 1);
     if ((cbf_luma || cbf_cb || cbf_cr) && p.cu_qp_delta_enabled && !IsCuQpDeltaCoded) {
@@ -658,7 +746,7 @@ struct Parser {
   template <int LOG2>
   K0_FN void transform_tree(int x0, int y0, int xBase, int yBase, int depth, int blkIdx, int max_depth, int intra_split,
                             int parent_cbf_cb, int parent_cbf_cr) {
-    const Pic& p = *P;
+    const Pic& p = pic();
     if (err || cabac.overrun()) { fail(ERR_BITSTREAM); return; }
     int split;
     if (LOG2 <= p.log2_max_tb && LOG2 > p.log2_min_tb && depth < max_depth && !(intra_split && depth == 0)) split = bin(CX_SPLIT_TRANSFORM + 5 - LOG2);
@@ -696,7 +784,7 @@ struct Parser {
   // ---- 7.3.8.5 coding_unit (I slices) ----
   template <int LOG2>
   K0_FN void coding_unit(int x0, int y0, int depth) {
-    const Pic& p = *P;
+    const Pic& p = pic();
     constexpr int nCbS = 1 << LOG2;
     cu_x0 = x0; cu_y0 = y0; cu_log2 = LOG2;
     {
@@ -709,28 +797,31 @@ struct Parser {
     filterTopCbEdge = y0 != 0;
     {
       const int ctbmask = (1 << p.log2_ctb) - 1;
-      if (x0 && (x0 & ctbmask) == 0 && !sh->loop_filter_across_slices && slice_addr_of_ctb(ctb_of(x0 - 1, y0)) != sh->slice_addr_rs) filterLeftCbEdge = 0;
-      if (y0 && (y0 & ctbmask) == 0 && !sh->loop_filter_across_slices && slice_addr_of_ctb(ctb_of(x0, y0 - 1)) != sh->slice_addr_rs) filterTopCbEdge = 0;
+      if (x0 && (x0 & ctbmask) == 0 && !slice().loop_filter_across_slices && slice_addr_of_ctb(ctb_of(x0 - 1, y0)) != slice().slice_addr_rs) filterLeftCbEdge = 0;
+      if (y0 && (y0 & ctbmask) == 0 && !slice().loop_filter_across_slices && slice_addr_of_ctb(ctb_of(x0, y0 - 1)) != slice().slice_addr_rs) filterTopCbEdge = 0;
     }
     derive_qp(x0, y0);
 
+    const Tables& t = tab();
+    uint8_t* const ctx = ctxs();
+    Cabac cb = cabac;
     bool nxn = false;
     if (LOG2 == p.log2_min_cb) {
-      nxn = !bin(CX_PART_MODE);
+      nxn = !cb.bin(t, ctx[CX_PART_MODE]);
       if (nxn && LOG2 <= p.log2_min_tb) { fail(ERR_BITSTREAM); return; }
     }
     // ---- intra prediction modes ----
     const int pbOffset = nxn ? nCbS / 2 : nCbS;
     const int nparts = nxn ? 4 : 1;
     int prev_flag[4], mpm_idx[4] = {0, 0, 0, 0}, rem[4] = {0, 0, 0, 0};
-    for (int i = 0; i < nparts; i++) prev_flag[i] = bin(CX_PREV_INTRA_LUMA);
+    for (int i = 0; i < nparts; i++) prev_flag[i] = cb.bin(t, ctx[CX_PREV_INTRA_LUMA]);
     for (int i = 0; i < nparts; i++) {
       if (prev_flag[i]) {
         int v = 0;
-        while (v < 2 && cabac.bypass()) v++;
+        while (v < 2 && cb.bypass()) v++;
         mpm_idx[i] = v;
       } else {
-        rem[i] = (int)cabac.bypass_bits(5);
+        rem[i] = (int)cb.bypass_bits(5);
       }
     }
     const bool availA0 = ctb_available(x0, y0, x0 - 1, y0), availB0 = ctb_available(x0, y0, x0, y0 - 1);
@@ -774,20 +865,21 @@ struct Parser {
       const int nchroma = cat == 3 ? nparts : 1;
       for (int idx = 0; idx < nchroma; idx++) {
         int icpm = 4;
-        if (bin(CX_INTRA_CHROMA)) icpm = (int)cabac.bypass_bits(2);
+        if (cb.bin(t, ctx[CX_INTRA_CHROMA])) icpm = (int)cb.bypass_bits(2);
         const int luma = luma_modes[idx];
         int m = luma;
         if (icpm != 4) {
           m = icpm == 0 ? 0 : (icpm == 1 ? 26 : (icpm == 2 ? 10 : 1));
           if (m == luma) m = 34;
         }
-        if (cat == 2) m = T->mode422[m];
+        if (cat == 2) m = tab().mode422[m];
         const int i = cat == 3 ? (idx & 1) * pbOffset : 0, j = cat == 3 ? (idx >> 1) * pbOffset : 0;
         const int n4 = (cat == 3 ? pbOffset : nCbS) >> 2;
         for (int yy = 0; yy < n4; yy++)
           for (int xx = 0; xx < n4; xx++) p.ipm_c[(((x0 + i) >> 2) + xx) + (((y0 + j) >> 2) + yy) * p.w4] = (uint8_t)m;
       }
     }
+    cabac = cb;
     const int max_depth = p.max_th_depth_intra + (nxn ? 1 : 0);
     transform_tree<LOG2>(x0, y0, x0, y0, 0, 0, max_depth, nxn ? 1 : 0, 1, 1);
   }
@@ -795,7 +887,7 @@ struct Parser {
   // ---- 7.3.8.4 coding_quadtree ----
   template <int LOG2>
   K0_FN void coding_quadtree(int x0, int y0, int depth) {
-    const Pic& p = *P;
+    const Pic& p = pic();
     if (err || cabac.overrun()) { fail(ERR_BITSTREAM); return; }
     constexpr int size = 1 << LOG2;
     bool split;
@@ -827,50 +919,68 @@ struct Parser {
 
   // ---- one CTU ----
   K0_FN void decode_ctu() {
-    const Pic& p = *P;
+    const Pic& p = pic();
     hc_ctu& ctu = p.ctus[ctb_rs];
     nblk[0] = nblk[1] = nblk[2] = 0;
     ntb = ncoeff = nresid = 0;
     for (int c = 0; c < 3; c++) { ctu.sao_type[c] = 0; ctu.sao_band_or_class[c] = 0; for (int i = 0; i < 4; i++) ctu.sao_offset[c][i] = 0; }
-    if (sh->sao_luma || sh->sao_chroma) read_sao(ctu);
+    if (slice().sao_luma || slice().sao_chroma) read_sao(ctu);
     const int x0 = ctb_x << p.log2_ctb, y0 = ctb_y << p.log2_ctb;
     if (p.log2_ctb == 6) coding_quadtree<6>(x0, y0, 0);
     else if (p.log2_ctb == 5) coding_quadtree<5>(x0, y0, 0);
     else if (p.log2_ctb == 4) coding_quadtree<4>(x0, y0, 0);
     else coding_quadtree<3>(x0, y0, 0);
+    // K1 launch lists: one reservation per size class and CTB instead of one atomic per transform block
+    if (ntb) {
+      const uint8_t* ts = scratch().tb_size;
+      const uint32_t tb0 = p.tb_global_base + (uint32_t)ctb_rs * p.tb_cap_ctb;
+      unsigned long long packed = 0;   // four 16-bit counters
+      for (uint32_t t = 0; t < ntb; t++) packed += 1ull << (16 * ts[t]);
+      for (int l = 0; l < 4; l++) {
+        const unsigned n = (unsigned)(packed >> (16 * l)) & 0xffffu;
+        if (!n) continue;
+        unsigned slot = list_reserve(p.tb_counts + l, n);
+        uint32_t* dst = p.tb_lists[l];
+        for (uint32_t t = 0; t < ntb; t++)
+          if (ts[t] == l) dst[slot++] = tb0 + t;
+      }
+    }
     uint32_t base = (uint32_t)ctb_rs * p.blk_cap_ctb;
     for (int c = 0; c < 3; c++) {
       ctu.blk_first[c] = base;
       ctu.blk_count[c] = (uint16_t)nblk[c];
       base += p.blk_cap[c];
     }
-    ctu.beta_offset = sh->beta_offset;
-    ctu.tc_offset = sh->tc_offset;
+    ctu.beta_offset = slice().beta_offset;
+    ctu.tc_offset = slice().tc_offset;
     const uint8_t* st = p.ctu_static + 4 * ctb_rs;
     ctu.sao_nb = st[0];
     ctu.sao_nb_c = st[1];
-    ctu.flags = (uint8_t)(st[2] | (sh->deblocking_disabled ? HC_CTU_DEBLOCK_OFF : 0));
+    ctu.flags = (uint8_t)(st[2] | (slice().deblocking_disabled ? HC_CTU_DEBLOCK_OFF : 0));
     ctu.pad[0] = ctu.pad[1] = ctu.pad[2] = 0;
   }
 
   // ---- a chain of substreams (decode_slice_segment loop of the host parser) ----
   K0_FN void run_chain(const Pic* pics, const Sub* subs, uint32_t first_sub, uint32_t nsubs) {
     err = ERR_NONE;
-    const Pic* first_pic = pics + subs[first_sub].pic;
+    uint32_t loaded_pic = 0xffffffffu;
+    uint8_t* const ctx = ctxs();
     for (uint32_t s = 0; s < nsubs && !err; s++) {
-      const Sub& sub = subs[first_sub + s];
-      P = pics + sub.pic;
-      const Pic& p = *P;
-      sh = p.slices + sub.slice;
-      const uint8_t* seg_end = p.bytes + sh->data_end;
+      const Sub sub = subs[first_sub + s];
+      if (sub.pic != loaded_pic) { scratch().pic = pics[sub.pic]; loaded_pic = sub.pic; }
+      const Pic& p = pic();
+      scratch().slice = p.slices[sub.slice];
+      slice_addr = slice().slice_addr_rs;
+      const uint8_t* seg_end = p.bytes + slice().data_end;
       if (sub.byte_begin != 0xffffffffu) cabac.init(p.bytes + sub.byte_begin, seg_end);
       const bool row_chain = sub.flags & SUB_ROW_CHAIN;
       ctb_rs = sub.first_ctb;
       currentQG_x = currentQG_y = -1;
       currentQPY = 0;
-      if (!row_chain && sub.first_ctb == sh->segment_address && sh->segment_address > 0) {
+      if (s == 0) { IsCuQpDeltaCoded = false; CuQpDeltaVal = 0; lastQPYinPreviousQG = 0; }
+      if (!row_chain && sub.first_ctb == slice().segment_address && slice().segment_address > 0) {
         // thread-context initialisation of the reference (decctx.cc:467-506)
-        const int prev = sh->segment_address - 1;
+        const int prev = slice().segment_address - 1;
         int x = (((prev % p.ctbs_w) + 1) << p.log2_ctb) - 1, y = (((prev / p.ctbs_w) + 1) << p.log2_ctb) - 1;
         if (x > p.W - 1) x = p.W - 1;
         if (y > p.H - 1) y = p.H - 1;
@@ -878,22 +988,23 @@ struct Parser {
       }
       // 9.3.1: context initialisation at the start of the slice segment (dependent segments of a serial chain keep
       // the table of the previous segment; rows of a WPP picture synchronise below)
-      const bool segment_start = sub.first_ctb == sh->segment_address;
-      if (segment_start && !sh->dependent) init_contexts();
-      bool first_of_independent = segment_start && !sh->dependent;
+      const bool segment_start = sub.first_ctb == slice().segment_address;
+      if (segment_start && !slice().dependent) init_contexts();
+      bool first_of_independent = segment_start && !slice().dependent;
 
+      ctb_x = ctb_rs % p.ctbs_w;
+      ctb_y = ctb_rs / p.ctbs_w;
       while (ctb_rs < sub.end_ctb && !err) {
-        ctb_x = ctb_rs % p.ctbs_w;
-        ctb_y = ctb_rs / p.ctbs_w;
         if (row_chain && ctb_y > 0) {
           // wavefront: the row above must be two CTBs ahead (its context table, split depths and SAO parameters)
           const int need = ctb_x + 2 < p.ctbs_w ? ctb_x + 2 : p.ctbs_w;
           while (progress_load(p.progress + ctb_y - 1) < need) backoff();
         }
-        if (p.entropy_coding_sync && ctb_x == 0 && ctb_y >= 1 && !(first_of_independent && ctb_rs == sh->segment_address)) {
+        if (p.entropy_coding_sync && ctb_x == 0 && ctb_y >= 1 && !(first_of_independent && ctb_rs == slice().segment_address)) {
           if (p.ctbs_w > 1) {
-            const uint8_t* src = p.wpp_ctx + (size_t)(ctb_y - 1) * CTX_BYTES;
-            for (int i = 0; i < CX_COUNT; i++) ctx[i] = src[i];
+            const uint32_t* src = reinterpret_cast<const uint32_t*>(p.wpp_ctx + (size_t)(ctb_y - 1) * CTX_BYTES);
+            uint32_t* dst = reinterpret_cast<uint32_t*>(ctx);
+            for (int i = 0; i < CTX_BYTES / 4; i++) dst[i] = src[i];
           } else {
             init_contexts();
           }
@@ -902,15 +1013,17 @@ struct Parser {
         if (err) break;
         if (cabac.overrun()) { fail(ERR_BITSTREAM); break; }
         if (p.entropy_coding_sync && ctb_x == 1 && ctb_y < p.ctbs_h - 1) {
-          uint8_t* dst = p.wpp_ctx + (size_t)ctb_y * CTX_BYTES;
-          for (int i = 0; i < CX_COUNT; i++) dst[i] = ctx[i];
+          uint32_t* dst = reinterpret_cast<uint32_t*>(p.wpp_ctx + (size_t)ctb_y * CTX_BYTES);
+          const uint32_t* src = reinterpret_cast<const uint32_t*>(ctx);
+          for (int i = 0; i < CTX_BYTES / 4; i++) dst[i] = src[i];
         }
         if (row_chain) progress_store(p.progress + ctb_y, ctb_x + 1);
         const int end_of_slice_segment = cabac.terminate();
         ctb_rs++;
+        if (++ctb_x == p.ctbs_w) { ctb_x = 0; ctb_y++; }
         if (end_of_slice_segment) break;
         if (ctb_rs >= p.ctbs_w * p.ctbs_h) { fail(ERR_BITSTREAM); break; }
-        if (p.entropy_coding_sync && (ctb_rs % p.ctbs_w) == 0) {
+        if (p.entropy_coding_sync && ctb_x == 0) {
           if (!cabac.terminate()) { fail(ERR_BITSTREAM); break; }   // end_of_subset_one_bit
           if (row_chain) break;                                       // the next row is another chain
           const uint8_t* np = cabac.position();
@@ -923,7 +1036,8 @@ struct Parser {
     }
     if (err) {
       // unblock every waiter of this picture, then report
-      const Pic& p = *(P ? P : first_pic);
+      if (loaded_pic == 0xffffffffu) scratch().pic = pics[subs[first_sub].pic];
+      const Pic& p = pic();
       for (int r = 0; r < p.ctbs_h; r++) progress_store(p.progress + r, 1 << 30);
       *p.error = err;
     }

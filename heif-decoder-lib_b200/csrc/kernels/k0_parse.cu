@@ -1,34 +1,46 @@
-// k0_parse.cu — K0 on the device: one CTA (one warp, lane 0 walks the syntax) per substream chain.
+// k0_parse.cu — K0 on the device: one warp (lane 0 walks the syntax) per substream chain, K0_WARPS chains per CTA.
 //
 // CABAC is serial inside a substream, so the parallelism is across substreams: the CTB rows of WPP pictures
 // (wavefront-synchronised with the row above, kernels/k0_core.cuh) and across the pictures / grid tiles / files of a
 // batch — a 12 MP iPhone-style grid image is 48 tiles x 8 rows = 384 chains; a batch of 8 such files keeps 3072
 // chains in flight. Chains are ordered row-major across all pictures so that a chain only ever waits for a chain
-// with a smaller index (scheduled no later than itself). The context table of a chain lives in shared memory.
+// with a smaller index (scheduled no later than itself). Tables, context states and the picture / slice descriptors
+// of a chain live in shared memory (k0_core.cuh: Scratch).
 #include "launch.h"
 #include "k0_core.cuh"
 
 namespace hc {
 
-__global__ void __launch_bounds__(32, 20) k0_parse_kernel(const k0::Tables* __restrict__ tables, const k0::Pic* __restrict__ pics,
-                                                      const k0::Sub* __restrict__ subs, const k0::Chain* __restrict__ chains,
-                                                      int nchains) {
-  __shared__ uint8_t ctx[k0::CTX_BYTES];
-  if (threadIdx.x != 0 || (int)blockIdx.x >= nchains) return;
-  const k0::Chain ch = chains[blockIdx.x];
+// Chains per CTA: the warps of a CTA share one shared-memory copy of the parser tables; each warp owns a Scratch
+// (context states, picture / slice descriptors, K1 list staging). Consecutive chains are the same CTB row of
+// consecutive pictures, so the warps of a CTA run for about the same time.
+constexpr int K0_WARPS = 4;
+
+__global__ void __launch_bounds__(32 * K0_WARPS, 5) k0_parse_kernel(const k0::Tables* __restrict__ tables, const k0::Pic* __restrict__ pics,
+                                                                   const k0::Sub* __restrict__ subs, const k0::Chain* __restrict__ chains,
+                                                                   int nchains) {
+  {
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(tables);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(k0::k0_smem);
+    for (int i = threadIdx.x; i < (int)(sizeof(k0::Tables) / 4); i += blockDim.x) dst[i] = src[i];
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5;
+  const int chain = blockIdx.x * K0_WARPS + warp;
+  if ((threadIdx.x & 31) != 0 || chain >= nchains) return;
+  const k0::Chain ch = chains[chain];
   k0::Parser ps;
-  ps.T = tables;
-  ps.cabac.T = tables;
-  ps.ctx = ctx;
-  ps.P = nullptr;
-  ps.sh = nullptr;
+  memset(&ps, 0, sizeof(ps));   // CuQpDeltaVal & co. are read even when the stream never codes them
+  ps.wbase = (uint32_t)(k0::TABLE_BYTES + warp * k0::SCRATCH_BYTES);
   ps.run_chain(pics, subs, ch.first_sub, ch.nsubs);
 }
 
 void launch_k0(const k0::Tables* tables, const k0::Pic* pics, const k0::Sub* subs, const k0::Chain* chains, int nchains,
                cudaStream_t stream) {
   if (nchains <= 0) return;
-  k0_parse_kernel<<<nchains, 32, 0, stream>>>(tables, pics, subs, chains, nchains);
+  static_assert(sizeof(k0::Tables) % 4 == 0, "tables are copied word-wise");
+  const int smem = k0::TABLE_BYTES + K0_WARPS * k0::SCRATCH_BYTES;
+  k0_parse_kernel<<<(nchains + K0_WARPS - 1) / K0_WARPS, 32 * K0_WARPS, smem, stream>>>(tables, pics, subs, chains, nchains);
 }
 
 }  // namespace hc
