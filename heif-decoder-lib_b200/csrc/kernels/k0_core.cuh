@@ -29,6 +29,13 @@
 #else
 #define K0_FN __attribute__((noinline))
 #endif
+// Loops are not unrolled on the device: the parser is one thread per warp and bound by instruction fetch
+// (ncu: "no_instruction" was the top stall of the running warps), so code size matters more than loop overhead.
+#if defined(__CUDA_ARCH__)
+#define K0_LOOP _Pragma("unroll 1")
+#else
+#define K0_LOOP
+#endif
 
 namespace hc {
 namespace k0 {
@@ -311,7 +318,7 @@ struct Parser {
     const Tables& t = tab();
     uint8_t* ctx = ctxs();
     const int qp = slice().slice_qp_y;
-    for (int i = 0; i < CX_COUNT; i++) ctx[i] = ctx_init_state(t.ctx_init[i], qp);
+    K0_LOOP for (int i = 0; i < CX_COUNT; i++) ctx[i] = ctx_init_state(t.ctx_init[i], qp);
   }
 
   // ---- availability (no tiles: TS == RS) ----
@@ -347,10 +354,10 @@ struct Parser {
     if (ctb_y > 0 && !merge_left && slice_addr_of_ctb(ctb_rs - p.ctbs_w) == slice().slice_addr_rs) merge_up = cb.bin(t, ctx[CX_SAO_MERGE]);
     if (merge_left || merge_up) {
       const hc_ctu& src = p.ctus[merge_left ? ctb_rs - 1 : ctb_rs - p.ctbs_w];
-      for (int c = 0; c < 3; c++) {
+      K0_LOOP for (int c = 0; c < 3; c++) {
         ctu.sao_type[c] = src.sao_type[c];
         ctu.sao_band_or_class[c] = src.sao_band_or_class[c];
-        for (int i = 0; i < 4; i++) ctu.sao_offset[c][i] = src.sao_offset[c][i];
+        K0_LOOP for (int i = 0; i < 4; i++) ctu.sao_offset[c][i] = src.sao_offset[c][i];
       }
       if (!slice().sao_luma) ctu.sao_type[0] = 0;
       if (!slice().sao_chroma) ctu.sao_type[1] = ctu.sao_type[2] = 0;
@@ -358,7 +365,7 @@ struct Parser {
       return;
     }
     const int ncomp = p.chroma_array_type != 0 ? 3 : 1;
-    for (int c = 0; c < ncomp; c++) {
+    K0_LOOP for (int c = 0; c < ncomp; c++) {
       if (!((slice().sao_luma && c == 0) || (slice().sao_chroma && c > 0))) { ctu.sao_type[c] = 0; continue; }
       if (c < 2) {
         int ty = 0;
@@ -371,18 +378,18 @@ struct Parser {
       const int bitDepth = c == 0 ? p.bit_depth_y : p.bit_depth_c;
       const int cMax = (1 << ((bitDepth < 10 ? bitDepth : 10) - 5)) - 1;
       int absv[4];
-      for (int i = 0; i < 4; i++) {
+      K0_LOOP for (int i = 0; i < 4; i++) {
         int v = 0;
-        while (v < cMax && cb.bypass()) v++;
+        K0_LOOP while (v < cMax && cb.bypass()) v++;
         absv[i] = v;
       }
       const int scale = c == 0 ? p.log2_sao_offset_scale_luma : p.log2_sao_offset_scale_chroma;
       if (ctu.sao_type[c] == 1) {
         int sign[4] = {0, 0, 0, 0};
-        for (int i = 0; i < 4; i++)
+        K0_LOOP for (int i = 0; i < 4; i++)
           if (absv[i]) sign[i] = cb.bypass();
         ctu.sao_band_or_class[c] = (uint8_t)cb.bypass_bits(5);
-        for (int i = 0; i < 4; i++) ctu.sao_offset[c][i] = (int8_t)((sign[i] ? -absv[i] : absv[i]) * (1 << scale));
+        K0_LOOP for (int i = 0; i < 4; i++) ctu.sao_offset[c][i] = (int8_t)((sign[i] ? -absv[i] : absv[i]) * (1 << scale));
       } else {
         if (c < 2) ctu.sao_band_or_class[c] = (uint8_t)cb.bypass_bits(2);
         else ctu.sao_band_or_class[2] = ctu.sao_band_or_class[1];
@@ -426,7 +433,7 @@ struct Parser {
     qPCbPrime = qPCb + p.qp_bd_offset_c < 0 ? 0 : qPCb + p.qp_bd_offset_c;
     qPCrPrime = qPCr + p.qp_bd_offset_c < 0 ? 0 : qPCr + p.qp_bd_offset_c;
     const int n8 = ((1 << cu_log2) >> 3) < 1 ? 1 : ((1 << cu_log2) >> 3);
-    for (int y = 0; y < n8; y++)
+    K0_LOOP for (int y = 0; y < n8; y++)
       for (int x = 0; x < n8; x++) {
         const int xx = (cu_x0 >> 3) + x, yy = (cu_y0 >> 3) + y;
         if (xx < p.w8 && yy < p.h8) p.qp_map[xx + yy * p.w8] = (int8_t)QPY;
@@ -443,10 +450,12 @@ struct Parser {
     uint8_t* e = p.edge_map + (x0 >> 2) + (y0 >> 2) * p.w4;
     const uint8_t fl = left ? HC_EDGE_V : 0, ft = top ? HC_EDGE_H : 0;
     if (fl | ft) e[0] = (uint8_t)(fl | ft);
-    if (left)
-      for (int k = 1; k < n4; k++) e[k * p.w4] = HC_EDGE_V;
-    if (top)
-      for (int k = 1; k < n4; k++) e[k] = HC_EDGE_H;
+    if (left) {
+      K0_LOOP for (int k = 1; k < n4; k++) e[k * p.w4] = HC_EDGE_V;
+    }
+    if (top) {
+      K0_LOOP for (int k = 1; k < n4; k++) e[k] = HC_EDGE_H;
+    }
   }
 
   // neighbour availability of one prediction block (intrapred.h:443-543, :838-940)
@@ -475,18 +484,19 @@ struct Parser {
     if (nRight > 2 * nT) nRight = 2 * nT;
     const int currAddr = zs_addr(xBL, yBL);
     unsigned left = 0, top = 0;
-    if (aL)
-      for (int y = nBottom - 1; y >= 0; y -= 4)
+    if (aL) {
+      K0_LOOP for (int y = nBottom - 1; y >= 0; y -= 4)
         if (zs_addr((xB - 1) * SubW, (yB + y) * SubH) <= currAddr) left |= 1u << (y >> 2);
+    }
     bool tl = false;
     if (aTL) tl = zs_addr((xB - 1) * SubW, (yB - 1) * SubH) <= currAddr;
-    for (int x = 0; x < nRight; x += 4) {
+    K0_LOOP for (int x = 0; x < nRight; x += 4) {
       const bool ba = x < nT ? aT : aTR;
       if (ba && zs_addr((xB + x) * SubW, (yB - 1) * SubH) <= currAddr) top |= 1u << (x >> 2);
     }
     if (nblk[cIdx] >= p.blk_cap[cIdx]) { fail(ERR_CAPACITY); return; }
     uint32_t base = (uint32_t)ctb_rs * p.blk_cap_ctb;
-    for (int c = 0; c < cIdx; c++) base += p.blk_cap[c];
+    K0_LOOP for (int c = 0; c < cIdx; c++) base += p.blk_cap[c];
     hc_blk b;
     b.x = (uint16_t)xB;
     b.y = (uint16_t)yB;
@@ -519,10 +529,10 @@ struct Parser {
       int offset, shift;
       if (cIdx == 0) { offset = 3 * (log2 - 2) + ((log2 - 1) >> 2); shift = (log2 + 1) >> 2; }
       else { offset = 15; shift = log2 - 2; }
-      for (int d = 0; d < 2; d++) {
+      K0_LOOP for (int d = 0; d < 2; d++) {
         int v = 0;
         const int base = (d ? CX_LAST_Y : CX_LAST_X) + offset;
-        while (v < cMax && cb.bin(t, ctx[base + (v >> shift)])) v++;
+        K0_LOOP while (v < cMax && cb.bin(t, ctx[base + (v >> shift)])) v++;
         last[d] = v;
       }
     }
@@ -575,7 +585,7 @@ struct Parser {
     const int ts_c = chroma ? 43 : 42;
     const int sig_size = log2 == 3 ? (scanIdx == 0 ? 0 : 1) : 2;
 
-    for (int i = lastSubBlock; i >= 0; i--) {
+    K0_LOOP for (int i = lastSubBlock; i >= 0; i--) {
       const int sxy = scanSub[i];
       const int Sx = sxy & 7, Sy = sxy >> 3;
       const int prevCsbf = (int)((csbf_right >> sxy) & 1) | ((int)((csbf_below >> sxy) & 1) << 1);
@@ -598,12 +608,12 @@ struct Parser {
       const int last_coeff = (i == lastSubBlock) ? lastScanPos - 1 : 15;
       if (i == lastSubBlock) { spos = (unsigned long long)lastScanPos; n = 1; }
       if (ts_ctx) {
-        for (int k = last_coeff; k > 0; k--) {
+        K0_LOOP for (int k = last_coeff; k > 0; k--) {
           const int b = cb.bin(t, ctx[CX_SIG + ts_c]);
           if (b) { spos |= (unsigned long long)k << (4 * n); n++; }
         }
       } else {
-        for (int k = last_coeff; k > 0; k--) {
+        K0_LOOP for (int k = last_coeff; k > 0; k--) {
           const int b = cb.bin(t, ctx[CX_SIG + sigtab[k]]);
           if (b) { spos |= (unsigned long long)k << (4 * n); n++; }
         }
@@ -621,7 +631,7 @@ struct Parser {
       const int ng1 = n < 8 ? n : 8;
       const int g1base = CX_G1 + ctxSet * 4 + (cIdx > 0 ? 16 : 0);
       uint32_t g1mask = 0;              // coefficient c has abs level >= 2
-      for (int c = 0; c < ng1; c++) {
+      K0_LOOP for (int c = 0; c < ng1; c++) {
         const int b = cb.bin(t, ctx[g1base + c1]);
         g1mask |= (uint32_t)b << c;
         if (b && c < firstG1) firstG1 = c;
@@ -643,7 +653,7 @@ struct Parser {
 
       if (ncoeff_total + (uint32_t)n > coeff_room) { fail(ERR_CAPACITY); return 0; }
       int sumAbs = 0, rice = 0;
-      for (int c = 0; c < n; c++) {
+      K0_LOOP for (int c = 0; c < n; c++) {
         const int base = 1 + (int)((g1mask >> c) & 1) + ((c == firstG1) ? g2 : 0);
         int rem = 0;
         if ((escmask >> c) & 1) {
@@ -658,7 +668,7 @@ struct Parser {
             cb.consume(len, bins);
           } else {
             int prefix = 0;
-            while (prefix < 32 && cb.bypass()) prefix++;
+            K0_LOOP while (prefix < 32 && cb.bypass()) prefix++;
             if (prefix >= 32) { fail(ERR_BITSTREAM); return 0; }
             if (prefix <= 3) rem = (prefix << rice) + (int)cb.bypass_bits(rice);
             else rem = (((1 << (prefix - 3)) + 3 - 1) << rice) + (int)cb.bypass_bits(prefix - 3 + rice);
@@ -699,10 +709,10 @@ struct Parser {
       int v = 0;
       if (bin(CX_CU_QP_DELTA)) {
         v = 1;
-        while (v < 5 && bin(CX_CU_QP_DELTA + 1)) v++;
+        K0_LOOP while (v < 5 && bin(CX_CU_QP_DELTA + 1)) v++;
         if (v == 5) {
           int k = 0;
-          while (k < 32 && cabac.bypass()) k++;
+          K0_LOOP while (k < 32 && cabac.bypass()) k++;
           if (k >= 32) { fail(ERR_BITSTREAM); return; }
           v += ((1 << k) - 1) + (int)cabac.bypass_bits(k);
         }
@@ -726,10 +736,10 @@ struct Parser {
     if (!own && blkIdx != 3) return;
     const int bx = own ? x0 : xBase, by = own ? y0 : yBase;
     const int l2 = own ? log2C : 2, nTC = 1 << l2;
-    for (int c = 1; c <= 2; c++) {
+    K0_LOOP for (int c = 1; c <= 2; c++) {
       const int cbf = c == 1 ? cbf_cb : cbf_cr;
       const int nblk2 = cat == 2 ? 2 : 1;
-      for (int t = 0; t < nblk2; t++) {
+      K0_LOOP for (int t = 0; t < nblk2; t++) {
         const int xB = bx / SubW, yB = by / SubH + t * nTC;
         const int lx = xB * SubW, ly = yB * SubH;   // mode lookup position of the reference (slice.cc:3760-3763)
         const int m = p.ipm_c[((lx < p.W - 1 ? lx : p.W - 1) >> 2) + ((ly < p.H - 1 ? ly : p.H - 1) >> 2) * p.w4];
@@ -742,29 +752,44 @@ struct Parser {
     }
   }
 
-  // ---- 7.3.8.8 transform_tree: compile-time recursion over the block size ----
+  // ---- 7.3.8.8 transform_tree: the flags are read by one size-independent function, the compile-time recursion
+  // over the block size is a thin shell around it (code size: the parser is instruction-fetch bound) ----
+  // returns split | cbf_cb << 1 | cbf_cr << 3 | cbf_luma << 5
+  K0_FN int transform_tree_flags(int log2, int depth, int max_depth, int intra_split, int parent_cbf_cb, int parent_cbf_cr) {
+    const Pic& p = pic();
+    const Tables& t = tab();
+    uint8_t* const ctx = ctxs();
+    Cabac cb = cabac;
+    int split;
+    if (log2 <= p.log2_max_tb && log2 > p.log2_min_tb && depth < max_depth && !(intra_split && depth == 0)) split = cb.bin(t, ctx[CX_SPLIT_TRANSFORM + 5 - log2]);
+    else split = (log2 > p.log2_max_tb || (intra_split && depth == 0)) ? 1 : 0;
+    int cbf_cb = -1, cbf_cr = -1;
+    if ((log2 > 2 && p.chroma_array_type != 0) || p.chroma_array_type == 3) {
+      const bool second = p.chroma_array_type == 2 && (!split || log2 == 3);
+      if (parent_cbf_cb) {
+        cbf_cb = cb.bin(t, ctx[CX_CBF_CHROMA + depth]);
+        if (second) cbf_cb |= cb.bin(t, ctx[CX_CBF_CHROMA + depth]) << 1;
+      }
+      if (parent_cbf_cr) {
+        cbf_cr = cb.bin(t, ctx[CX_CBF_CHROMA + depth]);
+        if (second) cbf_cr |= cb.bin(t, ctx[CX_CBF_CHROMA + depth]) << 1;
+      }
+    }
+    if (cbf_cb < 0) cbf_cb = (depth > 0 && log2 == 2) ? parent_cbf_cb : 0;
+    if (cbf_cr < 0) cbf_cr = (depth > 0 && log2 == 2) ? parent_cbf_cr : 0;
+    int cbf_luma = 0;
+    if (!split) cbf_luma = cb.bin(t, ctx[CX_CBF_LUMA + (depth == 0 ? 1 : 0)]);
+    cabac = cb;
+    return split | (cbf_cb << 1) | (cbf_cr << 3) | (cbf_luma << 5);
+  }
+
   template <int LOG2>
   K0_FN void transform_tree(int x0, int y0, int xBase, int yBase, int depth, int blkIdx, int max_depth, int intra_split,
                             int parent_cbf_cb, int parent_cbf_cr) {
-    const Pic& p = pic();
-    if (err || cabac.overrun()) { fail(ERR_BITSTREAM); return; }
-    int split;
-    if (LOG2 <= p.log2_max_tb && LOG2 > p.log2_min_tb && depth < max_depth && !(intra_split && depth == 0)) split = bin(CX_SPLIT_TRANSFORM + 5 - LOG2);
-    else split = (LOG2 > p.log2_max_tb || (intra_split && depth == 0)) ? 1 : 0;
-    int cbf_cb = -1, cbf_cr = -1;
-    if ((LOG2 > 2 && p.chroma_array_type != 0) || p.chroma_array_type == 3) {
-      if (parent_cbf_cb) {
-        cbf_cb = bin(CX_CBF_CHROMA + depth);
-        if (p.chroma_array_type == 2 && (!split || LOG2 == 3)) cbf_cb |= bin(CX_CBF_CHROMA + depth) << 1;
-      }
-      if (parent_cbf_cr) {
-        cbf_cr = bin(CX_CBF_CHROMA + depth);
-        if (p.chroma_array_type == 2 && (!split || LOG2 == 3)) cbf_cr |= bin(CX_CBF_CHROMA + depth) << 1;
-      }
-    }
-    if (cbf_cb < 0) cbf_cb = (depth > 0 && LOG2 == 2) ? parent_cbf_cb : 0;
-    if (cbf_cr < 0) cbf_cr = (depth > 0 && LOG2 == 2) ? parent_cbf_cr : 0;
-    if (split) {
+    if (err) return;
+    const int f = transform_tree_flags(LOG2, depth, max_depth, intra_split, parent_cbf_cb, parent_cbf_cr);
+    const int cbf_cb = (f >> 1) & 3, cbf_cr = (f >> 3) & 3;
+    if (f & 1) {
       if (LOG2 > 2) {
         constexpr int L = LOG2 > 2 ? LOG2 - 1 : 2;
         constexpr int h = 1 << L;
@@ -776,20 +801,19 @@ struct Parser {
         fail(ERR_BITSTREAM);
       }
     } else {
-      const int cbf_luma = bin(CX_CBF_LUMA + (depth == 0 ? 1 : 0));
-      transform_unit(x0, y0, xBase, yBase, LOG2, blkIdx, cbf_luma, cbf_cb, cbf_cr);
+      transform_unit(x0, y0, xBase, yBase, LOG2, blkIdx, (f >> 5) & 1, cbf_cb, cbf_cr);
     }
   }
 
   // ---- 7.3.8.5 coding_unit (I slices) ----
-  template <int LOG2>
-  K0_FN void coding_unit(int x0, int y0, int depth) {
+  // size-independent part: everything up to the transform tree; returns max transform depth | intra_split << 4
+  K0_FN int coding_unit_modes(int LOG2, int x0, int y0, int depth) {
     const Pic& p = pic();
-    constexpr int nCbS = 1 << LOG2;
+    const int nCbS = 1 << LOG2;
     cu_x0 = x0; cu_y0 = y0; cu_log2 = LOG2;
     {
-      constexpr int n8 = nCbS >> 3;
-      for (int y = 0; y < n8; y++)
+      const int n8 = nCbS >> 3;
+      K0_LOOP for (int y = 0; y < n8; y++)
         for (int x = 0; x < n8; x++) p.ct_depth[((x0 >> 3) + x) + ((y0 >> 3) + y) * p.w8] = (uint8_t)depth;
     }
     // deblocking: which CU edges may be filtered (deblock.cc:165-215)
@@ -808,17 +832,17 @@ struct Parser {
     bool nxn = false;
     if (LOG2 == p.log2_min_cb) {
       nxn = !cb.bin(t, ctx[CX_PART_MODE]);
-      if (nxn && LOG2 <= p.log2_min_tb) { fail(ERR_BITSTREAM); return; }
+      if (nxn && LOG2 <= p.log2_min_tb) { fail(ERR_BITSTREAM); return 0; }
     }
     // ---- intra prediction modes ----
     const int pbOffset = nxn ? nCbS / 2 : nCbS;
     const int nparts = nxn ? 4 : 1;
     int prev_flag[4], mpm_idx[4] = {0, 0, 0, 0}, rem[4] = {0, 0, 0, 0};
-    for (int i = 0; i < nparts; i++) prev_flag[i] = cb.bin(t, ctx[CX_PREV_INTRA_LUMA]);
-    for (int i = 0; i < nparts; i++) {
+    K0_LOOP for (int i = 0; i < nparts; i++) prev_flag[i] = cb.bin(t, ctx[CX_PREV_INTRA_LUMA]);
+    K0_LOOP for (int i = 0; i < nparts; i++) {
       if (prev_flag[i]) {
         int v = 0;
-        while (v < 2 && cb.bypass()) v++;
+        K0_LOOP while (v < 2 && cb.bypass()) v++;
         mpm_idx[i] = v;
       } else {
         rem[i] = (int)cb.bypass_bits(5);
@@ -826,7 +850,7 @@ struct Parser {
     }
     const bool availA0 = ctb_available(x0, y0, x0 - 1, y0), availB0 = ctb_available(x0, y0, x0, y0 - 1);
     int luma_modes[4];
-    for (int idx = 0; idx < nparts; idx++) {
+    K0_LOOP for (int idx = 0; idx < nparts; idx++) {
       const int i = (idx & 1) * pbOffset, j = (idx >> 1) * pbOffset;
       const int x = x0 + i, y = y0 + j;
       const bool availA = availA0 || i > 0, availB = availB0 || j > 0;
@@ -852,18 +876,18 @@ struct Parser {
         if (cand[0] > cand[2]) { t = cand[0]; cand[0] = cand[2]; cand[2] = t; }
         if (cand[1] > cand[2]) { t = cand[1]; cand[1] = cand[2]; cand[2] = t; }
         mode = rem[idx];
-        for (int n = 0; n < 3; n++)
+        K0_LOOP for (int n = 0; n < 3; n++)
           if (mode >= cand[n]) mode++;
       }
       luma_modes[idx] = mode;
       const int n4 = pbOffset >> 2;
-      for (int yy = 0; yy < n4; yy++)
+      K0_LOOP for (int yy = 0; yy < n4; yy++)
         for (int xx = 0; xx < n4; xx++) p.ipm[((x >> 2) + xx) + ((y >> 2) + yy) * p.w4] = (uint8_t)mode;
     }
     const int cat = p.chroma_array_type;
     if (cat != 0) {
       const int nchroma = cat == 3 ? nparts : 1;
-      for (int idx = 0; idx < nchroma; idx++) {
+      K0_LOOP for (int idx = 0; idx < nchroma; idx++) {
         int icpm = 4;
         if (cb.bin(t, ctx[CX_INTRA_CHROMA])) icpm = (int)cb.bypass_bits(2);
         const int luma = luma_modes[idx];
@@ -875,33 +899,44 @@ struct Parser {
         if (cat == 2) m = tab().mode422[m];
         const int i = cat == 3 ? (idx & 1) * pbOffset : 0, j = cat == 3 ? (idx >> 1) * pbOffset : 0;
         const int n4 = (cat == 3 ? pbOffset : nCbS) >> 2;
-        for (int yy = 0; yy < n4; yy++)
+        K0_LOOP for (int yy = 0; yy < n4; yy++)
           for (int xx = 0; xx < n4; xx++) p.ipm_c[(((x0 + i) >> 2) + xx) + (((y0 + j) >> 2) + yy) * p.w4] = (uint8_t)m;
       }
     }
     cabac = cb;
-    const int max_depth = p.max_th_depth_intra + (nxn ? 1 : 0);
-    transform_tree<LOG2>(x0, y0, x0, y0, 0, 0, max_depth, nxn ? 1 : 0, 1, 1);
+    return (p.max_th_depth_intra + (nxn ? 1 : 0)) | (nxn ? 16 : 0);
+  }
+
+  template <int LOG2>
+  HC_HD void coding_unit(int x0, int y0, int depth) {
+    const int r = coding_unit_modes(LOG2, x0, y0, depth);
+    if (err) return;
+    transform_tree<LOG2>(x0, y0, x0, y0, 0, 0, r & 15, r >> 4, 1, 1);
   }
 
   // ---- 7.3.8.4 coding_quadtree ----
-  template <int LOG2>
-  K0_FN void coding_quadtree(int x0, int y0, int depth) {
+  K0_FN int coding_quadtree_split(int log2, int x0, int y0, int depth) {
     const Pic& p = pic();
-    if (err || cabac.overrun()) { fail(ERR_BITSTREAM); return; }
-    constexpr int size = 1 << LOG2;
-    bool split;
-    if (x0 + size <= p.W && y0 + size <= p.H && LOG2 > p.log2_min_cb) {
+    const int size = 1 << log2;
+    int split;
+    if (x0 + size <= p.W && y0 + size <= p.H && log2 > p.log2_min_cb) {
       int condL = 0, condA = 0;
       if (ctb_available(x0, y0, x0 - 1, y0) && p.ct_depth[((x0 - 1) >> 3) + (y0 >> 3) * p.w8] > depth) condL = 1;
       if (ctb_available(x0, y0, x0, y0 - 1) && p.ct_depth[(x0 >> 3) + ((y0 - 1) >> 3) * p.w8] > depth) condA = 1;
       split = bin(CX_SPLIT_CU + condL + condA);
     } else {
-      split = LOG2 > p.log2_min_cb;
+      split = log2 > p.log2_min_cb;
     }
-    if (p.cu_qp_delta_enabled && LOG2 >= p.log2_min_cu_qp_delta_size) { IsCuQpDeltaCoded = false; CuQpDeltaVal = 0; }
-    if (split) {
+    if (p.cu_qp_delta_enabled && log2 >= p.log2_min_cu_qp_delta_size) { IsCuQpDeltaCoded = false; CuQpDeltaVal = 0; }
+    return split;
+  }
+
+  template <int LOG2>
+  K0_FN void coding_quadtree(int x0, int y0, int depth) {
+    if (err || cabac.overrun()) { fail(ERR_BITSTREAM); return; }
+    if (coding_quadtree_split(LOG2, x0, y0, depth)) {
       if (LOG2 > 3) {
+        const Pic& p = pic();
         constexpr int L = LOG2 > 3 ? LOG2 - 1 : 3;
         constexpr int h = 1 << L;
         const int x1 = x0 + h, y1 = y0 + h;
@@ -923,7 +958,7 @@ struct Parser {
     hc_ctu& ctu = p.ctus[ctb_rs];
     nblk[0] = nblk[1] = nblk[2] = 0;
     ntb = ncoeff = nresid = 0;
-    for (int c = 0; c < 3; c++) { ctu.sao_type[c] = 0; ctu.sao_band_or_class[c] = 0; for (int i = 0; i < 4; i++) ctu.sao_offset[c][i] = 0; }
+    K0_LOOP for (int c = 0; c < 3; c++) { ctu.sao_type[c] = 0; ctu.sao_band_or_class[c] = 0; for (int i = 0; i < 4; i++) ctu.sao_offset[c][i] = 0; }
     if (slice().sao_luma || slice().sao_chroma) read_sao(ctu);
     const int x0 = ctb_x << p.log2_ctb, y0 = ctb_y << p.log2_ctb;
     if (p.log2_ctb == 6) coding_quadtree<6>(x0, y0, 0);
@@ -935,18 +970,18 @@ struct Parser {
       const uint8_t* ts = scratch().tb_size;
       const uint32_t tb0 = p.tb_global_base + (uint32_t)ctb_rs * p.tb_cap_ctb;
       unsigned long long packed = 0;   // four 16-bit counters
-      for (uint32_t t = 0; t < ntb; t++) packed += 1ull << (16 * ts[t]);
-      for (int l = 0; l < 4; l++) {
+      K0_LOOP for (uint32_t t = 0; t < ntb; t++) packed += 1ull << (16 * ts[t]);
+      K0_LOOP for (int l = 0; l < 4; l++) {
         const unsigned n = (unsigned)(packed >> (16 * l)) & 0xffffu;
         if (!n) continue;
         unsigned slot = list_reserve(p.tb_counts + l, n);
         uint32_t* dst = p.tb_lists[l];
-        for (uint32_t t = 0; t < ntb; t++)
+        K0_LOOP for (uint32_t t = 0; t < ntb; t++)
           if (ts[t] == l) dst[slot++] = tb0 + t;
       }
     }
     uint32_t base = (uint32_t)ctb_rs * p.blk_cap_ctb;
-    for (int c = 0; c < 3; c++) {
+    K0_LOOP for (int c = 0; c < 3; c++) {
       ctu.blk_first[c] = base;
       ctu.blk_count[c] = (uint16_t)nblk[c];
       base += p.blk_cap[c];
@@ -965,7 +1000,7 @@ struct Parser {
     err = ERR_NONE;
     uint32_t loaded_pic = 0xffffffffu;
     uint8_t* const ctx = ctxs();
-    for (uint32_t s = 0; s < nsubs && !err; s++) {
+    K0_LOOP for (uint32_t s = 0; s < nsubs && !err; s++) {
       const Sub sub = subs[first_sub + s];
       if (sub.pic != loaded_pic) { scratch().pic = pics[sub.pic]; loaded_pic = sub.pic; }
       const Pic& p = pic();
@@ -994,17 +1029,17 @@ struct Parser {
 
       ctb_x = ctb_rs % p.ctbs_w;
       ctb_y = ctb_rs / p.ctbs_w;
-      while (ctb_rs < sub.end_ctb && !err) {
+      K0_LOOP while (ctb_rs < sub.end_ctb && !err) {
         if (row_chain && ctb_y > 0) {
           // wavefront: the row above must be two CTBs ahead (its context table, split depths and SAO parameters)
           const int need = ctb_x + 2 < p.ctbs_w ? ctb_x + 2 : p.ctbs_w;
-          while (progress_load(p.progress + ctb_y - 1) < need) backoff();
+          K0_LOOP while (progress_load(p.progress + ctb_y - 1) < need) backoff();
         }
         if (p.entropy_coding_sync && ctb_x == 0 && ctb_y >= 1 && !(first_of_independent && ctb_rs == slice().segment_address)) {
           if (p.ctbs_w > 1) {
             const uint32_t* src = reinterpret_cast<const uint32_t*>(p.wpp_ctx + (size_t)(ctb_y - 1) * CTX_BYTES);
             uint32_t* dst = reinterpret_cast<uint32_t*>(ctx);
-            for (int i = 0; i < CTX_BYTES / 4; i++) dst[i] = src[i];
+            K0_LOOP for (int i = 0; i < CTX_BYTES / 4; i++) dst[i] = src[i];
           } else {
             init_contexts();
           }
@@ -1015,7 +1050,7 @@ struct Parser {
         if (p.entropy_coding_sync && ctb_x == 1 && ctb_y < p.ctbs_h - 1) {
           uint32_t* dst = reinterpret_cast<uint32_t*>(p.wpp_ctx + (size_t)ctb_y * CTX_BYTES);
           const uint32_t* src = reinterpret_cast<const uint32_t*>(ctx);
-          for (int i = 0; i < CTX_BYTES / 4; i++) dst[i] = src[i];
+          K0_LOOP for (int i = 0; i < CTX_BYTES / 4; i++) dst[i] = src[i];
         }
         if (row_chain) progress_store(p.progress + ctb_y, ctb_x + 1);
         const int end_of_slice_segment = cabac.terminate();
@@ -1038,7 +1073,7 @@ struct Parser {
       // unblock every waiter of this picture, then report
       if (loaded_pic == 0xffffffffu) scratch().pic = pics[subs[first_sub].pic];
       const Pic& p = pic();
-      for (int r = 0; r < p.ctbs_h; r++) progress_store(p.progress + r, 1 << 30);
+      K0_LOOP for (int r = 0; r < p.ctbs_h; r++) progress_store(p.progress + r, 1 << 30);
       *p.error = err;
     }
   }
