@@ -48,6 +48,7 @@ struct hc_engine {
   std::vector<cudaStream_t> free_streams;
   hc::k0::Tables* d_k0_tables = nullptr;   // read-only tables of the device parser
   int device_parse = 1;                    // hc_heic_job: let K0 parse every picture it accepts
+  int sm_count = 148;
 
   Block take(std::vector<Block>& list, size_t size, bool pinned) {
     std::lock_guard<std::mutex> lk(mu);
@@ -130,6 +131,8 @@ struct hc_batch {
   size_t k0_status_off = 0;                        // [int error per K0 picture][4 list counters]
   const uint32_t* d_k0_tb_index[4] = {nullptr, nullptr, nullptr, nullptr};
   int k0_tb_counts[4] = {0, 0, 0, 0};
+  long long k0_list_cap[4] = {0, 0, 0, 0};
+  bool k0_status_pending = false;                  // K0 ran; its status words were copied to h_status but not looked at yet
   std::vector<int> k0_pic_of;                      // K0 picture -> batch picture index
   Block h_status;
   cudaEvent_t ev_k0[2] = {};
@@ -183,6 +186,7 @@ hc_engine* hc_engine_create(int device) {
   hc_engine* eng = new (std::nothrow) hc_engine;
   if (!eng) return nullptr;
   eng->device = device;
+  cudaDeviceGetAttribute(&eng->sm_count, cudaDevAttrMultiProcessorCount, device);
   if (const char* m = getenv("HEIFCUDA_PARSER")) eng->device_parse = strcmp(m, "host") != 0;
   if (!cuda_ok(cudaMalloc(&eng->d_k0_tables, sizeof(hc::k0::Tables)), "cudaMalloc(K0 tables)") ||
       !cuda_ok(cudaMemcpy(eng->d_k0_tables, &hc::k0_tables(), sizeof(hc::k0::Tables), cudaMemcpyHostToDevice), "cudaMemcpy(K0 tables)")) {
@@ -511,9 +515,10 @@ int hc_batch_upload(hc_batch* b) {
     b->d_k0_pics = (const hc::k0::Pic*)(Dk + o_kpics);
     b->d_k0_subs = (const hc::k0::Sub*)(Dk + o_ksubs);
     b->d_k0_chains = (const hc::k0::Chain*)(Dk + o_kchains);
-    for (int l = 0; l < 4; l++) b->d_k0_tb_index[l] = (const uint32_t*)(Dk + z_lists[l]);
+    for (int l = 0; l < 4; l++) { b->d_k0_tb_index[l] = (const uint32_t*)(Dk + z_lists[l]); b->k0_list_cap[l] = (long long)list_cap[l]; }
   }
   b->k0_done = false;
+  b->k0_status_pending = false;
 
   // ---- pack: every picture's records go to disjoint slices of the pinned arena, in parallel ----
   memcpy(H + o_pics, b->hpics.data(), sizeof(hc_pic) * np);
@@ -609,7 +614,30 @@ int hc_batch_upload(hc_batch* b) {
   return HC_OK;
 }
 
-int hc_batch_reconstruct(hc_batch* b, int stages) {
+// Looks at the status words K0 left in pinned memory. The stream must have been synchronised.
+static int k0_check_status(hc_batch* b) {
+  if (!b->k0_status_pending) return HC_OK;
+  b->k0_status_pending = false;
+  const int* status = (const int*)b->h_status.p;
+  for (int l = 0; l < 4; l++) { b->k0_tb_counts[l] = status[b->nk0 + l]; b->launches += b->k0_tb_counts[l] > 0; }
+  for (int q = 0; q < b->nk0; q++)
+    if (status[q]) {
+      hc::set_last_error("picture " + std::to_string(b->k0_pic_of[q]) + (status[q] == hc::k0::ERR_CAPACITY ? ": device parser capacity exceeded"
+                                                                                                           : ": malformed slice data (device parser)"));
+      return HC_ERR_BITSTREAM;
+    }
+  return HC_OK;
+}
+
+// Synchronises the stream and reports a K0 parse error of the batch, if any.
+static int batch_sync_checked(hc_batch* b, const char* what) {
+  if (!cuda_ok(cudaStreamSynchronize(b->stream), what)) return HC_ERR_CUDA;
+  return k0_check_status(b);
+}
+
+// Enqueues K0 (first run only) and K1..K4 without waiting for anything: the K1 launch lists K0 builds are consumed
+// through their device-side counters. A K0 parse error surfaces at the next synchronising call.
+int hc_batch_reconstruct_async(hc_batch* b, int stages) {
   if (!b || !b->uploaded) { hc::set_last_error("hc_batch_reconstruct: batch not uploaded"); return HC_ERR_ARGUMENT; }
   if (!cuda_ok(cudaSetDevice(b->eng->device), "cudaSetDevice")) return HC_ERR_CUDA;
   cudaStream_t s = b->stream;
@@ -617,37 +645,29 @@ int hc_batch_reconstruct(hc_batch* b, int stages) {
   for (auto& p : b->csc_events) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
   b->csc_events.clear();
   cudaMemsetAsync(b->d_progress.p, 0, std::max<size_t>((size_t)b->ntasks * sizeof(int), 4), s);
+  uint8_t* D = (uint8_t*)b->d_arena.p;
   if (b->nk0 && !b->k0_done) {
     // K0: the slice data of the pictures added as bitstreams is parsed on the device, straight into their record
     // regions; afterwards the records stay resident (a second hc_batch_reconstruct re-uses them)
-    uint8_t* D = (uint8_t*)b->d_arena.p;
     cudaEventRecord(b->ev_k0[0], s);
     cudaMemsetAsync(D + b->k0_ones_off, 1, b->k0_ones_bytes, s);
     cudaMemsetAsync(D + b->k0_zero_off, 0, b->k0_zero_bytes, s);
     hc::launch_k0(b->eng->d_k0_tables, b->d_k0_pics, b->d_k0_subs, b->d_k0_chains, b->nchains, s);
     cudaEventRecord(b->ev_k0[1], s);
     const size_t status_bytes = 4 * ((size_t)b->nk0 + 4);
-    if (!cuda_ok(cudaMemcpyAsync(b->h_status.p, D + b->k0_status_off, status_bytes, cudaMemcpyDeviceToHost, s), "cudaMemcpyAsync(K0 status)") ||
-        !cuda_ok(cudaStreamSynchronize(s), "K0 (device CABAC parse)"))
+    if (!cuda_ok(cudaMemcpyAsync(b->h_status.p, D + b->k0_status_off, status_bytes, cudaMemcpyDeviceToHost, s), "cudaMemcpyAsync(K0 status)"))
       return HC_ERR_CUDA;
-    const int* status = (const int*)b->h_status.p;
-    for (int q = 0; q < b->nk0; q++)
-      if (status[q]) {
-        hc::set_last_error("picture " + std::to_string(b->k0_pic_of[q]) + (status[q] == hc::k0::ERR_CAPACITY ? ": device parser capacity exceeded"
-                                                                                                             : ": malformed slice data (device parser)"));
-        return HC_ERR_BITSTREAM;
-      }
-    for (int l = 0; l < 4; l++) b->k0_tb_counts[l] = status[b->nk0 + l];
+    b->k0_status_pending = true;
     b->k0_done = true;
     b->launches += 1;
   }
   cudaEventRecord(b->ev[2], s);
   hc::launch_k1(b->view, b->d_tb_index, b->tb_counts, s);
   for (int l = 0; l < 4; l++) b->launches += b->tb_counts[l] > 0;
-  if (b->nk0) {
-    hc::launch_k1(b->view, b->d_k0_tb_index, b->k0_tb_counts, s);
-    for (int l = 0; l < 4; l++) b->launches += b->k0_tb_counts[l] > 0;
-  }
+  if (b->nk0 && !b->k0_status_pending)
+    for (int l = 0; l < 4; l++) b->launches += b->k0_tb_counts[l] > 0;   // counted by k0_check_status on the first run
+  if (b->nk0)
+    hc::launch_k1_indirect(b->view, b->d_k0_tb_index, b->k0_list_cap, (const unsigned*)(D + b->k0_status_off) + b->nk0, b->eng->sm_count, s);
   cudaEventRecord(b->ev[3], s);
   hc::launch_k2(b->view, b->d_tasks, b->ntasks, b->k2_smem, (int*)b->d_progress.p, s);
   b->launches += 1;
@@ -664,6 +684,14 @@ int hc_batch_reconstruct(hc_batch* b, int stages) {
   b->launches += 1;
   cudaEventRecord(b->ev[6], s);
   if (!cuda_ok(cudaGetLastError(), "kernel launch")) return HC_ERR_CUDA;
+  return HC_OK;
+}
+
+// Same, but a batch with device-parsed pictures waits for K0's verdict, so that malformed slice data is reported here.
+int hc_batch_reconstruct(hc_batch* b, int stages) {
+  const int rc = hc_batch_reconstruct_async(b, stages);
+  if (rc != HC_OK) return rc;
+  if (b->k0_status_pending) return batch_sync_checked(b, "K0 (device CABAC parse)");
   return HC_OK;
 }
 
@@ -723,8 +751,7 @@ int hc_batch_convert(hc_batch* b, int canvas, const hc_csc_params* params) {
 
 int hc_batch_sync(hc_batch* b) {
   if (!b) return HC_ERR_ARGUMENT;
-  if (!cuda_ok(cudaStreamSynchronize(b->stream), "cudaStreamSynchronize")) return HC_ERR_CUDA;
-  return HC_OK;
+  return batch_sync_checked(b, "cudaStreamSynchronize");
 }
 
 int hc_batch_read_plane(hc_batch* b, int canvas, int plane, void* dst, size_t dst_stride) {
@@ -742,7 +769,7 @@ int hc_batch_read_plane(hc_batch* b, int canvas, int plane, void* dst, size_t ds
                                     (size_t)c.pw[plane] * ps, c.ph[plane], cudaMemcpyDeviceToHost, b->stream);
   cudaEventRecord(e1, b->stream);
   if (!cuda_ok(e, "cudaMemcpy2DAsync(D2H plane)")) return HC_ERR_CUDA;
-  if (!cuda_ok(cudaStreamSynchronize(b->stream), "cudaStreamSynchronize")) return HC_ERR_CUDA;
+  if (int rc = batch_sync_checked(b, "cudaStreamSynchronize")) return rc;
   cudaEventElapsedTime(&b->last_d2h_ms, e0, e1);
   cudaEventDestroy(e0); cudaEventDestroy(e1);
   return HC_OK;
@@ -759,7 +786,7 @@ int hc_batch_read_rgb(hc_batch* b, int canvas, void* dst, size_t dst_stride) {
                                     cudaMemcpyDeviceToHost, b->stream);
   cudaEventRecord(e1, b->stream);
   if (!cuda_ok(e, "cudaMemcpy2DAsync(D2H rgb)")) return HC_ERR_CUDA;
-  if (!cuda_ok(cudaStreamSynchronize(b->stream), "cudaStreamSynchronize")) return HC_ERR_CUDA;
+  if (int rc = batch_sync_checked(b, "cudaStreamSynchronize")) return rc;
   cudaEventElapsedTime(&b->last_d2h_ms, e0, e1);
   cudaEventDestroy(e0); cudaEventDestroy(e1);
   return HC_OK;
@@ -772,7 +799,7 @@ int hc_batch_copy_rgb_device(hc_batch* b, int canvas, void* dst, size_t dst_stri
   cudaError_t e = cudaMemcpy2DAsync(dst, dst_stride, (const uint8_t*)b->d_rgb.p + c.rgb_off, c.rgb_stride, (size_t)c.w * c.rgb_bpp, c.h,
                                     cudaMemcpyDeviceToDevice, b->stream);
   if (!cuda_ok(e, "cudaMemcpy2DAsync(D2D rgb)")) return HC_ERR_CUDA;
-  return cuda_ok(cudaStreamSynchronize(b->stream), "cudaStreamSynchronize") ? HC_OK : HC_ERR_CUDA;
+  return batch_sync_checked(b, "cudaStreamSynchronize");
 }
 
 int hc_batch_read_rgb_async(hc_batch* b, int canvas, void* dst, size_t dst_stride) {
@@ -790,13 +817,12 @@ int hc_batch_read_residual(hc_batch* b, int pic, int16_t* dst, size_t count) {
   if (count > p.resid_count) count = p.resid_count;
   if (!cuda_ok(cudaMemcpyAsync(dst, (const int16_t*)b->d_resid.p + p.resid_base, count * 2, cudaMemcpyDeviceToHost, b->stream), "D2H residual"))
     return HC_ERR_CUDA;
-  if (!cuda_ok(cudaStreamSynchronize(b->stream), "cudaStreamSynchronize")) return HC_ERR_CUDA;
-  return HC_OK;
+  return batch_sync_checked(b, "cudaStreamSynchronize");
 }
 
 int hc_batch_stage_ms(hc_batch* b, float ms[8]) {
   if (!b || !ms) return HC_ERR_ARGUMENT;
-  if (!cuda_ok(cudaStreamSynchronize(b->stream), "cudaStreamSynchronize")) return HC_ERR_CUDA;
+  if (int rc = batch_sync_checked(b, "cudaStreamSynchronize")) return rc;
   for (int i = 0; i < 8; i++) ms[i] = 0.f;
   cudaEventElapsedTime(&ms[0], b->ev[0], b->ev[1]);
   for (int k = 0; k < 4; k++) cudaEventElapsedTime(&ms[1 + k], b->ev[2 + k], b->ev[3 + k]);

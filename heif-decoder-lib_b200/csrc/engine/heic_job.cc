@@ -8,6 +8,8 @@
 // (:2029-2078), the nclx precedence (:1844-1847) and convert_colorspace (colorconversion.cc:487).
 #include <atomic>
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
 #include <chrono>
 #include <future>
 #include <thread>
@@ -15,6 +17,10 @@
 #include "../capi/capi_internal.h"
 
 namespace {
+
+// HEIFCUDA_TRACE=1: per-batch phase times of the job / stream pipeline on stderr
+bool trace_on() { static const bool on = getenv("HEIFCUDA_TRACE") != nullptr; return on; }
+double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
 struct CodedItem {
   int file;
@@ -134,6 +140,7 @@ static hc_heic_job* job_create(hc_engine* e, int nfiles, const uint8_t* const* d
     }
   }
 
+  const double t_containers = now_s();
   // ---- serial CABAC parse of every coded item, in parallel across items ----
   int nthreads = threads > 0 ? threads : (int)std::thread::hardware_concurrency();
   if (nthreads < 1) nthreads = 1;
@@ -178,6 +185,7 @@ static hc_heic_job* job_create(hc_engine* e, int nfiles, const uint8_t* const* d
       return nullptr;
     }
   j->parse_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  const double t_parsed = now_s();
 
   // ---- batch placement ----
   j->batch = hc_batch_create(e);
@@ -235,6 +243,10 @@ static hc_heic_job* job_create(hc_engine* e, int nfiles, const uint8_t* const* d
     im.desc.has_alpha = has_alpha; im.desc.out_format = fmt; im.desc.bytes_per_pixel = bpp_of[fmt];
     im.desc.coded_pictures = (int)im.tiles.size() + (has_alpha ? 1 : 0);
   }
+  if (trace_on())
+    fprintf(stderr, "[heifcuda] job_create: %d files, %zu items: containers %.2f ms, parse/prepare %.2f ms (%d threads), placement %.2f ms\n", nfiles,
+            j->items.size(), (t_containers - std::chrono::duration<double>(t0.time_since_epoch()).count()) * 1e3, (t_parsed - t_containers) * 1e3, nthreads,
+            (now_s() - t_parsed) * 1e3);
   return j.release();
 }
 
@@ -271,7 +283,7 @@ int hc_heic_job_upload(hc_heic_job* j) { return j ? hc_batch_upload(j->batch) : 
 
 int hc_heic_job_run(hc_heic_job* j) {
   if (!j) return HC_ERR_ARGUMENT;
-  int rc = hc_batch_reconstruct(j->batch, HC_STAGE_ALL);
+  int rc = hc_batch_reconstruct_async(j->batch, HC_STAGE_ALL);   // K0 errors surface in hc_heic_job_sync / read
   if (rc != HC_OK) return rc;
   for (ImagePlan& im : j->images) {
     rc = hc_batch_convert(j->batch, im.canvas, &im.csc);
@@ -324,10 +336,68 @@ int hc_heic_decode_stream(hc_engine* e, int nfiles, const uint8_t* const* data, 
     return p;
   };
 
-  void* pinned = nullptr;
-  size_t pinned_cap = 0;
+  // stage 2 (this thread): submit — upload, [K0,] K1..K5 and the read-back into one of two pinned buffers are only
+  // ENQUEUED on the batch's stream; stage 3 (this thread, one batch behind): deliver — wait for the stream, hand the
+  // images out, release the batch. So the GPU parses / reconstructs batch b+1 while batch b is copied back and consumed.
+  struct InFlight { hc_heic_job* job = nullptr; int index = 0; int slot = 0; std::vector<size_t> offs; clock::time_point t0; };
+  void* pinned[2] = {nullptr, nullptr};
+  size_t pinned_cap[2] = {0, 0};
   int rc = HC_OK;
   std::string err;
+  auto submit = [&](hc_heic_job* j, int b, InFlight& f) -> int {
+    f.job = j; f.index = b; f.slot = b & 1; f.t0 = clock::now();
+    size_t need = 0;
+    f.offs.resize(j->images.size());
+    for (size_t i = 0; i < j->images.size(); i++) {
+      f.offs[i] = need;
+      need += ((size_t)j->images[i].desc.width * j->images[i].desc.bytes_per_pixel * j->images[i].desc.height + 255) & ~(size_t)255;
+    }
+    if (need > pinned_cap[f.slot]) {
+      if (pinned[f.slot]) hc_host_free(pinned[f.slot]);
+      pinned[f.slot] = hc_host_alloc(need + need / 8);
+      pinned_cap[f.slot] = pinned[f.slot] ? need + need / 8 : 0;
+    }
+    const double ta = now_s();
+    int r = pinned[f.slot] ? hc_heic_job_upload(j) : HC_ERR_MEMORY;
+    const double tb = now_s();
+    if (r == HC_OK) r = hc_heic_job_run(j);
+    for (size_t i = 0; r == HC_OK && i < j->images.size(); i++)
+      r = hc_batch_read_rgb_async(j->batch, j->images[i].canvas, (uint8_t*)pinned[f.slot] + f.offs[i],
+                                  (size_t)j->images[i].desc.width * j->images[i].desc.bytes_per_pixel);
+    if (trace_on()) fprintf(stderr, "[heifcuda] batch %d submit: pinned %.2f ms, upload %.2f ms, enqueue %.2f ms\n", b, (ta - std::chrono::duration<double>(f.t0.time_since_epoch()).count()) * 1e3, (tb - ta) * 1e3, (now_s() - tb) * 1e3);
+    return r;
+  };
+  auto deliver = [&](InFlight& f, int r) {
+    hc_heic_job* j = f.job;
+    const double ta = now_s();
+    if (r == HC_OK) r = hc_heic_job_sync(j);
+    const double tb = now_s();
+    double tc = tb;
+    if (r == HC_OK) {
+      float ms[8];
+      if (hc_heic_job_stage_ms(j, ms) == HC_OK) st.device_ms += ms[1] + ms[2] + ms[3] + ms[4] + ms[5] + ms[7];
+      st.bytes_h2d += hc_heic_job_upload_bytes(j);
+      st.launches += hc_heic_job_launch_count(j);
+      for (size_t i = 0; i < j->images.size(); i++) {
+        const hc_image_desc& d = j->images[i].desc;
+        st.bytes_d2h += (uint64_t)d.width * d.bytes_per_pixel * d.height;
+        st.pixels += (int64_t)d.width * d.height;
+        if (on_image) on_image(user, f.index * files_per_batch + (int)i, &d, (const uint8_t*)pinned[f.slot] + f.offs[i], (size_t)d.width * d.bytes_per_pixel);
+      }
+      tc = now_s();
+    } else if (rc == HC_OK) {
+      rc = r;
+      err = hc_last_error();
+    }
+    hc_heic_job_destroy(j);
+    if (trace_on()) fprintf(stderr, "[heifcuda] batch %d deliver: wait %.2f ms, callbacks %.2f ms, destroy %.2f ms\n", f.index, (tb - ta) * 1e3, (tc - tb) * 1e3, (now_s() - tc) * 1e3);
+    st.seconds_gpu_phase += secs(f.t0, clock::now());
+    st.batches++;
+    f.job = nullptr;
+  };
+
+  InFlight prev, cur_f;
+  int prev_rc = HC_OK;
   std::future<Parsed> ahead = std::async(std::launch::async, parse_batch, 0);
   for (int b = 0; b < nbatches; b++) {
     Parsed cur = ahead.get();
@@ -338,46 +408,14 @@ int hc_heic_decode_stream(hc_engine* e, int nfiles, const uint8_t* const* data, 
       continue;   // keep draining the pipeline
     }
     if (rc != HC_OK) { hc_heic_job_destroy(cur.job); continue; }
-    // stage 2 (this thread): upload, K1..K5, read-back into pinned memory, hand out
-    const auto t0 = clock::now();
-    hc_heic_job* j = cur.job;
-    size_t need = 0;
-    std::vector<size_t> offs(j->images.size());
-    for (size_t i = 0; i < j->images.size(); i++) {
-      offs[i] = need;
-      need += ((size_t)j->images[i].desc.width * j->images[i].desc.bytes_per_pixel * j->images[i].desc.height + 255) & ~(size_t)255;
-    }
-    if (need > pinned_cap) {
-      if (pinned) hc_host_free(pinned);
-      pinned = hc_host_alloc(need + need / 8);
-      pinned_cap = pinned ? need + need / 8 : 0;
-    }
-    int r = pinned ? hc_heic_job_upload(j) : HC_ERR_MEMORY;
-    if (r == HC_OK) r = hc_heic_job_run(j);
-    for (size_t i = 0; r == HC_OK && i < j->images.size(); i++)
-      r = hc_batch_read_rgb_async(j->batch, j->images[i].canvas, (uint8_t*)pinned + offs[i],
-                                  (size_t)j->images[i].desc.width * j->images[i].desc.bytes_per_pixel);
-    if (r == HC_OK) r = hc_heic_job_sync(j);
-    if (r == HC_OK) {
-      float ms[8];
-      if (hc_heic_job_stage_ms(j, ms) == HC_OK) st.device_ms += ms[1] + ms[2] + ms[3] + ms[4] + ms[5];
-      st.bytes_h2d += hc_heic_job_upload_bytes(j);
-      st.launches += hc_heic_job_launch_count(j);
-      for (size_t i = 0; i < j->images.size(); i++) {
-        const hc_image_desc& d = j->images[i].desc;
-        st.bytes_d2h += (uint64_t)d.width * d.bytes_per_pixel * d.height;
-        st.pixels += (int64_t)d.width * d.height;
-        if (on_image) on_image(user, b * files_per_batch + (int)i, &d, (const uint8_t*)pinned + offs[i], (size_t)d.width * d.bytes_per_pixel);
-      }
-    } else if (rc == HC_OK) {
-      rc = r;
-      err = hc_last_error();
-    }
-    hc_heic_job_destroy(j);
-    st.seconds_gpu_phase += secs(t0, clock::now());
-    st.batches++;
+    const int r = submit(cur.job, b, cur_f);
+    if (prev.job) deliver(prev, prev_rc);
+    prev = std::move(cur_f);
+    prev_rc = r;
   }
-  if (pinned) hc_host_free(pinned);
+  if (prev.job) deliver(prev, prev_rc);
+  for (void* p : pinned)
+    if (p) hc_host_free(p);
   st.seconds_total = secs(t_begin, clock::now());
   if (stats) *stats = st;
   if (rc != HC_OK) hc::set_last_error(err);

@@ -3,6 +3,7 @@
 // Reference counterpart: third-party/libde265/libde265/nal-parser.cc:116-140 (remove_stuffing_bytes),
 // bitstream.cc (get_bits/get_uvlc/get_svlc).
 #pragma once
+#include <cstring>
 #include <cstdint>
 #include <cstddef>
 #include <vector>
@@ -14,22 +15,27 @@ namespace hc {
 // and are corrected with it (reference: decctx.cc:674-680).
 inline void nal_unescape(const uint8_t* in, size_t n, std::vector<uint8_t>& out,
                          std::vector<uint32_t>* skipped) {
-  out.clear();
-  out.reserve(n);
-  size_t i = 0;
-  int zeros = 0;
+  // emulation prevention bytes are rare: find candidate 0x03 bytes with memchr and copy the spans between them
+  out.resize(n);
+  uint8_t* dst = out.data();
+  size_t from = 0, i = 2;
   while (i < n) {
-    uint8_t b = in[i];
-    if (zeros >= 2 && b == 3) {
+    const uint8_t* hit = (const uint8_t*)memchr(in + i, 3, n - i);
+    if (!hit) break;
+    i = (size_t)(hit - in);
+    if (in[i - 1] == 0 && in[i - 2] == 0) {
+      memcpy(dst, in + from, i - from);
+      dst += i - from;
       if (skipped) skipped->push_back((uint32_t)i);
-      zeros = 0;
+      from = i + 1;
+      i += 3;      // the two bytes after an escape cannot complete another 00 00 03 with it
+    } else {
       i++;
-      continue;
     }
-    out.push_back(b);
-    zeros = (b == 0) ? zeros + 1 : 0;
-    i++;
   }
+  memcpy(dst, in + from, n - from);
+  dst += n - from;
+  out.resize((size_t)(dst - out.data()));
 }
 
 struct BitReader {

@@ -13,6 +13,7 @@
 // int16 clip in between.
 //
 // Algorithmic bytes per block: 4*ncoeff (records) + 16 (hc_tb) read, 2*N*N written.
+#include <algorithm>
 #include "launch.h"
 #include "k1_core.cuh"
 
@@ -21,26 +22,16 @@ namespace hc {
 constexpr int K1_WARPS = 4;
 
 template <int LOG2>
-__global__ void __launch_bounds__(K1_WARPS * 32)
-k1_transform_kernel(BatchView bv, const uint32_t* __restrict__ tb_index, int count) {
+__device__ __forceinline__ void k1_block(const BatchView& bv, const uint32_t* __restrict__ tb_index, long long slot,
+                                         int16_t* tile, int grp, int t, unsigned grp_mask) {
   constexpr int N = 1 << LOG2;
-  constexpr int PER_WARP = 32 / N;
   constexpr int S = N + 2;  // padded row stride (int16): conflict-free column and row access
-  __shared__ int16_t tiles[K1_WARPS][PER_WARP][N * S];
-
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int grp = lane / N, t = lane % N;
-  const unsigned grp_mask = (N == 32) ? 0xffffffffu : (((1u << N) - 1u) << (grp * N));
-  const long long slot = ((long long)blockIdx.x * K1_WARPS + warp) * PER_WARP + grp;
-  if (slot >= count) return;  // whole group leaves together
-
   const hc_tb tb = bv.tbs[tb_index[slot]];
   const hc_pic& pic = bv.pics[tb.pic];
   const int cidx = tb.type & HC_TB_CIDX_MASK;
   const int bit_depth = cidx == 0 ? pic.bit_depth_y : pic.bit_depth_c;
   const hc_coeff* __restrict__ co = bv.coeffs + pic.coeff_base + tb.coeff_off;
   int16_t* __restrict__ out = bv.resid + pic.resid_base + tb.resid_off;
-  int16_t* tile = tiles[warp][grp];
 
   // ---- zero the tile, then scatter the dequantised coefficients -------------------------------
 #pragma unroll
@@ -139,24 +130,56 @@ k1_transform_kernel(BatchView bv, const uint32_t* __restrict__ tb_index, int cou
   }
 }
 
+// The launch list holds `count` entries, or *count_ptr when that is non-null: lists built on the device by K0 are
+// consumed without a host round trip, by a grid sized for the list capacity whose CTAs stride over the real count.
+template <int LOG2>
+__global__ void __launch_bounds__(K1_WARPS * 32)
+k1_transform_kernel(BatchView bv, const uint32_t* __restrict__ tb_index, int count, const unsigned* __restrict__ count_ptr) {
+  constexpr int N = 1 << LOG2;
+  constexpr int PER_WARP = 32 / N;
+  constexpr int S = N + 2;
+  __shared__ int16_t tiles[K1_WARPS][PER_WARP][N * S];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int grp = lane / N, t = lane % N;
+  const unsigned grp_mask = (N == 32) ? 0xffffffffu : (((1u << N) - 1u) << (grp * N));
+  const long long cnt = count_ptr ? (long long)*count_ptr : (long long)count;
+  const long long step = (long long)gridDim.x * K1_WARPS * PER_WARP;
+  for (long long slot = ((long long)blockIdx.x * K1_WARPS + warp) * PER_WARP + grp; slot < cnt; slot += step) {  // whole groups
+    k1_block<LOG2>(bv, tb_index, slot, tiles[warp][grp], grp, t, grp_mask);
+    __syncwarp(grp_mask);   // the tile is reused by the next block of this group
+  }
+}
+
 // Host-side launcher. counts[l] blocks of log2 size l+2, indices in tb_index[l] (device pointers).
 void launch_k1(const BatchView& bv, const uint32_t* const tb_index[4], const int counts[4], cudaStream_t stream) {
   if (counts[0] > 0) {
     int per_cta = K1_WARPS * 8;
-    k1_transform_kernel<2><<<(counts[0] + per_cta - 1) / per_cta, K1_WARPS * 32, 0, stream>>>(bv, tb_index[0], counts[0]);
+    k1_transform_kernel<2><<<(counts[0] + per_cta - 1) / per_cta, K1_WARPS * 32, 0, stream>>>(bv, tb_index[0], counts[0], nullptr);
   }
   if (counts[1] > 0) {
     int per_cta = K1_WARPS * 4;
-    k1_transform_kernel<3><<<(counts[1] + per_cta - 1) / per_cta, K1_WARPS * 32, 0, stream>>>(bv, tb_index[1], counts[1]);
+    k1_transform_kernel<3><<<(counts[1] + per_cta - 1) / per_cta, K1_WARPS * 32, 0, stream>>>(bv, tb_index[1], counts[1], nullptr);
   }
   if (counts[2] > 0) {
     int per_cta = K1_WARPS * 2;
-    k1_transform_kernel<4><<<(counts[2] + per_cta - 1) / per_cta, K1_WARPS * 32, 0, stream>>>(bv, tb_index[2], counts[2]);
+    k1_transform_kernel<4><<<(counts[2] + per_cta - 1) / per_cta, K1_WARPS * 32, 0, stream>>>(bv, tb_index[2], counts[2], nullptr);
   }
   if (counts[3] > 0) {
     int per_cta = K1_WARPS;
-    k1_transform_kernel<5><<<(counts[3] + per_cta - 1) / per_cta, K1_WARPS * 32, 0, stream>>>(bv, tb_index[3], counts[3]);
+    k1_transform_kernel<5><<<(counts[3] + per_cta - 1) / per_cta, K1_WARPS * 32, 0, stream>>>(bv, tb_index[3], counts[3], nullptr);
   }
+}
+
+// Lists whose lengths only the device knows (d_counts[4], written by K0): a fixed grid of a few CTAs per SM strides
+// over each list.
+void launch_k1_indirect(const BatchView& bv, const uint32_t* const tb_index[4], const long long capacity[4], const unsigned* d_counts,
+                        int sm_count, cudaStream_t stream) {
+  const int per_cta[4] = {K1_WARPS * 8, K1_WARPS * 4, K1_WARPS * 2, K1_WARPS};
+  auto grid = [&](int l) { return (int)std::max<long long>(1, std::min<long long>((capacity[l] + per_cta[l] - 1) / per_cta[l], (long long)sm_count * 16)); };
+  if (capacity[0] > 0) k1_transform_kernel<2><<<grid(0), K1_WARPS * 32, 0, stream>>>(bv, tb_index[0], 0, d_counts + 0);
+  if (capacity[1] > 0) k1_transform_kernel<3><<<grid(1), K1_WARPS * 32, 0, stream>>>(bv, tb_index[1], 0, d_counts + 1);
+  if (capacity[2] > 0) k1_transform_kernel<4><<<grid(2), K1_WARPS * 32, 0, stream>>>(bv, tb_index[2], 0, d_counts + 2);
+  if (capacity[3] > 0) k1_transform_kernel<5><<<grid(3), K1_WARPS * 32, 0, stream>>>(bv, tb_index[3], 0, d_counts + 3);
 }
 
 }  // namespace hc

@@ -21,6 +21,9 @@ namespace k0 { struct Tables; struct Pic; struct Sub; struct Chain; }
 void launch_k0(const k0::Tables* tables, const k0::Pic* pics, const k0::Sub* subs, const k0::Chain* chains, int nchains,
                cudaStream_t stream);
 void launch_k1(const BatchView& bv, const uint32_t* const tb_index[4], const int counts[4], cudaStream_t stream);
+// lists built on the device (K0): capacity[l] entries at most, the real lengths are d_counts[0..3] in device memory
+void launch_k1_indirect(const BatchView& bv, const uint32_t* const tb_index[4], const long long capacity[4], const unsigned* d_counts,
+                        int sm_count, cudaStream_t stream);
 // shared-memory bytes one K2 row task needs (CTB of ctb_w x ctb_h samples of this component)
 int k2_task_smem_bytes(int ctb_w, int ctb_h, int pixel_bytes);
 // smem_bytes: dynamic shared memory per CTA = max over CTAs of the sum of its K2_WARPS tasks

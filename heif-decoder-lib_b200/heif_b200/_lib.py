@@ -109,6 +109,7 @@ SYMBOLS = [
     ("hc_batch_k0_pictures", _i, [_vp]),
     ("hc_batch_upload", _i, [_vp]),
     ("hc_batch_reconstruct", _i, [_vp, _i]),
+    ("hc_batch_reconstruct_async", _i, [_vp, _i]),
     ("hc_batch_convert", _i, [_vp, _i, C.POINTER(CscParams)]),
     ("hc_batch_sync", _i, [_vp]),
     ("hc_batch_read_plane", _i, [_vp, _i, _i, _vp, _sz]),

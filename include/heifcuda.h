@@ -194,8 +194,13 @@ int hc_batch_upload(hc_batch* b);
 #define HC_STAGE_DEBLOCK 1
 #define HC_STAGE_SAO 2
 #define HC_STAGE_ALL 3
-/* K1 (dequant+transform) -> K2 (intra wavefront) -> K3 (deblock) -> K4 (SAO+crop+paste), async */
+/* [K0 (device CABAC parse) ->] K1 (dequant+transform) -> K2 (intra wavefront) -> K3 (deblock) -> K4 (SAO+crop+paste).
+ * Asynchronous for host-parsed batches; a batch with device-parsed pictures waits for K0's verdict so that malformed
+ * slice data is reported here (HC_ERR_BITSTREAM). */
 int hc_batch_reconstruct(hc_batch* b, int stages);
+/* Same, never waits: a K0 parse error is reported by the next synchronising call on the batch (hc_batch_sync,
+ * hc_batch_read_*, hc_batch_stage_ms). */
+int hc_batch_reconstruct_async(hc_batch* b, int stages);
 /* K5 for one canvas into the engine's device RGB buffer, async */
 int hc_batch_convert(hc_batch* b, int canvas, const hc_csc_params* params);
 int hc_batch_sync(hc_batch* b);
