@@ -16,6 +16,7 @@ struct TablesBuilder {
   k0::Tables t;
   TablesBuilder() {
     memset(&t, 0, sizeof(t));
+    for (int i = 0; i < 256; i++) t.recip[i] = (uint32_t)((1ull << 34) / (uint64_t)(256 + i) + 1);
     memcpy(t.range_lps, detail::kRangeLps, sizeof(t.range_lps));
     memcpy(t.next_state, detail::kTransitions.next, sizeof(t.next_state));
     uint8_t init[CTX_COUNT];

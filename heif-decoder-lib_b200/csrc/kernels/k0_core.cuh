@@ -51,6 +51,7 @@ constexpr int CTX_BYTES = 160;   // padded
 
 // All read-only tables of the parser in one block (constant memory on the device).
 struct alignas(16) Tables {
+  uint32_t recip[256];             // floor(2^34 / (256 + i)) + 1: x / range == (x * recip) >> 34 for x < 2^25 (bypass strings)
   uint8_t range_lps[64][4];
   uint8_t next_state[128][2];      // [state][is_lps]
   uint8_t ctx_init[CX_COUNT];      // initValue per context (initType 0)
@@ -180,7 +181,7 @@ struct Cabac {
     return r;
   }
   HC_HD void refill() {
-    if (avail < 16) {
+    if (__builtin_expect(avail < 16, 0)) {
       value = (value << 32) | next32();
       avail += 32;
     }
@@ -231,12 +232,14 @@ struct Cabac {
     refill();
     return b;
   }
-  HC_HD uint32_t bypass_bits(int n) {
+  // x / range for x < 2^25, by the reciprocal table (an integer division is ~25 instructions on the device)
+  HC_HD uint32_t div_range(const Tables& t, uint32_t x) const { return (uint32_t)(((unsigned long long)x * t.recip[range - 256]) >> 34); }
+  HC_HD uint32_t bypass_bits(const Tables& t, int n) {
     uint32_t out = 0;
     while (n > 0) {
       const int k = n > 16 ? 16 : n;
       avail -= k;
-      const uint32_t q = (uint32_t)(value >> avail) / range;
+      const uint32_t q = div_range(t, (uint32_t)(value >> avail));
       value -= (unsigned long long)(q * range) << avail;
       out = (out << k) | q;
       refill();
@@ -244,7 +247,7 @@ struct Cabac {
     }
     return out;
   }
-  HC_HD uint32_t peek16() const { return (uint32_t)(value >> (avail - 16)) / range; }
+  HC_HD uint32_t peek16(const Tables& t) const { return div_range(t, (uint32_t)(value >> (avail - 16))); }
   HC_HD void consume(int n, uint32_t bins) {
     avail -= n;
     value -= (unsigned long long)(bins * range) << avail;
@@ -388,10 +391,10 @@ struct Parser {
         int sign[4] = {0, 0, 0, 0};
         K0_LOOP for (int i = 0; i < 4; i++)
           if (absv[i]) sign[i] = cb.bypass();
-        ctu.sao_band_or_class[c] = (uint8_t)cb.bypass_bits(5);
+        ctu.sao_band_or_class[c] = (uint8_t)cb.bypass_bits(t, 5);
         K0_LOOP for (int i = 0; i < 4; i++) ctu.sao_offset[c][i] = (int8_t)((sign[i] ? -absv[i] : absv[i]) * (1 << scale));
       } else {
-        if (c < 2) ctu.sao_band_or_class[c] = (uint8_t)cb.bypass_bits(2);
+        if (c < 2) ctu.sao_band_or_class[c] = (uint8_t)cb.bypass_bits(t, 2);
         else ctu.sao_band_or_class[2] = ctu.sao_band_or_class[1];
         ctu.sao_offset[c][0] = (int8_t)(absv[0] * (1 << scale));
         ctu.sao_offset[c][1] = (int8_t)(absv[1] * (1 << scale));
@@ -537,8 +540,8 @@ struct Parser {
       }
     }
     int LastX = last[0], LastY = last[1];
-    if (last[0] > 3) { const int nb = (last[0] >> 1) - 1; LastX = ((2 + (last[0] & 1)) << nb) + (int)cb.bypass_bits(nb); }
-    if (last[1] > 3) { const int nb = (last[1] >> 1) - 1; LastY = ((2 + (last[1] & 1)) << nb) + (int)cb.bypass_bits(nb); }
+    if (last[0] > 3) { const int nb = (last[0] >> 1) - 1; LastX = ((2 + (last[0] & 1)) << nb) + (int)cb.bypass_bits(t, nb); }
+    if (last[1] > 3) { const int nb = (last[1] >> 1) - 1; LastY = ((2 + (last[1] & 1)) << nb) + (int)cb.bypass_bits(t, nb); }
 
     int scanIdx = 0;
     if (log2 == 2 || (log2 == 3 && (cIdx == 0 || p.chroma_array_type == 3))) {
@@ -598,31 +601,30 @@ struct Parser {
       if (Sx > 0) csbf_right |= 1ull << (sxy - 1);
       if (Sy > 0) csbf_below |= 1ull << (sxy - 8);
 
-      // significant positions of this sub-block in decoding order: 4 bits each, entry c at bits [4c, 4c + 4)
-      unsigned long long spos = 0;
-      int n = 0;
+      // significance map of this sub-block: bit k = coefficient at scan position k; decoding order is from the
+      // highest position down
+      uint32_t sig = 0;
       const int xS0 = Sx << 2, yS0 = Sy << 2;
       const uint8_t* sigtab = log2 == 2 ? t.sig_b4[chroma][scanIdx] : t.sig_sb[chroma][sig_size][(Sx | Sy) ? 1 : 0][prevCsbf][scanIdx];
       const int dc_ctx = ts_ctx ? ts_c : ((log2 == 2 || i > 0) ? sigtab[0] : (chroma ? 27 : 0));
 
       const int last_coeff = (i == lastSubBlock) ? lastScanPos - 1 : 15;
-      if (i == lastSubBlock) { spos = (unsigned long long)lastScanPos; n = 1; }
+      if (i == lastSubBlock) sig = 1u << lastScanPos;
       if (ts_ctx) {
-        K0_LOOP for (int k = last_coeff; k > 0; k--) {
-          const int b = cb.bin(t, ctx[CX_SIG + ts_c]);
-          if (b) { spos |= (unsigned long long)k << (4 * n); n++; }
-        }
+        K0_LOOP for (int k = last_coeff; k > 0; k--) sig |= (uint32_t)cb.bin(t, ctx[CX_SIG + ts_c]) << k;
       } else {
-        K0_LOOP for (int k = last_coeff; k > 0; k--) {
-          const int b = cb.bin(t, ctx[CX_SIG + sigtab[k]]);
-          if (b) { spos |= (unsigned long long)k << (4 * n); n++; }
-        }
+        K0_LOOP for (int k = last_coeff; k > 0; k--) sig |= (uint32_t)cb.bin(t, ctx[CX_SIG + sigtab[k]]) << k;
       }
       if (last_coeff >= 0) {
-        if (n > 0 || !inferSbDc) n += cb.bin(t, ctx[CX_SIG + dc_ctx]);   // position 0: nothing to OR into spos
-        else n++;
+        if (sig != 0 || !inferSbDc) sig |= (uint32_t)cb.bin(t, ctx[CX_SIG + dc_ctx]);
+        else sig = 1;
       }
-      if (n == 0) continue;
+      if (sig == 0) continue;
+#if defined(__CUDA_ARCH__)
+      const int n = __popc(sig);
+#else
+      const int n = __builtin_popcount(sig);
+#endif
 
       int ctxSet = (i == 0 || cIdx > 0) ? 0 : 2;
       if (c1 == 0) ctxSet++;
@@ -646,10 +648,10 @@ struct Parser {
         if (!g2) escmask &= ~(1u << firstG1);
       }
 
-      const int pos_first = (int)(spos & 15), pos_last = (int)((spos >> (4 * (n - 1))) & 15);
+      const int pos_first = 31 - k0_clz(sig), pos_last = 31 - k0_clz(sig & (0u - sig));
       const bool signHidden = sign_hiding_possible && (pos_first - pos_last > 3);
       const int nsign = signHidden ? n - 1 : n;
-      const uint32_t signs = cb.bypass_bits(nsign) << (16 - nsign);
+      const uint32_t signs = cb.bypass_bits(t, nsign) << (16 - nsign);
 
       if (ncoeff_total + (uint32_t)n > coeff_room) { fail(ERR_CAPACITY); return 0; }
       int sumAbs = 0, rice = 0;
@@ -657,7 +659,7 @@ struct Parser {
         const int base = 1 + (int)((g1mask >> c) & 1) + ((c == firstG1) ? g2 : 0);
         int rem = 0;
         if ((escmask >> c) & 1) {
-          const uint32_t q16 = cb.peek16();
+          const uint32_t q16 = cb.peek16(t);
           const int ones = q16 == 0xffffu ? 16 : k0_clz(~(q16 << 16));
           const int suffix_len = ones <= 3 ? rice : ones - 3 + rice;
           const int len = ones + 1 + suffix_len;
@@ -670,8 +672,8 @@ struct Parser {
             int prefix = 0;
             K0_LOOP while (prefix < 32 && cb.bypass()) prefix++;
             if (prefix >= 32) { fail(ERR_BITSTREAM); return 0; }
-            if (prefix <= 3) rem = (prefix << rice) + (int)cb.bypass_bits(rice);
-            else rem = (((1 << (prefix - 3)) + 3 - 1) << rice) + (int)cb.bypass_bits(prefix - 3 + rice);
+            if (prefix <= 3) rem = (prefix << rice) + (int)cb.bypass_bits(t, rice);
+            else rem = (((1 << (prefix - 3)) + 3 - 1) << rice) + (int)cb.bypass_bits(t, prefix - 3 + rice);
           }
           if (base + rem > 3 * (1 << rice)) { rice++; if (rice > 4) rice = 4; }
         }
@@ -682,7 +684,9 @@ struct Parser {
           sumAbs += base + rem;
           if (c == n - 1 && (sumAbs & 1)) level = -level;
         }
-        const int sp = scanPos[(int)((spos >> (4 * c)) & 15)];
+        const int k = 31 - k0_clz(sig);
+        sig ^= 1u << k;
+        const int sp = scanPos[k];
         hc_coeff co;
         co.pos = (uint16_t)((xS0 + (sp & 3)) + ((yS0 + (sp >> 2)) << log2));
         co.level = (int16_t)level;
@@ -714,7 +718,7 @@ struct Parser {
           int k = 0;
           K0_LOOP while (k < 32 && cabac.bypass()) k++;
           if (k >= 32) { fail(ERR_BITSTREAM); return; }
-          v += ((1 << k) - 1) + (int)cabac.bypass_bits(k);
+          v += ((1 << k) - 1) + (int)cabac.bypass_bits(tab(), k);
         }
       }
       int sign = 0;
@@ -845,7 +849,7 @@ struct Parser {
         K0_LOOP while (v < 2 && cb.bypass()) v++;
         mpm_idx[i] = v;
       } else {
-        rem[i] = (int)cb.bypass_bits(5);
+        rem[i] = (int)cb.bypass_bits(t, 5);
       }
     }
     const bool availA0 = ctb_available(x0, y0, x0 - 1, y0), availB0 = ctb_available(x0, y0, x0, y0 - 1);
@@ -889,7 +893,7 @@ struct Parser {
       const int nchroma = cat == 3 ? nparts : 1;
       K0_LOOP for (int idx = 0; idx < nchroma; idx++) {
         int icpm = 4;
-        if (cb.bin(t, ctx[CX_INTRA_CHROMA])) icpm = (int)cb.bypass_bits(2);
+        if (cb.bin(t, ctx[CX_INTRA_CHROMA])) icpm = (int)cb.bypass_bits(t, 2);
         const int luma = luma_modes[idx];
         int m = luma;
         if (icpm != 4) {

@@ -6,6 +6,7 @@
 // chains in flight. Chains are ordered row-major across all pictures so that a chain only ever waits for a chain
 // with a smaller index (scheduled no later than itself). Tables, context states and the picture / slice descriptors
 // of a chain live in shared memory (k0_core.cuh: Scratch).
+#include <cstdlib>
 #include "launch.h"
 #include "k0_core.cuh"
 
@@ -16,9 +17,13 @@ namespace hc {
 // consecutive pictures, so the warps of a CTA run for about the same time.
 constexpr int K0_WARPS = 4;
 
-__global__ void __launch_bounds__(32 * K0_WARPS, 5) k0_parse_kernel(const k0::Tables* __restrict__ tables, const k0::Pic* __restrict__ pics,
-                                                                   const k0::Sub* __restrict__ subs, const k0::Chain* __restrict__ chains,
-                                                                   int nchains) {
+// MIN_CTAS: CTAs per SM the register allocation must allow (5 -> 96 registers, 8 -> 64, 10 -> 48). A chain uses one
+// lane, so resident chains per SM = 4 * MIN_CTAS is limited by registers x 32 lanes; HEIFCUDA_K0_OCC picks the trade-off
+// between spills in a chain and chains in flight (measured: see DESIGN.md).
+template <int MIN_CTAS>
+__global__ void __launch_bounds__(32 * K0_WARPS, MIN_CTAS) k0_parse_kernel(const k0::Tables* __restrict__ tables, const k0::Pic* __restrict__ pics,
+                                                                          const k0::Sub* __restrict__ subs, const k0::Chain* __restrict__ chains,
+                                                                          int nchains) {
   {
     const uint32_t* src = reinterpret_cast<const uint32_t*>(tables);
     uint32_t* dst = reinterpret_cast<uint32_t*>(k0::k0_smem);
@@ -39,8 +44,12 @@ void launch_k0(const k0::Tables* tables, const k0::Pic* pics, const k0::Sub* sub
                cudaStream_t stream) {
   if (nchains <= 0) return;
   static_assert(sizeof(k0::Tables) % 4 == 0, "tables are copied word-wise");
+  static const int occ = []() { const char* e = getenv("HEIFCUDA_K0_OCC"); return e ? atoi(e) : 5; }();
   const int smem = k0::TABLE_BYTES + K0_WARPS * k0::SCRATCH_BYTES;
-  k0_parse_kernel<<<(nchains + K0_WARPS - 1) / K0_WARPS, 32 * K0_WARPS, smem, stream>>>(tables, pics, subs, chains, nchains);
+  const int grid = (nchains + K0_WARPS - 1) / K0_WARPS;
+  if (occ >= 10) k0_parse_kernel<10><<<grid, 32 * K0_WARPS, smem, stream>>>(tables, pics, subs, chains, nchains);
+  else if (occ >= 8) k0_parse_kernel<8><<<grid, 32 * K0_WARPS, smem, stream>>>(tables, pics, subs, chains, nchains);
+  else k0_parse_kernel<5><<<grid, 32 * K0_WARPS, smem, stream>>>(tables, pics, subs, chains, nchains);
 }
 
 }  // namespace hc
