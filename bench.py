@@ -132,6 +132,8 @@ def main():
     ap.add_argument("--images", type=int, default=8, help="12 MP files per step and GPU")
     ap.add_argument("--distinct", type=int, default=2, help="distinct synthetic files (replicated to --images)")
     ap.add_argument("--threads", type=int, default=0, help="host parse threads (0 = all cores)")
+    ap.add_argument("--host-share", type=int, default=-1, help="with --parser device: %% of the coded items parsed by the host threads "
+                    "meanwhile in the e2e arm (default: engine default)")
     ap.add_argument("--parser", default="device", choices=["device", "host"],
                     help="where the CABAC slice data is parsed: K0 on the GPU (default) or the host parser")
     args = ap.parse_args()
@@ -195,6 +197,8 @@ def main():
 
     eng = hb.Engine(local_rank)
     eng.set_option("device_parse", 1 if args.parser == "device" else 0)
+    if args.host_share >= 0:
+        eng.set_option("host_share_pct", args.host_share)
     threads = args.threads or cores // max(1, world)
     # R: bytes of packed records per output pixel as the host parser emits them (what K1/K2 read from HBM either way)
     hf = hb.HeifFile(files[0], host_only=False)

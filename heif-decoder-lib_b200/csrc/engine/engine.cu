@@ -49,6 +49,7 @@ struct hc_engine {
   hc::k0::Tables* d_k0_tables = nullptr;   // read-only tables of the device parser
   int device_parse = 1;                    // hc_heic_job: let K0 parse every picture it accepts
   int sm_count = 148;
+  int host_share_pct = -1;                 // hc_heic_job with device_parse: percentage of the coded items the host threads parse meanwhile
 
   Block take(std::vector<Block>& list, size_t size, bool pinned) {
     std::lock_guard<std::mutex> lk(mu);
@@ -188,6 +189,7 @@ hc_engine* hc_engine_create(int device) {
   eng->device = device;
   cudaDeviceGetAttribute(&eng->sm_count, cudaDevAttrMultiProcessorCount, device);
   if (const char* m = getenv("HEIFCUDA_PARSER")) eng->device_parse = strcmp(m, "host") != 0;
+  if (const char* m = getenv("HEIFCUDA_HOST_SHARE")) eng->host_share_pct = std::max(-1, std::min(100, atoi(m)));
   if (!cuda_ok(cudaMalloc(&eng->d_k0_tables, sizeof(hc::k0::Tables)), "cudaMalloc(K0 tables)") ||
       !cuda_ok(cudaMemcpy(eng->d_k0_tables, &hc::k0_tables(), sizeof(hc::k0::Tables), cudaMemcpyHostToDevice), "cudaMemcpy(K0 tables)")) {
     delete eng;
@@ -209,12 +211,14 @@ void hc_engine_destroy(hc_engine* e) {
 int hc_engine_set_option(hc_engine* e, const char* name, int value) {
   if (!e || !name) return HC_ERR_ARGUMENT;
   if (!strcmp(name, "device_parse")) { e->device_parse = value; return HC_OK; }
+  if (!strcmp(name, "host_share_pct")) { e->host_share_pct = value < 0 ? -1 : (value > 100 ? 100 : value); return HC_OK; }
   hc::set_last_error(std::string("unknown engine option ") + name);
   return HC_ERR_ARGUMENT;
 }
 int hc_engine_get_option(const hc_engine* e, const char* name) {
   if (!e || !name) return 0;
   if (!strcmp(name, "device_parse")) return e->device_parse;
+  if (!strcmp(name, "host_share_pct")) return e->host_share_pct;
   return 0;
 }
 

@@ -72,8 +72,10 @@ void hc_heic_job_destroy(hc_heic_job* j) {
 }  // extern "C"
 
 // band_begin/band_end: tile rows [begin, end) of a grid image to decode (band_end < 0: everything)
+// host_share: percentage of the coded items the host threads parse although the device parser is on (hybrid; < 0: the
+// engine option, where "auto" means none outside hc_heic_decode_stream)
 static hc_heic_job* job_create(hc_engine* e, int nfiles, const uint8_t* const* data, const size_t* sizes,
-                               int want_alpha, int threads, int band_begin, int band_end) {
+                               int want_alpha, int threads, int band_begin, int band_end, int host_share_arg = -1) {
   if (!e || nfiles <= 0 || !data || !sizes) {
     hc::set_last_error("hc_heic_job_create: bad argument");
     return nullptr;
@@ -146,6 +148,7 @@ static hc_heic_job* job_create(hc_engine* e, int nfiles, const uint8_t* const* d
   if (nthreads < 1) nthreads = 1;
   nthreads = std::min<int>(nthreads, (int)j->items.size());
   const bool device_parse = hc_engine_get_option(e, "device_parse") != 0;
+  const int host_share = !device_parse ? 0 : (host_share_arg >= 0 ? host_share_arg : std::max(0, hc_engine_get_option(e, "host_share_pct")));
   std::atomic<size_t> next{0};
   auto worker = [&]() {
     for (;;) {
@@ -154,7 +157,9 @@ static hc_heic_job* job_create(hc_engine* e, int nfiles, const uint8_t* const* d
       CodedItem& ci = j->items[i];
       std::string err = j->files[ci.file]->coded_stream(ci.item_id, ci.stream);
       if (!err.empty()) { ci.error = err; continue; }
-      if (device_parse) {
+      // hybrid: while the GPU parses the previous batch, the host cores parse an evenly spread share of this one
+      const bool to_host = host_share > 0 && ((i + 1) * (size_t)host_share) / 100 != (i * (size_t)host_share) / 100;
+      if (device_parse && !to_host) {
         // K0: only parameter sets and slice headers are read here; the GPU parses the slice data
         std::unique_ptr<hc_k0_picture> k(new hc_k0_picture);
         err = hc::k0_prepare(ci.stream.data(), ci.stream.size(), HC_STREAM_LENGTH_PREFIXED, k->hp);
@@ -325,12 +330,19 @@ int hc_heic_decode_stream(hc_engine* e, int nfiles, const uint8_t* const* data, 
   const int nbatches = (nfiles + files_per_batch - 1) / files_per_batch;
 
   // stage 1 (host threads): container + CABAC parse of one batch; runs one batch ahead of stage 2
-  struct Parsed { hc_heic_job* job = nullptr; std::string error; double seconds = 0; };
+  // Hybrid parse: with the device parser on, the host threads that prepare batch b+1 would idle while the GPU works on
+  // batch b, so they parse a share of the coded items themselves. "auto" (engine option -1) starts at 20 % and follows
+  // the measured ratio of GPU time to host time per batch, so that a rank with few host threads ends up near 0.
+  const int share_opt = hc_engine_get_option(e, "host_share_pct");
+  std::atomic<int> share{share_opt >= 0 ? share_opt : 20};
+  double c_host = 0, c_dev = 0;
+  struct Parsed { hc_heic_job* job = nullptr; std::string error; double seconds = 0; int share = 0; };
   auto parse_batch = [&](int b) -> Parsed {
     Parsed p;
     const int first = b * files_per_batch, n = std::min(files_per_batch, nfiles - first);
     const auto t0 = clock::now();
-    p.job = hc_heic_job_create(e, n, data + first, sizes + first, want_alpha, threads);
+    p.share = nbatches > 1 ? share.load() : 0;
+    p.job = job_create(e, n, data + first, sizes + first, want_alpha, threads, 0, -1, p.share);
     if (!p.job) p.error = hc_last_error();   // thread-local: fetch on the parsing thread
     p.seconds = secs(t0, clock::now());
     return p;
@@ -339,7 +351,7 @@ int hc_heic_decode_stream(hc_engine* e, int nfiles, const uint8_t* const* data, 
   // stage 2 (this thread): submit — upload, [K0,] K1..K5 and the read-back into one of two pinned buffers are only
   // ENQUEUED on the batch's stream; stage 3 (this thread, one batch behind): deliver — wait for the stream, hand the
   // images out, release the batch. So the GPU parses / reconstructs batch b+1 while batch b is copied back and consumed.
-  struct InFlight { hc_heic_job* job = nullptr; int index = 0; int slot = 0; std::vector<size_t> offs; clock::time_point t0; };
+  struct InFlight { hc_heic_job* job = nullptr; int index = 0; int slot = 0; std::vector<size_t> offs; clock::time_point t0; double host_s = 0; int share = 0; };
   void* pinned[2] = {nullptr, nullptr};
   size_t pinned_cap[2] = {0, 0};
   int rc = HC_OK;
@@ -375,7 +387,22 @@ int hc_heic_decode_stream(hc_engine* e, int nfiles, const uint8_t* const* data, 
     double tc = tb;
     if (r == HC_OK) {
       float ms[8];
-      if (hc_heic_job_stage_ms(j, ms) == HC_OK) st.device_ms += ms[1] + ms[2] + ms[3] + ms[4] + ms[5] + ms[7];
+      if (hc_heic_job_stage_ms(j, ms) == HC_OK) {
+        const double gpu_ms = ms[1] + ms[2] + ms[3] + ms[4] + ms[5] + ms[7];
+        st.device_ms += gpu_ms;
+        if (share_opt < 0 && f.index > 2 && f.host_s > 0 && gpu_ms > 0) {
+          // cost per coded item on either side, smoothed; the balanced share is c_dev / (c_host + c_dev). The estimate
+          // does not depend on the share the batch was parsed with, so the two-batch lag of the pipeline is harmless.
+          const double n_items = (double)j->items.size();
+          const double n_host = std::max(1.0, n_items * f.share / 100.0), n_dev = std::max(1.0, n_items - n_items * f.share / 100.0);
+          const double ch = f.host_s / n_host, cd = gpu_ms * 1e-3 / n_dev;
+          c_host = c_host > 0 ? 0.5 * c_host + 0.5 * ch : ch;
+          c_dev = c_dev > 0 ? 0.5 * c_dev + 0.5 * cd : cd;
+          const int next = (int)(85.0 * c_dev / (c_host + c_dev) + 0.5);
+          share.store(std::max(3, std::min(50, next)));
+          if (trace_on()) fprintf(stderr, "[heifcuda] batch %d: host %.1f ms, gpu %.1f ms at share %d%% -> %d%%\n", f.index, f.host_s * 1e3, gpu_ms, f.share, share.load());
+        }
+      }
       st.bytes_h2d += hc_heic_job_upload_bytes(j);
       st.launches += hc_heic_job_launch_count(j);
       for (size_t i = 0; i < j->images.size(); i++) {
@@ -408,6 +435,8 @@ int hc_heic_decode_stream(hc_engine* e, int nfiles, const uint8_t* const* data, 
       continue;   // keep draining the pipeline
     }
     if (rc != HC_OK) { hc_heic_job_destroy(cur.job); continue; }
+    cur_f.host_s = cur.seconds;
+    cur_f.share = cur.share;
     const int r = submit(cur.job, b, cur_f);
     if (prev.job) deliver(prev, prev_rc);
     prev = std::move(cur_f);

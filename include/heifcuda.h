@@ -170,7 +170,11 @@ typedef struct hc_batch hc_batch;
 hc_engine* hc_engine_create(int device);
 void hc_engine_destroy(hc_engine* e);
 /* Options: "device_parse" (default 1; environment HEIFCUDA_PARSER=host sets 0): hc_heic_job / hc_heic_decode_stream
- * let kernel K0 parse the slice data of every picture it accepts instead of the host CABAC parser. */
+ * let kernel K0 parse the slice data of every picture it accepts instead of the host CABAC parser.
+ * "host_share_pct" (environment HEIFCUDA_HOST_SHARE): with device_parse, this percentage of the coded items of every job
+ * is parsed by the host threads instead, which run while the GPU is busy with the previous batch of
+ * hc_heic_decode_stream (hybrid parse). Default -1 = automatic: none for a single hc_heic_job, and in
+ * hc_heic_decode_stream a share that follows the measured host / GPU time per batch. */
 int hc_engine_set_option(hc_engine* e, const char* name, int value);
 int hc_engine_get_option(const hc_engine* e, const char* name);
 
