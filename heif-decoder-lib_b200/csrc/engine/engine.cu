@@ -369,7 +369,7 @@ int hc_batch_upload(hc_batch* b) {
     n_tasks += (size_t)ncomp * p.ctbs_h;
     b->max_planes = std::max(b->max_planes, ncomp);
     b->max_dbk_units = std::max(b->max_dbk_units, (long long)(p.width >> 3) * (p.height >> 2));
-    b->max_sao_quads = std::max(b->max_sao_quads, ((long long)p.ctbs_w * p.ctbs_h) << std::max(0, 2 * p.log2_ctb - 8));
+    b->max_sao_quads = std::max(b->max_sao_quads, (long long)p.ctbs_w * p.ctbs_h);   // CTBs: K4 runs one warp per CTB
     // reconstruction planes
     const int ps = (p.bit_depth_y == 8 && p.bit_depth_c == 8) ? 1 : 2;
     const int SubW = (p.chroma_format == 1 || p.chroma_format == 2) ? 2 : 1, SubH = p.chroma_format == 1 ? 2 : 1;
@@ -749,6 +749,73 @@ int hc_batch_convert(hc_batch* b, int canvas, const hc_csc_params* params) {
   b->csc_events.push_back({e0, e1});
   b->launches += 1;
   c.converted = true;
+  if (!cuda_ok(cudaGetLastError(), "kernel launch (K5)")) return HC_ERR_CUDA;
+  return HC_OK;
+}
+
+// K5 for several canvases with as few launches as possible (one per group of up to CSC_BATCH_MAX canvases of the
+// same sample size). Same result as calling hc_batch_convert for each of them.
+int hc_batch_convert_many(hc_batch* b, int n, const int* canvases, const hc_csc_params* params) {
+  if (!b || n <= 0 || !canvases || !params || !b->uploaded) { hc::set_last_error("hc_batch_convert_many: bad argument"); return HC_ERR_ARGUMENT; }
+  if (!cuda_ok(cudaSetDevice(b->eng->device), "cudaSetDevice")) return HC_ERR_CUDA;
+  static const int bpp_of[6] = {3, 4, 6, 8, 6, 8};
+  for (int i = 0; i < n; i++) {
+    if (canvases[i] < 0 || canvases[i] >= (int)b->canvases.size() || params[i].out_format < 0 || params[i].out_format > 5) {
+      hc::set_last_error("hc_batch_convert_many: bad canvas or output format");
+      return HC_ERR_ARGUMENT;
+    }
+    Canvas& c = b->canvases[canvases[i]];
+    if ((params[i].out_format <= HC_OUT_RGBA) != (c.bit_depth == 8)) {
+      hc::set_last_error("8-bit images convert to RGB/RGBA, deeper images to RRGGBB(AA)");
+      return HC_ERR_UNSUPPORTED;
+    }
+    c.rgb_bpp = bpp_of[params[i].out_format];
+    c.rgb_stride = align_up((size_t)((c.w + 7) & ~7) * c.rgb_bpp, 256);
+  }
+  size_t total = 0;
+  for (auto& cv : b->canvases) {
+    const int bp = cv.rgb_bpp ? cv.rgb_bpp : (cv.bit_depth == 8 ? 4 : 8);
+    cv.rgb_off = total;
+    total += align_up(align_up((size_t)((cv.w + 7) & ~7) * bp, 256) * cv.h, 256);
+  }
+  if (b->d_rgb.cap < total) {
+    b->eng->give(b->eng->free_dev, b->d_rgb);
+    b->d_rgb = b->eng->take(b->eng->free_dev, total, false);
+    if (!b->d_rgb.p) return HC_ERR_MEMORY;
+    for (auto& cv : b->canvases) cv.converted = false;
+  }
+  const uint8_t* P = (const uint8_t*)b->d_planes.p;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  cudaEventRecord(e0, b->stream);
+  for (int sixteen = 0; sixteen < 2; sixteen++) {
+    hc::CscBatch cb;
+    cb.n = 0;
+    for (int i = 0; i <= n; i++) {
+      if (i < n && (b->canvases[canvases[i]].bit_depth != 8) == (sixteen != 0)) {
+        Canvas& c = b->canvases[canvases[i]];
+        hc::CscArgs& a = cb.a[cb.n++];
+        a.y = P + c.off[0];
+        a.cb = c.chroma ? P + c.off[1] : nullptr;
+        a.cr = c.chroma ? P + c.off[2] : nullptr;
+        a.a = c.alpha ? P + c.off[3] : nullptr;
+        a.y_stride = c.stride[0]; a.c_stride = c.stride[1]; a.a_stride = c.stride[3];
+        a.width = c.w; a.height = c.h; a.chroma_format = c.chroma;
+        a.out = (uint8_t*)b->d_rgb.p + c.rgb_off;
+        a.out_stride = (long long)c.rgb_stride;
+        a.p = params[i];
+        a.p.bit_depth = c.bit_depth;
+        c.converted = true;
+      }
+      if (cb.n == hc::CSC_BATCH_MAX || (i == n && cb.n > 0)) {
+        hc::launch_k5_batch(cb, sixteen != 0, b->stream);
+        b->launches += 1;
+        cb.n = 0;
+      }
+    }
+  }
+  cudaEventRecord(e1, b->stream);
+  b->csc_events.push_back({e0, e1});
   if (!cuda_ok(cudaGetLastError(), "kernel launch (K5)")) return HC_ERR_CUDA;
   return HC_OK;
 }

@@ -290,11 +290,10 @@ int hc_heic_job_run(hc_heic_job* j) {
   if (!j) return HC_ERR_ARGUMENT;
   int rc = hc_batch_reconstruct_async(j->batch, HC_STAGE_ALL);   // K0 errors surface in hc_heic_job_sync / read
   if (rc != HC_OK) return rc;
-  for (ImagePlan& im : j->images) {
-    rc = hc_batch_convert(j->batch, im.canvas, &im.csc);
-    if (rc != HC_OK) return rc;
-  }
-  return HC_OK;
+  std::vector<int> canvases;
+  std::vector<hc_csc_params> params;
+  for (ImagePlan& im : j->images) { canvases.push_back(im.canvas); params.push_back(im.csc); }
+  return hc_batch_convert_many(j->batch, (int)canvases.size(), canvases.data(), params.data());
 }
 
 int hc_heic_job_sync(hc_heic_job* j) { return j ? hc_batch_sync(j->batch) : HC_ERR_ARGUMENT; }

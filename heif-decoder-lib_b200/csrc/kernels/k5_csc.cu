@@ -16,6 +16,7 @@
 // Mapping: one thread converts 8 horizontally adjacent pixels (8/16-byte plane loads) and writes them
 // with 64-bit / 128-bit stores; a warp writes 768 (RGB) .. 2048 (RRGGBBAA) contiguous bytes. Pure streaming:
 // algorithmic bytes = s*c (+s alpha) read + bytes-per-pixel written.
+#include <algorithm>
 #include "launch.h"
 
 namespace hc {
@@ -107,9 +108,8 @@ HC_D void load_px4(const Pixel* p, int n, int fill, int v[8]) {
 // One thread converts 8 horizontally adjacent pixels: 8/16-byte plane loads, 8/16-byte interleaved stores
 // (24 .. 64 bytes per thread, contiguous across the warp). Output rows are padded to a multiple of 8 pixels.
 template <typename Pixel>
-__global__ void __launch_bounds__(256) k5_csc_kernel(CscArgs a) {
+__device__ __forceinline__ void csc_unit(const CscArgs& a, unsigned tid) {
   const unsigned nq = (unsigned)(a.width + 7) >> 3;
-  const unsigned tid = blockIdx.x * blockDim.x + threadIdx.x;
   if (tid >= nq * (unsigned)a.height) return;
   const int y = (int)(tid / nq), x0 = (int)(tid - (unsigned)y * nq) << 3;
   const int n = min(8, a.width - x0);
@@ -203,12 +203,40 @@ __global__ void __launch_bounds__(256) k5_csc_kernel(CscArgs a) {
   }
 }
 
+template <typename Pixel>
+__global__ void __launch_bounds__(256) k5_csc_kernel(CscArgs a) {
+  csc_unit<Pixel>(a, blockIdx.x * blockDim.x + threadIdx.x);
+}
+
+// All canvases of a batch in one launch (blockIdx.y = canvas): a 12 MP canvas is a ~10 us kernel at HBM speed, so
+// per-canvas launches are dominated by launch gaps and tails.
+template <typename Pixel>
+__global__ void __launch_bounds__(256) k5_csc_batch_kernel(CscBatch b) {
+  __shared__ CscArgs sa;
+  {
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(&b.a[blockIdx.y]);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(&sa);
+    for (int i = threadIdx.x; i < (int)(sizeof(CscArgs) / 4); i += blockDim.x) dst[i] = src[i];
+  }
+  __syncthreads();
+  csc_unit<Pixel>(sa, blockIdx.x * blockDim.x + threadIdx.x);
+}
+
 void launch_k5(const CscArgs& a, bool sixteen_bit, cudaStream_t stream) {
   const long long n = (long long)((a.width + 7) >> 3) * a.height;
   if (n <= 0) return;
   const unsigned grid = (unsigned)((n + 255) / 256);
   if (sixteen_bit) k5_csc_kernel<uint16_t><<<grid, 256, 0, stream>>>(a);
   else k5_csc_kernel<uint8_t><<<grid, 256, 0, stream>>>(a);
+}
+
+void launch_k5_batch(const CscBatch& b, bool sixteen_bit, cudaStream_t stream) {
+  long long nmax = 0;
+  for (int i = 0; i < b.n; i++) nmax = std::max(nmax, (long long)((b.a[i].width + 7) >> 3) * b.a[i].height);
+  if (nmax <= 0 || b.n <= 0) return;
+  dim3 grid((unsigned)((nmax + 255) / 256), (unsigned)b.n);
+  if (sixteen_bit) k5_csc_batch_kernel<uint16_t><<<grid, 256, 0, stream>>>(b);
+  else k5_csc_batch_kernel<uint8_t><<<grid, 256, 0, stream>>>(b);
 }
 
 }  // namespace hc

@@ -16,6 +16,13 @@ struct CscArgs {
   hc_csc_params p;
 };
 
+// up to CSC_BATCH_MAX canvases of one sample size converted by one launch (kernel parameter space: 4 KB)
+constexpr int CSC_BATCH_MAX = 24;
+struct CscBatch {
+  CscArgs a[CSC_BATCH_MAX];
+  int n;
+};
+
 namespace k0 { struct Tables; struct Pic; struct Sub; struct Chain; }
 // K0: device CABAC parse of the pictures added as bitstreams (one CTA per substream chain)
 void launch_k0(const k0::Tables* tables, const k0::Pic* pics, const k0::Sub* subs, const k0::Chain* chains, int nchains,
@@ -29,7 +36,8 @@ int k2_task_smem_bytes(int ctb_w, int ctb_h, int pixel_bytes);
 // smem_bytes: dynamic shared memory per CTA = max over CTAs of the sum of its K2_WARPS tasks
 void launch_k2(const BatchView& bv, const RowTask* tasks, int ntasks, int smem_bytes, int* progress, cudaStream_t stream);
 void launch_k3(const BatchView& bv, long long max_units, int planes, cudaStream_t stream);
-void launch_k4(const BatchView& bv, long long max_quads, int planes, cudaStream_t stream);
+void launch_k4(const BatchView& bv, long long max_ctbs, int planes, cudaStream_t stream);
 void launch_k5(const CscArgs& a, bool sixteen_bit, cudaStream_t stream);
+void launch_k5_batch(const CscBatch& b, bool sixteen_bit, cudaStream_t stream);
 
 }  // namespace hc

@@ -111,6 +111,7 @@ SYMBOLS = [
     ("hc_batch_reconstruct", _i, [_vp, _i]),
     ("hc_batch_reconstruct_async", _i, [_vp, _i]),
     ("hc_batch_convert", _i, [_vp, _i, C.POINTER(CscParams)]),
+    ("hc_batch_convert_many", _i, [_vp, _i, C.POINTER(C.c_int), C.POINTER(CscParams)]),
     ("hc_batch_sync", _i, [_vp]),
     ("hc_batch_read_plane", _i, [_vp, _i, _i, _vp, _sz]),
     ("hc_batch_read_rgb", _i, [_vp, _i, _vp, _sz]),

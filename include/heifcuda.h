@@ -207,6 +207,8 @@ int hc_batch_reconstruct(hc_batch* b, int stages);
 int hc_batch_reconstruct_async(hc_batch* b, int stages);
 /* K5 for one canvas into the engine's device RGB buffer, async */
 int hc_batch_convert(hc_batch* b, int canvas, const hc_csc_params* params);
+/* K5 for n canvases (canvases[i] with params[i]) in as few launches as possible, async */
+int hc_batch_convert_many(hc_batch* b, int n, const int* canvases, const hc_csc_params* params);
 int hc_batch_sync(hc_batch* b);
 /* D2H reads (synchronous). plane: 0 Y, 1 Cb, 2 Cr, 3 alpha. Samples are 1 byte for 8-bit canvases,
  * 2 bytes little-endian otherwise. */
