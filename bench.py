@@ -4,12 +4,13 @@
 Workload (config.workload): BASELINE config C2 — 4032x3024 "iPhone-style" grid of 48 (8x6) 512x512
 HEVC intra tiles, 8-bit 4:2:0, CTB 64, WPP, SAO + deblocking, QP 26, full-range BT.601 VUI -> interleaved
 RGB. Content is synthetic (tools/hevc_enc closed-loop encoder + tools/heif_writer), generated untimed
-at start-up. One step = one batch of `--images` such files (default 8 = 384 coded pictures in flight).
+at start-up. One step = one batch of `--images` such files (default 16 = 768 coded pictures in flight).
 
   value : device time of K steps of K1..K5 with the packed records already resident in HBM
           (CUDA events on the engine's stream), whole-job MP/s over all ranks
-  e2e   : the same metric through the C ABI from HEIC bytes in host memory to RGB bytes in pinned host
-          memory: host CABAC parse (all host threads) + H2D + kernels + D2H inside the timed region
+  e2e   : the same metric through the C ABI (hc_heic_decode_stream) from HEIC bytes in host memory to RGB bytes in
+          pinned host memory: container + header parse, slice-data parse (K0 on the GPU, plus the share the host
+          threads take meanwhile; --parser host: host threads only), H2D, K1..K5 and D2H inside the timed region
   roofline     : the dominant kernel's algorithmic bytes / its CUDA-event duration vs MEASURED_PEAKS.json
   cpu_baseline : the unmodified reference (oracle/_ref: libheif + libde265, heif_decode_image -> RGB) on
                  the host cores, bounded sample of the same file
@@ -129,7 +130,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
-    ap.add_argument("--images", type=int, default=8, help="12 MP files per step and GPU")
+    ap.add_argument("--images", type=int, default=16, help="12 MP files per step and GPU")
     ap.add_argument("--distinct", type=int, default=2, help="distinct synthetic files (replicated to --images)")
     ap.add_argument("--threads", type=int, default=0, help="host parse threads (0 = all cores)")
     ap.add_argument("--host-share", type=int, default=-1, help="with --parser device: %% of the coded items parsed by the host threads "
@@ -161,6 +162,10 @@ def main():
         print(json.dumps(line))
         return 0
 
+    # stdout carries exactly one JSON line: NCCL's version / debug lines go to stderr
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+    if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"
     import numpy as np
     import torch
     import heif_b200 as hb
@@ -281,12 +286,15 @@ def main():
     alg = {"k1_transform": rec_bytes_per_px * coded_px + 3.0 * coded_px, "k2_intra": 4.5 * coded_px, "k3_deblock": 2 * 3.0 * coded_px,
            "k4_sao": 1.5 * coded_px + 1.5 * px, "k5_csc": 4.5 * px}
     kernels = {k: stage_last[k] for k in alg}
+    k0_ms = stage_last.get("k0_parse", 0.0)
     dom = max(kernels, key=kernels.get)
     achieved = alg[dom] / (kernels[dom] * 1e-3) / 1e9 if kernels[dom] > 0 else 0.0
     roofline = {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": None, "peak_source": peak_src,
                 "all_kernels": {k: {"ms": round(kernels[k], 4), "algorithmic_GBps": round(alg[k] / (kernels[k] * 1e-3) / 1e9, 1) if kernels[k] > 0 else None}
                                 for k in alg},
+                "k0_parse": {"ms": round(k0_ms, 4), "note": "device CABAC parse, once per upload, outside `value`, inside e2e; serial per substream: "
+                             "bound by single-thread instruction latency, not by HBM (DESIGN.md)"} if k0_ms > 0 else None,
                 "note": "k2_intra is a dependency-latency-bound CTB wavefront, not a streaming kernel (DESIGN.md)"}
 
     # ---- CPU baseline on the box's cores (rank 0, N = 1 only) ----
@@ -311,10 +319,12 @@ def main():
             "e2e": {"value": world * mp_per_step / e2e_dt, "unit": UNIT, "h2d_bytes_per_step": upload_bytes, "d2h_bytes_per_step": rgb_bytes,
                     "ms_per_step": e2e_dt * 1e3, "host_parse_ms_per_step": parse_s * 1e3, "gpu_phase_ms_per_step": gpu_phase_s * 1e3,
                     "first_batch_ms": first_batch_s * 1e3, "steps": e2e_steps,
-                    "api": "hc_heic_decode_stream: host parse of batch b+1 overlaps H2D + K1..K5 + D2H of batch b; pinned host output"},
+                    "api": "hc_heic_decode_stream: header parse (+ host share of the slice data) of batch b+1 and D2H + delivery of batch "
+                           "b-1 overlap [K0,] K1..K5 of batch b; pinned host output"},
             "gpu_launches": launches,
             "clocks": clocks,
             "stage_ms_last_step": {k: round(v, 4) for k, v in stage_last.items()},
+            "value_incl_parse": (world * mp_per_step / ((ms_per_step + stage_last.get("k0_parse", 0.0)) * 1e-3)) if args.parser == "device" else None,
             "record_bytes_per_px": rec_bytes_per_px, "uploaded_bytes_per_px": upload_bytes / px,
             "parser": "K0 on the device (runs once per upload; `value` times K1..K5 with the records resident in HBM, k0_parse is "
                       "listed in stage_ms_last_step and is inside e2e)" if args.parser == "device" else "host CABAC parser",

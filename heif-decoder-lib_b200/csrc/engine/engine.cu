@@ -133,6 +133,7 @@ struct hc_batch {
   const uint32_t* d_k0_tb_index[4] = {nullptr, nullptr, nullptr, nullptr};
   int k0_tb_counts[4] = {0, 0, 0, 0};
   long long k0_list_cap[4] = {0, 0, 0, 0};
+  long long k0_max_ctbs = 0;
   bool k0_status_pending = false;                  // K0 ran; its status words were copied to h_status but not looked at yet
   std::vector<int> k0_pic_of;                      // K0 picture -> batch picture index
   Block h_status;
@@ -349,6 +350,7 @@ int hc_batch_upload(hc_batch* b) {
       p.resid_count = nctb * k->pic.resid_cap_ctb;
       p.resid_base = n_resid;         n_resid += align_up(p.resid_count, 8);
       b->k0_pic_of.push_back(i);
+      b->k0_max_ctbs = b->nk0 ? std::max<long long>(b->k0_max_ctbs, (long long)nctb) : (long long)nctb;
       b->nk0++;
     } else {
       const hc::PictureRecords& r = *b->pics[i].rec;
@@ -657,13 +659,14 @@ int hc_batch_reconstruct_async(hc_batch* b, int stages) {
     cudaMemsetAsync(D + b->k0_ones_off, 1, b->k0_ones_bytes, s);
     cudaMemsetAsync(D + b->k0_zero_off, 0, b->k0_zero_bytes, s);
     hc::launch_k0(b->eng->d_k0_tables, b->d_k0_pics, b->d_k0_subs, b->d_k0_chains, b->nchains, s);
+    hc::launch_k0_finish(b->d_k0_pics, b->nk0, (int)b->k0_max_ctbs, s);
     cudaEventRecord(b->ev_k0[1], s);
     const size_t status_bytes = 4 * ((size_t)b->nk0 + 4);
     if (!cuda_ok(cudaMemcpyAsync(b->h_status.p, D + b->k0_status_off, status_bytes, cudaMemcpyDeviceToHost, s), "cudaMemcpyAsync(K0 status)"))
       return HC_ERR_CUDA;
     b->k0_status_pending = true;
     b->k0_done = true;
-    b->launches += 1;
+    b->launches += 2;
   }
   cudaEventRecord(b->ev[2], s);
   hc::launch_k1(b->view, b->d_tb_index, b->tb_counts, s);

@@ -120,6 +120,7 @@ std::unique_ptr<PictureRecords> k0_parse_on_cpu(const K0HostPicture& hp, std::st
     if (error) break;
   }
   if (error) { if (err) *err = error == k0::ERR_CAPACITY ? "K0: per-CTB capacity exceeded" : "K0: malformed slice data"; return nullptr; }
+  for (size_t c = 0; c < nctb; c++) k0::finish_ctb(p, (int)c, 0, 1);   // second half of K0 (k0_finish_kernel on the device)
 
   // compact the fixed-capacity CTB slices into the host parser's sequential record form
   std::unique_ptr<PictureRecords> rec(new PictureRecords);

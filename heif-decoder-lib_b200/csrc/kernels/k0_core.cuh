@@ -281,6 +281,58 @@ HC_HD int morton4(int x, int y) {   // interleave 4 bits of x (even positions) a
   return (int)((v & 0xffu) | (v >> 7));
 }
 
+// ---- neighbour availability of one prediction block (intrapred.h:443-543, :838-940), no tiles: TS == RS ---------
+// Fills avail_left / avail_top / HC_BLK_AVAIL_TL of a record emitted by Parser::emit_blk. `p` may live anywhere.
+HC_HD void finish_blk(const Pic& p, hc_blk& b) {
+  const int cIdx = b.cidx, xB = b.x, yB = b.y, log2 = b.log2;
+  const int nT = 1 << log2;
+  const int SubW = cIdx == 0 ? 1 : p.sub_w, SubH = cIdx == 0 ? 1 : p.sub_h;
+  const int xBL = xB * SubW, yBL = yB * SubH;
+  const int l2c = p.log2_ctb, cw = p.ctbs_w;
+  const int sh2 = l2c - p.log2_min_tb, mask = (1 << l2c) - 1;
+  auto zs = [&](int x, int y) { return ((((x >> l2c) + (y >> l2c) * cw)) << (2 * sh2)) + morton4((x & mask) >> p.log2_min_tb, (y & mask) >> p.log2_min_tb); };
+  auto sa_of = [&](int n) { return p.nslices == 1 ? 0 : p.slices[p.ctb_slice[n]].slice_addr_rs; };
+  bool aL = true, aT = true, aTR = true, aTL = true;
+  if (xBL == 0) { aL = false; aTL = false; }
+  if (yBL == 0) { aT = false; aTL = false; aTR = false; }
+  if (xBL + nT * SubW >= p.W) aTR = false;
+  if (p.nslices != 1) {
+    const int xCur = xBL >> l2c, yCur = yBL >> l2c;
+    const int xLeft = (xBL - 1) >> l2c, xRight = (xBL + nT * SubW) >> l2c, yTop = (yBL - 1) >> l2c;
+    const int sa = sa_of(xCur + yCur * cw);
+    if (aL && sa_of(xLeft + yCur * cw) != sa) aL = false;
+    if (aT && sa_of(xCur + yTop * cw) != sa) aT = false;
+    if (aTL && sa_of(xLeft + yTop * cw) != sa) aTL = false;
+    if (aTR && sa_of(xRight + yTop * cw) != sa) aTR = false;
+  }
+  int nBottom = (p.H - yBL + SubH - 1) / SubH;
+  if (nBottom > 2 * nT) nBottom = 2 * nT;
+  int nRight = (p.W - xBL + SubW - 1) / SubW;
+  if (nRight > 2 * nT) nRight = 2 * nT;
+  const int currAddr = zs(xBL, yBL);
+  unsigned left = 0, top = 0;
+  if (aL) {
+    for (int y = nBottom - 1; y >= 0; y -= 4)
+      if (zs((xB - 1) * SubW, (yB + y) * SubH) <= currAddr) left |= 1u << (y >> 2);
+  }
+  bool tl = false;
+  if (aTL) tl = zs((xB - 1) * SubW, (yB - 1) * SubH) <= currAddr;
+  for (int x = 0; x < nRight; x += 4) {
+    const bool ba = x < nT ? aT : aTR;
+    if (ba && zs((xB + x) * SubW, (yB - 1) * SubH) <= currAddr) top |= 1u << (x >> 2);
+  }
+  b.flags = (uint8_t)((b.flags & ~HC_BLK_AVAIL_TL) | (tl ? HC_BLK_AVAIL_TL : 0));
+  b.avail_left = (uint16_t)left;
+  b.avail_top = (uint16_t)top;
+}
+
+// All blocks of one CTB, lanes [lane, lane + stride, ...] (host: lane 0, stride 1).
+HC_HD void finish_ctb(const Pic& p, int ctb, int lane, int stride) {
+  const hc_ctu& ctu = p.ctus[ctb];
+  for (int c = 0; c < 3; c++)
+    for (int k = lane; k < (int)ctu.blk_count[c]; k += stride) finish_blk(p, p.blks[ctu.blk_first[c] + k]);
+}
+
 // ---- the parser of one chain ---------------------------------------------------------------------------------
 struct Parser {
   // host build: the tables, picture, slice segment and scratch are reached through these pointers; the device build
@@ -461,54 +513,24 @@ struct Parser {
     }
   }
 
-  // neighbour availability of one prediction block (intrapred.h:443-543, :838-940)
-  K0_FN void emit_blk(int cIdx, int xB, int yB, int log2, int mode, bool has_resid, uint32_t resid_off) {
+  // One prediction block record. The neighbour availability masks (avail_left / avail_top / HC_BLK_AVAIL_TL) only
+  // depend on the block geometry and the slice layout, not on the parse, so they are filled in afterwards by a
+  // massively parallel pass (finish_blk below: k0_finish_kernel on the device) instead of by the serial chain.
+  HC_HD void emit_blk(int cIdx, int xB, int yB, int log2, int mode, bool has_resid, uint32_t resid_off) {
     const Pic& p = pic();
-    const int nT = 1 << log2;
-    const int SubW = cIdx == 0 ? 1 : p.sub_w, SubH = cIdx == 0 ? 1 : p.sub_h;
-    const int xBL = xB * SubW, yBL = yB * SubH;
-    bool aL = true, aT = true, aTR = true, aTL = true;
-    if (xBL == 0) { aL = false; aTL = false; }
-    if (yBL == 0) { aT = false; aTL = false; aTR = false; }
-    if (xBL + nT * SubW >= p.W) aTR = false;
-    const int l2c = p.log2_ctb, cw = p.ctbs_w;
-    const int xCur = xBL >> l2c, yCur = yBL >> l2c;
-    const int xLeft = (xBL - 1) >> l2c, xRight = (xBL + nT * SubW) >> l2c, yTop = (yBL - 1) >> l2c;
-    if (p.nslices != 1) {
-      const int sa = slice_addr_of_ctb(xCur + yCur * cw);
-      if (aL && slice_addr_of_ctb(xLeft + yCur * cw) != sa) aL = false;
-      if (aT && slice_addr_of_ctb(xCur + yTop * cw) != sa) aT = false;
-      if (aTL && slice_addr_of_ctb(xLeft + yTop * cw) != sa) aTL = false;
-      if (aTR && slice_addr_of_ctb(xRight + yTop * cw) != sa) aTR = false;
-    }
-    int nBottom = (p.H - yBL + SubH - 1) / SubH;
-    if (nBottom > 2 * nT) nBottom = 2 * nT;
-    int nRight = (p.W - xBL + SubW - 1) / SubW;
-    if (nRight > 2 * nT) nRight = 2 * nT;
-    const int currAddr = zs_addr(xBL, yBL);
-    unsigned left = 0, top = 0;
-    if (aL) {
-      K0_LOOP for (int y = nBottom - 1; y >= 0; y -= 4)
-        if (zs_addr((xB - 1) * SubW, (yB + y) * SubH) <= currAddr) left |= 1u << (y >> 2);
-    }
-    bool tl = false;
-    if (aTL) tl = zs_addr((xB - 1) * SubW, (yB - 1) * SubH) <= currAddr;
-    K0_LOOP for (int x = 0; x < nRight; x += 4) {
-      const bool ba = x < nT ? aT : aTR;
-      if (ba && zs_addr((xB + x) * SubW, (yB - 1) * SubH) <= currAddr) top |= 1u << (x >> 2);
-    }
     if (nblk[cIdx] >= p.blk_cap[cIdx]) { fail(ERR_CAPACITY); return; }
     uint32_t base = (uint32_t)ctb_rs * p.blk_cap_ctb;
-    K0_LOOP for (int c = 0; c < cIdx; c++) base += p.blk_cap[c];
+    if (cIdx > 0) base += p.blk_cap[0];
+    if (cIdx > 1) base += p.blk_cap[1];
     hc_blk b;
     b.x = (uint16_t)xB;
     b.y = (uint16_t)yB;
     b.log2 = (uint8_t)log2;
     b.mode = (uint8_t)mode;
-    b.flags = (uint8_t)((tl ? HC_BLK_AVAIL_TL : 0) | (has_resid ? HC_BLK_HAS_RESID : 0));
+    b.flags = (uint8_t)(has_resid ? HC_BLK_HAS_RESID : 0);
     b.cidx = (uint8_t)cIdx;
-    b.avail_left = (uint16_t)left;
-    b.avail_top = (uint16_t)top;
+    b.avail_left = 0;
+    b.avail_top = 0;
     b.resid_off = has_resid ? resid_off : 0;
     p.blks[base + nblk[cIdx]++] = b;
   }

@@ -40,6 +40,27 @@ __global__ void __launch_bounds__(32 * K0_WARPS, MIN_CTAS) k0_parse_kernel(const
   ps.run_chain(pics, subs, ch.first_sub, ch.nsubs);
 }
 
+// Second, fully parallel half of K0: the neighbour availability masks of every block record (k0_core.cuh: finish_blk),
+// one warp per CTB, the picture descriptor in shared memory.
+__global__ void __launch_bounds__(256) k0_finish_kernel(const k0::Pic* __restrict__ pics) {
+  __shared__ k0::Pic sp;
+  {
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(pics + blockIdx.y);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(&sp);
+    for (int i = threadIdx.x; i < (int)(sizeof(k0::Pic) / 4); i += blockDim.x) dst[i] = src[i];
+  }
+  __syncthreads();
+  const int ctb = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (ctb >= sp.ctbs_w * sp.ctbs_h || *sp.error) return;
+  k0::finish_ctb(sp, ctb, threadIdx.x & 31, 32);
+}
+
+void launch_k0_finish(const k0::Pic* pics, int npics, int max_ctbs, cudaStream_t stream) {
+  if (npics <= 0 || max_ctbs <= 0) return;
+  static_assert(sizeof(k0::Pic) % 4 == 0, "descriptor is copied word-wise");
+  k0_finish_kernel<<<dim3((unsigned)((max_ctbs + 7) / 8), (unsigned)npics), 256, 0, stream>>>(pics);
+}
+
 void launch_k0(const k0::Tables* tables, const k0::Pic* pics, const k0::Sub* subs, const k0::Chain* chains, int nchains,
                cudaStream_t stream) {
   if (nchains <= 0) return;

@@ -27,6 +27,7 @@ namespace k0 { struct Tables; struct Pic; struct Sub; struct Chain; }
 // K0: device CABAC parse of the pictures added as bitstreams (one CTA per substream chain)
 void launch_k0(const k0::Tables* tables, const k0::Pic* pics, const k0::Sub* subs, const k0::Chain* chains, int nchains,
                cudaStream_t stream);
+void launch_k0_finish(const k0::Pic* pics, int npics, int max_ctbs, cudaStream_t stream);
 void launch_k1(const BatchView& bv, const uint32_t* const tb_index[4], const int counts[4], cudaStream_t stream);
 // lists built on the device (K0): capacity[l] entries at most, the real lengths are d_counts[0..3] in device memory
 void launch_k1_indirect(const BatchView& bv, const uint32_t* const tb_index[4], const long long capacity[4], const unsigned* d_counts,
