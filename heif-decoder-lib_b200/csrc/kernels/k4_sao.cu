@@ -172,9 +172,8 @@ __device__ __forceinline__ void sao_picture(const BatchView& bv, const hc_pic& p
       } else {
         const int lwid = min(1 << log2w, width - (ctbx << log2w)), lhei = min(1 << log2h, height - (ctby << log2h));
         const int ly = y & mh;
-#pragma unroll
-        for (int k = 0; k < 8; k++) {
-          if (k >= nvalid || ((skip >> k) & 1)) continue;
+        // may sample x0 + k use both of its neighbours? (picture edge, neighbouring CTB not usable, reference quirk)
+        auto sample_ok = [&](int k) -> bool {
           const int x = x0 + k;
           bool ok = true;
 #pragma unroll
@@ -195,7 +194,23 @@ __device__ __forceinline__ void sao_picture(const BatchView& bv, const hc_pic& p
               if (lx == 0 || ly == 0 || lx == lwid - 1 || ly == lhei - 1) ok = false;
             }
           }
-          if (!ok) continue;
+          return ok;
+        };
+        unsigned okmask = 0;
+        if (nvalid == 8 && !self_quirk) {
+          // a full unit lies inside one CTB column: samples 1..6 have both neighbours in that column, so they share one
+          // verdict (only the row above / below can be foreign); samples 0 and 7 may also look into the CTB beside
+          const bool ok0 = sample_ok(0), okm = sample_ok(1), ok7 = sample_ok(7);
+          okmask = (ok0 ? 1u : 0u) | (okm ? 0x7eu : 0u) | (ok7 ? 0x80u : 0u);
+        } else {
+#pragma unroll
+          for (int k = 0; k < 8; k++)
+            if (k < nvalid && sample_ok(k)) okmask |= 1u << k;
+        }
+        okmask &= ~skip;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+          if (!((okmask >> k) & 1)) continue;
           const int a = hx < 0 ? ra[k] : (hx == 0 ? ra[k + 1] : ra[k + 2]);
           const int b = hx < 0 ? rb[k + 2] : (hx == 0 ? rb[k + 1] : rb[k]);
           const int e = sign3(orig[k] - a) + sign3(orig[k] - b);   // -2..2

@@ -26,17 +26,18 @@ HC_D int clip_f(float fx, int maxi) {
   return x < 0 ? 0 : (x > maxi ? maxi : (int)x);
 }
 
-template <typename Pixel>
-__device__ void convert_px(const CscArgs& a, int yv, int cbv, int crv, int& r, int& g, int& b) {
+// MODE is a compile-time constant at every call site (the per-pixel loop is instantiated once per conversion mode)
+template <typename Pixel, int MODE>
+__device__ __forceinline__ void convert_px(const CscArgs& a, int yv, int cbv, int crv, int& r, int& g, int& b) {
   const hc_csc_params& p = a.p;
   const int bpp = p.bit_depth;
   const int maxv = (1 << bpp) - 1, half = 1 << (bpp - 1);
-  if (p.mode == HC_CSC_INT420) {
+  if (MODE == HC_CSC_INT420) {
     const int cb = cbv - 128, cr = crv - 128;
     r = clip3i(0, 255, yv + ((p.r_cr_i * cr + 128) >> 8));
     g = clip3i(0, 255, yv + ((p.g_cb_i * cb + p.g_cr_i * cr + 128) >> 8));
     b = clip3i(0, 255, yv + ((p.b_cb_i * cb + 128) >> 8));
-  } else if (p.mode == HC_CSC_FLOAT) {
+  } else if (MODE == HC_CSC_FLOAT) {
     float fy = (float)yv, cb = (float)(cbv - half), cr = (float)(crv - half);
     if (!p.full_range) {
       fy = __fmul_rn(__fsub_rn(fy, (float)(16 << (bpp - 8))), 1.1689f);
@@ -46,7 +47,7 @@ __device__ void convert_px(const CscArgs& a, int yv, int cbv, int crv, int& r, i
     r = clip_f(__fadd_rn(fy, __fmul_rn(p.r_cr, cr)), maxv);
     g = clip_f(__fadd_rn(__fadd_rn(fy, __fmul_rn(p.g_cb, cb)), __fmul_rn(p.g_cr, cr)), maxv);
     b = clip_f(__fadd_rn(fy, __fmul_rn(p.b_cb, cb)), maxv);
-  } else if (p.mode == HC_CSC_GBR) {
+  } else if (MODE == HC_CSC_GBR) {
     if (p.full_range) { r = crv; g = yv; b = cbv; }
     else {
       const float off = (float)(16 << (bpp - 8));
@@ -143,10 +144,21 @@ __device__ __forceinline__ void csc_unit(const CscArgs& a, unsigned tid) {
   }
 
   int R[8], G[8], B[8];
+  if (!a.chroma_format) {
 #pragma unroll
-  for (int k = 0; k < 8; k++) {
-    if (a.chroma_format) convert_px<Pixel>(a, Y[k], Cb[k], Cr[k], R[k], G[k], B[k]);
-    else { R[k] = G[k] = B[k] = Y[k]; }
+    for (int k = 0; k < 8; k++) R[k] = G[k] = B[k] = Y[k];
+  } else if (a.p.mode == HC_CSC_INT420) {
+#pragma unroll
+    for (int k = 0; k < 8; k++) convert_px<Pixel, HC_CSC_INT420>(a, Y[k], Cb[k], Cr[k], R[k], G[k], B[k]);
+  } else if (a.p.mode == HC_CSC_FLOAT) {
+#pragma unroll
+    for (int k = 0; k < 8; k++) convert_px<Pixel, HC_CSC_FLOAT>(a, Y[k], Cb[k], Cr[k], R[k], G[k], B[k]);
+  } else if (a.p.mode == HC_CSC_GBR) {
+#pragma unroll
+    for (int k = 0; k < 8; k++) convert_px<Pixel, HC_CSC_GBR>(a, Y[k], Cb[k], Cr[k], R[k], G[k], B[k]);
+  } else {
+#pragma unroll
+    for (int k = 0; k < 8; k++) convert_px<Pixel, HC_CSC_YCGCO>(a, Y[k], Cb[k], Cr[k], R[k], G[k], B[k]);
   }
 
   uint8_t* orow = a.out + (size_t)y * a.out_stride;
