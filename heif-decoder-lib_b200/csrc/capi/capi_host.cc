@@ -1,4 +1,5 @@
 // capi_host.cc — C ABI over the host front-end (include/heifcuda.h, section "host front-end").
+#include <algorithm>
 #include "capi_internal.h"
 #include "../host/k0_host.h"
 #include <cstdlib>
@@ -127,6 +128,9 @@ int hc_heif_get_image_info(const hc_heif* f, uint32_t id, hc_heif_image_info* in
   info->alpha_id = f->file.alpha_item(id);
   info->rot = it->rot;
   info->mirror = it->mirror;
+  info->n_transforms = (int32_t)std::min<size_t>(it->xforms.size(), 8);
+  for (int k = 0; k < info->n_transforms; k++) info->transforms[k] = it->xforms[k];
+  info->has_clap = it->has_clap;
   info->nclx_present = it->nclx.present;
   info->primaries = it->nclx.primaries;
   info->transfer = it->nclx.transfer;

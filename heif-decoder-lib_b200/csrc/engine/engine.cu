@@ -92,6 +92,13 @@ struct Canvas {
   size_t off[4] = {0, 0, 0, 0};     // byte offsets in the plane pool
   int stride[4] = {0, 0, 0, 0};     // samples
   int pw[4] = {0, 0, 0, 0}, ph[4] = {0, 0, 0, 0};
+  // geometric transform between K4 and K5 (irot / imir): the "output view" below is what K5 and the read-backs use;
+  // without a transform it is the canvas itself
+  int xf_swap = 0, xf_fx = 0, xf_fy = 0;
+  bool transformed() const { return xf_swap || xf_fx || xf_fy; }
+  int ow = 0, oh = 0;               // output image size
+  size_t ooff[4] = {0, 0, 0, 0};
+  int ostride[4] = {0, 0, 0, 0}, opw[4] = {0, 0, 0, 0}, oph[4] = {0, 0, 0, 0};
   // rgb output of the last convert
   size_t rgb_off = 0;
   size_t rgb_stride = 0;
@@ -273,6 +280,14 @@ int hc_batch_add_canvas(hc_batch* b, int width, int height, int chroma_format, i
   return (int)b->canvases.size() - 1;
 }
 
+int hc_batch_set_canvas_transform(hc_batch* b, int canvas, int swap, int flip_x, int flip_y) {
+  if (!b || canvas < 0 || canvas >= (int)b->canvases.size()) { hc::set_last_error("hc_batch_set_canvas_transform: bad argument"); return HC_ERR_ARGUMENT; }
+  Canvas& c = b->canvases[canvas];
+  c.xf_swap = swap != 0; c.xf_fx = flip_x != 0; c.xf_fy = flip_y != 0;
+  b->uploaded = false;
+  return HC_OK;
+}
+
 static int add_picture(hc_batch* b, const hc::PictureRecords* rec, const hc::K0HostPicture* k0, int canvas, int x, int y, int role,
                        int rescale_limited) {
   if (!b || (!rec && !k0) || canvas < 0 || canvas >= (int)b->canvases.size() || x < 0 || y < 0) {
@@ -328,6 +343,17 @@ int hc_batch_upload(hc_batch* b) {
       pool += align_up((size_t)c.stride[k] * c.ph[k] * ps, 256);
     }
     c.converted = false;
+    c.ow = c.xf_swap ? c.h : c.w;
+    c.oh = c.xf_swap ? c.w : c.h;
+    for (int k = 0; k < 4; k++) {
+      c.ooff[k] = c.off[k]; c.ostride[k] = c.stride[k]; c.opw[k] = c.pw[k]; c.oph[k] = c.ph[k];
+      if (!c.transformed() || c.pw[k] == 0 || (k == 3 && !c.alpha)) continue;
+      c.opw[k] = c.xf_swap ? c.ph[k] : c.pw[k];
+      c.oph[k] = c.xf_swap ? c.pw[k] : c.ph[k];
+      c.ostride[k] = (int)(align_up((size_t)(c.opw[k] + 4) * ps, 128) / ps);
+      c.ooff[k] = pool;
+      pool += align_up((size_t)c.ostride[k] * c.oph[k] * ps, 256);
+    }
   }
   // ---- record bases ----
   size_t n_ctu = 0, n_blk = 0, n_tb = 0, n_coeff = 0, n_edge = 0, n_qp = 0, n_scal = 0;
@@ -689,6 +715,20 @@ int hc_batch_reconstruct_async(hc_batch* b, int stages) {
   v.flags = (stages & HC_STAGE_SAO) ? 0 : hc::HC_VIEW_NO_SAO;
   hc::launch_k4(v, b->max_sao_quads, b->max_planes, s);
   b->launches += 1;
+  // K6: irot / imir of the canvases that carry a transform, plane by plane (rare; timed with K4)
+  for (const Canvas& c : b->canvases) {
+    if (!c.transformed()) continue;
+    for (int k = 0; k < 4; k++) {
+      if (c.pw[k] == 0 || (k == 3 && !c.alpha)) continue;
+      hc::XformArgs a;
+      a.src = (const uint8_t*)b->d_planes.p + c.off[k];
+      a.dst = (uint8_t*)b->d_planes.p + c.ooff[k];
+      a.w = c.pw[k]; a.h = c.ph[k]; a.src_stride = c.stride[k]; a.dst_stride = c.ostride[k];
+      a.swap = c.xf_swap; a.flip_x = c.xf_fx; a.flip_y = c.xf_fy;
+      hc::launch_k6(a, c.bit_depth != 8, s);
+      b->launches += 1;
+    }
+  }
   cudaEventRecord(b->ev[6], s);
   if (!cuda_ok(cudaGetLastError(), "kernel launch")) return HC_ERR_CUDA;
   return HC_OK;
@@ -716,13 +756,13 @@ int hc_batch_convert(hc_batch* b, int canvas, const hc_csc_params* params) {
     return HC_ERR_UNSUPPORTED;
   }
   c.rgb_bpp = bpp_of[params->out_format];
-  c.rgb_stride = align_up((size_t)((c.w + 7) & ~7) * c.rgb_bpp, 256);
+  c.rgb_stride = align_up((size_t)((c.ow + 7) & ~7) * c.rgb_bpp, 256);
   // lay all canvases' rgb buffers out in one block (grow if needed)
   size_t total = 0;
   for (auto& cv : b->canvases) {
     const int bp = &cv == &c ? c.rgb_bpp : (cv.rgb_bpp ? cv.rgb_bpp : (cv.bit_depth == 8 ? 4 : 8));
     cv.rgb_off = total;
-    total += align_up(align_up((size_t)((cv.w + 7) & ~7) * bp, 256) * cv.h, 256);
+    total += align_up(align_up((size_t)((cv.ow + 7) & ~7) * bp, 256) * cv.oh, 256);
   }
   if (b->d_rgb.cap < total) {
     bool any = false;
@@ -734,12 +774,12 @@ int hc_batch_convert(hc_batch* b, int canvas, const hc_csc_params* params) {
   }
   hc::CscArgs a;
   const uint8_t* P = (const uint8_t*)b->d_planes.p;
-  a.y = P + c.off[0];
-  a.cb = c.chroma ? P + c.off[1] : nullptr;
-  a.cr = c.chroma ? P + c.off[2] : nullptr;
-  a.a = c.alpha ? P + c.off[3] : nullptr;
-  a.y_stride = c.stride[0]; a.c_stride = c.stride[1]; a.a_stride = c.stride[3];
-  a.width = c.w; a.height = c.h; a.chroma_format = c.chroma;
+  a.y = P + c.ooff[0];
+  a.cb = c.chroma ? P + c.ooff[1] : nullptr;
+  a.cr = c.chroma ? P + c.ooff[2] : nullptr;
+  a.a = c.alpha ? P + c.ooff[3] : nullptr;
+  a.y_stride = c.ostride[0]; a.c_stride = c.ostride[1]; a.a_stride = c.ostride[3];
+  a.width = c.ow; a.height = c.oh; a.chroma_format = c.chroma;
   a.out = (uint8_t*)b->d_rgb.p + c.rgb_off;
   a.out_stride = (long long)c.rgb_stride;
   a.p = *params;
@@ -773,13 +813,13 @@ int hc_batch_convert_many(hc_batch* b, int n, const int* canvases, const hc_csc_
       return HC_ERR_UNSUPPORTED;
     }
     c.rgb_bpp = bpp_of[params[i].out_format];
-    c.rgb_stride = align_up((size_t)((c.w + 7) & ~7) * c.rgb_bpp, 256);
+    c.rgb_stride = align_up((size_t)((c.ow + 7) & ~7) * c.rgb_bpp, 256);
   }
   size_t total = 0;
   for (auto& cv : b->canvases) {
     const int bp = cv.rgb_bpp ? cv.rgb_bpp : (cv.bit_depth == 8 ? 4 : 8);
     cv.rgb_off = total;
-    total += align_up(align_up((size_t)((cv.w + 7) & ~7) * bp, 256) * cv.h, 256);
+    total += align_up(align_up((size_t)((cv.ow + 7) & ~7) * bp, 256) * cv.oh, 256);
   }
   if (b->d_rgb.cap < total) {
     b->eng->give(b->eng->free_dev, b->d_rgb);
@@ -798,12 +838,12 @@ int hc_batch_convert_many(hc_batch* b, int n, const int* canvases, const hc_csc_
       if (i < n && (b->canvases[canvases[i]].bit_depth != 8) == (sixteen != 0)) {
         Canvas& c = b->canvases[canvases[i]];
         hc::CscArgs& a = cb.a[cb.n++];
-        a.y = P + c.off[0];
-        a.cb = c.chroma ? P + c.off[1] : nullptr;
-        a.cr = c.chroma ? P + c.off[2] : nullptr;
-        a.a = c.alpha ? P + c.off[3] : nullptr;
-        a.y_stride = c.stride[0]; a.c_stride = c.stride[1]; a.a_stride = c.stride[3];
-        a.width = c.w; a.height = c.h; a.chroma_format = c.chroma;
+        a.y = P + c.ooff[0];
+        a.cb = c.chroma ? P + c.ooff[1] : nullptr;
+        a.cr = c.chroma ? P + c.ooff[2] : nullptr;
+        a.a = c.alpha ? P + c.ooff[3] : nullptr;
+        a.y_stride = c.ostride[0]; a.c_stride = c.ostride[1]; a.a_stride = c.ostride[3];
+        a.width = c.ow; a.height = c.oh; a.chroma_format = c.chroma;
         a.out = (uint8_t*)b->d_rgb.p + c.rgb_off;
         a.out_stride = (long long)c.rgb_stride;
         a.p = params[i];
@@ -839,8 +879,8 @@ int hc_batch_read_plane(hc_batch* b, int canvas, int plane, void* dst, size_t ds
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0); cudaEventCreate(&e1);
   cudaEventRecord(e0, b->stream);
-  cudaError_t e = cudaMemcpy2DAsync(dst, dst_stride, (const uint8_t*)b->d_planes.p + c.off[plane], (size_t)c.stride[plane] * ps,
-                                    (size_t)c.pw[plane] * ps, c.ph[plane], cudaMemcpyDeviceToHost, b->stream);
+  cudaError_t e = cudaMemcpy2DAsync(dst, dst_stride, (const uint8_t*)b->d_planes.p + c.ooff[plane], (size_t)c.ostride[plane] * ps,
+                                    (size_t)c.opw[plane] * ps, c.oph[plane], cudaMemcpyDeviceToHost, b->stream);
   cudaEventRecord(e1, b->stream);
   if (!cuda_ok(e, "cudaMemcpy2DAsync(D2H plane)")) return HC_ERR_CUDA;
   if (int rc = batch_sync_checked(b, "cudaStreamSynchronize")) return rc;
@@ -856,7 +896,7 @@ int hc_batch_read_rgb(hc_batch* b, int canvas, void* dst, size_t dst_stride) {
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0); cudaEventCreate(&e1);
   cudaEventRecord(e0, b->stream);
-  cudaError_t e = cudaMemcpy2DAsync(dst, dst_stride, (const uint8_t*)b->d_rgb.p + c.rgb_off, c.rgb_stride, (size_t)c.w * c.rgb_bpp, c.h,
+  cudaError_t e = cudaMemcpy2DAsync(dst, dst_stride, (const uint8_t*)b->d_rgb.p + c.rgb_off, c.rgb_stride, (size_t)c.ow * c.rgb_bpp, c.oh,
                                     cudaMemcpyDeviceToHost, b->stream);
   cudaEventRecord(e1, b->stream);
   if (!cuda_ok(e, "cudaMemcpy2DAsync(D2H rgb)")) return HC_ERR_CUDA;
@@ -870,7 +910,7 @@ int hc_batch_copy_rgb_device(hc_batch* b, int canvas, void* dst, size_t dst_stri
   if (!b || !dst || canvas < 0 || canvas >= (int)b->canvases.size()) { hc::set_last_error("hc_batch_copy_rgb_device: bad argument"); return HC_ERR_ARGUMENT; }
   const Canvas& c = b->canvases[canvas];
   if (!c.converted) { hc::set_last_error("canvas was not converted"); return HC_ERR_ARGUMENT; }
-  cudaError_t e = cudaMemcpy2DAsync(dst, dst_stride, (const uint8_t*)b->d_rgb.p + c.rgb_off, c.rgb_stride, (size_t)c.w * c.rgb_bpp, c.h,
+  cudaError_t e = cudaMemcpy2DAsync(dst, dst_stride, (const uint8_t*)b->d_rgb.p + c.rgb_off, c.rgb_stride, (size_t)c.ow * c.rgb_bpp, c.oh,
                                     cudaMemcpyDeviceToDevice, b->stream);
   if (!cuda_ok(e, "cudaMemcpy2DAsync(D2D rgb)")) return HC_ERR_CUDA;
   return batch_sync_checked(b, "cudaStreamSynchronize");
@@ -880,7 +920,7 @@ int hc_batch_read_rgb_async(hc_batch* b, int canvas, void* dst, size_t dst_strid
   if (!b || !dst || canvas < 0 || canvas >= (int)b->canvases.size()) { hc::set_last_error("hc_batch_read_rgb_async: bad argument"); return HC_ERR_ARGUMENT; }
   const Canvas& c = b->canvases[canvas];
   if (!c.converted) { hc::set_last_error("canvas was not converted"); return HC_ERR_ARGUMENT; }
-  cudaError_t e = cudaMemcpy2DAsync(dst, dst_stride, (const uint8_t*)b->d_rgb.p + c.rgb_off, c.rgb_stride, (size_t)c.w * c.rgb_bpp, c.h,
+  cudaError_t e = cudaMemcpy2DAsync(dst, dst_stride, (const uint8_t*)b->d_rgb.p + c.rgb_off, c.rgb_stride, (size_t)c.ow * c.rgb_bpp, c.oh,
                                     cudaMemcpyDeviceToHost, b->stream);
   return cuda_ok(e, "cudaMemcpy2DAsync(D2H rgb)") ? HC_OK : HC_ERR_CUDA;
 }

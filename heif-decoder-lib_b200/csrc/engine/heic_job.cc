@@ -240,6 +240,37 @@ static hc_heic_job* job_create(hc_engine* e, int nfiles, const uint8_t* const* d
       }
       if (add_item(j->batch, j->items[im.alpha], im.canvas, 0, 0, HC_ROLE_ALPHA, 0) < 0) return nullptr;
     }
+    // ---- irot / imir of the image item, in ipma order (context.cc:1955-1978); composed into one dihedral map ----
+    {
+      const hc::HeifItem* pit = j->files[im.file]->item(im.info.id);
+      int swap = 0, fx = 0, fy = 0;
+      if (pit) {
+        if (pit->has_clap) { hc::set_last_error("clean-aperture (clap) transformations are not supported"); return nullptr; }
+        for (uint8_t op : pit->xforms) {
+          const int s2 = (op == HC_XF_ROT90 || op == HC_XF_ROT270) ? 1 : 0;
+          const int fx2 = (op == HC_XF_ROT90 || op == HC_XF_ROT180 || op == HC_XF_MIRROR_H) ? 1 : 0;
+          const int fy2 = (op == HC_XF_ROT270 || op == HC_XF_ROT180 || op == HC_XF_MIRROR_V) ? 1 : 0;
+          if ((op == HC_XF_MIRROR_H || op == HC_XF_MIRROR_V) && p0.bit_depth_y != 8) {
+            hc::set_last_error("Can currently only mirror images with 8 bits per pixel");   // pixelimage.cc:748-752
+            return nullptr;
+          }
+          // out2(x, y) = out1(x1, y1): see hc_batch_set_canvas_transform for the map of one operation
+          const int nfx = swap ? (fx ^ fy2) : (fx ^ fx2), nfy = swap ? (fy ^ fx2) : (fy ^ fy2);
+          swap ^= s2; fx = nfx; fy = nfy;
+        }
+      }
+      if (swap | fx | fy) {
+        if (band_end >= 0) { hc::set_last_error("banded decode of transformed images is not supported"); return nullptr; }
+        if (swap && p0.chroma_format == 2) { hc::set_last_error("quarter turns of 4:2:2 images are not supported"); return nullptr; }
+        if (has_alpha) {
+          // the alpha item carries its own properties in the reference (context.cc:2040); only identical ones are supported
+          const hc::HeifItem* ait = j->files[im.file]->item(im.info.alpha_id);
+          if (!ait || ait->xforms != pit->xforms) { hc::set_last_error("alpha image with different transformations than its colour image"); return nullptr; }
+        }
+        if (hc_batch_set_canvas_transform(j->batch, im.canvas, swap, fx, fy) != HC_OK) return nullptr;
+        if (swap) std::swap(W, H);
+      }
+    }
     const bool hdr = p0.bit_depth_y != 8;
     const int fmt = hdr ? (j->want_alpha ? HC_OUT_RRGGBBAA_LE : HC_OUT_RRGGBB_LE) : (j->want_alpha ? HC_OUT_RGBA : HC_OUT_RGB);
     if (hc_csc_select(matrix, primaries, full, p0.chroma_format, p0.bit_depth_y, has_alpha, fmt, &im.csc) != HC_OK) return nullptr;

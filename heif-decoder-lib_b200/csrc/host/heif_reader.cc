@@ -239,8 +239,10 @@ std::string HeifFile::parse(const uint8_t* data, size_t size) {
         }
       } else if (p.type == fourcc("irot")) {
         item.rot = (int)(c.u8() & 3);
+        if (item.rot) item.xforms.push_back((uint8_t)item.rot);
       } else if (p.type == fourcc("imir")) {
         item.mirror = (int)(c.u8() & 1);
+        item.xforms.push_back((uint8_t)(item.mirror ? 4 : 5));   // box.cc:3626-3636: axis & 1 -> "horizontal"
       } else if (p.type == fourcc("clap")) {
         item.has_clap = true;
       } else if (p.type == fourcc("auxC")) {

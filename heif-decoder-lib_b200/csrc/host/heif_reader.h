@@ -39,6 +39,8 @@ struct HeifItem {
   int rot = 0;                  // irot: anti-clockwise quarter turns
   int mirror = -1;              // imir: -1 none, 0 vertical axis, 1 horizontal axis
   bool has_clap = false;
+  std::vector<uint8_t> xforms;  // irot / imir in ipma order (context.cc:1955-1978): 1..3 = quarter turns anti-clockwise,
+                                // 4 = mirror direction horizontal (rows reversed), 5 = vertical (row order reversed)
   std::string aux_type;         // auxC
   int pixi_bits = 0;
 };

@@ -23,6 +23,15 @@ struct CscBatch {
   int n;
 };
 
+// K6: one plane through one dihedral map (see hc_batch_set_canvas_transform); strides in samples
+struct XformArgs {
+  const uint8_t* src;
+  uint8_t* dst;
+  int w, h;                  // input plane size
+  int src_stride, dst_stride;
+  int swap, flip_x, flip_y;
+};
+
 namespace k0 { struct Tables; struct Pic; struct Sub; struct Chain; }
 // K0: device CABAC parse of the pictures added as bitstreams (one CTA per substream chain)
 void launch_k0(const k0::Tables* tables, const k0::Pic* pics, const k0::Sub* subs, const k0::Chain* chains, int nchains,
@@ -40,5 +49,6 @@ void launch_k3(const BatchView& bv, long long max_units, int planes, cudaStream_
 void launch_k4(const BatchView& bv, long long max_ctbs, int planes, cudaStream_t stream);
 void launch_k5(const CscArgs& a, bool sixteen_bit, cudaStream_t stream);
 void launch_k5_batch(const CscBatch& b, bool sixteen_bit, cudaStream_t stream);
+void launch_k6(const XformArgs& a, bool sixteen_bit, cudaStream_t stream);
 
 }  // namespace hc

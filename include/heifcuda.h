@@ -113,7 +113,15 @@ typedef struct hc_heif_image_info {
   int32_t mirror;              /* imir: -1 none, 0 vertical axis, 1 horizontal axis             */
   int32_t nclx_present;        /* container colr(nclx) overrides the bitstream VUI              */
   int32_t primaries, transfer, matrix, full_range;
+  int32_t n_transforms;        /* irot / imir properties in ipma order (the order the reference applies them) */
+  uint8_t transforms[8];       /* HC_XF_*                                                                     */
+  int32_t has_clap;            /* a clean-aperture crop is present (not applied by this library)             */
 } hc_heif_image_info;
+#define HC_XF_ROT90 1          /* anti-clockwise quarter turns, HeifPixelImage::rotate_ccw pixelimage.cc:539 */
+#define HC_XF_ROT180 2
+#define HC_XF_ROT270 3
+#define HC_XF_MIRROR_H 4       /* heif_transform_mirror_direction_horizontal: every row reversed (:778-783)  */
+#define HC_XF_MIRROR_V 5       /* ..._vertical: row order reversed (:784-789)                                */
 
 /* `data` must stay valid until hc_heif_close. NULL + error text on malformed files. */
 hc_heif* hc_heif_open(const uint8_t* data, size_t size);
@@ -205,6 +213,12 @@ int hc_batch_reconstruct(hc_batch* b, int stages);
 /* Same, never waits: a K0 parse error is reported by the next synchronising call on the batch (hc_batch_sync,
  * hc_batch_read_*, hc_batch_stage_ms). */
 int hc_batch_reconstruct_async(hc_batch* b, int stages);
+/* Geometric transform of a canvas between K4 and K5 (irot / imir of the reference, applied plane by plane like
+ * HeifPixelImage::rotate_ccw / mirror_inplace): output sample (x', y') of a plane of w x h input samples is input
+ * sample (sx, sy) with  !swap: sx = flip_x ? w-1-x' : x', sy = flip_y ? h-1-y' : y'   (output w x h)
+ *                        swap: sx = flip_x ? w-1-y' : y', sy = flip_y ? h-1-x' : x'   (output h x w).
+ * Call before hc_batch_upload. hc_batch_convert / read_rgb / read_plane then see the transformed canvas. */
+int hc_batch_set_canvas_transform(hc_batch* b, int canvas, int swap, int flip_x, int flip_y);
 /* K5 for one canvas into the engine's device RGB buffer, async */
 int hc_batch_convert(hc_batch* b, int canvas, const hc_csc_params* params);
 /* K5 for n canvases (canvases[i] with params[i]) in as few launches as possible, async */

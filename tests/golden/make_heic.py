@@ -53,6 +53,20 @@ def build():
     files["alpha_422_12"] = heif_writer.single_image(enc(200, 120, 2, 12, 22), 200, 120, 2, 12, alpha_stream=enc(200, 120, 0, 12, 23))
     files["alpha_444_8_limited"] = heif_writer.single_image(enc(200, 120, 3, 8, 24, full_range=0), 200, 120, 3, 8,
                                                             alpha_stream=enc(200, 120, 1, 8, 25), alpha_chroma_format=1)
+    # geometric transformations: irot / imir on single images, grids, odd sizes, alpha, 10 bit
+    W = heif_writer
+    files["irot90_420_8_odd"] = W.single_image(enc(263, 199, 1, 8, 30), 263, 199, 1, 8, transforms=(W.irot(1),))
+    files["irot180_420_8"] = W.single_image(enc(264, 200, 1, 8, 31), 264, 200, 1, 8, transforms=(W.irot(2),))
+    files["irot270_444_8"] = W.single_image(enc(200, 120, 3, 8, 32), 200, 120, 3, 8, transforms=(W.irot(3),))
+    files["imir_h_420_8_odd"] = W.single_image(enc(263, 199, 1, 8, 33), 263, 199, 1, 8, transforms=(W.imir(1),))
+    files["imir_v_422_8"] = W.single_image(enc(200, 120, 2, 8, 34), 200, 120, 2, 8, transforms=(W.imir(0),))
+    files["irot90_imir_420_8"] = W.single_image(enc(264, 200, 1, 8, 35), 264, 200, 1, 8, transforms=(W.irot(1), W.imir(1)))
+    files["imir_irot270_420_8"] = W.single_image(enc(264, 200, 1, 8, 36), 264, 200, 1, 8, transforms=(W.imir(0), W.irot(3)))
+    files["grid_irot90_300x200"] = W.synth_grid_heic(300, 200, tile=128, seed=37, transforms=(W.irot(1),))
+    files["grid_irot270_imir_301x199"] = W.synth_grid_heic(301, 199, tile=128, seed=38, transforms=(W.irot(3), W.imir(1)))
+    files["irot90_420_10"] = W.single_image(enc(200, 120, 1, 10, 39), 200, 120, 1, 10, transforms=(W.irot(1),))
+    files["alpha_irot90_420_8"] = W.single_image(enc(200, 120, 1, 8, 40), 200, 120, 1, 8, alpha_stream=enc(200, 120, 0, 8, 41),
+                                                 transforms=(W.irot(1),))
     return files
 
 

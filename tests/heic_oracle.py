@@ -75,8 +75,22 @@ def decode_planes(data, item_id=None):
     if info.alpha_id:
         a = hb.parse_picture(hf.coded_stream(info.alpha_id), host_only=True)
         apl, _ = oracle_lib.reconstruct(a)
-        alpha = apl[0]
+        alpha = _transform(apl[0], hf.image_info(info.alpha_id))
+    planes = [_transform(p, info) for p in planes]
     return planes, alpha, cf, bd, nclx
+
+
+def _transform(plane, info):
+    """irot / imir in ipma order, plane by plane (context.cc:1955-1978, pixelimage.cc:539-794)"""
+    for k in range(info.n_transforms):
+        op = info.transforms[k]
+        if op in (1, 2, 3):
+            plane = np.rot90(plane, op)          # anti-clockwise: out[y][x] = in[x][w-1-y] for one quarter turn
+        elif op == 4:
+            plane = plane[:, ::-1]               # "horizontal" direction: every row reversed
+        elif op == 5:
+            plane = plane[::-1, :]
+    return np.ascontiguousarray(plane)
 
 
 def decode_rgb(data, out_format, item_id=None):

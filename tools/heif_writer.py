@@ -66,20 +66,22 @@ class HeifBuilder:
             props.append(self.add_prop(p))
         return self.add_item(b"hvc1", data, props, hidden)
 
-    def add_grid(self, tile_ids, rows, cols, out_w, out_h, nclx=None):
+    def add_grid(self, tile_ids, rows, cols, out_w, out_h, nclx=None, extra_props=()):
         big = out_w > 65535 or out_h > 65535
         payload = bytes([0, 1 if big else 0, rows - 1, cols - 1]) + (struct.pack(">II", out_w, out_h) if big else struct.pack(">HH", out_w, out_h))
         props = [self.add_prop(fullbox(b"ispe", 0, 0, struct.pack(">II", out_w, out_h)))]
         if nclx is not None:
             prim, trc, mat, full = nclx
             props.append(self.add_prop(box(b"colr", b"nclx" + struct.pack(">HHHB", prim, trc, mat, 0x80 if full else 0))))
+        for p in extra_props:
+            props.append(self.add_prop(p))
         gid = self.add_item(b"grid", payload, props)
         self.refs.append((b"dimg", gid, list(tile_ids)))
         return gid
 
-    def add_alpha(self, master_id, stream, width, height, chroma_format, bit_depth):
+    def add_alpha(self, master_id, stream, width, height, chroma_format, bit_depth, extra_props=()):
         auxc = fullbox(b"auxC", 0, 0, b"urn:mpeg:hevc:2015:auxid:1\x00")
-        aid = self.add_hevc_image(stream, width, height, chroma_format, bit_depth, hidden=True, extra_props=(auxc,))
+        aid = self.add_hevc_image(stream, width, height, chroma_format, bit_depth, hidden=True, extra_props=(auxc,) + tuple(extra_props))
         self.refs.append((b"auxl", aid, [master_id]))
         return aid
 
@@ -123,25 +125,37 @@ class HeifBuilder:
         return ftyp + meta + mdat
 
 
-def single_image(stream, width, height, chroma_format=1, bit_depth=8, nclx=None, alpha_stream=None, alpha_chroma_format=0):
+def irot(quarter_turns_ccw):
+    """ImageRotation property (anti-clockwise quarter turns)"""
+    return box(b"irot", bytes([quarter_turns_ccw & 3]))
+
+
+def imir(axis):
+    """ImageMirror property: axis bit 0 (libheif box.cc:3626: 1 -> "horizontal" direction, every row reversed)"""
+    return box(b"imir", bytes([axis & 1]))
+
+
+def single_image(stream, width, height, chroma_format=1, bit_depth=8, nclx=None, alpha_stream=None, alpha_chroma_format=0,
+                 transforms=()):
+    """transforms: property boxes (irot / imir) attached, in this order, to the image and to its alpha image"""
     b = HeifBuilder()
-    iid = b.add_hevc_image(stream, width, height, chroma_format, bit_depth, nclx=nclx)
+    iid = b.add_hevc_image(stream, width, height, chroma_format, bit_depth, nclx=nclx, extra_props=tuple(transforms))
     if alpha_stream is not None:
-        b.add_alpha(iid, alpha_stream, width, height, alpha_chroma_format, bit_depth)
+        b.add_alpha(iid, alpha_stream, width, height, alpha_chroma_format, bit_depth, extra_props=tuple(transforms))
     b.primary = iid
     return b.serialize()
 
 
 def grid_image(tile_streams, rows, cols, tile_w, tile_h, out_w, out_h, chroma_format=1, bit_depth=8, nclx=None,
-               tile_nclx=None):
+               tile_nclx=None, transforms=()):
     b = HeifBuilder()
     tiles = [b.add_hevc_image(s, tile_w, tile_h, chroma_format, bit_depth, hidden=True, nclx=tile_nclx) for s in tile_streams]
-    gid = b.add_grid(tiles, rows, cols, out_w, out_h, nclx=nclx)
+    gid = b.add_grid(tiles, rows, cols, out_w, out_h, nclx=nclx, extra_props=tuple(transforms))
     b.primary = gid
     return b.serialize()
 
 
-def synth_grid_heic(out_w, out_h, tile=512, chroma_format=1, bit_depth=8, seed=0, **enc_opts):
+def synth_grid_heic(out_w, out_h, tile=512, chroma_format=1, bit_depth=8, seed=0, transforms=(), **enc_opts):
     """A whole synthetic photo cut into tile x tile HEVC pictures, iPhone style (BASELINE config C2)."""
     cols, rows = (out_w + tile - 1) // tile, (out_h + tile - 1) // tile
     full = hevcenc.synth_image(cols * tile, rows * tile, chroma_format, bit_depth, seed)
@@ -157,4 +171,4 @@ def synth_grid_heic(out_w, out_h, tile=512, chroma_format=1, bit_depth=8, seed=0
             opts = dict(enc_opts)
             opts.setdefault("seed", seed * 1000 + r * cols + c + 1)
             streams.append(hevcenc.encode(planes, chroma_format=chroma_format, bit_depth=bit_depth, **opts))
-    return grid_image(streams, rows, cols, tile, tile, out_w, out_h, chroma_format, bit_depth)
+    return grid_image(streams, rows, cols, tile, tile, out_w, out_h, chroma_format, bit_depth, transforms=transforms)
