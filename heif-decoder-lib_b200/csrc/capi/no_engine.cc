@@ -24,6 +24,7 @@ int hc_batch_convert(hc_batch*, int, const hc_csc_params*) { return NO_ENGINE();
 int hc_batch_convert_many(hc_batch*, int, const int*, const hc_csc_params*) { return NO_ENGINE(); }
 int hc_batch_sync(hc_batch*) { return NO_ENGINE(); }
 int hc_batch_read_plane(hc_batch*, int, int, void*, size_t) { return NO_ENGINE(); }
+int hc_batch_read_planes(hc_batch*, int, int, void* const*, const size_t*) { return NO_ENGINE(); }
 int hc_batch_read_rgb(hc_batch*, int, void*, size_t) { return NO_ENGINE(); }
 int hc_batch_copy_rgb_device(hc_batch*, int, void*, size_t) { return NO_ENGINE(); }
 int hc_batch_read_rgb_async(hc_batch*, int, void*, size_t) { return NO_ENGINE(); }

@@ -46,6 +46,7 @@ struct hc_engine {
   std::mutex mu;
   std::vector<Block> free_dev, free_pin;
   std::vector<cudaStream_t> free_streams;
+  std::vector<cudaEvent_t> free_events;     // events are recycled: a batch needs 14 and the plugin creates one batch per tile
   hc::k0::Tables* d_k0_tables = nullptr;   // read-only tables of the device parser
   int device_parse = 1;                    // hc_heic_job: let K0 parse every picture it accepts
   int sm_count = 148;
@@ -76,6 +77,20 @@ struct hc_engine {
     }
     b.cap = cap;
     return b;
+  }
+  cudaEvent_t take_event() {
+    {
+      std::lock_guard<std::mutex> lk(mu);
+      if (!free_events.empty()) { cudaEvent_t ev = free_events.back(); free_events.pop_back(); return ev; }
+    }
+    cudaEvent_t ev = nullptr;
+    if (cudaEventCreate(&ev) != cudaSuccess) return nullptr;
+    return ev;
+  }
+  void give_event(cudaEvent_t ev) {
+    if (!ev) return;
+    std::lock_guard<std::mutex> lk(mu);
+    free_events.push_back(ev);
   }
   void give(std::vector<Block>& list, Block b) {
     if (!b.p) return;
@@ -145,6 +160,7 @@ struct hc_batch {
   std::vector<int> k0_pic_of;                      // K0 picture -> batch picture index
   Block h_status;
   cudaEvent_t ev_k0[2] = {};
+  cudaEvent_t ev_d2h[2] = {};
   size_t k0_input_bytes = 0;
   long long max_dbk_units = 0, max_sao_quads = 0;
   int max_planes = 1;
@@ -212,6 +228,7 @@ void hc_engine_destroy(hc_engine* e) {
   for (auto& b : e->free_dev) cudaFree(b.p);
   for (auto& b : e->free_pin) cudaFreeHost(b.p);
   for (auto s : e->free_streams) cudaStreamDestroy(s);
+  for (auto ev : e->free_events) cudaEventDestroy(ev);
   if (e->d_k0_tables) cudaFree(e->d_k0_tables);
   delete e;
 }
@@ -244,12 +261,12 @@ hc_batch* hc_batch_create(hc_engine* e) {
     delete b;
     return nullptr;
   }
-  for (auto& ev : b->ev)
-    if (!cuda_ok(cudaEventCreate(&ev), "cudaEventCreate")) { delete b; return nullptr; }
-  for (auto& ev : b->timer)
-    if (!cuda_ok(cudaEventCreate(&ev), "cudaEventCreate")) { delete b; return nullptr; }
-  for (auto& ev : b->ev_k0)
-    if (!cuda_ok(cudaEventCreate(&ev), "cudaEventCreate")) { delete b; return nullptr; }
+  bool ok = true;
+  for (auto& ev : b->ev) ok &= (ev = e->take_event()) != nullptr;
+  for (auto& ev : b->timer) ok &= (ev = e->take_event()) != nullptr;
+  for (auto& ev : b->ev_k0) ok &= (ev = e->take_event()) != nullptr;
+  for (auto& ev : b->ev_d2h) ok &= (ev = e->take_event()) != nullptr;
+  if (!ok) { hc::set_last_error("cudaEventCreate failed"); hc_batch_destroy(b); return nullptr; }
   return b;
 }
 
@@ -258,10 +275,11 @@ void hc_batch_destroy(hc_batch* b) {
   cudaSetDevice(b->eng->device);
   cudaStreamSynchronize(b->stream);
   release_blocks(b);
-  for (auto& ev : b->ev) if (ev) cudaEventDestroy(ev);
-  for (auto& ev : b->timer) if (ev) cudaEventDestroy(ev);
-  for (auto& ev : b->ev_k0) if (ev) cudaEventDestroy(ev);
-  for (auto& p : b->csc_events) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
+  for (auto& ev : b->ev) b->eng->give_event(ev);
+  for (auto& ev : b->timer) b->eng->give_event(ev);
+  for (auto& ev : b->ev_k0) b->eng->give_event(ev);
+  for (auto& ev : b->ev_d2h) b->eng->give_event(ev);
+  for (auto& p : b->csc_events) { b->eng->give_event(p.first); b->eng->give_event(p.second); }
   {
     std::lock_guard<std::mutex> lk(b->eng->mu);
     b->eng->free_streams.push_back(b->stream);
@@ -674,7 +692,7 @@ int hc_batch_reconstruct_async(hc_batch* b, int stages) {
   if (!cuda_ok(cudaSetDevice(b->eng->device), "cudaSetDevice")) return HC_ERR_CUDA;
   cudaStream_t s = b->stream;
   b->launches = 0;
-  for (auto& p : b->csc_events) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
+  for (auto& p : b->csc_events) { b->eng->give_event(p.first); b->eng->give_event(p.second); }
   b->csc_events.clear();
   cudaMemsetAsync(b->d_progress.p, 0, std::max<size_t>((size_t)b->ntasks * sizeof(int), 4), s);
   uint8_t* D = (uint8_t*)b->d_arena.p;
@@ -784,8 +802,7 @@ int hc_batch_convert(hc_batch* b, int canvas, const hc_csc_params* params) {
   a.out_stride = (long long)c.rgb_stride;
   a.p = *params;
   a.p.bit_depth = c.bit_depth;
-  cudaEvent_t e0, e1;
-  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  cudaEvent_t e0 = b->eng->take_event(), e1 = b->eng->take_event();
   cudaEventRecord(e0, b->stream);
   hc::launch_k5(a, c.bit_depth != 8, b->stream);
   cudaEventRecord(e1, b->stream);
@@ -828,8 +845,7 @@ int hc_batch_convert_many(hc_batch* b, int n, const int* canvases, const hc_csc_
     for (auto& cv : b->canvases) cv.converted = false;
   }
   const uint8_t* P = (const uint8_t*)b->d_planes.p;
-  cudaEvent_t e0, e1;
-  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  cudaEvent_t e0 = b->eng->take_event(), e1 = b->eng->take_event();
   cudaEventRecord(e0, b->stream);
   for (int sixteen = 0; sixteen < 2; sixteen++) {
     hc::CscBatch cb;
@@ -876,8 +892,7 @@ int hc_batch_read_plane(hc_batch* b, int canvas, int plane, void* dst, size_t ds
   const Canvas& c = b->canvases[canvas];
   if (c.pw[plane] == 0 || (plane == 3 && !c.alpha)) { hc::set_last_error("canvas has no such plane"); return HC_ERR_ARGUMENT; }
   const int ps = c.bit_depth == 8 ? 1 : 2;
-  cudaEvent_t e0, e1;
-  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  cudaEvent_t e0 = b->ev_d2h[0], e1 = b->ev_d2h[1];
   cudaEventRecord(e0, b->stream);
   cudaError_t e = cudaMemcpy2DAsync(dst, dst_stride, (const uint8_t*)b->d_planes.p + c.ooff[plane], (size_t)c.ostride[plane] * ps,
                                     (size_t)c.opw[plane] * ps, c.oph[plane], cudaMemcpyDeviceToHost, b->stream);
@@ -885,16 +900,51 @@ int hc_batch_read_plane(hc_batch* b, int canvas, int plane, void* dst, size_t ds
   if (!cuda_ok(e, "cudaMemcpy2DAsync(D2H plane)")) return HC_ERR_CUDA;
   if (int rc = batch_sync_checked(b, "cudaStreamSynchronize")) return rc;
   cudaEventElapsedTime(&b->last_d2h_ms, e0, e1);
-  cudaEventDestroy(e0); cudaEventDestroy(e1);
   return HC_OK;
+}
+
+// Planes 0..nplanes-1 of a canvas with ONE synchronisation: device -> pinned staging (async) -> caller's rows.
+// The plugin returns its planes in libheif's pageable memory; three separate pageable read-backs cost three
+// driver-serialised synchronous copies per tile.
+int hc_batch_read_planes(hc_batch* b, int canvas, int nplanes, void* const* dst, const size_t* dst_strides) {
+  if (!b || !dst || !dst_strides || canvas < 0 || canvas >= (int)b->canvases.size() || nplanes < 1 || nplanes > 4) {
+    hc::set_last_error("hc_batch_read_planes: bad argument");
+    return HC_ERR_ARGUMENT;
+  }
+  const Canvas& c = b->canvases[canvas];
+  const int ps = c.bit_depth == 8 ? 1 : 2;
+  size_t off[4] = {0, 0, 0, 0}, total = 0;
+  for (int k = 0; k < nplanes; k++) {
+    if (c.opw[k] == 0 || (k == 3 && !c.alpha) || !dst[k]) { hc::set_last_error("canvas has no such plane"); return HC_ERR_ARGUMENT; }
+    off[k] = total;
+    total += align_up((size_t)c.opw[k] * ps * c.oph[k], 256);
+  }
+  Block stage = b->eng->take(b->eng->free_pin, total, true);
+  if (!stage.p) return HC_ERR_MEMORY;
+  cudaEventRecord(b->ev_d2h[0], b->stream);
+  cudaError_t e = cudaSuccess;
+  for (int k = 0; k < nplanes && e == cudaSuccess; k++)
+    e = cudaMemcpy2DAsync((uint8_t*)stage.p + off[k], (size_t)c.opw[k] * ps, (const uint8_t*)b->d_planes.p + c.ooff[k], (size_t)c.ostride[k] * ps,
+                          (size_t)c.opw[k] * ps, c.oph[k], cudaMemcpyDeviceToHost, b->stream);
+  cudaEventRecord(b->ev_d2h[1], b->stream);
+  int rc = cuda_ok(e, "cudaMemcpy2DAsync(D2H planes)") ? batch_sync_checked(b, "cudaStreamSynchronize") : HC_ERR_CUDA;
+  if (rc == HC_OK) {
+    for (int k = 0; k < nplanes; k++) {
+      const size_t row = (size_t)c.opw[k] * ps;
+      const uint8_t* src = (const uint8_t*)stage.p + off[k];
+      for (int y = 0; y < c.oph[k]; y++) memcpy((uint8_t*)dst[k] + (size_t)y * dst_strides[k], src + (size_t)y * row, row);
+    }
+    cudaEventElapsedTime(&b->last_d2h_ms, b->ev_d2h[0], b->ev_d2h[1]);
+  }
+  b->eng->give(b->eng->free_pin, stage);
+  return rc;
 }
 
 int hc_batch_read_rgb(hc_batch* b, int canvas, void* dst, size_t dst_stride) {
   if (!b || !dst || canvas < 0 || canvas >= (int)b->canvases.size()) { hc::set_last_error("hc_batch_read_rgb: bad argument"); return HC_ERR_ARGUMENT; }
   const Canvas& c = b->canvases[canvas];
   if (!c.converted) { hc::set_last_error("canvas was not converted"); return HC_ERR_ARGUMENT; }
-  cudaEvent_t e0, e1;
-  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  cudaEvent_t e0 = b->ev_d2h[0], e1 = b->ev_d2h[1];
   cudaEventRecord(e0, b->stream);
   cudaError_t e = cudaMemcpy2DAsync(dst, dst_stride, (const uint8_t*)b->d_rgb.p + c.rgb_off, c.rgb_stride, (size_t)c.ow * c.rgb_bpp, c.oh,
                                     cudaMemcpyDeviceToHost, b->stream);
@@ -902,7 +952,6 @@ int hc_batch_read_rgb(hc_batch* b, int canvas, void* dst, size_t dst_stride) {
   if (!cuda_ok(e, "cudaMemcpy2DAsync(D2H rgb)")) return HC_ERR_CUDA;
   if (int rc = batch_sync_checked(b, "cudaStreamSynchronize")) return rc;
   cudaEventElapsedTime(&b->last_d2h_ms, e0, e1);
-  cudaEventDestroy(e0); cudaEventDestroy(e1);
   return HC_OK;
 }
 
@@ -943,7 +992,7 @@ int hc_batch_stage_ms(hc_batch* b, float ms[8]) {
   for (auto& p : b->csc_events) {
     float t = 0.f;
     if (cudaEventElapsedTime(&t, p.first, p.second) == cudaSuccess) ms[5] += t;
-    cudaEventDestroy(p.first); cudaEventDestroy(p.second);
+    b->eng->give_event(p.first); b->eng->give_event(p.second);
   }
   b->csc_events.clear();
   ms[6] = b->last_d2h_ms;

@@ -28,6 +28,7 @@
 //     folded into the gather (the substitute is itself a reconstructed sample of the tile).
 //
 // Bound: instruction issue / dependency latency of the per-block chain, not HBM; see DESIGN.md.
+#include <atomic>
 #include "launch.h"
 
 namespace hc {
@@ -570,8 +571,19 @@ k2_intra_kernel(BatchView bv, const RowTask* __restrict__ tasks, int ntasks, int
 
 void launch_k2(const BatchView& bv, const RowTask* tasks, int ntasks, int smem_bytes, int* progress, cudaStream_t stream) {
   if (ntasks <= 0) return;
-  // per device attribute; cheap enough to set on every launch (several engines / devices per process)
-  cudaFuncSetAttribute(k2_intra_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+  // per device attribute: raised only when a launch needs more than any earlier one on this device (the plugin launches
+  // K2 once per tile from many threads, and every CUDA call serialises on the context)
+  {
+    static std::atomic<int> max_set[64];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    dev &= 63;
+    if (smem_bytes > max_set[dev].load(std::memory_order_relaxed)) {
+      cudaFuncSetAttribute(k2_intra_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+      int cur = max_set[dev].load();
+      while (smem_bytes > cur && !max_set[dev].compare_exchange_weak(cur, smem_bytes)) {}
+    }
+  }
   const int grid = (ntasks + K2_WARPS - 1) / K2_WARPS;
   k2_intra_kernel<<<grid, K2_WARPS * 32, smem_bytes, stream>>>(bv, tasks, ntasks, progress);
 }

@@ -185,16 +185,22 @@ hcp_error cuda_decode_image(void* raw, void** out_img) {
                                      pic->chroma_format /* heif_chroma == de265_chroma numerically */, &img);
   if (err.code) return err;
   const int SubW = (pic->chroma_format == 1 || pic->chroma_format == 2) ? 2 : 1, SubH = pic->chroma_format == 1 ? 2 : 1;
-  for (int c = 0; c < (mono ? 1 : 3); c++) {
+  void* plane_dst[3] = {nullptr, nullptr, nullptr};
+  size_t plane_stride[3] = {0, 0, 0};
+  const int nplanes = mono ? 1 : 3;
+  for (int c = 0; c < nplanes; c++) {
     const int w = c ? (pic->crop_w + SubW - 1) / SubW : pic->crop_w, h = c ? (pic->crop_h + SubH - 1) / SubH : pic->crop_h;
     err = g_api.image_add_plane(img, HCP_CHANNEL_Y + c, w, h, pic->bit_depth_y);
     if (err.code) { g_api.image_release(img); return err; }
     int stride = 0;
-    uint8_t* dst = g_api.image_get_plane(img, HCP_CHANNEL_Y + c, &stride);
-    if (!dst || hc_batch_read_plane(g.b, canvas, c, dst, (size_t)stride) != HC_OK) {
-      g_api.image_release(img);
-      return plugin_error(std::string("decoder_cuda: ") + hc_last_error());
-    }
+    plane_dst[c] = g_api.image_get_plane(img, HCP_CHANNEL_Y + c, &stride);
+    plane_stride[c] = (size_t)stride;
+    if (!plane_dst[c]) { g_api.image_release(img); return plugin_error("decoder_cuda: heif_image_get_plane failed"); }
+  }
+  // one synchronisation for all planes (and the first point where a GPU error of this tile can surface)
+  if (hc_batch_read_planes(g.b, canvas, nplanes, plane_dst, plane_stride) != HC_OK) {
+    g_api.image_release(img);
+    return plugin_error(std::string("decoder_cuda: ") + hc_last_error());
   }
 
   // nclx from the VUI, defaults 2/2/2 + limited range when absent (decoder_libde265.cc:339-362, vui.cc:93-97)

@@ -116,6 +116,7 @@ SYMBOLS = [
     ("hc_batch_convert_many", _i, [_vp, _i, C.POINTER(C.c_int), C.POINTER(CscParams)]),
     ("hc_batch_sync", _i, [_vp]),
     ("hc_batch_read_plane", _i, [_vp, _i, _i, _vp, _sz]),
+    ("hc_batch_read_planes", _i, [_vp, _i, _i, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
     ("hc_batch_read_rgb", _i, [_vp, _i, _vp, _sz]),
     ("hc_batch_read_rgb_async", _i, [_vp, _i, _vp, _sz]),
     ("hc_batch_copy_rgb_device", _i, [_vp, _i, _vp, _sz]),

@@ -227,6 +227,8 @@ int hc_batch_sync(hc_batch* b);
 /* D2H reads (synchronous). plane: 0 Y, 1 Cb, 2 Cr, 3 alpha. Samples are 1 byte for 8-bit canvases,
  * 2 bytes little-endian otherwise. */
 int hc_batch_read_plane(hc_batch* b, int canvas, int plane, void* dst, size_t dst_stride_bytes);
+/* planes 0..nplanes-1 of a canvas with one synchronisation (pinned staging inside) */
+int hc_batch_read_planes(hc_batch* b, int canvas, int nplanes, void* const* dst, const size_t* dst_strides);
 int hc_batch_read_rgb(hc_batch* b, int canvas, void* dst, size_t dst_stride_bytes);
 int hc_batch_copy_rgb_device(hc_batch* b, int canvas, void* device_dst, size_t dst_stride_bytes);
 /* same copy without the final synchronisation (dst should be pinned); pair with hc_batch_sync */
