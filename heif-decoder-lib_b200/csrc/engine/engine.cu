@@ -151,6 +151,7 @@ struct hc_batch {
   const hc::k0::Chain* d_k0_chains = nullptr;
   size_t k0_zero_off = 0, k0_zero_bytes = 0;      // device-only zone: cleared to 0 before K0 (edge maps, progress, errors, counters)
   size_t k0_ones_off = 0, k0_ones_bytes = 0;      // cleared to 1 (intra mode maps: DC)
+  size_t k0_ctu_off = 0, k0_ctu_bytes = 0;         // CTU records of the K0 pictures (cleared to 0 before K0)
   size_t k0_status_off = 0;                        // [int error per K0 picture][4 list counters]
   const uint32_t* d_k0_tb_index[4] = {nullptr, nullptr, nullptr, nullptr};
   int k0_tb_counts[4] = {0, 0, 0, 0};
@@ -475,6 +476,10 @@ int hc_batch_upload(hc_batch* b) {
       z = o_ctus + align_up(z - o_ctus, sizeof(hc_ctu));
       koff[q].ctus = z; z += sizeof(hc_ctu) * (size_t)kp.ctbs_w * kp.ctbs_h;
     }
+    // the CTU records of all K0 pictures form one contiguous run; it is cleared before K0 so that a CTB a failing chain
+    // never reached has no blocks and no SAO (K2..K4 run on the batch without waiting for K0's verdict)
+    b->k0_ctu_off = koff[0].ctus;
+    b->k0_ctu_bytes = z - koff[0].ctus;
     for (int q = 0; q < nk0; q++) { const hc::k0::Pic& kp = b->pics[b->k0_pic_of[q]].k0->pic; koff[q].blks = zplace(sizeof(hc_blk) * (size_t)kp.ctbs_w * kp.ctbs_h * kp.blk_cap_ctb, 16); }
     for (int q = 0; q < nk0; q++) { const hc::k0::Pic& kp = b->pics[b->k0_pic_of[q]].k0->pic; koff[q].tbs = zplace(sizeof(hc_tb) * (size_t)kp.ctbs_w * kp.ctbs_h * kp.tb_cap_ctb, 16); }
     for (int q = 0; q < nk0; q++) { const hc::k0::Pic& kp = b->pics[b->k0_pic_of[q]].k0->pic; koff[q].coeffs = zplace(sizeof(hc_coeff) * (size_t)kp.ctbs_w * kp.ctbs_h * kp.coeff_cap_ctb, 16); }
@@ -702,6 +707,7 @@ int hc_batch_reconstruct_async(hc_batch* b, int stages) {
     cudaEventRecord(b->ev_k0[0], s);
     cudaMemsetAsync(D + b->k0_ones_off, 1, b->k0_ones_bytes, s);
     cudaMemsetAsync(D + b->k0_zero_off, 0, b->k0_zero_bytes, s);
+    cudaMemsetAsync(D + b->k0_ctu_off, 0, b->k0_ctu_bytes, s);
     hc::launch_k0(b->eng->d_k0_tables, b->d_k0_pics, b->d_k0_subs, b->d_k0_chains, b->nchains, s);
     hc::launch_k0_finish(b->d_k0_pics, b->nk0, (int)b->k0_max_ctbs, s);
     cudaEventRecord(b->ev_k0[1], s);

@@ -80,9 +80,12 @@ def test_gpu_decode_heic_python_path(engine):
 
 
 @pytest.mark.gpu
-def test_gpu_decode_stream_pipelined_batches(engine):
-    """hc_heic_decode_stream: batches of 4 files, parse of batch b+1 overlapping the GPU phase of batch b;
+@pytest.mark.parametrize("host_share", [-1, 0, 50, 100])
+def test_gpu_decode_stream_pipelined_batches(engine, host_share):
+    """hc_heic_decode_stream: batches of 4 files, submit / deliver pipelined over two pinned buffers, slice data parsed
+    by K0 with the host threads taking `host_share` per cent of the coded items meanwhile (-1: automatic);
     every image arrives once, in order, bit-exact."""
+    engine.set_option("host_share_pct", host_share)
     files = [load(n) for n in NAMES] * 2
     seen = []
 
@@ -92,6 +95,7 @@ def test_gpu_decode_stream_pipelined_batches(engine):
         seen.append((index, md5(rows.tobytes()) == META[name][key + "_md5"]))
 
     st = hb.decode_stream(engine, files, on_image, want_alpha=False, threads=4, files_per_batch=4)
+    engine.set_option("host_share_pct", -1)
     assert [i for i, _ in seen] == list(range(len(files)))
     assert all(ok for _, ok in seen)
     assert st["batches"] == (len(files) + 3) // 4 and st["pixels"] == 2 * sum(META[n]["width"] * META[n]["height"] for n in NAMES)
