@@ -130,7 +130,12 @@ int hc_heif_get_image_info(const hc_heif* f, uint32_t id, hc_heif_image_info* in
   info->mirror = it->mirror;
   info->n_transforms = (int32_t)std::min<size_t>(it->xforms.size(), 8);
   for (int k = 0; k < info->n_transforms; k++) info->transforms[k] = it->xforms[k];
-  info->has_clap = it->has_clap;
+  info->has_clap = (int32_t)std::min<size_t>(it->claps.size(), 4);
+  for (int k = 0; k < info->has_clap; k++) {
+    const hc::HeifItem::Clap& cl = it->claps[k];
+    const uint32_t v[8] = {cl.w_num, cl.w_den, cl.h_num, cl.h_den, (uint32_t)cl.hoff_num, cl.hoff_den, (uint32_t)cl.voff_num, cl.voff_den};
+    for (int q = 0; q < 8; q++) info->claps[k][q] = v[q];
+  }
   info->nclx_present = it->nclx.present;
   info->primaries = it->nclx.primaries;
   info->transfer = it->nclx.transfer;

@@ -107,10 +107,18 @@ struct Canvas {
   size_t off[4] = {0, 0, 0, 0};     // byte offsets in the plane pool
   int stride[4] = {0, 0, 0, 0};     // samples
   int pw[4] = {0, 0, 0, 0}, ph[4] = {0, 0, 0, 0};
-  // geometric transform between K4 and K5 (irot / imir): the "output view" below is what K5 and the read-backs use;
-  // without a transform it is the canvas itself
-  int xf_swap = 0, xf_fx = 0, xf_fy = 0;
-  bool transformed() const { return xf_swap || xf_fx || xf_fy; }
+  // geometric passes between K4 and K5 (irot / imir / clap of the reference, in the order they are given); the "output
+  // view" below is what K5 and the read-backs use; without passes it is the canvas itself
+  struct Pass {
+    int kind;                        // 0: dihedral map (a = swap, b = flip_x, c = flip_y), 1: crop (a..d = left, top, right, bottom)
+    int a, b, c, d;
+    // filled at upload: the planes this pass writes
+    int w = 0, h = 0;                // image size after the pass
+    size_t off[4] = {0, 0, 0, 0};
+    int stride[4] = {0, 0, 0, 0}, pw[4] = {0, 0, 0, 0}, ph[4] = {0, 0, 0, 0};
+  };
+  std::vector<Pass> passes;
+  bool transformed() const { return !passes.empty(); }
   int ow = 0, oh = 0;               // output image size
   size_t ooff[4] = {0, 0, 0, 0};
   int ostride[4] = {0, 0, 0, 0}, opw[4] = {0, 0, 0, 0}, oph[4] = {0, 0, 0, 0};
@@ -302,7 +310,22 @@ int hc_batch_add_canvas(hc_batch* b, int width, int height, int chroma_format, i
 int hc_batch_set_canvas_transform(hc_batch* b, int canvas, int swap, int flip_x, int flip_y) {
   if (!b || canvas < 0 || canvas >= (int)b->canvases.size()) { hc::set_last_error("hc_batch_set_canvas_transform: bad argument"); return HC_ERR_ARGUMENT; }
   Canvas& c = b->canvases[canvas];
-  c.xf_swap = swap != 0; c.xf_fx = flip_x != 0; c.xf_fy = flip_y != 0;
+  c.passes.clear();
+  b->uploaded = false;
+  if (swap || flip_x || flip_y) return hc_batch_add_canvas_pass(b, canvas, HC_PASS_DIHEDRAL, swap != 0, flip_x != 0, flip_y != 0, 0);
+  return HC_OK;
+}
+
+int hc_batch_add_canvas_pass(hc_batch* b, int canvas, int kind, int a0, int a1, int a2, int a3) {
+  if (!b || canvas < 0 || canvas >= (int)b->canvases.size() || (kind != HC_PASS_DIHEDRAL && kind != HC_PASS_CROP)) {
+    hc::set_last_error("hc_batch_add_canvas_pass: bad argument");
+    return HC_ERR_ARGUMENT;
+  }
+  Canvas& c = b->canvases[canvas];
+  if (kind == HC_PASS_CROP && (a0 < 0 || a1 < 0 || a2 < a0 || a3 < a1)) { hc::set_last_error("hc_batch_add_canvas_pass: bad crop window"); return HC_ERR_ARGUMENT; }
+  Canvas::Pass p;
+  p.kind = kind; p.a = a0; p.b = a1; p.c = a2; p.d = a3;
+  c.passes.push_back(p);
   b->uploaded = false;
   return HC_OK;
 }
@@ -362,16 +385,38 @@ int hc_batch_upload(hc_batch* b) {
       pool += align_up((size_t)c.stride[k] * c.ph[k] * ps, 256);
     }
     c.converted = false;
-    c.ow = c.xf_swap ? c.h : c.w;
-    c.oh = c.xf_swap ? c.w : c.h;
-    for (int k = 0; k < 4; k++) {
-      c.ooff[k] = c.off[k]; c.ostride[k] = c.stride[k]; c.opw[k] = c.pw[k]; c.oph[k] = c.ph[k];
-      if (!c.transformed() || c.pw[k] == 0 || (k == 3 && !c.alpha)) continue;
-      c.opw[k] = c.xf_swap ? c.ph[k] : c.pw[k];
-      c.oph[k] = c.xf_swap ? c.pw[k] : c.ph[k];
-      c.ostride[k] = (int)(align_up((size_t)(c.opw[k] + 4) * ps, 128) / ps);
-      c.ooff[k] = pool;
-      pool += align_up((size_t)c.ostride[k] * c.oph[k] * ps, 256);
+    // pass outputs: every pass writes its own set of planes (passes are rare; the chain stays simple and exact)
+    {
+      int iw = c.w, ih = c.h;
+      const int* ipw = c.pw; const int* iph = c.ph;
+      for (Canvas::Pass& ps_ : c.passes) {
+        int nw, nh;
+        if (ps_.kind == HC_PASS_DIHEDRAL) { nw = ps_.a ? ih : iw; nh = ps_.a ? iw : ih; }
+        else {
+          if (ps_.c >= iw || ps_.d >= ih) { hc::set_last_error("crop window outside the image"); return HC_ERR_ARGUMENT; }
+          nw = ps_.c - ps_.a + 1; nh = ps_.d - ps_.b + 1;
+        }
+        for (int k = 0; k < 4; k++) {
+          ps_.pw[k] = ps_.ph[k] = 0;
+          if (ipw[k] == 0 || (k == 3 && !c.alpha)) continue;
+          if (ps_.kind == HC_PASS_DIHEDRAL) { ps_.pw[k] = ps_.a ? iph[k] : ipw[k]; ps_.ph[k] = ps_.a ? ipw[k] : iph[k]; }
+          else {
+            // HeifPixelImage::crop (pixelimage.cc:820-823): the window is scaled to every plane by integer division
+            const int pl = ps_.a * ipw[k] / iw, pr = ps_.c * ipw[k] / iw, pt = ps_.b * iph[k] / ih, pb = ps_.d * iph[k] / ih;
+            ps_.pw[k] = pr - pl + 1; ps_.ph[k] = pb - pt + 1;
+          }
+          ps_.stride[k] = (int)(align_up((size_t)(ps_.pw[k] + 4) * ps, 128) / ps);
+          ps_.off[k] = pool;
+          pool += align_up((size_t)ps_.stride[k] * ps_.ph[k] * ps, 256);
+        }
+        ps_.w = nw; ps_.h = nh;
+        iw = nw; ih = nh; ipw = ps_.pw; iph = ps_.ph;
+      }
+      c.ow = iw; c.oh = ih;
+      for (int k = 0; k < 4; k++) {
+        if (c.passes.empty()) { c.ooff[k] = c.off[k]; c.ostride[k] = c.stride[k]; c.opw[k] = c.pw[k]; c.oph[k] = c.ph[k]; }
+        else { const Canvas::Pass& l = c.passes.back(); c.ooff[k] = l.off[k]; c.ostride[k] = l.stride[k]; c.opw[k] = l.pw[k]; c.oph[k] = l.ph[k]; }
+      }
     }
   }
   // ---- record bases ----
@@ -739,18 +784,31 @@ int hc_batch_reconstruct_async(hc_batch* b, int stages) {
   v.flags = (stages & HC_STAGE_SAO) ? 0 : hc::HC_VIEW_NO_SAO;
   hc::launch_k4(v, b->max_sao_quads, b->max_planes, s);
   b->launches += 1;
-  // K6: irot / imir of the canvases that carry a transform, plane by plane (rare; timed with K4)
+  // K6: irot / imir / clap passes of the canvases that carry any, plane by plane (rare; timed with K4)
   for (const Canvas& c : b->canvases) {
     if (!c.transformed()) continue;
-    for (int k = 0; k < 4; k++) {
-      if (c.pw[k] == 0 || (k == 3 && !c.alpha)) continue;
-      hc::XformArgs a;
-      a.src = (const uint8_t*)b->d_planes.p + c.off[k];
-      a.dst = (uint8_t*)b->d_planes.p + c.ooff[k];
-      a.w = c.pw[k]; a.h = c.ph[k]; a.src_stride = c.stride[k]; a.dst_stride = c.ostride[k];
-      a.swap = c.xf_swap; a.flip_x = c.xf_fx; a.flip_y = c.xf_fy;
-      hc::launch_k6(a, c.bit_depth != 8, s);
-      b->launches += 1;
+    const int ps = c.bit_depth == 8 ? 1 : 2;
+    int iw = c.w, ih = c.h;
+    const size_t* ioff = c.off; const int* istride = c.stride; const int* ipw = c.pw; const int* iph = c.ph;
+    for (const Canvas::Pass& p : c.passes) {
+      for (int k = 0; k < 4; k++) {
+        if (p.pw[k] == 0) continue;
+        const uint8_t* src = (const uint8_t*)b->d_planes.p + ioff[k];
+        uint8_t* dst = (uint8_t*)b->d_planes.p + p.off[k];
+        if (p.kind == HC_PASS_DIHEDRAL) {
+          hc::XformArgs a;
+          a.src = src; a.dst = dst;
+          a.w = ipw[k]; a.h = iph[k]; a.src_stride = istride[k]; a.dst_stride = p.stride[k];
+          a.swap = p.a; a.flip_x = p.b; a.flip_y = p.c;
+          hc::launch_k6(a, c.bit_depth != 8, s);
+        } else {
+          const int pl = p.a * ipw[k] / iw, pt = p.b * iph[k] / ih;
+          cudaMemcpy2DAsync(dst, (size_t)p.stride[k] * ps, src + ((size_t)pt * istride[k] + pl) * ps, (size_t)istride[k] * ps,
+                            (size_t)p.pw[k] * ps, p.ph[k], cudaMemcpyDeviceToDevice, s);
+        }
+        b->launches += 1;
+      }
+      iw = p.w; ih = p.h; ioff = p.off; istride = p.stride; ipw = p.pw; iph = p.ph;
     }
   }
   cudaEventRecord(b->ev[6], s);

@@ -8,7 +8,9 @@
 // (:2029-2078), the nclx precedence (:1844-1847) and convert_colorspace (colorconversion.cc:487).
 #include <atomic>
 #include <algorithm>
+#include <cstdint>
 #include <cstdio>
+#include <cstring>
 #include <cstdlib>
 #include <chrono>
 #include <future>
@@ -21,6 +23,65 @@ namespace {
 // HEIFCUDA_TRACE=1: per-batch phase times of the job / stream pipeline on stderr
 bool trace_on() { static const bool on = getenv("HEIFCUDA_TRACE") != nullptr; return on; }
 double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
+// Rational arithmetic of the reference's clean-aperture evaluation (class Fraction, box.cc:51-147: 32-bit numerator /
+// denominator, halved until they fit, truncating division) — the crop window must round exactly like it does.
+struct Frac {
+  int32_t n = 0, d = 1;
+  static Frac from32(int32_t num, int32_t den) {
+    Frac f; f.n = num; f.d = den;
+    while (f.d > 0x10000 || f.d < -0x10000) { f.n /= 2; f.d /= 2; }
+    while (f.d > 1 && (f.n > 0x10000 || f.n < -0x10000)) { f.n /= 2; f.d /= 2; }
+    return f;
+  }
+  static Frac from64(int64_t num, int64_t den) {
+    while (num < INT32_MIN || num > INT32_MAX || den < INT32_MIN || den > INT32_MAX) {
+      num = (num + (num >= 0 ? 1 : -1)) / 2;
+      den = (den + (den >= 0 ? 1 : -1)) / 2;
+    }
+    Frac f; f.n = (int32_t)num; f.d = (int32_t)den;
+    return f;
+  }
+  Frac plus(const Frac& b) const {
+    if (d == b.d) return from64((int64_t)n + b.n, d);
+    return from64((int64_t)n * b.d + (int64_t)b.n * d, (int64_t)d * b.d);
+  }
+  Frac minus(const Frac& b) const {
+    if (d == b.d) return from64((int64_t)n - b.n, d);
+    return from64((int64_t)n * b.d - (int64_t)b.n * d, (int64_t)d * b.d);
+  }
+  Frac plus_int(int v) const { return from64(n + v * (int64_t)d, d); }
+  Frac minus_int(int v) const { return from64(n - v * (int64_t)d, d); }
+  Frac div_int(int v) const { return from64(n, (int64_t)d * v); }
+  int32_t round_down() const { return n / d; }
+  int32_t round() const { return (int32_t)((n + (int64_t)d / 2) / d); }
+  bool valid() const { return d != 0; }
+};
+
+// clap -> inclusive crop window of a w x h image (Box_clap::left_rounded .. bottom_rounded, box.cc:3771-3804, and the
+// clamping of context.cc:1990-2003). Returns an error text or "".
+std::string clap_window(const hc::HeifItem::Clap& cl, int w, int h, int win[4]) {
+  if (cl.w_num > (uint32_t)INT32_MAX || cl.w_den > (uint32_t)INT32_MAX || cl.h_num > (uint32_t)INT32_MAX || cl.h_den > (uint32_t)INT32_MAX ||
+      cl.hoff_den > (uint32_t)INT32_MAX || cl.voff_den > (uint32_t)INT32_MAX)
+    return "clap: exceeded supported value range";
+  const Frac caw = Frac::from32((int32_t)cl.w_num, (int32_t)cl.w_den), cah = Frac::from32((int32_t)cl.h_num, (int32_t)cl.h_den);
+  const Frac hoff = Frac::from32(cl.hoff_num, (int32_t)cl.hoff_den), voff = Frac::from32(cl.voff_num, (int32_t)cl.voff_den);
+  if (!caw.valid() || !cah.valid() || !hoff.valid() || !voff.valid()) return "clap: invalid fractional number";
+  const Frac pcx = hoff.plus(Frac::from32(w - 1, 2)), pcy = voff.plus(Frac::from32(h - 1, 2));
+  const Frac fl = pcx.minus(caw.minus_int(1).div_int(2)), ft = pcy.minus(cah.minus_int(1).div_int(2));
+  if (!fl.valid() || !ft.valid()) return "clap: invalid fractional number";
+  int left = fl.round_down();
+  int right = caw.minus_int(1).plus_int(left).round();
+  int top = ft.round();
+  int bottom = cah.minus_int(1).plus_int(top).round();
+  if (left < 0) left = 0;
+  if (top < 0) top = 0;
+  if (right >= w) right = w - 1;
+  if (bottom >= h) bottom = h - 1;
+  if (left > right || top > bottom) return "invalid clean aperture";
+  win[0] = left; win[1] = top; win[2] = right; win[3] = bottom;
+  return "";
+}
 
 struct CodedItem {
   int file;
@@ -240,13 +301,33 @@ static hc_heic_job* job_create(hc_engine* e, int nfiles, const uint8_t* const* d
       }
       if (add_item(j->batch, j->items[im.alpha], im.canvas, 0, 0, HC_ROLE_ALPHA, 0) < 0) return nullptr;
     }
-    // ---- irot / imir of the image item, in ipma order (context.cc:1955-1978); composed into one dihedral map ----
+    // ---- irot / imir / clap of the image item, in ipma order (context.cc:1955-2016). Consecutive rotations and mirrors
+    // are composed into one dihedral pass; a clap becomes a crop pass on the image as it is at that point. ----
     {
       const hc::HeifItem* pit = j->files[im.file]->item(im.info.id);
       int swap = 0, fx = 0, fy = 0;
+      bool any = false;
+      size_t next_clap = 0;
+      auto flush_dihedral = [&]() -> bool {
+        if (!(swap | fx | fy)) return true;
+        if (swap && p0.chroma_format == 2) { hc::set_last_error("quarter turns of 4:2:2 images are not supported"); return false; }
+        if (hc_batch_add_canvas_pass(j->batch, im.canvas, HC_PASS_DIHEDRAL, swap, fx, fy, 0) != HC_OK) return false;
+        swap = fx = fy = 0;
+        return true;
+      };
       if (pit) {
-        if (pit->has_clap) { hc::set_last_error("clean-aperture (clap) transformations are not supported"); return nullptr; }
         for (uint8_t op : pit->xforms) {
+          any = true;
+          if (op == HC_XF_CLAP) {
+            if (!flush_dihedral()) return nullptr;
+            if (next_clap >= pit->claps.size()) { hc::set_last_error("clap property without its box"); return nullptr; }
+            int win[4];
+            const std::string e = clap_window(pit->claps[next_clap++], W, H, win);
+            if (!e.empty()) { hc::set_last_error(e); return nullptr; }
+            if (hc_batch_add_canvas_pass(j->batch, im.canvas, HC_PASS_CROP, win[0], win[1], win[2], win[3]) != HC_OK) return nullptr;
+            W = win[2] - win[0] + 1; H = win[3] - win[1] + 1;
+            continue;
+          }
           const int s2 = (op == HC_XF_ROT90 || op == HC_XF_ROT270) ? 1 : 0;
           const int fx2 = (op == HC_XF_ROT90 || op == HC_XF_ROT180 || op == HC_XF_MIRROR_H) ? 1 : 0;
           const int fy2 = (op == HC_XF_ROT270 || op == HC_XF_ROT180 || op == HC_XF_MIRROR_V) ? 1 : 0;
@@ -257,18 +338,19 @@ static hc_heic_job* job_create(hc_engine* e, int nfiles, const uint8_t* const* d
           // out2(x, y) = out1(x1, y1): see hc_batch_set_canvas_transform for the map of one operation
           const int nfx = swap ? (fx ^ fy2) : (fx ^ fx2), nfy = swap ? (fy ^ fx2) : (fy ^ fy2);
           swap ^= s2; fx = nfx; fy = nfy;
+          if (s2) std::swap(W, H);
         }
+        if (!flush_dihedral()) return nullptr;
       }
-      if (swap | fx | fy) {
+      if (any) {
         if (band_end >= 0) { hc::set_last_error("banded decode of transformed images is not supported"); return nullptr; }
-        if (swap && p0.chroma_format == 2) { hc::set_last_error("quarter turns of 4:2:2 images are not supported"); return nullptr; }
         if (has_alpha) {
           // the alpha item carries its own properties in the reference (context.cc:2040); only identical ones are supported
           const hc::HeifItem* ait = j->files[im.file]->item(im.info.alpha_id);
-          if (!ait || ait->xforms != pit->xforms) { hc::set_last_error("alpha image with different transformations than its colour image"); return nullptr; }
+          bool same = ait && ait->xforms == pit->xforms && ait->claps.size() == pit->claps.size();
+          for (size_t k = 0; same && k < pit->claps.size(); k++) same = memcmp(&ait->claps[k], &pit->claps[k], sizeof(hc::HeifItem::Clap)) == 0;
+          if (!same) { hc::set_last_error("alpha image with different transformations than its colour image"); return nullptr; }
         }
-        if (hc_batch_set_canvas_transform(j->batch, im.canvas, swap, fx, fy) != HC_OK) return nullptr;
-        if (swap) std::swap(W, H);
       }
     }
     const bool hdr = p0.bit_depth_y != 8;

@@ -245,6 +245,12 @@ std::string HeifFile::parse(const uint8_t* data, size_t size) {
         item.xforms.push_back((uint8_t)(item.mirror ? 4 : 5));   // box.cc:3626-3636: axis & 1 -> "horizontal"
       } else if (p.type == fourcc("clap")) {
         item.has_clap = true;
+        HeifItem::Clap cl;
+        cl.w_num = c.u32(); cl.w_den = c.u32(); cl.h_num = c.u32(); cl.h_den = c.u32();
+        cl.hoff_num = (int32_t)c.u32(); cl.hoff_den = c.u32(); cl.voff_num = (int32_t)c.u32(); cl.voff_den = c.u32();
+        if (c.bad) return "malformed clap box";
+        item.claps.push_back(cl);
+        item.xforms.push_back(6);
       } else if (p.type == fourcc("auxC")) {
         c.u32();
         item.aux_type = c.cstr();

@@ -39,8 +39,10 @@ struct HeifItem {
   int rot = 0;                  // irot: anti-clockwise quarter turns
   int mirror = -1;              // imir: -1 none, 0 vertical axis, 1 horizontal axis
   bool has_clap = false;
+  struct Clap { uint32_t w_num, w_den, h_num, h_den; int32_t hoff_num; uint32_t hoff_den; int32_t voff_num; uint32_t voff_den; };
+  std::vector<Clap> claps;      // clap boxes in ipma order; xforms code 6 consumes the next one
   std::vector<uint8_t> xforms;  // irot / imir in ipma order (context.cc:1955-1978): 1..3 = quarter turns anti-clockwise,
-                                // 4 = mirror direction horizontal (rows reversed), 5 = vertical (row order reversed)
+                                // 4 = mirror direction horizontal (rows reversed), 5 = vertical (row order reversed), 6 = clap
   std::string aux_type;         // auxC
   int pixi_bits = 0;
 };

@@ -50,7 +50,7 @@ class HeifImageInfo(C.Structure):
                 ("rows", C.c_int32), ("cols", C.c_int32), ("alpha_id", C.c_uint32), ("rot", C.c_int32),
                 ("mirror", C.c_int32), ("nclx_present", C.c_int32), ("primaries", C.c_int32),
                 ("transfer", C.c_int32), ("matrix", C.c_int32), ("full_range", C.c_int32), ("n_transforms", C.c_int32), ("transforms", C.c_uint8 * 8),
-                ("has_clap", C.c_int32)]
+                ("has_clap", C.c_int32), ("claps", (C.c_uint32 * 8) * 4)]
 
 
 class StreamStats(C.Structure):
@@ -109,6 +109,7 @@ SYMBOLS = [
     ("hc_batch_add_k0_picture", _i, [_vp, _vp, _i, _i, _i, _i, _i]),
     ("hc_batch_k0_pictures", _i, [_vp]),
     ("hc_batch_set_canvas_transform", _i, [_vp, _i, _i, _i, _i]),
+    ("hc_batch_add_canvas_pass", _i, [_vp, _i, _i, _i, _i, _i, _i]),
     ("hc_batch_upload", _i, [_vp]),
     ("hc_batch_reconstruct", _i, [_vp, _i]),
     ("hc_batch_reconstruct_async", _i, [_vp, _i]),

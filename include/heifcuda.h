@@ -115,13 +115,15 @@ typedef struct hc_heif_image_info {
   int32_t primaries, transfer, matrix, full_range;
   int32_t n_transforms;        /* irot / imir properties in ipma order (the order the reference applies them) */
   uint8_t transforms[8];       /* HC_XF_*                                                                     */
-  int32_t has_clap;            /* a clean-aperture crop is present (not applied by this library)             */
+  int32_t has_clap;            /* number of clean-aperture (clap) properties, consumed in order by HC_XF_CLAP */
+  uint32_t claps[4][8];        /* width num/den, height num/den, horizontal offset num/den, vertical offset num/den */
 } hc_heif_image_info;
 #define HC_XF_ROT90 1          /* anti-clockwise quarter turns, HeifPixelImage::rotate_ccw pixelimage.cc:539 */
 #define HC_XF_ROT180 2
 #define HC_XF_ROT270 3
 #define HC_XF_MIRROR_H 4       /* heif_transform_mirror_direction_horizontal: every row reversed (:778-783)  */
 #define HC_XF_MIRROR_V 5       /* ..._vertical: row order reversed (:784-789)                                */
+#define HC_XF_CLAP 6           /* clean aperture crop (context.cc:1981-2015)                                  */
 
 /* `data` must stay valid until hc_heif_close. NULL + error text on malformed files. */
 hc_heif* hc_heif_open(const uint8_t* data, size_t size);
@@ -219,6 +221,13 @@ int hc_batch_reconstruct_async(hc_batch* b, int stages);
  *                        swap: sx = flip_x ? w-1-y' : y', sy = flip_y ? h-1-x' : x'   (output h x w).
  * Call before hc_batch_upload. hc_batch_convert / read_rgb / read_plane then see the transformed canvas. */
 int hc_batch_set_canvas_transform(hc_batch* b, int canvas, int swap, int flip_x, int flip_y);
+/* General form: an ordered list of passes per canvas (set_canvas_transform replaces the list by one dihedral pass).
+ * HC_PASS_DIHEDRAL: a0 = swap, a1 = flip_x, a2 = flip_y as above. HC_PASS_CROP: the window [a0, a2] x [a1, a3]
+ * (left, top, right, bottom, inclusive, in pixels of the image at that point), scaled to every plane like
+ * HeifPixelImage::crop does (pixelimage.cc:797-870) — the clap property of the reference. */
+#define HC_PASS_DIHEDRAL 0
+#define HC_PASS_CROP 1
+int hc_batch_add_canvas_pass(hc_batch* b, int canvas, int kind, int a0, int a1, int a2, int a3);
 /* K5 for one canvas into the engine's device RGB buffer, async */
 int hc_batch_convert(hc_batch* b, int canvas, const hc_csc_params* params);
 /* K5 for n canvases (canvases[i] with params[i]) in as few launches as possible, async */

@@ -67,6 +67,14 @@ def build():
     files["irot90_420_10"] = W.single_image(enc(200, 120, 1, 10, 39), 200, 120, 1, 10, transforms=(W.irot(1),))
     files["alpha_irot90_420_8"] = W.single_image(enc(200, 120, 1, 8, 40), 200, 120, 1, 8, alpha_stream=enc(200, 120, 0, 8, 41),
                                                  transforms=(W.irot(1),))
+    # clean aperture (clap): centred and off-centre windows, fractional values, after / before a rotation, 4:2:0 odd windows
+    files["clap_centre_420_8"] = W.single_image(enc(264, 200, 1, 8, 50), 264, 200, 1, 8, transforms=(W.clap(200, 1, 120, 1, 0, 1, 0, 1),))
+    files["clap_offset_420_8"] = W.single_image(enc(264, 200, 1, 8, 51), 264, 200, 1, 8, transforms=(W.clap(101, 1, 77, 1, -31, 2, 17, 2),))
+    files["clap_frac_444_8"] = W.single_image(enc(200, 120, 3, 8, 52), 200, 120, 3, 8, transforms=(W.clap(301, 2, 201, 4, 7, 3, -5, 3),))
+    files["irot90_clap_420_8"] = W.single_image(enc(264, 200, 1, 8, 53), 264, 200, 1, 8, transforms=(W.irot(1), W.clap(150, 1, 201, 1, 3, 1, -10, 1)))
+    files["clap_irot270_420_8"] = W.single_image(enc(264, 200, 1, 8, 54), 264, 200, 1, 8, transforms=(W.clap(151, 1, 99, 1, 5, 1, 4, 1), W.irot(3)))
+    files["grid_clap_imir_300x200"] = W.synth_grid_heic(300, 200, tile=128, seed=55, transforms=(W.clap(255, 1, 131, 1, -11, 1, 9, 1), W.imir(1)))
+    files["clap_422_10"] = W.single_image(enc(200, 120, 2, 10, 56), 200, 120, 2, 10, transforms=(W.clap(99, 1, 61, 1, 10, 1, 0, 1),))
     return files
 
 

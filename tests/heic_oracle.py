@@ -75,22 +75,89 @@ def decode_planes(data, item_id=None):
     if info.alpha_id:
         a = hb.parse_picture(hf.coded_stream(info.alpha_id), host_only=True)
         apl, _ = oracle_lib.reconstruct(a)
-        alpha = _transform(apl[0], hf.image_info(info.alpha_id))
-    planes = [_transform(p, info) for p in planes]
+        alpha = _transform_all([apl[0]], hf.image_info(info.alpha_id))[0]
+    planes = _transform_all(planes, info)
     return planes, alpha, cf, bd, nclx
 
 
-def _transform(plane, info):
-    """irot / imir in ipma order, plane by plane (context.cc:1955-1978, pixelimage.cc:539-794)"""
+def _tdiv(a, b):
+    """C integer division (truncation toward zero)"""
+    q = abs(a) // abs(b)
+    return q if (a >= 0) == (b >= 0) else -q
+
+
+class _Frac:
+    """libheif's Fraction (box.cc:51-147): 32-bit numerator / denominator, halved until they fit, truncating division"""
+
+    def __init__(self, n, d, wide=False):
+        if wide:
+            lo, hi = -(1 << 31), (1 << 31) - 1
+            while n < lo or n > hi or d < lo or d > hi:
+                n = _tdiv(n + (1 if n >= 0 else -1), 2)
+                d = _tdiv(d + (1 if d >= 0 else -1), 2)
+        else:
+            while d > 0x10000 or d < -0x10000:
+                n, d = _tdiv(n, 2), _tdiv(d, 2)
+            while d > 1 and (n > 0x10000 or n < -0x10000):
+                n, d = _tdiv(n, 2), _tdiv(d, 2)
+        self.n, self.d = n, d
+
+    def add(self, b):
+        return _Frac(self.n + b.n, self.d, True) if self.d == b.d else _Frac(self.n * b.d + b.n * self.d, self.d * b.d, True)
+
+    def sub(self, b):
+        return _Frac(self.n - b.n, self.d, True) if self.d == b.d else _Frac(self.n * b.d - b.n * self.d, self.d * b.d, True)
+
+    def addi(self, v):
+        return _Frac(self.n + v * self.d, self.d, True)
+
+    def divi(self, v):
+        return _Frac(self.n, self.d * v, True)
+
+    def round_down(self):
+        return _tdiv(self.n, self.d)
+
+    def round(self):
+        return _tdiv(self.n + _tdiv(self.d, 2), self.d)
+
+
+def _s32(v):
+    return v - (1 << 32) if v >= (1 << 31) else v
+
+
+def clap_window(c, w, h):
+    """(left, top, right, bottom) of a clap box on a w x h image: Box_clap::*_rounded (box.cc:3771-3804) + context.cc:1990-2003"""
+    caw, cah = _Frac(c[0], c[1]), _Frac(c[2], c[3])
+    hoff, voff = _Frac(_s32(c[4]), c[5]), _Frac(_s32(c[6]), c[7])
+    left = hoff.add(_Frac(w - 1, 2)).sub(caw.addi(-1).divi(2)).round_down()
+    right = caw.addi(-1).addi(left).round()
+    top = voff.add(_Frac(h - 1, 2)).sub(cah.addi(-1).divi(2)).round()
+    bottom = cah.addi(-1).addi(top).round()
+    return max(left, 0), max(top, 0), min(right, w - 1), min(bottom, h - 1)
+
+
+def _transform_all(planes, info):
+    """irot / imir / clap in ipma order, plane by plane (context.cc:1955-2016, pixelimage.cc:539-870); planes[0] has the
+    image size"""
+    nclap = 0
     for k in range(info.n_transforms):
         op = info.transforms[k]
+        H, W = planes[0].shape
         if op in (1, 2, 3):
-            plane = np.rot90(plane, op)          # anti-clockwise: out[y][x] = in[x][w-1-y] for one quarter turn
+            planes = [np.rot90(p, op) for p in planes]       # anti-clockwise: out[y][x] = in[x][w-1-y] for one quarter turn
         elif op == 4:
-            plane = plane[:, ::-1]               # "horizontal" direction: every row reversed
+            planes = [p[:, ::-1] for p in planes]            # "horizontal" direction: every row reversed
         elif op == 5:
-            plane = plane[::-1, :]
-    return np.ascontiguousarray(plane)
+            planes = [p[::-1, :] for p in planes]
+        elif op == 6:
+            l, t, r, b = clap_window(list(info.claps[nclap]), W, H)
+            nclap += 1
+            out = []
+            for p in planes:
+                ph, pw = p.shape
+                out.append(p[t * ph // H:b * ph // H + 1, l * pw // W:r * pw // W + 1])
+            planes = out
+    return [np.ascontiguousarray(p) for p in planes]
 
 
 def decode_rgb(data, out_format, item_id=None):

@@ -135,6 +135,11 @@ def imir(axis):
     return box(b"imir", bytes([axis & 1]))
 
 
+def clap(w_num, w_den, h_num, h_den, hoff_num, hoff_den, voff_num, voff_den):
+    """CleanAperture property"""
+    return box(b"clap", struct.pack(">IIIIiIiI", w_num, w_den, h_num, h_den, hoff_num, hoff_den, voff_num, voff_den))
+
+
 def single_image(stream, width, height, chroma_format=1, bit_depth=8, nclx=None, alpha_stream=None, alpha_chroma_format=0,
                  transforms=()):
     """transforms: property boxes (irot / imir) attached, in this order, to the image and to its alpha image"""
