@@ -325,8 +325,17 @@ def main():
     k0_ms = stage_last.get("k0_parse", 0.0)
     dom = max(kernels, key=kernels.get)
     achieved = alg[dom] / (kernels[dom] * 1e-3) / 1e9 if kernels[dom] > 0 else 0.0
+    # DRAM traffic of the dominant kernel per launch, from the committed ncu capture of this very configuration
+    traffic, traffic_src = None, None
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json"))).get(dom)
+        if t and t["images_per_step"] == args.images:
+            traffic, traffic_src = t["dram_bytes_read"] + t["dram_bytes_write"], t["source"]
+    except (OSError, ValueError, KeyError):
+        pass
     roofline = {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src,
+                "traffic": traffic, "traffic_unit": "bytes per launch (dram read + write, ncu)", "traffic_source": traffic_src,
+                "algorithmic_bytes_per_launch": alg[dom], "peak_source": peak_src,
                 "all_kernels": {k: {"ms": round(kernels[k], 4), "algorithmic_GBps": round(alg[k] / (kernels[k] * 1e-3) / 1e9, 1) if kernels[k] > 0 else None}
                                 for k in alg},
                 "k0_parse": {"ms": round(k0_ms, 4), "note": "device CABAC parse, once per upload, outside `value`, inside e2e; serial per substream: "
