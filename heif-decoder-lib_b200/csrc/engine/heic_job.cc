@@ -209,6 +209,24 @@ static hc_heic_job* job_create(hc_engine* e, int nfiles, const uint8_t* const* d
   if (nthreads < 1) nthreads = 1;
   nthreads = std::min<int>(nthreads, (int)j->items.size());
   const bool device_parse = hc_engine_get_option(e, "device_parse") != 0;
+  const int k0_max_critical = hc_engine_get_option(e, "k0_max_critical_ctbs");
+  bool device_parse_job = device_parse;
+  if (device_parse && host_share_arg < 0 && hc_engine_get_option(e, "host_share_pct") < 0) {
+    // A single job cannot overlap its host parse with K0 (K0 starts at hc_heic_job_run), so with the automatic setting
+    // it takes whichever side is expected to finish first: K0 costs its critical path (~3 ms per CTB of a chain, measured
+    // on B200) or its throughput (~1000 CTBs in flight), the host ~0.09 ms per CTB and thread. One 12 MP grid file parses
+    // faster on 16 host threads (17 ms vs 66 ms); from a handful of files on, the GPU wins.
+    double ctbs = 0, critical = 0;
+    for (const CodedItem& ci : j->items) {
+      const hc::HeifItem* it = j->files[ci.file]->item(ci.item_id);
+      if (!it) continue;
+      const double cw = (it->ispe_w + 63) / 64, ch = (it->ispe_h + 63) / 64;
+      ctbs += cw * ch;
+      critical = std::max(critical, cw + 2 * (ch - 1));
+    }
+    const double est_host = ctbs * 0.09 / nthreads, est_k0 = std::max(critical * 3.0, ctbs * 3.0 / 1000.0);
+    device_parse_job = est_k0 < est_host;
+  }
   const int host_share = !device_parse ? 0 : (host_share_arg >= 0 ? host_share_arg : std::max(0, hc_engine_get_option(e, "host_share_pct")));
   std::atomic<size_t> next{0};
   auto worker = [&]() {
@@ -220,12 +238,22 @@ static hc_heic_job* job_create(hc_engine* e, int nfiles, const uint8_t* const* d
       if (!err.empty()) { ci.error = err; continue; }
       // hybrid: while the GPU parses the previous batch, the host cores parse an evenly spread share of this one
       const bool to_host = host_share > 0 && ((i + 1) * (size_t)host_share) / 100 != (i * (size_t)host_share) / 100;
-      if (device_parse && !to_host) {
+      if (device_parse_job && !to_host) {
         // K0: only parameter sets and slice headers are read here; the GPU parses the slice data
         std::unique_ptr<hc_k0_picture> k(new hc_k0_picture);
         err = hc::k0_prepare(ci.stream.data(), ci.stream.size(), HC_STREAM_LENGTH_PREFIXED, k->hp);
         if (!err.empty()) { ci.error = err; continue; }
+        // K0 is serial per substream: a picture is worth parsing on the GPU when its critical path is short — CTB rows of
+        // a WPP picture advance two CTBs behind each other, a picture without WPP is ONE chain of all its CTBs (a 1080p
+        // picture: 510 CTBs x ~3 ms against ~40 ms on one host core). Long ones stay with the host parser.
+        bool short_enough = false;
         if (k->hp.eligible) {
+          const hc::k0::Pic& kp = k->hp.pic;
+          const bool rows = !k->hp.subs.empty() && (k->hp.subs[0].flags & hc::k0::SUB_ROW_CHAIN);
+          const int critical = rows ? kp.ctbs_w + 2 * (kp.ctbs_h - 1) : kp.ctbs_w * kp.ctbs_h;
+          short_enough = critical <= k0_max_critical;
+        }
+        if (k->hp.eligible && short_enough) {
           ci.k0 = std::move(k);
           std::vector<uint8_t>().swap(ci.stream);
           continue;
@@ -511,7 +539,7 @@ int hc_heic_decode_stream(hc_engine* e, int nfiles, const uint8_t* const* data, 
           c_host = c_host > 0 ? 0.5 * c_host + 0.5 * ch : ch;
           c_dev = c_dev > 0 ? 0.5 * c_dev + 0.5 * cd : cd;
           const int next = (int)(85.0 * c_dev / (c_host + c_dev) + 0.5);
-          share.store(std::max(3, std::min(50, next)));
+          share.store(std::max(3, std::min(90, next)));
           if (trace_on()) fprintf(stderr, "[heifcuda] batch %d: host %.1f ms, gpu %.1f ms at share %d%% -> %d%%\n", f.index, f.host_s * 1e3, gpu_ms, f.share, share.load());
         }
       }

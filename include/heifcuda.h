@@ -184,7 +184,10 @@ void hc_engine_destroy(hc_engine* e);
  * "host_share_pct" (environment HEIFCUDA_HOST_SHARE): with device_parse, this percentage of the coded items of every job
  * is parsed by the host threads instead, which run while the GPU is busy with the previous batch of
  * hc_heic_decode_stream (hybrid parse). Default -1 = automatic: none for a single hc_heic_job, and in
- * hc_heic_decode_stream a share that follows the measured host / GPU time per batch. */
+ * hc_heic_decode_stream a share that follows the measured host / GPU time per batch.
+ * "k0_max_critical_ctbs" (default 160): K0 is serial per substream, so hc_heic_job only hands it pictures whose parse
+ * critical path is at most this many CTBs (WPP: CTB columns + 2 x (CTB rows - 1); no WPP: all CTBs of the picture);
+ * the others stay with the host parser. */
 int hc_engine_set_option(hc_engine* e, const char* name, int value);
 int hc_engine_get_option(const hc_engine* e, const char* name);
 

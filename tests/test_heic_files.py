@@ -54,8 +54,10 @@ def test_gpu_heic_job_matches_reference(engine, want_alpha, device_parse):
     """All fixture files in ONE job (one upload, one launch sequence for every tile of every file); slice data
     parsed by K0 on the GPU (device_parse=1, the default) or by the host CABAC parser (0)."""
     engine.set_option("device_parse", device_parse)
+    engine.set_option("host_share_pct", 0)     # not "auto": a job this small would otherwise pick the host parser by itself
     job = hb.HeicJob(engine, [load(n) for n in NAMES], want_alpha=want_alpha, threads=4)
     engine.set_option("device_parse", 1)
+    engine.set_option("host_share_pct", -1)
     job.upload()
     job.run()
     for i, name in enumerate(NAMES):
