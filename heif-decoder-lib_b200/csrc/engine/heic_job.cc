@@ -474,8 +474,12 @@ int hc_heic_decode_stream(hc_engine* e, int nfiles, const uint8_t* const* data, 
   // batch b, so they parse a share of the coded items themselves. "auto" (engine option -1) starts at 20 % and follows
   // the measured ratio of GPU time to host time per batch, so that a rank with few host threads ends up near 0.
   const int share_opt = hc_engine_get_option(e, "host_share_pct");
-  std::atomic<int> share{share_opt >= 0 ? share_opt : 20};
-  double c_host = 0, c_dev = 0;
+  // static estimate (per coded 512 x 512 item, measured on B200 + this box's cores): device 0.14 ms, one host thread 6.6 ms
+  const int pool_threads = threads > 0 ? threads : std::max(1, (int)std::thread::hardware_concurrency());
+  const double c_dev0 = 0.14e-3, c_host0 = 6.6e-3 / pool_threads;
+  const int share0 = (int)(85.0 * c_dev0 / (c_host0 + c_dev0) + 0.5);
+  std::atomic<int> share{share_opt >= 0 ? share_opt : share0};
+  double c_host = c_host0, c_dev = c_dev0;
   struct Parsed { hc_heic_job* job = nullptr; std::string error; double seconds = 0; int share = 0; };
   auto parse_batch = [&](int b) -> Parsed {
     Parsed p;
@@ -536,10 +540,12 @@ int hc_heic_decode_stream(hc_engine* e, int nfiles, const uint8_t* const* data, 
           const double n_items = (double)j->items.size();
           const double n_host = std::max(1.0, n_items * f.share / 100.0), n_dev = std::max(1.0, n_items - n_items * f.share / 100.0);
           const double ch = f.host_s / n_host, cd = gpu_ms * 1e-3 / n_dev;
-          c_host = c_host > 0 ? 0.5 * c_host + 0.5 * ch : ch;
-          c_dev = c_dev > 0 ? 0.5 * c_dev + 0.5 * cd : cd;
+          // slow, outlier-resistant tracking: one noisy batch (a host thread descheduled, two K0 kernels overlapping on the
+          // GPU) must not swing the share
+          c_host = 0.8 * c_host + 0.2 * std::min(ch, 2.0 * c_host);
+          c_dev = 0.8 * c_dev + 0.2 * std::min(cd, 2.0 * c_dev);
           const int next = (int)(85.0 * c_dev / (c_host + c_dev) + 0.5);
-          share.store(std::max(3, std::min(90, next)));
+          share.store(std::max(2, std::min(90, next)));
           if (trace_on()) fprintf(stderr, "[heifcuda] batch %d: host %.1f ms, gpu %.1f ms at share %d%% -> %d%%\n", f.index, f.host_s * 1e3, gpu_ms, f.share, share.load());
         }
       }
