@@ -198,10 +198,27 @@ __device__ __forceinline__ void sao_picture(const BatchView& bv, const hc_pic& p
         };
         unsigned okmask = 0;
         if (nvalid == 8 && !self_quirk) {
-          // a full unit lies inside one CTB column: samples 1..6 have both neighbours in that column, so they share one
-          // verdict (only the row above / below can be foreign); samples 0 and 7 may also look into the CTB beside
-          const bool ok0 = sample_ok(0), okm = sample_ok(1), ok7 = sample_ok(7);
-          okmask = (ok0 ? 1u : 0u) | (okm ? 0x7eu : 0u) | (ok7 ? 0x80u : 0u);
+          // A full unit lies inside one CTB column. Which CTB does a neighbour fall into? 3 x 3 bits, (dy + 1) * 3 + dx + 1,
+          // the centre (this CTB) always usable, the others from the CTB's neighbour mask (a CTB beyond the picture edge
+          // has no bit; the edge of a partial CTB counts as its border). Samples 1..6 can only leave the CTB vertically,
+          // sample 0 also to the left, sample 7 also to the right.
+          const unsigned grid9 = 0x10u | ((nb & HC_NB_TL) ? 0x001u : 0u) | ((nb & HC_NB_T) ? 0x002u : 0u) | ((nb & HC_NB_TR) ? 0x004u : 0u) |
+                                 ((nb & HC_NB_L) ? 0x008u : 0u) | ((nb & HC_NB_R) ? 0x020u : 0u) | ((nb & HC_NB_BL) ? 0x040u : 0u) |
+                                 ((nb & HC_NB_B) ? 0x080u : 0u) | ((nb & HC_NB_BR) ? 0x100u : 0u);
+          const int cy1 = (vy && ly == 0) ? -1 : 0, cy2 = (vy && ly == lhei - 1) ? 1 : 0;   // first neighbour looks up, second down
+          auto okbit = [&](int cx, int cy) -> unsigned { return (grid9 >> ((cy + 1) * 3 + cx + 1)) & 1u; };
+          okmask = (okbit(0, cy1) & okbit(0, cy2)) ? 0xffu : 0u;
+          if (hx) {
+            const int lx0 = x0 & mw;
+            if (lx0 == 0) {
+              const unsigned o0 = hx < 0 ? (okbit(-1, cy1) & okbit(0, cy2)) : (okbit(0, cy1) & okbit(-1, cy2));
+              okmask = (okmask & ~1u) | o0;
+            }
+            if (lx0 + 8 == lwid) {
+              const unsigned o7 = hx > 0 ? (okbit(1, cy1) & okbit(0, cy2)) : (okbit(0, cy1) & okbit(1, cy2));
+              okmask = (okmask & ~0x80u) | (o7 << 7);
+            }
+          }
         } else {
 #pragma unroll
           for (int k = 0; k < 8; k++)
