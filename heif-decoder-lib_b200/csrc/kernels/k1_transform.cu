@@ -132,8 +132,10 @@ __device__ __forceinline__ void k1_block(const BatchView& bv, const uint32_t* __
 
 // The launch list holds `count` entries, or *count_ptr when that is non-null: lists built on the device by K0 are
 // consumed without a host round trip, by a grid sized for the list capacity whose CTAs stride over the real count.
+// Resident CTAs the register allocation must allow: the kernels wait on their sparse record loads (long-scoreboard
+// stalls), so occupancy is worth a few spills — 32x32: 156 -> 96 registers (5 CTAs), 16x16: 56 -> 40 (12 CTAs).
 template <int LOG2>
-__global__ void __launch_bounds__(K1_WARPS * 32)
+__global__ void __launch_bounds__(K1_WARPS * 32, LOG2 == 5 ? 8 : 16)
 k1_transform_kernel(BatchView bv, const uint32_t* __restrict__ tb_index, int count, const unsigned* __restrict__ count_ptr) {
   constexpr int N = 1 << LOG2;
   constexpr int PER_WARP = 32 / N;

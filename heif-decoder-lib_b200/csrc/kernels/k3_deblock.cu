@@ -227,7 +227,7 @@ __device__ void deblock_picture(const BatchView& bv, const hc_pic& pic, int plan
 }
 
 template <bool VERTICAL>
-__global__ void __launch_bounds__(256) k3_deblock_kernel(BatchView bv) {
+__global__ void __launch_bounds__(256, 8) k3_deblock_kernel(BatchView bv) {
   const hc_pic& pic = bv.pics[blockIdx.y];
   if (!(pic.flags & HC_PIC_HAS_DEBLOCK)) return;
   const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;

@@ -259,7 +259,7 @@ __device__ __forceinline__ void sao_picture(const BatchView& bv, const hc_pic& p
 // One warp per CTB (it walks the CTB's row groups), 8 CTBs per CTA, the picture descriptor staged in shared memory:
 // a CTA moves 8 x 4 KB instead of 2 KB, so the pass is no longer bound by CTA launch rate and descriptor loads
 // (the first version was: 147 K CTAs per 8 x 12 MP step, half of them empty chroma CTAs).
-__global__ void __launch_bounds__(256) k4_sao_kernel(BatchView bv) {
+__global__ void __launch_bounds__(256, 5) k4_sao_kernel(BatchView bv) {
   __shared__ hc_pic spic;
   {
     const uint32_t* src = reinterpret_cast<const uint32_t*>(bv.pics + blockIdx.y);
