@@ -139,7 +139,7 @@ __device__ __forceinline__ void process_block(const Geo& g, uint32_t w0, uint32_
   uint8_t* out = g.sm + store_off + yb * pitch + x * PS;
 
   if (w1 & BP_PCM) {
-#pragma unroll 4
+#pragma unroll 1
     for (int j = 0; j < ITER; j++) *reinterpret_cast<Pixel*>(out + j * RPI * pitch) = (Pixel)(uint16_t)res[s0 + 32 * j];
     __syncwarp();
     return;
@@ -217,7 +217,7 @@ __device__ __forceinline__ void process_block(const Geo& g, uint32_t w0, uint32_
   if (mode == 0) {
     const int tr = p[1 + nT], bl = p[-1 - nT];
     const int top = p[1 + x], hx = (x + 1) * tr + nT;
-#pragma unroll 4
+#pragma unroll 1
     for (int j = 0; j < ITER; j++) {
       const int y = yb + j * RPI;
       int v = ((nT - 1 - x) * p[-1 - y] + hx + (nT - 1 - y) * top + (y + 1) * bl) >> (LOG2 + 1);
@@ -231,7 +231,7 @@ __device__ __forceinline__ void process_block(const Geo& g, uint32_t w0, uint32_
     for (int o = nT >> 1; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
     const int dc = (sum + nT) >> (LOG2 + 1);
     const int top = (p[x + 1] + 3 * dc + 2) >> 2;
-#pragma unroll 4
+#pragma unroll 1
     for (int j = 0; j < ITER; j++) {
       const int y = yb + j * RPI;
       int v = dc;
@@ -252,7 +252,7 @@ __device__ __forceinline__ void process_block(const Geo& g, uint32_t w0, uint32_
       // modes 10 / 26: copy the reference, optional boundary filter on the first row / column
       const bool edge_flt = edge_ok && !(w1 & BP_NOEDGEFLT);
       const int p0 = p[0], p1 = p[sgn];
-#pragma unroll 4
+#pragma unroll 1
       for (int j = 0; j < ITER; j++) {
         const int y = yb + j * RPI;
         const int u = vertical ? x : y, w = vertical ? y : x;
@@ -263,7 +263,7 @@ __device__ __forceinline__ void process_block(const Geo& g, uint32_t w0, uint32_
       }
     } else if (angle > 0) {
       // the reference index never goes negative; (32a + 16) >> 5 == a covers iFact == 0
-#pragma unroll 4
+#pragma unroll 1
       for (int j = 0; j < ITER; j++) {
         const int y = yb + j * RPI;
         const int u = vertical ? x : y, w = vertical ? y : x;
@@ -276,7 +276,7 @@ __device__ __forceinline__ void process_block(const Geo& g, uint32_t w0, uint32_
     } else {
       // negative angles: indices below zero project onto the other reference through the inverse angle
       const int inv = c_inv_angle[mode - 11];
-#pragma unroll 4
+#pragma unroll 1
       for (int j = 0; j < ITER; j++) {
         const int y = yb + j * RPI;
         const int u = vertical ? x : y, w = vertical ? y : x;
