@@ -48,24 +48,22 @@ HC_D void store8(uint16_t* p, const int v[8]) {
   *reinterpret_cast<uint4*>(p) = w;
 }
 
+// One CTB of one colour plane by one warp: the geometry (crop / paste windows, CTB position, SAO parameters) is set up
+// once, then the warp walks the CTB's row groups. lane -> (8-sample unit in the CTB row, row inside the group).
 template <typename Pixel>
-__device__ __forceinline__ void sao_picture(const BatchView& bv, const hc_pic& pic, int c, unsigned warp_index, int lane) {
+__device__ __forceinline__ void sao_ctb(const BatchView& bv, const hc_pic& pic, int c, unsigned ctb, int lane) {
   const int sw = (c && (pic.chroma_format == 1 || pic.chroma_format == 2)) ? 1 : 0;   // log2 subsampling
   const int sh = (c && pic.chroma_format == 1) ? 1 : 0;
   const int SubW = 1 << sw, SubH = 1 << sh;
   const int width = pic.width >> sw, height = pic.height >> sh;  // coded plane size (multiples of 4)
   const int log2w = pic.log2_ctb - sw, log2h = pic.log2_ctb - sh;
-  // a warp covers (CTB width / 8) units x (256 / CTB width) rows of ONE CTB, so the SAO type / class /
+  // a warp pass covers (CTB width / 8) units x (256 / CTB width) rows of ONE CTB, so the SAO type / class /
   // offsets are warp-uniform and only the CTB-border handling differs between lanes
   const int lu = log2w - 3;                          // log2 units per CTB row (0..3)
-  const int rows = 32 >> lu;                         // rows per warp
-  const unsigned wpc = (unsigned)((1 << log2h) + rows - 1) / (unsigned)rows;   // warps per CTB
-  const unsigned ctb = warp_index / wpc, part = warp_index - ctb * wpc;
-  if (ctb >= (unsigned)pic.ctbs_w * pic.ctbs_h) return;
+  const int rows = 32 >> lu;                         // rows per warp pass
   const int ctby = (int)(ctb / pic.ctbs_w), ctbx = (int)(ctb - (unsigned)ctby * pic.ctbs_w);
   const int x0 = (ctbx << log2w) + ((lane & ((1 << lu) - 1)) << 3);
-  const int y = (ctby << log2h) + (int)part * rows + (lane >> lu);
-  if (x0 >= width || y >= height || (y >> log2h) != ctby) return;
+  if (x0 >= width) return;
 
   // crop window and destination clip, in samples of this plane (context.cc:2467-2497)
   const int cx0 = pic.crop_x >> sw, cy0 = pic.crop_y >> sh;
@@ -73,8 +71,6 @@ __device__ __forceinline__ void sao_picture(const BatchView& bv, const hc_pic& p
   const int dx0 = (pic.dst_x + SubW - 1) >> sw, dy0 = (pic.dst_y + SubH - 1) >> sh;
   const int dw = (pic.dst_w + SubW - 1) >> sw, dh = (pic.dst_h + SubH - 1) >> sh;
   const int copy_w = min(cw, dw - dx0), copy_h = min(ch, dh - dy0);
-  const int oy = y - cy0;
-  if (oy < 0 || oy >= copy_h) return;
   const int ox0 = x0 - cx0;                         // destination column of sample 0 of the unit
   if (ox0 + 8 <= 0 || ox0 >= copy_w) return;
 
@@ -86,7 +82,11 @@ __device__ __forceinline__ void sao_picture(const BatchView& bv, const hc_pic& p
   const int maxv = (1 << bit_depth) - 1;
   const hc_ctu& ctu = bv.ctus[pic.ctu_base + ctbx + ctby * pic.ctbs_w];
   const int nvalid = min(8, width - x0);            // 4 or 8
+  const int y_end = min(height, (ctby + 1) << log2h);
 
+  for (int y = (ctby << log2h) + (lane >> lu); y < y_end; y += rows) {
+  const int oy = y - cy0;
+  if (oy < 0 || oy >= copy_h) continue;
   const Pixel* row = src + (size_t)y * sstride + x0;
   int v[8];
   if (nvalid == 8) load8<Pixel>(row, v);
@@ -254,6 +254,7 @@ __device__ __forceinline__ void sao_picture(const BatchView& bv, const hc_pic& p
     for (int k = 0; k < 8; k++)
       if (k < nvalid && ox0 + k >= 0 && ox0 + k < copy_w) out[k] = (Pixel)v[k];
   }
+  }
 }
 
 // One warp per CTB (it walks the CTB's row groups), 8 CTBs per CTA, the picture descriptor staged in shared memory:
@@ -274,14 +275,8 @@ __global__ void __launch_bounds__(256, 5) k4_sao_kernel(BatchView bv) {
   const unsigned ctb = blockIdx.x * 8u + (threadIdx.x >> 5);
   if (ctb >= (unsigned)pic.ctbs_w * pic.ctbs_h) return;
   const int lane = threadIdx.x & 31;
-  const int sw = (c && (pic.chroma_format == 1 || pic.chroma_format == 2)) ? 1 : 0, sh = (c && pic.chroma_format == 1) ? 1 : 0;
-  const int rows = 32 >> (pic.log2_ctb - sw - 3);                                        // rows per warp pass (sao_picture)
-  const unsigned wpc = (unsigned)((1 << (pic.log2_ctb - sh)) + rows - 1) / (unsigned)rows;   // passes per CTB
-  const bool eight = pic.bit_depth_y == 8 && pic.bit_depth_c == 8;
-  for (unsigned part = 0; part < wpc; part++) {
-    if (eight) sao_picture<uint8_t>(bv, pic, c, ctb * wpc + part, lane);
-    else sao_picture<uint16_t>(bv, pic, c, ctb * wpc + part, lane);
-  }
+  if (pic.bit_depth_y == 8 && pic.bit_depth_c == 8) sao_ctb<uint8_t>(bv, pic, c, ctb, lane);
+  else sao_ctb<uint16_t>(bv, pic, c, ctb, lane);
 }
 
 // max_ctbs = max over pictures of the number of CTBs
