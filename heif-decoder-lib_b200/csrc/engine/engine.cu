@@ -45,7 +45,9 @@ struct hc_engine {
   int device = 0;
   std::mutex mu;
   std::vector<Block> free_dev, free_pin;
-  std::vector<cudaStream_t> free_streams;
+  std::vector<cudaStream_t> free_streams;      // batch streams (highest priority: K1..K5, copies)
+  std::vector<cudaStream_t> free_k0_streams;   // K0 streams (lowest priority), see hc_batch_reconstruct_async
+  int prio_lo = 0, prio_hi = 0;
   std::vector<cudaEvent_t> free_events;     // events are recycled: a batch needs 14 and the plugin creates one batch per tile
   hc::k0::Tables* d_k0_tables = nullptr;   // read-only tables of the device parser
   int device_parse = 1;                    // hc_heic_job: let K0 parse every picture it accepts
@@ -141,6 +143,8 @@ struct Placement {
 struct hc_batch {
   hc_engine* eng = nullptr;
   cudaStream_t stream = nullptr;
+  cudaStream_t k0_stream = nullptr;   // taken on the first K0 launch
+  cudaEvent_t ev_fork = nullptr;
   std::vector<Canvas> canvases;
   std::vector<Placement> pics;
   std::vector<hc_pic> hpics;  // host copy with bases / placement filled
@@ -222,6 +226,7 @@ hc_engine* hc_engine_create(int device) {
   if (!eng) return nullptr;
   eng->device = device;
   cudaDeviceGetAttribute(&eng->sm_count, cudaDevAttrMultiProcessorCount, device);
+  cudaDeviceGetStreamPriorityRange(&eng->prio_lo, &eng->prio_hi);   // (least, greatest): greatest is numerically lowest
   if (const char* m = getenv("HEIFCUDA_PARSER")) eng->device_parse = strcmp(m, "host") != 0;
   if (const char* m = getenv("HEIFCUDA_HOST_SHARE")) eng->host_share_pct = std::max(-1, std::min(100, atoi(m)));
   if (!cuda_ok(cudaMalloc(&eng->d_k0_tables, sizeof(hc::k0::Tables)), "cudaMalloc(K0 tables)") ||
@@ -238,6 +243,7 @@ void hc_engine_destroy(hc_engine* e) {
   for (auto& b : e->free_dev) cudaFree(b.p);
   for (auto& b : e->free_pin) cudaFreeHost(b.p);
   for (auto s : e->free_streams) cudaStreamDestroy(s);
+  for (auto s : e->free_k0_streams) cudaStreamDestroy(s);
   for (auto ev : e->free_events) cudaEventDestroy(ev);
   if (e->d_k0_tables) cudaFree(e->d_k0_tables);
   delete e;
@@ -269,7 +275,7 @@ hc_batch* hc_batch_create(hc_engine* e) {
     std::lock_guard<std::mutex> lk(e->mu);
     if (!e->free_streams.empty()) { b->stream = e->free_streams.back(); e->free_streams.pop_back(); }
   }
-  if (!b->stream && !cuda_ok(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking), "cudaStreamCreate")) {
+  if (!b->stream && !cuda_ok(cudaStreamCreateWithPriority(&b->stream, cudaStreamNonBlocking, e->prio_hi), "cudaStreamCreate")) {
     delete b;
     return nullptr;
   }
@@ -277,6 +283,7 @@ hc_batch* hc_batch_create(hc_engine* e) {
   for (auto& ev : b->ev) ok &= (ev = e->take_event()) != nullptr;
   for (auto& ev : b->timer) ok &= (ev = e->take_event()) != nullptr;
   for (auto& ev : b->ev_k0) ok &= (ev = e->take_event()) != nullptr;
+  ok &= (b->ev_fork = e->take_event()) != nullptr;
   for (auto& ev : b->ev_d2h) ok &= (ev = e->take_event()) != nullptr;
   if (!ok) { hc::set_last_error("cudaEventCreate failed"); hc_batch_destroy(b); return nullptr; }
   return b;
@@ -286,15 +293,18 @@ void hc_batch_destroy(hc_batch* b) {
   if (!b) return;
   cudaSetDevice(b->eng->device);
   cudaStreamSynchronize(b->stream);
+  if (b->k0_stream) cudaStreamSynchronize(b->k0_stream);
   release_blocks(b);
   for (auto& ev : b->ev) b->eng->give_event(ev);
   for (auto& ev : b->timer) b->eng->give_event(ev);
   for (auto& ev : b->ev_k0) b->eng->give_event(ev);
+  b->eng->give_event(b->ev_fork);
   for (auto& ev : b->ev_d2h) b->eng->give_event(ev);
   for (auto& p : b->csc_events) { b->eng->give_event(p.first); b->eng->give_event(p.second); }
   {
     std::lock_guard<std::mutex> lk(b->eng->mu);
     b->eng->free_streams.push_back(b->stream);
+    if (b->k0_stream) b->eng->free_k0_streams.push_back(b->k0_stream);
   }
   delete b;
 }
@@ -752,13 +762,29 @@ int hc_batch_reconstruct_async(hc_batch* b, int stages) {
   if (b->nk0 && !b->k0_done) {
     // K0: the slice data of the pictures added as bitstreams is parsed on the device, straight into their record
     // regions; afterwards the records stay resident (a second hc_batch_reconstruct re-uses them)
-    cudaEventRecord(b->ev_k0[0], s);
-    cudaMemsetAsync(D + b->k0_ones_off, 1, b->k0_ones_bytes, s);
-    cudaMemsetAsync(D + b->k0_zero_off, 0, b->k0_zero_bytes, s);
-    cudaMemsetAsync(D + b->k0_ctu_off, 0, b->k0_ctu_bytes, s);
-    hc::launch_k0(b->eng->d_k0_tables, b->d_k0_pics, b->d_k0_subs, b->d_k0_chains, b->nchains, s);
-    hc::launch_k0_finish(b->d_k0_pics, b->nk0, (int)b->k0_max_ctbs, s);
-    cudaEventRecord(b->ev_k0[1], s);
+    // K0 runs on a stream of the LOWEST priority, K1..K5 and the copies on the batch stream (highest): K0's chains live for
+    // tens of milliseconds and fill the register file, so when the K0 kernels of consecutive batches overlap (the tail of
+    // one wavefront leaves most chain slots idle, the next batch's chains take them) the short streaming kernels of the
+    // finished batch get every CTA slot that frees up first instead of queueing behind the next parse.
+    if (!b->k0_stream) {
+      {
+        std::lock_guard<std::mutex> lk(b->eng->mu);
+        if (!b->eng->free_k0_streams.empty()) { b->k0_stream = b->eng->free_k0_streams.back(); b->eng->free_k0_streams.pop_back(); }
+      }
+      if (!b->k0_stream && !cuda_ok(cudaStreamCreateWithPriority(&b->k0_stream, cudaStreamNonBlocking, b->eng->prio_lo), "cudaStreamCreate(K0)"))
+        return HC_ERR_CUDA;
+    }
+    cudaStream_t ks = b->k0_stream;
+    cudaEventRecord(b->ev_fork, s);          // upload + progress reset
+    cudaStreamWaitEvent(ks, b->ev_fork, 0);
+    cudaEventRecord(b->ev_k0[0], ks);
+    cudaMemsetAsync(D + b->k0_ones_off, 1, b->k0_ones_bytes, ks);
+    cudaMemsetAsync(D + b->k0_zero_off, 0, b->k0_zero_bytes, ks);
+    cudaMemsetAsync(D + b->k0_ctu_off, 0, b->k0_ctu_bytes, ks);
+    hc::launch_k0(b->eng->d_k0_tables, b->d_k0_pics, b->d_k0_subs, b->d_k0_chains, b->nchains, ks);
+    hc::launch_k0_finish(b->d_k0_pics, b->nk0, (int)b->k0_max_ctbs, ks);
+    cudaEventRecord(b->ev_k0[1], ks);
+    cudaStreamWaitEvent(s, b->ev_k0[1], 0);
     const size_t status_bytes = 4 * ((size_t)b->nk0 + 4);
     if (!cuda_ok(cudaMemcpyAsync(b->h_status.p, D + b->k0_status_off, status_bytes, cudaMemcpyDeviceToHost, s), "cudaMemcpyAsync(K0 status)"))
       return HC_ERR_CUDA;

@@ -13,7 +13,9 @@
 #include <cstring>
 #include <cstdlib>
 #include <chrono>
+#include <deque>
 #include <future>
+#include <mutex>
 #include <thread>
 #include <vector>
 #include "../capi/capi_internal.h"
@@ -474,16 +476,19 @@ int hc_heic_decode_stream(hc_engine* e, int nfiles, const uint8_t* const* data, 
   // batch b, so they parse a share of the coded items themselves. "auto" (engine option -1) starts at 20 % and follows
   // the measured ratio of GPU time to host time per batch, so that a rank with few host threads ends up near 0.
   const int share_opt = hc_engine_get_option(e, "host_share_pct");
-  // static estimate (per coded 512 x 512 item, measured on B200 + this box's cores): device 0.14 ms, one host thread 6.6 ms
+  // static prior (per coded 512 x 512 item, measured on B200 + this box's cores): device 0.105 ms in the steady state of
+  // the pipeline (K0-bound: 80 ms per 768 items), one host thread 6.6 ms
   const int pool_threads = threads > 0 ? threads : std::max(1, (int)std::thread::hardware_concurrency());
-  const double c_dev0 = 0.14e-3, c_host0 = 6.6e-3 / pool_threads;
-  const int share0 = (int)(85.0 * c_dev0 / (c_host0 + c_dev0) + 0.5);
+  const double c_dev0 = 0.105e-3, c_host0 = 6.6e-3 / pool_threads;
+  const int share0 = (int)(90.0 * c_dev0 / (c_host0 + c_dev0) + 0.5);
   std::atomic<int> share{share_opt >= 0 ? share_opt : share0};
   double c_host = c_host0, c_dev = c_dev0;
+  std::mutex parse_mu;
   struct Parsed { hc_heic_job* job = nullptr; std::string error; double seconds = 0; int share = 0; };
   auto parse_batch = [&](int b) -> Parsed {
     Parsed p;
     const int first = b * files_per_batch, n = std::min(files_per_batch, nfiles - first);
+    std::lock_guard<std::mutex> one_at_a_time(parse_mu);   // the look-ahead is two batches deep, the thread pool is one
     const auto t0 = clock::now();
     p.share = nbatches > 1 ? share.load() : 0;
     p.job = job_create(e, n, data + first, sizes + first, want_alpha, threads, 0, -1, p.share);
@@ -492,16 +497,21 @@ int hc_heic_decode_stream(hc_engine* e, int nfiles, const uint8_t* const* data, 
     return p;
   };
 
-  // stage 2 (this thread): submit — upload, [K0,] K1..K5 and the read-back into one of two pinned buffers are only
-  // ENQUEUED on the batch's stream; stage 3 (this thread, one batch behind): deliver — wait for the stream, hand the
-  // images out, release the batch. So the GPU parses / reconstructs batch b+1 while batch b is copied back and consumed.
-  struct InFlight { hc_heic_job* job = nullptr; int index = 0; int slot = 0; std::vector<size_t> offs; clock::time_point t0; double host_s = 0; int share = 0; };
-  void* pinned[2] = {nullptr, nullptr};
-  size_t pinned_cap[2] = {0, 0};
+  // stage 2 (this thread): submit — upload, [K0,] K1..K5 and the read-back into one of DEPTH pinned buffers are only
+  // ENQUEUED on the batch's streams; stage 3 (this thread, DEPTH-1 batches behind): deliver — wait for the stream, hand the
+  // images out, release the batch. DEPTH = 3 keeps two batches queued on the GPU behind the one that is about to be
+  // delivered: K0 is a wavefront per picture, so the head and the tail of one batch's K0 leave most of the resident chain
+  // slots idle (16 files: 22 CTB slots of time for 16.6 slots of work); with the next batch's K0 already queued on its own
+  // low-priority stream, its chains take those slots, and K1..K5 + D2H of the finished batch run at high priority meanwhile.
+  constexpr int DEPTH = 3;
+  struct InFlight { hc_heic_job* job = nullptr; int index = 0; int slot = 0; std::vector<size_t> offs; clock::time_point t0; double host_s = 0, host_wait_s = 0; int share = 0; int rc = HC_OK; };
+  void* pinned[DEPTH] = {};
+  size_t pinned_cap[DEPTH] = {};
+  double t_done[3] = {0, 0, 0};   // host time at which the last three batches were seen complete
   int rc = HC_OK;
   std::string err;
   auto submit = [&](hc_heic_job* j, int b, InFlight& f) -> int {
-    f.job = j; f.index = b; f.slot = b & 1; f.t0 = clock::now();
+    f.job = j; f.index = b; f.slot = b % DEPTH; f.t0 = clock::now();
     size_t need = 0;
     f.offs.resize(j->images.size());
     for (size_t i = 0; i < j->images.size(); i++) {
@@ -534,19 +544,23 @@ int hc_heic_decode_stream(hc_engine* e, int nfiles, const uint8_t* const* data, 
       if (hc_heic_job_stage_ms(j, ms) == HC_OK) {
         const double gpu_ms = ms[1] + ms[2] + ms[3] + ms[4] + ms[5] + ms[7];
         st.device_ms += gpu_ms;
-        if (share_opt < 0 && f.index > 2 && f.host_s > 0 && gpu_ms > 0) {
-          // cost per coded item on either side, smoothed; the balanced share is c_dev / (c_host + c_dev). The estimate
-          // does not depend on the share the batch was parsed with, so the two-batch lag of the pipeline is harmless.
+        t_done[0] = t_done[1]; t_done[1] = t_done[2]; t_done[2] = tb;
+        if (share_opt < 0 && f.index > DEPTH && f.host_s > 0 && t_done[0] > 0) {
+          // Cost per coded item on either side, smoothed; the balanced share is c_dev / (c_host + c_dev). The K0 kernels of
+          // consecutive batches overlap, so a batch's own event times say little; what the device costs per item is the
+          // pipeline period (completion to completion, averaged over two batches because overlapping batches tend to finish
+          // in pairs) — but only while the GPU is what the pipeline waits for, i.e. this thread did not have to wait for the
+          // host parse of the batch.
           const double n_items = (double)j->items.size();
           const double n_host = std::max(1.0, n_items * f.share / 100.0), n_dev = std::max(1.0, n_items - n_items * f.share / 100.0);
-          const double ch = f.host_s / n_host, cd = gpu_ms * 1e-3 / n_dev;
-          // slow, outlier-resistant tracking: one noisy batch (a host thread descheduled, two K0 kernels overlapping on the
-          // GPU) must not swing the share
-          c_host = 0.8 * c_host + 0.2 * std::min(ch, 2.0 * c_host);
-          c_dev = 0.8 * c_dev + 0.2 * std::min(cd, 2.0 * c_dev);
-          const int next = (int)(85.0 * c_dev / (c_host + c_dev) + 0.5);
+          const double period = (t_done[2] - t_done[0]) / 2, ch = f.host_s / n_host, cd = period / n_dev;
+          // slow, outlier-resistant tracking: one noisy batch (a host thread descheduled) must not swing the share
+          c_host = 0.7 * c_host + 0.3 * std::min(ch, 2.0 * c_host);
+          const bool gpu_bound = f.host_wait_s < 0.05 * period;
+          if (gpu_bound) c_dev = 0.7 * c_dev + 0.3 * std::min(cd, 2.0 * c_dev);
+          const int next = (int)(90.0 * c_dev / (c_host + c_dev) + 0.5);
           share.store(std::max(2, std::min(90, next)));
-          if (trace_on()) fprintf(stderr, "[heifcuda] batch %d: host %.1f ms, gpu %.1f ms at share %d%% -> %d%%\n", f.index, f.host_s * 1e3, gpu_ms, f.share, share.load());
+          if (trace_on()) fprintf(stderr, "[heifcuda] batch %d: host %.1f ms (waited %.1f ms for it), period %.1f ms, own gpu events %.1f ms, share %d%% -> %d%%\n", f.index, f.host_s * 1e3, f.host_wait_s * 1e3, period * 1e3, gpu_ms, f.share, share.load());
         }
       }
       st.bytes_h2d += hc_heic_job_upload_bytes(j);
@@ -569,26 +583,41 @@ int hc_heic_decode_stream(hc_engine* e, int nfiles, const uint8_t* const* data, 
     f.job = nullptr;
   };
 
-  InFlight prev, cur_f;
-  int prev_rc = HC_OK;
-  std::future<Parsed> ahead = std::async(std::launch::async, parse_batch, 0);
+  InFlight ring[DEPTH];
+  // the host side runs up to two batches ahead of the submit stage: completions of overlapping batches come in bursts,
+  // and a single batch of look-ahead left this thread waiting for the parser right after every burst
+  constexpr int PARSE_AHEAD = 2;
+  std::deque<std::future<Parsed>> ahead;
+  int next_parse = 0;
+  auto top_up = [&]() {
+    while ((int)ahead.size() < PARSE_AHEAD && next_parse < nbatches) ahead.push_back(std::async(std::launch::async, parse_batch, next_parse++));
+  };
+  top_up();
   for (int b = 0; b < nbatches; b++) {
-    Parsed cur = ahead.get();
-    if (b + 1 < nbatches) ahead = std::async(std::launch::async, parse_batch, b + 1);
+    const auto tw = clock::now();
+    Parsed cur = ahead.front().get();
+    ahead.pop_front();
+    const double host_wait = secs(tw, clock::now());
+    top_up();
     st.seconds_parse += cur.seconds;
     if (!cur.job) {
       if (rc == HC_OK) { rc = HC_ERR_BITSTREAM; err = "batch " + std::to_string(b) + ": " + cur.error; }
       continue;   // keep draining the pipeline
     }
     if (rc != HC_OK) { hc_heic_job_destroy(cur.job); continue; }
-    cur_f.host_s = cur.seconds;
-    cur_f.share = cur.share;
-    const int r = submit(cur.job, b, cur_f);
-    if (prev.job) deliver(prev, prev_rc);
-    prev = std::move(cur_f);
-    prev_rc = r;
+    InFlight& f = ring[b % DEPTH];
+    if (f.job) deliver(f, f.rc);    // batch b - DEPTH (only after a skipped batch; normally delivered below)
+    f.host_s = cur.seconds;
+    f.host_wait_s = host_wait;
+    f.share = cur.share;
+    f.rc = submit(cur.job, b, f);
+    InFlight& o = ring[(b + 1) % DEPTH];   // batch b - (DEPTH - 1)
+    if (o.job) deliver(o, o.rc);
   }
-  if (prev.job) deliver(prev, prev_rc);
+  for (int k = 1; k <= DEPTH; k++) {       // drain in submission order
+    InFlight& o = ring[(nbatches + k) % DEPTH];
+    if (o.job) deliver(o, o.rc);
+  }
   for (void* p : pinned)
     if (p) hc_host_free(p);
   st.seconds_total = secs(t_begin, clock::now());

@@ -128,13 +128,17 @@ HC_D int k0_clz(unsigned v) { return __clz((int)v); }
 HC_D int progress_load(const int* p) { return ld_acquire_s32(p); }
 HC_D void progress_store(int* p, int v) { __threadfence(); st_release_s32(p, v); }
 HC_D unsigned list_reserve(unsigned int* counter, unsigned n) { return atomicAdd(counter, n); }
-HC_D void backoff() { __nanosleep(400); }
+// A waiting chain polls a progress word of the row above. A CTB takes milliseconds to parse, so the poll interval grows
+// to ~16 us: the first version polled every ~80 ns (__nanosleep(400) returns much earlier than asked), and the wait loops
+// of the chains that cannot start yet issued as many instructions — and L2 requests on a handful of hot words — as all
+// working chains together (ncu: 14.3 G of 29.7 G warp instructions of an 8 x 12 MP batch).
+HC_D void backoff(unsigned& ns) { __nanosleep(ns); if (ns < 16384u) ns <<= 1; }
 #else
 HC_HD int k0_clz(unsigned v) { return __builtin_clz(v); }
 HC_HD int progress_load(const int* p) { return *p; }
 HC_HD void progress_store(int* p, int v) { *p = v; }
 HC_HD unsigned list_reserve(unsigned int* counter, unsigned n) { const unsigned r = *counter; *counter += n; return r; }
-HC_HD void backoff() {}
+HC_HD void backoff(unsigned&) {}
 #endif
 
 // Per-chain scratch. On the device it lives in shared memory next to ONE copy of the tables per CTA (k0_parse.cu),
@@ -1059,7 +1063,8 @@ struct Parser {
         if (row_chain && ctb_y > 0) {
           // wavefront: the row above must be two CTBs ahead (its context table, split depths and SAO parameters)
           const int need = ctb_x + 2 < p.ctbs_w ? ctb_x + 2 : p.ctbs_w;
-          K0_LOOP while (progress_load(p.progress + ctb_y - 1) < need) backoff();
+          unsigned ns = 256;
+          K0_LOOP while (progress_load(p.progress + ctb_y - 1) < need) backoff(ns);
         }
         if (p.entropy_coding_sync && ctb_x == 0 && ctb_y >= 1 && !(first_of_independent && ctb_rs == slice().segment_address)) {
           if (p.ctbs_w > 1) {
