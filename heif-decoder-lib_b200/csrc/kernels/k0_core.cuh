@@ -145,7 +145,18 @@ HC_HD void backoff(unsigned&) {}
 // so every table lookup, context-state access and parameter read of the hot loops is an LDS / STS with a
 // compile-time-known address space; on the host it is a member of the parser.
 constexpr int TB_CAP_MAX = 768;      // transform blocks of one CTB: 64x64 4:4:4 in 4x4 blocks
+// Device build: the arithmetic decoder's registers live HERE, not in the parser object (see CabacDev below).
+struct alignas(16) CabState {
+  unsigned long long value;          // offset + look-ahead bits, as in Cabac
+  uint32_t range;
+  int avail;
+  const uint8_t* next;               // next byte of the substream to move into `value`
+  const uint8_t* start;
+  const uint8_t* end;
+  uint32_t pad[2];
+};
 struct Scratch {
+  CabState cab;
   uint8_t ctx[CTX_BYTES];            // CABAC context states
   Pic pic;                           // copy of the picture descriptor
   Slice slice;                       // copy of the current slice segment descriptor
@@ -228,6 +239,7 @@ struct Cabac {
     refill();
     return (int)((st & 1) ^ is_lps);
   }
+  HC_HD int bin(const Tables& t, uint8_t* ctx, int i) { return bin(t, ctx[i]); }
   HC_HD int bypass() {
     avail--;
     const unsigned long long scaled = (unsigned long long)range << avail;
@@ -266,6 +278,152 @@ struct Cabac {
     return 0;
   }
 };
+
+
+#if defined(__CUDACC__)
+// ---- device form of the arithmetic decoder -------------------------------------------------------------------
+// K0 is one lane per warp and, with every resident chain working, bound by INSTRUCTION FETCH (ncu at 32 files per batch:
+// no_instruction is 49 % of the stall samples, and the kernel takes the same 143 ms at 16, 20, 24, 28 and 32 chains per
+// SM): every warp of an SM partition walks its own part of a 40 KB hot path, so the 6 KB L0 / 32 KB L1.5 instruction
+// caches miss all the time. 42 % of the executed instructions were copies of bin() + refill() inlined at 27 call sites.
+// Here the decoder is a handful of small functions that are NOT inlined and keep their state (value / range / avail /
+// byte pointer) in the chain's shared-memory scratch: one copy of the hot code for all call sites and all warps, and no
+// decoder registers held across the syntax functions.
+// Explicit shared-space accesses with 32-bit addresses: through a generic pointer every function recomputed the shared
+// window (two S2R + LEA) before its first access.
+HC_D uint4 lds128(uint32_t a) { uint4 v; asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory"); return v; }
+HC_D void sts128(uint32_t a, uint4 v) { asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory"); }
+HC_D uint2 lds64(uint32_t a) { uint2 v; asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a) : "memory"); return v; }
+HC_D void sts64(uint32_t a, uint2 v) { asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(a), "r"(v.x), "r"(v.y) : "memory"); }
+HC_D uint32_t lds32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
+HC_D uint32_t lds16(uint32_t a) { uint32_t v; asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
+HC_D uint32_t lds8(uint32_t a) { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
+HC_D void sts8(uint32_t a, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+
+// `sa` = shared-space address of the chain's CabState (the Scratch starts with it), `ta` = of the CTA's Tables
+constexpr uint32_t CAB_NEXT = (uint32_t)offsetof(CabState, next), CAB_CTX = (uint32_t)offsetof(Scratch, ctx);
+constexpr uint32_t TAB_LPS = (uint32_t)offsetof(Tables, range_lps), TAB_NEXT = (uint32_t)offsetof(Tables, next_state), TAB_RECIP = (uint32_t)offsetof(Tables, recip);
+
+static __device__ __noinline__ uint32_t cab_next32(uint32_t sa) {
+  const uint2 pv = lds64(sa + CAB_NEXT);
+  const unsigned long long pa = ((unsigned long long)pv.y << 32) | pv.x;
+  const unsigned a = pv.x & 3u;
+  const uint32_t* w = reinterpret_cast<const uint32_t*>(pa - a);
+  const uint32_t hi = __byte_perm(__ldg(w), 0, 0x0123), lo = __byte_perm(__ldg(w + 1), 0, 0x0123);
+  const unsigned long long pn = pa + 4;
+  sts64(sa + CAB_NEXT, make_uint2((uint32_t)pn, (uint32_t)(pn >> 32)));
+  return __funnelshift_l(lo, hi, 8 * a);
+}
+#define K0_CAB_LOAD  const uint4 s_ = lds128(sa); unsigned long long value = ((unsigned long long)s_.y << 32) | s_.x; uint32_t range = s_.z; int avail = (int)s_.w;
+#define K0_CAB_REFILL if (avail < 16) { value = (value << 32) | cab_next32(sa); avail += 32; }
+#define K0_CAB_STORE sts128(sa, make_uint4((uint32_t)value, (uint32_t)(value >> 32), range, (uint32_t)avail));
+
+static __device__ __noinline__ int cab_bin(uint32_t sa, uint32_t ta, int ci) {
+  const uint32_t sp = sa + CAB_CTX + (uint32_t)ci;
+  const uint32_t st = lds8(sp);
+  K0_CAB_LOAD
+  const uint32_t lps = lds8(ta + TAB_LPS + ((st >> 1) << 2) + ((range >> 6) & 3));
+  const uint32_t nxt = lds16(ta + TAB_NEXT + (st << 1));   // both successors; picked below
+  const uint32_t rmps = range - lps;
+  const unsigned long long scaled = (unsigned long long)rmps << avail;
+  const uint32_t is_lps = value >= scaled;
+  if (is_lps) value -= scaled;
+  const uint32_t r = is_lps ? lps : rmps;
+  const int n = __clz((int)r) - 23;
+  range = r << n;
+  avail -= n;
+  sts8(sp, is_lps ? nxt >> 8 : nxt & 0xffu);
+  K0_CAB_REFILL
+  K0_CAB_STORE
+  return (int)((st & 1) ^ is_lps);
+}
+static __device__ __noinline__ int cab_bypass(uint32_t sa) {
+  K0_CAB_LOAD
+  avail--;
+  const unsigned long long scaled = (unsigned long long)range << avail;
+  int b = 0;
+  if (value >= scaled) { value -= scaled; b = 1; }
+  K0_CAB_REFILL
+  K0_CAB_STORE
+  return b;
+}
+static __device__ __noinline__ uint32_t cab_bypass_bits(uint32_t sa, uint32_t ta, int n) {
+  K0_CAB_LOAD
+  const unsigned long long recip = lds32(ta + TAB_RECIP + ((range - 256) << 2));
+  uint32_t out = 0;
+  K0_LOOP while (n > 0) {
+    const int k = n > 16 ? 16 : n;
+    avail -= k;
+    const uint32_t q = (uint32_t)(((unsigned long long)(uint32_t)(value >> avail) * recip) >> 34);
+    value -= (unsigned long long)(q * range) << avail;
+    out = (out << k) | q;
+    K0_CAB_REFILL
+    n -= k;
+  }
+  K0_CAB_STORE
+  return out;
+}
+static __device__ __noinline__ uint32_t cab_peek16(uint32_t sa, uint32_t ta) {
+  const uint4 s_ = lds128(sa);
+  const unsigned long long value = ((unsigned long long)s_.y << 32) | s_.x;
+  const unsigned long long recip = lds32(ta + TAB_RECIP + ((s_.z - 256) << 2));
+  return (uint32_t)(((unsigned long long)(uint32_t)(value >> ((int)s_.w - 16)) * recip) >> 34);
+}
+static __device__ __noinline__ void cab_consume(uint32_t sa, int n, uint32_t bins) {
+  K0_CAB_LOAD
+  avail -= n;
+  value -= (unsigned long long)(bins * range) << avail;
+  K0_CAB_REFILL
+  K0_CAB_STORE
+}
+static __device__ __noinline__ int cab_terminate(uint32_t sa) {
+  K0_CAB_LOAD
+  range -= 2;
+  const unsigned long long scaled = (unsigned long long)range << avail;
+  int r = 1;
+  if (value < scaled) {
+    r = 0;
+    if (range < 256) { range <<= 1; avail--; }
+    K0_CAB_REFILL
+  }
+  K0_CAB_STORE
+  return r;
+}
+#undef K0_CAB_LOAD
+#undef K0_CAB_REFILL
+#undef K0_CAB_STORE
+
+// Same interface as Cabac; its only state are the two shared-space addresses (set once per chain, k0_parse.cu), so
+// copying it in and out of the hot functions is free.
+struct CabacDev {
+  uint32_t sa, ta;
+  HC_D CabState& state() const { return *reinterpret_cast<CabState*>(__cvta_shared_to_generic(sa)); }
+  HC_D void init(const uint8_t* p, const uint8_t* e) {
+    CabState& c = state();
+    c.start = p; c.end = e; c.next = p;
+    c.range = 510;
+    c.value = cab_next32(sa);
+    c.avail = 32 - 9;
+  }
+  HC_D const uint8_t* position() const {
+    const CabState& c = state();
+    const long long shifts = (long long)(c.next - c.start) * 8 - 9 - c.avail;
+    return c.start + 2 + (shifts >> 3);
+  }
+  HC_D bool overrun() const { return position() > state().end; }
+  HC_D int bin(const Tables&, uint8_t*, int i) { return cab_bin(sa, ta, i); }
+  HC_D int bypass() { return cab_bypass(sa); }
+  HC_D uint32_t bypass_bits(const Tables&, int n) { return cab_bypass_bits(sa, ta, n); }
+  HC_D uint32_t peek16(const Tables&) const { return cab_peek16(sa, ta); }
+  HC_D void consume(int n, uint32_t bins) { cab_consume(sa, n, bins); }
+  HC_D int terminate() { return cab_terminate(sa); }
+};
+#endif
+#if defined(__CUDA_ARCH__)
+typedef CabacDev CabacT;
+#else
+typedef Cabac CabacT;
+#endif
 
 HC_HD uint8_t ctx_init_state(int init_value, int slice_qp) {
   const int slope = init_value >> 4, offs = init_value & 15;
@@ -346,7 +504,7 @@ struct Parser {
   const Slice* sh;
   Scratch* S;
   uint32_t wbase;          // device: byte offset of this chain's Scratch in k0_smem
-  Cabac cabac;
+  CabacT cabac;
   int err;
   // CTB state
   int ctb_rs, ctb_x, ctb_y;
@@ -371,7 +529,7 @@ struct Parser {
   HC_HD const Slice& slice() const { return scratch().slice; }
   HC_HD uint8_t* ctxs() const { return scratch().ctx; }
 
-  HC_HD int bin(int c) { return cabac.bin(tab(), ctxs()[c]); }
+  HC_HD int bin(int c) { return cabac.bin(tab(), ctxs(), c); }
   HC_HD void fail(int code) { if (!err) err = code; }
   HC_HD void init_contexts() {
     const Tables& t = tab();
@@ -407,10 +565,10 @@ struct Parser {
     const Pic& p = pic();
     const Tables& t = tab();
     uint8_t* const ctx = ctxs();
-    Cabac cb = cabac;
+    CabacT cb = cabac;
     bool merge_left = false, merge_up = false;
-    if (ctb_x > 0 && slice_addr_of_ctb(ctb_rs - 1) == slice().slice_addr_rs) merge_left = cb.bin(t, ctx[CX_SAO_MERGE]);
-    if (ctb_y > 0 && !merge_left && slice_addr_of_ctb(ctb_rs - p.ctbs_w) == slice().slice_addr_rs) merge_up = cb.bin(t, ctx[CX_SAO_MERGE]);
+    if (ctb_x > 0 && slice_addr_of_ctb(ctb_rs - 1) == slice().slice_addr_rs) merge_left = cb.bin(t, ctx, CX_SAO_MERGE);
+    if (ctb_y > 0 && !merge_left && slice_addr_of_ctb(ctb_rs - p.ctbs_w) == slice().slice_addr_rs) merge_up = cb.bin(t, ctx, CX_SAO_MERGE);
     if (merge_left || merge_up) {
       const hc_ctu& src = p.ctus[merge_left ? ctb_rs - 1 : ctb_rs - p.ctbs_w];
       K0_LOOP for (int c = 0; c < 3; c++) {
@@ -428,7 +586,7 @@ struct Parser {
       if (!((slice().sao_luma && c == 0) || (slice().sao_chroma && c > 0))) { ctu.sao_type[c] = 0; continue; }
       if (c < 2) {
         int ty = 0;
-        if (cb.bin(t, ctx[CX_SAO_TYPE])) ty = cb.bypass() ? 2 : 1;
+        if (cb.bin(t, ctx, CX_SAO_TYPE)) ty = cb.bypass() ? 2 : 1;
         ctu.sao_type[c] = (uint8_t)ty;
       } else {
         ctu.sao_type[2] = ctu.sao_type[1];
@@ -547,9 +705,9 @@ struct Parser {
     const Pic& p = pic();
     const Tables& t = tab();
     uint8_t* const ctx = ctxs();
-    Cabac cb = cabac;
+    CabacT cb = cabac;
     bool tskip = false;
-    if (p.transform_skip_enabled && log2 <= p.log2_max_transform_skip_size) tskip = cb.bin(t, ctx[CX_TSKIP + (cIdx ? 1 : 0)]);
+    if (p.transform_skip_enabled && log2 <= p.log2_max_transform_skip_size) tskip = cb.bin(t, ctx, CX_TSKIP + (cIdx ? 1 : 0));
 
     // last significant coefficient position
     int last[2];
@@ -561,7 +719,7 @@ struct Parser {
       K0_LOOP for (int d = 0; d < 2; d++) {
         int v = 0;
         const int base = (d ? CX_LAST_Y : CX_LAST_X) + offset;
-        K0_LOOP while (v < cMax && cb.bin(t, ctx[base + (v >> shift)])) v++;
+        K0_LOOP while (v < cMax && cb.bin(t, ctx, base + (v >> shift))) v++;
         last[d] = v;
       }
     }
@@ -620,7 +778,7 @@ struct Parser {
       const int prevCsbf = (int)((csbf_right >> sxy) & 1) | ((int)((csbf_below >> sxy) & 1) << 1);
       int inferSbDc = 0, coded = 1;
       if (i < lastSubBlock && i > 0) {
-        coded = cb.bin(t, ctx[CX_CSBF + (prevCsbf ? 1 : 0) + (cIdx ? 2 : 0)]);
+        coded = cb.bin(t, ctx, CX_CSBF + (prevCsbf ? 1 : 0) + (cIdx ? 2 : 0));
         inferSbDc = 1;
       }
       if (!coded) continue;
@@ -637,12 +795,12 @@ struct Parser {
       const int last_coeff = (i == lastSubBlock) ? lastScanPos - 1 : 15;
       if (i == lastSubBlock) sig = 1u << lastScanPos;
       if (ts_ctx) {
-        K0_LOOP for (int k = last_coeff; k > 0; k--) sig |= (uint32_t)cb.bin(t, ctx[CX_SIG + ts_c]) << k;
+        K0_LOOP for (int k = last_coeff; k > 0; k--) sig |= (uint32_t)cb.bin(t, ctx, CX_SIG + ts_c) << k;
       } else {
-        K0_LOOP for (int k = last_coeff; k > 0; k--) sig |= (uint32_t)cb.bin(t, ctx[CX_SIG + sigtab[k]]) << k;
+        K0_LOOP for (int k = last_coeff; k > 0; k--) sig |= (uint32_t)cb.bin(t, ctx, CX_SIG + sigtab[k]) << k;
       }
       if (last_coeff >= 0) {
-        if (sig != 0 || !inferSbDc) sig |= (uint32_t)cb.bin(t, ctx[CX_SIG + dc_ctx]);
+        if (sig != 0 || !inferSbDc) sig |= (uint32_t)cb.bin(t, ctx, CX_SIG + dc_ctx);
         else sig = 1;
       }
       if (sig == 0) continue;
@@ -660,7 +818,7 @@ struct Parser {
       const int g1base = CX_G1 + ctxSet * 4 + (cIdx > 0 ? 16 : 0);
       uint32_t g1mask = 0;              // coefficient c has abs level >= 2
       K0_LOOP for (int c = 0; c < ng1; c++) {
-        const int b = cb.bin(t, ctx[g1base + c1]);
+        const int b = cb.bin(t, ctx, g1base + c1);
         g1mask |= (uint32_t)b << c;
         if (b && c < firstG1) firstG1 = c;
         c1 = b ? 0 : ((c1 > 0 && c1 < 3) ? c1 + 1 : c1);
@@ -670,7 +828,7 @@ struct Parser {
       uint32_t escmask = (g1mask | ~((1u << ng1) - 1u)) & ((1u << n) - 1u);
       int g2 = 0;
       if (firstG1 < 16) {
-        g2 = cb.bin(t, ctx[CX_G2 + ctxSet + (cIdx > 0 ? 4 : 0)]);
+        g2 = cb.bin(t, ctx, CX_G2 + ctxSet + (cIdx > 0 ? 4 : 0));
         if (!g2) escmask &= ~(1u << firstG1);
       }
 
@@ -789,26 +947,26 @@ struct Parser {
     const Pic& p = pic();
     const Tables& t = tab();
     uint8_t* const ctx = ctxs();
-    Cabac cb = cabac;
+    CabacT cb = cabac;
     int split;
-    if (log2 <= p.log2_max_tb && log2 > p.log2_min_tb && depth < max_depth && !(intra_split && depth == 0)) split = cb.bin(t, ctx[CX_SPLIT_TRANSFORM + 5 - log2]);
+    if (log2 <= p.log2_max_tb && log2 > p.log2_min_tb && depth < max_depth && !(intra_split && depth == 0)) split = cb.bin(t, ctx, CX_SPLIT_TRANSFORM + 5 - log2);
     else split = (log2 > p.log2_max_tb || (intra_split && depth == 0)) ? 1 : 0;
     int cbf_cb = -1, cbf_cr = -1;
     if ((log2 > 2 && p.chroma_array_type != 0) || p.chroma_array_type == 3) {
       const bool second = p.chroma_array_type == 2 && (!split || log2 == 3);
       if (parent_cbf_cb) {
-        cbf_cb = cb.bin(t, ctx[CX_CBF_CHROMA + depth]);
-        if (second) cbf_cb |= cb.bin(t, ctx[CX_CBF_CHROMA + depth]) << 1;
+        cbf_cb = cb.bin(t, ctx, CX_CBF_CHROMA + depth);
+        if (second) cbf_cb |= cb.bin(t, ctx, CX_CBF_CHROMA + depth) << 1;
       }
       if (parent_cbf_cr) {
-        cbf_cr = cb.bin(t, ctx[CX_CBF_CHROMA + depth]);
-        if (second) cbf_cr |= cb.bin(t, ctx[CX_CBF_CHROMA + depth]) << 1;
+        cbf_cr = cb.bin(t, ctx, CX_CBF_CHROMA + depth);
+        if (second) cbf_cr |= cb.bin(t, ctx, CX_CBF_CHROMA + depth) << 1;
       }
     }
     if (cbf_cb < 0) cbf_cb = (depth > 0 && log2 == 2) ? parent_cbf_cb : 0;
     if (cbf_cr < 0) cbf_cr = (depth > 0 && log2 == 2) ? parent_cbf_cr : 0;
     int cbf_luma = 0;
-    if (!split) cbf_luma = cb.bin(t, ctx[CX_CBF_LUMA + (depth == 0 ? 1 : 0)]);
+    if (!split) cbf_luma = cb.bin(t, ctx, CX_CBF_LUMA + (depth == 0 ? 1 : 0));
     cabac = cb;
     return split | (cbf_cb << 1) | (cbf_cr << 3) | (cbf_luma << 5);
   }
@@ -858,17 +1016,17 @@ struct Parser {
 
     const Tables& t = tab();
     uint8_t* const ctx = ctxs();
-    Cabac cb = cabac;
+    CabacT cb = cabac;
     bool nxn = false;
     if (LOG2 == p.log2_min_cb) {
-      nxn = !cb.bin(t, ctx[CX_PART_MODE]);
+      nxn = !cb.bin(t, ctx, CX_PART_MODE);
       if (nxn && LOG2 <= p.log2_min_tb) { fail(ERR_BITSTREAM); return 0; }
     }
     // ---- intra prediction modes ----
     const int pbOffset = nxn ? nCbS / 2 : nCbS;
     const int nparts = nxn ? 4 : 1;
     int prev_flag[4], mpm_idx[4] = {0, 0, 0, 0}, rem[4] = {0, 0, 0, 0};
-    K0_LOOP for (int i = 0; i < nparts; i++) prev_flag[i] = cb.bin(t, ctx[CX_PREV_INTRA_LUMA]);
+    K0_LOOP for (int i = 0; i < nparts; i++) prev_flag[i] = cb.bin(t, ctx, CX_PREV_INTRA_LUMA);
     K0_LOOP for (int i = 0; i < nparts; i++) {
       if (prev_flag[i]) {
         int v = 0;
@@ -919,7 +1077,7 @@ struct Parser {
       const int nchroma = cat == 3 ? nparts : 1;
       K0_LOOP for (int idx = 0; idx < nchroma; idx++) {
         int icpm = 4;
-        if (cb.bin(t, ctx[CX_INTRA_CHROMA])) icpm = (int)cb.bypass_bits(t, 2);
+        if (cb.bin(t, ctx, CX_INTRA_CHROMA)) icpm = (int)cb.bypass_bits(t, 2);
         const int luma = luma_modes[idx];
         int m = luma;
         if (icpm != 4) {

@@ -37,6 +37,10 @@ __global__ void __launch_bounds__(32 * K0_WARPS, MIN_CTAS) k0_parse_kernel(const
   k0::Parser ps;
   memset(&ps, 0, sizeof(ps));   // CuQpDeltaVal & co. are read even when the stream never codes them
   ps.wbase = (uint32_t)(k0::TABLE_BYTES + warp * k0::SCRATCH_BYTES);
+#if defined(__CUDA_ARCH__)
+  ps.cabac.ta = (uint32_t)__cvta_generic_to_shared(k0::k0_smem);
+  ps.cabac.sa = ps.cabac.ta + ps.wbase;   // the Scratch starts with the decoder state
+#endif
   ps.run_chain(pics, subs, ch.first_sub, ch.nsubs);
 }
 
@@ -68,8 +72,12 @@ void launch_k0(const k0::Tables* tables, const k0::Pic* pics, const k0::Sub* sub
   static const int occ = []() { const char* e = getenv("HEIFCUDA_K0_OCC"); return e ? atoi(e) : 5; }();
   const int smem = k0::TABLE_BYTES + K0_WARPS * k0::SCRATCH_BYTES;
   const int grid = (nchains + K0_WARPS - 1) / K0_WARPS;
-  if (occ >= 10) k0_parse_kernel<10><<<grid, 32 * K0_WARPS, smem, stream>>>(tables, pics, subs, chains, nchains);
+  if (occ >= 12) k0_parse_kernel<12><<<grid, 32 * K0_WARPS, smem, stream>>>(tables, pics, subs, chains, nchains);
+  else if (occ >= 10) k0_parse_kernel<10><<<grid, 32 * K0_WARPS, smem, stream>>>(tables, pics, subs, chains, nchains);
   else if (occ >= 8) k0_parse_kernel<8><<<grid, 32 * K0_WARPS, smem, stream>>>(tables, pics, subs, chains, nchains);
+  else if (occ == 7) k0_parse_kernel<7><<<grid, 32 * K0_WARPS, smem, stream>>>(tables, pics, subs, chains, nchains);
+  else if (occ == 6) k0_parse_kernel<6><<<grid, 32 * K0_WARPS, smem, stream>>>(tables, pics, subs, chains, nchains);
+  else if (occ == 4) k0_parse_kernel<4><<<grid, 32 * K0_WARPS, smem, stream>>>(tables, pics, subs, chains, nchains);
   else k0_parse_kernel<5><<<grid, 32 * K0_WARPS, smem, stream>>>(tables, pics, subs, chains, nchains);
 }
 
