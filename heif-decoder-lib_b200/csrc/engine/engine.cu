@@ -146,6 +146,7 @@ struct hc_batch {
   cudaStream_t k0_stream = nullptr;   // taken on the first K0 launch
   cudaEvent_t ev_fork = nullptr;
   std::vector<Canvas> canvases;
+  std::vector<std::pair<int, int>> alpha_links;   // (canvas, alpha canvas): hc_batch_link_alpha
   std::vector<Placement> pics;
   std::vector<hc_pic> hpics;  // host copy with bases / placement filled
   Block d_arena, h_arena, d_resid, d_planes, d_rgb, d_progress;
@@ -343,6 +344,20 @@ int hc_batch_add_canvas_pass(hc_batch* b, int canvas, int kind, int a0, int a1, 
   return HC_OK;
 }
 
+int hc_batch_link_alpha(hc_batch* b, int canvas, int alpha_canvas) {
+  if (!b || canvas < 0 || canvas >= (int)b->canvases.size() || alpha_canvas < 0 || alpha_canvas >= (int)b->canvases.size() || canvas == alpha_canvas) {
+    hc::set_last_error("hc_batch_link_alpha: bad argument");
+    return HC_ERR_ARGUMENT;
+  }
+  const Canvas& c = b->canvases[canvas];
+  const Canvas& a = b->canvases[alpha_canvas];
+  if (!c.alpha) { hc::set_last_error("canvas has no alpha plane"); return HC_ERR_ARGUMENT; }
+  if ((a.bit_depth == 8) != (c.bit_depth == 8)) { hc::set_last_error("alpha image sample size differs from the colour image"); return HC_ERR_UNSUPPORTED; }
+  b->alpha_links.push_back({canvas, alpha_canvas});
+  b->uploaded = false;
+  return HC_OK;
+}
+
 static int add_picture(hc_batch* b, const hc::PictureRecords* rec, const hc::K0HostPicture* k0, int canvas, int x, int y, int role,
                        int rescale_limited) {
   if (!b || (!rec && !k0) || canvas < 0 || canvas >= (int)b->canvases.size() || x < 0 || y < 0) {
@@ -358,9 +373,15 @@ static int add_picture(hc_batch* b, const hc::PictureRecords* rec, const hc::K0H
       hc::set_last_error("picture has a different bit depth than its canvas");
       return HC_ERR_BITSTREAM;
     }
-  } else {
+  } else if (role == HC_ROLE_LUMA) {
+    if (c.chroma != 0 || c.alpha) { hc::set_last_error("a luma-only picture needs a monochrome canvas"); return HC_ERR_ARGUMENT; }
+    if (p.bit_depth_y != c.bit_depth) { hc::set_last_error("picture has a different bit depth than its canvas"); return HC_ERR_BITSTREAM; }
+  } else if (role == HC_ROLE_ALPHA) {
     if (!c.alpha) { hc::set_last_error("canvas has no alpha plane"); return HC_ERR_ARGUMENT; }
     if ((p.bit_depth_y == 8) != (c.bit_depth == 8)) { hc::set_last_error("alpha image sample size differs from the colour image"); return HC_ERR_UNSUPPORTED; }
+  } else {
+    hc::set_last_error("hc_batch_add_picture: unknown role");
+    return HC_ERR_ARGUMENT;
   }
   if (x >= c.w || y >= c.h) { hc::set_last_error("picture placed outside its canvas"); return HC_ERR_BITSTREAM; }
   b->pics.push_back({rec, canvas, x, y, role, rescale_limited, k0});
@@ -491,6 +512,9 @@ int hc_batch_upload(hc_batch* b) {
     if (b->pics[i].rescale) p.dst_flags |= HC_DST_RESCALE_LIMITED;
     if (b->pics[i].role == HC_ROLE_ALPHA) {
       p.dst_off[0] = cv.off[3]; p.dst_stride[0] = (uint32_t)cv.stride[3];
+      p.dst_flags |= HC_DST_SKIP_CB | HC_DST_SKIP_CR;
+    } else if (b->pics[i].role == HC_ROLE_LUMA) {
+      p.dst_off[0] = cv.off[0]; p.dst_stride[0] = (uint32_t)cv.stride[0];
       p.dst_flags |= HC_DST_SKIP_CB | HC_DST_SKIP_CR;
     } else {
       for (int c = 0; c < ncomp; c++) { p.dst_off[c] = cv.off[c]; p.dst_stride[c] = (uint32_t)cv.stride[c]; }
@@ -839,6 +863,15 @@ int hc_batch_reconstruct_async(hc_batch* b, int stages) {
       }
       iw = p.w; ih = p.h; ioff = p.off; istride = p.stride; ipw = p.pw; iph = p.ph;
     }
+  }
+  // alpha planes that come from an alpha image of another size (hc_batch_link_alpha): nearest-neighbour rescale of the
+  // alpha canvas' output view into the alpha plane of the colour canvas' output view
+  for (const auto& l : b->alpha_links) {
+    const Canvas& c = b->canvases[l.first];
+    const Canvas& a = b->canvases[l.second];
+    hc::launch_k6_scale((const uint8_t*)b->d_planes.p + a.ooff[0], a.opw[0], a.oph[0], a.ostride[0], (uint8_t*)b->d_planes.p + c.ooff[3], c.opw[3],
+                        c.oph[3], c.ostride[3], c.bit_depth != 8, s);
+    b->launches += 1;
   }
   cudaEventRecord(b->ev[6], s);
   if (!cuda_ok(cudaGetLastError(), "kernel launch")) return HC_ERR_CUDA;

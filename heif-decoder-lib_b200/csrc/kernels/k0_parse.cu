@@ -69,7 +69,7 @@ void launch_k0(const k0::Tables* tables, const k0::Pic* pics, const k0::Sub* sub
                cudaStream_t stream) {
   if (nchains <= 0) return;
   static_assert(sizeof(k0::Tables) % 4 == 0, "tables are copied word-wise");
-  static const int occ = []() { const char* e = getenv("HEIFCUDA_K0_OCC"); return e ? atoi(e) : 5; }();
+  static const int occ = []() { const char* e = getenv("HEIFCUDA_K0_OCC"); return e ? atoi(e) : 6; }();
   const int smem = k0::TABLE_BYTES + K0_WARPS * k0::SCRATCH_BYTES;
   const int grid = (nchains + K0_WARPS - 1) / K0_WARPS;
   if (occ >= 12) k0_parse_kernel<12><<<grid, 32 * K0_WARPS, smem, stream>>>(tables, pics, subs, chains, nchains);

@@ -52,6 +52,33 @@ __global__ void __launch_bounds__(256) k6_transform_kernel(XformArgs a) {
   }
 }
 
+// Nearest-neighbour rescale of a plane: HeifPixelImage::scale_nearest_neighbor (pixelimage.cc:1231-1250), used by the
+// reference for an alpha image whose size differs from its colour image's (context.cc:2064-2071).
+template <typename Pixel>
+__global__ void __launch_bounds__(256) k6_scale_kernel(const Pixel* __restrict__ src, int sw, int sh, int src_stride, Pixel* __restrict__ dst,
+                                                       int dw, int dh, int dst_stride) {
+  const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+  if (x >= dw) return;
+  const int ix = (int)((long long)x * sw / dw);
+#pragma unroll
+  for (int r = 0; r < 4; r++) {
+    const int y = blockIdx.y * 32 + (threadIdx.x >> 5) + 8 * r;
+    if (y >= dh) continue;
+    const int iy = (int)((long long)y * sh / dh);
+    dst[(size_t)y * dst_stride + x] = src[(size_t)iy * src_stride + ix];
+  }
+}
+
+void launch_k6_scale(const uint8_t* src, int sw, int sh, int src_stride, uint8_t* dst, int dw, int dh, int dst_stride, bool sixteen_bit,
+                     cudaStream_t stream) {
+  if (sw <= 0 || sh <= 0 || dw <= 0 || dh <= 0) return;
+  dim3 grid((unsigned)((dw + 31) / 32), (unsigned)((dh + 31) / 32));
+  if (sixteen_bit)
+    k6_scale_kernel<uint16_t><<<grid, 256, 0, stream>>>(reinterpret_cast<const uint16_t*>(src), sw, sh, src_stride, reinterpret_cast<uint16_t*>(dst), dw, dh, dst_stride);
+  else
+    k6_scale_kernel<uint8_t><<<grid, 256, 0, stream>>>(src, sw, sh, src_stride, dst, dw, dh, dst_stride);
+}
+
 void launch_k6(const XformArgs& a, bool sixteen_bit, cudaStream_t stream) {
   if (a.w <= 0 || a.h <= 0) return;
   const int ow = a.swap ? a.h : a.w, oh = a.swap ? a.w : a.h;

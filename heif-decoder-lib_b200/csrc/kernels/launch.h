@@ -50,5 +50,8 @@ void launch_k4(const BatchView& bv, long long max_ctbs, int planes, cudaStream_t
 void launch_k5(const CscArgs& a, bool sixteen_bit, cudaStream_t stream);
 void launch_k5_batch(const CscBatch& b, bool sixteen_bit, cudaStream_t stream);
 void launch_k6(const XformArgs& a, bool sixteen_bit, cudaStream_t stream);
+// nearest-neighbour rescale of one plane (strides in samples): dst(x, y) = src(x * sw / dw, y * sh / dh)
+void launch_k6_scale(const uint8_t* src, int sw, int sh, int src_stride, uint8_t* dst, int dw, int dh, int dst_stride, bool sixteen_bit,
+                     cudaStream_t stream);
 
 }  // namespace hc

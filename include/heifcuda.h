@@ -199,6 +199,8 @@ void hc_batch_destroy(hc_batch* b);
 int hc_batch_add_canvas(hc_batch* b, int width, int height, int chroma_format, int bit_depth, int with_alpha);
 #define HC_ROLE_COLOUR 0
 #define HC_ROLE_ALPHA 1 /* the picture's luma becomes the canvas' alpha plane (context.cc:2029-2078) */
+#define HC_ROLE_LUMA 2  /* only the picture's luma is kept, as plane 0 of a (monochrome) canvas: an alpha image that is
+                         * decoded on its own because its size differs from the colour image's (hc_batch_link_alpha) */
 /* `rec` must stay alive until hc_batch_upload returns. (x,y): paste position of the picture's
  * conformance window on the canvas, luma samples. rescale_limited: apply the reference's
  * limited->full range rescale while pasting (grid tiles whose nclx is limited range). */
@@ -231,6 +233,11 @@ int hc_batch_set_canvas_transform(hc_batch* b, int canvas, int swap, int flip_x,
 #define HC_PASS_DIHEDRAL 0
 #define HC_PASS_CROP 1
 int hc_batch_add_canvas_pass(hc_batch* b, int canvas, int kind, int a0, int a1, int a2, int a3);
+/* The alpha plane of `canvas` (created with_alpha) is plane 0 of `alpha_canvas`, rescaled to the size of `canvas` by
+ * nearest neighbour exactly like HeifPixelImage::scale_nearest_neighbor (pixelimage.cc:1156-1253: ix = x * in_w / out_w,
+ * iy = y * in_h / out_h) as HeifContext::decode_image_planar does for an alpha image whose size differs from the colour
+ * image's (context.cc:2064-2071). Both canvases are taken after their own geometric passes. Call before hc_batch_upload. */
+int hc_batch_link_alpha(hc_batch* b, int canvas, int alpha_canvas);
 /* K5 for one canvas into the engine's device RGB buffer, async */
 int hc_batch_convert(hc_batch* b, int canvas, const hc_csc_params* params);
 /* K5 for n canvases (canvases[i] with params[i]) in as few launches as possible, async */
