@@ -323,65 +323,79 @@ static hc_heic_job* job_create(hc_engine* e, int nfiles, const uint8_t* const* d
       primaries = im.info.nclx_present ? im.info.primaries : p0.colour_primaries;
       full = im.info.nclx_present ? im.info.full_range : p0.full_range;
     }
-    if (has_alpha) {
-      const hc_pic& pa = j->items[im.alpha].pic();
-      if (pa.crop_w != W || pa.crop_h != H) {
-        hc::set_last_error("alpha image of a different size than the colour image (nearest-neighbour rescale) is not supported");
-        return nullptr;
-      }
-      if (add_item(j->batch, j->items[im.alpha], im.canvas, 0, 0, HC_ROLE_ALPHA, 0) < 0) return nullptr;
-    }
-    // ---- irot / imir / clap of the image item, in ipma order (context.cc:1955-2016). Consecutive rotations and mirrors
-    // are composed into one dihedral pass; a clap becomes a crop pass on the image as it is at that point. ----
-    {
-      const hc::HeifItem* pit = j->files[im.file]->item(im.info.id);
+    // ---- irot / imir / clap of an image item, in ipma order (context.cc:1955-2016). Consecutive rotations and mirrors
+    // are composed into one dihedral pass; a clap becomes a crop pass on the image as it is at that point. Returns
+    // false on error; `any` reports whether the item carries transformations at all. ----
+    auto apply_xforms = [&](int canvas, const hc::HeifItem* pit, int& Wc, int& Hc, int chroma_format, int bit_depth, bool& any) -> bool {
       int swap = 0, fx = 0, fy = 0;
-      bool any = false;
+      any = false;
       size_t next_clap = 0;
       auto flush_dihedral = [&]() -> bool {
         if (!(swap | fx | fy)) return true;
-        if (swap && p0.chroma_format == 2) { hc::set_last_error("quarter turns of 4:2:2 images are not supported"); return false; }
-        if (hc_batch_add_canvas_pass(j->batch, im.canvas, HC_PASS_DIHEDRAL, swap, fx, fy, 0) != HC_OK) return false;
+        if (swap && chroma_format == 2) { hc::set_last_error("quarter turns of 4:2:2 images are not supported"); return false; }
+        if (hc_batch_add_canvas_pass(j->batch, canvas, HC_PASS_DIHEDRAL, swap, fx, fy, 0) != HC_OK) return false;
         swap = fx = fy = 0;
         return true;
       };
-      if (pit) {
-        for (uint8_t op : pit->xforms) {
-          any = true;
-          if (op == HC_XF_CLAP) {
-            if (!flush_dihedral()) return nullptr;
-            if (next_clap >= pit->claps.size()) { hc::set_last_error("clap property without its box"); return nullptr; }
-            int win[4];
-            const std::string e = clap_window(pit->claps[next_clap++], W, H, win);
-            if (!e.empty()) { hc::set_last_error(e); return nullptr; }
-            if (hc_batch_add_canvas_pass(j->batch, im.canvas, HC_PASS_CROP, win[0], win[1], win[2], win[3]) != HC_OK) return nullptr;
-            W = win[2] - win[0] + 1; H = win[3] - win[1] + 1;
-            continue;
-          }
-          const int s2 = (op == HC_XF_ROT90 || op == HC_XF_ROT270) ? 1 : 0;
-          const int fx2 = (op == HC_XF_ROT90 || op == HC_XF_ROT180 || op == HC_XF_MIRROR_H) ? 1 : 0;
-          const int fy2 = (op == HC_XF_ROT270 || op == HC_XF_ROT180 || op == HC_XF_MIRROR_V) ? 1 : 0;
-          if ((op == HC_XF_MIRROR_H || op == HC_XF_MIRROR_V) && p0.bit_depth_y != 8) {
-            hc::set_last_error("Can currently only mirror images with 8 bits per pixel");   // pixelimage.cc:748-752
-            return nullptr;
-          }
-          // out2(x, y) = out1(x1, y1): see hc_batch_set_canvas_transform for the map of one operation
-          const int nfx = swap ? (fx ^ fy2) : (fx ^ fx2), nfy = swap ? (fy ^ fx2) : (fy ^ fy2);
-          swap ^= s2; fx = nfx; fy = nfy;
-          if (s2) std::swap(W, H);
+      if (!pit) return true;
+      for (uint8_t op : pit->xforms) {
+        any = true;
+        if (op == HC_XF_CLAP) {
+          if (!flush_dihedral()) return false;
+          if (next_clap >= pit->claps.size()) { hc::set_last_error("clap property without its box"); return false; }
+          int win[4] = {0, 0, 0, 0};
+          const std::string e = clap_window(pit->claps[next_clap++], Wc, Hc, win);
+          if (!e.empty()) { hc::set_last_error(e); return false; }
+          if (hc_batch_add_canvas_pass(j->batch, canvas, HC_PASS_CROP, win[0], win[1], win[2], win[3]) != HC_OK) return false;
+          Wc = win[2] - win[0] + 1; Hc = win[3] - win[1] + 1;
+          continue;
         }
-        if (!flush_dihedral()) return nullptr;
-      }
-      if (any) {
-        if (band_end >= 0) { hc::set_last_error("banded decode of transformed images is not supported"); return nullptr; }
-        if (has_alpha) {
-          // the alpha item carries its own properties in the reference (context.cc:2040); only identical ones are supported
-          const hc::HeifItem* ait = j->files[im.file]->item(im.info.alpha_id);
-          bool same = ait && ait->xforms == pit->xforms && ait->claps.size() == pit->claps.size();
-          for (size_t k = 0; same && k < pit->claps.size(); k++) same = memcmp(&ait->claps[k], &pit->claps[k], sizeof(hc::HeifItem::Clap)) == 0;
-          if (!same) { hc::set_last_error("alpha image with different transformations than its colour image"); return nullptr; }
+        const int s2 = (op == HC_XF_ROT90 || op == HC_XF_ROT270) ? 1 : 0;
+        const int fx2 = (op == HC_XF_ROT90 || op == HC_XF_ROT180 || op == HC_XF_MIRROR_H) ? 1 : 0;
+        const int fy2 = (op == HC_XF_ROT270 || op == HC_XF_ROT180 || op == HC_XF_MIRROR_V) ? 1 : 0;
+        if ((op == HC_XF_MIRROR_H || op == HC_XF_MIRROR_V) && bit_depth != 8) {
+          hc::set_last_error("Can currently only mirror images with 8 bits per pixel");   // pixelimage.cc:748-752
+          return false;
         }
+        // out2(x, y) = out1(x1, y1): see hc_batch_set_canvas_transform for the map of one operation
+        const int nfx = swap ? (fx ^ fy2) : (fx ^ fx2), nfy = swap ? (fy ^ fx2) : (fy ^ fy2);
+        swap ^= s2; fx = nfx; fy = nfy;
+        if (s2) std::swap(Wc, Hc);
       }
+      return flush_dihedral();
+    };
+    const hc::HeifItem* pit = j->files[im.file]->item(im.info.id);
+    const hc::HeifItem* ait = has_alpha ? j->files[im.file]->item(im.info.alpha_id) : nullptr;
+    // Is the alpha image pasted straight into the canvas' alpha plane (same decoded size, same transformations), or
+    // decoded on its own canvas, transformed by its own properties and rescaled by nearest neighbour afterwards
+    // (context.cc:2040-2071: decode_image_planar of the alpha item, then scale_nearest_neighbor to the colour image's size)?
+    bool alpha_separate = false;
+    if (has_alpha) {
+      const hc_pic& pa = j->items[im.alpha].pic();
+      bool same = pa.crop_w == W && pa.crop_h == H;
+      if (same && pit && !pit->xforms.empty()) {
+        same = ait && ait->xforms == pit->xforms && ait->claps.size() == pit->claps.size();
+        for (size_t k = 0; same && k < pit->claps.size(); k++) same = memcmp(&ait->claps[k], &pit->claps[k], sizeof(hc::HeifItem::Clap)) == 0;
+      } else if (same && ait && !ait->xforms.empty()) {
+        same = false;
+      }
+      alpha_separate = !same;
+      if (!alpha_separate && add_item(j->batch, j->items[im.alpha], im.canvas, 0, 0, HC_ROLE_ALPHA, 0) < 0) return nullptr;
+    }
+    {
+      bool any = false;
+      if (!apply_xforms(im.canvas, pit, W, H, p0.chroma_format, p0.bit_depth_y, any)) return nullptr;
+      if (any && band_end >= 0) { hc::set_last_error("banded decode of transformed images is not supported"); return nullptr; }
+    }
+    if (alpha_separate) {
+      const hc_pic& pa = j->items[im.alpha].pic();
+      int Wa = pa.crop_w, Ha = pa.crop_h;
+      const int ac = hc_batch_add_canvas(j->batch, Wa, Ha, 0, pa.bit_depth_y, 0);
+      if (ac < 0) return nullptr;
+      if (add_item(j->batch, j->items[im.alpha], ac, 0, 0, HC_ROLE_LUMA, 0) < 0) return nullptr;
+      bool any = false;
+      if (!apply_xforms(ac, ait, Wa, Ha, 0, pa.bit_depth_y, any)) return nullptr;
+      if (hc_batch_link_alpha(j->batch, im.canvas, ac) != HC_OK) return nullptr;
     }
     const bool hdr = p0.bit_depth_y != 8;
     const int fmt = hdr ? (j->want_alpha ? HC_OUT_RRGGBBAA_LE : HC_OUT_RRGGBB_LE) : (j->want_alpha ? HC_OUT_RGBA : HC_OUT_RGB);

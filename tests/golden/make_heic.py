@@ -75,6 +75,14 @@ def build():
     files["clap_irot270_420_8"] = W.single_image(enc(264, 200, 1, 8, 54), 264, 200, 1, 8, transforms=(W.clap(151, 1, 99, 1, 5, 1, 4, 1), W.irot(3)))
     files["grid_clap_imir_300x200"] = W.synth_grid_heic(300, 200, tile=128, seed=55, transforms=(W.clap(255, 1, 131, 1, -11, 1, 9, 1), W.imir(1)))
     files["clap_422_10"] = W.single_image(enc(200, 120, 2, 10, 56), 200, 120, 2, 10, transforms=(W.clap(99, 1, 61, 1, 10, 1, 0, 1),))
+    # alpha image of another size / with other transformations than the colour image: nearest-neighbour rescale
+    # (context.cc:2064-2071, pixelimage.cc:1156-1253)
+    files["alpha_half_420_8"] = W.single_image(enc(200, 120, 1, 8, 60), 200, 120, 1, 8, alpha_stream=enc(100, 60, 0, 8, 61), alpha_size=(100, 60))
+    files["alpha_odd_422_10"] = W.single_image(enc(200, 120, 2, 10, 62), 200, 120, 2, 10, alpha_stream=enc(136, 72, 0, 10, 63), alpha_size=(136, 72))
+    files["alpha_larger_420_8_irot90"] = W.single_image(enc(200, 120, 1, 8, 64), 200, 120, 1, 8, alpha_stream=enc(264, 200, 1, 8, 65),
+                                                        alpha_chroma_format=1, alpha_size=(264, 200), transforms=(W.irot(1),))
+    files["alpha_unrotated_420_8"] = W.single_image(enc(200, 120, 1, 8, 66), 200, 120, 1, 8, alpha_stream=enc(200, 120, 0, 8, 67),
+                                                    transforms=(W.irot(1),), alpha_transforms=())
     return files
 
 
@@ -96,7 +104,12 @@ def reference_outputs(data):
 def main():
     os.makedirs(OUT, exist_ok=True)
     meta = {}
+    only = set(sys.argv[1:])   # names to (re)generate; default: everything
+    if only:
+        meta = json.load(open(os.path.join(HERE, "heic.json")))
     for name, data in sorted(build().items()):
+        if only and name not in only:
+            continue
         open(os.path.join(OUT, name + ".heic"), "wb").write(data)
         meta[name] = reference_outputs(data)
         meta[name]["bytes"] = len(data)

@@ -77,6 +77,12 @@ def decode_planes(data, item_id=None):
         apl, _ = oracle_lib.reconstruct(a)
         alpha = _transform_all([apl[0]], hf.image_info(info.alpha_id))[0]
     planes = _transform_all(planes, info)
+    if alpha is not None and alpha.shape != planes[0].shape:
+        # context.cc:2064-2071 -> HeifPixelImage::scale_nearest_neighbor (pixelimage.cc:1231-1250)
+        h, w = planes[0].shape
+        iy = np.arange(h) * alpha.shape[0] // h
+        ix = np.arange(w) * alpha.shape[1] // w
+        alpha = alpha[iy][:, ix]
     return planes, alpha, cf, bd, nclx
 
 

@@ -141,12 +141,16 @@ def clap(w_num, w_den, h_num, h_den, hoff_num, hoff_den, voff_num, voff_den):
 
 
 def single_image(stream, width, height, chroma_format=1, bit_depth=8, nclx=None, alpha_stream=None, alpha_chroma_format=0,
-                 transforms=()):
-    """transforms: property boxes (irot / imir) attached, in this order, to the image and to its alpha image"""
+                 transforms=(), alpha_size=None, alpha_transforms=None):
+    """transforms: property boxes (irot / imir / clap) attached, in this order, to the image and to its alpha image
+    (alpha_transforms: the alpha image's own list instead); alpha_size: (width, height) of the alpha image when it
+    differs from the colour image's (the reference rescales it by nearest neighbour, context.cc:2064-2071)"""
     b = HeifBuilder()
     iid = b.add_hevc_image(stream, width, height, chroma_format, bit_depth, nclx=nclx, extra_props=tuple(transforms))
     if alpha_stream is not None:
-        b.add_alpha(iid, alpha_stream, width, height, alpha_chroma_format, bit_depth, extra_props=tuple(transforms))
+        aw, ah = alpha_size if alpha_size else (width, height)
+        b.add_alpha(iid, alpha_stream, aw, ah, alpha_chroma_format, bit_depth,
+                    extra_props=tuple(transforms if alpha_transforms is None else alpha_transforms))
     b.primary = iid
     return b.serialize()
 
