@@ -291,7 +291,7 @@ def main():
     # `--images` files: the host CABAC parse of batch b+1 overlaps H2D + kernels + D2H of batch b, which is how a
     # long file list is meant to be fed (BASELINE config C4). The first batch (pipeline fill, allocations) is
     # timed separately and excluded.
-    e2e_steps = max(4, min(args.steps, 12))
+    e2e_steps = max(6, min(args.steps, 16))
     marks = []
     checksum = [0]
 

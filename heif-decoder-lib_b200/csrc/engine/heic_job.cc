@@ -490,10 +490,10 @@ int hc_heic_decode_stream(hc_engine* e, int nfiles, const uint8_t* const* data, 
   // batch b, so they parse a share of the coded items themselves. "auto" (engine option -1) starts at 20 % and follows
   // the measured ratio of GPU time to host time per batch, so that a rank with few host threads ends up near 0.
   const int share_opt = hc_engine_get_option(e, "host_share_pct");
-  // static prior (per coded 512 x 512 item, measured on B200 + this box's cores): device 0.105 ms in the steady state of
-  // the pipeline (K0-bound: 80 ms per 768 items), one host thread 6.6 ms
+  // static prior (per coded 512 x 512 item, measured on B200 + this box's cores): device 0.078 ms in the steady state of
+  // the pipeline (K0-bound: 109 ms + 10 ms of K1..K5 per 1536 items), one host thread 6.6 ms
   const int pool_threads = threads > 0 ? threads : std::max(1, (int)std::thread::hardware_concurrency());
-  const double c_dev0 = 0.105e-3, c_host0 = 6.6e-3 / pool_threads;
+  const double c_dev0 = 0.078e-3, c_host0 = 6.6e-3 / pool_threads;
   const int share0 = (int)(90.0 * c_dev0 / (c_host0 + c_dev0) + 0.5);
   std::atomic<int> share{share_opt >= 0 ? share_opt : share0};
   double c_host = c_host0, c_dev = c_dev0;
