@@ -84,7 +84,7 @@ def test_gpu_decode_heic_python_path(engine):
 @pytest.mark.gpu
 @pytest.mark.parametrize("host_share", [-1, 0, 50, 100])
 def test_gpu_decode_stream_pipelined_batches(engine, host_share):
-    """hc_heic_decode_stream: batches of 4 files, submit / deliver pipelined over two pinned buffers, slice data parsed
+    """hc_heic_decode_stream: batches of 4 files, submit / deliver pipelined three batches deep, slice data parsed
     by K0 with the host threads taking `host_share` per cent of the coded items meanwhile (-1: automatic);
     every image arrives once, in order, bit-exact."""
     engine.set_option("host_share_pct", host_share)
@@ -102,6 +102,22 @@ def test_gpu_decode_stream_pipelined_batches(engine, host_share):
     assert all(ok for _, ok in seen)
     assert st["batches"] == (len(files) + 3) // 4 and st["pixels"] == 2 * sum(META[n]["width"] * META[n]["height"] for n in NAMES)
     assert st["launches"] > 0 and st["bytes_d2h"] > 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("nbatches", [1, 2, 3, 4])
+def test_gpu_decode_stream_fill_and_drain(engine, nbatches):
+    """Streams shorter than, as long as and longer than the pipeline depth (3): every image once, in order, bit-exact."""
+    names = (NAMES * 2)[:3 * nbatches - 1]          # the last batch is ragged
+    seen = []
+
+    def on_image(index, desc, rows):
+        key = {hb.OUT_RGB: "rgb", hb.OUT_RGBA: "rgba", hb.OUT_RRGGBB_LE: "rrggbb_le", hb.OUT_RRGGBBAA_LE: "rrggbbaa_le"}[desc.out_format]
+        seen.append((index, md5(rows.tobytes()) == META[names[index]][key + "_md5"]))
+
+    st = hb.decode_stream(engine, [load(n) for n in names], on_image, want_alpha=False, threads=2, files_per_batch=3)
+    assert [i for i, _ in seen] == list(range(len(names))) and all(ok for _, ok in seen)
+    assert st["batches"] == nbatches
 
 
 @pytest.mark.gpu
