@@ -487,16 +487,22 @@ int hc_heic_decode_stream(hc_engine* e, int nfiles, const uint8_t* const* data, 
 
   // stage 1 (host threads): container + CABAC parse of one batch; runs one batch ahead of stage 2
   // Hybrid parse: with the device parser on, the host threads that prepare batch b+1 would idle while the GPU works on
-  // batch b, so they parse a share of the coded items themselves. "auto" (engine option -1) starts at 20 % and follows
-  // the measured ratio of GPU time to host time per batch, so that a rank with few host threads ends up near 0.
+  // batch b, so they parse a share of the coded items themselves. "auto" (engine option -1) starts from a static prior
+  // and follows the measured costs per item on either side, so that a rank with few host threads ends up at 0.
   const int share_opt = hc_engine_get_option(e, "host_share_pct");
   // static prior (per coded 512 x 512 item, measured on B200 + this box's cores): device 0.078 ms in the steady state of
-  // the pipeline (K0-bound: 109 ms + 10 ms of K1..K5 per 1536 items), one host thread 6.6 ms
+  // the pipeline (K0-bound: 109 ms + 10 ms of K1..K5 per 1536 items); one host thread 6.6 ms for the slice data of an item
+  // it parses itself and 0.13 ms for the container / header work every item needs. The host must finish
+  // n * c_hdr + share * n * c_host within 0.9 of the device's (1 - share) * n * c_dev, hence balanced_share() — which is 0
+  // for a rank with two host threads (8 ranks on a 16-core box): there the headers alone take most of a period.
   const int pool_threads = threads > 0 ? threads : std::max(1, (int)std::thread::hardware_concurrency());
-  const double c_dev0 = 0.078e-3, c_host0 = 6.6e-3 / pool_threads;
-  const int share0 = (int)(90.0 * c_dev0 / (c_host0 + c_dev0) + 0.5);
-  std::atomic<int> share{share_opt >= 0 ? share_opt : share0};
-  double c_host = c_host0, c_dev = c_dev0;
+  const double c_dev0 = 0.078e-3, c_host0 = 6.6e-3 / pool_threads, c_hdr0 = 0.13e-3 / pool_threads;
+  auto balanced_share = [](double c_dev, double c_host, double c_hdr) {
+    const double s = (0.9 * c_dev - c_hdr) / (c_host + 0.9 * c_dev);
+    return std::max(0, std::min(90, (int)(100.0 * s + 0.5)));
+  };
+  std::atomic<int> share{share_opt >= 0 ? share_opt : balanced_share(c_dev0, c_host0, c_hdr0)};
+  double c_host = c_host0, c_dev = c_dev0, c_hdr = c_hdr0;
   std::mutex parse_mu;
   struct Parsed { hc_heic_job* job = nullptr; std::string error; double seconds = 0; int share = 0; };
   auto parse_batch = [&](int b) -> Parsed {
@@ -566,14 +572,14 @@ int hc_heic_decode_stream(hc_engine* e, int nfiles, const uint8_t* const* data, 
           // in pairs) — but only while the GPU is what the pipeline waits for, i.e. this thread did not have to wait for the
           // host parse of the batch.
           const double n_items = (double)j->items.size();
-          const double n_host = std::max(1.0, n_items * f.share / 100.0), n_dev = std::max(1.0, n_items - n_items * f.share / 100.0);
-          const double period = (t_done[2] - t_done[0]) / 2, ch = f.host_s / n_host, cd = period / n_dev;
+          const double n_host = n_items * f.share / 100.0, n_dev = std::max(1.0, n_items - n_host);
+          const double period = (t_done[2] - t_done[0]) / 2, cd = period / n_dev;
           // slow, outlier-resistant tracking: one noisy batch (a host thread descheduled) must not swing the share
-          c_host = 0.7 * c_host + 0.3 * std::min(ch, 2.0 * c_host);
+          if (n_host < 1.0) c_hdr = 0.7 * c_hdr + 0.3 * std::min(f.host_s / n_items, 2.0 * c_hdr);
+          else c_host = 0.7 * c_host + 0.3 * std::min(std::max(0.0, f.host_s - n_items * c_hdr) / n_host, 2.0 * c_host);
           const bool gpu_bound = f.host_wait_s < 0.05 * period;
           if (gpu_bound) c_dev = 0.7 * c_dev + 0.3 * std::min(cd, 2.0 * c_dev);
-          const int next = (int)(90.0 * c_dev / (c_host + c_dev) + 0.5);
-          share.store(std::max(2, std::min(90, next)));
+          share.store(balanced_share(c_dev, c_host, c_hdr));
           if (trace_on()) fprintf(stderr, "[heifcuda] batch %d: host %.1f ms (waited %.1f ms for it), period %.1f ms, own gpu events %.1f ms, share %d%% -> %d%%\n", f.index, f.host_s * 1e3, f.host_wait_s * 1e3, period * 1e3, gpu_ms, f.share, share.load());
         }
       }
