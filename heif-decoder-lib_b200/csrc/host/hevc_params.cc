@@ -440,21 +440,31 @@ static void derive_pps(const Sps& sps, Pps& pps) {
     pps.tile_id_rs[rs] = tileY * pps.num_tile_cols + tileX;
     if (tbX == pps.col_bd[tileX] && tbY == pps.row_bd[tileY]) pps.tile_start_ctb[rs] = 1;
   }
-  // §6.5.2 MinTbAddrZs
-  int shift = sps.log2_ctb - sps.log2_min_tb;
-  pps.min_tb_addr_zs.assign((size_t)sps.tbs_w * sps.tbs_h, 0);
-  for (int y = 0; y < sps.tbs_h; y++)
-    for (int x = 0; x < sps.tbs_w; x++) {
-      int tbX = x >> shift, tbY = y >> shift;
-      int v = pps.ctb_addr_rs_to_ts[W * tbY + tbX] << (shift * 2);
-      for (int i = 0; i < shift; i++) {
-        int m = 1 << i;
-        v += (m & x ? m * m : 0) + (m & y ? 2 * m * m : 0);
-      }
-      pps.min_tb_addr_zs[x + (size_t)y * sps.tbs_w] = v;
-    }
+  // §6.5.2 MinTbAddrZs: derive_min_tb_addr_zs(), on demand (only the host slice-data parser needs it)
+  pps.min_tb_addr_zs.clear();
   pps.log2_min_cu_qp_delta_size = sps.log2_ctb - pps.diff_cu_qp_delta_depth;
   pps.log2_min_cu_chroma_qp_offset_size = sps.log2_ctb - pps.diff_cu_chroma_qp_offset_depth;
+}
+
+// §6.5.2 MinTbAddrZs. One entry per minimum transform block of the picture (16 K for a 512 x 512 tile): this table was
+// 95 % of the host work per device-parsed item while it was built with every PPS, so it is built when a picture that the
+// HOST parser decodes starts (HevcIntraParser::Impl::start_picture) — K0 computes z-scan addresses itself.
+void derive_min_tb_addr_zs(const Sps& sps, Pps& pps) {
+  const int W = sps.ctbs_w, shift = sps.log2_ctb - sps.log2_min_tb, mask = (1 << shift) - 1;
+  int morton[16][16];   // shift <= 4 (CTB 64, minimum TB 4)
+  for (int y = 0; y <= mask; y++)
+    for (int x = 0; x <= mask; x++) {
+      int v = 0;
+      for (int i = 0; i < shift; i++) {
+        const int m = 1 << i;
+        v += (m & x ? m * m : 0) + (m & y ? 2 * m * m : 0);
+      }
+      morton[y][x] = v;
+    }
+  pps.min_tb_addr_zs.assign((size_t)sps.tbs_w * sps.tbs_h, 0);
+  for (int y = 0; y < sps.tbs_h; y++)
+    for (int x = 0; x < sps.tbs_w; x++)
+      pps.min_tb_addr_zs[x + (size_t)y * sps.tbs_w] = (pps.ctb_addr_rs_to_ts[W * (y >> shift) + (x >> shift)] << (shift * 2)) + morton[y & mask][x & mask];
 }
 
 std::string parse_pps(const uint8_t* rbsp, size_t n, const Sps* sps_table, Pps& pps) {

@@ -136,6 +136,8 @@ struct SliceHeader {
 
 // Parses parameter sets. All functions return an empty string on success, else an error text.
 std::string parse_sps(const uint8_t* rbsp, size_t n, Sps& sps);
+// fills pps.min_tb_addr_zs (left empty by parse_pps)
+void derive_min_tb_addr_zs(const Sps& sps, Pps& pps);
 std::string parse_pps(const uint8_t* rbsp, size_t n, const Sps* sps_table /*[16]*/, Pps& pps);
 // `skipped` are the escaped-input positions of removed emulation-prevention bytes (relative to the
 // NAL payload start incl. the 2-byte NAL header), used to convert entry points.

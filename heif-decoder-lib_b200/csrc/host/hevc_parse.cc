@@ -270,6 +270,21 @@ std::string HevcIntraParser::push_nal(const uint8_t* nal, size_t size) {
 
 void HevcIntraParser::set_collect_only(bool on) { impl_->collect_only = on; }
 
+void HevcIntraParser::reset() {
+  Impl& d = *impl_;
+  for (Sps& s : d.sps_tab) s.valid = false;
+  for (Pps& p : d.pps_tab) p.valid = false;
+  d.started = false;
+  d.S = nullptr;
+  d.P = nullptr;
+  d.rec.reset();
+  d.slices.clear();
+  d.have_prev_independent = false;
+  d.ctbs_done = 0;
+  d.k0_rbsp.clear();
+  d.k0_rbsp_size.clear();
+}
+
 // Builds the K0 inputs from the collected slice segments (see kernels/k0_core.cuh for what K0 accepts).
 std::string HevcIntraParser::take_k0(K0HostPicture& out) {
   Impl& d = *impl_;
@@ -437,15 +452,18 @@ std::string HevcIntraParser::Impl::start_picture(const SliceHeader& first) {
   W = S->width;
   H = S->height;
   w8 = W >> 3; h8 = H >> 3; w4 = W >> 2; h4 = H >> 2;
-  ct_depth.assign((size_t)w8 * h8, 0);
-  cu_flags.assign((size_t)w8 * h8, 0);
-  qp_y.assign((size_t)w8 * h8, 0);
-  ipm.assign((size_t)w4 * h4, 1);
-  ipm_c.assign((size_t)w4 * h4, 1);
-  ctb_slice_addr.assign(S->pic_size_in_ctbs, -1);
-  ctb_slice_idx.assign(S->pic_size_in_ctbs, -1);
-  wpp_ctx.assign(S->ctbs_h, CtxSet());
-  wpp_ctx_valid.assign(S->ctbs_h, 0);
+  if (!collect_only) {   // state of the host CABAC parse; K0 keeps its own on the device
+    derive_min_tb_addr_zs(sps_copy, pps_copy);
+    ct_depth.assign((size_t)w8 * h8, 0);
+    cu_flags.assign((size_t)w8 * h8, 0);
+    qp_y.assign((size_t)w8 * h8, 0);
+    ipm.assign((size_t)w4 * h4, 1);
+    ipm_c.assign((size_t)w4 * h4, 1);
+    ctb_slice_addr.assign(S->pic_size_in_ctbs, -1);
+    ctb_slice_idx.assign(S->pic_size_in_ctbs, -1);
+    wpp_ctx.assign(S->ctbs_h, CtxSet());
+    wpp_ctx_valid.assign(S->ctbs_h, 0);
+  }
   dep_ctx_valid = false;
   slices.clear();
   slices.reserve(64);
@@ -477,10 +495,12 @@ std::string HevcIntraParser::Impl::start_picture(const SliceHeader& first) {
   p.transfer_characteristics = (uint8_t)S->transfer_characteristics;
   p.matrix_coeffs = (uint8_t)S->matrix_coeffs;
   p.full_range = (uint8_t)S->video_full_range;
-  rec->ctus.assign(S->pic_size_in_ctbs, hc_ctu());
-  for (auto& c : rec->ctus) memset(&c, 0, sizeof(c));
-  rec->edge_map.assign((size_t)w4 * h4, 0);
-  rec->qp_map.assign((size_t)w8 * h8, 0);
+  if (!collect_only) {
+    rec->ctus.assign(S->pic_size_in_ctbs, hc_ctu());
+    for (auto& c : rec->ctus) memset(&c, 0, sizeof(c));
+    rec->edge_map.assign((size_t)w4 * h4, 0);
+    rec->qp_map.assign((size_t)w8 * h8, 0);
+  }
   if (S->scaling_list_enabled) {
     p.flags |= HC_PIC_SCALING_LIST;
     rec->scaling.resize(HC_SCALING_BLOB_BYTES);

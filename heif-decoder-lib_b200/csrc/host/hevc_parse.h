@@ -51,6 +51,10 @@ class HevcIntraParser {
   void set_collect_only(bool on);
   std::string take_k0(struct K0HostPicture& out);
 
+  // Forgets every parameter set and any picture in progress, so that one parser object (its tables are ~700 KB) can
+  // serve many independent coded items — a grid file is 48 of them — without being rebuilt for each.
+  void reset();
+
   // True when every CTB of the current picture has been parsed.
   bool picture_complete() const;
   // True when at least one slice of a picture has been seen.
