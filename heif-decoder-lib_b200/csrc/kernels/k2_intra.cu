@@ -82,6 +82,7 @@ HC_D void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) 
 }
 HC_D void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 HC_D void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+HC_D void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 HC_D uint2 ld_cg_v2(const void* p) {
   uint2 v;
   asm volatile("ld.global.cg.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
@@ -144,6 +145,21 @@ __device__ __forceinline__ void process_block(const Geo& g, uint32_t w0, uint32_
     __syncwarp();
     return;
   }
+  // The residual add is the last step of the block, but its operands do not depend on the prediction: ncu put 27 % of the
+  // kernel's stall samples on the `v + res[...]` lines (the load is issued behind the warp barriers of the gather / filter
+  // phases and every sample pass waits for it). Small blocks (staged in shared memory) read theirs now, into registers;
+  // 16x16 / 32x32 blocks (read from global memory, one 64-byte row group per pass) pull their lines into L1 now.
+  const bool has_res = w1 & BP_HAS_RES;
+  int rpre0 = 0, rpre1 = 0;
+  if (has_res) {
+    if (LOG2 <= 3) {
+      rpre0 = res[s0];
+      if (ITER == 2) rpre1 = res[s0 + 32];
+    } else if (lane * 128 < NS * 2 + 128) {
+      prefetch_l1(reinterpret_cast<const char*>(res) + lane * 128);
+    }
+  }
+  auto residual = [&](int j) -> int { return LOG2 <= 3 ? (j == 0 ? rpre0 : rpre1) : (int)res[s0 + 32 * j]; };
 
   // ---- 1. gather reference samples p[-2nT..2nT]; substitution folded in (intrapred.h:838-984) ----
   const int left_off = w0 & 0xffff, top_off = w0 >> 16;
@@ -212,7 +228,6 @@ __device__ __forceinline__ void process_block(const Geo& g, uint32_t w0, uint32_
   }
 
   // ---- 3. prediction + residual + store into the tile --------------------------------------------
-  const bool has_res = w1 & BP_HAS_RES;
   const bool edge_ok = w1 & BP_EDGE;
   if (mode == 0) {
     const int tr = p[1 + nT], bl = p[-1 - nT];
@@ -221,7 +236,7 @@ __device__ __forceinline__ void process_block(const Geo& g, uint32_t w0, uint32_
     for (int j = 0; j < ITER; j++) {
       const int y = yb + j * RPI;
       int v = ((nT - 1 - x) * p[-1 - y] + hx + (nT - 1 - y) * top + (y + 1) * bl) >> (LOG2 + 1);
-      if (has_res) v = clip3i(0, maxv, v + res[s0 + 32 * j]);
+      if (has_res) v = clip3i(0, maxv, v + residual(j));
       *reinterpret_cast<Pixel*>(out + j * RPI * pitch) = (Pixel)v;
     }
   } else if (mode == 1) {
@@ -239,7 +254,7 @@ __device__ __forceinline__ void process_block(const Geo& g, uint32_t w0, uint32_
         if (y == 0) v = x == 0 ? (p[-1] + 2 * dc + p[1] + 2) >> 2 : top;
         else if (x == 0) v = (p[-y - 1] + 3 * dc + 2) >> 2;
       }
-      if (has_res) v = clip3i(0, maxv, v + res[s0 + 32 * j]);
+      if (has_res) v = clip3i(0, maxv, v + residual(j));
       *reinterpret_cast<Pixel*>(out + j * RPI * pitch) = (Pixel)v;
     }
   } else {
@@ -258,7 +273,7 @@ __device__ __forceinline__ void process_block(const Geo& g, uint32_t w0, uint32_
         const int u = vertical ? x : y, w = vertical ? y : x;
         int v = p[sgn * (u + 1)];
         if (edge_flt && u == 0) v = clip3i(0, maxv, p1 + ((p[-sgn * (1 + w)] - p0) >> 1));
-        if (has_res) v = clip3i(0, maxv, v + res[s0 + 32 * j]);
+        if (has_res) v = clip3i(0, maxv, v + residual(j));
         *reinterpret_cast<Pixel*>(out + j * RPI * pitch) = (Pixel)v;
       }
     } else if (angle > 0) {
@@ -270,7 +285,7 @@ __device__ __forceinline__ void process_block(const Geo& g, uint32_t w0, uint32_
         const int t = (w + 1) * angle;
         const int k0 = u + (t >> 5) + 1, f = t & 31;
         int v = ((32 - f) * p[sgn * k0] + f * p[sgn * (k0 + 1)] + 16) >> 5;
-        if (has_res) v = clip3i(0, maxv, v + res[s0 + 32 * j]);
+        if (has_res) v = clip3i(0, maxv, v + residual(j));
         *reinterpret_cast<Pixel*>(out + j * RPI * pitch) = (Pixel)v;
       }
     } else {
@@ -285,7 +300,7 @@ __device__ __forceinline__ void process_block(const Geo& g, uint32_t w0, uint32_
         const int i0 = k0 >= 0 ? sgn * k0 : -sgn * ((k0 * inv + 128) >> 8);
         const int i1 = k1 >= 0 ? sgn * k1 : -sgn * ((k1 * inv + 128) >> 8);
         int v = ((32 - f) * p[i0] + f * p[i1] + 16) >> 5;
-        if (has_res) v = clip3i(0, maxv, v + res[s0 + 32 * j]);
+        if (has_res) v = clip3i(0, maxv, v + residual(j));
         *reinterpret_cast<Pixel*>(out + j * RPI * pitch) = (Pixel)v;
       }
     }
