@@ -79,6 +79,21 @@ class HeifBuilder:
         self.refs.append((b"dimg", gid, list(tile_ids)))
         return gid
 
+    def add_overlay(self, child_ids, canvas_w, canvas_h, offsets, background=(0, 0, 0, 0xffff), extra_props=()):
+        """'iovl' derived image (ISO/IEC 23008-12 6.6.2.2; libheif context.cc:318-369): 16-bit RGBA background colour,
+        canvas size and one signed (x, y) offset per referenced image"""
+        big = canvas_w > 65535 or canvas_h > 65535 or any(abs(v) > 32767 for o in offsets for v in o)
+        f = ">II" if big else ">HH"
+        fs = ">ii" if big else ">hh"
+        payload = bytes([0, 1 if big else 0]) + struct.pack(">HHHH", *background) + struct.pack(f, canvas_w, canvas_h)
+        payload += b"".join(struct.pack(fs, x, y) for x, y in offsets)
+        props = [self.add_prop(fullbox(b"ispe", 0, 0, struct.pack(">II", canvas_w, canvas_h)))]
+        for p in extra_props:
+            props.append(self.add_prop(p))
+        oid = self.add_item(b"iovl", payload, props)
+        self.refs.append((b"dimg", oid, list(child_ids)))
+        return oid
+
     def add_alpha(self, master_id, stream, width, height, chroma_format, bit_depth, extra_props=()):
         auxc = fullbox(b"auxC", 0, 0, b"urn:mpeg:hevc:2015:auxid:1\x00")
         aid = self.add_hevc_image(stream, width, height, chroma_format, bit_depth, hidden=True, extra_props=(auxc,) + tuple(extra_props))
