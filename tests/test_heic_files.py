@@ -40,6 +40,30 @@ def test_oracle_reproduces_reference(name):
             assert md5(heic_oracle.decode_rgb(load(name), fmt).tobytes()) == m[key + "_md5"], key
 
 
+def _iovl_file(chroma_format):
+    from tools import heif_writer as W, hevcenc
+    b = W.HeifBuilder()
+    kids = [b.add_hevc_image(hevcenc.encode(hevcenc.synth_image(64, 64, chroma_format, 8, 70 + k), chroma_format=chroma_format, bit_depth=8, seed=70 + k),
+                             64, 64, chroma_format, 8, hidden=True) for k in range(2)]
+    b.primary = b.add_overlay(kids, 100, 80, [(3, 5), (30, 12)], background=(0x1234, 0x8000, 0xffff, 0xffff))
+    return b.serialize()
+
+
+def test_iovl_items_are_reported_not_decoded():
+    """An 'iovl' derived image is outside the path: the reader names the item type instead of
+    guessing, and the unmodified reference itself only composes overlays whose children are 4:4:4."""
+    data = _iovl_file(1)
+    hf = hb.HeifFile(data, host_only=True)
+    with pytest.raises(hb.HeifCudaError, match="not an HEVC image"):
+        hf.coded_stream(hf.primary_id)
+    import refheif as R
+    if not R.available():
+        pytest.skip("oracle/_ref not built")
+    with pytest.raises(RuntimeError, match="Unsupported color conversion"):
+        R.decode(data, R.COLORSPACE_RGB, R.CHROMA_RGB)
+    assert R.decode(_iovl_file(3), R.COLORSPACE_RGB, R.CHROMA_RGB)["interleaved"][1:] == (100, 80)
+
+
 @pytest.fixture(scope="module")
 def engine():
     e = hb.Engine(0)
