@@ -269,18 +269,6 @@ struct Cabac {
     value -= (unsigned long long)(bins * range) << avail;
     refill();
   }
-  // coeff_abs_level_remaining (9.3.3.11) when the whole codeword fits the 16 peeked bypass bins; -1 (nothing consumed) otherwise
-  HC_HD int coeff_rem(const Tables& t, int rice) {
-    const uint32_t q16 = peek16(t);
-    const int ones = q16 == 0xffffu ? 16 : k0_clz(~(q16 << 16));
-    const int suffix_len = ones <= 3 ? rice : ones - 3 + rice;
-    const int len = ones + 1 + suffix_len;
-    if (len > 16) return -1;
-    const uint32_t bins = q16 >> (16 - len);
-    const int suffix = (int)(bins & ((1u << suffix_len) - 1u));
-    consume(len, bins);
-    return ones <= 3 ? (ones << rice) + suffix : (((1 << (ones - 3)) + 3 - 1) << rice) + suffix;
-  }
   HC_HD int terminate() {
     range -= 2;
     const unsigned long long scaled = (unsigned long long)range << avail;
@@ -381,24 +369,6 @@ static __device__ __noinline__ uint32_t cab_peek16(uint32_t sa, uint32_t ta) {
   const unsigned long long recip = lds32(ta + TAB_RECIP + ((s_.z - 256) << 2));
   return (uint32_t)(((unsigned long long)(uint32_t)(value >> ((int)s_.w - 16)) * recip) >> 34);
 }
-// coeff_abs_level_remaining in one call (peek + consume shared one state load / store): -1 when the codeword is longer
-// than the 16 peeked bins, with nothing consumed
-static __device__ __noinline__ int cab_coeff_rem(uint32_t sa, uint32_t ta, int rice) {
-  K0_CAB_LOAD
-  const unsigned long long recip = lds32(ta + TAB_RECIP + ((range - 256) << 2));
-  const uint32_t q16 = (uint32_t)(((unsigned long long)(uint32_t)(value >> (avail - 16)) * recip) >> 34);
-  const int ones = q16 == 0xffffu ? 16 : __clz((int)~(q16 << 16));
-  const int suffix_len = ones <= 3 ? rice : ones - 3 + rice;
-  const int len = ones + 1 + suffix_len;
-  if (len > 16) return -1;
-  const uint32_t bins = q16 >> (16 - len);
-  const int suffix = (int)(bins & ((1u << suffix_len) - 1u));
-  avail -= len;
-  value -= (unsigned long long)(bins * range) << avail;
-  K0_CAB_REFILL
-  K0_CAB_STORE
-  return ones <= 3 ? (ones << rice) + suffix : (((1 << (ones - 3)) + 3 - 1) << rice) + suffix;
-}
 static __device__ __noinline__ void cab_consume(uint32_t sa, int n, uint32_t bins) {
   K0_CAB_LOAD
   avail -= n;
@@ -446,7 +416,6 @@ struct CabacDev {
   HC_D uint32_t bypass_bits(const Tables&, int n) { return cab_bypass_bits(sa, ta, n); }
   HC_D uint32_t peek16(const Tables&) const { return cab_peek16(sa, ta); }
   HC_D void consume(int n, uint32_t bins) { cab_consume(sa, n, bins); }
-  HC_D int coeff_rem(const Tables&, int rice) { return cab_coeff_rem(sa, ta, rice); }
   HC_D int terminate() { return cab_terminate(sa); }
 };
 #endif
@@ -874,8 +843,16 @@ struct Parser {
         const int base = 1 + (int)((g1mask >> c) & 1) + ((c == firstG1) ? g2 : 0);
         int rem = 0;
         if ((escmask >> c) & 1) {
-          rem = cb.coeff_rem(t, rice);
-          if (rem < 0) {
+          const uint32_t q16 = cb.peek16(t);
+          const int ones = q16 == 0xffffu ? 16 : k0_clz(~(q16 << 16));
+          const int suffix_len = ones <= 3 ? rice : ones - 3 + rice;
+          const int len = ones + 1 + suffix_len;
+          if (len <= 16) {
+            const uint32_t bins = q16 >> (16 - len);
+            const int suffix = (int)(bins & ((1u << suffix_len) - 1u));
+            rem = ones <= 3 ? (ones << rice) + suffix : (((1 << (ones - 3)) + 3 - 1) << rice) + suffix;
+            cb.consume(len, bins);
+          } else {
             int prefix = 0;
             K0_LOOP while (prefix < 32 && cb.bypass()) prefix++;
             if (prefix >= 32) { fail(ERR_BITSTREAM); return 0; }
