@@ -160,15 +160,13 @@ __device__ __forceinline__ void sao_ctb(const BatchView& bv, const hc_pic& pic, 
       // interior unit: no sample's neighbour leaves the CTB (or the picture) in the direction of this class
       const bool in_x = hx == 0 || ((x0 & mw) != 0 && ((x0 + 8) & mw) != 0 && x0 + 8 < width);
       const bool in_y = vy == 0 || ((y & mh) != 0 && ((y + 1) & mh) != 0 && y + 1 < height);
+      // One arithmetic path for every unit of the warp: an interior unit uses all eight samples, a border unit only those
+      // whose neighbours are usable (okmask). The first version ran a fast loop for interior units and a second, branchy
+      // loop for border units — a warp holds both kinds (units 0 and 7 of every 64-sample CTB row are border units for
+      // three of the four edge classes), so it executed both loops one after the other.
+      unsigned okmask = 0;
       if (nvalid == 8 && skip == 0 && in_x && in_y && !self_quirk) {
-#pragma unroll
-        for (int k = 0; k < 8; k++) {
-          const int a = hx < 0 ? ra[k] : (hx == 0 ? ra[k + 1] : ra[k + 2]);
-          const int b = hx < 0 ? rb[k + 2] : (hx == 0 ? rb[k + 1] : rb[k]);
-          const int e = sign3(orig[k] - a) + sign3(orig[k] - b);
-          const int off = (int)(int8_t)(packed >> (8 * (e + 2)));
-          v[k] = clip3i(0, maxv, orig[k] + off);
-        }
+        okmask = 0xffu;
       } else {
         const int lwid = min(1 << log2w, width - (ctbx << log2w)), lhei = min(1 << log2h, height - (ctby << log2h));
         const int ly = y & mh;
@@ -196,7 +194,6 @@ __device__ __forceinline__ void sao_ctb(const BatchView& bv, const hc_pic& pic, 
           }
           return ok;
         };
-        unsigned okmask = 0;
         if (nvalid == 8 && !self_quirk) {
           // A full unit lies inside one CTB column. Which CTB does a neighbour fall into? 3 x 3 bits, (dy + 1) * 3 + dx + 1,
           // the centre (this CTB) always usable, the others from the CTB's neighbour mask (a CTB beyond the picture edge
@@ -225,14 +222,15 @@ __device__ __forceinline__ void sao_ctb(const BatchView& bv, const hc_pic& pic, 
             if (k < nvalid && sample_ok(k)) okmask |= 1u << k;
         }
         okmask &= ~skip;
+      }
 #pragma unroll
-        for (int k = 0; k < 8; k++) {
-          if (!((okmask >> k) & 1)) continue;
-          const int a = hx < 0 ? ra[k] : (hx == 0 ? ra[k + 1] : ra[k + 2]);
-          const int b = hx < 0 ? rb[k + 2] : (hx == 0 ? rb[k + 1] : rb[k]);
-          const int e = sign3(orig[k] - a) + sign3(orig[k] - b);   // -2..2
-          if (e) v[k] = clip3i(0, maxv, orig[k] + (e == -2 ? o0 : e == -1 ? o1 : e == 1 ? o2 : o3));
-        }
+      for (int k = 0; k < 8; k++) {
+        const int a = hx < 0 ? ra[k] : (hx == 0 ? ra[k + 1] : ra[k + 2]);
+        const int b = hx < 0 ? rb[k + 2] : (hx == 0 ? rb[k + 1] : rb[k]);
+        const int e = sign3(orig[k] - a) + sign3(orig[k] - b);   // -2..2; the packed table holds 0 for e == 0
+        const int off = (int)(int8_t)(packed >> (8 * (e + 2)));
+        const int r = clip3i(0, maxv, orig[k] + off);
+        v[k] = ((okmask >> k) & 1) ? r : orig[k];
       }
     }
   }
