@@ -44,7 +44,7 @@ void launch_k1_indirect(const BatchView& bv, const uint32_t* const tb_index[4], 
 // shared-memory bytes one K2 row task needs (CTB of ctb_w x ctb_h samples of this component)
 int k2_task_smem_bytes(int ctb_w, int ctb_h, int pixel_bytes);
 // smem_bytes: dynamic shared memory per CTA = max over CTAs of the sum of its K2_WARPS tasks
-void launch_k2(const BatchView& bv, const RowTask* tasks, int ntasks, int smem_bytes, int* progress, cudaStream_t stream);
+void launch_k2(const BatchView& bv, const RowTask* tasks, int ntasks, int smem_bytes, int* progress, int packed, cudaStream_t stream);
 void launch_k3(const BatchView& bv, long long max_units, int planes, cudaStream_t stream);
 void launch_k4(const BatchView& bv, long long max_ctbs, int planes, cudaStream_t stream);
 void launch_k5(const CscArgs& a, bool sixteen_bit, cudaStream_t stream);
