@@ -155,9 +155,11 @@ struct hc_batch {
   const uint32_t* d_tb_index[4] = {nullptr, nullptr, nullptr, nullptr};
   int tb_counts[4] = {0, 0, 0, 0};
   const hc::RowTask* d_tasks = nullptr;
+  const hc::WarpWork* d_work = nullptr;   // packed K2 mapping (k2_packed == 3): 3 lists per CTA
+  int k2_ctas = 0;
   int ntasks = 0;
   int k2_smem = 0;   // dynamic shared memory per K2 CTA
-  int k2_packed = 0;        // 0: six warps per CTA; 1: Y, Y, CbCr, CbCr; 2: Y, Y, 4 x chroma (all pictures 4:2:0)
+  int k2_packed = 0;        // 0: six warps per CTA; 1: Y, Y, CbCr, CbCr; 2: Y, Y, 4 x chroma (all 4:2:0, HEIFCUDA_K2_PACKED); 3: lists (default)
   // K0 (device CABAC parse) of the pictures added as bitstreams
   int nk0 = 0, nchains = 0;
   bool k0_done = false;
@@ -531,6 +533,7 @@ int hc_batch_upload(hc_batch* b) {
   size_t o_idx[4];
   for (int l = 0; l < 4; l++) o_idx[l] = place(sizeof(uint32_t) * counts[l]);
   const size_t o_tasks = place(sizeof(hc::RowTask) * n_tasks);
+  const size_t o_work = place(sizeof(hc::WarpWork) * 3 * n_tasks);   // packed K2 mapping: at most one CTA per task
   // K0 inputs (uploaded): picture descriptors, slices, per-CTB tables, substreams, chains, RBSP bytes
   const int nk0 = b->nk0;
   size_t k_slices = 0, k_ctbs = 0, k_subs = 0, k_chains = 0, k_bytes = 0;
@@ -735,7 +738,50 @@ int hc_batch_upload(hc_batch* b) {
     for (int i = 0; i < np; i++) all420 = all420 && b->hpics[i].chroma_format == 1;
     b->k2_packed = all420 ? 2 : 0;   // measured per 32 x 12 MP: six-warp CTAs 6.48 ms, mode 1 5.35 ms, mode 2 5.04 ms
     if (const char* m = getenv("HEIFCUDA_K2_PACKED")) b->k2_packed = all420 ? atoi(m) : 0;
-    if (b->k2_packed) {
+    // Default for every batch: explicit per-warp lists (mode 3). A luma-class row (luma, or chroma that is not subsampled)
+    // takes a warp of its own, subsampled chroma rows share the third warp up to four units (4:2:0 row = 1, 4:2:2 row = 2).
+    if (!getenv("HEIFCUDA_K2_PACKED") && t > 0) {
+      b->k2_packed = 3;
+      hc::WarpWork* work = (hc::WarpWork*)(H + o_work);
+      auto task_bytes = [&](int idx, int& units) {
+        const hc_pic& p = b->hpics[tasks[idx].pic];
+        const int ps = (p.bit_depth_y == 8 && p.bit_depth_c == 8) ? 1 : 2;
+        const int c = tasks[idx].comp;
+        const int sw = (c && (p.chroma_format == 1 || p.chroma_format == 2)) ? 1 : 0, sh = (c && p.chroma_format == 1) ? 1 : 0;
+        units = (sw + sh == 2) ? 1 : (sw + sh == 1 ? 2 : 0);   // 0: luma class
+        return hc::k2_task_smem_bytes((1 << p.log2_ctb) >> sw, (1 << p.log2_ctb) >> sh, ps);
+      };
+      int ncta = 0;
+      b->k2_smem = 0;
+      int luma[2], nl = 0, chroma[4], nc = 0, cunits = 0;
+      auto flush = [&]() {
+        if (nl == 0 && nc == 0) return;
+        hc::WarpWork* w = work + 3 * (size_t)ncta;
+        memset(w, 0, 3 * sizeof(hc::WarpWork));
+        int off = 0, u;
+        for (int k = 0; k < nl; k++) { w[k].task[0] = (uint32_t)luma[k]; w[k].n = 1; tasks[luma[k]].smem_off = (uint32_t)off; off += task_bytes(luma[k], u); }
+        int cmax = 0;
+        for (int k = 0; k < nc; k++) { w[2].task[k] = (uint32_t)chroma[k]; tasks[chroma[k]].smem_off = (uint32_t)off; cmax = std::max(cmax, task_bytes(chroma[k], u)); }
+        w[2].n = (uint32_t)nc;
+        b->k2_smem = std::max(b->k2_smem, off + cmax);
+        ncta++;
+        nl = nc = cunits = 0;
+      };
+      for (int idx = 0; idx < t; idx++) {
+        int units;
+        task_bytes(idx, units);
+        if (units == 0) {
+          if (nl == 2) flush();
+          luma[nl++] = idx;
+        } else {
+          if (cunits + units > 4 || nc == 4) flush();
+          chroma[nc++] = idx;
+          cunits += units;
+        }
+      }
+      flush();
+      b->k2_ctas = ncta;
+    } else if (b->k2_packed) {
       b->k2_smem = 0;
       for (int base = 0; base < t; base += 6) {
         auto bytes = [&](int idx) {
@@ -775,6 +821,7 @@ int hc_batch_upload(hc_batch* b) {
   b->view.npics = np;
   for (int l = 0; l < 4; l++) { b->d_tb_index[l] = (const uint32_t*)(D + o_idx[l]); b->tb_counts[l] = counts[l]; }
   b->d_tasks = (const hc::RowTask*)(D + o_tasks);
+  b->d_work = (const hc::WarpWork*)(D + o_work);
 
   cudaEventRecord(b->ev[0], b->stream);
   if (!cuda_ok(cudaMemcpyAsync(D, H, o, cudaMemcpyHostToDevice, b->stream), "cudaMemcpyAsync(H2D records)")) return HC_ERR_CUDA;
@@ -856,7 +903,8 @@ int hc_batch_reconstruct_async(hc_batch* b, int stages) {
   if (b->nk0)
     hc::launch_k1_indirect(b->view, b->d_k0_tb_index, b->k0_list_cap, (const unsigned*)(D + b->k0_status_off) + b->nk0, b->eng->sm_count, s);
   cudaEventRecord(b->ev[3], s);
-  hc::launch_k2(b->view, b->d_tasks, b->ntasks, b->k2_smem, (int*)b->d_progress.p, b->k2_packed, s);
+  if (b->k2_packed == 3) hc::launch_k2_lists(b->view, b->d_tasks, b->d_work, b->k2_ctas, b->k2_smem, (int*)b->d_progress.p, s);
+  else hc::launch_k2(b->view, b->d_tasks, b->ntasks, b->k2_smem, (int*)b->d_progress.p, b->k2_packed, s);
   b->launches += 1;
   cudaEventRecord(b->ev[4], s);
   if (stages & HC_STAGE_DEBLOCK) {

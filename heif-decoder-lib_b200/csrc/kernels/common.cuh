@@ -44,7 +44,13 @@ struct RowTask {
   int32_t dep;   // task index of the row above (same picture / component), -1 for row 0
   uint32_t smem_off;  // byte offset of this warp's slice of the CTA's dynamic shared memory
 };
-constexpr int K2_WARPS = 6;   // row tasks per CTA (two Y/Cb/Cr triples of a 4:2:0 picture)
+constexpr int K2_WARPS = 6;   // row tasks per CTA (two Y/Cb/Cr triples of a 4:2:0 picture) — six-warp mapping
+// Packed mapping of K2: the row tasks one warp runs one after the other (a CTA is three warps: two luma-class rows and one
+// list of up to four subsampled chroma rows; see k2_intra_lists_kernel)
+struct WarpWork {
+  uint32_t task[4];
+  uint32_t n;
+};
 
 #if defined(__CUDACC__)
 // L2-coherent loads: neighbour samples and progress counters are produced by other SMs while

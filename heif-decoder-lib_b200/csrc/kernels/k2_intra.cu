@@ -620,6 +620,44 @@ k2_intra_packed_kernel(BatchView bv, const RowTask* __restrict__ tasks, int ntas
   }
 }
 
+// General form of the packed mapping (any mix of chroma formats, monochrome alpha pictures): the host builds the three task
+// lists of every CTA (engine.cu: two luma-class rows on a warp each, up to four units of subsampled chroma rows on the
+// third). Lists are filled in task order, a luma-class list holds one task and all chroma rows of a CTA share one warp, so
+// a task still only waits for a task in an earlier CTA, in another warp's single-task list, or earlier in its own list.
+__global__ void __launch_bounds__(96, 6)
+k2_intra_lists_kernel(BatchView bv, const RowTask* __restrict__ tasks, const WarpWork* __restrict__ work, int* progress) {
+  extern __shared__ __align__(16) uint8_t k2_smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const WarpWork ww = work[blockIdx.x * 3 + warp];
+#pragma unroll 1
+  for (uint32_t k = 0; k < ww.n; k++) {
+    const int index = (int)ww.task[k];
+    const RowTask task = tasks[index];
+    const hc_pic& pic = bv.pics[task.pic];
+    if (pic.bit_depth_y == 8 && pic.bit_depth_c == 8)
+      run_row<uint8_t>(bv, pic, task, progress, index, k2_smem + task.smem_off, lane);
+    else
+      run_row<uint16_t>(bv, pic, task, progress, index, k2_smem + task.smem_off, lane);
+    __syncwarp();
+  }
+}
+
+void launch_k2_lists(const BatchView& bv, const RowTask* tasks, const WarpWork* work, int nctas, int smem_bytes, int* progress, cudaStream_t stream) {
+  if (nctas <= 0) return;
+  {
+    static std::atomic<int> max_set[64];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    dev &= 63;
+    if (smem_bytes > max_set[dev].load(std::memory_order_relaxed)) {
+      cudaFuncSetAttribute(k2_intra_lists_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+      int cur = max_set[dev].load();
+      while (smem_bytes > cur && !max_set[dev].compare_exchange_weak(cur, smem_bytes)) {}
+    }
+  }
+  k2_intra_lists_kernel<<<nctas, 96, smem_bytes, stream>>>(bv, tasks, work, progress);
+}
+
 void launch_k2(const BatchView& bv, const RowTask* tasks, int ntasks, int smem_bytes, int* progress, int packed, cudaStream_t stream) {
   if (ntasks <= 0) return;
   // per device attribute: raised only when a launch needs more than any earlier one on this device (the plugin launches

@@ -45,6 +45,8 @@ void launch_k1_indirect(const BatchView& bv, const uint32_t* const tb_index[4], 
 int k2_task_smem_bytes(int ctb_w, int ctb_h, int pixel_bytes);
 // smem_bytes: dynamic shared memory per CTA = max over CTAs of the sum of its K2_WARPS tasks
 void launch_k2(const BatchView& bv, const RowTask* tasks, int ntasks, int smem_bytes, int* progress, int packed, cudaStream_t stream);
+// packed mapping with explicit per-warp task lists: `work` holds 3 entries per CTA
+void launch_k2_lists(const BatchView& bv, const RowTask* tasks, const WarpWork* work, int nctas, int smem_bytes, int* progress, cudaStream_t stream);
 void launch_k3(const BatchView& bv, long long max_units, int planes, cudaStream_t stream);
 void launch_k4(const BatchView& bv, long long max_ctbs, int planes, cudaStream_t stream);
 void launch_k5(const CscArgs& a, bool sixteen_bit, cudaStream_t stream);
