@@ -372,8 +372,8 @@ def main():
                     "d2h_bytes_per_step": int(st["bytes_d2h"] / max(1, st["batches"])),
                     "ms_per_step": e2e_dt * 1e3, "host_parse_ms_per_step": parse_s * 1e3, "gpu_phase_ms_per_step": gpu_phase_s * 1e3,
                     "first_batch_ms": first_batch_s * 1e3, "steps": e2e_steps,
-                    "api": "hc_heic_decode_stream: header parse (+ host share of the slice data) of batch b+1 and D2H + delivery of batch "
-                           "b-1 overlap [K0,] K1..K5 of batch b; pinned host output"},
+                    "api": "hc_heic_decode_stream: three batches in flight on the GPU (K0 on a low-priority stream, K1..K5 + copies on "
+                           "high-priority ones), header parse (+ host share of the slice data) two batches ahead; pinned host output"},
             "gpu_launches": launches,
             "clocks": clocks,
             "stage_ms_last_step": {k: round(v, 4) for k, v in stage_last.items()},
