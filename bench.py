@@ -173,6 +173,7 @@ def main():
                     "meanwhile in the e2e arm (default: engine default)")
     ap.add_argument("--parser", default="device", choices=["device", "host"],
                     help="where the CABAC slice data is parsed: K0 on the GPU (default) or the host parser")
+    ap.add_argument("--skip-baselines", action="store_true", help="kernel experiments: leave out the cpu_baseline and plugin_dropin arms")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -345,7 +346,7 @@ def main():
 
     # ---- CPU baseline on the box's cores (rank 0, N = 1 only) ----
     cpu = None
-    if rank == 0 and world == 1:
+    if rank == 0 and world == 1 and not args.skip_baselines:
         r = reference_arm(distinct, 2, 1, cores)
         if r is not None:
             cpu = {"value": r["value"], "unit": UNIT, "cores": cores, "kind": "reference", "sample": r["sample"]}
@@ -353,7 +354,7 @@ def main():
             cpu = {"value": None, "unit": UNIT, "cores": cores, "kind": "reference", "sample": "oracle/_ref missing on this box"}
 
     plugin = None
-    if rank == 0 and world == 1:
+    if rank == 0 and world == 1 and not args.skip_baselines:
         eng.close()
         eng = None
         plugin = plugin_arm(distinct, cores)

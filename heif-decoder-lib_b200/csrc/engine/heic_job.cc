@@ -137,8 +137,8 @@ void hc_heic_job_destroy(hc_heic_job* j) {
 // band_begin/band_end: tile rows [begin, end) of a grid image to decode (band_end < 0: everything)
 // host_share: percentage of the coded items the host threads parse although the device parser is on (hybrid; < 0: the
 // engine option, where "auto" means none outside hc_heic_decode_stream)
-static hc_heic_job* job_create(hc_engine* e, int nfiles, const uint8_t* const* data, const size_t* sizes,
-                               int want_alpha, int threads, int band_begin, int band_end, int host_share_arg = -1) {
+static hc_heic_job* job_create_impl(hc_engine* e, int nfiles, const uint8_t* const* data, const size_t* sizes,
+                                    int want_alpha, int threads, int band_begin, int band_end, int host_share_arg) {
   if (!e || nfiles <= 0 || !data || !sizes) {
     hc::set_last_error("hc_heic_job_create: bad argument");
     return nullptr;
@@ -178,6 +178,11 @@ static hc_heic_job* job_create(hc_engine* e, int nfiles, const uint8_t* const* d
       if (!err.empty()) { hc::set_last_error("file " + std::to_string(f) + ": " + err); return nullptr; }
       im.info.is_grid = 1;
       im.info.rows = g.rows; im.info.cols = g.cols; im.info.width = g.out_w; im.info.height = g.out_h;
+      // the reference's security limit (context.cc:547-560 check_resolution, heif_limits.h:37-38)
+      if (g.out_w <= 0 || g.out_h <= 0 || (uint64_t)g.out_w * (uint64_t)g.out_h > (uint64_t)32768 * 32768) {
+        hc::set_last_error("file " + std::to_string(f) + ": grid output size exceeds the maximum image size");
+        return nullptr;
+      }
       ids = g.tiles;
       if (band_end >= 0) {
         if (band_begin < 0 || band_begin >= band_end || band_end > g.rows) { hc::set_last_error("tile row band outside the grid"); return nullptr; }
@@ -231,20 +236,17 @@ static hc_heic_job* job_create(hc_engine* e, int nfiles, const uint8_t* const* d
   }
   const int host_share = !device_parse ? 0 : (host_share_arg >= 0 ? host_share_arg : std::max(0, hc_engine_get_option(e, "host_share_pct")));
   std::atomic<size_t> next{0};
-  auto worker = [&]() {
-    for (;;) {
-      size_t i = next.fetch_add(1);
-      if (i >= j->items.size()) return;
+  auto parse_item = [&](size_t i) {
       CodedItem& ci = j->items[i];
       std::string err = j->files[ci.file]->coded_stream(ci.item_id, ci.stream);
-      if (!err.empty()) { ci.error = err; continue; }
+      if (!err.empty()) { ci.error = err; return; }
       // hybrid: while the GPU parses the previous batch, the host cores parse an evenly spread share of this one
       const bool to_host = host_share > 0 && ((i + 1) * (size_t)host_share) / 100 != (i * (size_t)host_share) / 100;
       if (device_parse_job && !to_host) {
         // K0: only parameter sets and slice headers are read here; the GPU parses the slice data
         std::unique_ptr<hc_k0_picture> k(new hc_k0_picture);
         err = hc::k0_prepare(ci.stream.data(), ci.stream.size(), HC_STREAM_LENGTH_PREFIXED, k->hp);
-        if (!err.empty()) { ci.error = err; continue; }
+        if (!err.empty()) { ci.error = err; return; }
         // K0 is serial per substream: a picture is worth parsing on the GPU when its critical path is short — CTB rows of
         // a WPP picture advance two CTBs behind each other, a picture without WPP is ONE chain of all its CTBs (a 1080p
         // picture: 510 CTBs x ~3 ms against ~40 ms on one host core). Long ones stay with the host parser.
@@ -258,17 +260,30 @@ static hc_heic_job* job_create(hc_engine* e, int nfiles, const uint8_t* const* d
         if (k->hp.eligible && short_enough) {
           ci.k0 = std::move(k);
           std::vector<uint8_t>().swap(ci.stream);
-          continue;
+          return;
         }
       }
       thread_local hc::HevcIntraParser parser;   // reused: see k0_prepare
       parser.reset();
       parser.set_collect_only(false);
       err = parser.push_length_prefixed(ci.stream.data(), ci.stream.size());
-      if (!err.empty()) { ci.error = err; continue; }
+      if (!err.empty()) { ci.error = err; return; }
       ci.rec.rec = parser.take_picture(&err);
       if (!ci.rec.rec) ci.error = err;
       std::vector<uint8_t>().swap(ci.stream);
+  };
+  // the workers are std::threads: an exception leaving one would terminate the process
+  auto worker = [&]() {
+    for (;;) {
+      const size_t i = next.fetch_add(1);
+      if (i >= j->items.size()) return;
+      try {
+        parse_item(i);
+      } catch (const std::bad_alloc&) {
+        j->items[i].error = "out of memory while parsing";
+      } catch (const std::exception& ex) {
+        j->items[i].error = std::string("parser failure: ") + ex.what();
+      }
     }
   };
   if (nthreads == 1) worker();
@@ -308,6 +323,13 @@ static hc_heic_job* job_create(hc_engine* e, int nfiles, const uint8_t* const* d
         CodedItem& ci = j->items[im.tiles[k]];
         const hc_pic& p = ci.pic();
         const hc::HeifItem* tit = j->files[im.file]->item(ci.item_id);
+        // context.cc:2328-2337: every tile has the size of the first one ("Grid tiles have different sizes"); tiles of another
+        // chroma format or bit depth cannot share a canvas (the reference fails in its paste, context.cc:2452-2465)
+        if (p.crop_w != tw || p.crop_h != th) { hc::set_last_error("Grid tiles have different sizes"); return nullptr; }
+        if (p.chroma_format != p0.chroma_format || p.bit_depth_y != p0.bit_depth_y) { hc::set_last_error("grid tiles differ in chroma format or bit depth"); return nullptr; }
+        // the reference decodes every tile through decode_image_planar, which applies the tile item's own irot / imir / clap
+        // (context.cc:1955-2016) before the paste; that combination is not built here
+        if (tit && !tit->xforms.empty()) { hc::set_last_error("transformations on grid tile items are not supported"); return nullptr; }
         const int tfull = tit && tit->nclx.present ? tit->nclx.full_range : p.full_range;
         const int tmatrix = tit && tit->nclx.present ? tit->nclx.matrix : p.matrix_coeffs;
         const int x0 = (int)(k % im.info.cols) * tw, y0 = (int)(k / im.info.cols) * th;
@@ -412,6 +434,19 @@ static hc_heic_job* job_create(hc_engine* e, int nfiles, const uint8_t* const* d
             j->items.size(), (t_containers - std::chrono::duration<double>(t0.time_since_epoch()).count()) * 1e3, (t_parsed - t_containers) * 1e3, nthreads,
             (now_s() - t_parsed) * 1e3);
   return j.release();
+}
+
+// No exception may cross the C ABI: a crafted file can make any allocation of the walk above fail.
+static hc_heic_job* job_create(hc_engine* e, int nfiles, const uint8_t* const* data, const size_t* sizes,
+                               int want_alpha, int threads, int band_begin, int band_end, int host_share_arg = -1) {
+  try {
+    return job_create_impl(e, nfiles, data, sizes, want_alpha, threads, band_begin, band_end, host_share_arg);
+  } catch (const std::bad_alloc&) {
+    hc::set_last_error("out of memory while preparing the job");
+  } catch (const std::exception& ex) {
+    hc::set_last_error(std::string("job preparation failed: ") + ex.what());
+  }
+  return nullptr;
 }
 
 extern "C" {

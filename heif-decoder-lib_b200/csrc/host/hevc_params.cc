@@ -299,6 +299,8 @@ std::string parse_sps(const uint8_t* rbsp, size_t n, Sps& sps) {
   sps.SubHeightC = (cf == 1) ? 2 : 1;
   uint32_t w = br.ue(), h = br.ue();
   if (w == 0 || h == 0 || w > 65535 || h > 65535) return "SPS: picture size out of range";
+  // the reference's security limit (heif_limits.h:37-38, context.cc:547-560 check_resolution): 32768 x 32768 samples in total
+  if ((uint64_t)w * h > (uint64_t)32768 * 32768) return "SPS: picture size exceeds the maximum image size";
   sps.width = (int)w;
   sps.height = (int)h;
   if (br.flag()) {
@@ -401,6 +403,9 @@ std::string parse_sps(const uint8_t* rbsp, size_t n, Sps& sps) {
   if (sps.conf_left * sps.SubWidthC + sps.conf_right * sps.SubWidthC >= sps.width ||
       sps.conf_top * sps.SubHeightC + sps.conf_bottom * sps.SubHeightC >= sps.height)
     return "SPS: conformance window larger than the picture";
+  // A monochrome stream still codes bit_depth_chroma; nothing decodes with it, but the pixel type of a picture is chosen
+  // from both depths further down, so it follows luma here (the reference ignores it for chroma_format_idc 0).
+  if (sps.chroma_format_idc == 0) { sps.bit_depth_c = sps.bit_depth_y; sps.qp_bd_offset_c = sps.qp_bd_offset_y; }
   sps.valid = true;
   return "";
 }

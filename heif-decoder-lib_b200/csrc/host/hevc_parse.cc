@@ -229,6 +229,13 @@ std::string HevcIntraParser::push_nal(const uint8_t* nal, size_t size) {
     Sps s;
     std::string e = parse_sps(rbsp.data() + 2, rbsp_size - 2, s);
     if (!e.empty()) return e;
+    // parameter sets precede the first VCL NAL unit of their access unit (7.4.2.4.4); a picture in progress keeps its own
+    // copies, but later slice headers of it would be read against the new tables
+    if (d.started) return "SPS inside a picture";
+    // a re-sent SPS invalidates every PPS that refers to it (their derived tables are sized by the old one; the reference
+    // does the same, decctx.cc process_sps): a slice that still names such a PPS fails with "refers to a missing PPS"
+    for (Pps& p : d.pps_tab)
+      if (p.valid && p.sps_id == s.sps_id) p.valid = false;
     d.sps_tab[s.sps_id] = s;
     return "";
   }
@@ -236,6 +243,7 @@ std::string HevcIntraParser::push_nal(const uint8_t* nal, size_t size) {
     Pps p;
     std::string e = parse_pps(rbsp.data() + 2, rbsp_size - 2, d.sps_tab, p);
     if (!e.empty()) return e;
+    if (d.started) return "PPS inside a picture";
     d.pps_tab[p.pps_id] = std::move(p);
     return "";
   }
