@@ -975,16 +975,13 @@ int hc_batch_convert(hc_batch* b, int canvas, const hc_csc_params* params) {
   Canvas& c = b->canvases[canvas];
   static const int bpp_of[6] = {3, 4, 6, 8, 6, 8};
   if (params->out_format < 0 || params->out_format > 5) { hc::set_last_error("bad output format"); return HC_ERR_ARGUMENT; }
-  if ((params->out_format <= HC_OUT_RGBA) != (c.bit_depth == 8)) {
-    hc::set_last_error("8-bit images convert to RGB/RGBA, deeper images to RRGGBB(AA)");
-    return HC_ERR_UNSUPPORTED;
-  }
+  if (params->in_depth != c.bit_depth) { hc::set_last_error("conversion parameters were selected for another bit depth"); return HC_ERR_ARGUMENT; }
   c.rgb_bpp = bpp_of[params->out_format];
   c.rgb_stride = align_up((size_t)((c.ow + 7) & ~7) * c.rgb_bpp, 256);
   // lay all canvases' rgb buffers out in one block (grow if needed)
   size_t total = 0;
   for (auto& cv : b->canvases) {
-    const int bp = &cv == &c ? c.rgb_bpp : (cv.rgb_bpp ? cv.rgb_bpp : (cv.bit_depth == 8 ? 4 : 8));
+    const int bp = &cv == &c ? c.rgb_bpp : (cv.rgb_bpp ? cv.rgb_bpp : 8);
     cv.rgb_off = total;
     total += align_up(align_up((size_t)((cv.ow + 7) & ~7) * bp, 256) * cv.oh, 256);
   }
@@ -1007,7 +1004,6 @@ int hc_batch_convert(hc_batch* b, int canvas, const hc_csc_params* params) {
   a.out = (uint8_t*)b->d_rgb.p + c.rgb_off;
   a.out_stride = (long long)c.rgb_stride;
   a.p = *params;
-  a.p.bit_depth = c.bit_depth;
   cudaEvent_t e0 = b->eng->take_event(), e1 = b->eng->take_event();
   cudaEventRecord(e0, b->stream);
   hc::launch_k5(a, c.bit_depth != 8, b->stream);
@@ -1031,16 +1027,13 @@ int hc_batch_convert_many(hc_batch* b, int n, const int* canvases, const hc_csc_
       return HC_ERR_ARGUMENT;
     }
     Canvas& c = b->canvases[canvases[i]];
-    if ((params[i].out_format <= HC_OUT_RGBA) != (c.bit_depth == 8)) {
-      hc::set_last_error("8-bit images convert to RGB/RGBA, deeper images to RRGGBB(AA)");
-      return HC_ERR_UNSUPPORTED;
-    }
+    if (params[i].in_depth != c.bit_depth) { hc::set_last_error("conversion parameters were selected for another bit depth"); return HC_ERR_ARGUMENT; }
     c.rgb_bpp = bpp_of[params[i].out_format];
     c.rgb_stride = align_up((size_t)((c.ow + 7) & ~7) * c.rgb_bpp, 256);
   }
   size_t total = 0;
   for (auto& cv : b->canvases) {
-    const int bp = cv.rgb_bpp ? cv.rgb_bpp : (cv.bit_depth == 8 ? 4 : 8);
+    const int bp = cv.rgb_bpp ? cv.rgb_bpp : 8;
     cv.rgb_off = total;
     total += align_up(align_up((size_t)((cv.ow + 7) & ~7) * bp, 256) * cv.oh, 256);
   }
@@ -1069,7 +1062,6 @@ int hc_batch_convert_many(hc_batch* b, int n, const int* canvases, const hc_csc_
         a.out = (uint8_t*)b->d_rgb.p + c.rgb_off;
         a.out_stride = (long long)c.rgb_stride;
         a.p = params[i];
-        a.p.bit_depth = c.bit_depth;
         c.converted = true;
       }
       if (cb.n == hc::CSC_BATCH_MAX || (i == n && cb.n > 0)) {

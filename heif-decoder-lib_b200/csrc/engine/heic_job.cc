@@ -122,6 +122,7 @@ struct hc_heic_job {
   std::vector<ImagePlan> images;
   double parse_seconds = 0;
   bool want_alpha = false;
+  int forced_format = -1;   // HC_OUT_* for every image, or -1: by bit depth
 };
 
 extern "C" {
@@ -145,7 +146,12 @@ static hc_heic_job* job_create_impl(hc_engine* e, int nfiles, const uint8_t* con
   }
   std::unique_ptr<hc_heic_job> j(new hc_heic_job);
   j->eng = e;
-  j->want_alpha = want_alpha != 0;
+  // `want_alpha` doubles as the output selector: 0 / 1 = automatic (RGB(A) for 8-bit images, RRGGBB(AA)_LE for deeper ones),
+  // HC_OUTPUT_FORMAT(fmt) = that interleaved format for every image, whatever its bit depth
+  j->forced_format = (want_alpha & 0x100) ? (want_alpha & 0xff) : -1;
+  if (j->forced_format > HC_OUT_RRGGBBAA_LE) { hc::set_last_error("hc_heic_job_create: unknown output format"); return nullptr; }
+  j->want_alpha = j->forced_format >= 0 ? (j->forced_format == HC_OUT_RGBA || j->forced_format == HC_OUT_RRGGBBAA_BE || j->forced_format == HC_OUT_RRGGBBAA_LE)
+                                        : want_alpha != 0;
   const auto t0 = std::chrono::steady_clock::now();
 
   // ---- containers: which coded items does every image need? ----
@@ -422,7 +428,7 @@ static hc_heic_job* job_create_impl(hc_engine* e, int nfiles, const uint8_t* con
       if (hc_batch_link_alpha(j->batch, im.canvas, ac) != HC_OK) return nullptr;
     }
     const bool hdr = p0.bit_depth_y != 8;
-    const int fmt = hdr ? (j->want_alpha ? HC_OUT_RRGGBBAA_LE : HC_OUT_RRGGBB_LE) : (j->want_alpha ? HC_OUT_RGBA : HC_OUT_RGB);
+    const int fmt = j->forced_format >= 0 ? j->forced_format : (hdr ? (j->want_alpha ? HC_OUT_RRGGBBAA_LE : HC_OUT_RRGGBB_LE) : (j->want_alpha ? HC_OUT_RGBA : HC_OUT_RGB));
     if (hc_csc_select(matrix, primaries, full, p0.chroma_format, p0.bit_depth_y, has_alpha, fmt, &im.csc) != HC_OK) return nullptr;
     static const int bpp_of[6] = {3, 4, 6, 8, 6, 8};
     im.desc.width = W; im.desc.height = H; im.desc.chroma_format = p0.chroma_format; im.desc.bit_depth = p0.bit_depth_y;

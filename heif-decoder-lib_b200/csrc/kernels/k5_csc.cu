@@ -10,6 +10,10 @@
 //                   rgb2rgb.cc:28-272,613-729 — each of which is a separate full-image pass with
 //                   its own allocation in the reference
 //   HC_CSC_GBR / HC_CSC_YCGCO : the matrix_coefficients 0 / 8 branches        yuv2rgb.cc:197-226
+//   HC_CSC_MONO   : Op_mono_to_RGB24_32 (monochrome.cc:150-260); monochrome input of the other modes gets the constant
+//                   chroma planes of Op_mono_to_YCbCr420 (monochrome.cc:53-140)
+//   pre_op / post_op : Op_to_sdr_planes / Op_to_hdr_planes (hdr_sdr.cc:24-236) before or after the matrix, wherever the
+//                   reference's pipeline search puts them — 10/12-bit images to RGB(A) 8, 8-bit images to RRGGBB(AA)
 // Float arithmetic uses explicit round-to-nearest mul/add (no FMA contraction) and the
 // reference's (long)(x + 0.5f) rounding (common_utils.h:64-70) so results are bit-exact.
 //
@@ -108,6 +112,12 @@ HC_D void load_px4(const Pixel* p, int n, int fill, int v[8]) {
 
 // One thread converts 8 horizontally adjacent pixels: 8/16-byte plane loads, 8/16-byte interleaved stores
 // (24 .. 64 bytes per thread, contiguous across the warp). Output rows are padded to a multiple of 8 pixels.
+// Op_to_sdr_planes / Op_to_hdr_planes (hdr_sdr.cc:54-97,140-236) on one sample: `from` is the sample's depth for TO_SDR,
+// `to` the target depth for TO_HDR (the input is 8 bit there)
+HC_D int depth_op(int op, int v, int from, int to) {
+  return op == HC_DEPTH_TO_SDR ? v >> (from - 8) : (op == HC_DEPTH_TO_HDR ? ((v << (to - 8)) | (v >> (16 - to))) : v);
+}
+
 template <typename Pixel>
 __device__ __forceinline__ void csc_unit(const CscArgs& a, unsigned tid) {
   const unsigned nq = (unsigned)(a.width + 7) >> 3;
@@ -116,9 +126,11 @@ __device__ __forceinline__ void csc_unit(const CscArgs& a, unsigned tid) {
   const int n = min(8, a.width - x0);
   const int shiftH = (a.chroma_format == 1 || a.chroma_format == 2) ? 1 : 0;
   const int shiftV = a.chroma_format == 1 ? 1 : 0;
-  const int bpp = a.p.bit_depth;
   const int fmt = a.p.out_format;
-  const int half = 1 << (bpp - 1);
+  const int ind = a.p.in_depth, outd = a.p.out_depth, pre = a.p.pre_op, post = a.p.post_op;
+  // the neutral chroma value of the planes as stored: padding lanes, and the planes Op_mono_to_YCbCr420 adds to a
+  // monochrome image (monochrome.cc:99-100,128)
+  const int half_in = 128 << (ind - 8);
 
   int Y[8], Cb[8], Cr[8], A[8];
   load_px8<Pixel>(reinterpret_cast<const Pixel*>(a.y) + (size_t)y * a.y_stride + x0, n, Y);
@@ -128,23 +140,31 @@ __device__ __forceinline__ void csc_unit(const CscArgs& a, unsigned tid) {
     const int nc = shiftH ? (n + 1) >> 1 : n;
     if (shiftH) {
       // 4 (or fewer) chroma samples cover the 8 pixels: nearest neighbour, cx = x >> 1 (yuv2rgb.cc:173-174)
-      load_px4<Pixel>(reinterpret_cast<const Pixel*>(a.cb) + coff, nc, half, cb);
-      load_px4<Pixel>(reinterpret_cast<const Pixel*>(a.cr) + coff, nc, half, cr);
+      load_px4<Pixel>(reinterpret_cast<const Pixel*>(a.cb) + coff, nc, half_in, cb);
+      load_px4<Pixel>(reinterpret_cast<const Pixel*>(a.cr) + coff, nc, half_in, cr);
 #pragma unroll
       for (int k = 0; k < 8; k++) { Cb[k] = cb[k >> 1]; Cr[k] = cr[k >> 1]; }
     } else {
       load_px8<Pixel>(reinterpret_cast<const Pixel*>(a.cb) + coff, n, Cb);
       load_px8<Pixel>(reinterpret_cast<const Pixel*>(a.cr) + coff, n, Cr);
     }
+  } else {
+#pragma unroll
+    for (int k = 0; k < 8; k++) Cb[k] = Cr[k] = half_in;
   }
   if (a.a) load_px8<Pixel>(reinterpret_cast<const Pixel*>(a.a) + (size_t)y * a.a_stride + x0, n, A);
-  else {
+  if (pre != HC_DEPTH_NONE) {   // warp-uniform
 #pragma unroll
-    for (int k = 0; k < 8; k++) A[k] = (1 << bpp) - 1;
+    for (int k = 0; k < 8; k++) {
+      Y[k] = depth_op(pre, Y[k], ind, outd);
+      Cb[k] = depth_op(pre, Cb[k], ind, outd);
+      Cr[k] = depth_op(pre, Cr[k], ind, outd);
+      A[k] = depth_op(pre, A[k], ind, outd);
+    }
   }
 
   int R[8], G[8], B[8];
-  if (!a.chroma_format) {
+  if (a.p.mode == HC_CSC_MONO) {
 #pragma unroll
     for (int k = 0; k < 8; k++) R[k] = G[k] = B[k] = Y[k];
   } else if (a.p.mode == HC_CSC_INT420) {
@@ -159,6 +179,19 @@ __device__ __forceinline__ void csc_unit(const CscArgs& a, unsigned tid) {
   } else {
 #pragma unroll
     for (int k = 0; k < 8; k++) convert_px<Pixel, HC_CSC_YCGCO>(a, Y[k], Cb[k], Cr[k], R[k], G[k], B[k]);
+  }
+  if (post != HC_DEPTH_NONE) {   // warp-uniform; the matrix ran at the input depth
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      R[k] = depth_op(post, R[k], ind, outd);
+      G[k] = depth_op(post, G[k], ind, outd);
+      B[k] = depth_op(post, B[k], ind, outd);
+      A[k] = depth_op(post, A[k], ind, outd);
+    }
+  }
+  if (!a.a) {   // a missing alpha plane is opaque at the final depth (yuv2rgb.cc:470, rgb2rgb.cc:251,264)
+#pragma unroll
+    for (int k = 0; k < 8; k++) A[k] = (1 << outd) - 1;
   }
 
   uint8_t* orow = a.out + (size_t)y * a.out_stride;
@@ -289,6 +322,7 @@ __global__ void __launch_bounds__(256) k5_int420_rgb24_kernel(CscBatch b) {
 
 static bool k5_fast_path(const CscArgs& a, bool sixteen_bit) {
   return !sixteen_bit && a.chroma_format == 1 && a.p.mode == HC_CSC_INT420 && a.p.out_format == HC_OUT_RGB && a.a == nullptr &&
+         a.p.pre_op == HC_DEPTH_NONE && a.p.post_op == HC_DEPTH_NONE &&
          (a.width & 7) == 0 && (a.height & 1) == 0 && (a.y_stride & 7) == 0 && (a.c_stride & 3) == 0 &&
          (reinterpret_cast<uintptr_t>(a.y) & 7) == 0 && (reinterpret_cast<uintptr_t>(a.cb) & 3) == 0 && (reinterpret_cast<uintptr_t>(a.cr) & 3) == 0 &&
          (a.out_stride & 7) == 0 && (reinterpret_cast<uintptr_t>(a.out) & 7) == 0;

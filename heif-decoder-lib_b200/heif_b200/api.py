@@ -265,6 +265,12 @@ def _place_image(hf, batch, item_id):
     Mirrors HeifContext::decode_image_planar / decode_full_grid_image (context.cc:1729-2404).
     Returns (canvas, effective nclx tuple (matrix, primaries, full_range), has_alpha, bit_depth, chroma_format)."""
     info = hf.image_info(item_id)
+    # this stage-level helper places pictures only; the native job (hc_heic_job, HeicJob) is what applies irot / imir /
+    # clap and rescales an alpha image of another size — refuse rather than return an untransformed image
+    if info.n_transforms:
+        raise HeifCudaError("item %d carries transformations: decode it through HeicJob" % item_id)
+    if info.alpha_id and hf.image_info(info.alpha_id).n_transforms:
+        raise HeifCudaError("the alpha image of item %d carries transformations: decode it through HeicJob" % item_id)
     recs, tiles = [], []
     if info.is_grid:
         ids = hf.grid_tiles(item_id)
@@ -293,14 +299,28 @@ def _place_image(hf, batch, item_id):
         cf, bd = p.chroma_format, p.bit_depth_y
     if info.alpha_id:
         a = parse_picture(hf.coded_stream(info.alpha_id))
+        cw, ch = (info.width, info.height) if info.is_grid else (recs[0].pic.crop_w if recs else p.crop_w, recs[0].pic.crop_h if recs else p.crop_h)
+        if (a.pic.crop_w, a.pic.crop_h) != (cw, ch):
+            raise HeifCudaError("the alpha image of item %d has another size: decode it through HeicJob" % item_id)
         batch.add_picture(a, canvas, 0, 0, ROLE_ALPHA)
     return canvas, nclx, bool(info.alpha_id), bd, cf
 
 
 def decode_heic(engine, data, out_format=OUT_RGB, item_id=None):
     """HEIC file bytes -> interleaved RGB rows (numpy uint8 [h, w*bytes_per_pixel]), the Python
-    twin of heif_decode_image(handle, &img, heif_colorspace_RGB, heif_chroma_interleaved_*, NULL)."""
+    twin of heif_decode_image(handle, &img, heif_colorspace_RGB, heif_chroma_interleaved_*, NULL).
+    The primary image goes through the native job (hc_heic_job: transformations, alpha of any size, every output format);
+    another item of the file (item_id) through the stage-level calls, which refuse what they do not apply."""
     hf = HeifFile(data)
+    if item_id is None or item_id == hf.primary_id:
+        hf.close()
+        job = HeicJob(engine, [data], out_format=out_format)
+        try:
+            job.upload()
+            job.run()
+            return job.read_rgb(0)
+        finally:
+            job.close()
     batch = engine.batch()
     try:
         canvas, (matrix, primaries, full_range), has_alpha, bd, cf = _place_image(hf, batch, item_id or hf.primary_id)
@@ -318,8 +338,11 @@ class HeicJob:
     """Many HEIC files -> interleaved RGB through the native batch path (hc_heic_job): host threads
     parse every coded item, the GPU reconstructs all of them as one batch."""
 
-    def __init__(self, engine, files, want_alpha=False, threads=0):
+    def __init__(self, engine, files, want_alpha=False, threads=0, out_format=None):
+        """out_format: one of OUT_* for every image whatever its bit depth (HC_OUTPUT_FORMAT), default by bit depth"""
         from ._lib import ImageDesc
+        if out_format is not None:
+            want_alpha = 0x100 | int(out_format)
         self._L, self._eng = engine._L, engine
         self._bufs = [C.create_string_buffer(f, len(f)) for f in files]
         n = len(files)
@@ -396,12 +419,14 @@ class HeicJob:
         self.close()
 
 
-def decode_stream(engine, files, on_image=None, want_alpha=False, threads=0, files_per_batch=8):
+def decode_stream(engine, files, on_image=None, want_alpha=False, threads=0, files_per_batch=8, out_format=None):
     """Long file lists (hc_heic_decode_stream): host parse of batch b+1 overlaps upload + kernels + read-back of
     batch b. on_image(file_index, desc, rows) gets every image as a numpy view [h, w*bytes_per_pixel] of PINNED
     host memory that is only valid inside the callback. Returns the hc_stream_stats as a dict."""
     from ._lib import IMAGE_CALLBACK, StreamStats
     L = engine._L
+    if out_format is not None:
+        want_alpha = 0x100 | int(out_format)    # HC_OUTPUT_FORMAT
     bufs = {}
     ptr_list = []
     for f in files:                         # identical bytes objects share one buffer

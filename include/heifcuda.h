@@ -152,22 +152,37 @@ void hc_free(void* p);
 #define HC_CSC_FLOAT 1  /* Op_YCbCr_to_RGB<> / Op_YCbCr420_to_RRGGBBaa: fp32     yuv2rgb.cc:28-254,498-643 */
 #define HC_CSC_GBR 2    /* matrix_coefficients == 0                               yuv2rgb.cc:197-211 */
 #define HC_CSC_YCGCO 3  /* matrix_coefficients == 8                               yuv2rgb.cc:212-226 */
+#define HC_CSC_MONO 4   /* Op_mono_to_RGB24_32: R = G = B = Y                     monochrome.cc:150-260 */
+
+/* bit-depth changing plane ops of the reference (hdr_sdr.cc:24-236), fused into K5 */
+#define HC_DEPTH_NONE 0
+#define HC_DEPTH_TO_SDR 1 /* Op_to_sdr_planes: v >> (depth - 8), no rounding                              */
+#define HC_DEPTH_TO_HDR 2 /* Op_to_hdr_planes: (v << (t - 8)) | (v >> (16 - t)), 8 bit -> t bit           */
 
 typedef struct hc_csc_params {
   int32_t mode;          /* HC_CSC_*                                                             */
   int32_t out_format;    /* HC_OUT_*                                                             */
   int32_t full_range;
-  int32_t bit_depth;
+  int32_t bit_depth;     /* depth the conversion arithmetic runs at (after pre_op)               */
   int32_t r_cr_i, g_cb_i, g_cr_i, b_cb_i; /* lround(256*coefficient), INT420 mode                */
   float r_cr, g_cb, g_cr, b_cb;           /* nclx.cc:151-171                                     */
+  int32_t in_depth;      /* sample depth of the decoded planes                                   */
+  int32_t out_depth;     /* depth of the written channels: 8 for RGB / RGBA, else the input depth (10 for 8-bit input) */
+  int32_t pre_op;        /* HC_DEPTH_* applied to Y, Cb, Cr, A as they are loaded                */
+  int32_t post_op;       /* HC_DEPTH_* applied to R, G, B, A before they are written             */
+  int32_t coeff_matrix;  /* matrix_coefficients the coefficients were derived from: an unspecified matrix (2) stays 2 —
+                            the literal BT.601 defaults — when the matrix op is the first op of the reference's chain and
+                            becomes 6 behind any other op (see csc_select.cc)                     */
 } hc_csc_params;
 
 /* Chooses the conversion the reference's pipeline would run with default decoding options
  * (colorconversion.cc:266-420, table in SURVEY.md 3.5) and fills the coefficients exactly as
  * nclx.cc:82-171 computes them. `matrix`/`primaries`/`full_range` are the image's nclx values
- * (pass matrix=2 for "unspecified": replaced by BT.601 like nclx.cc:346-359). Returns
- * HC_ERR_UNSUPPORTED for combinations the reference cannot convert either (matrix 11/14) or that
- * depend on colour-primaries tables not implemented here (matrix 12/13). */
+ * (pass matrix=2 for "unspecified": replaced by BT.601 like nclx.cc:346-359); matrix 12 / 13 derive Kr / Kb from the
+ * chromaticities of `primaries` (nclx.cc:88-110). Every output format is available for every bit depth: the reference
+ * inserts Op_to_sdr_planes / Op_to_hdr_planes (hdr_sdr.cc) before or after the matrix depending on the input — the chain
+ * it picks (tools/csc_pipeline_probe.cc asks the unmodified reference; table in DESIGN.md) is encoded in pre_op / post_op.
+ * Returns HC_ERR_UNSUPPORTED for combinations the reference cannot convert either (matrix 11/14). */
 int hc_csc_select(int matrix, int primaries, int full_range, int chroma_format, int bit_depth,
                   int has_alpha, int out_format, hc_csc_params* out);
 
@@ -282,14 +297,19 @@ typedef struct hc_image_desc {
   int32_t chroma_format;     /* of the decoded YCbCr image                                        */
   int32_t bit_depth;
   int32_t has_alpha;
-  int32_t out_format;        /* HC_OUT_* chosen for this image (8-bit -> RGB/RGBA, else RRGGBB(AA)) */
+  int32_t out_format;        /* HC_OUT_* of this image (automatic: 8-bit -> RGB/RGBA, else RRGGBB(AA)_LE) */
   int32_t bytes_per_pixel;
   int32_t coded_pictures;    /* HEVC pictures decoded for this image (tiles + alpha)              */
 } hc_image_desc;
 
 /* Parses `nfiles` HEIC files held in host memory (the primary image of each) with `threads` host
  * threads (<=0: hardware concurrency). The buffers must stay valid until hc_heic_job_destroy.
- * want_alpha: 0 -> interleaved RGB / RRGGBB_LE, 1 -> RGBA / RRGGBBAA_LE. */
+ * want_alpha: 0 -> interleaved RGB / RRGGBB_LE, 1 -> RGBA / RRGGBBAA_LE (8-bit images / deeper images), or
+ * HC_OUTPUT_FORMAT(HC_OUT_*) -> that format for every image whatever its bit depth, like the `chroma` argument of
+ * heif_decode_image (heif.cc:1150): a 10-bit image to interleaved RGB goes through the reference's Op_to_sdr_planes, an
+ * 8-bit image to RRGGBB through Op_to_hdr_planes (10 bit), both fused into K5. The same encoding is accepted by
+ * hc_heic_job_create_band and hc_heic_decode_stream. */
+#define HC_OUTPUT_FORMAT(fmt) (0x100 | (fmt))
 hc_heic_job* hc_heic_job_create(hc_engine* e, int nfiles, const uint8_t* const* data, const size_t* sizes,
                                 int want_alpha, int threads);
 /* Multi-GPU decode of ONE huge grid image (BASELINE config C5): every GPU decodes a band of tile rows

@@ -12,6 +12,8 @@
  *   color-conversion/yuv2rgb.cc:28-254    Op_YCbCr_to_RGB<Pixel> (fp32)
  *   color-conversion/yuv2rgb.cc:498-643   Op_YCbCr420_to_RRGGBBaa (fp32)
  *   color-conversion/rgb2rgb.cc:28-272,613-729  interleave / endianness ops
+ *   color-conversion/hdr_sdr.cc:24-236    Op_to_hdr_planes / Op_to_sdr_planes (bit-depth changes)
+ *   color-conversion/monochrome.cc:53-140  Op_mono_to_YCbCr420
  *   common_utils.h:56-79           clip helpers
  * Compile with -ffp-contract=off: every float product and sum is rounded separately, as in the
  * reference's SSE2 build.
@@ -30,15 +32,42 @@ static uint8_t clip_int_u8(int x) { return x < 0 ? 0 : (x > 255 ? 255 : (uint8_t
 
 typedef struct { float r_cr, g_cb, g_cr, b_cb; } coeffs_t;
 
-static coeffs_t get_coeffs(int matrix) { /* nclx.cc:82-171 */
+/* nclx.cc:46-75 get_colour_primaries: {green x,y, blue x,y, red x,y, white x,y}; zeros when undefined */
+static int get_primaries(int idx, float p[8]) {
+  static const float tab[][9] = {
+      {1, 0.300f, 0.600f, 0.150f, 0.060f, 0.640f, 0.330f, 0.3127f, 0.3290f}, {4, 0.21f, 0.71f, 0.14f, 0.08f, 0.67f, 0.33f, 0.310f, 0.316f},
+      {5, 0.29f, 0.60f, 0.15f, 0.06f, 0.64f, 0.33f, 0.3127f, 0.3290f},       {6, 0.310f, 0.595f, 0.155f, 0.070f, 0.630f, 0.340f, 0.3127f, 0.3290f},
+      {7, 0.310f, 0.595f, 0.155f, 0.070f, 0.630f, 0.340f, 0.3127f, 0.3290f}, {8, 0.243f, 0.692f, 0.145f, 0.049f, 0.681f, 0.319f, 0.310f, 0.316f},
+      {9, 0.170f, 0.797f, 0.131f, 0.046f, 0.708f, 0.292f, 0.3127f, 0.3290f}, {10, 0.0f, 1.0f, 0.0f, 0.0f, 1.0f, 0.0f, 0.333333f, 0.33333f},
+      {11, 0.265f, 0.690f, 0.150f, 0.060f, 0.680f, 0.320f, 0.314f, 0.351f},  {12, 0.265f, 0.690f, 0.150f, 0.060f, 0.680f, 0.320f, 0.3127f, 0.3290f},
+      {22, 0.295f, 0.605f, 0.155f, 0.077f, 0.630f, 0.340f, 0.3127f, 0.3290f}};
+  for (size_t i = 0; i < sizeof(tab) / sizeof(tab[0]); i++)
+    if ((int)tab[i][0] == idx) { for (int k = 0; k < 8; k++) p[k] = tab[i][1 + k]; return 1; }
+  for (int k = 0; k < 8; k++) p[k] = 0.f;
+  return 0;
+}
+
+static coeffs_t get_coeffs(int matrix, int primaries) { /* nclx.cc:82-171 */
   float Kr = 0.f, Kb = 0.f;
-  switch (matrix) {
-    case 1: Kr = 0.2126f; Kb = 0.0722f; break;
-    case 4: Kr = 0.30f; Kb = 0.11f; break;
-    case 5: case 6: Kr = 0.299f; Kb = 0.114f; break;
-    case 7: Kr = 0.212f; Kb = 0.087f; break;
-    case 9: case 10: Kr = 0.2627f; Kb = 0.0593f; break;
-    default: break;
+  if (matrix == 12 || matrix == 13) { /* nclx.cc:88-110: Kr / Kb from the chromaticities of the colour primaries */
+    float p[8];
+    get_primaries(primaries, p);
+    const float gx = p[0], gy = p[1], bx = p[2], by = p[3], rx = p[4], ry = p[5], wx = p[6], wy = p[7];
+    const float zr = 1 - (rx + ry), zg = 1 - (gx + gy), zb = 1 - (bx + by), zw = 1 - (wx + wy);
+    const float denom = wy * (rx * (gy * zb - by * zg) + gx * (by * zr - ry * zb) + bx * (ry * zg - gy * zr));
+    if (denom != 0.0f) {
+      Kr = (ry * (wx * (gy * zb - by * zg) + wy * (bx * zg - gx * zb) + zw * (gx * by - bx * gy))) / denom;
+      Kb = (by * (wx * (ry * zg - gy * zr) + wy * (gx * zr - rx * zg) + zw * (rx * gy - gx * ry))) / denom;
+    }
+  } else {
+    switch (matrix) {
+      case 1: Kr = 0.2126f; Kb = 0.0722f; break;
+      case 4: Kr = 0.30f; Kb = 0.11f; break;
+      case 5: case 6: Kr = 0.299f; Kb = 0.114f; break;
+      case 7: Kr = 0.212f; Kb = 0.087f; break;
+      case 9: case 10: Kr = 0.2627f; Kb = 0.0593f; break;
+      default: break;
+    }
   }
   coeffs_t c;
   if (Kb != 0 || Kr != 0) {
@@ -52,42 +81,100 @@ static coeffs_t get_coeffs(int matrix) { /* nclx.cc:82-171 */
   return c;
 }
 
+/* hdr_sdr.cc:54-97 Op_to_hdr_planes (8 -> out_bits) and :140-236 Op_to_sdr_planes (in_bits -> 8, no rounding) */
+static int to_hdr(int v, int out_bits) { return ((v << (out_bits - 8)) | (v >> (16 - out_bits))) & 0xffff; }
+static int to_sdr(int v, int in_bits) { return (v >> (in_bits - 8)) & 0xff; }
+
 /* out_format: 0 RGB, 1 RGBA, 2 RRGGBB_BE, 3 RRGGBBAA_BE, 4 RRGGBB_LE, 5 RRGGBBAA_LE.
  * Planes are uint16 arrays (any bit depth), strides in samples. `a` may be NULL.
- * Returns 0, or -1 for combinations the reference cannot convert. */
+ * Returns 0, or -1 for combinations the reference cannot convert.
+ *
+ * Which ops run, for the default decoding options, was read off the unmodified reference with
+ * tools/csc_pipeline_probe.cc (ColorConversionPipeline::construct_pipeline + debug_dump_pipeline; table in DESIGN.md):
+ *   target interleaved RGB / RGBA (8 bit, colorconversion.cc:571-587):
+ *     4:2:0 full range (matrix not 0 / 8):  [Op_to_sdr_planes on Y Cb Cr A]  Op_YCbCr420_to_RGB24 / _RGB32     (integer)
+ *     monochrome:                           [Op_to_sdr_planes]               Op_mono_to_RGB24_32               (copy)
+ *     everything else:      Op_YCbCr_to_RGB<> at the input depth (fp32)  [Op_to_sdr_planes on R G B A]  Op_RGB_to_RGB24_32
+ *   target RRGGBB(AA) (input depth, or 10 bit for 8-bit input):
+ *     4:2:0 or monochrome (Op_mono_to_YCbCr420: Cb = Cr = 128 << (bpp - 8)), matrix not 0 / 8, and the output has alpha
+ *     only if the input has:                [Op_to_hdr_planes on Y Cb Cr A]  Op_YCbCr420_to_RRGGBBaa           (fp32)
+ *     everything else:      Op_YCbCr_to_RGB<> at the input depth  [Op_to_hdr_planes on R G B A]  Op_RGB_HDR_to_RRGGBBaa_BE
+ *                           [Op_RRGGBBaa_swap_endianness]; a missing alpha plane is filled with the maximum of the final depth */
 int hc_oracle_csc(const uint16_t* y, const uint16_t* cb, const uint16_t* cr, const uint16_t* a, int y_stride,
                   int c_stride, int a_stride, int width, int height, int chroma_format, int bit_depth, int matrix,
-                  int full_range, int out_format, uint8_t* out, size_t out_stride) {
+                  int primaries, int full_range, int out_format, uint8_t* out, size_t out_stride) {
   /* matrix 2 (unspecified) reaches the ops unchanged: Kr = Kb = 0 -> the literal BT.601 defaults
    * (nclx.cc:140-149,159-169), NOT the values computed from Kr/Kb of matrix 6 */
-  if (matrix == 11 || matrix == 14 || matrix == 12 || matrix == 13) return -1;
+  if (matrix == 11 || matrix == 14) return -1;
+  /* Op_mono_to_YCbCr420 hands on a fresh colour state (monochrome.cc:36-45: nothing copies the nclx), so whatever follows
+   * it converts with the defaults of color_profile_nclx (nclx.h:165-168): full range, matrix unspecified */
+  const int image_matrix = matrix, image_full = full_range;
+  if (chroma_format == 0 && out_format > 1) { matrix = 2; full_range = 1; }
   const int to_alpha = out_format == 1 || out_format == 3 || out_format == 5;
+  const int out8 = out_format <= 1;
   const int has_alpha = a != NULL;
-  const coeffs_t k = get_coeffs(matrix);
+  const int in8 = bit_depth == 8;
+  const int special = matrix == 0 || matrix == 8;
+  const int cls420 = chroma_format == 0 || chroma_format == 1;       /* monochrome goes through Op_mono_to_YCbCr420 */
+  coeffs_t k = get_coeffs(matrix, primaries);
   const int shiftH = (chroma_format == 1 || chroma_format == 2) ? 1 : 0;
   const int shiftV = chroma_format == 1 ? 1 : 0;
-  const int maxv = (1 << bit_depth) - 1;
-  const int half = 1 << (bit_depth - 1);
-  /* the fixed-point ops win only for 8-bit 4:2:0 full-range input */
-  /* (also when an alpha plane is present but not wanted: the pipeline drops it and still takes the
-   * fixed-point op — checked against the reference with tests/golden/heic/alpha_420_8.heic) */
-  const int use_int = bit_depth == 8 && chroma_format == 1 && full_range && matrix != 0 && matrix != 8;
+
+  int pre = 0, post = 0;     /* 1: to_sdr, 2: to_hdr; pre on Y Cb Cr A, post on R G B A */
+  int op;                    /* 0 integer 4:2:0, 1 fp32 general, 2 monochrome copy */
+  const int target = out8 ? 8 : (in8 ? 10 : bit_depth);
+  if (out8) {
+    if (chroma_format == 0) { op = 2; pre = in8 ? 0 : 1; }
+    else if (chroma_format == 1 && full_range && !special) { op = 0; pre = in8 ? 0 : 1; }
+    else { op = 1; post = in8 ? 0 : 1; }
+  } else {
+    op = 1;
+    if (cls420 && !special && (!to_alpha || has_alpha)) pre = in8 ? 2 : 0;
+    else if (in8) {
+      /* equal-cost alternatives "matrix at 8 bit, then Op_to_hdr_planes" / "Op_to_hdr_planes, then matrix at 10 bit": the
+       * search's expansion order decides; read off the exhaustive table tests/golden/csc_pipelines.json */
+      const int hdr_first = (has_alpha && !to_alpha && (chroma_format == 3 || image_matrix == 0)) ||
+                            (chroma_format == 0 && !has_alpha && to_alpha && image_matrix == 0 && image_full);
+      if (hdr_first) pre = 2; else post = 2;
+    }
+  }
+  const int work = pre == 1 ? 8 : (pre == 2 ? target : bit_depth);   /* depth the conversion runs at */
+  const int maxv = (1 << work) - 1;
+  const int half = 1 << (work - 1);
+  /* An op reads the nclx of the image it is handed (yuv2rgb.cc:121-128,598-603). The FIRST op of a chain gets the decoded
+   * image with its own nclx — matrix 2 (unspecified) then means the literal BT.601 defaults (nclx.cc:140-149); every later
+   * op gets an image stamped with the pipeline's colour state (colorconversion.cc:454-455), in which unspecified values
+   * were replaced by matrix 6 / primaries 1 (colorconversion.cc:528, nclx.cc:346-359) — coefficients computed from Kr / Kb,
+   * which differ from the literals in the last ulp. The matrix op is not first behind Op_drop_alpha_plane or a plane op. */
+  if (chroma_format != 0 || out8) {
+    /* Op_RGB_to_RGB24_32 ignores an alpha plane it does not need: no Op_drop_alpha_plane in front of the general 8-bit path */
+    const int drops_alpha = has_alpha && !to_alpha && !(out8 && op == 1);
+    const int matrix_first = !drops_alpha && pre == 0;
+    if (!matrix_first) {
+      const coeffs_t k2 = get_coeffs(matrix == 2 ? 6 : matrix, primaries == 2 ? 1 : primaries);
+      k = k2;
+    }
+  }
   const int r_cr = (int)lround(256 * k.r_cr), g_cr = (int)lround(256 * k.g_cr);
   const int g_cb = (int)lround(256 * k.g_cb), b_cb = (int)lround(256 * k.b_cb);
-  const float lro = (float)(16 << (bit_depth - 8));
+  const float lro = (float)(16 << (work - 8));
+#define PRE(v) (pre == 1 ? to_sdr((v), bit_depth) : (pre == 2 ? to_hdr((v), target) : (v)))
+#define POST(v) (post == 1 ? to_sdr((v), work) : (post == 2 ? to_hdr((v), target) : (v)))
 
   for (int yy = 0; yy < height; yy++)
     for (int x = 0; x < width; x++) {
-      const int yv = y[(size_t)yy * y_stride + x];
-      int cbv = half, crv = half;
+      const int yv = PRE(y[(size_t)yy * y_stride + x]);
+      int cbv, crv;
       if (chroma_format) {
-        cbv = cb[(size_t)(yy >> shiftV) * c_stride + (x >> shiftH)];
-        crv = cr[(size_t)(yy >> shiftV) * c_stride + (x >> shiftH)];
+        cbv = PRE(cb[(size_t)(yy >> shiftV) * c_stride + (x >> shiftH)]);
+        crv = PRE(cr[(size_t)(yy >> shiftV) * c_stride + (x >> shiftH)]);
+      } else {
+        cbv = crv = PRE(128 << (bit_depth - 8));      /* monochrome.cc:99-100,128: the planes Op_mono_to_YCbCr420 adds */
       }
       int R, G, B;
-      if (!chroma_format) {
+      if (op == 2) {
         R = G = B = yv;
-      } else if (use_int) { /* yuv2rgb.cc:349-361 */
+      } else if (op == 0) { /* yuv2rgb.cc:349-361 */
         const int cbi = cbv - 128, cri = crv - 128;
         R = clip_int_u8(yv + ((r_cr * cri + 128) >> 8));
         G = clip_int_u8(yv + ((g_cb * cbi + g_cr * cri + 128) >> 8));
@@ -115,7 +202,12 @@ int hc_oracle_csc(const uint16_t* y, const uint16_t* cb, const uint16_t* cr, con
         G = clip_f_u16(fy + k.g_cb * fcb + k.g_cr * fcr, maxv);
         B = clip_f_u16(fy + k.b_cb * fcb, maxv);
       }
-      const int A = has_alpha ? a[(size_t)yy * a_stride + x] : maxv;
+      R = POST(R); G = POST(G); B = POST(B);
+      /* alpha rides through the same plane ops; a missing plane is filled at the final depth (rgb2rgb.cc:251,264; 0xFF in
+       * the 8-bit interleavers) */
+      int A;
+      if (has_alpha) { A = PRE(a[(size_t)yy * a_stride + x]); A = POST(A); }
+      else A = (1 << target) - 1;
       uint8_t* o = out + (size_t)yy * out_stride;
       if (out_format == 0) {
         o[3 * x + 0] = (uint8_t)R; o[3 * x + 1] = (uint8_t)G; o[3 * x + 2] = (uint8_t)B;
@@ -130,5 +222,7 @@ int hc_oracle_csc(const uint16_t* y, const uint16_t* cb, const uint16_t* cr, con
         }
       }
     }
+#undef PRE
+#undef POST
   return 0;
 }

@@ -83,7 +83,32 @@ def build():
                                                         alpha_chroma_format=1, alpha_size=(264, 200), transforms=(W.irot(1),))
     files["alpha_unrotated_420_8"] = W.single_image(enc(200, 120, 1, 8, 66), 200, 120, 1, 8, alpha_stream=enc(200, 120, 0, 8, 67),
                                                     transforms=(W.irot(1),), alpha_transforms=())
+    # bit-depth changing conversions and chromaticity-derived matrices: monochrome deeper than
+    # 8 bit (Op_mono_to_YCbCr420 + range handling), 4:4:4 12 bit limited, 4:2:2 10 bit full, matrix_coefficients 12 with
+    # BT.2020 / BT.709 primaries
+    files["single_mono_10_novui"] = heif_writer.single_image(enc(200, 120, 0, 10, 70, vui=0), 200, 120, 0, 10)
+    files["single_mono_12_full"] = heif_writer.single_image(enc(200, 120, 0, 12, 71), 200, 120, 0, 12)
+    files["single_444_12_limited"] = heif_writer.single_image(enc(200, 120, 3, 12, 72, full_range=0, matrix=1), 200, 120, 3, 12)
+    files["single_422_10_full"] = heif_writer.single_image(enc(200, 120, 2, 10, 73), 200, 120, 2, 10)
+    files["single_420_8_matrix12_bt2020"] = heif_writer.single_image(enc(200, 120, 1, 8, 74, matrix=12, primaries=9), 200, 120, 1, 8)
+    files["single_444_10_matrix13_bt709"] = heif_writer.single_image(enc(200, 120, 3, 10, 75, matrix=13, primaries=1, full_range=0), 200, 120, 3, 10)
+    files["single_420_8_gbr"] = heif_writer.single_image(enc(200, 120, 1, 8, 76, matrix=0), 200, 120, 1, 8)
     return files
+
+
+ALL_FORMATS = {"rgb": R.CHROMA_RGB, "rgba": R.CHROMA_RGBA, "rrggbb_be": R.CHROMA_RRGGBB_BE, "rrggbbaa_be": R.CHROMA_RRGGBBAA_BE,
+               "rrggbb_le": R.CHROMA_RRGGBB_LE, "rrggbbaa_le": R.CHROMA_RRGGBBAA_LE}
+
+
+def reference_all_formats(data):
+    """heif_decode_image(..., heif_colorspace_RGB, chroma) of the unmodified reference for every interleaved chroma"""
+    out = {}
+    for name, chroma in ALL_FORMATS.items():
+        try:
+            out[name + "_md5"] = md5(R.decode(data, R.COLORSPACE_RGB, chroma)["interleaved"][0])
+        except RuntimeError as e:
+            out[name + "_error"] = str(e)
+    return out
 
 
 def reference_outputs(data):
@@ -115,6 +140,11 @@ def main():
         meta[name]["bytes"] = len(data)
         print(name, meta[name])
     json.dump(meta, open(os.path.join(HERE, "heic.json"), "w"), indent=1, sort_keys=True)
+    # every fixture (read back from the committed files) x every interleaved output format, bit-depth changing ones included
+    fmts = {}
+    for name in sorted(meta):
+        fmts[name] = reference_all_formats(open(os.path.join(OUT, name + ".heic"), "rb").read())
+    json.dump(fmts, open(os.path.join(HERE, "heic_formats.json"), "w"), indent=1, sort_keys=True)
 
 
 if __name__ == "__main__":

@@ -11,7 +11,7 @@ import oracle_lib
 OUT_BPP = {0: 3, 1: 4, 2: 6, 3: 8, 4: 6, 5: 8}
 
 
-def csc(planes, chroma_format, bit_depth, matrix, full_range, out_format, alpha=None):
+def csc(planes, chroma_format, bit_depth, matrix, full_range, out_format, alpha=None, primaries=2):
     O = oracle_lib.lib()
     h, w = planes[0].shape
     out = np.zeros((h, w * OUT_BPP[out_format]), np.uint8)
@@ -20,7 +20,7 @@ def csc(planes, chroma_format, bit_depth, matrix, full_range, out_format, alpha=
     rc = O.hc_oracle_csc(C.c_void_p(pl[0].ctypes.data), C.c_void_p(pl[1].ctypes.data if len(pl) > 1 else None),
                          C.c_void_p(pl[2].ctypes.data if len(pl) > 2 else None), C.c_void_p(a.ctypes.data if a is not None else None),
                          pl[0].shape[1], pl[1].shape[1] if len(pl) > 1 else 0, a.shape[1] if a is not None else 0,
-                         w, h, chroma_format, bit_depth, matrix, int(full_range), out_format,
+                         w, h, chroma_format, bit_depth, matrix, int(primaries), int(full_range), out_format,
                          C.c_void_p(out.ctypes.data), C.c_size_t(out.strides[0]))
     if rc != 0:
         raise RuntimeError("oracle csc cannot convert this combination")
@@ -36,7 +36,7 @@ def _rescale_limited(plane, chroma, bit_depth):
 
 
 def decode_planes(data, item_id=None):
-    """Returns (planes[list], alpha or None, chroma_format, bit_depth, (matrix, full_range))"""
+    """Returns (planes[list], alpha or None, chroma_format, bit_depth, (matrix, full_range, primaries))"""
     hf = hb.HeifFile(data, host_only=True)
     iid = item_id or hf.primary_id
     info = hf.image_info(iid)
@@ -64,13 +64,13 @@ def decode_planes(data, item_id=None):
                 xx, yy = (x0, y0) if k == 0 else ((x0 + sw - 1) // sw, (y0 + sh - 1) // sh)
                 hh, ww = min(p.shape[0], canvas[k].shape[0] - yy), min(p.shape[1], canvas[k].shape[1] - xx)
                 canvas[k][yy:yy + hh, xx:xx + ww] = p[:hh, :ww]
-        nclx = (info.matrix, info.full_range) if info.nclx_present else (2, 1)
+        nclx = (info.matrix, info.full_range, info.primaries) if info.nclx_present else (2, 1, 2)
         planes = canvas
     else:
         r = hb.parse_picture(hf.coded_stream(iid), host_only=True)
         planes, _ = oracle_lib.reconstruct(r)
         cf, bd = r.pic.chroma_format, r.pic.bit_depth_y
-        nclx = (info.matrix, info.full_range) if info.nclx_present else (r.pic.matrix_coeffs, r.pic.full_range)
+        nclx = (info.matrix, info.full_range, info.primaries) if info.nclx_present else (r.pic.matrix_coeffs, r.pic.full_range, r.pic.colour_primaries)
     alpha = None
     if info.alpha_id:
         a = hb.parse_picture(hf.coded_stream(info.alpha_id), host_only=True)
@@ -167,5 +167,5 @@ def _transform_all(planes, info):
 
 
 def decode_rgb(data, out_format, item_id=None):
-    planes, alpha, cf, bd, (matrix, full) = decode_planes(data, item_id)
-    return csc(planes, cf, bd, matrix, full, out_format, alpha)
+    planes, alpha, cf, bd, (matrix, full, primaries) = decode_planes(data, item_id)
+    return csc(planes, cf, bd, matrix, full, out_format, alpha, primaries)

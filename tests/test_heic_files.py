@@ -18,6 +18,10 @@ DIR = os.path.join(ROOT, "tests", "golden", "heic")
 META = json.load(open(os.path.join(ROOT, "tests", "golden", "heic.json")))
 NAMES = sorted(META)
 FORMATS = {"rgb": hb.OUT_RGB, "rgba": hb.OUT_RGBA, "rrggbb_le": hb.OUT_RRGGBB_LE, "rrggbbaa_le": hb.OUT_RRGGBBAA_LE}
+# every fixture x every interleaved chroma of heif_decode_image, the bit-depth changing ones included (10/12-bit images to
+# RGB(A) 8 through Op_to_sdr_planes, 8-bit images to RRGGBB(AA) through Op_to_hdr_planes) and both byte orders
+FMETA = json.load(open(os.path.join(ROOT, "tests", "golden", "heic_formats.json")))
+ALL_FORMATS = dict(FORMATS, rrggbb_be=hb.OUT_RRGGBB_BE, rrggbbaa_be=hb.OUT_RRGGBBAA_BE)
 
 
 def load(name):
@@ -38,6 +42,17 @@ def test_oracle_reproduces_reference(name):
     for key, fmt in FORMATS.items():
         if key + "_md5" in m:
             assert md5(heic_oracle.decode_rgb(load(name), fmt).tobytes()) == m[key + "_md5"], key
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_oracle_reproduces_reference_in_every_output_format(name):
+    data = load(name)
+    checked = 0
+    for key, fmt in ALL_FORMATS.items():
+        if key + "_md5" in FMETA[name]:
+            assert md5(heic_oracle.decode_rgb(data, fmt).tobytes()) == FMETA[name][key + "_md5"], key
+            checked += 1
+    assert checked >= 4, FMETA[name]
 
 
 def _iovl_file(chroma_format):
@@ -96,6 +111,21 @@ def test_gpu_heic_job_matches_reference(engine, want_alpha, device_parse):
         assert md5(b"".join(p.astype(dt).tobytes() for p in planes)) == m["planes_md5"], name
     assert job.launch_count >= 6
     job.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("key", sorted(ALL_FORMATS))
+def test_gpu_heic_job_every_output_format(engine, key):
+    """hc_heic_job with HC_OUTPUT_FORMAT: all fixtures to ONE interleaved format whatever their bit depth — K5 with the
+    reference's Op_to_sdr_planes / Op_to_hdr_planes fused before or after the matrix (csc_select.cc)."""
+    names = [n for n in NAMES if key + "_md5" in FMETA[n]]
+    assert len(names) >= 40
+    job = hb.HeicJob(engine, [load(n) for n in names], threads=4, out_format=ALL_FORMATS[key])
+    job.upload()
+    job.run()
+    bad = [n for i, n in enumerate(names) if md5(job.read_rgb(i).tobytes()) != FMETA[n][key + "_md5"]]
+    job.close()
+    assert not bad, (key, bad)
 
 
 @pytest.mark.gpu

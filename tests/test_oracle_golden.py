@@ -37,7 +37,7 @@ def oracle_csc(planes, pic, matrix, full_range, out_format, alpha=None):
     rc = O.hc_oracle_csc(C.c_void_p(pl[0].ctypes.data), C.c_void_p(pl[1].ctypes.data if len(pl) > 1 else None),
                          C.c_void_p(pl[2].ctypes.data if len(pl) > 2 else None), C.c_void_p(a.ctypes.data if a is not None else None),
                          pl[0].shape[1], pl[1].shape[1] if len(pl) > 1 else 0, a.shape[1] if a is not None else 0,
-                         w, h, pic.chroma_format, pic.bit_depth_y, matrix, int(full_range), out_format,
+                         w, h, pic.chroma_format, pic.bit_depth_y, matrix, int(pic.colour_primaries), int(full_range), out_format,
                          C.c_void_p(out.ctypes.data), C.c_size_t(out.strides[0]))
     assert rc == 0
     return out
