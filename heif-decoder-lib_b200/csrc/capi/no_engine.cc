@@ -36,6 +36,16 @@ int hc_batch_timer_start(hc_batch*) { return NO_ENGINE(); }
 int hc_batch_timer_stop_ms(hc_batch*, float*) { return NO_ENGINE(); }
 int hc_batch_launch_count(const hc_batch*) { return 0; }
 size_t hc_batch_upload_bytes(const hc_batch*) { return 0; }
+int hc_batch_set_rgb_target(hc_batch*, int, void*, size_t) { return NO_ENGINE(); }
+hc_shared_image* hc_shared_image_create(hc_engine*, int, int, int) { NO_ENGINE(); return nullptr; }
+int hc_shared_image_export(const hc_shared_image*, uint8_t*) { return NO_ENGINE(); }
+hc_shared_image* hc_shared_image_open(hc_engine*, const uint8_t*, int, int, int) { NO_ENGINE(); return nullptr; }
+hc_shared_image* hc_shared_image_attach(hc_engine*, const hc_shared_image*) { NO_ENGINE(); return nullptr; }
+void hc_shared_image_destroy(hc_shared_image*) {}
+void* hc_shared_image_device_ptr(const hc_shared_image*) { return nullptr; }
+size_t hc_shared_image_stride(const hc_shared_image*) { return 0; }
+int hc_shared_image_read(hc_shared_image*, int, int, void*, size_t) { return NO_ENGINE(); }
+int hc_shared_image_geometry(const hc_shared_image*, int*, int*, int*) { return NO_ENGINE(); }
 void* hc_host_alloc(size_t) { NO_ENGINE(); return nullptr; }
 void hc_host_free(void*) {}
 }

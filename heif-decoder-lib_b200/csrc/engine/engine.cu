@@ -125,6 +125,10 @@ struct Canvas {
   int ow = 0, oh = 0;               // output image size
   size_t ooff[4] = {0, 0, 0, 0};
   int ostride[4] = {0, 0, 0, 0}, opw[4] = {0, 0, 0, 0}, oph[4] = {0, 0, 0, 0};
+  // K5 writes here instead of the batch's RGB buffer when set (hc_batch_set_rgb_target: a band of a shared image on this or
+  // on a peer GPU)
+  uint8_t* ext_rgb = nullptr;
+  size_t ext_stride = 0;
   // rgb output of the last convert
   size_t rgb_off = 0;
   size_t rgb_stride = 0;
@@ -1001,8 +1005,9 @@ int hc_batch_convert(hc_batch* b, int canvas, const hc_csc_params* params) {
   a.a = c.alpha ? P + c.ooff[3] : nullptr;
   a.y_stride = c.ostride[0]; a.c_stride = c.ostride[1]; a.a_stride = c.ostride[3];
   a.width = c.ow; a.height = c.oh; a.chroma_format = c.chroma;
-  a.out = (uint8_t*)b->d_rgb.p + c.rgb_off;
-  a.out_stride = (long long)c.rgb_stride;
+  a.out = c.ext_rgb ? c.ext_rgb : (uint8_t*)b->d_rgb.p + c.rgb_off;
+  a.out_stride = (long long)(c.ext_rgb ? c.ext_stride : c.rgb_stride);
+  if (c.ext_rgb && c.ext_stride < (size_t)((c.ow + 7) & ~7) * c.rgb_bpp) { hc::set_last_error("external RGB target: rows too short for this format"); return HC_ERR_ARGUMENT; }
   a.p = *params;
   cudaEvent_t e0 = b->eng->take_event(), e1 = b->eng->take_event();
   cudaEventRecord(e0, b->stream);
@@ -1030,6 +1035,7 @@ int hc_batch_convert_many(hc_batch* b, int n, const int* canvases, const hc_csc_
     if (params[i].in_depth != c.bit_depth) { hc::set_last_error("conversion parameters were selected for another bit depth"); return HC_ERR_ARGUMENT; }
     c.rgb_bpp = bpp_of[params[i].out_format];
     c.rgb_stride = align_up((size_t)((c.ow + 7) & ~7) * c.rgb_bpp, 256);
+    if (c.ext_rgb && c.ext_stride < (size_t)((c.ow + 7) & ~7) * c.rgb_bpp) { hc::set_last_error("external RGB target: rows too short for this format"); return HC_ERR_ARGUMENT; }
   }
   size_t total = 0;
   for (auto& cv : b->canvases) {
@@ -1059,8 +1065,8 @@ int hc_batch_convert_many(hc_batch* b, int n, const int* canvases, const hc_csc_
         a.a = c.alpha ? P + c.ooff[3] : nullptr;
         a.y_stride = c.ostride[0]; a.c_stride = c.ostride[1]; a.a_stride = c.ostride[3];
         a.width = c.ow; a.height = c.oh; a.chroma_format = c.chroma;
-        a.out = (uint8_t*)b->d_rgb.p + c.rgb_off;
-        a.out_stride = (long long)c.rgb_stride;
+        a.out = c.ext_rgb ? c.ext_rgb : (uint8_t*)b->d_rgb.p + c.rgb_off;
+        a.out_stride = (long long)(c.ext_rgb ? c.ext_stride : c.rgb_stride);
         a.p = params[i];
         c.converted = true;
       }
@@ -1142,6 +1148,7 @@ int hc_batch_read_rgb(hc_batch* b, int canvas, void* dst, size_t dst_stride) {
   if (!b || !dst || canvas < 0 || canvas >= (int)b->canvases.size()) { hc::set_last_error("hc_batch_read_rgb: bad argument"); return HC_ERR_ARGUMENT; }
   const Canvas& c = b->canvases[canvas];
   if (!c.converted) { hc::set_last_error("canvas was not converted"); return HC_ERR_ARGUMENT; }
+  if (c.ext_rgb) { hc::set_last_error("this image is written to an external RGB target (hc_batch_set_rgb_target): read it there"); return HC_ERR_ARGUMENT; }
   cudaEvent_t e0 = b->ev_d2h[0], e1 = b->ev_d2h[1];
   cudaEventRecord(e0, b->stream);
   cudaError_t e = cudaMemcpy2DAsync(dst, dst_stride, (const uint8_t*)b->d_rgb.p + c.rgb_off, c.rgb_stride, (size_t)c.ow * c.rgb_bpp, c.oh,
@@ -1157,8 +1164,10 @@ int hc_batch_copy_rgb_device(hc_batch* b, int canvas, void* dst, size_t dst_stri
   if (!b || !dst || canvas < 0 || canvas >= (int)b->canvases.size()) { hc::set_last_error("hc_batch_copy_rgb_device: bad argument"); return HC_ERR_ARGUMENT; }
   const Canvas& c = b->canvases[canvas];
   if (!c.converted) { hc::set_last_error("canvas was not converted"); return HC_ERR_ARGUMENT; }
+  if (c.ext_rgb) { hc::set_last_error("this image is written to an external RGB target (hc_batch_set_rgb_target)"); return HC_ERR_ARGUMENT; }
+  // cudaMemcpyDefault: `dst` may live on a peer device (unified addressing; a peer copy over NVLink then)
   cudaError_t e = cudaMemcpy2DAsync(dst, dst_stride, (const uint8_t*)b->d_rgb.p + c.rgb_off, c.rgb_stride, (size_t)c.ow * c.rgb_bpp, c.oh,
-                                    cudaMemcpyDeviceToDevice, b->stream);
+                                    cudaMemcpyDefault, b->stream);
   if (!cuda_ok(e, "cudaMemcpy2DAsync(D2D rgb)")) return HC_ERR_CUDA;
   return batch_sync_checked(b, "cudaStreamSynchronize");
 }
@@ -1170,6 +1179,18 @@ int hc_batch_read_rgb_async(hc_batch* b, int canvas, void* dst, size_t dst_strid
   cudaError_t e = cudaMemcpy2DAsync(dst, dst_stride, (const uint8_t*)b->d_rgb.p + c.rgb_off, c.rgb_stride, (size_t)c.ow * c.rgb_bpp, c.oh,
                                     cudaMemcpyDeviceToHost, b->stream);
   return cuda_ok(e, "cudaMemcpy2DAsync(D2H rgb)") ? HC_OK : HC_ERR_CUDA;
+}
+
+int hc_batch_set_rgb_target(hc_batch* b, int canvas, void* device_dst, size_t stride_bytes) {
+  if (!b || canvas < 0 || canvas >= (int)b->canvases.size() || (device_dst && ((reinterpret_cast<uintptr_t>(device_dst) | stride_bytes) & 15))) {
+    hc::set_last_error("hc_batch_set_rgb_target: bad argument (the target and its stride must be 16-byte aligned)");
+    return HC_ERR_ARGUMENT;
+  }
+  Canvas& c = b->canvases[canvas];
+  c.ext_rgb = (uint8_t*)device_dst;
+  c.ext_stride = device_dst ? stride_bytes : 0;
+  c.converted = false;
+  return HC_OK;
 }
 
 int hc_batch_read_residual(hc_batch* b, int pic, int16_t* dst, size_t count) {
@@ -1219,5 +1240,104 @@ int hc_batch_timer_stop_ms(hc_batch* b, float* ms) {
 int hc_batch_launch_count(const hc_batch* b) { return b ? b->launches : 0; }
 size_t hc_batch_upload_bytes(const hc_batch* b) { return b ? b->arena_bytes : 0; }
 int hc_batch_k0_pictures(const hc_batch* b) { return b ? b->nk0 : 0; }
+
+
+// ---- hc_shared_image: one RGB buffer on the owner GPU that the K5 kernels of other GPUs store into ----------------------
+struct hc_shared_image {
+  int device = 0;          // device the VIEW belongs to (the engine that created / opened / attached it)
+  int owner_device = 0;
+  void* ptr = nullptr;
+  size_t stride = 0;
+  int width = 0, height = 0, bpp = 0;
+  int kind = 0;            // 0 owner (cudaMalloc), 1 IPC mapping, 2 same-process peer view
+};
+
+static size_t shared_stride(int width, int bpp) { return align_up((size_t)((width + 7) & ~7) * bpp, 256); }
+
+hc_shared_image* hc_shared_image_create(hc_engine* e, int width, int height, int bytes_per_pixel) {
+  if (!e || width <= 0 || height <= 0 || bytes_per_pixel < 3 || bytes_per_pixel > 8) { hc::set_last_error("hc_shared_image_create: bad argument"); return nullptr; }
+  if (!cuda_ok(cudaSetDevice(e->device), "cudaSetDevice")) return nullptr;
+  hc_shared_image* s = new (std::nothrow) hc_shared_image;
+  if (!s) return nullptr;
+  s->device = s->owner_device = e->device;
+  s->width = width; s->height = height; s->bpp = bytes_per_pixel;
+  s->stride = shared_stride(width, bytes_per_pixel);
+  if (!cuda_ok(cudaMalloc(&s->ptr, s->stride * (size_t)height), "cudaMalloc(shared image)")) { delete s; return nullptr; }
+  return s;
+}
+
+int hc_shared_image_export(const hc_shared_image* s, uint8_t handle[HC_IPC_HANDLE_BYTES]) {
+  static_assert(sizeof(cudaIpcMemHandle_t) == HC_IPC_HANDLE_BYTES, "IPC handle size");
+  if (!s || !handle || s->kind != 0) { hc::set_last_error("hc_shared_image_export: only the owner exports"); return HC_ERR_ARGUMENT; }
+  if (!cuda_ok(cudaSetDevice(s->device), "cudaSetDevice")) return HC_ERR_CUDA;
+  cudaIpcMemHandle_t h;
+  if (!cuda_ok(cudaIpcGetMemHandle(&h, s->ptr), "cudaIpcGetMemHandle")) return HC_ERR_CUDA;
+  memcpy(handle, &h, sizeof(h));
+  return HC_OK;
+}
+
+hc_shared_image* hc_shared_image_open(hc_engine* e, const uint8_t handle[HC_IPC_HANDLE_BYTES], int width, int height, int bytes_per_pixel) {
+  if (!e || !handle || width <= 0 || height <= 0) { hc::set_last_error("hc_shared_image_open: bad argument"); return nullptr; }
+  if (!cuda_ok(cudaSetDevice(e->device), "cudaSetDevice")) return nullptr;
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, sizeof(h));
+  hc_shared_image* s = new (std::nothrow) hc_shared_image;
+  if (!s) return nullptr;
+  // the mapping is made in this device's context; stores through it travel over NVLink when the owner is a peer
+  if (!cuda_ok(cudaIpcOpenMemHandle(&s->ptr, h, cudaIpcMemLazyEnablePeerAccess), "cudaIpcOpenMemHandle")) { delete s; return nullptr; }
+  s->device = e->device; s->owner_device = -1; s->kind = 1;
+  s->width = width; s->height = height; s->bpp = bytes_per_pixel;
+  s->stride = shared_stride(width, bytes_per_pixel);
+  return s;
+}
+
+hc_shared_image* hc_shared_image_attach(hc_engine* e, const hc_shared_image* owner) {
+  if (!e || !owner || owner->kind != 0) { hc::set_last_error("hc_shared_image_attach: bad argument"); return nullptr; }
+  if (!cuda_ok(cudaSetDevice(e->device), "cudaSetDevice")) return nullptr;
+  if (e->device != owner->device) {
+    int can = 0;
+    cudaDeviceCanAccessPeer(&can, e->device, owner->device);
+    if (!can) { hc::set_last_error("no peer access between the two devices"); return nullptr; }
+    const cudaError_t r = cudaDeviceEnablePeerAccess(owner->device, 0);
+    if (r != cudaSuccess && r != cudaErrorPeerAccessAlreadyEnabled) { cuda_ok(r, "cudaDeviceEnablePeerAccess"); return nullptr; }
+    cudaGetLastError();   // clear "already enabled"
+  }
+  hc_shared_image* s = new (std::nothrow) hc_shared_image(*owner);
+  if (!s) return nullptr;
+  s->device = e->device;
+  s->kind = 2;
+  return s;
+}
+
+void hc_shared_image_destroy(hc_shared_image* s) {
+  if (!s) return;
+  cudaSetDevice(s->device);
+  if (s->kind == 0) cudaFree(s->ptr);
+  else if (s->kind == 1) cudaIpcCloseMemHandle(s->ptr);
+  delete s;
+}
+
+void* hc_shared_image_device_ptr(const hc_shared_image* s) { return s ? s->ptr : nullptr; }
+size_t hc_shared_image_stride(const hc_shared_image* s) { return s ? s->stride : 0; }
+
+int hc_shared_image_read(hc_shared_image* s, int first_row, int rows, void* dst, size_t dst_stride) {
+  if (!s || !dst || first_row < 0 || rows <= 0 || first_row + rows > s->height || dst_stride < (size_t)s->width * s->bpp) {
+    hc::set_last_error("hc_shared_image_read: bad argument");
+    return HC_ERR_ARGUMENT;
+  }
+  if (!cuda_ok(cudaSetDevice(s->device), "cudaSetDevice")) return HC_ERR_CUDA;
+  if (!cuda_ok(cudaDeviceSynchronize(), "cudaDeviceSynchronize")) return HC_ERR_CUDA;
+  return cuda_ok(cudaMemcpy2D(dst, dst_stride, (const uint8_t*)s->ptr + (size_t)first_row * s->stride, s->stride, (size_t)s->width * s->bpp, rows,
+                              cudaMemcpyDeviceToHost), "cudaMemcpy2D(shared image)") ? HC_OK : HC_ERR_CUDA;
+}
+
+// used by hc_heic_job_set_rgb_target (heic_job.cc)
+int hc_shared_image_geometry(const hc_shared_image* s, int* width, int* height, int* bpp) {
+  if (!s) return HC_ERR_ARGUMENT;
+  if (width) *width = s->width;
+  if (height) *height = s->height;
+  if (bpp) *bpp = s->bpp;
+  return HC_OK;
+}
 
 }  // extern "C"

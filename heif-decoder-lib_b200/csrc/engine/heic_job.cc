@@ -471,6 +471,20 @@ hc_heic_job* hc_heic_job_create_band(hc_engine* e, const uint8_t* data, size_t s
   return j;
 }
 
+extern "C" int hc_shared_image_geometry(const hc_shared_image* s, int* width, int* height, int* bpp);
+
+int hc_heic_job_set_rgb_target(hc_heic_job* j, int image, hc_shared_image* dst, int first_row) {
+  if (!j || image < 0 || image >= (int)j->images.size() || !dst || first_row < 0) { hc::set_last_error("hc_heic_job_set_rgb_target: bad argument"); return HC_ERR_ARGUMENT; }
+  const ImagePlan& im = j->images[image];
+  int w = 0, h = 0, bpp = 0;
+  hc_shared_image_geometry(dst, &w, &h, &bpp);
+  if (w != im.desc.width || bpp != im.desc.bytes_per_pixel || first_row + im.desc.height > h) {
+    hc::set_last_error("hc_heic_job_set_rgb_target: the image does not fit the shared image (width / pixel size / rows)");
+    return HC_ERR_ARGUMENT;
+  }
+  return hc_batch_set_rgb_target(j->batch, im.canvas, (uint8_t*)hc_shared_image_device_ptr(dst) + (size_t)first_row * hc_shared_image_stride(dst), hc_shared_image_stride(dst));
+}
+
 int hc_heic_job_copy_rgb_device(hc_heic_job* j, int image, void* device_dst, size_t dst_stride_bytes) {
   if (!j || image < 0 || image >= (int)j->images.size()) { hc::set_last_error("hc_heic_job_copy_rgb_device: bad argument"); return HC_ERR_ARGUMENT; }
   return hc_batch_copy_rgb_device(j->batch, j->images[image].canvas, device_dst, dst_stride_bytes);

@@ -476,7 +476,20 @@ std::string HevcIntraParser::Impl::start_picture(const SliceHeader& first) {
   slices.clear();
   slices.reserve(64);
   ctbs_done = 0;
+  // Per-picture CU / quantisation-group state. A parser object is reused for many pictures (reset(), one per host thread):
+  // CuQpDeltaVal and the chroma offsets are READ by every QP derivation but only WRITTEN when the stream codes them, so a
+  // picture without cu_qp_delta decoded after one that ended on a non-zero delta got every QP shifted (found by a
+  // single-item job after example.heic: the whole picture differed).
   currentQPY = 0;
+  lastQPYinPreviousQG = 0;
+  currentQG_x = currentQG_y = -1;
+  IsCuQpDeltaCoded = false;
+  CuQpDeltaVal = 0;
+  IsCuChromaQpOffsetCoded = false;
+  CuQpOffsetCb = CuQpOffsetCr = 0;
+  cu_transquant_bypass = false;
+  for (int i = 0; i < 4; i++) stat_coeff[i] = 0;
+  error.clear();
 
   rec.reset(new PictureRecords);
   hc_pic& p = rec->pic;

@@ -132,6 +132,16 @@ SYMBOLS = [
     ("hc_heic_job_create", _vp, [_vp, _i, C.POINTER(C.c_char_p), C.POINTER(_sz), _i, _i]),
     ("hc_heic_job_create_band", _vp, [_vp, C.c_char_p, _sz, _i, _i, _i, _i, C.POINTER(_i), C.POINTER(_i)]),
     ("hc_heic_job_copy_rgb_device", _i, [_vp, _i, _vp, _sz]),
+    ("hc_heic_job_set_rgb_target", _i, [_vp, _i, _vp, _i]),
+    ("hc_batch_set_rgb_target", _i, [_vp, _i, _vp, _sz]),
+    ("hc_shared_image_create", _vp, [_vp, _i, _i, _i]),
+    ("hc_shared_image_export", _i, [_vp, C.POINTER(C.c_uint8)]),
+    ("hc_shared_image_open", _vp, [_vp, C.POINTER(C.c_uint8), _i, _i, _i]),
+    ("hc_shared_image_attach", _vp, [_vp, _vp]),
+    ("hc_shared_image_destroy", None, [_vp]),
+    ("hc_shared_image_device_ptr", _vp, [_vp]),
+    ("hc_shared_image_stride", _sz, [_vp]),
+    ("hc_shared_image_read", _i, [_vp, _i, _i, _vp, _sz]),
     ("hc_heic_job_destroy", None, [_vp]),
     ("hc_heic_job_image_count", _i, [_vp]),
     ("hc_heic_job_image_desc", _i, [_vp, _i, C.POINTER(ImageDesc)]),

@@ -320,7 +320,34 @@ hc_heic_job* hc_heic_job_create(hc_engine* e, int nfiles, const uint8_t* const* 
  * data crosses GPUs before the stitch. */
 hc_heic_job* hc_heic_job_create_band(hc_engine* e, const uint8_t* data, size_t size, int want_alpha, int threads,
                                      int tile_row_begin, int tile_row_end, int* first_output_row, int* full_height);
-/* device-to-device copy of a converted image into caller-owned device memory (same device), synchronous */
+/* ---- one huge grid image on several GPUs (BASELINE config C5; reference: one process, std::async per tile,
+ * libheif/context.cc:2120-2404) ----
+ * The output lives in ONE device buffer on the owner GPU (hc_shared_image). Every GPU decodes a band of tile rows
+ * (hc_heic_job_create_band) and its K5 writes the band's RGB rows straight into the owner's buffer: ordinary stores on the
+ * owner, NVLink peer stores everywhere else (cudaDeviceEnablePeerAccess within one process, CUDA IPC between the
+ * processes of a one-process-per-GPU launch). No collective, no staging copy. */
+typedef struct hc_shared_image hc_shared_image;
+#define HC_IPC_HANDLE_BYTES 64
+/* owner: `height` rows of `width` pixels of `bytes_per_pixel` on the engine's device (rows padded for K5's 8-pixel units) */
+hc_shared_image* hc_shared_image_create(hc_engine* e, int width, int height, int bytes_per_pixel);
+/* another PROCESS: the owner exports 64 bytes, the peer opens them on its own engine's device */
+int hc_shared_image_export(const hc_shared_image* s, uint8_t handle[HC_IPC_HANDLE_BYTES]);
+hc_shared_image* hc_shared_image_open(hc_engine* e, const uint8_t handle[HC_IPC_HANDLE_BYTES], int width, int height, int bytes_per_pixel);
+/* another engine (device) of the SAME process: enables peer access from e's device to the owner's */
+hc_shared_image* hc_shared_image_attach(hc_engine* e, const hc_shared_image* owner);
+void hc_shared_image_destroy(hc_shared_image* s);
+void* hc_shared_image_device_ptr(const hc_shared_image* s);
+size_t hc_shared_image_stride(const hc_shared_image* s);
+/* owner: rows [first_row, first_row + rows) to host memory, synchronous (device-wide: call it after every writer's
+ * hc_heic_job_sync and whatever barrier orders the writers before the reader) */
+int hc_shared_image_read(hc_shared_image* s, int first_row, int rows, void* dst, size_t dst_stride_bytes);
+/* K5 of image `image` writes its rows to rows [first_row, ...) of `dst` instead of the job's own RGB buffer. Call before
+ * hc_heic_job_run; hc_heic_job_read_rgb is not available for such an image. */
+int hc_heic_job_set_rgb_target(hc_heic_job* j, int image, hc_shared_image* dst, int first_row);
+/* same at batch level: any device pointer K5 may store to (peer-mapped or local), rows `stride_bytes` apart */
+int hc_batch_set_rgb_target(hc_batch* b, int canvas, void* device_dst, size_t stride_bytes);
+/* device-to-device copy of a converted image into caller-owned device memory (any device reachable from the job's: the copy
+ * is a peer copy over NVLink then), synchronous */
 int hc_heic_job_copy_rgb_device(hc_heic_job* j, int image, void* device_dst, size_t dst_stride_bytes);
 void hc_heic_job_destroy(hc_heic_job* j);
 int hc_heic_job_image_count(const hc_heic_job* j);

@@ -87,3 +87,38 @@ def test_monochrome_ignores_the_coded_chroma_bit_depth():
     for name, depth in (("mono_8", 8), ("mono_12", 12)):
         rec = hb.parse_picture(annexb(nals(open(os.path.join(GEN_DIR, name + ".hevc"), "rb").read())), hb.STREAM_ANNEXB, host_only=True)
         assert rec.pic.chroma_format == 0 and rec.pic.bit_depth_c == rec.pic.bit_depth_y == depth
+
+
+def test_a_reused_parser_starts_every_picture_from_clean_cu_state():
+    """One parser object decodes many pictures (one per host thread in hc_heic_job). CuQpDeltaVal is read by every QP
+    derivation but only written when the stream codes cu_qp_delta: after example.heic (cu_qp_delta on) a picture without it
+    came out with every QP shifted. The records of the second picture must equal those of a fresh parser."""
+    import ctypes as C
+    import numpy as np
+    from heif_b200 import _lib
+    from heif_b200.api import Records
+    from conftest import STREAMS
+    L = _lib.load(True)
+
+    def primary_stream(path):
+        hf = hb.HeifFile(open(path, "rb").read(), host_only=True)
+        return hf.coded_stream(hf.primary_id)
+
+    first = primary_stream(os.path.join(STREAMS, "example.heic"))
+    second = primary_stream(os.path.join(STREAMS, "test_832x480.heic"))
+    fresh = hb.parse_picture(second, host_only=True)
+    p = L.hc_parser_new()
+    try:
+        assert L.hc_parser_push(p, first, len(first), hb.STREAM_LENGTH_PREFIXED) == 0
+        Records(L, L.hc_parser_take_picture(p))
+        assert L.hc_parser_push(p, second, len(second), hb.STREAM_LENGTH_PREFIXED) == 0
+        reused = Records(L, L.hc_parser_take_picture(p))
+    finally:
+        L.hc_parser_free(p)
+    for name, size in (("ctus", 44), ("blks", 16), ("tbs", 16), ("coeffs", 4), ("edge_map", 1), ("qp_map", 1)):
+        pa, na = fresh.array(name)
+        pb, nb = reused.array(name)
+        assert na == nb, name
+        xa = np.ctypeslib.as_array(C.cast(pa, C.POINTER(C.c_uint8)), shape=(na * size,))
+        xb = np.ctypeslib.as_array(C.cast(pb, C.POINTER(C.c_uint8)), shape=(nb * size,))
+        assert np.array_equal(xa, xb), name
