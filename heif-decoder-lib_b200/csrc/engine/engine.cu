@@ -53,6 +53,7 @@ struct hc_engine {
   int device_parse = 1;                    // hc_heic_job: let K0 parse every picture it accepts
   int sm_count = 148;
   int k0_max_critical = 160;               // hc_heic_job: pictures whose parse critical path exceeds this many CTBs stay with the host parser
+  int chroma_upsampling = 0;               // HC_UPSAMPLE_*: colour conversion of hc_heic_job / hc_heic_decode_stream
   int host_share_pct = -1;                 // hc_heic_job with device_parse: percentage of the coded items the host threads parse meanwhile
 
   Block take(std::vector<Block>& list, size_t size, bool pinned) {
@@ -262,6 +263,11 @@ int hc_engine_set_option(hc_engine* e, const char* name, int value) {
   if (!strcmp(name, "device_parse")) { e->device_parse = value; return HC_OK; }
   if (!strcmp(name, "k0_max_critical_ctbs")) { e->k0_max_critical = value < 1 ? 1 : value; return HC_OK; }
   if (!strcmp(name, "host_share_pct")) { e->host_share_pct = value < 0 ? -1 : (value > 100 ? 100 : value); return HC_OK; }
+  if (!strcmp(name, "chroma_upsampling")) {
+    if (value != HC_UPSAMPLE_NEAREST && value != HC_UPSAMPLE_BILINEAR) { hc::set_last_error("chroma_upsampling: HC_UPSAMPLE_NEAREST or HC_UPSAMPLE_BILINEAR"); return HC_ERR_ARGUMENT; }
+    e->chroma_upsampling = value;
+    return HC_OK;
+  }
   hc::set_last_error(std::string("unknown engine option ") + name);
   return HC_ERR_ARGUMENT;
 }
@@ -269,6 +275,7 @@ int hc_engine_get_option(const hc_engine* e, const char* name) {
   if (!e || !name) return 0;
   if (!strcmp(name, "device_parse")) return e->device_parse;
   if (!strcmp(name, "host_share_pct")) return e->host_share_pct;
+  if (!strcmp(name, "chroma_upsampling")) return e->chroma_upsampling;
   if (!strcmp(name, "k0_max_critical_ctbs")) return e->k0_max_critical;
   return 0;
 }

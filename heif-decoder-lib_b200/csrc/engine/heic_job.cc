@@ -429,7 +429,7 @@ static hc_heic_job* job_create_impl(hc_engine* e, int nfiles, const uint8_t* con
     }
     const bool hdr = p0.bit_depth_y != 8;
     const int fmt = j->forced_format >= 0 ? j->forced_format : (hdr ? (j->want_alpha ? HC_OUT_RRGGBBAA_LE : HC_OUT_RRGGBB_LE) : (j->want_alpha ? HC_OUT_RGBA : HC_OUT_RGB));
-    if (hc_csc_select(matrix, primaries, full, p0.chroma_format, p0.bit_depth_y, has_alpha, fmt, &im.csc) != HC_OK) return nullptr;
+    if (hc_csc_select_opt(matrix, primaries, full, p0.chroma_format, p0.bit_depth_y, has_alpha, fmt, hc_engine_get_option(e, "chroma_upsampling"), &im.csc) != HC_OK) return nullptr;
     static const int bpp_of[6] = {3, 4, 6, 8, 6, 8};
     im.desc.width = W; im.desc.height = H; im.desc.chroma_format = p0.chroma_format; im.desc.bit_depth = p0.bit_depth_y;
     im.desc.has_alpha = has_alpha; im.desc.out_format = fmt; im.desc.bytes_per_pixel = bpp_of[fmt];
@@ -532,6 +532,12 @@ double hc_heic_job_parse_seconds(const hc_heic_job* j) { return j ? j->parse_sec
 int hc_heic_decode_stream(hc_engine* e, int nfiles, const uint8_t* const* data, const size_t* sizes, int want_alpha,
                           int threads, int files_per_batch, hc_image_callback on_image, void* user,
                           hc_stream_stats* stats) {
+  return hc_heic_decode_stream_ext(e, nfiles, data, sizes, want_alpha, threads, files_per_batch, nullptr, on_image, user, stats);
+}
+
+int hc_heic_decode_stream_ext(hc_engine* e, int nfiles, const uint8_t* const* data, const size_t* sizes, int want_alpha,
+                              int threads, int files_per_batch, const hc_stream_dest* dests, hc_image_callback on_image, void* user,
+                              hc_stream_stats* stats) {
   if (!e || nfiles <= 0 || !data || !sizes || files_per_batch <= 0) {
     hc::set_last_error("hc_heic_decode_stream: bad argument");
     return HC_ERR_ARGUMENT;
@@ -581,7 +587,7 @@ int hc_heic_decode_stream(hc_engine* e, int nfiles, const uint8_t* const* data, 
   // slots idle (16 files: 22 CTB slots of time for 16.6 slots of work); with the next batch's K0 already queued on its own
   // low-priority stream, its chains take those slots, and K1..K5 + D2H of the finished batch run at high priority meanwhile.
   constexpr int DEPTH = 3;
-  struct InFlight { hc_heic_job* job = nullptr; int index = 0; int slot = 0; std::vector<size_t> offs; clock::time_point t0; double host_s = 0, host_wait_s = 0; int share = 0; int rc = HC_OK; };
+  struct InFlight { hc_heic_job* job = nullptr; int index = 0; int slot = 0; std::vector<size_t> offs; std::vector<uint8_t*> ptrs; std::vector<size_t> strides; clock::time_point t0; double host_s = 0, host_wait_s = 0; int share = 0; int rc = HC_OK; };
   void* pinned[DEPTH] = {};
   size_t pinned_cap[DEPTH] = {};
   double t_done[3] = {0, 0, 0};   // host time at which the last three batches were seen complete
@@ -591,9 +597,22 @@ int hc_heic_decode_stream(hc_engine* e, int nfiles, const uint8_t* const* data, 
     f.job = j; f.index = b; f.slot = b % DEPTH; f.t0 = clock::now();
     size_t need = 0;
     f.offs.resize(j->images.size());
+    f.ptrs.assign(j->images.size(), nullptr);
+    f.strides.assign(j->images.size(), 0);
     for (size_t i = 0; i < j->images.size(); i++) {
+      const hc_image_desc& d = j->images[i].desc;
+      const size_t row = (size_t)d.width * d.bytes_per_pixel;
       f.offs[i] = need;
-      need += ((size_t)j->images[i].desc.width * j->images[i].desc.bytes_per_pixel * j->images[i].desc.height + 255) & ~(size_t)255;
+      // external destination (the reference's heif_decoding_options::ext_dst, heif.h:1605-1615, pixelimage.cc:221-266): the
+      // final pixels land in the caller's buffer with the caller's stride when it is large enough, else in our own memory
+      const hc_stream_dest* xd = dests ? &dests[(size_t)b * files_per_batch + i] : nullptr;
+      if (xd && xd->dst && xd->stride >= row && xd->len >= xd->stride * (size_t)(d.height - 1) + row) {
+        f.ptrs[i] = (uint8_t*)xd->dst;
+        f.strides[i] = xd->stride;
+        continue;
+      }
+      f.strides[i] = row;
+      need += (row * d.height + 255) & ~(size_t)255;
     }
     if (need > pinned_cap[f.slot]) {
       if (pinned[f.slot]) hc_host_free(pinned[f.slot]);
@@ -601,12 +620,13 @@ int hc_heic_decode_stream(hc_engine* e, int nfiles, const uint8_t* const* data, 
       pinned_cap[f.slot] = pinned[f.slot] ? need + need / 8 : 0;
     }
     const double ta = now_s();
-    int r = pinned[f.slot] ? hc_heic_job_upload(j) : HC_ERR_MEMORY;
+    int r = (pinned[f.slot] || need == 0) ? hc_heic_job_upload(j) : HC_ERR_MEMORY;
     const double tb = now_s();
     if (r == HC_OK) r = hc_heic_job_run(j);
-    for (size_t i = 0; r == HC_OK && i < j->images.size(); i++)
-      r = hc_batch_read_rgb_async(j->batch, j->images[i].canvas, (uint8_t*)pinned[f.slot] + f.offs[i],
-                                  (size_t)j->images[i].desc.width * j->images[i].desc.bytes_per_pixel);
+    for (size_t i = 0; r == HC_OK && i < j->images.size(); i++) {
+      if (!f.ptrs[i]) f.ptrs[i] = (uint8_t*)pinned[f.slot] + f.offs[i];
+      r = hc_batch_read_rgb_async(j->batch, j->images[i].canvas, f.ptrs[i], f.strides[i]);
+    }
     if (trace_on()) fprintf(stderr, "[heifcuda] batch %d submit: pinned %.2f ms, upload %.2f ms, enqueue %.2f ms\n", b, (ta - std::chrono::duration<double>(f.t0.time_since_epoch()).count()) * 1e3, (tb - ta) * 1e3, (now_s() - tb) * 1e3);
     return r;
   };
@@ -646,7 +666,7 @@ int hc_heic_decode_stream(hc_engine* e, int nfiles, const uint8_t* const* data, 
         const hc_image_desc& d = j->images[i].desc;
         st.bytes_d2h += (uint64_t)d.width * d.bytes_per_pixel * d.height;
         st.pixels += (int64_t)d.width * d.height;
-        if (on_image) on_image(user, f.index * files_per_batch + (int)i, &d, (const uint8_t*)pinned[f.slot] + f.offs[i], (size_t)d.width * d.bytes_per_pixel);
+        if (on_image) on_image(user, f.index * files_per_batch + (int)i, &d, f.ptrs[i], f.strides[i]);
       }
       tc = now_s();
     } else if (rc == HC_OK) {

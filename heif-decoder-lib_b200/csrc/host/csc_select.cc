@@ -53,7 +53,12 @@ KrKb kr_kb(int matrix, int primaries) {
 
 extern "C" int hc_csc_select(int matrix, int primaries, int full_range, int chroma_format, int bit_depth,
                              int has_alpha, int out_format, hc_csc_params* out) {
-  if (!out || out_format < HC_OUT_RGB || out_format > HC_OUT_RRGGBBAA_LE || bit_depth < 8 || bit_depth > 16 || chroma_format < 0 ||
+  return hc_csc_select_opt(matrix, primaries, full_range, chroma_format, bit_depth, has_alpha, out_format, HC_UPSAMPLE_NEAREST, out);
+}
+
+extern "C" int hc_csc_select_opt(int matrix, int primaries, int full_range, int chroma_format, int bit_depth,
+                                 int has_alpha, int out_format, int upsampling, hc_csc_params* out) {
+  if (!out || (upsampling != HC_UPSAMPLE_NEAREST && upsampling != HC_UPSAMPLE_BILINEAR) || out_format < HC_OUT_RGB || out_format > HC_OUT_RRGGBBAA_LE || bit_depth < 8 || bit_depth > 16 || chroma_format < 0 ||
       chroma_format > 3) {
     hc::set_last_error("hc_csc_select: bad argument");
     return HC_ERR_ARGUMENT;
@@ -74,6 +79,16 @@ extern "C" int hc_csc_select(int matrix, int primaries, int full_range, int chro
   p.out_format = out_format;
   p.full_range = full_range ? 1 : 0;
   p.in_depth = bit_depth;
+  p.upsampling = HC_UPSAMPLE_NEAREST;
+  const bool bilinear = upsampling == HC_UPSAMPLE_BILINEAR && (chroma_format == 1 || chroma_format == 2);
+  if (upsampling == HC_UPSAMPLE_BILINEAR && chroma_format == 0 && out_format != HC_OUT_RGB && out_format != HC_OUT_RGBA) {
+    hc::set_last_error("monochrome images to RRGGBB(AA) with the bilinear-only option are not supported");
+    return HC_ERR_UNSUPPORTED;
+  }
+  if (bilinear && matrix == 0) {
+    hc::set_last_error("bilinear chroma upsampling of GBR-coded (matrix_coefficients 0) subsampled images: the reference finds no pipeline either");
+    return HC_ERR_UNSUPPORTED;
+  }
 
   // ---- which ops the reference's pipeline search ends up with (colorconversion.cc:266-420, default options), read off
   // the unmodified reference with tools/csc_pipeline_probe.cc for every input class x output format (table: DESIGN.md) ----
@@ -84,7 +99,17 @@ extern "C" int hc_csc_select(int matrix, int primaries, int full_range, int chro
   const int general = matrix == 0 ? HC_CSC_GBR : (matrix == 8 ? HC_CSC_YCGCO : HC_CSC_FLOAT);   // Op_YCbCr_to_RGB<>
   p.out_depth = out8 ? 8 : (in8 ? 10 : bit_depth);            // colorconversion.cc:571-587
   p.pre_op = p.post_op = HC_DEPTH_NONE;
-  if (out8) {
+  if (bilinear) {
+    // only_use_preferred_chroma_algorithm rules the nearest-neighbour 4:2:0 ops out (yuv2rgb.cc:272-279,504-511): the chain
+    // is always Op_YCbCr42x_bilinear_to_YCbCr444 -> Op_YCbCr_to_RGB<> -> interleaver, with the depth-changing plane op in
+    // front of the upsampling — or behind the matrix when an alpha plane is dropped on the way
+    // (tests/golden/csc_pipelines_bilinear.json, 2304 cases)
+    p.mode = general;
+    p.upsampling = HC_UPSAMPLE_BILINEAR;
+    const int op = (out8 && !in8) ? HC_DEPTH_TO_SDR : ((!out8 && in8) ? HC_DEPTH_TO_HDR : HC_DEPTH_NONE);
+    if (has_alpha && !out_alpha) p.post_op = op;
+    else p.pre_op = op;
+  } else if (out8) {
     if (chroma_format == 0) {                                 // [Op_to_sdr_planes] Op_mono_to_RGB24_32
       p.mode = HC_CSC_MONO;
       p.pre_op = in8 ? HC_DEPTH_NONE : HC_DEPTH_TO_SDR;
@@ -124,7 +149,7 @@ extern "C" int hc_csc_select(int matrix, int primaries, int full_range, int chro
   // Op_RGB_HDR_to_RRGGBBaa_BE's feeders); Op_RGB_to_RGB24_32 simply ignores an alpha plane it does not need.
   const bool fresh_state = chroma_format == 0 && !out8;
   const bool drops_alpha = has_alpha && !out_alpha && !(out8 && p.mode != HC_CSC_INT420);
-  const bool matrix_first = !drops_alpha && p.pre_op == HC_DEPTH_NONE;
+  const bool matrix_first = !drops_alpha && p.pre_op == HC_DEPTH_NONE && !bilinear;
   if (!fresh_state && !matrix_first) {
     if (matrix == 2) matrix = 6;
     if (primaries == 2) primaries = 1;

@@ -118,6 +118,43 @@ HC_D int depth_op(int op, int v, int from, int to) {
   return op == HC_DEPTH_TO_SDR ? v >> (from - 8) : (op == HC_DEPTH_TO_HDR ? ((v << (to - 8)) | (v >> (16 - to))) : v);
 }
 
+// Op_YCbCr420_bilinear_to_YCbCr444 / Op_YCbCr422_bilinear_to_YCbCr444 (chroma_sampling.cc:441-705, :709-933) for ONE output
+// sample (x, y) of one chroma plane: 3/4 - 1/4 weights between the surrounding chroma samples, chroma sited in the middle
+// of its 2x2 (2x1) luma samples. The image border follows the reference statement by statement, including its
+// `in[cx / 2]` indexing of the first / last row and column of 4:2:0 pictures (it halves the chroma index once more there).
+// `pre` / `ind` / `outd`: the plane op in front of the upsampling is applied to every chroma sample that is read.
+template <typename Pixel>
+__device__ __forceinline__ int bilinear_chroma(const Pixel* P, int stride, int w, int h, int x, int y, bool v420, int pre, int ind, int outd) {
+  auto S = [&](int cx, int cy) -> int { return depth_op(pre, (int)P[(size_t)cy * stride + cx], ind, outd); };
+  const bool right = x == w - 1 && !(w & 1);
+  if (!v420) {   // 4:2:2: horizontal only
+    if (x == 0) return S(0, y);
+    if (right) return S(w / 2 - 1, y);
+    const int bx = (x & 1) ? x : x - 1, cx = bx >> 1;
+    const int a0 = S(cx, y), a1 = S(cx + 1, y);
+    return x == bx ? (a0 * 3 + a1 + 2) / 4 : (a0 + a1 * 3 + 2) / 4;
+  }
+  const bool bottom = y == h - 1 && !(h & 1);
+  if (y == 0 || bottom) {
+    const int cy = y == 0 ? 0 : h / 2 - 1;
+    if (x == 0) return S(0, cy);
+    if (right) return S(w / 2 - 1, cy);
+    const int q = (((x & 1) ? x - 1 : x - 2) >> 1) / 2;     // "cx / 2" of the reference's border loops
+    const int a0 = S(q, cy), a1 = S(q + 1, cy);
+    return (x & 1) ? (3 * a0 + a1 + 2) / 4 : (a0 + 3 * a1 + 2) / 4;
+  }
+  if (x == 0 || right) {
+    const int cx = x == 0 ? 0 : w / 2 - 1;
+    const int q = (((y & 1) ? y - 1 : y - 2) >> 1) / 2;     // "cy / 2"
+    const int a0 = S(cx, q), a1 = S(cx, q + 1);
+    return (y & 1) ? (3 * a0 + a1 + 2) / 4 : (a0 + 3 * a1 + 2) / 4;
+  }
+  const int bx = (x & 1) ? x : x - 1, by = (y & 1) ? y : y - 1, cx = bx >> 1, cy = by >> 1;
+  const int c00 = S(cx, cy), c01 = S(cx + 1, cy), c10 = S(cx, cy + 1), c11 = S(cx + 1, cy + 1);
+  const int wx0 = x == bx ? 3 : 1, wx1 = 4 - wx0, wy0 = y == by ? 3 : 1, wy1 = 4 - wy0;
+  return (c00 * wx0 * wy0 + c01 * wx1 * wy0 + c10 * wx0 * wy1 + c11 * wx1 * wy1 + 8) / 16;
+}
+
 template <typename Pixel>
 __device__ __forceinline__ void csc_unit(const CscArgs& a, unsigned tid) {
   const unsigned nq = (unsigned)(a.width + 7) >> 3;
@@ -134,7 +171,15 @@ __device__ __forceinline__ void csc_unit(const CscArgs& a, unsigned tid) {
 
   int Y[8], Cb[8], Cr[8], A[8];
   load_px8<Pixel>(reinterpret_cast<const Pixel*>(a.y) + (size_t)y * a.y_stride + x0, n, Y);
-  if (a.chroma_format) {
+  const bool bilinear = a.p.upsampling == HC_UPSAMPLE_BILINEAR && shiftH;   // warp-uniform
+  if (bilinear) {
+#pragma unroll 1
+    for (int k = 0; k < 8; k++) {
+      const int x = min(x0 + k, a.width - 1);
+      Cb[k] = bilinear_chroma<Pixel>(reinterpret_cast<const Pixel*>(a.cb), a.c_stride, a.width, a.height, x, y, shiftV != 0, pre, ind, outd);
+      Cr[k] = bilinear_chroma<Pixel>(reinterpret_cast<const Pixel*>(a.cr), a.c_stride, a.width, a.height, x, y, shiftV != 0, pre, ind, outd);
+    }
+  } else if (a.chroma_format) {
     const size_t coff = (size_t)(y >> shiftV) * a.c_stride + (x0 >> shiftH);
     int cb[8], cr[8];
     const int nc = shiftH ? (n + 1) >> 1 : n;
@@ -157,8 +202,10 @@ __device__ __forceinline__ void csc_unit(const CscArgs& a, unsigned tid) {
 #pragma unroll
     for (int k = 0; k < 8; k++) {
       Y[k] = depth_op(pre, Y[k], ind, outd);
-      Cb[k] = depth_op(pre, Cb[k], ind, outd);
-      Cr[k] = depth_op(pre, Cr[k], ind, outd);
+      if (!bilinear) {          // the bilinear fetch applied it to the samples it read
+        Cb[k] = depth_op(pre, Cb[k], ind, outd);
+        Cr[k] = depth_op(pre, Cr[k], ind, outd);
+      }
       A[k] = depth_op(pre, A[k], ind, outd);
     }
   }
@@ -322,7 +369,7 @@ __global__ void __launch_bounds__(256) k5_int420_rgb24_kernel(CscBatch b) {
 
 static bool k5_fast_path(const CscArgs& a, bool sixteen_bit) {
   return !sixteen_bit && a.chroma_format == 1 && a.p.mode == HC_CSC_INT420 && a.p.out_format == HC_OUT_RGB && a.a == nullptr &&
-         a.p.pre_op == HC_DEPTH_NONE && a.p.post_op == HC_DEPTH_NONE &&
+         a.p.pre_op == HC_DEPTH_NONE && a.p.post_op == HC_DEPTH_NONE && a.p.upsampling == HC_UPSAMPLE_NEAREST &&
          (a.width & 7) == 0 && (a.height & 1) == 0 && (a.y_stride & 7) == 0 && (a.c_stride & 3) == 0 &&
          (reinterpret_cast<uintptr_t>(a.y) & 7) == 0 && (reinterpret_cast<uintptr_t>(a.cb) & 3) == 0 && (reinterpret_cast<uintptr_t>(a.cr) & 3) == 0 &&
          (a.out_stride & 7) == 0 && (reinterpret_cast<uintptr_t>(a.out) & 7) == 0;

@@ -36,7 +36,7 @@ class CscParams(C.Structure):
     _fields_ = [("mode", C.c_int32), ("out_format", C.c_int32), ("full_range", C.c_int32), ("bit_depth", C.c_int32),
                 ("r_cr_i", C.c_int32), ("g_cb_i", C.c_int32), ("g_cr_i", C.c_int32), ("b_cb_i", C.c_int32),
                 ("r_cr", C.c_float), ("g_cb", C.c_float), ("g_cr", C.c_float), ("b_cb", C.c_float),
-                ("in_depth", C.c_int32), ("out_depth", C.c_int32), ("pre_op", C.c_int32), ("post_op", C.c_int32), ("coeff_matrix", C.c_int32)]
+                ("in_depth", C.c_int32), ("out_depth", C.c_int32), ("pre_op", C.c_int32), ("post_op", C.c_int32), ("upsampling", C.c_int32), ("coeff_matrix", C.c_int32)]
 
 
 class ImageDesc(C.Structure):
@@ -59,6 +59,11 @@ class StreamStats(C.Structure):
     _fields_ = [("seconds_total", C.c_double), ("seconds_parse", C.c_double), ("seconds_gpu_phase", C.c_double),
                 ("device_ms", C.c_double), ("bytes_h2d", C.c_uint64), ("bytes_d2h", C.c_uint64), ("pixels", C.c_int64),
                 ("batches", C.c_int32), ("launches", C.c_int32)]
+
+
+class StreamDest(C.Structure):
+    """hc_stream_dest"""
+    _fields_ = [("dst", C.c_void_p), ("len", C.c_size_t), ("stride", C.c_size_t)]
 
 
 IMAGE_CALLBACK = C.CFUNCTYPE(None, C.c_void_p, C.c_int, C.POINTER(ImageDesc), C.c_void_p, C.c_size_t)
@@ -99,6 +104,7 @@ SYMBOLS = [
     ("hc_heif_coded_stream", _i, [_vp, _u32, C.POINTER(_vp), C.POINTER(_sz)]),
     ("hc_free", None, [_vp]),
     ("hc_csc_select", _i, [_i, _i, _i, _i, _i, _i, _i, C.POINTER(CscParams)]),
+    ("hc_csc_select_opt", _i, [_i, _i, _i, _i, _i, _i, _i, _i, C.POINTER(CscParams)]),
     ("hc_engine_create", _vp, [_i]),
     ("hc_engine_destroy", None, [_vp]),
     ("hc_engine_set_option", _i, [_vp, C.c_char_p, _i]),
@@ -158,6 +164,8 @@ SYMBOLS = [
     ("hc_heic_job_parse_seconds", C.c_double, [_vp]),
     ("hc_heic_decode_stream", _i, [_vp, _i, C.POINTER(C.c_char_p), C.POINTER(_sz), _i, _i, _i, IMAGE_CALLBACK, _vp,
                                C.POINTER(StreamStats)]),
+    ("hc_heic_decode_stream_ext", _i, [_vp, _i, C.POINTER(C.c_char_p), C.POINTER(_sz), _i, _i, _i, _vp, IMAGE_CALLBACK, _vp,
+                                   C.POINTER(StreamStats)]),
     ("hc_host_alloc", _vp, [_sz]),
     ("hc_host_free", None, [_vp]),
 ]

@@ -141,11 +141,14 @@ class HeifFile:
         self.close()
 
 
-def csc_select(matrix, primaries, full_range, chroma_format, bit_depth, has_alpha, out_format, host_only=False):
+UPSAMPLE_NEAREST, UPSAMPLE_BILINEAR = 0, 1
+
+
+def csc_select(matrix, primaries, full_range, chroma_format, bit_depth, has_alpha, out_format, host_only=False, upsampling=UPSAMPLE_NEAREST):
     L = _lib.load(host_only)
     p = CscParams()
-    check(L, L.hc_csc_select(matrix, primaries, int(full_range), chroma_format, bit_depth, int(has_alpha), out_format, C.byref(p)),
-          "hc_csc_select")
+    check(L, L.hc_csc_select_opt(matrix, primaries, int(full_range), chroma_format, bit_depth, int(has_alpha), out_format, int(upsampling),
+                                 C.byref(p)), "hc_csc_select")
     return p
 
 
@@ -419,7 +422,7 @@ class HeicJob:
         self.close()
 
 
-def decode_stream(engine, files, on_image=None, want_alpha=False, threads=0, files_per_batch=8, out_format=None):
+def decode_stream(engine, files, on_image=None, want_alpha=False, threads=0, files_per_batch=8, out_format=None, dests=None):
     """Long file lists (hc_heic_decode_stream): host parse of batch b+1 overlaps upload + kernels + read-back of
     batch b. on_image(file_index, desc, rows) gets every image as a numpy view [h, w*bytes_per_pixel] of PINNED
     host memory that is only valid inside the callback. Returns the hc_stream_stats as a dict."""
@@ -445,6 +448,13 @@ def decode_stream(engine, files, on_image=None, want_alpha=False, threads=0, fil
 
     cb = IMAGE_CALLBACK(_cb)
     st = StreamStats()
-    check(L, L.hc_heic_decode_stream(engine._h, n, ptrs, sizes, int(want_alpha), threads, files_per_batch, cb, None, C.byref(st)),
+    xd = None
+    if dests is not None:    # external destinations: one writable uint8 numpy array [rows, stride] (or None) per file
+        from ._lib import StreamDest
+        xd = (StreamDest * n)()
+        for k, a in enumerate(dests):
+            if a is not None:
+                xd[k].dst, xd[k].len, xd[k].stride = a.ctypes.data, a.nbytes, a.strides[0]
+    check(L, L.hc_heic_decode_stream_ext(engine._h, n, ptrs, sizes, int(want_alpha), threads, files_per_batch, xd, cb, None, C.byref(st)),
           "hc_heic_decode_stream")
     return {k: getattr(st, k) for k, _ in StreamStats._fields_}

@@ -170,6 +170,7 @@ typedef struct hc_csc_params {
   int32_t out_depth;     /* depth of the written channels: 8 for RGB / RGBA, else the input depth (10 for 8-bit input) */
   int32_t pre_op;        /* HC_DEPTH_* applied to Y, Cb, Cr, A as they are loaded                */
   int32_t post_op;       /* HC_DEPTH_* applied to R, G, B, A before they are written             */
+  int32_t upsampling;    /* HC_UPSAMPLE_*: how 4:2:0 / 4:2:2 chroma is brought to the luma grid                  */
   int32_t coeff_matrix;  /* matrix_coefficients the coefficients were derived from: an unspecified matrix (2) stays 2 —
                             the literal BT.601 defaults — when the matrix op is the first op of the reference's chain and
                             becomes 6 behind any other op (see csc_select.cc)                     */
@@ -185,6 +186,16 @@ typedef struct hc_csc_params {
  * Returns HC_ERR_UNSUPPORTED for combinations the reference cannot convert either (matrix 11/14). */
 int hc_csc_select(int matrix, int primaries, int full_range, int chroma_format, int bit_depth,
                   int has_alpha, int out_format, hc_csc_params* out);
+/* Chroma upsampling choice of heif_color_conversion_options (heif.h:1546-1562). NEAREST is what the reference's pipeline
+ * search ends up with under its default options. BILINEAR mirrors `preferred_chroma_upsampling_algorithm = bilinear,
+ * only_use_preferred_chroma_algorithm = true` (what heif-dec -C bilinear sets, examples/heif_dec.cc:502-509):
+ * Op_YCbCr420/422_bilinear_to_YCbCr444 (chroma_sampling.cc:441-933, border rules included) in front of Op_YCbCr_to_RGB<>.
+ * 4:4:4 images convert as usual; matrix_coefficients 0 with subsampled chroma has no pipeline in the reference either
+ * (HC_ERR_UNSUPPORTED), nor has monochrome input to RRGGBB(AA) here. */
+#define HC_UPSAMPLE_NEAREST 0
+#define HC_UPSAMPLE_BILINEAR 1
+int hc_csc_select_opt(int matrix, int primaries, int full_range, int chroma_format, int bit_depth,
+                      int has_alpha, int out_format, int upsampling, hc_csc_params* out);
 
 /* ------------------------------------------------------------------ device engine ---------- */
 typedef struct hc_engine hc_engine;
@@ -200,6 +211,8 @@ void hc_engine_destroy(hc_engine* e);
  * is parsed by the host threads instead, which run while the GPU is busy with the previous batch of
  * hc_heic_decode_stream (hybrid parse). Default -1 = automatic: none for a single hc_heic_job, and in
  * hc_heic_decode_stream a share that follows the measured host / GPU time per batch.
+ * "chroma_upsampling" (default HC_UPSAMPLE_NEAREST): HC_UPSAMPLE_BILINEAR makes hc_heic_job / hc_heic_decode_stream convert
+ * with bilinear chroma upsampling (see hc_csc_select_opt).
  * "k0_max_critical_ctbs" (default 160): K0 is serial per substream, so hc_heic_job only hands it pictures whose parse
  * critical path is at most this many CTBs (WPP: CTB columns + 2 x (CTB rows - 1); no WPP: all CTBs of the picture);
  * the others stay with the host parser. */
@@ -388,6 +401,20 @@ typedef struct hc_stream_stats {
 int hc_heic_decode_stream(hc_engine* e, int nfiles, const uint8_t* const* data, const size_t* sizes, int want_alpha,
                           int threads, int files_per_batch, hc_image_callback on_image, void* user,
                           hc_stream_stats* stats);
+/* External destinations (the reference's heif_decoding_options::ext_dst / heif_decoding_options_add_external_dest,
+ * heif.h:1605-1615; HeifPixelImage::add_shared_rgba_plane, pixelimage.cc:221-266): dests[k] describes where the final
+ * pixels of file k go — `len` bytes at `dst` (pinned memory makes the copy asynchronous), rows `stride` bytes apart. Like
+ * the reference, a destination that is absent or too small (len < stride * (height - 1) + row bytes, or stride < row
+ * bytes) is ignored and the image is delivered in the library's own pinned memory; the callback receives whichever pointer
+ * and stride were used. dests may be NULL (then this is hc_heic_decode_stream). */
+typedef struct hc_stream_dest {
+  void* dst;
+  size_t len;
+  size_t stride;
+} hc_stream_dest;
+int hc_heic_decode_stream_ext(hc_engine* e, int nfiles, const uint8_t* const* data, const size_t* sizes, int want_alpha,
+                              int threads, int files_per_batch, const hc_stream_dest* dests, hc_image_callback on_image, void* user,
+                              hc_stream_stats* stats);
 /* pinned host memory for fast H2D/D2H in the caller (NULL when no CUDA engine) */
 void* hc_host_alloc(size_t bytes);
 void hc_host_free(void* p);

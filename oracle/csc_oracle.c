@@ -21,6 +21,7 @@
 #include <math.h>
 #include <stddef.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 static uint16_t clip_f_u16(float fx, int32_t maxi) { /* common_utils.h:64-70 */
   long x = (long)(fx + 0.5f);
@@ -85,6 +86,103 @@ static coeffs_t get_coeffs(int matrix, int primaries) { /* nclx.cc:82-171 */
 static int to_hdr(int v, int out_bits) { return ((v << (out_bits - 8)) | (v >> (16 - out_bits))) & 0xffff; }
 static int to_sdr(int v, int in_bits) { return (v >> (in_bits - 8)) & 0xff; }
 
+/* Op_YCbCr420_bilinear_to_YCbCr444 (chroma_sampling.cc:441-705) on one chroma plane, restated loop by loop: borders
+ * first (the first / last row and column index the chroma row with cx / 2, as the reference does), then every 2x2 square
+ * between four chroma samples. `in` has ((w+1)/2) x ((h+1)/2) samples, `out` w x h. */
+void hc_oracle_bilinear_420(const uint16_t* in, int in_stride, uint16_t* out, int out_stride, int width, int height) {
+  out[0] = in[0];
+  for (int cx = 0; cx < (width - 1) / 2; cx++) {
+    out[2 * cx + 1] = (uint16_t)((3 * in[cx / 2] + 1 * in[cx / 2 + 1] + 2) / 4);
+    out[2 * cx + 2] = (uint16_t)((1 * in[cx / 2] + 3 * in[cx / 2 + 1] + 2) / 4);
+  }
+  if (width % 2 == 0) out[width - 1] = in[width / 2 - 1];
+  for (int cy = 0; cy < (height - 1) / 2; cy++) {
+    out[(2 * cy + 1) * out_stride] = (uint16_t)((3 * in[cy / 2 * in_stride] + 1 * in[(cy / 2 + 1) * in_stride] + 2) / 4);
+    out[(2 * cy + 2) * out_stride] = (uint16_t)((1 * in[cy / 2 * in_stride] + 3 * in[(cy / 2 + 1) * in_stride] + 2) / 4);
+  }
+  if (height % 2 == 0) out[(height - 1) * out_stride] = in[(height / 2 - 1) * in_stride];
+  if (width % 2 == 0)
+    for (int cy = 0; cy < (height - 1) / 2; cy++) {
+      out[(2 * cy + 1) * out_stride + width - 1] = (uint16_t)((3 * in[cy / 2 * in_stride + width / 2 - 1] + 1 * in[(cy / 2 + 1) * in_stride + width / 2 - 1] + 2) / 4);
+      out[(2 * cy + 2) * out_stride + width - 1] = (uint16_t)((1 * in[cy / 2 * in_stride + width / 2 - 1] + 3 * in[(cy / 2 + 1) * in_stride + width / 2 - 1] + 2) / 4);
+    }
+  if (height % 2 == 0)
+    for (int cx = 0; cx < (width - 1) / 2; cx++) {
+      out[(height - 1) * out_stride + 2 * cx + 1] = (uint16_t)((3 * in[(height / 2 - 1) * in_stride + cx / 2] + 1 * in[(height / 2 - 1) * in_stride + cx / 2 + 1] + 2) / 4);
+      out[(height - 1) * out_stride + 2 * cx + 2] = (uint16_t)((1 * in[(height / 2 - 1) * in_stride + cx / 2] + 3 * in[(height / 2 - 1) * in_stride + cx / 2 + 1] + 2) / 4);
+    }
+  if (width % 2 == 0 && height % 2 == 0) out[(height - 1) * out_stride + width - 1] = in[(height / 2 - 1) * in_stride + width / 2 - 1];
+  for (int y = 1; y < height - 1; y += 2)
+    for (int x = 1; x < width - 1; x += 2) {
+      const int cx = x / 2, cy = y / 2;
+      const int c00 = in[cy * in_stride + cx], c01 = in[cy * in_stride + cx + 1], c10 = in[(cy + 1) * in_stride + cx], c11 = in[(cy + 1) * in_stride + cx + 1];
+      out[(y + 0) * out_stride + x + 0] = (uint16_t)((c00 * 3 * 3 + c01 * 1 * 3 + c10 * 3 * 1 + c11 * 1 * 1 + 8) / 16);
+      out[(y + 0) * out_stride + x + 1] = (uint16_t)((c00 * 1 * 3 + c01 * 3 * 3 + c10 * 1 * 1 + c11 * 3 * 1 + 8) / 16);
+      out[(y + 1) * out_stride + x + 0] = (uint16_t)((c00 * 3 * 1 + c01 * 1 * 1 + c10 * 3 * 3 + c11 * 1 * 3 + 8) / 16);
+      out[(y + 1) * out_stride + x + 1] = (uint16_t)((c00 * 1 * 1 + c01 * 3 * 1 + c10 * 1 * 3 + c11 * 3 * 3 + 8) / 16);
+    }
+}
+
+/* Op_YCbCr422_bilinear_to_YCbCr444 (chroma_sampling.cc:709-933): `in` has ((w+1)/2) x h samples */
+void hc_oracle_bilinear_422(const uint16_t* in, int in_stride, uint16_t* out, int out_stride, int width, int height) {
+  for (int y = 0; y < height; y++) out[y * out_stride] = in[y * in_stride];
+  if (width % 2 == 0)
+    for (int y = 0; y < height; y++) out[y * out_stride + width - 1] = in[y * in_stride + width / 2 - 1];
+  for (int y = 0; y < height; y++)
+    for (int x = 1; x < width - 1; x += 2) {
+      const int cx = x / 2;
+      const int c0 = in[y * in_stride + cx], c1 = in[y * in_stride + cx + 1];
+      out[y * out_stride + x + 0] = (uint16_t)((c0 * 3 + c1 * 1 + 2) / 4);
+      out[y * out_stride + x + 1] = (uint16_t)((c0 * 1 + c1 * 3 + 2) / 4);
+    }
+}
+
+static int hc_oracle_csc_core(const uint16_t* y, const uint16_t* cb, const uint16_t* cr, const uint16_t* a, int y_stride,
+                              int c_stride, int a_stride, int width, int height, int chroma_format, int bit_depth, int matrix,
+                              int primaries, int full_range, int out_format, uint8_t* out, size_t out_stride, int bilinear_in);
+
+/* upsampling 1 = the options heif-dec -C bilinear sets (bilinear chroma upsampling, only the preferred algorithm): the
+ * chain is [plane op] Op_YCbCr42x_bilinear_to_YCbCr444 -> Op_YCbCr_to_RGB<> [plane op] -> interleaver
+ * (tests/golden/csc_pipelines_bilinear.json); restated literally: upsample whole planes, then convert as 4:4:4. */
+int hc_oracle_csc_opt(const uint16_t* y, const uint16_t* cb, const uint16_t* cr, const uint16_t* a, int y_stride,
+                      int c_stride, int a_stride, int width, int height, int chroma_format, int bit_depth, int matrix,
+                      int primaries, int full_range, int out_format, int upsampling, uint8_t* out, size_t out_stride) {
+  if (!upsampling || (chroma_format != 1 && chroma_format != 2))
+    return hc_oracle_csc_core(y, cb, cr, a, y_stride, c_stride, a_stride, width, height, chroma_format, bit_depth, matrix, primaries, full_range,
+                              out_format, out, out_stride, 0);
+  if (matrix == 0) return -1;
+  const int out8 = out_format <= 1, to_alpha = out_format == 1 || out_format == 3 || out_format == 5, in8 = bit_depth == 8;
+  const int op = (out8 && !in8) ? 1 : ((!out8 && in8) ? 2 : 0);
+  const int pre = (a != NULL && !to_alpha) ? 0 : op;        /* the plane op goes behind the matrix when an alpha plane is dropped */
+  const int target = out8 ? 8 : (in8 ? 10 : bit_depth);
+  const int cw = (width + 1) / 2, ch = chroma_format == 1 ? (height + 1) / 2 : height;
+  uint16_t* tmp = (uint16_t*)malloc(sizeof(uint16_t) * ((size_t)2 * cw * ch + (size_t)2 * width * height));
+  if (!tmp) return -2;
+  uint16_t *pcb = tmp, *pcr = tmp + (size_t)cw * ch, *ucb = pcr + (size_t)cw * ch, *ucr = ucb + (size_t)width * height;
+  for (int yy = 0; yy < ch; yy++)
+    for (int x = 0; x < cw; x++) {
+      int vb = cb[(size_t)yy * c_stride + x], vr = cr[(size_t)yy * c_stride + x];
+      if (pre == 1) { vb = to_sdr(vb, bit_depth); vr = to_sdr(vr, bit_depth); }
+      else if (pre == 2) { vb = to_hdr(vb, target); vr = to_hdr(vr, target); }
+      pcb[(size_t)yy * cw + x] = (uint16_t)vb;
+      pcr[(size_t)yy * cw + x] = (uint16_t)vr;
+    }
+  if (chroma_format == 1) { hc_oracle_bilinear_420(pcb, cw, ucb, width, width, height); hc_oracle_bilinear_420(pcr, cw, ucr, width, width, height); }
+  else { hc_oracle_bilinear_422(pcb, cw, ucb, width, width, height); hc_oracle_bilinear_422(pcr, cw, ucr, width, width, height); }
+  /* bilinear_in: 1 = the chroma planes handed over already went through `pre` (luma and alpha have not), 2 = no plane op in front */
+  const int rc = hc_oracle_csc_core(y, ucb, ucr, a, y_stride, width, a_stride, width, height, 3, bit_depth, matrix, primaries, full_range, out_format, out,
+                                    out_stride, pre ? 1 : 2);
+  free(tmp);
+  return rc;
+}
+
+int hc_oracle_csc(const uint16_t* y, const uint16_t* cb, const uint16_t* cr, const uint16_t* a, int y_stride,
+                  int c_stride, int a_stride, int width, int height, int chroma_format, int bit_depth, int matrix,
+                  int primaries, int full_range, int out_format, uint8_t* out, size_t out_stride) {
+  return hc_oracle_csc_core(y, cb, cr, a, y_stride, c_stride, a_stride, width, height, chroma_format, bit_depth, matrix, primaries, full_range, out_format,
+                            out, out_stride, 0);
+}
+
 /* out_format: 0 RGB, 1 RGBA, 2 RRGGBB_BE, 3 RRGGBBAA_BE, 4 RRGGBB_LE, 5 RRGGBBAA_LE.
  * Planes are uint16 arrays (any bit depth), strides in samples. `a` may be NULL.
  * Returns 0, or -1 for combinations the reference cannot convert.
@@ -100,9 +198,9 @@ static int to_sdr(int v, int in_bits) { return (v >> (in_bits - 8)) & 0xff; }
  *     only if the input has:                [Op_to_hdr_planes on Y Cb Cr A]  Op_YCbCr420_to_RRGGBBaa           (fp32)
  *     everything else:      Op_YCbCr_to_RGB<> at the input depth  [Op_to_hdr_planes on R G B A]  Op_RGB_HDR_to_RRGGBBaa_BE
  *                           [Op_RRGGBBaa_swap_endianness]; a missing alpha plane is filled with the maximum of the final depth */
-int hc_oracle_csc(const uint16_t* y, const uint16_t* cb, const uint16_t* cr, const uint16_t* a, int y_stride,
-                  int c_stride, int a_stride, int width, int height, int chroma_format, int bit_depth, int matrix,
-                  int primaries, int full_range, int out_format, uint8_t* out, size_t out_stride) {
+static int hc_oracle_csc_core(const uint16_t* y, const uint16_t* cb, const uint16_t* cr, const uint16_t* a, int y_stride,
+                              int c_stride, int a_stride, int width, int height, int chroma_format, int bit_depth, int matrix,
+                              int primaries, int full_range, int out_format, uint8_t* out, size_t out_stride, int bilinear_in) {
   /* matrix 2 (unspecified) reaches the ops unchanged: Kr = Kb = 0 -> the literal BT.601 defaults
    * (nclx.cc:140-149,159-169), NOT the values computed from Kr/Kb of matrix 6 */
   if (matrix == 11 || matrix == 14) return -1;
@@ -138,6 +236,12 @@ int hc_oracle_csc(const uint16_t* y, const uint16_t* cb, const uint16_t* cr, con
       if (hdr_first) pre = 2; else post = 2;
     }
   }
+  if (bilinear_in) {      /* behind the bilinear upsampling: general matrix op; plane op in front (1) or behind / absent (2) */
+    const int opd = (out8 && !in8) ? 1 : ((!out8 && in8) ? 2 : 0);
+    op = 1;
+    pre = bilinear_in == 1 ? opd : 0;
+    post = bilinear_in == 1 ? 0 : opd;
+  }
   const int work = pre == 1 ? 8 : (pre == 2 ? target : bit_depth);   /* depth the conversion runs at */
   const int maxv = (1 << work) - 1;
   const int half = 1 << (work - 1);
@@ -149,7 +253,7 @@ int hc_oracle_csc(const uint16_t* y, const uint16_t* cb, const uint16_t* cr, con
   if (chroma_format != 0 || out8) {
     /* Op_RGB_to_RGB24_32 ignores an alpha plane it does not need: no Op_drop_alpha_plane in front of the general 8-bit path */
     const int drops_alpha = has_alpha && !to_alpha && !(out8 && op == 1);
-    const int matrix_first = !drops_alpha && pre == 0;
+    const int matrix_first = !drops_alpha && pre == 0 && !bilinear_in;
     if (!matrix_first) {
       const coeffs_t k2 = get_coeffs(matrix == 2 ? 6 : matrix, primaries == 2 ? 1 : primaries);
       k = k2;
@@ -166,8 +270,9 @@ int hc_oracle_csc(const uint16_t* y, const uint16_t* cb, const uint16_t* cr, con
       const int yv = PRE(y[(size_t)yy * y_stride + x]);
       int cbv, crv;
       if (chroma_format) {
-        cbv = PRE(cb[(size_t)(yy >> shiftV) * c_stride + (x >> shiftH)]);
-        crv = PRE(cr[(size_t)(yy >> shiftV) * c_stride + (x >> shiftH)]);
+        cbv = cb[(size_t)(yy >> shiftV) * c_stride + (x >> shiftH)];
+        crv = cr[(size_t)(yy >> shiftV) * c_stride + (x >> shiftH)];
+        if (bilinear_in != 1) { cbv = PRE(cbv); crv = PRE(crv); }
       } else {
         cbv = crv = PRE(128 << (bit_depth - 8));      /* monochrome.cc:99-100,128: the planes Op_mono_to_YCbCr420 adds */
       }

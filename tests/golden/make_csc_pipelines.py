@@ -17,8 +17,9 @@ with tempfile.TemporaryDirectory() as tmp:
     subprocess.check_call(["g++", "-std=gnu++11", "-w", "-I" + os.path.join(LIB, "gen"), "-I" + os.path.join(LIB, "gen", "libheif"), "-I" + REF,
                            "-I" + os.path.join(REF, "libheif"), "-I" + os.path.join(REF, "libheif", "api"),
                            os.path.join(ROOT, "tools", "csc_pipeline_probe.cc"), "-o", exe, "-L" + LIB, "-lheifref", "-lde265ref", "-Wl,-rpath," + LIB])
-    rows = json.loads(subprocess.check_output([exe]))
-# compact form: one string per case
-out = ["%d %d %d %d %d %d %s" % (r["chroma"], r["depth"], r["full"], r["matrix"], r["alpha"], r["out"], r["ops"]) for r in rows]
-json.dump(out, open(os.path.join(HERE, "csc_pipelines.json"), "w"), indent=0)
-print(len(out), "cases;", len({r["ops"] for r in rows}), "distinct chains")
+    for arg, name in (([], "csc_pipelines.json"), (["bilinear"], "csc_pipelines_bilinear.json")):
+        rows = json.loads(subprocess.check_output([exe] + arg))
+        # compact form: one string per case
+        out = ["%d %d %d %d %d %d %s" % (r["chroma"], r["depth"], r["full"], r["matrix"], r["alpha"], r["out"], r["ops"]) for r in rows]
+        json.dump(out, open(os.path.join(HERE, name), "w"), indent=0)
+        print(name, len(out), "cases;", len({r["ops"] for r in rows}), "distinct chains")

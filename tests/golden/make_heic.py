@@ -100,12 +100,13 @@ ALL_FORMATS = {"rgb": R.CHROMA_RGB, "rgba": R.CHROMA_RGBA, "rrggbb_be": R.CHROMA
                "rrggbb_le": R.CHROMA_RRGGBB_LE, "rrggbbaa_le": R.CHROMA_RRGGBBAA_LE}
 
 
-def reference_all_formats(data):
-    """heif_decode_image(..., heif_colorspace_RGB, chroma) of the unmodified reference for every interleaved chroma"""
+def reference_all_formats(data, bilinear=False):
+    """heif_decode_image(..., heif_colorspace_RGB, chroma) of the unmodified reference for every interleaved chroma;
+    bilinear: with the colour conversion options heif-dec -C bilinear sets"""
     out = {}
     for name, chroma in ALL_FORMATS.items():
         try:
-            out[name + "_md5"] = md5(R.decode(data, R.COLORSPACE_RGB, chroma)["interleaved"][0])
+            out[name + "_md5"] = md5(R.decode(data, R.COLORSPACE_RGB, chroma, bilinear=bilinear)["interleaved"][0])
         except RuntimeError as e:
             out[name + "_error"] = str(e)
     return out
@@ -145,6 +146,10 @@ def main():
     for name in sorted(meta):
         fmts[name] = reference_all_formats(open(os.path.join(OUT, name + ".heic"), "rb").read())
     json.dump(fmts, open(os.path.join(HERE, "heic_formats.json"), "w"), indent=1, sort_keys=True)
+    bil = {}
+    for name in sorted(meta):
+        bil[name] = reference_all_formats(open(os.path.join(OUT, name + ".heic"), "rb").read(), bilinear=True)
+    json.dump(bil, open(os.path.join(HERE, "heic_formats_bilinear.json"), "w"), indent=1, sort_keys=True)
 
 
 if __name__ == "__main__":

@@ -11,16 +11,16 @@ import oracle_lib
 OUT_BPP = {0: 3, 1: 4, 2: 6, 3: 8, 4: 6, 5: 8}
 
 
-def csc(planes, chroma_format, bit_depth, matrix, full_range, out_format, alpha=None, primaries=2):
+def csc(planes, chroma_format, bit_depth, matrix, full_range, out_format, alpha=None, primaries=2, upsampling=0):
     O = oracle_lib.lib()
     h, w = planes[0].shape
     out = np.zeros((h, w * OUT_BPP[out_format]), np.uint8)
     pl = [np.ascontiguousarray(p, np.uint16) for p in planes]
     a = np.ascontiguousarray(alpha, np.uint16) if alpha is not None else None
-    rc = O.hc_oracle_csc(C.c_void_p(pl[0].ctypes.data), C.c_void_p(pl[1].ctypes.data if len(pl) > 1 else None),
+    rc = O.hc_oracle_csc_opt(C.c_void_p(pl[0].ctypes.data), C.c_void_p(pl[1].ctypes.data if len(pl) > 1 else None),
                          C.c_void_p(pl[2].ctypes.data if len(pl) > 2 else None), C.c_void_p(a.ctypes.data if a is not None else None),
                          pl[0].shape[1], pl[1].shape[1] if len(pl) > 1 else 0, a.shape[1] if a is not None else 0,
-                         w, h, chroma_format, bit_depth, matrix, int(primaries), int(full_range), out_format,
+                         w, h, chroma_format, bit_depth, matrix, int(primaries), int(full_range), out_format, int(upsampling),
                          C.c_void_p(out.ctypes.data), C.c_size_t(out.strides[0]))
     if rc != 0:
         raise RuntimeError("oracle csc cannot convert this combination")
@@ -166,6 +166,6 @@ def _transform_all(planes, info):
     return [np.ascontiguousarray(p) for p in planes]
 
 
-def decode_rgb(data, out_format, item_id=None):
+def decode_rgb(data, out_format, item_id=None, upsampling=0):
     planes, alpha, cf, bd, (matrix, full, primaries) = decode_planes(data, item_id)
-    return csc(planes, cf, bd, matrix, full, out_format, alpha, primaries)
+    return csc(planes, cf, bd, matrix, full, out_format, alpha, primaries, upsampling)

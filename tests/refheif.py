@@ -92,7 +92,7 @@ def plane_bytes(img, channel, bytes_per_px):
     return b"".join(buf[y * stride.value: y * stride.value + row] for y in range(h)), w, h
 
 
-def decode(data, colorspace, chroma, item_id=None, threads=None, decoder_id=None):
+def decode(data, colorspace, chroma, item_id=None, threads=None, decoder_id=None, bilinear=False):
     """heif_decode_image on an in-memory HEIC. Returns dict of channel -> (bytes, w, h) plus bpp.
     decoder_id: None = the reference's libde265 plugin; "" = let libheif choose by priority."""
     L = lib()
@@ -113,8 +113,15 @@ def decode(data, colorspace, chroma, item_id=None, threads=None, decoder_id=None
             L.heif_context_set_threads(ctx, h, threads)
         img = C.c_void_p()
         opts = None
-        if decoder_id is not None:
+        if decoder_id is not None or bilinear:
             opts = L.heif_decoding_options_alloc()
+        if bilinear:
+            # color_conversion_options sits behind decoder_id (offset 56): version u8, downsampling enum @60, upsampling enum @64,
+            # only_use_preferred_chroma_algorithm u8 @68 — what heif-dec -C bilinear sets (examples/heif_dec.cc:502-509);
+            # heif_chroma_upsampling_bilinear = 2 (heif.h)
+            C.memmove(opts + 64, C.byref(C.c_int(2)), 4)
+            C.memmove(opts + 68, C.byref(C.c_uint8(1)), 1)
+        if decoder_id is not None:
             # struct heif_decoding_options (heif.h:1565-1611): decoder_id is the const char* after
             # version(u8) ignore_transformations(u8) start_progress/on_progress/end_progress/progress_user_data
             # (4 pointers) convert_hdr_to_8bit(u8) strict_decoding(u8) -> offset 8+32+8 = 48

@@ -55,6 +55,20 @@ def test_oracle_reproduces_reference_in_every_output_format(name):
     assert checked >= 4, FMETA[name]
 
 
+BMETA = json.load(open(os.path.join(ROOT, "tests", "golden", "heic_formats_bilinear.json")))
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_oracle_reproduces_reference_with_bilinear_upsampling(name):
+    """heif_decode_image with the colour conversion options of heif-dec -C bilinear (bilinear chroma upsampling, only the
+    preferred algorithm): every fixture, every interleaved format the reference converts."""
+    data = load(name)
+    cf = heic_oracle.decode_planes(data)[2]
+    for key, fmt in ALL_FORMATS.items():
+        if key + "_md5" in BMETA[name] and not (cf == 0 and fmt > hb.OUT_RGBA):
+            assert md5(heic_oracle.decode_rgb(data, fmt, upsampling=1).tobytes()) == BMETA[name][key + "_md5"], key
+
+
 def _iovl_file(chroma_format):
     from tools import heif_writer as W, hevcenc
     b = W.HeifBuilder()
@@ -129,6 +143,25 @@ def test_gpu_heic_job_every_output_format(engine, key):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("key", ["rgb", "rgba", "rrggbb_le", "rrggbbaa_be"])
+def test_gpu_heic_job_bilinear_chroma_upsampling(engine, key):
+    """engine option chroma_upsampling = HC_UPSAMPLE_BILINEAR: K5 fetches chroma through the reference's bilinear ops
+    (border rules included), bit-exact against the reference run with the same option."""
+    fmt = ALL_FORMATS[key]
+    names = [n for n in NAMES if key + "_md5" in BMETA[n] and not (META[n].get("chroma_mono") or n.startswith("single_mono") and fmt > hb.OUT_RGBA)]
+    engine.set_option("chroma_upsampling", 1)
+    try:
+        job = hb.HeicJob(engine, [load(n) for n in names], threads=4, out_format=fmt)
+    finally:
+        engine.set_option("chroma_upsampling", 0)
+    job.upload()
+    job.run()
+    bad = [n for i, n in enumerate(names) if md5(job.read_rgb(i).tobytes()) != BMETA[n][key + "_md5"]]
+    job.close()
+    assert len(names) >= 35 and not bad, (key, bad)
+
+
+@pytest.mark.gpu
 def test_gpu_decode_heic_python_path(engine):
     for name in ("grid_300x200_t128", "single_420_8_novui", "alpha_420_8"):
         rgb = hb.decode_heic(engine, load(name), hb.OUT_RGB)
@@ -172,6 +205,43 @@ def test_gpu_decode_stream_fill_and_drain(engine, nbatches):
     st = hb.decode_stream(engine, [load(n) for n in names], on_image, want_alpha=False, threads=2, files_per_batch=3)
     assert [i for i, _ in seen] == list(range(len(names))) and all(ok for _, ok in seen)
     assert st["batches"] == nbatches
+
+
+@pytest.mark.gpu
+def test_gpu_decode_stream_external_destinations(engine):
+    """hc_heic_decode_stream_ext: the reference's ext_dst semantics (heif.h:1605-1615, pixelimage.cc:221-266) — final pixels in
+    the caller's buffer with the caller's stride when it is large enough, the library's own memory otherwise."""
+    names = NAMES[:9]
+    files = [load(n) for n in names]
+    dests, kinds = [], []
+    for k, n in enumerate(names):
+        m = META[n]
+        bpp = 3 if m["bit_depth"] == 8 else 6
+        row = m["width"] * bpp
+        if k % 3 == 0:
+            dests.append(np.zeros((m["height"], row + 40), np.uint8)); kinds.append("padded")      # larger stride
+        elif k % 3 == 1:
+            dests.append(np.zeros((m["height"] - 1, row), np.uint8)); kinds.append("small")         # too small: ignored
+        else:
+            dests.append(None); kinds.append("none")
+    seen = {}
+
+    def on_image(index, desc, rows):
+        key = "rgb_md5" if desc.out_format == hb.OUT_RGB else "rrggbb_le_md5"
+        row = desc.width * desc.bytes_per_pixel
+        ext = dests[index] is not None and rows.ctypes.data == dests[index].ctypes.data
+        seen[index] = (ext, rows.shape[1], md5(np.ascontiguousarray(rows[:, :row]).tobytes()) == META[names[index]][key])
+
+    hb.decode_stream(engine, files, on_image, threads=2, files_per_batch=4, dests=dests)
+    for k, kind in enumerate(kinds):
+        ext, stride, ok = seen[k]
+        assert ok, names[k]
+        assert ext == (kind == "padded"), (names[k], kind)
+        if kind == "padded":
+            m = META[names[k]]
+            key = "rgb_md5" if m["bit_depth"] == 8 else "rrggbb_le_md5"
+            row = m["width"] * (3 if m["bit_depth"] == 8 else 6)
+            assert stride == row + 40 and md5(np.ascontiguousarray(dests[k][:, :row]).tobytes()) == m[key]
 
 
 @pytest.mark.gpu

@@ -94,3 +94,16 @@ def test_heic_items_match_live_reference(fname, item):
     planes, _ = oracle_lib.reconstruct(rec)
     for p, k in zip(planes, ("Y", "Cb", "Cr")):
         assert p.astype(np.uint8).tobytes() == ref[k][0]
+
+
+def test_oracle_bilinear_upsampling_reproduces_the_reference_vectors():
+    """tests/conversion.cc:645-669 ("Bilinear upsampling"): the only colour-path op the reference pins with exact values —
+    a 4x4 4:2:0 image, Cb / Cr 2x2 -> 4x4 through Op_YCbCr420_bilinear_to_YCbCr444."""
+    O = oracle_lib.lib()
+    cases = [([10, 40, 100, 240], [10, 18, 33, 40, 33, 47, 76, 90, 78, 106, 162, 190, 100, 135, 205, 240]),
+             ([255, 200, 50, 0], [255, 241, 214, 200, 204, 190, 163, 150, 101, 88, 63, 50, 50, 38, 13, 0])]
+    for src, want in cases:
+        a = np.array(src, np.uint16).reshape(2, 2)
+        out = np.zeros((4, 4), np.uint16)
+        O.hc_oracle_bilinear_420(C.c_void_p(a.ctypes.data), 2, C.c_void_p(out.ctypes.data), 4, 4, 4)
+        assert out.flatten().tolist() == want

@@ -10,7 +10,9 @@
 #include <string>
 #include "libheif/color-conversion/colorconversion.h"
 
-int main() {
+int main(int argc, char** argv) {
+  // argument "bilinear": the options heif-dec -C bilinear sets (examples/heif_dec.cc:502-509): bilinear chroma upsampling only
+  const bool only_bilinear = argc > 1 && std::string(argv[1]) == "bilinear";
   ColorConversionPipeline::init_ops();
   const heif_chroma chromas[4] = {heif_chroma_monochrome, heif_chroma_420, heif_chroma_422, heif_chroma_444};
   const int depths[3] = {8, 10, 12};
@@ -42,7 +44,7 @@ int main() {
               opt.version = 1;
               opt.preferred_chroma_downsampling_algorithm = heif_chroma_downsampling_average;
               opt.preferred_chroma_upsampling_algorithm = heif_chroma_upsampling_bilinear;
-              opt.only_use_preferred_chroma_algorithm = false;
+              opt.only_use_preferred_chroma_algorithm = only_bilinear;
               ColorConversionPipeline p;
               std::string ops;
               if (p.construct_pipeline(a, b, opt)) {
