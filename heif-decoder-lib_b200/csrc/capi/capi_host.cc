@@ -107,6 +107,20 @@ int hc_heif_top_level_ids(const hc_heif* f, uint32_t* ids, int max) {
   for (int i = 0; i < (int)v.size() && i < max; i++) ids[i] = v[i];
   return (int)v.size();
 }
+int hc_heif_get_overlay(const hc_heif* f, uint32_t id, hc_heif_overlay_info* info) {
+  if (!f || !info || !f->file.is_overlay(id)) { g_last_error = "hc_heif_get_overlay: not an overlay item"; return HC_ERR_ARGUMENT; }
+  hc::HeifOverlay o;
+  std::string e = f->file.overlay(id, o);
+  if (!e.empty()) { g_last_error = e; return HC_ERR_BITSTREAM; }
+  if (o.children.size() > HC_OVERLAY_MAX_CHILDREN || o.children.size() != o.offsets.size()) { g_last_error = "overlay: too many or mismatched references"; return HC_ERR_UNSUPPORTED; }
+  memset(info, 0, sizeof(*info));
+  info->canvas_w = o.canvas_w; info->canvas_h = o.canvas_h;
+  for (int k = 0; k < 4; k++) info->background[k] = o.background[k];
+  info->n = (int32_t)o.children.size();
+  for (int k = 0; k < info->n; k++) { info->children[k] = o.children[k]; info->dx[k] = o.offsets[k].first; info->dy[k] = o.offsets[k].second; }
+  return HC_OK;
+}
+
 int hc_heif_get_image_info(const hc_heif* f, uint32_t id, hc_heif_image_info* info) {
   const hc::HeifItem* it = f->file.item(id);
   if (!it || !info) { g_last_error = "hc_heif_get_image_info: no such item"; return HC_ERR_ARGUMENT; }
@@ -126,6 +140,7 @@ int hc_heif_get_image_info(const hc_heif* f, uint32_t id, hc_heif_image_info* in
     info->height = g.out_h;
   }
   info->alpha_id = f->file.alpha_item(id);
+  info->premultiplied_alpha = f->file.premultiplied(id) ? 1 : 0;
   info->rot = it->rot;
   info->mirror = it->mirror;
   info->n_transforms = (int32_t)std::min<size_t>(it->xforms.size(), 8);

@@ -53,6 +53,7 @@ struct hc_engine {
   int device_parse = 1;                    // hc_heic_job: let K0 parse every picture it accepts
   int sm_count = 148;
   int k0_max_critical = 160;               // hc_heic_job: pictures whose parse critical path exceeds this many CTBs stay with the host parser
+  int premultiply_alpha = 0;               // hc_heic_job: RGBA output multiplied by alpha in K5
   int chroma_upsampling = 0;               // HC_UPSAMPLE_*: colour conversion of hc_heic_job / hc_heic_decode_stream
   int host_share_pct = -1;                 // hc_heic_job with device_parse: percentage of the coded items the host threads parse meanwhile
 
@@ -126,6 +127,11 @@ struct Canvas {
   int ow = 0, oh = 0;               // output image size
   size_t ooff[4] = {0, 0, 0, 0};
   int ostride[4] = {0, 0, 0, 0}, opw[4] = {0, 0, 0, 0}, oph[4] = {0, 0, 0, 0};
+  // 'iovl' derived image (hc_batch_add_overlay_canvas): no planes of its own; K7 composes the child canvases into its RGB output
+  bool overlay = false;
+  int bkg[3] = {0, 0, 0};
+  struct OverlayChild { int canvas, dx, dy; hc_csc_params p; };
+  std::vector<OverlayChild> children;
   // K5 writes here instead of the batch's RGB buffer when set (hc_batch_set_rgb_target: a band of a shared image on this or
   // on a peer GPU)
   uint8_t* ext_rgb = nullptr;
@@ -263,6 +269,7 @@ int hc_engine_set_option(hc_engine* e, const char* name, int value) {
   if (!strcmp(name, "device_parse")) { e->device_parse = value; return HC_OK; }
   if (!strcmp(name, "k0_max_critical_ctbs")) { e->k0_max_critical = value < 1 ? 1 : value; return HC_OK; }
   if (!strcmp(name, "host_share_pct")) { e->host_share_pct = value < 0 ? -1 : (value > 100 ? 100 : value); return HC_OK; }
+  if (!strcmp(name, "premultiply_alpha")) { e->premultiply_alpha = value != 0; return HC_OK; }
   if (!strcmp(name, "chroma_upsampling")) {
     if (value != HC_UPSAMPLE_NEAREST && value != HC_UPSAMPLE_BILINEAR) { hc::set_last_error("chroma_upsampling: HC_UPSAMPLE_NEAREST or HC_UPSAMPLE_BILINEAR"); return HC_ERR_ARGUMENT; }
     e->chroma_upsampling = value;
@@ -276,6 +283,7 @@ int hc_engine_get_option(const hc_engine* e, const char* name) {
   if (!strcmp(name, "device_parse")) return e->device_parse;
   if (!strcmp(name, "host_share_pct")) return e->host_share_pct;
   if (!strcmp(name, "chroma_upsampling")) return e->chroma_upsampling;
+  if (!strcmp(name, "premultiply_alpha")) return e->premultiply_alpha;
   if (!strcmp(name, "k0_max_critical_ctbs")) return e->k0_max_critical;
   return 0;
 }
@@ -425,8 +433,8 @@ int hc_batch_upload(hc_batch* b) {
     const int ps = c.bit_depth == 8 ? 1 : 2;
     for (int k = 0; k < 4; k++) {
       if (k == 3 && !c.alpha) continue;
-      c.pw[k] = plane_w(c.w, c.chroma, k);
-      c.ph[k] = plane_h(c.h, c.chroma, k);
+      c.pw[k] = c.overlay ? 0 : plane_w(c.w, c.chroma, k);
+      c.ph[k] = c.overlay ? 0 : plane_h(c.h, c.chroma, k);
       if (c.pw[k] == 0) continue;
       c.stride[k] = (int)(align_up((size_t)(c.pw[k] + 4) * ps, 128) / ps);
       c.off[k] = pool;
@@ -1039,7 +1047,7 @@ int hc_batch_convert_many(hc_batch* b, int n, const int* canvases, const hc_csc_
       return HC_ERR_ARGUMENT;
     }
     Canvas& c = b->canvases[canvases[i]];
-    if (params[i].in_depth != c.bit_depth) { hc::set_last_error("conversion parameters were selected for another bit depth"); return HC_ERR_ARGUMENT; }
+    if (!c.overlay && params[i].in_depth != c.bit_depth) { hc::set_last_error("conversion parameters were selected for another bit depth"); return HC_ERR_ARGUMENT; }
     c.rgb_bpp = bpp_of[params[i].out_format];
     c.rgb_stride = align_up((size_t)((c.ow + 7) & ~7) * c.rgb_bpp, 256);
     if (c.ext_rgb && c.ext_stride < (size_t)((c.ow + 7) & ~7) * c.rgb_bpp) { hc::set_last_error("external RGB target: rows too short for this format"); return HC_ERR_ARGUMENT; }
@@ -1059,11 +1067,36 @@ int hc_batch_convert_many(hc_batch* b, int n, const int* canvases, const hc_csc_
   const uint8_t* P = (const uint8_t*)b->d_planes.p;
   cudaEvent_t e0 = b->eng->take_event(), e1 = b->eng->take_event();
   cudaEventRecord(e0, b->stream);
+  for (int i = 0; i < n; i++) {          // 'iovl' canvases: K7 composes their children (timed with K5)
+    Canvas& c = b->canvases[canvases[i]];
+    if (!c.overlay) continue;
+    hc::OverlayArgs oa;
+    memset(&oa, 0, sizeof(oa));
+    oa.n = (int)c.children.size();
+    for (int k = 0; k < oa.n; k++) {
+      const Canvas& ch = b->canvases[c.children[k].canvas];
+      hc::OverlayChild& oc = oa.child[k];
+      oc.y = P + ch.ooff[0]; oc.cb = P + ch.ooff[1]; oc.cr = P + ch.ooff[2]; oc.a = ch.alpha ? P + ch.ooff[3] : nullptr;
+      oc.y_stride = ch.ostride[0]; oc.c_stride = ch.ostride[1]; oc.a_stride = ch.ostride[3];
+      oc.w = ch.ow; oc.h = ch.oh; oc.dx = c.children[k].dx; oc.dy = c.children[k].dy;
+      const hc_csc_params& cp = c.children[k].p;
+      oc.mode = cp.mode; oc.full_range = cp.full_range;
+      oc.r_cr = cp.r_cr; oc.g_cb = cp.g_cb; oc.g_cr = cp.g_cr; oc.b_cb = cp.b_cb;
+    }
+    oa.width = c.w; oa.height = c.h;
+    for (int k = 0; k < 3; k++) oa.bkg[k] = c.bkg[k];
+    oa.out_format = params[i].out_format;
+    oa.out = c.ext_rgb ? c.ext_rgb : (uint8_t*)b->d_rgb.p + c.rgb_off;
+    oa.out_stride = (long long)(c.ext_rgb ? c.ext_stride : c.rgb_stride);
+    hc::launch_k7(oa, b->stream);
+    b->launches += 1;
+    c.converted = true;
+  }
   for (int sixteen = 0; sixteen < 2; sixteen++) {
     hc::CscBatch cb;
     cb.n = 0;
     for (int i = 0; i <= n; i++) {
-      if (i < n && (b->canvases[canvases[i]].bit_depth != 8) == (sixteen != 0)) {
+      if (i < n && !b->canvases[canvases[i]].overlay && (b->canvases[canvases[i]].bit_depth != 8) == (sixteen != 0)) {
         Canvas& c = b->canvases[canvases[i]];
         hc::CscArgs& a = cb.a[cb.n++];
         a.y = P + c.ooff[0];
@@ -1186,6 +1219,34 @@ int hc_batch_read_rgb_async(hc_batch* b, int canvas, void* dst, size_t dst_strid
   cudaError_t e = cudaMemcpy2DAsync(dst, dst_stride, (const uint8_t*)b->d_rgb.p + c.rgb_off, c.rgb_stride, (size_t)c.ow * c.rgb_bpp, c.oh,
                                     cudaMemcpyDeviceToHost, b->stream);
   return cuda_ok(e, "cudaMemcpy2DAsync(D2H rgb)") ? HC_OK : HC_ERR_CUDA;
+}
+
+int hc_batch_add_overlay_canvas(hc_batch* b, int width, int height, const uint16_t background[4]) {
+  if (!b || width <= 0 || height <= 0 || !background) { hc::set_last_error("hc_batch_add_overlay_canvas: bad argument"); return HC_ERR_ARGUMENT; }
+  Canvas c;
+  c.w = c.ow = width; c.h = c.oh = height; c.chroma = 3; c.bit_depth = 8; c.alpha = false;
+  c.overlay = true;
+  for (int k = 0; k < 3; k++) c.bkg[k] = background[k] >> 8;      // fill_RGB_16bit keeps the high byte (pixelimage.cc:983)
+  b->canvases.push_back(c);
+  b->uploaded = false;
+  return (int)b->canvases.size() - 1;
+}
+
+int hc_batch_overlay_add_child(hc_batch* b, int overlay_canvas, int child_canvas, int dx, int dy, const hc_csc_params* child_params) {
+  if (!b || !child_params || overlay_canvas < 0 || overlay_canvas >= (int)b->canvases.size() || child_canvas < 0 ||
+      child_canvas >= (int)b->canvases.size() || !b->canvases[overlay_canvas].overlay || b->canvases[child_canvas].overlay) {
+    hc::set_last_error("hc_batch_overlay_add_child: bad argument");
+    return HC_ERR_ARGUMENT;
+  }
+  Canvas& o = b->canvases[overlay_canvas];
+  const Canvas& c = b->canvases[child_canvas];
+  // the reference converts every child to planar RGB 4:4:4 before overlaying and only finds a pipeline for 4:4:4 input
+  // (context.cc:2650-2654 -> "Unsupported color conversion"); its canvas is 8 bit (context.cc:2629-2631)
+  if (c.chroma != 3 || c.bit_depth != 8) { hc::set_last_error("Unsupported color conversion: overlay children must be 8-bit 4:4:4 images"); return HC_ERR_UNSUPPORTED; }
+  if (dx < 0 || dy < 0) { hc::set_last_error("overlay children with negative offsets are not supported"); return HC_ERR_UNSUPPORTED; }
+  if ((int)o.children.size() >= hc::OVERLAY_MAX) { hc::set_last_error("too many overlay children"); return HC_ERR_UNSUPPORTED; }
+  o.children.push_back({child_canvas, dx, dy, *child_params});
+  return HC_OK;
 }
 
 int hc_batch_set_rgb_target(hc_batch* b, int canvas, void* device_dst, size_t stride_bytes) {

@@ -106,6 +106,11 @@ struct ImagePlan {
   int canvas = -1;
   hc_image_desc desc{};
   hc_csc_params csc{};
+  // 'iovl' derived image: its children are decoded on canvases of their own (hc_heic_job::children) and composed by K7
+  bool overlay = false;
+  uint16_t background[4] = {0, 0, 0, 0};
+  std::vector<int> child_plans;                          // indices into hc_heic_job::children
+  std::vector<std::pair<int32_t, int32_t>> child_offsets;
 };
 
 int add_item(hc_batch* b, const CodedItem& ci, int canvas, int x, int y, int role, int rescale) {
@@ -120,6 +125,7 @@ struct hc_heic_job {
   std::vector<std::unique_ptr<hc::HeifFile>> files;
   std::vector<CodedItem> items;
   std::vector<ImagePlan> images;
+  std::vector<ImagePlan> children;      // images that are only decoded as input of an overlay image
   double parse_seconds = 0;
   bool want_alpha = false;
   int forced_format = -1;   // HC_OUT_* for every image, or -1: by bit depth
@@ -157,16 +163,13 @@ static hc_heic_job* job_create_impl(hc_engine* e, int nfiles, const uint8_t* con
   // ---- containers: which coded items does every image need? ----
   j->files.resize(nfiles);
   j->images.resize(nfiles);
-  for (int f = 0; f < nfiles; f++) {
-    j->files[f].reset(new hc::HeifFile);
-    std::string err = j->files[f]->parse(data[f], sizes[f]);
-    if (!err.empty()) { hc::set_last_error("file " + std::to_string(f) + ": " + err); return nullptr; }
+  // which coded items does image item `id` of file f need? (a single picture, the tiles of a grid, an alpha image)
+  auto plan_image = [&](int f, uint32_t id, ImagePlan& im) -> bool {
     hc::HeifFile& hf = *j->files[f];
-    ImagePlan& im = j->images[f];
+    std::string err;
     im.file = f;
-    const uint32_t id = hf.primary_id();
     const hc::HeifItem* it = hf.item(id);
-    if (!it) { hc::set_last_error("file " + std::to_string(f) + ": no primary item"); return nullptr; }
+    if (!it) { hc::set_last_error("file " + std::to_string(f) + ": no such image item"); return false; }
     im.info.id = id;
     im.info.rows = im.info.cols = 1;
     im.info.width = it->ispe_w;
@@ -181,26 +184,26 @@ static hc_heic_job* job_create_impl(hc_engine* e, int nfiles, const uint8_t* con
     if (hf.is_grid(id)) {
       hc::HeifGrid g;
       err = hf.grid(id, g);
-      if (!err.empty()) { hc::set_last_error("file " + std::to_string(f) + ": " + err); return nullptr; }
+      if (!err.empty()) { hc::set_last_error("file " + std::to_string(f) + ": " + err); return false; }
       im.info.is_grid = 1;
       im.info.rows = g.rows; im.info.cols = g.cols; im.info.width = g.out_w; im.info.height = g.out_h;
       // the reference's security limit (context.cc:547-560 check_resolution, heif_limits.h:37-38)
       if (g.out_w <= 0 || g.out_h <= 0 || (uint64_t)g.out_w * (uint64_t)g.out_h > (uint64_t)32768 * 32768) {
         hc::set_last_error("file " + std::to_string(f) + ": grid output size exceeds the maximum image size");
-        return nullptr;
+        return false;
       }
       ids = g.tiles;
       if (band_end >= 0) {
-        if (band_begin < 0 || band_begin >= band_end || band_end > g.rows) { hc::set_last_error("tile row band outside the grid"); return nullptr; }
+        if (band_begin < 0 || band_begin >= band_end || band_end > g.rows) { hc::set_last_error("tile row band outside the grid"); return false; }
         ids.assign(g.tiles.begin() + (size_t)band_begin * g.cols, g.tiles.begin() + (size_t)band_end * g.cols);
         im.band_first_row = band_begin;
         im.info.rows = band_end - band_begin;
       }
     } else {
-      if (band_end >= 0) { hc::set_last_error("a tile row band needs a grid image"); return nullptr; }
+      if (band_end >= 0) { hc::set_last_error("a tile row band needs a grid image"); return false; }
       ids.push_back(id);
     }
-    if (band_end >= 0 && im.info.alpha_id) { hc::set_last_error("banded decode of images with an alpha plane is not supported"); return nullptr; }
+    if (band_end >= 0 && im.info.alpha_id) { hc::set_last_error("banded decode of images with an alpha plane is not supported"); return false; }
     for (uint32_t t : ids) {
       im.tiles.push_back((int)j->items.size());
       j->items.emplace_back();
@@ -208,12 +211,47 @@ static hc_heic_job* job_create_impl(hc_engine* e, int nfiles, const uint8_t* con
       j->items.back().item_id = t;
     }
     if (im.info.alpha_id) {
-      if (hf.is_grid(im.info.alpha_id)) { hc::set_last_error("grid-coded alpha images are not supported"); return nullptr; }
+      if (hf.is_grid(im.info.alpha_id)) { hc::set_last_error("grid-coded alpha images are not supported"); return false; }
       im.alpha = (int)j->items.size();
       j->items.emplace_back();
       j->items.back().file = f;
       j->items.back().item_id = im.info.alpha_id;
     }
+    return true;
+  };
+  for (int f = 0; f < nfiles; f++) {
+    j->files[f].reset(new hc::HeifFile);
+    std::string err = j->files[f]->parse(data[f], sizes[f]);
+    if (!err.empty()) { hc::set_last_error("file " + std::to_string(f) + ": " + err); return nullptr; }
+    hc::HeifFile& hf = *j->files[f];
+    ImagePlan& im = j->images[f];
+    const uint32_t id = hf.primary_id();
+    if (hf.is_overlay(id)) {
+      // 'iovl' (context.cc:2579-2675): every referenced image is decoded like a top-level image, then composed
+      if (band_end >= 0) { hc::set_last_error("a tile row band needs a grid image"); return nullptr; }
+      hc::HeifOverlay ov;
+      err = hf.overlay(id, ov);
+      if (!err.empty()) { hc::set_last_error("file " + std::to_string(f) + ": " + err); return nullptr; }
+      if (ov.children.size() != ov.offsets.size()) { hc::set_last_error("Number of image offsets does not match the number of image references"); return nullptr; }
+      const hc::HeifItem* oit = hf.item(id);
+      if (oit && !oit->xforms.empty()) { hc::set_last_error("transformations on overlay images are not supported"); return nullptr; }
+      im.file = f;
+      im.overlay = true;
+      im.info.id = id;
+      im.info.rows = im.info.cols = 1;
+      im.info.width = ov.canvas_w; im.info.height = ov.canvas_h;
+      for (int k = 0; k < 4; k++) im.background[k] = ov.background[k];
+      im.child_offsets = ov.offsets;
+      for (uint32_t cid : ov.children) {
+        ImagePlan child;
+        if (hf.is_overlay(cid)) { hc::set_last_error("nested overlay images are not supported"); return nullptr; }
+        if (!plan_image(f, cid, child)) return nullptr;
+        im.child_plans.push_back((int)j->children.size());
+        j->children.push_back(child);
+      }
+      continue;
+    }
+    if (!plan_image(f, id, im)) return nullptr;
   }
 
   const double t_containers = now_s();
@@ -309,7 +347,9 @@ static hc_heic_job* job_create_impl(hc_engine* e, int nfiles, const uint8_t* con
   // ---- batch placement ----
   j->batch = hc_batch_create(e);
   if (!j->batch) return nullptr;
-  for (ImagePlan& im : j->images) {
+  // one image item -> canvas, pictures, transformation passes, colour conversion parameters (`fmt_override` >= 0: the
+  // conversion parameters are selected for that output format, used for overlay children)
+  auto place_image = [&](ImagePlan& im, int fmt_override) -> bool {
     const hc_pic& p0 = j->items[im.tiles[0]].pic();
     const bool has_alpha = im.alpha >= 0;
     int W = im.info.width, H = im.info.height;
@@ -317,11 +357,11 @@ static hc_heic_job* job_create_impl(hc_engine* e, int nfiles, const uint8_t* con
     im.full_height = H;
     if (im.info.is_grid && band_end >= 0) {                     // this job owns output rows [y0, y0 + H)
       im.band_y0 = im.band_first_row * p0.crop_h;
-      if (im.band_y0 >= H) { hc::set_last_error("tile row band lies below the output image"); return nullptr; }
+      if (im.band_y0 >= H) { hc::set_last_error("tile row band lies below the output image"); return false; }
       H = std::min(H, band_end * p0.crop_h) - im.band_y0;
     }
     im.canvas = hc_batch_add_canvas(j->batch, W, H, p0.chroma_format, p0.bit_depth_y, has_alpha);
-    if (im.canvas < 0) return nullptr;
+    if (im.canvas < 0) return false;
     int matrix, primaries, full;
     if (im.info.is_grid) {
       const int tw = p0.crop_w, th = p0.crop_h;
@@ -331,24 +371,24 @@ static hc_heic_job* job_create_impl(hc_engine* e, int nfiles, const uint8_t* con
         const hc::HeifItem* tit = j->files[im.file]->item(ci.item_id);
         // context.cc:2328-2337: every tile has the size of the first one ("Grid tiles have different sizes"); tiles of another
         // chroma format or bit depth cannot share a canvas (the reference fails in its paste, context.cc:2452-2465)
-        if (p.crop_w != tw || p.crop_h != th) { hc::set_last_error("Grid tiles have different sizes"); return nullptr; }
-        if (p.chroma_format != p0.chroma_format || p.bit_depth_y != p0.bit_depth_y) { hc::set_last_error("grid tiles differ in chroma format or bit depth"); return nullptr; }
+        if (p.crop_w != tw || p.crop_h != th) { hc::set_last_error("Grid tiles have different sizes"); return false; }
+        if (p.chroma_format != p0.chroma_format || p.bit_depth_y != p0.bit_depth_y) { hc::set_last_error("grid tiles differ in chroma format or bit depth"); return false; }
         // the reference decodes every tile through decode_image_planar, which applies the tile item's own irot / imir / clap
         // (context.cc:1955-2016) before the paste; that combination is not built here
-        if (tit && !tit->xforms.empty()) { hc::set_last_error("transformations on grid tile items are not supported"); return nullptr; }
+        if (tit && !tit->xforms.empty()) { hc::set_last_error("transformations on grid tile items are not supported"); return false; }
         const int tfull = tit && tit->nclx.present ? tit->nclx.full_range : p.full_range;
         const int tmatrix = tit && tit->nclx.present ? tit->nclx.matrix : p.matrix_coeffs;
         const int x0 = (int)(k % im.info.cols) * tw, y0 = (int)(k / im.info.cols) * th;
-        if (x0 >= W || y0 >= H) { hc::set_last_error("grid tile lies outside the output image"); return nullptr; }
+        if (x0 >= W || y0 >= H) { hc::set_last_error("grid tile lies outside the output image"); return false; }
         // context.cc:2504: limited-range tiles (matrix != 0) are expanded to full range while pasting
-        if (add_item(j->batch, ci, im.canvas, x0, y0, HC_ROLE_COLOUR, (!tfull && tmatrix != 0) ? 1 : 0) < 0) return nullptr;
+        if (add_item(j->batch, ci, im.canvas, x0, y0, HC_ROLE_COLOUR, (!tfull && tmatrix != 0) ? 1 : 0) < 0) return false;
       }
       // the canvas only has an nclx if the grid item itself carries one (context.cc:1841-1844)
       matrix = im.info.nclx_present ? im.info.matrix : 2;
       primaries = im.info.nclx_present ? im.info.primaries : 2;
       full = im.info.nclx_present ? im.info.full_range : 1;
     } else {
-      if (add_item(j->batch, j->items[im.tiles[0]], im.canvas, 0, 0, HC_ROLE_COLOUR, 0) < 0) return nullptr;
+      if (add_item(j->batch, j->items[im.tiles[0]], im.canvas, 0, 0, HC_ROLE_COLOUR, 0) < 0) return false;
       matrix = im.info.nclx_present ? im.info.matrix : p0.matrix_coeffs;
       primaries = im.info.nclx_present ? im.info.primaries : p0.colour_primaries;
       full = im.info.nclx_present ? im.info.full_range : p0.full_range;
@@ -410,30 +450,70 @@ static hc_heic_job* job_create_impl(hc_engine* e, int nfiles, const uint8_t* con
         same = false;
       }
       alpha_separate = !same;
-      if (!alpha_separate && add_item(j->batch, j->items[im.alpha], im.canvas, 0, 0, HC_ROLE_ALPHA, 0) < 0) return nullptr;
+      if (!alpha_separate && add_item(j->batch, j->items[im.alpha], im.canvas, 0, 0, HC_ROLE_ALPHA, 0) < 0) return false;
     }
     {
       bool any = false;
-      if (!apply_xforms(im.canvas, pit, W, H, p0.chroma_format, p0.bit_depth_y, any)) return nullptr;
-      if (any && band_end >= 0) { hc::set_last_error("banded decode of transformed images is not supported"); return nullptr; }
+      if (!apply_xforms(im.canvas, pit, W, H, p0.chroma_format, p0.bit_depth_y, any)) return false;
+      if (any && band_end >= 0) { hc::set_last_error("banded decode of transformed images is not supported"); return false; }
     }
     if (alpha_separate) {
       const hc_pic& pa = j->items[im.alpha].pic();
       int Wa = pa.crop_w, Ha = pa.crop_h;
       const int ac = hc_batch_add_canvas(j->batch, Wa, Ha, 0, pa.bit_depth_y, 0);
-      if (ac < 0) return nullptr;
-      if (add_item(j->batch, j->items[im.alpha], ac, 0, 0, HC_ROLE_LUMA, 0) < 0) return nullptr;
+      if (ac < 0) return false;
+      if (add_item(j->batch, j->items[im.alpha], ac, 0, 0, HC_ROLE_LUMA, 0) < 0) return false;
       bool any = false;
-      if (!apply_xforms(ac, ait, Wa, Ha, 0, pa.bit_depth_y, any)) return nullptr;
-      if (hc_batch_link_alpha(j->batch, im.canvas, ac) != HC_OK) return nullptr;
+      if (!apply_xforms(ac, ait, Wa, Ha, 0, pa.bit_depth_y, any)) return false;
+      if (hc_batch_link_alpha(j->batch, im.canvas, ac) != HC_OK) return false;
     }
     const bool hdr = p0.bit_depth_y != 8;
-    const int fmt = j->forced_format >= 0 ? j->forced_format : (hdr ? (j->want_alpha ? HC_OUT_RRGGBBAA_LE : HC_OUT_RRGGBB_LE) : (j->want_alpha ? HC_OUT_RGBA : HC_OUT_RGB));
-    if (hc_csc_select_opt(matrix, primaries, full, p0.chroma_format, p0.bit_depth_y, has_alpha, fmt, hc_engine_get_option(e, "chroma_upsampling"), &im.csc) != HC_OK) return nullptr;
+    const int fmt = fmt_override >= 0 ? fmt_override : j->forced_format >= 0 ? j->forced_format : (hdr ? (j->want_alpha ? HC_OUT_RRGGBBAA_LE : HC_OUT_RRGGBB_LE) : (j->want_alpha ? HC_OUT_RGBA : HC_OUT_RGB));
+    if (hc_csc_select_opt(matrix, primaries, full, p0.chroma_format, p0.bit_depth_y, has_alpha, fmt, hc_engine_get_option(e, "chroma_upsampling"), &im.csc) != HC_OK) return false;
     static const int bpp_of[6] = {3, 4, 6, 8, 6, 8};
     im.desc.width = W; im.desc.height = H; im.desc.chroma_format = p0.chroma_format; im.desc.bit_depth = p0.bit_depth_y;
     im.desc.has_alpha = has_alpha; im.desc.out_format = fmt; im.desc.bytes_per_pixel = bpp_of[fmt];
     im.desc.coded_pictures = (int)im.tiles.size() + (has_alpha ? 1 : 0);
+    // premultiplied alpha: a flag the file sets ('prem' reference, context.cc:1150-1161, :2074-2075) — or the result of
+    // heif_image_rgba_premultiply_alpha (heif.cc:1444-1490), which only takes interleaved RGBA that is not premultiplied yet
+    im.desc.premultiplied_alpha = has_alpha && j->files[im.file]->premultiplied(im.info.id) ? 1 : 0;
+    if (hc_engine_get_option(e, "premultiply_alpha") && fmt == HC_OUT_RGBA && !im.desc.premultiplied_alpha) {
+      im.csc.premultiply = 1;
+      im.desc.premultiplied_alpha = 1;
+    }
+    return true;
+  };
+  for (ImagePlan& im : j->images) {
+    if (!im.overlay) {
+      if (!place_image(im, -1)) return nullptr;
+      continue;
+    }
+    // 'iovl': children first (each on its own canvas, converted like Op_YCbCr_to_RGB<uint8_t> would), then the overlay canvas
+    im.canvas = -1;
+    std::vector<int> child_canvases;
+    for (int ci : im.child_plans) {
+      ImagePlan& ch = j->children[ci];
+      if (!place_image(ch, HC_OUT_RGB)) return nullptr;
+      if (ch.desc.bit_depth != 8 || ch.desc.chroma_format != 3) {   // context.cc:2650-2654: the only children the reference converts
+        hc::set_last_error("Unsupported color conversion: the reference only composes overlays of 8-bit 4:4:4 images");
+        return nullptr;
+      }
+      child_canvases.push_back(ch.canvas);
+    }
+    im.canvas = hc_batch_add_overlay_canvas(j->batch, im.info.width, im.info.height, im.background);
+    if (im.canvas < 0) return nullptr;
+    for (size_t k = 0; k < child_canvases.size(); k++) {
+      const ImagePlan& ch = j->children[im.child_plans[k]];
+      if (hc_batch_overlay_add_child(j->batch, im.canvas, child_canvases[k], im.child_offsets[k].first, im.child_offsets[k].second, &ch.csc) != HC_OK) return nullptr;
+    }
+    const int fmt = j->forced_format >= 0 ? j->forced_format : (j->want_alpha ? HC_OUT_RGBA : HC_OUT_RGB);
+    static const int bpp_of_fmt[6] = {3, 4, 6, 8, 6, 8};
+    memset(&im.csc, 0, sizeof(im.csc));
+    im.csc.out_format = fmt;
+    im.desc.width = im.info.width; im.desc.height = im.info.height; im.desc.chroma_format = 3; im.desc.bit_depth = 8;
+    im.desc.has_alpha = 0; im.desc.out_format = fmt; im.desc.bytes_per_pixel = bpp_of_fmt[fmt];
+    im.desc.coded_pictures = 0;
+    for (int ci : im.child_plans) im.desc.coded_pictures += j->children[ci].desc.coded_pictures;
   }
   if (trace_on())
     fprintf(stderr, "[heifcuda] job_create: %d files, %zu items: containers %.2f ms, parse/prepare %.2f ms (%d threads), placement %.2f ms\n", nfiles,

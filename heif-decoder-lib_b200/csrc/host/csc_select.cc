@@ -80,6 +80,7 @@ extern "C" int hc_csc_select_opt(int matrix, int primaries, int full_range, int 
   p.full_range = full_range ? 1 : 0;
   p.in_depth = bit_depth;
   p.upsampling = HC_UPSAMPLE_NEAREST;
+  p.premultiply = 0;
   const bool bilinear = upsampling == HC_UPSAMPLE_BILINEAR && (chroma_format == 1 || chroma_format == 2);
   if (upsampling == HC_UPSAMPLE_BILINEAR && chroma_format == 0 && out_format != HC_OUT_RGB && out_format != HC_OUT_RGBA) {
     hc::set_last_error("monochrome images to RRGGBB(AA) with the bilinear-only option are not supported");

@@ -330,6 +330,44 @@ std::string HeifFile::grid(uint32_t id, HeifGrid& g) const {
   return "";
 }
 
+bool HeifFile::is_overlay(uint32_t id) const {
+  const HeifItem* it = item(id);
+  return it && it->type == fourcc("iovl");
+}
+
+std::string HeifFile::overlay(uint32_t id, HeifOverlay& o) const {
+  const HeifItem* it = item(id);
+  if (!it || it->type != fourcc("iovl")) return "not an overlay item";
+  std::vector<uint8_t> d;
+  std::string e = read_item_data(*it, d);
+  if (!e.empty()) return e;
+  o = HeifOverlay();
+  for (auto& r : refs_)
+    if (r.from == id && r.type == fourcc("dimg")) o.children = r.to;
+  if (d.size() < 2 + 4 * 2) return "Overlay image data incomplete";
+  if (d[0] != 0) return "Overlay image data version " + std::to_string((int)d[0]) + " is not implemented yet";
+  const size_t fl = (d[1] & 1) ? 4 : 2;
+  if (2 + 4 * 2 + 2 * fl + o.children.size() * 2 * fl > d.size()) return "Overlay image data incomplete";
+  size_t p = 2;
+  auto rd = [&](size_t n) { uint32_t v = 0; for (size_t k = 0; k < n; k++) v = (v << 8) | d[p++]; return v; };
+  for (int k = 0; k < 4; k++) o.background[k] = (uint16_t)rd(2);
+  const uint32_t w = rd(fl), h = rd(fl);
+  if (w == 0 || h == 0) return "Overlay image with zero width or height.";
+  if (w > 0x7fffffffu || h > 0x7fffffffu || (uint64_t)w * h > (uint64_t)32768 * 32768) return "overlay canvas exceeds the maximum image size";
+  o.canvas_w = (int)w; o.canvas_h = (int)h;
+  for (size_t k = 0; k < o.children.size(); k++) {
+    const uint32_t x = rd(fl), y = rd(fl);
+    o.offsets.push_back({fl == 2 ? (int32_t)(int16_t)x : (int32_t)x, fl == 2 ? (int32_t)(int16_t)y : (int32_t)y});
+  }
+  return "";
+}
+
+bool HeifFile::premultiplied(uint32_t id) const {
+  for (auto& r : refs_)
+    if (r.type == fourcc("prem") && r.from == id) return true;
+  return false;
+}
+
 uint32_t HeifFile::alpha_item(uint32_t id) const {
   for (auto& r : refs_) {
     if (r.type != fourcc("auxl")) continue;

@@ -58,6 +58,14 @@ struct HeifGrid {
   std::vector<uint32_t> tiles;  // item ids, row-major
 };
 
+// 'iovl' derived image item (ISO/IEC 23008-12 6.6.2.2; libheif ImageOverlay::parse, context.cc:318-369)
+struct HeifOverlay {
+  int canvas_w = 0, canvas_h = 0;
+  uint16_t background[4] = {0, 0, 0, 0};   // R, G, B, A, 16 bit each
+  std::vector<uint32_t> children;          // 'dimg' references, bottom first
+  std::vector<std::pair<int32_t, int32_t>> offsets;
+};
+
 class HeifFile {
  public:
   // Parses the box structure. `data` must stay valid while the object is used.
@@ -69,8 +77,12 @@ class HeifFile {
   std::vector<uint32_t> top_level_images() const;
   bool is_grid(uint32_t id) const;
   std::string grid(uint32_t id, HeifGrid& g) const;
+  bool is_overlay(uint32_t id) const;
+  std::string overlay(uint32_t id, HeifOverlay& o) const;
   // alpha auxiliary image item of `id`, or 0
   uint32_t alpha_item(uint32_t id) const;
+  // a 'prem' item reference from the colour image: its samples are stored premultiplied by alpha (context.cc:1150-1161)
+  bool premultiplied(uint32_t id) const;
   // hvcC parameter sets followed by the item's coded data, every NAL prefixed by a 4-byte
   // big-endian length: exactly what libheif passes to heif_decoder_plugin::push_data
   // (file.cc:1496-1536, codecs/hevc.cc:226-247).

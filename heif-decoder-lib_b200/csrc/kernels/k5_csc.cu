@@ -240,6 +240,14 @@ __device__ __forceinline__ void csc_unit(const CscArgs& a, unsigned tid) {
 #pragma unroll
     for (int k = 0; k < 8; k++) A[k] = (1 << outd) - 1;
   }
+  if (a.p.premultiply && fmt == HC_OUT_RGBA) {   // heif_image_rgba_premultiply_alpha, PREMULTI_PIXEL (pixelimage.cc:896-900)
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      R[k] = (R[k] * A[k] + 128) >> 8;
+      G[k] = (G[k] * A[k] + 128) >> 8;
+      B[k] = (B[k] * A[k] + 128) >> 8;
+    }
+  }
 
   uint8_t* orow = a.out + (size_t)y * a.out_stride;
   if (fmt == HC_OUT_RGB) {
@@ -369,7 +377,7 @@ __global__ void __launch_bounds__(256) k5_int420_rgb24_kernel(CscBatch b) {
 
 static bool k5_fast_path(const CscArgs& a, bool sixteen_bit) {
   return !sixteen_bit && a.chroma_format == 1 && a.p.mode == HC_CSC_INT420 && a.p.out_format == HC_OUT_RGB && a.a == nullptr &&
-         a.p.pre_op == HC_DEPTH_NONE && a.p.post_op == HC_DEPTH_NONE && a.p.upsampling == HC_UPSAMPLE_NEAREST &&
+         a.p.pre_op == HC_DEPTH_NONE && a.p.post_op == HC_DEPTH_NONE && a.p.upsampling == HC_UPSAMPLE_NEAREST && !a.p.premultiply &&
          (a.width & 7) == 0 && (a.height & 1) == 0 && (a.y_stride & 7) == 0 && (a.c_stride & 3) == 0 &&
          (reinterpret_cast<uintptr_t>(a.y) & 7) == 0 && (reinterpret_cast<uintptr_t>(a.cb) & 3) == 0 && (reinterpret_cast<uintptr_t>(a.cr) & 3) == 0 &&
          (a.out_stride & 7) == 0 && (reinterpret_cast<uintptr_t>(a.out) & 7) == 0;

@@ -32,6 +32,26 @@ struct XformArgs {
   int swap, flip_x, flip_y;
 };
 
+// K7: one 'iovl' derived image composed from up to OVERLAY_MAX child canvases (8-bit 4:4:4, optional alpha plane)
+constexpr int OVERLAY_MAX = 16;
+struct OverlayChild {
+  const uint8_t* y; const uint8_t* cb; const uint8_t* cr; const uint8_t* a;
+  int y_stride, c_stride, a_stride;
+  int w, h, dx, dy;
+  int mode, full_range;            // HC_CSC_FLOAT / GBR / YCGCO of Op_YCbCr_to_RGB<uint8_t>
+  float r_cr, g_cb, g_cr, b_cb;
+};
+struct OverlayArgs {
+  OverlayChild child[OVERLAY_MAX];
+  int n;
+  int width, height;
+  int bkg[3];                      // background colour, already reduced to 8 bit
+  int out_format;
+  uint8_t* out;
+  long long out_stride;
+};
+void launch_k7(const OverlayArgs& a, cudaStream_t stream);
+
 namespace k0 { struct Tables; struct Pic; struct Sub; struct Chain; }
 // K0: device CABAC parse of the pictures added as bitstreams (one CTA per substream chain)
 void launch_k0(const k0::Tables* tables, const k0::Pic* pics, const k0::Sub* subs, const k0::Chain* chains, int nchains,

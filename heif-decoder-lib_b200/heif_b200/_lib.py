@@ -36,13 +36,13 @@ class CscParams(C.Structure):
     _fields_ = [("mode", C.c_int32), ("out_format", C.c_int32), ("full_range", C.c_int32), ("bit_depth", C.c_int32),
                 ("r_cr_i", C.c_int32), ("g_cb_i", C.c_int32), ("g_cr_i", C.c_int32), ("b_cb_i", C.c_int32),
                 ("r_cr", C.c_float), ("g_cb", C.c_float), ("g_cr", C.c_float), ("b_cb", C.c_float),
-                ("in_depth", C.c_int32), ("out_depth", C.c_int32), ("pre_op", C.c_int32), ("post_op", C.c_int32), ("upsampling", C.c_int32), ("coeff_matrix", C.c_int32)]
+                ("in_depth", C.c_int32), ("out_depth", C.c_int32), ("pre_op", C.c_int32), ("post_op", C.c_int32), ("premultiply", C.c_int32), ("upsampling", C.c_int32), ("coeff_matrix", C.c_int32)]
 
 
 class ImageDesc(C.Structure):
     """hc_image_desc"""
     _fields_ = [(n, C.c_int32) for n in ("width", "height", "chroma_format", "bit_depth", "has_alpha", "out_format",
-                                           "bytes_per_pixel", "coded_pictures")]
+                                           "bytes_per_pixel", "coded_pictures", "premultiplied_alpha")]
 
 
 class HeifImageInfo(C.Structure):
@@ -51,7 +51,13 @@ class HeifImageInfo(C.Structure):
                 ("rows", C.c_int32), ("cols", C.c_int32), ("alpha_id", C.c_uint32), ("rot", C.c_int32),
                 ("mirror", C.c_int32), ("nclx_present", C.c_int32), ("primaries", C.c_int32),
                 ("transfer", C.c_int32), ("matrix", C.c_int32), ("full_range", C.c_int32), ("n_transforms", C.c_int32), ("transforms", C.c_uint8 * 8),
-                ("has_clap", C.c_int32), ("claps", (C.c_uint32 * 8) * 4)]
+                ("has_clap", C.c_int32), ("claps", (C.c_uint32 * 8) * 4), ("premultiplied_alpha", C.c_int32)]
+
+
+class HeifOverlayInfo(C.Structure):
+    """hc_heif_overlay_info"""
+    _fields_ = [("canvas_w", C.c_int32), ("canvas_h", C.c_int32), ("background", C.c_uint16 * 4), ("n", C.c_int32),
+                ("children", C.c_uint32 * 16), ("dx", C.c_int32 * 16), ("dy", C.c_int32 * 16)]
 
 
 class StreamStats(C.Structure):
@@ -100,6 +106,7 @@ SYMBOLS = [
     ("hc_heif_primary_id", _u32, [_vp]),
     ("hc_heif_top_level_ids", _i, [_vp, C.POINTER(_u32), _i]),
     ("hc_heif_get_image_info", _i, [_vp, _u32, C.POINTER(HeifImageInfo)]),
+    ("hc_heif_get_overlay", _i, [_vp, _u32, C.POINTER(HeifOverlayInfo)]),
     ("hc_heif_grid_tiles", _i, [_vp, _u32, C.POINTER(_u32), _i]),
     ("hc_heif_coded_stream", _i, [_vp, _u32, C.POINTER(_vp), C.POINTER(_sz)]),
     ("hc_free", None, [_vp]),
@@ -140,6 +147,8 @@ SYMBOLS = [
     ("hc_heic_job_copy_rgb_device", _i, [_vp, _i, _vp, _sz]),
     ("hc_heic_job_set_rgb_target", _i, [_vp, _i, _vp, _i]),
     ("hc_batch_set_rgb_target", _i, [_vp, _i, _vp, _sz]),
+    ("hc_batch_add_overlay_canvas", _i, [_vp, _i, _i, C.POINTER(C.c_uint16)]),
+    ("hc_batch_overlay_add_child", _i, [_vp, _i, _i, _i, _i, C.POINTER(CscParams)]),
     ("hc_shared_image_create", _vp, [_vp, _i, _i, _i]),
     ("hc_shared_image_export", _i, [_vp, C.POINTER(C.c_uint8)]),
     ("hc_shared_image_open", _vp, [_vp, C.POINTER(C.c_uint8), _i, _i, _i]),

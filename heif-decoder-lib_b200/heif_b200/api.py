@@ -120,6 +120,13 @@ class HeifFile:
         check(self._L, self._L.hc_heif_get_image_info(self._h, item_id, C.byref(info)), "hc_heif_get_image_info")
         return info
 
+    def overlay(self, item_id):
+        """hc_heif_get_overlay: the 'iovl' description of an overlay item (raises for other items)"""
+        from ._lib import HeifOverlayInfo
+        info = HeifOverlayInfo()
+        check(self._L, self._L.hc_heif_get_overlay(self._h, item_id, C.byref(info)), "hc_heif_get_overlay")
+        return info
+
     def grid_tiles(self, item_id):
         tiles = (C.c_uint32 * 4096)()
         n = check(self._L, self._L.hc_heif_grid_tiles(self._h, item_id, tiles, 4096), "hc_heif_grid_tiles")

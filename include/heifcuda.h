@@ -117,6 +117,7 @@ typedef struct hc_heif_image_info {
   uint8_t transforms[8];       /* HC_XF_*                                                                     */
   int32_t has_clap;            /* number of clean-aperture (clap) properties, consumed in order by HC_XF_CLAP */
   uint32_t claps[4][8];        /* width num/den, height num/den, horizontal offset num/den, vertical offset num/den */
+  int32_t premultiplied_alpha; /* a 'prem' reference marks the colour samples as premultiplied by alpha (context.cc:1150-1161) */
 } hc_heif_image_info;
 #define HC_XF_ROT90 1          /* anti-clockwise quarter turns, HeifPixelImage::rotate_ccw pixelimage.cc:539 */
 #define HC_XF_ROT180 2
@@ -125,12 +126,24 @@ typedef struct hc_heif_image_info {
 #define HC_XF_MIRROR_V 5       /* ..._vertical: row order reversed (:784-789)                                */
 #define HC_XF_CLAP 6           /* clean aperture crop (context.cc:1981-2015)                                  */
 
+/* 'iovl' derived image item (ISO/IEC 23008-12 6.6.2.2; libheif ImageOverlay, context.cc:285-369) */
+#define HC_OVERLAY_MAX_CHILDREN 16
+typedef struct hc_heif_overlay_info {
+  int32_t canvas_w, canvas_h;
+  uint16_t background[4];      /* R, G, B, A, 16 bit each */
+  int32_t n;                   /* referenced images ('dimg'), composed in this order */
+  uint32_t children[HC_OVERLAY_MAX_CHILDREN];
+  int32_t dx[HC_OVERLAY_MAX_CHILDREN], dy[HC_OVERLAY_MAX_CHILDREN];
+} hc_heif_overlay_info;
+
 /* `data` must stay valid until hc_heif_close. NULL + error text on malformed files. */
 hc_heif* hc_heif_open(const uint8_t* data, size_t size);
 void hc_heif_close(hc_heif* f);
 uint32_t hc_heif_primary_id(const hc_heif* f);
 /* writes up to `max` ids, returns the total number of top-level images */
 int hc_heif_top_level_ids(const hc_heif* f, uint32_t* ids, int max);
+/* HC_ERR_ARGUMENT when `id` is not an overlay item */
+int hc_heif_get_overlay(const hc_heif* f, uint32_t id, hc_heif_overlay_info* info);
 int hc_heif_get_image_info(const hc_heif* f, uint32_t id, hc_heif_image_info* info);
 /* row-major tile item ids of a grid; returns rows*cols or a negative error */
 int hc_heif_grid_tiles(const hc_heif* f, uint32_t id, uint32_t* tiles, int max);
@@ -170,6 +183,7 @@ typedef struct hc_csc_params {
   int32_t out_depth;     /* depth of the written channels: 8 for RGB / RGBA, else the input depth (10 for 8-bit input) */
   int32_t pre_op;        /* HC_DEPTH_* applied to Y, Cb, Cr, A as they are loaded                */
   int32_t post_op;       /* HC_DEPTH_* applied to R, G, B, A before they are written             */
+  int32_t premultiply;   /* RGBA 8-bit output only: R, G, B = (v * A + 128) >> 8 (pixelimage.cc:896-941), set by the job */
   int32_t upsampling;    /* HC_UPSAMPLE_*: how 4:2:0 / 4:2:2 chroma is brought to the luma grid                  */
   int32_t coeff_matrix;  /* matrix_coefficients the coefficients were derived from: an unspecified matrix (2) stays 2 —
                             the literal BT.601 defaults — when the matrix op is the first op of the reference's chain and
@@ -213,6 +227,9 @@ void hc_engine_destroy(hc_engine* e);
  * hc_heic_decode_stream a share that follows the measured host / GPU time per batch.
  * "chroma_upsampling" (default HC_UPSAMPLE_NEAREST): HC_UPSAMPLE_BILINEAR makes hc_heic_job / hc_heic_decode_stream convert
  * with bilinear chroma upsampling (see hc_csc_select_opt).
+ * "premultiply_alpha" (default 0): 1 makes hc_heic_job / hc_heic_decode_stream multiply interleaved RGBA 8-bit output by its
+ * alpha like heif_image_rgba_premultiply_alpha (heif.cc:1444-1490, pixelimage.cc:896-941: (v * A + 128) >> 8), fused into K5;
+ * images the file already marks premultiplied ('prem') are left alone, as that call refuses them.
  * "k0_max_critical_ctbs" (default 160): K0 is serial per substream, so hc_heic_job only hands it pictures whose parse
  * critical path is at most this many CTBs (WPP: CTB columns + 2 x (CTB rows - 1); no WPP: all CTBs of the picture);
  * the others stay with the host parser. */
@@ -266,6 +283,14 @@ int hc_batch_add_canvas_pass(hc_batch* b, int canvas, int kind, int a0, int a1, 
  * iy = y * in_h / out_h) as HeifContext::decode_image_planar does for an alpha image whose size differs from the colour
  * image's (context.cc:2064-2071). Both canvases are taken after their own geometric passes. Call before hc_batch_upload. */
 int hc_batch_link_alpha(hc_batch* b, int canvas, int alpha_canvas);
+/* 'iovl' derived image (libheif context.cc:2579-2675): an output canvas without planes of its own. K7 fills it with the
+ * background colour (16-bit R, G, B, A as stored in the item; the reference keeps the high byte of R, G, B) and overlays
+ * the child canvases in the order they are added at (dx, dy) — copied, or alpha-blended when the child canvas has an alpha
+ * plane — and writes the interleaved result (hc_batch_convert_many with this canvas; params[].out_format selects the
+ * format, RGB(A) or RRGGBB(AA) at 10 bit like the reference). child_params: hc_csc_select(..., HC_OUT_RGB) of the child
+ * (Op_YCbCr_to_RGB<uint8_t>). Children must be 8-bit 4:4:4 canvases (the reference converts nothing else) with offsets >= 0. */
+int hc_batch_add_overlay_canvas(hc_batch* b, int width, int height, const uint16_t background[4]);
+int hc_batch_overlay_add_child(hc_batch* b, int overlay_canvas, int child_canvas, int dx, int dy, const hc_csc_params* child_params);
 /* K5 for one canvas into the engine's device RGB buffer, async */
 int hc_batch_convert(hc_batch* b, int canvas, const hc_csc_params* params);
 /* K5 for n canvases (canvases[i] with params[i]) in as few launches as possible, async */
@@ -313,6 +338,8 @@ typedef struct hc_image_desc {
   int32_t out_format;        /* HC_OUT_* of this image (automatic: 8-bit -> RGB/RGBA, else RRGGBB(AA)_LE) */
   int32_t bytes_per_pixel;
   int32_t coded_pictures;    /* HEVC pictures decoded for this image (tiles + alpha)              */
+  int32_t premultiplied_alpha; /* heif_image_is_premultiplied_alpha of the result: the file says so ('prem'), or the engine option
+                                "premultiply_alpha" multiplied the RGBA output (heif_image_rgba_premultiply_alpha) */
 } hc_image_desc;
 
 /* Parses `nfiles` HEIC files held in host memory (the primary image of each) with `threads` host

@@ -92,6 +92,7 @@ def build():
     files["single_422_10_full"] = heif_writer.single_image(enc(200, 120, 2, 10, 73), 200, 120, 2, 10)
     files["single_420_8_matrix12_bt2020"] = heif_writer.single_image(enc(200, 120, 1, 8, 74, matrix=12, primaries=9), 200, 120, 1, 8)
     files["single_444_10_matrix13_bt709"] = heif_writer.single_image(enc(200, 120, 3, 10, 75, matrix=13, primaries=1, full_range=0), 200, 120, 3, 10)
+    files["alpha_prem_420_8"] = heif_writer.single_image(enc(200, 120, 1, 8, 77), 200, 120, 1, 8, alpha_stream=enc(200, 120, 0, 8, 78), premultiplied=True)
     files["single_420_8_gbr"] = heif_writer.single_image(enc(200, 120, 1, 8, 76, matrix=0), 200, 120, 1, 8)
     return files
 
@@ -145,6 +146,12 @@ def main():
     fmts = {}
     for name in sorted(meta):
         fmts[name] = reference_all_formats(open(os.path.join(OUT, name + ".heic"), "rb").read())
+    for name in sorted(meta):        # RGBA run through heif_image_rgba_premultiply_alpha
+        try:
+            data = open(os.path.join(OUT, name + ".heic"), "rb").read()
+            fmts[name]["rgba_premultiplied_md5"] = md5(R.decode(data, R.COLORSPACE_RGB, R.CHROMA_RGBA, premultiply=True)["interleaved"][0])
+        except RuntimeError as e:
+            fmts[name]["rgba_premultiplied_error"] = str(e)
     json.dump(fmts, open(os.path.join(HERE, "heic_formats.json"), "w"), indent=1, sort_keys=True)
     bil = {}
     for name in sorted(meta):

@@ -92,7 +92,7 @@ def plane_bytes(img, channel, bytes_per_px):
     return b"".join(buf[y * stride.value: y * stride.value + row] for y in range(h)), w, h
 
 
-def decode(data, colorspace, chroma, item_id=None, threads=None, decoder_id=None, bilinear=False):
+def decode(data, colorspace, chroma, item_id=None, threads=None, decoder_id=None, bilinear=False, premultiply=False):
     """heif_decode_image on an in-memory HEIC. Returns dict of channel -> (bytes, w, h) plus bpp.
     decoder_id: None = the reference's libde265 plugin; "" = let libheif choose by priority."""
     L = lib()
@@ -132,6 +132,10 @@ def decode(data, colorspace, chroma, item_id=None, threads=None, decoder_id=None
         finally:
             if opts:
                 L.heif_decoding_options_free(opts)
+        if premultiply:      # heif_image_rgba_premultiply_alpha (heif.cc:1444): interleaved RGBA only
+            L.heif_image_rgba_premultiply_alpha.restype = HeifError
+            L.heif_image_rgba_premultiply_alpha.argtypes = [C.c_void_p]
+            _check(L.heif_image_rgba_premultiply_alpha(img), "premultiply")
         out = {"colorspace": L.heif_image_get_colorspace(img), "chroma": L.heif_image_get_chroma_format(img)}
         if chroma in (CHROMA_RGB, CHROMA_RGBA):
             bpp = 3 if chroma == CHROMA_RGB else 4

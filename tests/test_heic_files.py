@@ -55,6 +55,27 @@ def test_oracle_reproduces_reference_in_every_output_format(name):
     assert checked >= 4, FMETA[name]
 
 
+def _premultiply(rgba):
+    """PREMULTI_PIXEL of heif_image_rgba_premultiply_alpha (pixelimage.cc:896-941): (v * A + 128) >> 8 on R, G, B"""
+    px = rgba.reshape(rgba.shape[0], -1, 4).astype(np.uint32)
+    px[:, :, :3] = (px[:, :, :3] * px[:, :, 3:4] + 128) >> 8
+    return px.astype(np.uint8).reshape(rgba.shape)
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_oracle_premultiplied_rgba_matches_reference(name):
+    if "rgba_premultiplied_md5" not in FMETA[name]:
+        pytest.skip(FMETA[name].get("rgba_premultiplied_error", "no golden"))
+    assert md5(_premultiply(heic_oracle.decode_rgb(load(name), hb.OUT_RGBA)).tobytes()) == FMETA[name]["rgba_premultiplied_md5"]
+
+
+def test_prem_reference_is_reported():
+    hf = hb.HeifFile(load("alpha_prem_420_8"), host_only=True)
+    assert hf.image_info(hf.primary_id).premultiplied_alpha == 1
+    hf = hb.HeifFile(load("alpha_420_8"), host_only=True)
+    assert hf.image_info(hf.primary_id).premultiplied_alpha == 0
+
+
 BMETA = json.load(open(os.path.join(ROOT, "tests", "golden", "heic_formats_bilinear.json")))
 
 
@@ -159,6 +180,32 @@ def test_gpu_heic_job_bilinear_chroma_upsampling(engine, key):
     bad = [n for i, n in enumerate(names) if md5(job.read_rgb(i).tobytes()) != BMETA[n][key + "_md5"]]
     job.close()
     assert len(names) >= 35 and not bad, (key, bad)
+
+
+@pytest.mark.gpu
+def test_gpu_heic_job_premultiplied_alpha(engine):
+    """engine option premultiply_alpha: RGBA output multiplied by its alpha in K5, bit-exact with the reference's
+    heif_image_rgba_premultiply_alpha on its RGBA decode; a file that is already premultiplied ('prem') is left alone and
+    reported as such."""
+    names = [n for n in NAMES if "rgba_premultiplied_md5" in FMETA[n]]
+    engine.set_option("premultiply_alpha", 1)
+    try:
+        job = hb.HeicJob(engine, [load(n) for n in names], threads=4, out_format=hb.OUT_RGBA)
+    finally:
+        engine.set_option("premultiply_alpha", 0)
+    job.upload()
+    job.run()
+    bad = []
+    for i, n in enumerate(names):
+        assert job.descs[i].premultiplied_alpha == 1, n
+        want = FMETA[n]["rgba_md5"] if n == "alpha_prem_420_8" else FMETA[n]["rgba_premultiplied_md5"]
+        if md5(job.read_rgb(i).tobytes()) != want:
+            bad.append(n)
+    job.close()
+    assert not bad, bad
+    job = hb.HeicJob(engine, [load("alpha_prem_420_8"), load("alpha_420_8")], threads=2, out_format=hb.OUT_RGBA)
+    assert [d.premultiplied_alpha for d in job.descs] == [1, 0]
+    job.close()
 
 
 @pytest.mark.gpu

@@ -94,10 +94,12 @@ class HeifBuilder:
         self.refs.append((b"dimg", oid, list(child_ids)))
         return oid
 
-    def add_alpha(self, master_id, stream, width, height, chroma_format, bit_depth, extra_props=()):
+    def add_alpha(self, master_id, stream, width, height, chroma_format, bit_depth, extra_props=(), premultiplied=False):
         auxc = fullbox(b"auxC", 0, 0, b"urn:mpeg:hevc:2015:auxid:1\x00")
         aid = self.add_hevc_image(stream, width, height, chroma_format, bit_depth, hidden=True, extra_props=(auxc,) + tuple(extra_props))
         self.refs.append((b"auxl", aid, [master_id]))
+        if premultiplied:       # the colour samples are stored premultiplied by this alpha image (libheif context.cc:1150-1161)
+            self.refs.append((b"prem", master_id, [aid]))
         return aid
 
     def serialize(self):
@@ -156,7 +158,7 @@ def clap(w_num, w_den, h_num, h_den, hoff_num, hoff_den, voff_num, voff_den):
 
 
 def single_image(stream, width, height, chroma_format=1, bit_depth=8, nclx=None, alpha_stream=None, alpha_chroma_format=0,
-                 transforms=(), alpha_size=None, alpha_transforms=None):
+                 transforms=(), alpha_size=None, alpha_transforms=None, premultiplied=False):
     """transforms: property boxes (irot / imir / clap) attached, in this order, to the image and to its alpha image
     (alpha_transforms: the alpha image's own list instead); alpha_size: (width, height) of the alpha image when it
     differs from the colour image's (the reference rescales it by nearest neighbour, context.cc:2064-2071)"""
@@ -165,7 +167,7 @@ def single_image(stream, width, height, chroma_format=1, bit_depth=8, nclx=None,
     if alpha_stream is not None:
         aw, ah = alpha_size if alpha_size else (width, height)
         b.add_alpha(iid, alpha_stream, aw, ah, alpha_chroma_format, bit_depth,
-                    extra_props=tuple(transforms if alpha_transforms is None else alpha_transforms))
+                    extra_props=tuple(transforms if alpha_transforms is None else alpha_transforms), premultiplied=premultiplied)
     b.primary = iid
     return b.serialize()
 
