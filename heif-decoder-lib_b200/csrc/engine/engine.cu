@@ -199,6 +199,7 @@ struct hc_batch {
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> csc_events;
   int launches = 0;
   float last_d2h_ms = 0.f;
+  int pack_threads = 0;     // host threads hc_batch_upload may use to pack the pinned arena (0: hardware concurrency)
 };
 
 namespace {
@@ -622,6 +623,9 @@ int hc_batch_upload(hc_batch* b) {
   if (nk0 && !b->h_status.p) return HC_ERR_MEMORY;
   uint8_t* H = (uint8_t*)b->h_arena.p;
   uint8_t* Dk = (uint8_t*)b->d_arena.p;
+  // the RBSP bytes of the device-parsed pictures (the bulk of such a batch's upload) are copied by the packing threads below
+  struct K0Copy { uint8_t* dst; const uint8_t* src; size_t n; };
+  std::vector<K0Copy> k0_copies;
   // ---- K0 pictures: record bases (element offsets from the uploaded array bases into the device-only zone) + inputs ----
   if (nk0) {
     hc::k0::Pic* kp_out = (hc::k0::Pic*)(H + o_kpics);
@@ -662,7 +666,7 @@ int hc_batch_upload(hc_batch* b) {
       memcpy(ks_out + is, k.slices.data(), sizeof(hc::k0::Slice) * k.slices.size());
       memcpy(kc_out + ic, k.ctb_slice.data(), 4 * k.ctb_slice.size());
       memcpy(kst_out + 4 * ic, k.ctu_static.data(), k.ctu_static.size());
-      memcpy(H + o_kbytes + ib, k.bytes.data(), k.bytes.size());
+      k0_copies.push_back({H + o_kbytes + ib, k.bytes.data(), k.bytes.size()});
       for (size_t t = 0; t < k.subs.size(); t++) { ksub_out[isub + t] = k.subs[t]; ksub_out[isub + t].pic = (uint32_t)q; }
       for (const hc::k0::Chain& c : k.chains) chains.push_back({k.subs[c.first_sub].first_ctb / k.pic.ctbs_w, {(uint32_t)(isub + c.first_sub), c.nsubs}});
       is += k.slices.size(); ic += k.ctb_slice.size(); isub += k.subs.size(); ib += align_up(k.bytes.size(), 16);
@@ -708,15 +712,22 @@ int hc_batch_upload(hc_batch* b) {
     if (!r.scaling.empty()) memcpy(H + o_scal + p.scaling_base, r.scaling.data(), r.scaling.size());
   };
   {
-    int nthreads = (int)std::thread::hardware_concurrency();
-    nthreads = std::max(1, std::min(nthreads, std::min(np, (int)(o >> 22) + 1)));   // ~4 MB of records per thread at least
+    // `pack_threads` comes from the job (its host thread count): several ranks share one box, and a rank that took every
+    // hardware thread for a few milliseconds of memcpy made all of them slower
+    int nthreads = b->pack_threads > 0 ? b->pack_threads : (int)std::thread::hardware_concurrency();
+    const int nwork = np + (int)k0_copies.size();
+    nthreads = std::max(1, std::min(nthreads, std::min(nwork, (int)(o >> 22) + 1)));   // ~4 MB per thread at least
+    auto work = [&](int i) {
+      if (i < np) pack_picture(i);
+      else { const K0Copy& c = k0_copies[i - np]; memcpy(c.dst, c.src, c.n); }
+    };
     if (nthreads == 1) {
-      for (int i = 0; i < np; i++) pack_picture(i);
+      for (int i = 0; i < nwork; i++) work(i);
     } else {
       std::atomic<int> next{0};
       std::vector<std::thread> pool;
       for (int t = 0; t < nthreads; t++)
-        pool.emplace_back([&]() { for (int i; (i = next.fetch_add(1)) < np;) pack_picture(i); });
+        pool.emplace_back([&]() { for (int i; (i = next.fetch_add(1)) < nwork;) work(i); });
       for (auto& t : pool) t.join();
     }
   }
@@ -1308,6 +1319,8 @@ int hc_batch_timer_stop_ms(hc_batch* b, float* ms) {
 int hc_batch_launch_count(const hc_batch* b) { return b ? b->launches : 0; }
 size_t hc_batch_upload_bytes(const hc_batch* b) { return b ? b->arena_bytes : 0; }
 int hc_batch_k0_pictures(const hc_batch* b) { return b ? b->nk0 : 0; }
+// internal (heic_job.cc): host threads hc_batch_upload may use
+void hc_batch_set_pack_threads(hc_batch* b, int n) { if (b) b->pack_threads = n; }
 
 
 // ---- hc_shared_image: one RGB buffer on the owner GPU that the K5 kernels of other GPUs store into ----------------------

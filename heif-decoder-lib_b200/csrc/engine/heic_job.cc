@@ -20,6 +20,8 @@
 #include <vector>
 #include "../capi/capi_internal.h"
 
+extern "C" void hc_batch_set_pack_threads(hc_batch* b, int n);   // engine.cu (internal)
+
 namespace {
 
 // HEIFCUDA_TRACE=1: per-batch phase times of the job / stream pipeline on stderr
@@ -347,6 +349,7 @@ static hc_heic_job* job_create_impl(hc_engine* e, int nfiles, const uint8_t* con
   // ---- batch placement ----
   j->batch = hc_batch_create(e);
   if (!j->batch) return nullptr;
+  hc_batch_set_pack_threads(j->batch, threads > 0 ? threads : 0);
   // one image item -> canvas, pictures, transformation passes, colour conversion parameters (`fmt_override` >= 0: the
   // conversion parameters are selected for that output format, used for overlay children)
   auto place_image = [&](ImagePlan& im, int fmt_override) -> bool {
