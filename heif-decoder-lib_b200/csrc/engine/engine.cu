@@ -55,6 +55,7 @@ struct hc_engine {
   int k0_max_critical = 160;               // hc_heic_job: pictures whose parse critical path exceeds this many CTBs stay with the host parser
   int premultiply_alpha = 0;               // hc_heic_job: RGBA output multiplied by alpha in K5
   int chroma_upsampling = 0;               // HC_UPSAMPLE_*: colour conversion of hc_heic_job / hc_heic_decode_stream
+  bool fused_postfilter = false;           // HEIFCUDA_POSTFILTER=fused: K3+K4 as one shared-memory tile kernel (measured slower: both forms are bound by instruction issue, not HBM — DESIGN.md)
   int host_share_pct = -1;                 // hc_heic_job with device_parse: percentage of the coded items the host threads parse meanwhile
 
   Block take(std::vector<Block>& list, size_t size, bool pinned) {
@@ -191,7 +192,8 @@ struct hc_batch {
   cudaEvent_t ev_k0[2] = {};
   cudaEvent_t ev_d2h[2] = {};
   size_t k0_input_bytes = 0;
-  long long max_dbk_units = 0, max_sao_quads = 0;
+  long long max_dbk_units = 0, max_sao_quads = 0, max_pf_tiles = 0;
+  bool any_16bit = false;   // some picture has samples of more than 8 bits (sizes the fused post-filter's tile)
   int max_planes = 1;
   bool uploaded = false;
   cudaEvent_t ev[8] = {};
@@ -244,6 +246,7 @@ hc_engine* hc_engine_create(int device) {
   cudaDeviceGetAttribute(&eng->sm_count, cudaDevAttrMultiProcessorCount, device);
   cudaDeviceGetStreamPriorityRange(&eng->prio_lo, &eng->prio_hi);   // (least, greatest): greatest is numerically lowest
   if (const char* m = getenv("HEIFCUDA_PARSER")) eng->device_parse = strcmp(m, "host") != 0;
+  if (const char* m = getenv("HEIFCUDA_POSTFILTER")) eng->fused_postfilter = strcmp(m, "fused") == 0;
   if (const char* m = getenv("HEIFCUDA_HOST_SHARE")) eng->host_share_pct = std::max(-1, std::min(100, atoi(m)));
   if (!cuda_ok(cudaMalloc(&eng->d_k0_tables, sizeof(hc::k0::Tables)), "cudaMalloc(K0 tables)") ||
       !cuda_ok(cudaMemcpy(eng->d_k0_tables, &hc::k0_tables(), sizeof(hc::k0::Tables), cudaMemcpyHostToDevice), "cudaMemcpy(K0 tables)")) {
@@ -269,6 +272,7 @@ int hc_engine_set_option(hc_engine* e, const char* name, int value) {
   if (!e || !name) return HC_ERR_ARGUMENT;
   if (!strcmp(name, "device_parse")) { e->device_parse = value; return HC_OK; }
   if (!strcmp(name, "k0_max_critical_ctbs")) { e->k0_max_critical = value < 1 ? 1 : value; return HC_OK; }
+  if (!strcmp(name, "fused_postfilter")) { e->fused_postfilter = value != 0; return HC_OK; }
   if (!strcmp(name, "host_share_pct")) { e->host_share_pct = value < 0 ? -1 : (value > 100 ? 100 : value); return HC_OK; }
   if (!strcmp(name, "premultiply_alpha")) { e->premultiply_alpha = value != 0; return HC_OK; }
   if (!strcmp(name, "chroma_upsampling")) {
@@ -282,6 +286,7 @@ int hc_engine_set_option(hc_engine* e, const char* name, int value) {
 int hc_engine_get_option(const hc_engine* e, const char* name) {
   if (!e || !name) return 0;
   if (!strcmp(name, "device_parse")) return e->device_parse;
+  if (!strcmp(name, "fused_postfilter")) return e->fused_postfilter ? 1 : 0;
   if (!strcmp(name, "host_share_pct")) return e->host_share_pct;
   if (!strcmp(name, "chroma_upsampling")) return e->chroma_upsampling;
   if (!strcmp(name, "premultiply_alpha")) return e->premultiply_alpha;
@@ -483,7 +488,8 @@ int hc_batch_upload(hc_batch* b) {
   std::vector<int> idx_base((size_t)np * 4);   // first slot of picture i in the size-l launch list
   int max_rows = 0;
   size_t n_tasks = 0;
-  b->max_dbk_units = b->max_sao_quads = 0;
+  b->max_dbk_units = b->max_sao_quads = b->max_pf_tiles = 0;
+  b->any_16bit = false;
   b->max_planes = 1;
   b->nk0 = 0;
   b->k0_pic_of.clear();
@@ -519,6 +525,8 @@ int hc_batch_upload(hc_batch* b) {
     b->max_planes = std::max(b->max_planes, ncomp);
     b->max_dbk_units = std::max(b->max_dbk_units, (long long)(p.width >> 3) * (p.height >> 2));
     b->max_sao_quads = std::max(b->max_sao_quads, (long long)p.ctbs_w * p.ctbs_h);   // CTBs: K4 runs one warp per CTB
+    b->max_pf_tiles = std::max(b->max_pf_tiles, (long long)((p.width + 127) / 128) * ((p.height + 63) / 64));
+    if (p.bit_depth_y != 8 || p.bit_depth_c != 8) b->any_16bit = true;
     // reconstruction planes
     const int ps = (p.bit_depth_y == 8 && p.bit_depth_c == 8) ? 1 : 2;
     const int SubW = (p.chroma_format == 1 || p.chroma_format == 2) ? 2 : 1, SubH = p.chroma_format == 1 ? 2 : 1;
@@ -937,16 +945,25 @@ int hc_batch_reconstruct_async(hc_batch* b, int stages) {
   else hc::launch_k2(b->view, b->d_tasks, b->ntasks, b->k2_smem, (int*)b->d_progress.p, b->k2_packed, s);
   b->launches += 1;
   cudaEventRecord(b->ev[4], s);
-  if (stages & HC_STAGE_DEBLOCK) {
-    hc::launch_k3(b->view, b->max_dbk_units, b->max_planes, s);
-    b->launches += 2;
-  }
-  cudaEventRecord(b->ev[5], s);
-  // K4 always runs: it is also the crop + paste pass; SAO parameters are ignored when disabled
+  // K4 (or the fused K3+K4) always runs: it is also the crop + paste pass; SAO parameters are ignored when disabled
   hc::BatchView v = b->view;
   v.flags = (stages & HC_STAGE_SAO) ? 0 : hc::HC_VIEW_NO_SAO;
-  hc::launch_k4(v, b->max_sao_quads, b->max_planes, s);
-  b->launches += 1;
+  if (b->eng->fused_postfilter) {
+    // one tile kernel: deblocking + SAO + crop + paste with the tile in shared memory (k34_postfilter.cu); its time is
+    // reported as the K4 stage, the K3 stage is empty
+    cudaEventRecord(b->ev[5], s);
+    if (!(stages & HC_STAGE_DEBLOCK)) v.flags |= hc::HC_VIEW_NO_DEBLOCK;
+    hc::launch_k34(v, b->max_pf_tiles, b->max_planes, b->any_16bit, s);
+    b->launches += 1;
+  } else {
+    if (stages & HC_STAGE_DEBLOCK) {
+      hc::launch_k3(b->view, b->max_dbk_units, b->max_planes, s);
+      b->launches += 2;
+    }
+    cudaEventRecord(b->ev[5], s);
+    hc::launch_k4(v, b->max_sao_quads, b->max_planes, s);
+    b->launches += 1;
+  }
   // K6: irot / imir / clap passes of the canvases that carry any, plane by plane (rare; timed with K4)
   for (const Canvas& c : b->canvases) {
     if (!c.transformed()) continue;

@@ -34,6 +34,7 @@ struct BatchView {
   int flags;               // HC_VIEW_*
 };
 constexpr int HC_VIEW_NO_SAO = 1;  // K4 only crops + pastes (parity tests of the earlier stages)
+constexpr int HC_VIEW_NO_DEBLOCK = 2;  // fused post-filter: skip the two deblocking phases
 
 // One wavefront task of K2: a CTB row of one colour component of one picture.
 struct RowTask {

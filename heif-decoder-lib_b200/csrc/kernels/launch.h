@@ -69,6 +69,8 @@ void launch_k2(const BatchView& bv, const RowTask* tasks, int ntasks, int smem_b
 void launch_k2_lists(const BatchView& bv, const RowTask* tasks, const WarpWork* work, int nctas, int smem_bytes, int* progress, cudaStream_t stream);
 void launch_k3(const BatchView& bv, long long max_units, int planes, cudaStream_t stream);
 void launch_k4(const BatchView& bv, long long max_ctbs, int planes, cudaStream_t stream);
+// K3 + K4 fused, one shared-memory tile at a time (k34_postfilter.cu); bv.flags: HC_VIEW_NO_DEBLOCK / HC_VIEW_NO_SAO
+void launch_k34(const BatchView& bv, long long max_tiles, int planes, bool sixteen_bit, cudaStream_t stream);
 void launch_k5(const CscArgs& a, bool sixteen_bit, cudaStream_t stream);
 void launch_k5_batch(const CscBatch& b, bool sixteen_bit, cudaStream_t stream);
 void launch_k6(const XformArgs& a, bool sixteen_bit, cudaStream_t stream);

@@ -76,6 +76,21 @@ def test_planes_match_oracle_per_stage(engine, pictures, stages):
                 label, stages, k, len(bad), tuple(bad[0]))
 
 
+@pytest.mark.parametrize("stages", [0, hb.STAGE_DEBLOCK, hb.STAGE_ALL])
+def test_fused_postfilter_matches_oracle_per_stage(engine, pictures, stages):
+    """The fused deblock + SAO tile kernel (k34_postfilter.cu, engine option fused_postfilter; not the default — it is
+    slower than the split kernels) produces the same planes as the oracle on every bundled picture."""
+    engine.set_option("fused_postfilter", 1)
+    try:
+        for label, rec in pictures:
+            want, _ = oracle_lib.reconstruct(rec, stages)
+            got, _ = gpu_planes(engine, rec, stages)
+            for k, (g, w) in enumerate(zip(got, want)):
+                assert np.array_equal(g.astype(np.uint16), w), (label, stages, k)
+    finally:
+        engine.set_option("fused_postfilter", 0)
+
+
 def test_full_decode_matches_reference_golden(engine, pictures):
     for label, rec in pictures:
         got, _ = gpu_planes(engine, rec, hb.STAGE_ALL)
