@@ -201,6 +201,7 @@ struct hc_batch {
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> csc_events;
   int launches = 0;
   float last_d2h_ms = 0.f;
+  std::vector<int> failed_pics;   // pictures whose device parse failed (k0_check_status)
   int pack_threads = 0;     // host threads hc_batch_upload may use to pack the pinned arena (0: hardware concurrency)
 };
 
@@ -874,13 +875,17 @@ static int k0_check_status(hc_batch* b) {
   b->k0_status_pending = false;
   const int* status = (const int*)b->h_status.p;
   for (int l = 0; l < 4; l++) { b->k0_tb_counts[l] = status[b->nk0 + l]; b->launches += b->k0_tb_counts[l] > 0; }
+  // every failing picture is remembered (hc_batch_failed_pictures: the stream API isolates the files they belong to — a
+  // failing chain never touches another picture's regions); the first one names the error
+  b->failed_pics.clear();
   for (int q = 0; q < b->nk0; q++)
     if (status[q]) {
-      hc::set_last_error("picture " + std::to_string(b->k0_pic_of[q]) + (status[q] == hc::k0::ERR_CAPACITY ? ": device parser capacity exceeded"
-                                                                                                           : ": malformed slice data (device parser)"));
-      return HC_ERR_BITSTREAM;
+      if (b->failed_pics.empty())
+        hc::set_last_error("picture " + std::to_string(b->k0_pic_of[q]) + (status[q] == hc::k0::ERR_CAPACITY ? ": device parser capacity exceeded"
+                                                                                                             : ": malformed slice data (device parser)"));
+      b->failed_pics.push_back(b->k0_pic_of[q]);
     }
-  return HC_OK;
+  return b->failed_pics.empty() ? HC_OK : HC_ERR_BITSTREAM;
 }
 
 // Synchronises the stream and reports a K0 parse error of the batch, if any.
@@ -1336,6 +1341,12 @@ int hc_batch_timer_stop_ms(hc_batch* b, float* ms) {
 int hc_batch_launch_count(const hc_batch* b) { return b ? b->launches : 0; }
 size_t hc_batch_upload_bytes(const hc_batch* b) { return b ? b->arena_bytes : 0; }
 int hc_batch_k0_pictures(const hc_batch* b) { return b ? b->nk0 : 0; }
+// internal (heic_job.cc): pictures of the batch whose device parse failed at the last synchronising call
+int hc_batch_failed_pictures(const hc_batch* b, const int** pics) {
+  if (!b) return 0;
+  if (pics) *pics = b->failed_pics.data();
+  return (int)b->failed_pics.size();
+}
 // internal (heic_job.cc): host threads hc_batch_upload may use
 void hc_batch_set_pack_threads(hc_batch* b, int n) { if (b) b->pack_threads = n; }
 

@@ -21,6 +21,7 @@
 #include "../capi/capi_internal.h"
 
 extern "C" void hc_batch_set_pack_threads(hc_batch* b, int n);   // engine.cu (internal)
+extern "C" int hc_batch_failed_pictures(const hc_batch* b, const int** pics);
 
 namespace {
 
@@ -115,8 +116,13 @@ struct ImagePlan {
   std::vector<std::pair<int32_t, int32_t>> child_offsets;
 };
 
-int add_item(hc_batch* b, const CodedItem& ci, int canvas, int x, int y, int role, int rescale) {
-  return ci.k0 ? hc_batch_add_k0_picture(b, ci.k0.get(), canvas, x, y, role, rescale) : hc_batch_add_picture(b, &ci.rec, canvas, x, y, role, rescale);
+int add_item(hc_batch* b, std::vector<int>& pic_file, const CodedItem& ci, int canvas, int x, int y, int role, int rescale) {
+  const int pic = ci.k0 ? hc_batch_add_k0_picture(b, ci.k0.get(), canvas, x, y, role, rescale) : hc_batch_add_picture(b, &ci.rec, canvas, x, y, role, rescale);
+  if (pic >= 0) {
+    if ((int)pic_file.size() <= pic) pic_file.resize((size_t)pic + 1, -1);
+    pic_file[pic] = ci.file;
+  }
+  return pic;
 }
 
 }  // namespace
@@ -131,6 +137,7 @@ struct hc_heic_job {
   double parse_seconds = 0;
   bool want_alpha = false;
   int forced_format = -1;   // HC_OUT_* for every image, or -1: by bit depth
+  std::vector<int> pic_file;   // batch picture -> file it belongs to (error isolation of the stream API)
 };
 
 extern "C" {
@@ -384,14 +391,14 @@ static hc_heic_job* job_create_impl(hc_engine* e, int nfiles, const uint8_t* con
         const int x0 = (int)(k % im.info.cols) * tw, y0 = (int)(k / im.info.cols) * th;
         if (x0 >= W || y0 >= H) { hc::set_last_error("grid tile lies outside the output image"); return false; }
         // context.cc:2504: limited-range tiles (matrix != 0) are expanded to full range while pasting
-        if (add_item(j->batch, ci, im.canvas, x0, y0, HC_ROLE_COLOUR, (!tfull && tmatrix != 0) ? 1 : 0) < 0) return false;
+        if (add_item(j->batch, j->pic_file, ci, im.canvas, x0, y0, HC_ROLE_COLOUR, (!tfull && tmatrix != 0) ? 1 : 0) < 0) return false;
       }
       // the canvas only has an nclx if the grid item itself carries one (context.cc:1841-1844)
       matrix = im.info.nclx_present ? im.info.matrix : 2;
       primaries = im.info.nclx_present ? im.info.primaries : 2;
       full = im.info.nclx_present ? im.info.full_range : 1;
     } else {
-      if (add_item(j->batch, j->items[im.tiles[0]], im.canvas, 0, 0, HC_ROLE_COLOUR, 0) < 0) return false;
+      if (add_item(j->batch, j->pic_file, j->items[im.tiles[0]], im.canvas, 0, 0, HC_ROLE_COLOUR, 0) < 0) return false;
       matrix = im.info.nclx_present ? im.info.matrix : p0.matrix_coeffs;
       primaries = im.info.nclx_present ? im.info.primaries : p0.colour_primaries;
       full = im.info.nclx_present ? im.info.full_range : p0.full_range;
@@ -453,7 +460,7 @@ static hc_heic_job* job_create_impl(hc_engine* e, int nfiles, const uint8_t* con
         same = false;
       }
       alpha_separate = !same;
-      if (!alpha_separate && add_item(j->batch, j->items[im.alpha], im.canvas, 0, 0, HC_ROLE_ALPHA, 0) < 0) return false;
+      if (!alpha_separate && add_item(j->batch, j->pic_file, j->items[im.alpha], im.canvas, 0, 0, HC_ROLE_ALPHA, 0) < 0) return false;
     }
     {
       bool any = false;
@@ -465,7 +472,7 @@ static hc_heic_job* job_create_impl(hc_engine* e, int nfiles, const uint8_t* con
       int Wa = pa.crop_w, Ha = pa.crop_h;
       const int ac = hc_batch_add_canvas(j->batch, Wa, Ha, 0, pa.bit_depth_y, 0);
       if (ac < 0) return false;
-      if (add_item(j->batch, j->items[im.alpha], ac, 0, 0, HC_ROLE_LUMA, 0) < 0) return false;
+      if (add_item(j->batch, j->pic_file, j->items[im.alpha], ac, 0, 0, HC_ROLE_LUMA, 0) < 0) return false;
       bool any = false;
       if (!apply_xforms(ac, ait, Wa, Ha, 0, pa.bit_depth_y, any)) return false;
       if (hc_batch_link_alpha(j->batch, im.canvas, ac) != HC_OK) return false;
@@ -615,12 +622,12 @@ double hc_heic_job_parse_seconds(const hc_heic_job* j) { return j ? j->parse_sec
 int hc_heic_decode_stream(hc_engine* e, int nfiles, const uint8_t* const* data, const size_t* sizes, int want_alpha,
                           int threads, int files_per_batch, hc_image_callback on_image, void* user,
                           hc_stream_stats* stats) {
-  return hc_heic_decode_stream_ext(e, nfiles, data, sizes, want_alpha, threads, files_per_batch, nullptr, on_image, user, stats);
+  return hc_heic_decode_stream_ext(e, nfiles, data, sizes, want_alpha, threads, files_per_batch, nullptr, nullptr, on_image, user, stats);
 }
 
 int hc_heic_decode_stream_ext(hc_engine* e, int nfiles, const uint8_t* const* data, const size_t* sizes, int want_alpha,
-                              int threads, int files_per_batch, const hc_stream_dest* dests, hc_image_callback on_image, void* user,
-                              hc_stream_stats* stats) {
+                              int threads, int files_per_batch, const hc_stream_dest* dests, int* file_status, hc_image_callback on_image,
+                              void* user, hc_stream_stats* stats) {
   if (!e || nfiles <= 0 || !data || !sizes || files_per_batch <= 0) {
     hc::set_last_error("hc_heic_decode_stream: bad argument");
     return HC_ERR_ARGUMENT;
@@ -650,7 +657,16 @@ int hc_heic_decode_stream_ext(hc_engine* e, int nfiles, const uint8_t* const* da
   std::atomic<int> share{share_opt >= 0 ? share_opt : balanced_share(c_dev0, c_host0, c_hdr0)};
   double c_host = c_host0, c_dev = c_dev0, c_hdr = c_hdr0;
   std::mutex parse_mu;
-  struct Parsed { hc_heic_job* job = nullptr; std::string error; double seconds = 0; int share = 0; };
+  // `map`: image of the job -> file of the batch (identity unless files were dropped by the error isolation)
+  struct Parsed { hc_heic_job* job = nullptr; std::string error; double seconds = 0; int share = 0; std::vector<int> map; };
+  if (file_status) std::fill(file_status, file_status + nfiles, (int)HC_OK);
+  std::string first_file_error;
+  std::mutex file_error_mu;
+  auto fail_file = [&](int file, int code, const std::string& why) {
+    std::lock_guard<std::mutex> lk(file_error_mu);
+    if (file_status[file] == HC_OK) { file_status[file] = code; st.files_failed++; }
+    if (first_file_error.empty()) first_file_error = "file " + std::to_string(file) + ": " + why;
+  };
   auto parse_batch = [&](int b) -> Parsed {
     Parsed p;
     const int first = b * files_per_batch, n = std::min(files_per_batch, nfiles - first);
@@ -658,7 +674,32 @@ int hc_heic_decode_stream_ext(hc_engine* e, int nfiles, const uint8_t* const* da
     const auto t0 = clock::now();
     p.share = nbatches > 1 ? share.load() : 0;
     p.job = job_create(e, n, data + first, sizes + first, want_alpha, threads, 0, -1, p.share);
+    p.map.resize(n);
+    for (int k = 0; k < n; k++) p.map[k] = k;
     if (!p.job) p.error = hc_last_error();   // thread-local: fetch on the parsing thread
+    if (!p.job && file_status) {
+      // error isolation: find the files that cannot be decoded (each on its own, headers only unless the device parser
+      // cannot take the picture), report them through file_status and go on with the others
+      std::vector<const uint8_t*> gd; std::vector<size_t> gs;
+      p.map.clear();
+      for (int k = 0; k < n; k++) {
+        hc_heic_job* probe = job_create(e, 1, data + first + k, sizes + first + k, want_alpha, 1, 0, -1, 0);
+        if (probe) {
+          hc_heic_job_destroy(probe);
+          gd.push_back(data[first + k]); gs.push_back(sizes[first + k]); p.map.push_back(k);
+        } else {
+          fail_file(first + k, HC_ERR_BITSTREAM, hc_last_error());
+        }
+      }
+      p.error.clear();
+      if (!gd.empty() && (int)gd.size() < n) {
+        p.share = 0;
+        p.job = job_create(e, (int)gd.size(), gd.data(), gs.data(), want_alpha, threads, 0, -1, 0);
+        if (!p.job) p.error = hc_last_error();
+      } else if (!gd.empty()) {
+        p.error = "batch failed although every file of it decodes alone";   // e.g. out of memory: not a property of one file
+      }
+    }
     p.seconds = secs(t0, clock::now());
     return p;
   };
@@ -670,7 +711,7 @@ int hc_heic_decode_stream_ext(hc_engine* e, int nfiles, const uint8_t* const* da
   // slots idle (16 files: 22 CTB slots of time for 16.6 slots of work); with the next batch's K0 already queued on its own
   // low-priority stream, its chains take those slots, and K1..K5 + D2H of the finished batch run at high priority meanwhile.
   constexpr int DEPTH = 3;
-  struct InFlight { hc_heic_job* job = nullptr; int index = 0; int slot = 0; std::vector<size_t> offs; std::vector<uint8_t*> ptrs; std::vector<size_t> strides; clock::time_point t0; double host_s = 0, host_wait_s = 0; int share = 0; int rc = HC_OK; };
+  struct InFlight { hc_heic_job* job = nullptr; int index = 0; int slot = 0; std::vector<size_t> offs; std::vector<uint8_t*> ptrs; std::vector<size_t> strides; std::vector<int> map; clock::time_point t0; double host_s = 0, host_wait_s = 0; int share = 0; int rc = HC_OK; };
   void* pinned[DEPTH] = {};
   size_t pinned_cap[DEPTH] = {};
   double t_done[3] = {0, 0, 0};   // host time at which the last three batches were seen complete
@@ -688,7 +729,7 @@ int hc_heic_decode_stream_ext(hc_engine* e, int nfiles, const uint8_t* const* da
       f.offs[i] = need;
       // external destination (the reference's heif_decoding_options::ext_dst, heif.h:1605-1615, pixelimage.cc:221-266): the
       // final pixels land in the caller's buffer with the caller's stride when it is large enough, else in our own memory
-      const hc_stream_dest* xd = dests ? &dests[(size_t)b * files_per_batch + i] : nullptr;
+      const hc_stream_dest* xd = dests ? &dests[(size_t)b * files_per_batch + f.map[i]] : nullptr;
       if (xd && xd->dst && xd->stride >= row && xd->len >= xd->stride * (size_t)(d.height - 1) + row) {
         f.ptrs[i] = (uint8_t*)xd->dst;
         f.strides[i] = xd->stride;
@@ -717,6 +758,20 @@ int hc_heic_decode_stream_ext(hc_engine* e, int nfiles, const uint8_t* const* da
     hc_heic_job* j = f.job;
     const double ta = now_s();
     if (r == HC_OK) r = hc_heic_job_sync(j);
+    std::vector<char> bad(j->images.size(), 0);
+    if (r == HC_ERR_BITSTREAM && file_status) {
+      // slice data the device parser rejected: the pictures are known, the other files of the batch are intact
+      const int* pics = nullptr;
+      const int nbad = hc_batch_failed_pictures(j->batch, &pics);
+      const std::string why = hc_last_error();
+      for (int q = 0; q < nbad; q++) {
+        const int file = pics[q] < (int)j->pic_file.size() ? j->pic_file[pics[q]] : -1;
+        if (file < 0) continue;
+        bad[file] = 1;
+        fail_file(f.index * files_per_batch + f.map[file], HC_ERR_BITSTREAM, why);
+      }
+      if (nbad > 0) r = HC_OK;
+    }
     const double tb = now_s();
     double tc = tb;
     if (r == HC_OK) {
@@ -746,10 +801,11 @@ int hc_heic_decode_stream_ext(hc_engine* e, int nfiles, const uint8_t* const* da
       st.bytes_h2d += hc_heic_job_upload_bytes(j);
       st.launches += hc_heic_job_launch_count(j);
       for (size_t i = 0; i < j->images.size(); i++) {
+        if (bad[i]) continue;
         const hc_image_desc& d = j->images[i].desc;
         st.bytes_d2h += (uint64_t)d.width * d.bytes_per_pixel * d.height;
         st.pixels += (int64_t)d.width * d.height;
-        if (on_image) on_image(user, f.index * files_per_batch + (int)i, &d, f.ptrs[i], f.strides[i]);
+        if (on_image) on_image(user, f.index * files_per_batch + f.map[i], &d, f.ptrs[i], f.strides[i]);
       }
       tc = now_s();
     } else if (rc == HC_OK) {
@@ -781,13 +837,14 @@ int hc_heic_decode_stream_ext(hc_engine* e, int nfiles, const uint8_t* const* da
     top_up();
     st.seconds_parse += cur.seconds;
     if (!cur.job) {
-      if (rc == HC_OK) { rc = HC_ERR_BITSTREAM; err = "batch " + std::to_string(b) + ": " + cur.error; }
-      continue;   // keep draining the pipeline
+      if (rc == HC_OK && !cur.error.empty()) { rc = HC_ERR_BITSTREAM; err = "batch " + std::to_string(b) + ": " + cur.error; }
+      continue;   // keep draining the pipeline (with error isolation: every file of the batch failed and is reported)
     }
     if (rc != HC_OK) { hc_heic_job_destroy(cur.job); continue; }
     InFlight& f = ring[b % DEPTH];
     if (f.job) deliver(f, f.rc);    // batch b - DEPTH (only after a skipped batch; normally delivered below)
     f.host_s = cur.seconds;
+    f.map = cur.map;
     f.host_wait_s = host_wait;
     f.share = cur.share;
     f.rc = submit(cur.job, b, f);
@@ -803,6 +860,7 @@ int hc_heic_decode_stream_ext(hc_engine* e, int nfiles, const uint8_t* const* da
   st.seconds_total = secs(t_begin, clock::now());
   if (stats) *stats = st;
   if (rc != HC_OK) hc::set_last_error(err);
+  else if (!first_file_error.empty()) hc::set_last_error(first_file_error);
   return rc;
 }
 

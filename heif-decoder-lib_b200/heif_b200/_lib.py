@@ -64,7 +64,7 @@ class StreamStats(C.Structure):
     """hc_stream_stats"""
     _fields_ = [("seconds_total", C.c_double), ("seconds_parse", C.c_double), ("seconds_gpu_phase", C.c_double),
                 ("device_ms", C.c_double), ("bytes_h2d", C.c_uint64), ("bytes_d2h", C.c_uint64), ("pixels", C.c_int64),
-                ("batches", C.c_int32), ("launches", C.c_int32)]
+                ("batches", C.c_int32), ("launches", C.c_int32), ("files_failed", C.c_int32)]
 
 
 class StreamDest(C.Structure):
@@ -173,8 +173,8 @@ SYMBOLS = [
     ("hc_heic_job_parse_seconds", C.c_double, [_vp]),
     ("hc_heic_decode_stream", _i, [_vp, _i, C.POINTER(C.c_char_p), C.POINTER(_sz), _i, _i, _i, IMAGE_CALLBACK, _vp,
                                C.POINTER(StreamStats)]),
-    ("hc_heic_decode_stream_ext", _i, [_vp, _i, C.POINTER(C.c_char_p), C.POINTER(_sz), _i, _i, _i, _vp, IMAGE_CALLBACK, _vp,
-                                   C.POINTER(StreamStats)]),
+    ("hc_heic_decode_stream_ext", _i, [_vp, _i, C.POINTER(C.c_char_p), C.POINTER(_sz), _i, _i, _i, _vp, C.POINTER(_i), IMAGE_CALLBACK,
+                                   _vp, C.POINTER(StreamStats)]),
     ("hc_host_alloc", _vp, [_sz]),
     ("hc_host_free", None, [_vp]),
 ]

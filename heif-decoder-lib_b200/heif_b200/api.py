@@ -429,10 +429,13 @@ class HeicJob:
         self.close()
 
 
-def decode_stream(engine, files, on_image=None, want_alpha=False, threads=0, files_per_batch=8, out_format=None, dests=None):
+def decode_stream(engine, files, on_image=None, want_alpha=False, threads=0, files_per_batch=8, out_format=None, dests=None,
+                  isolate_errors=False):
     """Long file lists (hc_heic_decode_stream): host parse of batch b+1 overlaps upload + kernels + read-back of
     batch b. on_image(file_index, desc, rows) gets every image as a numpy view [h, w*bytes_per_pixel] of PINNED
-    host memory that is only valid inside the callback. Returns the hc_stream_stats as a dict."""
+    host memory that is only valid inside the callback. Returns the hc_stream_stats as a dict.
+    isolate_errors: a file that cannot be decoded does not fail the call; the dict gains "file_status" (one HC_* code per
+    file, 0 = delivered) and "first_error" (text)."""
     from ._lib import IMAGE_CALLBACK, StreamStats
     L = engine._L
     if out_format is not None:
@@ -462,6 +465,11 @@ def decode_stream(engine, files, on_image=None, want_alpha=False, threads=0, fil
         for k, a in enumerate(dests):
             if a is not None:
                 xd[k].dst, xd[k].len, xd[k].stride = a.ctypes.data, a.nbytes, a.strides[0]
-    check(L, L.hc_heic_decode_stream_ext(engine._h, n, ptrs, sizes, int(want_alpha), threads, files_per_batch, xd, cb, None, C.byref(st)),
-          "hc_heic_decode_stream")
-    return {k: getattr(st, k) for k, _ in StreamStats._fields_}
+    status = (C.c_int * n)() if isolate_errors else None
+    check(L, L.hc_heic_decode_stream_ext(engine._h, n, ptrs, sizes, int(want_alpha), threads, files_per_batch, xd, status, cb, None,
+                                         C.byref(st)), "hc_heic_decode_stream")
+    out = {k: getattr(st, k) for k, _ in StreamStats._fields_}
+    if isolate_errors:
+        out["file_status"] = list(status)
+        out["first_error"] = (L.hc_last_error() or b"").decode() if st.files_failed else ""
+    return out

@@ -424,6 +424,7 @@ typedef struct hc_stream_stats {
   uint64_t bytes_h2d, bytes_d2h;
   int64_t pixels;            /* output pixels delivered                                           */
   int32_t batches, launches;
+  int32_t files_failed;      /* files reported through file_status (hc_heic_decode_stream_ext)   */
 } hc_stream_stats;
 int hc_heic_decode_stream(hc_engine* e, int nfiles, const uint8_t* const* data, const size_t* sizes, int want_alpha,
                           int threads, int files_per_batch, hc_image_callback on_image, void* user,
@@ -433,15 +434,20 @@ int hc_heic_decode_stream(hc_engine* e, int nfiles, const uint8_t* const* data, 
  * pixels of file k go — `len` bytes at `dst` (pinned memory makes the copy asynchronous), rows `stride` bytes apart. Like
  * the reference, a destination that is absent or too small (len < stride * (height - 1) + row bytes, or stride < row
  * bytes) is ignored and the image is delivered in the library's own pinned memory; the callback receives whichever pointer
- * and stride were used. dests may be NULL (then this is hc_heic_decode_stream). */
+ * and stride were used. dests may be NULL.
+ * Error isolation: with file_status == NULL the first file that cannot be decoded fails the whole call (hc_heic_decode_stream).
+ * With file_status != NULL (nfiles entries) such a file gets its error code there and no callback, every other file is
+ * delivered, and the call returns HC_OK unless something other than the content of a file went wrong (CUDA, memory);
+ * stats->files_failed counts them and hc_last_error() describes the first. A damaged container, unsupported coding tools,
+ * slice data the parser rejects and the device parser's capacity limit are all per-file errors. */
 typedef struct hc_stream_dest {
   void* dst;
   size_t len;
   size_t stride;
 } hc_stream_dest;
 int hc_heic_decode_stream_ext(hc_engine* e, int nfiles, const uint8_t* const* data, const size_t* sizes, int want_alpha,
-                              int threads, int files_per_batch, const hc_stream_dest* dests, hc_image_callback on_image, void* user,
-                              hc_stream_stats* stats);
+                              int threads, int files_per_batch, const hc_stream_dest* dests, int* file_status,
+                              hc_image_callback on_image, void* user, hc_stream_stats* stats);
 /* pinned host memory for fast H2D/D2H in the caller (NULL when no CUDA engine) */
 void* hc_host_alloc(size_t bytes);
 void hc_host_free(void* p);

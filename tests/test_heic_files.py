@@ -296,3 +296,59 @@ def test_gpu_decode_stream_reports_bad_file(engine):
     files = [load(NAMES[0]), b"not a heic file at all", load(NAMES[1])]
     with pytest.raises(hb.HeifCudaError):
         hb.decode_stream(engine, files, None, files_per_batch=1)
+
+
+def _heic_with_rejected_slice_data():
+    """A well-formed HEIC whose slice data the K0 parser rejects (checked with the CPU build of the same parser), and the
+    undamaged file: (bad, good)."""
+    import test_fuzz as T
+    from tools import heif_writer as W
+    name = "wpp"
+    meta = T.GEN_META[name]
+    data = open(os.path.join(T.GEN_DIR, name + ".hevc"), "rb").read()
+    for seed in range(200):
+        bad = T.corrupt(data, seed * 7919 + 11)
+        if len(bad) != len(data):
+            continue                      # truncations change the parameter-set scan of the writer; keep the length
+        try:
+            hb.parse_picture_k0(bad, T._fmt(bad), host_only=True)
+        except hb.HeifCudaError:
+            return (W.single_image(bad, meta["width"], meta["height"], 1, 8), W.single_image(data, meta["width"], meta["height"], 1, 8))
+    raise AssertionError("no corruption of %s is rejected by the parser" % name)
+
+
+@pytest.mark.gpu
+def test_gpu_decode_stream_isolates_bad_files(engine):
+    """hc_heic_decode_stream_ext with file_status: a file that is not a HEIC at all (fails in the container parse on the
+    host) and a file whose slice data the DEVICE parser rejects each get an error code; every other file of their batches
+    is delivered bit-exactly, in every position of the batch."""
+    bad_slices, good_twin = _heic_with_rejected_slice_data()
+    files = [load(NAMES[0]), b"not a heic file at all", load(NAMES[1]), bad_slices, good_twin, load(NAMES[2]), bad_slices]
+    expect_bad = {1, 3, 6}
+    got = {}
+
+    def on_image(index, desc, rows):
+        got[index] = hashlib.md5(np.ascontiguousarray(rows[:, :desc.width * desc.bytes_per_pixel]).tobytes()).hexdigest()
+
+    for per_batch in (3, 7, 1):
+        got.clear()
+        st = hb.decode_stream(engine, files, on_image, files_per_batch=per_batch, isolate_errors=True)
+        assert {k for k, v in enumerate(st["file_status"]) if v != 0} == expect_bad, (per_batch, st["file_status"])
+        assert st["files_failed"] == 3 and st["first_error"]
+        assert set(got) == set(range(len(files))) - expect_bad
+        want = {}
+        for k in got:   # each good file alone through the same API
+            hb.decode_stream(engine, [files[k]], lambda i, d, r, k=k: want.__setitem__(
+                k, hashlib.md5(np.ascontiguousarray(r[:, :d.width * d.bytes_per_pixel]).tobytes()).hexdigest()), files_per_batch=1)
+        assert got == want, per_batch
+    # without file_status the call still fails as a whole
+    with pytest.raises(hb.HeifCudaError):
+        hb.decode_stream(engine, files, None, files_per_batch=3)
+
+
+def test_rejected_slice_data_fixture_is_a_wellformed_container():
+    bad, good = _heic_with_rejected_slice_data()
+    for data in (bad, good):
+        hf = hb.HeifFile(data, host_only=True)
+        assert hf.image_info(hf.primary_id).width == 264
+        hf.close()
