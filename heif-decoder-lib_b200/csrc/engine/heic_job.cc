@@ -102,7 +102,9 @@ struct ImagePlan {
   int file = 0;
   hc_heif_image_info info{};
   std::vector<int> tiles;   // indices into items (1 for a single image)
-  int alpha = -1;           // index into items
+  int alpha = -1;           // index into items (the first tile when the alpha image is a grid)
+  std::vector<int> alpha_tiles;   // grid-coded alpha image: its tiles (indices into items), row-major
+  int alpha_cols = 0, alpha_w = 0, alpha_h = 0;
   int band_first_row = 0;   // first tile row of a banded grid decode (multi-GPU, config C5)
   int band_y0 = 0;          // first output row of the band
   int full_height = 0;      // height of the whole image
@@ -219,8 +221,24 @@ static hc_heic_job* job_create_impl(hc_engine* e, int nfiles, const uint8_t* con
       j->items.back().file = f;
       j->items.back().item_id = t;
     }
-    if (im.info.alpha_id) {
-      if (hf.is_grid(im.info.alpha_id)) { hc::set_last_error("grid-coded alpha images are not supported"); return false; }
+    if (im.info.alpha_id && hf.is_grid(im.info.alpha_id)) {
+      // the alpha image is decoded like any image item (context.cc:2040-2071 decode_image_planar), so it may be a grid too
+      hc::HeifGrid ag;
+      err = hf.grid(im.info.alpha_id, ag);
+      if (!err.empty()) { hc::set_last_error("file " + std::to_string(f) + ": alpha image: " + err); return false; }
+      if (ag.out_w <= 0 || ag.out_h <= 0 || (uint64_t)ag.out_w * (uint64_t)ag.out_h > (uint64_t)32768 * 32768) {
+        hc::set_last_error("file " + std::to_string(f) + ": grid output size exceeds the maximum image size");
+        return false;
+      }
+      im.alpha = (int)j->items.size();
+      im.alpha_cols = ag.cols; im.alpha_w = ag.out_w; im.alpha_h = ag.out_h;
+      for (uint32_t t : ag.tiles) {
+        im.alpha_tiles.push_back((int)j->items.size());
+        j->items.emplace_back();
+        j->items.back().file = f;
+        j->items.back().item_id = t;
+      }
+    } else if (im.info.alpha_id) {
       im.alpha = (int)j->items.size();
       j->items.emplace_back();
       j->items.back().file = f;
@@ -373,6 +391,25 @@ static hc_heic_job* job_create_impl(hc_engine* e, int nfiles, const uint8_t* con
     im.canvas = hc_batch_add_canvas(j->batch, W, H, p0.chroma_format, p0.bit_depth_y, has_alpha);
     if (im.canvas < 0) return false;
     int matrix, primaries, full;
+    // the tiles of one grid item onto one canvas (context.cc:2328-2337, :2407-2539)
+    auto place_tiles = [&](const std::vector<int>& tiles, int cols, int canvas, int CW, int CH, int role) -> bool {
+      const hc_pic& t0 = j->items[tiles[0]].pic();
+      const int tw = t0.crop_w, th = t0.crop_h;
+      for (size_t k = 0; k < tiles.size(); k++) {
+        CodedItem& ci = j->items[tiles[k]];
+        const hc_pic& p = ci.pic();
+        const hc::HeifItem* tit = j->files[im.file]->item(ci.item_id);
+        if (p.crop_w != tw || p.crop_h != th) { hc::set_last_error("Grid tiles have different sizes"); return false; }
+        if (p.chroma_format != t0.chroma_format || p.bit_depth_y != t0.bit_depth_y) { hc::set_last_error("grid tiles differ in chroma format or bit depth"); return false; }
+        if (tit && !tit->xforms.empty()) { hc::set_last_error("transformations on grid tile items are not supported"); return false; }
+        const int tfull = tit && tit->nclx.present ? tit->nclx.full_range : p.full_range;
+        const int tmatrix = tit && tit->nclx.present ? tit->nclx.matrix : p.matrix_coeffs;
+        const int x0 = (int)(k % cols) * tw, y0 = (int)(k / cols) * th;
+        if (x0 >= CW || y0 >= CH) { hc::set_last_error("grid tile lies outside the output image"); return false; }
+        if (add_item(j->batch, j->pic_file, ci, canvas, x0, y0, role, (!tfull && tmatrix != 0) ? 1 : 0) < 0) return false;
+      }
+      return true;
+    };
     if (im.info.is_grid) {
       const int tw = p0.crop_w, th = p0.crop_h;
       for (size_t k = 0; k < im.tiles.size(); k++) {
@@ -450,9 +487,11 @@ static hc_heic_job* job_create_impl(hc_engine* e, int nfiles, const uint8_t* con
     // decoded on its own canvas, transformed by its own properties and rescaled by nearest neighbour afterwards
     // (context.cc:2040-2071: decode_image_planar of the alpha item, then scale_nearest_neighbor to the colour image's size)?
     bool alpha_separate = false;
+    const bool alpha_grid = !im.alpha_tiles.empty();
     if (has_alpha) {
       const hc_pic& pa = j->items[im.alpha].pic();
-      bool same = pa.crop_w == W && pa.crop_h == H;
+      // a grid-coded alpha image always gets a canvas of its own (its tiles are pasted there like those of any grid)
+      bool same = !alpha_grid && pa.crop_w == W && pa.crop_h == H;
       if (same && pit && !pit->xforms.empty()) {
         same = ait && ait->xforms == pit->xforms && ait->claps.size() == pit->claps.size();
         for (size_t k = 0; same && k < pit->claps.size(); k++) same = memcmp(&ait->claps[k], &pit->claps[k], sizeof(hc::HeifItem::Clap)) == 0;
@@ -469,10 +508,12 @@ static hc_heic_job* job_create_impl(hc_engine* e, int nfiles, const uint8_t* con
     }
     if (alpha_separate) {
       const hc_pic& pa = j->items[im.alpha].pic();
-      int Wa = pa.crop_w, Ha = pa.crop_h;
+      int Wa = alpha_grid ? im.alpha_w : pa.crop_w, Ha = alpha_grid ? im.alpha_h : pa.crop_h;
       const int ac = hc_batch_add_canvas(j->batch, Wa, Ha, 0, pa.bit_depth_y, 0);
       if (ac < 0) return false;
-      if (add_item(j->batch, j->pic_file, j->items[im.alpha], ac, 0, 0, HC_ROLE_LUMA, 0) < 0) return false;
+      if (alpha_grid) {
+        if (!place_tiles(im.alpha_tiles, im.alpha_cols, ac, Wa, Ha, HC_ROLE_LUMA)) return false;
+      } else if (add_item(j->batch, j->pic_file, j->items[im.alpha], ac, 0, 0, HC_ROLE_LUMA, 0) < 0) return false;
       bool any = false;
       if (!apply_xforms(ac, ait, Wa, Ha, 0, pa.bit_depth_y, any)) return false;
       if (hc_batch_link_alpha(j->batch, im.canvas, ac) != HC_OK) return false;
@@ -483,7 +524,7 @@ static hc_heic_job* job_create_impl(hc_engine* e, int nfiles, const uint8_t* con
     static const int bpp_of[6] = {3, 4, 6, 8, 6, 8};
     im.desc.width = W; im.desc.height = H; im.desc.chroma_format = p0.chroma_format; im.desc.bit_depth = p0.bit_depth_y;
     im.desc.has_alpha = has_alpha; im.desc.out_format = fmt; im.desc.bytes_per_pixel = bpp_of[fmt];
-    im.desc.coded_pictures = (int)im.tiles.size() + (has_alpha ? 1 : 0);
+    im.desc.coded_pictures = (int)im.tiles.size() + (has_alpha ? (alpha_grid ? (int)im.alpha_tiles.size() : 1) : 0);
     // premultiplied alpha: a flag the file sets ('prem' reference, context.cc:1150-1161, :2074-2075) — or the result of
     // heif_image_rgba_premultiply_alpha (heif.cc:1444-1490), which only takes interleaved RGBA that is not premultiplied yet
     im.desc.premultiplied_alpha = has_alpha && j->files[im.file]->premultiplied(im.info.id) ? 1 : 0;

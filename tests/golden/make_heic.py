@@ -92,6 +92,20 @@ def build():
     files["single_422_10_full"] = heif_writer.single_image(enc(200, 120, 2, 10, 73), 200, 120, 2, 10)
     files["single_420_8_matrix12_bt2020"] = heif_writer.single_image(enc(200, 120, 1, 8, 74, matrix=12, primaries=9), 200, 120, 1, 8)
     files["single_444_10_matrix13_bt709"] = heif_writer.single_image(enc(200, 120, 3, 10, 75, matrix=13, primaries=1, full_range=0), 200, 120, 3, 10)
+    # alpha images that are grids themselves (decode_image_planar of the alpha item, context.cc:2040-2071)
+    def alpha_grid(colour, cw, ch, aw, ah, tile, seed):
+        b = W.HeifBuilder()
+        cols, rows = (aw + tile - 1) // tile, (ah + tile - 1) // tile
+        tiles = [enc(tile, tile, 0, 8, seed + k) for k in range(rows * cols)]
+        b.primary = colour(b)
+        b.add_alpha_grid(b.primary, tiles, rows, cols, tile, tile, aw, ah, 8)
+        return b.serialize()
+    files["alpha_grid_single_420_8"] = alpha_grid(lambda b: b.add_hevc_image(enc(200, 120, 1, 8, 90), 200, 120, 1, 8), 200, 120, 200, 120, 64, 91)
+    files["alpha_grid_half_420_8"] = alpha_grid(lambda b: b.add_hevc_image(enc(200, 120, 1, 8, 100), 200, 120, 1, 8), 200, 120, 100, 60, 64, 101)
+    def colour_grid(b):
+        tiles = [b.add_hevc_image(enc(128, 128, 1, 8, 110 + k), 128, 128, 1, 8, hidden=True) for k in range(6)]
+        return b.add_grid(tiles, 2, 3, 300, 200)
+    files["alpha_grid_on_grid_420_8"] = alpha_grid(colour_grid, 300, 200, 300, 200, 128, 120)
     files["alpha_prem_420_8"] = heif_writer.single_image(enc(200, 120, 1, 8, 77), 200, 120, 1, 8, alpha_stream=enc(200, 120, 0, 8, 78), premultiplied=True)
     files["single_420_8_gbr"] = heif_writer.single_image(enc(200, 120, 1, 8, 76, matrix=0), 200, 120, 1, 8)
     return files

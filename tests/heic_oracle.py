@@ -73,9 +73,14 @@ def decode_planes(data, item_id=None):
         nclx = (info.matrix, info.full_range, info.primaries) if info.nclx_present else (r.pic.matrix_coeffs, r.pic.full_range, r.pic.colour_primaries)
     alpha = None
     if info.alpha_id:
-        a = hb.parse_picture(hf.coded_stream(info.alpha_id), host_only=True)
-        apl, _ = oracle_lib.reconstruct(a)
-        alpha = _transform_all([apl[0]], hf.image_info(info.alpha_id))[0]
+        ainfo = hf.image_info(info.alpha_id)
+        if ainfo.is_grid:     # the alpha image is decoded like any image item (context.cc:2040-2071): a grid of its own
+            apl = [decode_planes(data, info.alpha_id)[0][0]]
+            alpha = apl[0]    # decode_planes applied the alpha item's own transformations already
+        else:
+            a = hb.parse_picture(hf.coded_stream(info.alpha_id), host_only=True)
+            apl, _ = oracle_lib.reconstruct(a)
+            alpha = _transform_all([apl[0]], ainfo)[0]
     planes = _transform_all(planes, info)
     if alpha is not None and alpha.shape != planes[0].shape:
         # context.cc:2064-2071 -> HeifPixelImage::scale_nearest_neighbor (pixelimage.cc:1231-1250)

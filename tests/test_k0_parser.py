@@ -81,8 +81,9 @@ def test_k0_records_equal_host_parser_heic_items(name):
     info = hf.image_info(hf.primary_id)
     ids = hf.grid_tiles(hf.primary_id) if info.is_grid else [hf.primary_id]
     if info.alpha_id:
-        ids.append(info.alpha_id)
-    for i in ids[:6]:
+        ainfo = hf.image_info(info.alpha_id)
+        ids = ids[:5] + (hf.grid_tiles(info.alpha_id)[:2] if ainfo.is_grid else [info.alpha_id])
+    for i in ids[:7]:
         check_equal(hf.coded_stream(i), hb.STREAM_LENGTH_PREFIXED)
 
 

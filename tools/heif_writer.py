@@ -79,6 +79,18 @@ class HeifBuilder:
         self.refs.append((b"dimg", gid, list(tile_ids)))
         return gid
 
+    def add_alpha_grid(self, master_id, tile_streams, rows, cols, tile_w, tile_h, out_w, out_h, bit_depth, chroma_format=0,
+                       premultiplied=False):
+        """alpha auxiliary image that is itself a 'grid' of monochrome HEVC tiles"""
+        auxc = fullbox(b"auxC", 0, 0, b"urn:mpeg:hevc:2015:auxid:1\x00")
+        tiles = [self.add_hevc_image(t, tile_w, tile_h, chroma_format, bit_depth, hidden=True) for t in tile_streams]
+        aid = self.add_grid(tiles, rows, cols, out_w, out_h, extra_props=(auxc,))
+        self.items[aid - 1]["hidden"] = True
+        self.refs.append((b"auxl", aid, [master_id]))
+        if premultiplied:
+            self.refs.append((b"prem", master_id, [aid]))
+        return aid
+
     def add_overlay(self, child_ids, canvas_w, canvas_h, offsets, background=(0, 0, 0, 0xffff), extra_props=()):
         """'iovl' derived image (ISO/IEC 23008-12 6.6.2.2; libheif context.cc:318-369): 16-bit RGBA background colour,
         canvas size and one signed (x, y) offset per referenced image"""
