@@ -190,7 +190,15 @@ struct Cabac {
     w_lo = __byte_perm(__ldg(wp), 0, 0x0123);
     wp++;
 #else
-    const uint32_t r = be32(start + pos);
+    // never read behind the substream: damaged slice data can ask for any number of bins before the next overrun() check
+    // (found by the ASAN run of the fuzz inputs); the missing bytes read as zero, like the reference's decoder at the end
+    // of its buffer (cabac.cc:230-243)
+    const uint8_t* q = start + pos;
+    uint32_t r = 0;
+    if (q + 4 <= end) r = be32(q);
+    else
+      for (int k = 0; k < 4; k++)
+        if (q + k < end) r |= (uint32_t)q[k] << (24 - 8 * k);
 #endif
     pos += 4;
     return r;
@@ -301,12 +309,23 @@ HC_D uint32_t lds8(uint32_t a) { uint32_t v; asm volatile("ld.shared.u8 %0, [%1]
 HC_D void sts8(uint32_t a, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 
 // `sa` = shared-space address of the chain's CabState (the Scratch starts with it), `ta` = of the CTA's Tables
-constexpr uint32_t CAB_NEXT = (uint32_t)offsetof(CabState, next), CAB_CTX = (uint32_t)offsetof(Scratch, ctx);
+constexpr uint32_t CAB_NEXT = (uint32_t)offsetof(CabState, next), CAB_END = (uint32_t)offsetof(CabState, end), CAB_CTX = (uint32_t)offsetof(Scratch, ctx);
 constexpr uint32_t TAB_LPS = (uint32_t)offsetof(Tables, range_lps), TAB_NEXT = (uint32_t)offsetof(Tables, next_state), TAB_RECIP = (uint32_t)offsetof(Tables, recip);
 
 static __device__ __noinline__ uint32_t cab_next32(uint32_t sa) {
   const uint2 pv = lds64(sa + CAB_NEXT);
   const unsigned long long pa = ((unsigned long long)pv.y << 32) | pv.x;
+  {
+    // behind the end of the substream (damaged slice data between two overrun() checks) the decoder reads zeros and the
+    // read pointer stops: no load ever leaves the picture's bytes by more than the 8 bytes of the aligned pair below
+    const uint2 ev = lds64(sa + CAB_END);
+    const unsigned long long ea = ((unsigned long long)ev.y << 32) | ev.x;
+    if (pa >= ea) {   // keep counting (position() / overrun() follow the pointer), stop loading
+      const unsigned long long pe = pa + 4;
+      sts64(sa + CAB_NEXT, make_uint2((uint32_t)pe, (uint32_t)(pe >> 32)));
+      return 0u;
+    }
+  }
   const unsigned a = pv.x & 3u;
   const uint32_t* w = reinterpret_cast<const uint32_t*>(pa - a);
   const uint32_t hi = __byte_perm(__ldg(w), 0, 0x0123), lo = __byte_perm(__ldg(w + 1), 0, 0x0123);

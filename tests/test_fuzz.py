@@ -68,6 +68,60 @@ print("parsed", ok, "rejected", rejected)
 """
 
 
+_CONTAINER_CHILD = r"""
+import sys, os, glob
+sys.path.insert(0, sys.argv[1]); sys.path.insert(0, sys.argv[2])
+import numpy as np
+import heif_b200 as hb
+root = sys.argv[3]
+files = sorted(glob.glob(os.path.join(root, "tests", "golden", "heic", "*.heic")))[::5] + sorted(glob.glob(os.path.join(root, "tests", "golden", "iovl", "*.heic")))[:2]
+ok = rej = 0
+for path in files:
+    data = open(path, "rb").read()
+    meta_end = data.find(b"mdat")
+    meta_end = meta_end if meta_end > 0 else len(data)
+    for seed in range(60):
+        rng = np.random.default_rng(seed * 131 + len(data))
+        d = bytearray(data)
+        for _ in range(int(rng.integers(1, 6))):
+            i = int(rng.integers(0, meta_end))
+            mode = int(rng.integers(0, 4))
+            if mode == 0: d[i] = int(rng.integers(0, 256))
+            elif mode == 1: d[i] = 0xff
+            elif mode == 2: d[i] = 0
+            else: d[i:i + 4] = int(rng.integers(0, 2 ** 32)).to_bytes(4, "big")
+        if rng.integers(0, 5) == 0:
+            d = d[:int(rng.integers(8, len(d)))]
+        try:
+            hf = hb.HeifFile(bytes(d), host_only=True)
+            pid = hf.primary_id
+            info = hf.image_info(pid)
+            for t in (hf.grid_tiles(pid) if info.is_grid else [pid])[:4]:
+                try: hf.coded_stream(t)
+                except hb.HeifCudaError: pass
+            try: hf.overlay(pid)
+            except hb.HeifCudaError: pass
+            if info.alpha_id:
+                try: hf.image_info(info.alpha_id)
+                except hb.HeifCudaError: pass
+            hf.close()
+            ok += 1
+        except hb.HeifCudaError:
+            rej += 1
+print("read", ok, "rejected", rej)
+"""
+
+
+def test_container_reader_survives_damaged_files():
+    """ISO-BMFF level: random bytes / sizes / truncations in the meta box of bundled files. The reader (heif_reader.cc)
+    either answers or reports; a crash fails the child. tools/asan_fuzz.sh runs the same inputs (and the slice-data ones)
+    against an AddressSanitizer + UBSan build of the host library."""
+    r = subprocess.run([sys.executable, "-c", _CONTAINER_CHILD, os.path.join(ROOT, "heif-decoder-lib_b200"), os.path.join(ROOT, "tests"), ROOT],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, (r.returncode, r.stdout[-500:], r.stderr[-2000:])
+    assert "read" in r.stdout and "rejected" in r.stdout
+
+
 def test_cpu_parsers_survive_damaged_streams():
     r = subprocess.run([sys.executable, "-c", _CHILD, os.path.join(ROOT, "heif-decoder-lib_b200"), os.path.join(ROOT, "tests")],
                        capture_output=True, text=True, timeout=600)
