@@ -57,7 +57,8 @@ STAGES = ("k1_transform", "k2_intra", "k3_deblock", "k4_sao", "k5_csc")
 def _gen_c2(job):
     i, path = job
     from tools import heif_writer
-    data = heif_writer.synth_grid_heic(GRID_W, GRID_H, tile=TILE, seed=100 + i, qp=26, wpp=1, sao=1, log2_ctb=6)
+    wpp = 0 if "_nowpp" in os.path.basename(path) else 1      # --no-wpp: one substream per tile instead of one per CTB row
+    data = heif_writer.synth_grid_heic(GRID_W, GRID_H, tile=TILE, seed=100 + i, qp=26, wpp=wpp, sao=1, log2_ctb=6)
     with open(path + ".tmp", "wb") as f:
         f.write(data)
     os.replace(path + ".tmp", path)
@@ -91,10 +92,10 @@ def _make(gen, paths):
     return [open(p, "rb").read() for p in paths]
 
 
-def make_content(n_distinct, cache_dir):
+def make_content(n_distinct, cache_dir, wpp=True):
     """n_distinct synthetic 12 MP grid HEICs (cached on disk between runs of the same box)."""
     os.makedirs(cache_dir, exist_ok=True)
-    return _make(_gen_c2, [os.path.join(cache_dir, "c2_%dx%d_t%d_seed%d.heic" % (GRID_W, GRID_H, TILE, i)) for i in range(n_distinct)])
+    return _make(_gen_c2, [os.path.join(cache_dir, "c2_%dx%d_t%d_seed%d%s.heic" % (GRID_W, GRID_H, TILE, i, "" if wpp else "_nowpp")) for i in range(n_distinct)])
 
 
 def make_content_c4(n_distinct, cache_dir):
@@ -418,6 +419,8 @@ def main():
                     "meanwhile in the e2e arm (default: engine default)")
     ap.add_argument("--parser", default="device", choices=["device", "host"],
                     help="where the CABAC slice data is parsed: K0 on the GPU (default) or the host parser")
+    ap.add_argument("--no-wpp", action="store_true", help="c2 content without wavefront substreams (one CABAC chain per 512 x 512 tile): "
+                    "what K0's throughput depends on; not the BASELINE configuration")
     ap.add_argument("--skip-baselines", action="store_true", help="kernel experiments: leave out the cpu_baseline and plugin_dropin arms")
     ap.add_argument("--skip-extras", action="store_true", help="leave out the c4 / c5 side measurements of the default run")
     args = ap.parse_args()
@@ -486,8 +489,8 @@ def main():
         barrier()
         return fn(*a)
 
-    extras = wl == "c2" and not args.skip_extras
-    c2_files = content(make_content, args.distinct, cache) if wl in ("c2", "c5") else None
+    extras = wl == "c2" and not args.skip_extras and not args.no_wpp
+    c2_files = content(make_content, args.distinct, cache, not args.no_wpp) if wl in ("c2", "c5") else None
     c4_files = content(make_content_c4, args.distinct, cache) if wl == "c4" or extras else None
     c5_file = content(make_content_c5, c2_files, cache) if wl == "c5" or extras else None
 
@@ -541,7 +544,8 @@ def main():
             "value": world * mp_per_step / (m["dev_ms"] * 1e-3), "ms_per_step": m["dev_ms"], "scaling": "weak",
             "value_what": "per step: H2D of the step's inputs + K0 (device CABAC parse) + K1..K5, CUDA events on the streams they run on",
             "value_reconstruction_only": world * mp_per_step / (m["recon_ms"] * 1e-3), "ms_per_step_reconstruction_only": m["recon_ms"],
-            "config": {"workload": WORKLOADS[wl], "images_per_step_per_gpu": images, "distinct_files": len(distinct),
+            "config": {"workload": WORKLOADS[wl].replace("CTB64 WPP", "CTB64 no-WPP (NOT the BASELINE configuration)") if args.no_wpp else WORKLOADS[wl],
+                       "images_per_step_per_gpu": images, "distinct_files": len(distinct),
                        "coded_pictures_per_step_per_gpu": images * (48 if wl == "c2" else 1),
                        "l2": "working set per step (planes + residuals + RGB, ~%d MB) exceeds the 126 MB L2; no explicit flush" % int(
                            images * file_mp * (1.5 + 1.5 + 3.0 + 3.0)),

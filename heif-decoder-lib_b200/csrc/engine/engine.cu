@@ -595,16 +595,12 @@ int hc_batch_upload(hc_batch* b) {
     // never reached has no blocks and no SAO (K2..K4 run on the batch without waiting for K0's verdict)
     b->k0_ctu_off = koff[0].ctus;
     b->k0_ctu_bytes = z - koff[0].ctus;
-    for (int q = 0; q < nk0; q++) { const hc::k0::Pic& kp = b->pics[b->k0_pic_of[q]].k0->pic; koff[q].blks = zplace(sizeof(hc_blk) * (size_t)kp.ctbs_w * kp.ctbs_h * kp.blk_cap_ctb, 16); }
-    for (int q = 0; q < nk0; q++) { const hc::k0::Pic& kp = b->pics[b->k0_pic_of[q]].k0->pic; koff[q].tbs = zplace(sizeof(hc_tb) * (size_t)kp.ctbs_w * kp.ctbs_h * kp.tb_cap_ctb, 16); }
-    for (int q = 0; q < nk0; q++) { const hc::k0::Pic& kp = b->pics[b->k0_pic_of[q]].k0->pic; koff[q].coeffs = zplace(sizeof(hc_coeff) * (size_t)kp.ctbs_w * kp.ctbs_h * kp.coeff_cap_ctb, 16); }
+    // the byte-addressed maps first: their bases are 32-bit BYTE offsets from the uploaded arrays (hc_pic::edge_base / qp_base),
+    // so they must not sit behind the record regions (13 GB for 96 twelve-megapixel files); the record bases are element
+    // indices and reach 16 GB (coefficients) / 64 GB (blocks, transform blocks)
     for (int q = 0; q < nk0; q++) { const hc::k0::Pic& kp = b->pics[b->k0_pic_of[q]].k0->pic; koff[q].qp = zplace((size_t)kp.w8 * kp.h8, 1); }
     for (int q = 0; q < nk0; q++) { const hc::k0::Pic& kp = b->pics[b->k0_pic_of[q]].k0->pic; koff[q].ct_depth = zplace((size_t)kp.w8 * kp.h8, 1); }
     for (int q = 0; q < nk0; q++) { const hc::k0::Pic& kp = b->pics[b->k0_pic_of[q]].k0->pic; koff[q].wpp = zplace((size_t)kp.ctbs_h * hc::k0::CTX_BYTES, 16); }
-    for (int l = 0; l < 4; l++) {
-      for (int q = 0; q < nk0; q++) { const hc::k0::Pic& kp = b->pics[b->k0_pic_of[q]].k0->pic; list_cap[l] += ((size_t)kp.ctbs_w * kp.ctbs_h * kp.tb_cap_ctb >> (2 * l)) + 64; }
-      z_lists[l] = zplace(4 * list_cap[l], 16);
-    }
     // cleared to 1: intra prediction mode maps (DC)
     b->k0_ones_off = zplace(0, 256);
     for (int q = 0; q < nk0; q++) { const hc::k0::Pic& kp = b->pics[b->k0_pic_of[q]].k0->pic; koff[q].ipm = zplace((size_t)kp.w4 * kp.h4, 1); koff[q].ipm_c = zplace((size_t)kp.w4 * kp.h4, 1); }
@@ -615,6 +611,13 @@ int hc_batch_upload(hc_batch* b) {
     for (int q = 0; q < nk0; q++) { const hc::k0::Pic& kp = b->pics[b->k0_pic_of[q]].k0->pic; koff[q].progress = zplace(4 * (size_t)kp.ctbs_h, 4); }
     b->k0_status_off = zplace(4 * ((size_t)nk0 + 4), 16);
     b->k0_zero_bytes = z - b->k0_zero_off;
+    for (int q = 0; q < nk0; q++) { const hc::k0::Pic& kp = b->pics[b->k0_pic_of[q]].k0->pic; koff[q].blks = zplace(sizeof(hc_blk) * (size_t)kp.ctbs_w * kp.ctbs_h * kp.blk_cap_ctb, 16); }
+    for (int q = 0; q < nk0; q++) { const hc::k0::Pic& kp = b->pics[b->k0_pic_of[q]].k0->pic; koff[q].tbs = zplace(sizeof(hc_tb) * (size_t)kp.ctbs_w * kp.ctbs_h * kp.tb_cap_ctb, 16); }
+    for (int q = 0; q < nk0; q++) { const hc::k0::Pic& kp = b->pics[b->k0_pic_of[q]].k0->pic; koff[q].coeffs = zplace(sizeof(hc_coeff) * (size_t)kp.ctbs_w * kp.ctbs_h * kp.coeff_cap_ctb, 16); }
+    for (int l = 0; l < 4; l++) {
+      for (int q = 0; q < nk0; q++) { const hc::k0::Pic& kp = b->pics[b->k0_pic_of[q]].k0->pic; list_cap[l] += ((size_t)kp.ctbs_w * kp.ctbs_h * kp.tb_cap_ctb >> (2 * l)) + 64; }
+      z_lists[l] = zplace(4 * list_cap[l], 16);
+    }
   }
   const size_t arena_total = align_up(z, 256);
 
