@@ -125,9 +125,24 @@ constexpr int ERR_NONE = 0, ERR_BITSTREAM = 1, ERR_CAPACITY = 2;
 // ---- platform glue ------------------------------------------------------------------------------------------
 #if defined(__CUDA_ARCH__)
 HC_D int k0_clz(unsigned v) { return __clz((int)v); }
+HC_D int k0_popc(unsigned v) { return __popc(v); }
+HC_D int k0_ctz(unsigned v) { return __ffs((int)v) - 1; }
 HC_D int progress_load(const int* p) { return ld_acquire_s32(p); }
-HC_D void progress_store(int* p, int v) { __threadfence(); st_release_s32(p, v); }
-HC_D unsigned list_reserve(unsigned int* counter, unsigned n) { return atomicAdd(counter, n); }
+// the lanes of the chain's warp have all written parts of the row's maps / records: every lane fences its own writes, the
+// warp meets, one lane publishes
+HC_D void progress_store(int* p, int v) {
+  __threadfence();
+  __syncwarp();
+  if ((threadIdx.x & 31) == 0) st_release_s32(p, v);
+}
+// the lanes of a warp that run the same chain (warp-uniform execution) reserve once
+HC_D unsigned list_reserve(unsigned int* counter, unsigned n) {
+  const unsigned m = __activemask();
+  const int leader = __ffs((int)m) - 1;
+  unsigned r = 0;
+  if ((int)(threadIdx.x & 31) == leader) r = atomicAdd(counter, n);
+  return __shfl_sync(m, r, leader);
+}
 // A waiting chain polls a progress word of the row above. A CTB takes milliseconds to parse, so the poll interval grows
 // to ~16 us: the first version polled every ~80 ns (__nanosleep(400) returns much earlier than asked), and the wait loops
 // of the chains that cannot start yet issued as many instructions — and L2 requests on a handful of hot words — as all
@@ -135,6 +150,8 @@ HC_D unsigned list_reserve(unsigned int* counter, unsigned n) { return atomicAdd
 HC_D void backoff(unsigned& ns) { __nanosleep(ns); if (ns < 16384u) ns <<= 1; }
 #else
 HC_HD int k0_clz(unsigned v) { return __builtin_clz(v); }
+HC_HD int k0_popc(unsigned v) { return __builtin_popcount(v); }
+HC_HD int k0_ctz(unsigned v) { return __builtin_ctz(v); }
 HC_HD int progress_load(const int* p) { return *p; }
 HC_HD void progress_store(int* p, int v) { *p = v; }
 HC_HD unsigned list_reserve(unsigned int* counter, unsigned n) { const unsigned r = *counter; *counter += n; return r; }
@@ -161,6 +178,7 @@ struct Scratch {
   Pic pic;                           // copy of the picture descriptor
   Slice slice;                       // copy of the current slice segment descriptor
   uint8_t tb_size[TB_CAP_MAX];       // log2 - 2 of every transform block of the current CTB (K1 list flush, decode_ctu)
+  int32_t rem[16];                   // coeff_abs_level_remaining of the coefficients of the current sub-block (residual_coding)
 };
 constexpr int TABLE_BYTES = (int)((sizeof(Tables) + 15) & ~(size_t)15);
 constexpr int SCRATCH_BYTES = (int)((sizeof(Scratch) + 15) & ~(size_t)15);
@@ -537,10 +555,19 @@ struct Parser {
   int cu_x0, cu_y0, cu_log2;
   int filterLeftCbEdge, filterTopCbEdge;
 
+  // Device: the 32 lanes of a warp execute the parser with identical data (warp-uniform: one instruction issue serves all
+  // of them) and share out the data-parallel loops: `for (i = lane(); i < n; i += K0_LANES)`. After such a loop whose
+  // results later lanes read from memory, lanes_sync() orders the writes. Host: one lane.
 #if defined(__CUDA_ARCH__)
+  static constexpr int K0_LANES = 32;
+  HC_HD int lane() const { return (int)(threadIdx.x & 31); }
+  HC_HD void lanes_sync() const { __syncwarp(); }
   HC_HD const Tables& tab() const { return *reinterpret_cast<const Tables*>(k0_smem); }
   HC_HD Scratch& scratch() const { return *reinterpret_cast<Scratch*>(k0_smem + wbase); }
 #else
+  static constexpr int K0_LANES = 1;
+  HC_HD int lane() const { return 0; }
+  HC_HD void lanes_sync() const {}
   HC_HD const Tables& tab() const { return *T; }
   HC_HD Scratch& scratch() const { return *S; }
 #endif
@@ -554,7 +581,8 @@ struct Parser {
     const Tables& t = tab();
     uint8_t* ctx = ctxs();
     const int qp = slice().slice_qp_y;
-    K0_LOOP for (int i = 0; i < CX_COUNT; i++) ctx[i] = ctx_init_state(t.ctx_init[i], qp);
+    K0_LOOP for (int i = lane(); i < CX_COUNT; i += K0_LANES) ctx[i] = ctx_init_state(t.ctx_init[i], qp);
+    lanes_sync();
   }
 
   // ---- availability (no tiles: TS == RS) ----
@@ -668,12 +696,12 @@ struct Parser {
     }
     qPCbPrime = qPCb + p.qp_bd_offset_c < 0 ? 0 : qPCb + p.qp_bd_offset_c;
     qPCrPrime = qPCr + p.qp_bd_offset_c < 0 ? 0 : qPCr + p.qp_bd_offset_c;
-    const int n8 = ((1 << cu_log2) >> 3) < 1 ? 1 : ((1 << cu_log2) >> 3);
-    K0_LOOP for (int y = 0; y < n8; y++)
-      for (int x = 0; x < n8; x++) {
-        const int xx = (cu_x0 >> 3) + x, yy = (cu_y0 >> 3) + y;
-        if (xx < p.w8 && yy < p.h8) p.qp_map[xx + yy * p.w8] = (int8_t)QPY;
-      }
+    const int l8 = cu_log2 > 3 ? cu_log2 - 3 : 0, n8 = 1 << l8;
+    K0_LOOP for (int i = lane(); i < n8 * n8; i += K0_LANES) {
+      const int xx = (cu_x0 >> 3) + (i & (n8 - 1)), yy = (cu_y0 >> 3) + (i >> l8);
+      if (xx < p.w8 && yy < p.h8) p.qp_map[xx + yy * p.w8] = (int8_t)QPY;
+    }
+    lanes_sync();
     currentQPY = QPY;
   }
 
@@ -687,10 +715,10 @@ struct Parser {
     const uint8_t fl = left ? HC_EDGE_V : 0, ft = top ? HC_EDGE_H : 0;
     if (fl | ft) e[0] = (uint8_t)(fl | ft);
     if (left) {
-      K0_LOOP for (int k = 1; k < n4; k++) e[k * p.w4] = HC_EDGE_V;
+      K0_LOOP for (int k = 1 + lane(); k < n4; k += K0_LANES) e[k * p.w4] = HC_EDGE_V;
     }
     if (top) {
-      K0_LOOP for (int k = 1; k < n4; k++) e[k] = HC_EDGE_H;
+      K0_LOOP for (int k = 1 + lane(); k < n4; k += K0_LANES) e[k] = HC_EDGE_H;
     }
   }
 
@@ -857,44 +885,54 @@ struct Parser {
       const uint32_t signs = cb.bypass_bits(t, nsign) << (16 - nsign);
 
       if (ncoeff_total + (uint32_t)n > coeff_room) { fail(ERR_CAPACITY); return 0; }
-      int sumAbs = 0, rice = 0;
-      K0_LOOP for (int c = 0; c < n; c++) {
+      // (1) serial: coeff_abs_level_remaining of the coefficients that have one, in coding order (Rice adaptation)
+      int32_t* remv = scratch().rem;
+      int sumRem = 0, rice = 0;
+      uint32_t em = escmask;
+      K0_LOOP while (em) {
+        const int c = k0_ctz(em);
+        em &= em - 1;
         const int base = 1 + (int)((g1mask >> c) & 1) + ((c == firstG1) ? g2 : 0);
         int rem = 0;
-        if ((escmask >> c) & 1) {
-          const uint32_t q16 = cb.peek16(t);
-          const int ones = q16 == 0xffffu ? 16 : k0_clz(~(q16 << 16));
-          const int suffix_len = ones <= 3 ? rice : ones - 3 + rice;
-          const int len = ones + 1 + suffix_len;
-          if (len <= 16) {
-            const uint32_t bins = q16 >> (16 - len);
-            const int suffix = (int)(bins & ((1u << suffix_len) - 1u));
-            rem = ones <= 3 ? (ones << rice) + suffix : (((1 << (ones - 3)) + 3 - 1) << rice) + suffix;
-            cb.consume(len, bins);
-          } else {
-            int prefix = 0;
-            K0_LOOP while (prefix < 32 && cb.bypass()) prefix++;
-            if (prefix >= 32) { fail(ERR_BITSTREAM); return 0; }
-            if (prefix <= 3) rem = (prefix << rice) + (int)cb.bypass_bits(t, rice);
-            else rem = (((1 << (prefix - 3)) + 3 - 1) << rice) + (int)cb.bypass_bits(t, prefix - 3 + rice);
-          }
-          if (base + rem > 3 * (1 << rice)) { rice++; if (rice > 4) rice = 4; }
+        const uint32_t q16 = cb.peek16(t);
+        const int ones = q16 == 0xffffu ? 16 : k0_clz(~(q16 << 16));
+        const int suffix_len = ones <= 3 ? rice : ones - 3 + rice;
+        const int len = ones + 1 + suffix_len;
+        if (len <= 16) {
+          const uint32_t bins = q16 >> (16 - len);
+          const int suffix = (int)(bins & ((1u << suffix_len) - 1u));
+          rem = ones <= 3 ? (ones << rice) + suffix : (((1 << (ones - 3)) + 3 - 1) << rice) + suffix;
+          cb.consume(len, bins);
+        } else {
+          int prefix = 0;
+          K0_LOOP while (prefix < 32 && cb.bypass()) prefix++;
+          if (prefix >= 32) { fail(ERR_BITSTREAM); return 0; }
+          if (prefix <= 3) rem = (prefix << rice) + (int)cb.bypass_bits(t, rice);
+          else rem = (((1 << (prefix - 3)) + 3 - 1) << rice) + (int)cb.bypass_bits(t, prefix - 3 + rice);
         }
-        int level = base + rem;
-        const bool neg = (c < nsign) ? ((signs >> (15 - c)) & 1) : false;
-        if (neg) level = -level;
-        if (signHidden) {
-          sumAbs += base + rem;
-          if (c == n - 1 && (sumAbs & 1)) level = -level;
-        }
-        const int k = 31 - k0_clz(sig);
-        sig ^= 1u << k;
+        if (base + rem > 3 * (1 << rice)) { rice++; if (rice > 4) rice = 4; }
+        remv[c] = rem;
+        sumRem += rem;
+      }
+      // (2) lane-parallel: scan position k of the sub-block -> its record. Coefficient index c (coding order: from the
+      // highest position down) = number of significant positions above k; sign-data hiding flips the LAST coefficient when
+      // the sum of all absolute levels is odd — the sum of the base levels follows from the masks.
+      const int sumAbs = n + k0_popc(g1mask & ((1u << n) - 1u)) + (firstG1 < 16 ? g2 : 0) + sumRem;
+      const int pos0 = xS0 + (yS0 << log2);
+      K0_LOOP for (int k = 15 - lane(); k >= 0; k -= K0_LANES) {
+        if (!((sig >> k) & 1)) continue;
+        const int c = k0_popc(sig >> (k + 1));
+        int level = 1 + (int)((g1mask >> c) & 1) + ((c == firstG1) ? g2 : 0);
+        if ((escmask >> c) & 1) level += remv[c];
+        bool neg = (c < nsign) ? ((signs >> (15 - c)) & 1) : false;
+        if (signHidden && c == n - 1 && (sumAbs & 1)) neg = !neg;
         const int sp = scanPos[k];
         hc_coeff co;
-        co.pos = (uint16_t)((xS0 + (sp & 3)) + ((yS0 + (sp >> 2)) << log2));
-        co.level = (int16_t)level;
-        out[ncoeff_total++] = co;
+        co.pos = (uint16_t)(pos0 + (sp & 3) + ((sp >> 2) << log2));
+        co.level = (int16_t)(neg ? -level : level);
+        out[ncoeff_total + c] = co;
       }
+      ncoeff_total += (uint32_t)n;
     }
     cabac = cb;
     tb.ncoeff = (uint16_t)ncoeff_total;
@@ -1019,9 +1057,10 @@ struct Parser {
     const int nCbS = 1 << LOG2;
     cu_x0 = x0; cu_y0 = y0; cu_log2 = LOG2;
     {
-      const int n8 = nCbS >> 3;
-      K0_LOOP for (int y = 0; y < n8; y++)
-        for (int x = 0; x < n8; x++) p.ct_depth[((x0 >> 3) + x) + ((y0 >> 3) + y) * p.w8] = (uint8_t)depth;
+      const int l8 = LOG2 - 3, n8 = nCbS >> 3;     // CUs are at least 8 x 8
+      K0_LOOP for (int i = lane(); i < n8 * n8; i += K0_LANES)
+        p.ct_depth[((x0 >> 3) + (i & (n8 - 1))) + ((y0 >> 3) + (i >> l8)) * p.w8] = (uint8_t)depth;
+      lanes_sync();
     }
     // deblocking: which CU edges may be filtered (deblock.cc:165-215)
     filterLeftCbEdge = x0 != 0;
@@ -1087,9 +1126,10 @@ struct Parser {
           if (mode >= cand[n]) mode++;
       }
       luma_modes[idx] = mode;
-      const int n4 = pbOffset >> 2;
-      K0_LOOP for (int yy = 0; yy < n4; yy++)
-        for (int xx = 0; xx < n4; xx++) p.ipm[((x >> 2) + xx) + ((y >> 2) + yy) * p.w4] = (uint8_t)mode;
+      const int n4 = pbOffset >> 2, l4 = k0_ctz((unsigned)n4);
+      K0_LOOP for (int i = lane(); i < n4 * n4; i += K0_LANES)
+        p.ipm[((x >> 2) + (i & (n4 - 1))) + ((y >> 2) + (i >> l4)) * p.w4] = (uint8_t)mode;
+      lanes_sync();     // the next partition's candidate modes read this one's
     }
     const int cat = p.chroma_array_type;
     if (cat != 0) {
@@ -1105,10 +1145,11 @@ struct Parser {
         }
         if (cat == 2) m = tab().mode422[m];
         const int i = cat == 3 ? (idx & 1) * pbOffset : 0, j = cat == 3 ? (idx >> 1) * pbOffset : 0;
-        const int n4 = (cat == 3 ? pbOffset : nCbS) >> 2;
-        K0_LOOP for (int yy = 0; yy < n4; yy++)
-          for (int xx = 0; xx < n4; xx++) p.ipm_c[(((x0 + i) >> 2) + xx) + (((y0 + j) >> 2) + yy) * p.w4] = (uint8_t)m;
+        const int n4 = (cat == 3 ? pbOffset : nCbS) >> 2, l4 = k0_ctz((unsigned)n4);
+        K0_LOOP for (int q = lane(); q < n4 * n4; q += K0_LANES)
+          p.ipm_c[(((x0 + i) >> 2) + (q & (n4 - 1))) + (((y0 + j) >> 2) + (q >> l4)) * p.w4] = (uint8_t)m;
       }
+      lanes_sync();     // transform_unit reads the chroma mode of its position
     }
     cabac = cb;
     return (p.max_th_depth_intra + (nxn ? 1 : 0)) | (nxn ? 16 : 0);
@@ -1177,15 +1218,39 @@ struct Parser {
       const uint8_t* ts = scratch().tb_size;
       const uint32_t tb0 = p.tb_global_base + (uint32_t)ctb_rs * p.tb_cap_ctb;
       unsigned long long packed = 0;   // four 16-bit counters
+      unsigned slot[4];
+      uint32_t* dst[4];
+#if defined(__CUDA_ARCH__)
+      // lane-parallel: count, reserve once per size class, then an order-preserving compaction 32 blocks at a time
+      K0_LOOP for (uint32_t t = (uint32_t)lane(); t < ntb; t += K0_LANES) packed += 1ull << (16 * ts[t]);
+      K0_LOOP for (int o = 16; o > 0; o >>= 1) packed += __shfl_xor_sync(0xffffffffu, packed, o);
+      K0_LOOP for (int l = 0; l < 4; l++) {
+        const unsigned n = (unsigned)(packed >> (16 * l)) & 0xffffu;
+        slot[l] = n ? list_reserve(p.tb_counts + l, n) : 0u;
+        dst[l] = p.tb_lists[l];
+      }
+      const unsigned below = (1u << lane()) - 1u;
+      K0_LOOP for (uint32_t t0 = 0; t0 < ntb; t0 += K0_LANES) {
+        const uint32_t t = t0 + (uint32_t)lane();
+        const int sz = t < ntb ? (int)ts[t] : -1;
+#pragma unroll
+        for (int l = 0; l < 4; l++) {
+          const unsigned m = __ballot_sync(0xffffffffu, sz == l);
+          if (sz == l) dst[l][slot[l] + (unsigned)__popc(m & below)] = tb0 + t;
+          slot[l] += (unsigned)__popc(m);
+        }
+      }
+#else
       K0_LOOP for (uint32_t t = 0; t < ntb; t++) packed += 1ull << (16 * ts[t]);
       K0_LOOP for (int l = 0; l < 4; l++) {
         const unsigned n = (unsigned)(packed >> (16 * l)) & 0xffffu;
         if (!n) continue;
-        unsigned slot = list_reserve(p.tb_counts + l, n);
-        uint32_t* dst = p.tb_lists[l];
+        slot[l] = list_reserve(p.tb_counts + l, n);
+        dst[l] = p.tb_lists[l];
         K0_LOOP for (uint32_t t = 0; t < ntb; t++)
-          if (ts[t] == l) dst[slot++] = tb0 + t;
+          if (ts[t] == l) dst[l][slot[l]++] = tb0 + t;
       }
+#endif
     }
     uint32_t base = (uint32_t)ctb_rs * p.blk_cap_ctb;
     K0_LOOP for (int c = 0; c < 3; c++) {
@@ -1247,7 +1312,8 @@ struct Parser {
           if (p.ctbs_w > 1) {
             const uint32_t* src = reinterpret_cast<const uint32_t*>(p.wpp_ctx + (size_t)(ctb_y - 1) * CTX_BYTES);
             uint32_t* dst = reinterpret_cast<uint32_t*>(ctx);
-            K0_LOOP for (int i = 0; i < CTX_BYTES / 4; i++) dst[i] = src[i];
+            K0_LOOP for (int i = lane(); i < CTX_BYTES / 4; i += K0_LANES) dst[i] = src[i];
+            lanes_sync();
           } else {
             init_contexts();
           }
@@ -1258,7 +1324,7 @@ struct Parser {
         if (p.entropy_coding_sync && ctb_x == 1 && ctb_y < p.ctbs_h - 1) {
           uint32_t* dst = reinterpret_cast<uint32_t*>(p.wpp_ctx + (size_t)ctb_y * CTX_BYTES);
           const uint32_t* src = reinterpret_cast<const uint32_t*>(ctx);
-          K0_LOOP for (int i = 0; i < CTX_BYTES / 4; i++) dst[i] = src[i];
+          K0_LOOP for (int i = lane(); i < CTX_BYTES / 4; i += K0_LANES) dst[i] = src[i];
         }
         if (row_chain) progress_store(p.progress + ctb_y, ctb_x + 1);
         const int end_of_slice_segment = cabac.terminate();
