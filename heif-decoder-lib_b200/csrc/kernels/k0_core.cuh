@@ -148,6 +148,7 @@ HC_D unsigned list_reserve(unsigned int* counter, unsigned n) {
 // of the chains that cannot start yet issued as many instructions — and L2 requests on a handful of hot words — as all
 // working chains together (ncu: 14.3 G of 29.7 G warp instructions of an 8 x 12 MP batch).
 HC_D void backoff(unsigned& ns) { __nanosleep(ns); if (ns < 16384u) ns <<= 1; }
+HC_D void far_wait() { __nanosleep(200000u); }
 #else
 HC_HD int k0_clz(unsigned v) { return __builtin_clz(v); }
 HC_HD int k0_popc(unsigned v) { return __builtin_popcount(v); }
@@ -156,6 +157,7 @@ HC_HD int progress_load(const int* p) { return *p; }
 HC_HD void progress_store(int* p, int v) { *p = v; }
 HC_HD unsigned list_reserve(unsigned int* counter, unsigned n) { const unsigned r = *counter; *counter += n; return r; }
 HC_HD void backoff(unsigned&) {}
+HC_HD void far_wait() {}
 #endif
 
 // Per-chain scratch. On the device it lives in shared memory next to ONE copy of the tables per CTA (k0_parse.cu),
@@ -1305,8 +1307,16 @@ struct Parser {
         if (row_chain && ctb_y > 0) {
           // wavefront: the row above must be two CTBs ahead (its context table, split depths and SAO parameters)
           const int need = ctb_x + 2 < p.ctbs_w ? ctb_x + 2 : p.ctbs_w;
+          // a CTB of the row above takes milliseconds: while that row is two or more CTBs short of what this one needs
+          // (the chains of rows 1, 2 of a batch start long before their turn) the chain sleeps in long steps; within one CTB
+          // of its turn it polls with the short exponential back-off. The polling of the early rows was 6.7 % of all issued
+          // instructions of the kernel (profiles/r02_k0_v7_ncu.txt).
           unsigned ns = 256;
-          K0_LOOP while (progress_load(p.progress + ctb_y - 1) < need) backoff(ns);
+          K0_LOOP for (;;) {
+            const int have = progress_load(p.progress + ctb_y - 1);
+            if (have >= need) break;
+            if (need - have >= 2) far_wait(); else backoff(ns);
+          }
         }
         if (p.entropy_coding_sync && ctb_x == 0 && ctb_y >= 1 && !(first_of_independent && ctb_rs == slice().segment_address)) {
           if (p.ctbs_w > 1) {
