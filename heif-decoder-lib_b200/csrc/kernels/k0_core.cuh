@@ -376,6 +376,37 @@ static __device__ __noinline__ int cab_bin(uint32_t sa, uint32_t ta, int ci) {
   K0_CAB_STORE
   return (int)((st & 1) ^ is_lps);
 }
+// The sig_coeff_flag run of one sub-block (scan positions last_coeff .. 1) in one call. Lane k holds the context index
+// and the context state of position k; per bin the state comes by shuffle instead of a shared-memory load, the decoder
+// registers stay in registers, and a decoded bin updates every lane that holds the same context. The states go back to
+// shared memory once, at the end (lanes with the same context hold the same state).
+static __device__ __noinline__ uint32_t cab_sig_run(uint32_t sa, uint32_t ta, uint32_t myci, int last_coeff) {
+  const uint32_t sp = sa + CAB_CTX + myci;
+  uint32_t myst = lds8(sp);
+  K0_CAB_LOAD
+  uint32_t sig = 0;
+  K0_LOOP for (int k = last_coeff; k > 0; k--) {
+    const uint32_t st = __shfl_sync(0xffffffffu, myst, k);
+    const uint32_t ci = __shfl_sync(0xffffffffu, myci, k);
+    const uint32_t lps = lds8(ta + TAB_LPS + ((st >> 1) << 2) + ((range >> 6) & 3));
+    const uint32_t nxt = lds16(ta + TAB_NEXT + (st << 1));
+    const uint32_t rmps = range - lps;
+    const unsigned long long scaled = (unsigned long long)rmps << avail;
+    const uint32_t is_lps = value >= scaled;
+    if (is_lps) value -= scaled;
+    const uint32_t r = is_lps ? lps : rmps;
+    const int n = __clz((int)r) - 23;
+    range = r << n;
+    avail -= n;
+    const uint32_t ns = is_lps ? nxt >> 8 : nxt & 0xffu;
+    if (myci == ci) myst = ns;
+    sig |= ((st & 1u) ^ is_lps) << k;
+    K0_CAB_REFILL
+  }
+  sts8(sp, myst);
+  K0_CAB_STORE
+  return sig;
+}
 static __device__ __noinline__ int cab_bypass(uint32_t sa) {
   K0_CAB_LOAD
   avail--;
@@ -843,11 +874,15 @@ struct Parser {
 
       const int last_coeff = (i == lastSubBlock) ? lastScanPos - 1 : 15;
       if (i == lastSubBlock) sig = 1u << lastScanPos;
+#if defined(__CUDA_ARCH__)
+      if (last_coeff > 0) sig |= cab_sig_run(cb.sa, cb.ta, (uint32_t)(CX_SIG + (ts_ctx ? ts_c : sigtab[lane() & 15])), last_coeff);
+#else
       if (ts_ctx) {
         K0_LOOP for (int k = last_coeff; k > 0; k--) sig |= (uint32_t)cb.bin(t, ctx, CX_SIG + ts_c) << k;
       } else {
         K0_LOOP for (int k = last_coeff; k > 0; k--) sig |= (uint32_t)cb.bin(t, ctx, CX_SIG + sigtab[k]) << k;
       }
+#endif
       if (last_coeff >= 0) {
         if (sig != 0 || !inferSbDc) sig |= (uint32_t)cb.bin(t, ctx, CX_SIG + dc_ctx);
         else sig = 1;
