@@ -19,8 +19,9 @@ constexpr int K0_WARPS = 4;
 
 // MIN_CTAS: CTAs per SM the register allocation must allow (5 -> 96 registers, 6 -> 80, 8 -> 64). A chain uses one
 // lane, so resident chains per SM = 4 * MIN_CTAS is limited by registers x 32 lanes; HEIFCUDA_K0_OCC picks the trade-off
-// between spills in a chain and chains in flight. Measured per 32 x 12 MP: 5 -> 114 ms, 6 -> 109 ms (default),
-// 8 -> 109 ms, 10 -> 116 ms, 12 -> 129 ms.
+// between spills in a chain and chains in flight. Measured per 32 x 12 MP, v6 (one lane per chain): 5 -> 114 ms,
+// 6 -> 109 ms, 8 -> 109 ms, 10 -> 116 ms, 12 -> 129 ms; v7 (warp-uniform chains): 5 -> 102.8, 6 -> 103.2, 7 -> 100.2,
+// 8 -> 97.7 (default), 9 -> 97.4, 10 -> 110.2, 12 -> 115.0, 16 -> 126.2 ms.
 template <int MIN_CTAS>
 __global__ void __launch_bounds__(32 * K0_WARPS, MIN_CTAS) k0_parse_kernel(const k0::Tables* __restrict__ tables, const k0::Pic* __restrict__ pics,
                                                                           const k0::Sub* __restrict__ subs, const k0::Chain* __restrict__ chains,
@@ -73,10 +74,23 @@ void launch_k0(const k0::Tables* tables, const k0::Pic* pics, const k0::Sub* sub
                cudaStream_t stream) {
   if (nchains <= 0) return;
   static_assert(sizeof(k0::Tables) % 4 == 0, "tables are copied word-wise");
-  static const int occ = []() { const char* e = getenv("HEIFCUDA_K0_OCC"); return e ? atoi(e) : 6; }();
+  static const int occ = []() { const char* e = getenv("HEIFCUDA_K0_OCC"); return e ? atoi(e) : 8; }();
   const int smem = k0::TABLE_BYTES + K0_WARPS * k0::SCRATCH_BYTES;
   const int grid = (nchains + K0_WARPS - 1) / K0_WARPS;
-  if (occ >= 8) k0_parse_kernel<8><<<grid, 32 * K0_WARPS, smem, stream>>>(tables, pics, subs, chains, nchains);
+  // more than ten CTAs per SM need more shared memory than the default carve-out offers (12.4 KB per CTA)
+  static const bool carve = [&]() {
+    if (occ >= 16) cudaFuncSetAttribute(k0_parse_kernel<16>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    else if (occ >= 12) cudaFuncSetAttribute(k0_parse_kernel<12>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    else if (occ >= 10) cudaFuncSetAttribute(k0_parse_kernel<10>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    return true;
+  }();
+  (void)carve;
+  if (occ >= 16) k0_parse_kernel<16><<<grid, 32 * K0_WARPS, smem, stream>>>(tables, pics, subs, chains, nchains);
+  else if (occ >= 12) k0_parse_kernel<12><<<grid, 32 * K0_WARPS, smem, stream>>>(tables, pics, subs, chains, nchains);
+  else if (occ >= 10) k0_parse_kernel<10><<<grid, 32 * K0_WARPS, smem, stream>>>(tables, pics, subs, chains, nchains);
+  else if (occ >= 9) k0_parse_kernel<9><<<grid, 32 * K0_WARPS, smem, stream>>>(tables, pics, subs, chains, nchains);
+  else if (occ >= 8) k0_parse_kernel<8><<<grid, 32 * K0_WARPS, smem, stream>>>(tables, pics, subs, chains, nchains);
+  else if (occ == 7) k0_parse_kernel<7><<<grid, 32 * K0_WARPS, smem, stream>>>(tables, pics, subs, chains, nchains);
   else if (occ <= 5) k0_parse_kernel<5><<<grid, 32 * K0_WARPS, smem, stream>>>(tables, pics, subs, chains, nchains);
   else k0_parse_kernel<6><<<grid, 32 * K0_WARPS, smem, stream>>>(tables, pics, subs, chains, nchains);
 }
