@@ -684,13 +684,13 @@ int hc_heic_decode_stream_ext(hc_engine* e, int nfiles, const uint8_t* const* da
   // batch b, so they parse a share of the coded items themselves. "auto" (engine option -1) starts from a static prior
   // and follows the measured costs per item on either side, so that a rank with few host threads ends up at 0.
   const int share_opt = hc_engine_get_option(e, "host_share_pct");
-  // static prior (per coded 512 x 512 item, measured on B200 + this box's cores): device 0.078 ms in the steady state of
-  // the pipeline (K0-bound: 109 ms + 10 ms of K1..K5 per 1536 items); one host thread 6.6 ms for the slice data of an item
+  // static prior (per coded 512 x 512 item, measured on B200 + this box's cores): device 0.069 ms in the steady state of
+  // the pipeline (K0-bound: 97 ms + 9 ms of K1..K5 per 1536 items); one host thread 6.6 ms for the slice data of an item
   // it parses itself and 0.08 ms for the container / header work every item needs. The host must finish
   // n * c_hdr + share * n * c_host within 0.9 of the device's (1 - share) * n * c_dev, hence balanced_share() — which is 0
   // for a rank with two host threads (8 ranks on a 16-core box): there the headers alone take most of a period.
   const int pool_threads = threads > 0 ? threads : std::max(1, (int)std::thread::hardware_concurrency());
-  const double c_dev0 = 0.078e-3, c_host0 = 6.6e-3 / pool_threads, c_hdr0 = 0.08e-3 / pool_threads;
+  const double c_dev0 = 0.069e-3, c_host0 = 6.6e-3 / pool_threads, c_hdr0 = 0.08e-3 / pool_threads;
   auto balanced_share = [](double c_dev, double c_host, double c_hdr) {
     const double s = (0.9 * c_dev - c_hdr) / (c_host + 0.9 * c_dev);
     return std::max(0, std::min(90, (int)(100.0 * s + 0.5)));
