@@ -421,6 +421,7 @@ def main():
                     help="where the CABAC slice data is parsed: K0 on the GPU (default) or the host parser")
     ap.add_argument("--no-wpp", action="store_true", help="c2 content without wavefront substreams (one CABAC chain per 512 x 512 tile): "
                     "what K0's throughput depends on; not the BASELINE configuration")
+    ap.add_argument("--no-numa", action="store_true", help="multi-GPU runs: do not bind a rank's threads to the CPUs next to its GPU")
     ap.add_argument("--skip-baselines", action="store_true", help="kernel experiments: leave out the cpu_baseline and plugin_dropin arms")
     ap.add_argument("--skip-extras", action="store_true", help="leave out the c4 / c5 side measurements of the default run")
     args = ap.parse_args()
@@ -441,6 +442,22 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     cores = os.cpu_count() or 1
+    numa = None
+    if world > 1 and args.impl != "reference" and not args.no_numa:
+        # one rank per GPU on a two-socket box: keep the rank's threads (and with them its pinned buffers, which are placed
+        # where they are first touched) on the CPUs next to its GPU, so that uploads and read-backs do not cross the socket link
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+            words = pynvml.nvmlDeviceGetCpuAffinity(h, (cores + 63) // 64)
+            cpus = {64 * w + b for w, m in enumerate(words) for b in range(64) if (m >> b) & 1}
+            cpus &= set(os.sched_getaffinity(0))
+            if cpus and len(cpus) < cores:
+                os.sched_setaffinity(0, cpus)
+                numa = "%d cpus next to GPU %d" % (len(cpus), local_rank)
+        except Exception as e:      # no NVML, one socket, containers without the right: run unpinned
+            numa = "unpinned (%s)" % type(e).__name__
     cache = os.path.join(ROOT, "gpurun_out", "bench_content")
     file_mp = {"c2": GRID_W * GRID_H / 1e6, "c4": C4_W * C4_H / 1e6, "c5": C5_W * C5_H / 1e6}[wl]
 
@@ -560,7 +577,7 @@ def main():
             "value_what": "per step: H2D of the step's inputs + K0 (device CABAC parse) + K1..K5, CUDA events on the streams they run on",
             "value_reconstruction_only": world * mp_per_step / (m["recon_ms"] * 1e-3), "ms_per_step_reconstruction_only": m["recon_ms"],
             "config": {"workload": WORKLOADS[wl].replace("CTB64 WPP", "CTB64 no-WPP (NOT the BASELINE configuration)") if args.no_wpp else WORKLOADS[wl],
-                       "images_per_step_per_gpu": images, "distinct_files": len(distinct),
+                       "images_per_step_per_gpu": images, "distinct_files": len(distinct), "cpu_binding": numa,
                        "coded_pictures_per_step_per_gpu": images * (48 if wl == "c2" else 1),
                        "l2": "working set per step (planes + residuals + RGB, ~%d MB) exceeds the 126 MB L2; no explicit flush" % int(
                            images * file_mp * (1.5 + 1.5 + 3.0 + 3.0)),
