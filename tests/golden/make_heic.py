@@ -106,6 +106,25 @@ def build():
         tiles = [b.add_hevc_image(enc(128, 128, 1, 8, 110 + k), 128, 128, 1, 8, hidden=True) for k in range(6)]
         return b.add_grid(tiles, 2, 3, 300, 200)
     files["alpha_grid_on_grid_420_8"] = alpha_grid(colour_grid, 300, 200, 300, 200, 128, 120)
+    # what a phone writes around the picture: thumbnail ('thmb'), a non-alpha auxiliary image (HDR gain map URN), an Exif
+    # item, an ICC profile ('colr' prof) and pixi — none of it may disturb the decode of the primary grid
+    def phone_like():
+        import struct as _st
+        b = W.HeifBuilder()
+        tiles = [b.add_hevc_image(enc(128, 128, 1, 8, 130 + k), 128, 128, 1, 8, hidden=True) for k in range(6)]
+        icc = W.box(b"colr", b"prof" + bytes(range(64)) * 3)
+        pixi = W.fullbox(b"pixi", 0, 0, bytes([3, 8, 8, 8]))
+        gid = b.add_grid(tiles, 2, 3, 300, 200, extra_props=(icc, pixi, W.irot(1)))
+        thumb = b.add_hevc_image(enc(64, 48, 1, 8, 140), 64, 48, 1, 8, hidden=True)
+        b.refs.append((b"thmb", thumb, [gid]))
+        auxc = W.fullbox(b"auxC", 0, 0, b"urn:com:apple:photo:2020:aux:hdrgainmap\x00")
+        gain = b.add_hevc_image(enc(152, 104, 0, 8, 141), 152, 104, 0, 8, hidden=True, extra_props=(auxc,))
+        b.refs.append((b"auxl", gain, [gid]))
+        exif = b.add_item(b"Exif", _st.pack(">I", 6) + b"Exif\x00\x00MM\x00*" + bytes(40), [], hidden=True)
+        b.refs.append((b"cdsc", exif, [gid]))
+        b.primary = gid
+        return b.serialize()
+    files["phone_like_grid_irot90"] = phone_like()
     files["alpha_prem_420_8"] = heif_writer.single_image(enc(200, 120, 1, 8, 77), 200, 120, 1, 8, alpha_stream=enc(200, 120, 0, 8, 78), premultiplied=True)
     files["single_420_8_gbr"] = heif_writer.single_image(enc(200, 120, 1, 8, 76, matrix=0), 200, 120, 1, 8)
     return files
