@@ -685,12 +685,12 @@ int hc_heic_decode_stream_ext(hc_engine* e, int nfiles, const uint8_t* const* da
   // and follows the measured costs per item on either side, so that a rank with few host threads ends up at 0.
   const int share_opt = hc_engine_get_option(e, "host_share_pct");
   // static prior (per coded 512 x 512 item, measured on B200 + this box's cores): device 0.069 ms in the steady state of
-  // the pipeline (K0-bound: 97 ms + 9 ms of K1..K5 per 1536 items); one host thread 6.6 ms for the slice data of an item
+  // the pipeline (K0-bound: 97 ms + 9 ms of K1..K5 per 1536 items); one host thread 4 ms for the slice data of an item
   // it parses itself and 0.08 ms for the container / header work every item needs. The host must finish
   // n * c_hdr + share * n * c_host within 0.9 of the device's (1 - share) * n * c_dev, hence balanced_share() — which is 0
   // for a rank with two host threads (8 ranks on a 16-core box): there the headers alone take most of a period.
   const int pool_threads = threads > 0 ? threads : std::max(1, (int)std::thread::hardware_concurrency());
-  const double c_dev0 = 0.069e-3, c_host0 = 6.6e-3 / pool_threads, c_hdr0 = 0.08e-3 / pool_threads;
+  const double c_dev0 = 0.069e-3, c_host0 = 4.0e-3 / pool_threads, c_hdr0 = 0.08e-3 / pool_threads;
   auto balanced_share = [](double c_dev, double c_host, double c_hdr) {
     const double s = (0.9 * c_dev - c_hdr) / (c_host + 0.9 * c_dev);
     return std::max(0, std::min(90, (int)(100.0 * s + 0.5)));
@@ -755,7 +755,7 @@ int hc_heic_decode_stream_ext(hc_engine* e, int nfiles, const uint8_t* const* da
   struct InFlight { hc_heic_job* job = nullptr; int index = 0; int slot = 0; std::vector<size_t> offs; std::vector<uint8_t*> ptrs; std::vector<size_t> strides; std::vector<int> map; clock::time_point t0; double host_s = 0, host_wait_s = 0; int share = 0; int rc = HC_OK; };
   void* pinned[DEPTH] = {};
   size_t pinned_cap[DEPTH] = {};
-  double t_done[3] = {0, 0, 0};   // host time at which the last three batches were seen complete
+  double t_done[5] = {0, 0, 0, 0, 0};   // host time at which the last five batches were seen complete
   int rc = HC_OK;
   std::string err;
   auto submit = [&](hc_heic_job* j, int b, InFlight& f) -> int {
@@ -820,8 +820,9 @@ int hc_heic_decode_stream_ext(hc_engine* e, int nfiles, const uint8_t* const* da
       if (hc_heic_job_stage_ms(j, ms) == HC_OK) {
         const double gpu_ms = ms[1] + ms[2] + ms[3] + ms[4] + ms[5] + ms[7];
         st.device_ms += gpu_ms;
-        t_done[0] = t_done[1]; t_done[1] = t_done[2]; t_done[2] = tb;
-        if (share_opt < 0 && f.index > DEPTH && f.host_s > 0 && t_done[0] > 0) {
+        for (int q = 0; q < 4; q++) t_done[q] = t_done[q + 1];
+        t_done[4] = tb;
+        if (share_opt < 0 && f.index > DEPTH && f.host_s > 0 && t_done[2] > 0) {
           // Cost per coded item on either side, smoothed; the balanced share is c_dev / (c_host + c_dev). The K0 kernels of
           // consecutive batches overlap, so a batch's own event times say little; what the device costs per item is the
           // pipeline period (completion to completion, averaged over two batches because overlapping batches tend to finish
@@ -829,12 +830,14 @@ int hc_heic_decode_stream_ext(hc_engine* e, int nfiles, const uint8_t* const* da
           // host parse of the batch.
           const double n_items = (double)j->items.size();
           const double n_host = n_items * f.share / 100.0, n_dev = std::max(1.0, n_items - n_host);
-          const double period = (t_done[2] - t_done[0]) / 2, cd = period / n_dev;
+          // overlapping batches finish in pairs (60 ms, 250 ms, 60 ms, ...): the period is taken over four completions when
+          // there are that many, else over two
+          const double period = t_done[0] > 0 ? (t_done[4] - t_done[0]) / 4 : (t_done[4] - t_done[2]) / 2, cd = period / n_dev;
           // slow, outlier-resistant tracking: one noisy batch (a host thread descheduled) must not swing the share
-          if (n_host < 1.0) c_hdr = 0.7 * c_hdr + 0.3 * std::min(f.host_s / n_items, 2.0 * c_hdr);
-          else c_host = 0.7 * c_host + 0.3 * std::min(std::max(0.0, f.host_s - n_items * c_hdr) / n_host, 2.0 * c_host);
+          if (n_host < 1.0) c_hdr = 0.5 * c_hdr + 0.5 * std::min(f.host_s / n_items, 2.0 * c_hdr);
+          else c_host = 0.5 * c_host + 0.5 * std::min(std::max(0.0, f.host_s - n_items * c_hdr) / n_host, 2.0 * c_host);
           const bool gpu_bound = f.host_wait_s < 0.05 * period;
-          if (gpu_bound) c_dev = 0.7 * c_dev + 0.3 * std::min(cd, 2.0 * c_dev);
+          if (gpu_bound) c_dev = 0.5 * c_dev + 0.5 * std::min(cd, 2.0 * c_dev);
           share.store(balanced_share(c_dev, c_host, c_hdr));
           if (trace_on()) fprintf(stderr, "[heifcuda] batch %d: host %.1f ms (waited %.1f ms for it), period %.1f ms, own gpu events %.1f ms, share %d%% -> %d%%\n", f.index, f.host_s * 1e3, f.host_wait_s * 1e3, period * 1e3, gpu_ms, f.share, share.load());
         }
