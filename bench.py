@@ -412,7 +412,7 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--images", type=int, default=0, help="files per step and GPU (default: 64 for c2 — K0 is a wavefront per picture, its ramps "
-                    "amortise better over 64 files than 32: value 3.6 -> 3.9 GP/s — and 192 for c4)")
+                    "amortise better over 64 files than 32: value 3.6 -> 3.9 GP/s — and 384 for c4)")
     ap.add_argument("--distinct", type=int, default=8, help="distinct synthetic files (replicated to --images)")
     ap.add_argument("--threads", type=int, default=0, help="host parse threads (0 = all cores)")
     ap.add_argument("--host-share", type=int, default=-1, help="with --parser device: %% of the coded items parsed by the host threads "
@@ -427,7 +427,7 @@ def main():
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     wl = args.workload
-    images = args.images or (192 if wl == "c4" else 64)
+    images = args.images or (384 if wl == "c4" else 64)
     if not args.images and wl == "c2":
         # 64 files per step need ~8 GB of pinned host memory per rank in the stream API (three output buffers in flight); a box
         # that cannot give every rank three times that runs 32 files per step. Same answer on every rank of the box.
@@ -620,7 +620,7 @@ def main():
     # ---- side measurements of the default run: C4 (short) and C5 on the same box ----
     if extras:
         try:
-            n4 = 96
+            n4 = 384      # 1080p pictures are 17 chains each: 96 files fill a third of K0's chain slots (value 1.5 GP/s), 384 fill them (3.2)
             files4 = [c4_files[(i + rank) % len(c4_files)] for i in range(n4)]
             m4 = measure_list(hb, eng, files4, max(3, args.steps // 3), 3, threads, n4, barrier, max_over_ranks, local_rank, sample_clocks=False)
             mp4 = n4 * C4_W * C4_H / 1e6
