@@ -667,8 +667,21 @@ int hc_heic_decode_stream(hc_engine* e, int nfiles, const uint8_t* const* data, 
 }
 
 int hc_heic_decode_stream_ext(hc_engine* e, int nfiles, const uint8_t* const* data, const size_t* sizes, int want_alpha,
-                              int threads, int files_per_batch, const hc_stream_dest* dests, int* file_status, hc_image_callback on_image,
+                              int threads, int files_per_batch_arg, const hc_stream_dest* dests, int* file_status, hc_image_callback on_image,
                               void* user, hc_stream_stats* stats) {
+  int files_per_batch = files_per_batch_arg;
+  if (e && nfiles > 0 && data && sizes && files_per_batch == 0) {
+    // automatic batch size: the device parser wants some 20,000 substream chains in flight and the kernels behind it stream;
+    // measured optimum 64 files of 12 MP (3.6 -> 3.9 GP/s against 32) and 384 of 1080p (1.5 -> 3.2 GP/s against 96), i.e.
+    // about 800 MP of output per batch — taken from the size of the first file's primary image
+    double mp = 12.0;
+    hc::HeifFile hf;
+    if (hf.parse(data[0], sizes[0]).empty()) {
+      const hc::HeifItem* it = hf.item(hf.primary_id());
+      if (it && it->ispe_w > 0 && it->ispe_h > 0) mp = (double)it->ispe_w * it->ispe_h / 1e6;
+    }
+    files_per_batch = (int)std::max(1.0, std::min(512.0, 800.0 / std::max(mp, 0.05)));
+  }
   if (!e || nfiles <= 0 || !data || !sizes || files_per_batch <= 0) {
     hc::set_last_error("hc_heic_decode_stream: bad argument");
     return HC_ERR_ARGUMENT;

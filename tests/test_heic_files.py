@@ -255,6 +255,22 @@ def test_gpu_decode_stream_fill_and_drain(engine, nbatches):
 
 
 @pytest.mark.gpu
+def test_gpu_decode_stream_automatic_batch_size(engine):
+    """files_per_batch = 0: the library picks the batch size from the size of the first image (about 800 MP per batch;
+    these small fixtures all fit one batch of at most 512 files); every image once, in order, bit-exact."""
+    names = NAMES * 3
+    seen = []
+
+    def on_image(index, desc, rows):
+        key = {hb.OUT_RGB: "rgb", hb.OUT_RGBA: "rgba", hb.OUT_RRGGBB_LE: "rrggbb_le", hb.OUT_RRGGBBAA_LE: "rrggbbaa_le"}[desc.out_format]
+        seen.append((index, md5(rows.tobytes()) == META[names[index]][key + "_md5"]))
+
+    st = hb.decode_stream(engine, [load(n) for n in names], on_image, want_alpha=False, threads=4, files_per_batch=0)
+    assert [i for i, _ in seen] == list(range(len(names))) and all(ok for _, ok in seen)
+    assert st["batches"] == 1
+
+
+@pytest.mark.gpu
 def test_gpu_decode_stream_external_destinations(engine):
     """hc_heic_decode_stream_ext: the reference's ext_dst semantics (heif.h:1605-1615, pixelimage.cc:221-266) — final pixels in
     the caller's buffer with the caller's stride when it is large enough, the library's own memory otherwise."""
