@@ -673,13 +673,18 @@ int hc_heic_decode_stream_ext(hc_engine* e, int nfiles, const uint8_t* const* da
   if (e && nfiles > 0 && data && sizes && files_per_batch == 0) {
     // automatic batch size: the device parser wants some 20,000 substream chains in flight and the kernels behind it stream;
     // measured optimum 64 files of 12 MP (3.6 -> 3.9 GP/s against 32) and 384 of 1080p (1.5 -> 3.2 GP/s against 96), i.e.
-    // about 800 MP of output per batch — taken from the size of the first file's primary image
-    double mp = 12.0;
-    hc::HeifFile hf;
-    if (hf.parse(data[0], sizes[0]).empty()) {
+    // about 800 MP of output per batch — taken from the size of the LARGEST primary image among up to 32 files sampled
+    // evenly over the list (a batch of the largest must fit)
+    double mp = 0.0;
+    const int nsample = std::min(nfiles, 32);
+    for (int q = 0; q < nsample; q++) {
+      const int k = (int)((long long)q * nfiles / nsample);
+      hc::HeifFile hf;
+      if (!hf.parse(data[k], sizes[k]).empty()) continue;
       const hc::HeifItem* it = hf.item(hf.primary_id());
-      if (it && it->ispe_w > 0 && it->ispe_h > 0) mp = (double)it->ispe_w * it->ispe_h / 1e6;
+      if (it && it->ispe_w > 0 && it->ispe_h > 0) mp = std::max(mp, (double)it->ispe_w * it->ispe_h / 1e6);
     }
+    if (mp <= 0.0) mp = 12.0;
     files_per_batch = (int)std::max(1.0, std::min(512.0, 800.0 / std::max(mp, 0.05)));
   }
   if (!e || nfiles <= 0 || !data || !sizes || files_per_batch <= 0) {
