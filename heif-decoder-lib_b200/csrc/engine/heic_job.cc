@@ -769,10 +769,12 @@ int hc_heic_decode_stream_ext(hc_engine* e, int nfiles, const uint8_t* const* da
   // delivered: K0 is a wavefront per picture, so the head and the tail of one batch's K0 leave most of the resident chain
   // slots idle (16 files: 22 CTB slots of time for 16.6 slots of work); with the next batch's K0 already queued on its own
   // low-priority stream, its chains take those slots, and K1..K5 + D2H of the finished batch run at high priority meanwhile.
-  constexpr int DEPTH = 3;
+  constexpr int MAX_DEPTH = 6;
+  static const int depth_env = []() { const char* m = getenv("HEIFCUDA_STREAM_DEPTH"); const int v = m ? atoi(m) : 3; return v < 2 ? 2 : (v > MAX_DEPTH ? MAX_DEPTH : v); }();
+  const int DEPTH = depth_env;
   struct InFlight { hc_heic_job* job = nullptr; int index = 0; int slot = 0; std::vector<size_t> offs; std::vector<uint8_t*> ptrs; std::vector<size_t> strides; std::vector<int> map; clock::time_point t0; double host_s = 0, host_wait_s = 0; int share = 0; int rc = HC_OK; };
-  void* pinned[DEPTH] = {};
-  size_t pinned_cap[DEPTH] = {};
+  void* pinned[MAX_DEPTH] = {};
+  size_t pinned_cap[MAX_DEPTH] = {};
   double t_done[5] = {0, 0, 0, 0, 0};   // host time at which the last five batches were seen complete
   int rc = HC_OK;
   std::string err;
@@ -881,7 +883,7 @@ int hc_heic_decode_stream_ext(hc_engine* e, int nfiles, const uint8_t* const* da
     f.job = nullptr;
   };
 
-  InFlight ring[DEPTH];
+  InFlight ring[MAX_DEPTH];
   // the host side runs up to two batches ahead of the submit stage: completions of overlapping batches come in bursts,
   // and a single batch of look-ahead left this thread waiting for the parser right after every burst
   constexpr int PARSE_AHEAD = 2;
