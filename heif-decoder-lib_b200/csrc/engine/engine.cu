@@ -56,6 +56,7 @@ struct hc_engine {
   int premultiply_alpha = 0;               // hc_heic_job: RGBA output multiplied by alpha in K5
   int chroma_upsampling = 0;               // HC_UPSAMPLE_*: colour conversion of hc_heic_job / hc_heic_decode_stream
   bool fused_postfilter = false;           // HEIFCUDA_POSTFILTER=fused: K3+K4 as one shared-memory tile kernel (measured slower: both forms are bound by instruction issue, not HBM — DESIGN.md)
+  cudaEvent_t origin = nullptr;            // HEIFCUDA_TRACE: time zero of hc_batch_timeline_ms
   int host_share_pct = -1;                 // hc_heic_job with device_parse: percentage of the coded items the host threads parse meanwhile
 
   Block take(std::vector<Block>& list, size_t size, bool pinned) {
@@ -1320,6 +1321,24 @@ int hc_batch_stage_ms(hc_batch* b, float ms[8]) {
   b->csc_events.clear();
   ms[6] = b->last_d2h_ms;
   if (b->nk0 && b->k0_done) cudaEventElapsedTime(&ms[7], b->ev_k0[0], b->ev_k0[1]);
+  cudaGetLastError();
+  return HC_OK;
+}
+
+// internal (heic_job.cc, HEIFCUDA_TRACE): where the batch's device phases lie on the engine's clock — milliseconds since the
+// engine's origin event for [0] upload start, [1] K0 start, [2] K0 end, [3] K1 start, [4] K4 end (K5 follows)
+extern "C" int hc_batch_timeline_ms(hc_batch* b, float t[5]) {
+  if (!b || !t) return HC_ERR_ARGUMENT;
+  hc_engine* e = b->eng;
+  {
+    std::lock_guard<std::mutex> lk(e->mu);
+    if (!e->origin) { cudaEventCreate(&e->origin); cudaEventRecord(e->origin, b->stream); cudaEventSynchronize(e->origin); }
+  }
+  for (int i = 0; i < 5; i++) t[i] = 0.f;
+  cudaEventElapsedTime(&t[0], e->origin, b->ev[0]);
+  if (b->nk0 && b->k0_done) { cudaEventElapsedTime(&t[1], e->origin, b->ev_k0[0]); cudaEventElapsedTime(&t[2], e->origin, b->ev_k0[1]); }
+  cudaEventElapsedTime(&t[3], e->origin, b->ev[2]);
+  cudaEventElapsedTime(&t[4], e->origin, b->ev[6]);
   cudaGetLastError();
   return HC_OK;
 }

@@ -22,6 +22,7 @@
 
 extern "C" void hc_batch_set_pack_threads(hc_batch* b, int n);   // engine.cu (internal)
 extern "C" int hc_batch_failed_pictures(const hc_batch* b, const int** pics);
+extern "C" int hc_batch_timeline_ms(hc_batch* b, float t[5]);
 
 namespace {
 
@@ -838,6 +839,11 @@ int hc_heic_decode_stream_ext(hc_engine* e, int nfiles, const uint8_t* const* da
     if (r == HC_OK) {
       float ms[8];
       if (hc_heic_job_stage_ms(j, ms) == HC_OK) {
+        if (trace_on()) {
+          float tl[5];
+          if (hc_batch_timeline_ms(j->batch, tl) == HC_OK)
+            fprintf(stderr, "[heifcuda] batch %d timeline (ms on the GPU clock): upload %.1f, K0 %.1f .. %.1f, K1 %.1f .. K4 end %.1f\n", f.index, tl[0], tl[1], tl[2], tl[3], tl[4]);
+        }
         const double gpu_ms = ms[1] + ms[2] + ms[3] + ms[4] + ms[5] + ms[7];
         st.device_ms += gpu_ms;
         for (int q = 0; q < 4; q++) t_done[q] = t_done[q + 1];
