@@ -217,15 +217,15 @@ def plugin_arm(files, threads):
         mp = GRID_W * GRID_H / 1e6
         want = R.decode(f0, R.COLORSPACE_RGB, R.CHROMA_RGB, threads=threads, decoder_id="libde265")["interleaved"][0]
         got = R.decode(f0, R.COLORSPACE_RGB, R.CHROMA_RGB, threads=threads, decoder_id="cuda")["interleaved"][0]   # also the warm-up
-        n = 3
-        t0 = time.perf_counter()
-        for _ in range(n):
-            R.decode(f0, R.COLORSPACE_RGB, R.CHROMA_RGB, threads=threads, decoder_id="cuda")
-        dt = (time.perf_counter() - t0) / n
-        t0 = time.perf_counter()
-        for _ in range(n):
-            R.decode(f0, R.COLORSPACE_RGB, R.CHROMA_RGB, threads=threads, decoder_id="libde265")
-        dt_ref = (time.perf_counter() - t0) / n
+        def median_time(decoder, n=7):       # single decodes of one file vary by tens of per cent: the median of seven
+            ts = []
+            for _ in range(n):
+                t0 = time.perf_counter()
+                R.decode(f0, R.COLORSPACE_RGB, R.CHROMA_RGB, threads=threads, decoder_id=decoder)
+                ts.append(time.perf_counter() - t0)
+            return sorted(ts)[n // 2]
+        dt = median_time("cuda")
+        dt_ref = median_time("libde265")
         return {"value": mp / dt, "unit": UNIT, "ms_per_image": dt * 1e3, "tile_threads": threads,
                 "libde265_plugin_same_call": {"value": mp / dt_ref, "ms_per_image": dt_ref * 1e3},
                 "bit_exact_vs_libde265_plugin": hashlib.md5(got).digest() == hashlib.md5(want).digest(),
