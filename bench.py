@@ -48,6 +48,7 @@ WORKLOADS = {
     "c4": "C4: list of 1920x1080 single-picture HEIC files sharded by image, 8-bit 4:2:0, CTB64 WPP SAO+deblock QP26 -> RGB24",
     "c5": "C5: one 11520x8704 grid of 391 512x512 tiles, tile rows split across the GPUs, K5 writes into rank 0's buffer over NVLink -> RGB24",
 }
+STREAM_DEPTH = 6     # the most batches hc_heic_decode_stream keeps in flight (3, or 6 when read-backs are slow: heic_job.cc)
 METRIC = "decoded MP/s HEIC->RGB (device-timed)"
 UNIT = "MP/s"
 STAGES = ("k1_transform", "k2_intra", "k3_deblock", "k4_sao", "k5_csc")
@@ -283,10 +284,11 @@ def measure_list(hb, eng, files, steps, warmup, threads, images, barrier, max_ov
     job.close()
 
     # end to end: one call of the public streaming API. The figure is the STEADY-STATE period of the pipeline: deliveries of
-    # the first two and the last two batches are left out (three batches are in flight: the first delivery comes late
+    # the first and the last depth - 1 batches are left out (`depth` batches are in flight: the first delivery comes late
     # relative to the ones behind it, the last batches drain without successors — over 40 batches the first-to-last figure
     # is 6 % better than the middle of the run, tools/stream_depth_probe.py), so 4 + e2e_steps batches are decoded.
     e2e_steps = max(12, min(steps, 32))
+    skip = STREAM_DEPTH - 1   # deliveries left out at either end: the batches in flight behind / ahead of the window
     marks, checksum = [], [0]
 
     def on_image(index, desc, rows):
@@ -297,9 +299,9 @@ def measure_list(hb, eng, files, steps, warmup, threads, images, barrier, max_ov
 
     barrier()
     t_start = time.perf_counter()
-    st = hb.decode_stream(eng, files * (5 + e2e_steps), on_image, want_alpha=False, threads=threads, files_per_batch=images)
+    st = hb.decode_stream(eng, files * (2 * skip + 1 + e2e_steps), on_image, want_alpha=False, threads=threads, files_per_batch=images)
     barrier()
-    e2e_dt = max_over_ranks((marks[-3] - marks[2]) / e2e_steps)
+    e2e_dt = max_over_ranks((marks[-1 - skip] - marks[skip]) / e2e_steps)
     e2e_first_to_last = max_over_ranks((marks[-1] - marks[0]) / (len(marks) - 1))
     return {"dev_ms": dev_ms, "recon_ms": recon_ms, "stage": acc, "stage_recon": stage_recon, "launches": launches, "clocks": clocks,
             "upload_bytes": upload_bytes, "parity": check, "e2e_dt": e2e_dt, "e2e_steps": e2e_steps, "first_batch_s": marks[0] - t_start,
@@ -591,8 +593,8 @@ def main():
                     "d2h_bytes_per_step": int(st["bytes_d2h"] / max(1, st["batches"])), "ms_per_step": m["e2e_dt"] * 1e3,
                     "host_parse_ms_per_step": st["seconds_parse"] / st["batches"] * 1e3,
                     "gpu_phase_ms_per_step": st["seconds_gpu_phase"] / st["batches"] * 1e3, "first_batch_ms": m["first_batch_s"] * 1e3,
-                    "steps": m["e2e_steps"],
-                    "excluded": "steady-state period: deliveries of the first two batches (pipeline fill, first allocations, pinned buffers: first_batch_ms) and of the last two (drain) are outside the timed window",
+                    "steps": m["e2e_steps"], "batches_in_flight": st.get("depth"),
+                    "excluded": "steady-state period: deliveries of the first (pipeline depth - 1) batches (pipeline fill, first allocations, pinned buffers: first_batch_ms) and of the last (depth - 1) (drain) are outside the timed window",
                     "value_first_to_last_delivery": world * mp_per_step / m["e2e_first_to_last"],
                     "api": "hc_heic_decode_stream: three batches in flight on the GPU (K0 on a low-priority stream, K1..K5 + copies on "
                            "high-priority ones), header parse (+ host share of the slice data) two batches ahead; pinned host output"},

@@ -40,6 +40,8 @@ int hc_batch_set_rgb_target(hc_batch*, int, void*, size_t) { return NO_ENGINE();
 void hc_batch_set_pack_threads(hc_batch*, int) {}
 int hc_batch_failed_pictures(const hc_batch*, const int**) { return 0; }
 int hc_batch_timeline_ms(hc_batch*, float*) { return NO_ENGINE(); }
+void hc_batch_mark_d2h(hc_batch*, int) {}
+float hc_batch_async_d2h_ms(hc_batch*) { return 0.f; }
 int hc_batch_add_overlay_canvas(hc_batch*, int, int, const uint16_t*) { return NO_ENGINE(); }
 int hc_batch_overlay_add_child(hc_batch*, int, int, int, int, const hc_csc_params*) { return NO_ENGINE(); }
 hc_shared_image* hc_shared_image_create(hc_engine*, int, int, int) { NO_ENGINE(); return nullptr; }

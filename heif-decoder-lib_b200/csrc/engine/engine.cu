@@ -1249,6 +1249,17 @@ int hc_batch_copy_rgb_device(hc_batch* b, int canvas, void* dst, size_t dst_stri
   return batch_sync_checked(b, "cudaStreamSynchronize");
 }
 
+// internal (heic_job.cc): brackets the asynchronous read-backs of a batch with events; hc_batch_async_d2h_ms (after a sync)
+// says how long the copies took on the device's copy engine, queueing behind other batches' copies included
+extern "C" void hc_batch_mark_d2h(hc_batch* b, int which) {
+  if (b && (which == 0 || which == 1)) cudaEventRecord(b->ev_d2h[which], b->stream);
+}
+extern "C" float hc_batch_async_d2h_ms(hc_batch* b) {
+  float ms = 0.f;
+  if (b && cudaEventElapsedTime(&ms, b->ev_d2h[0], b->ev_d2h[1]) != cudaSuccess) { cudaGetLastError(); ms = 0.f; }
+  return ms;
+}
+
 int hc_batch_read_rgb_async(hc_batch* b, int canvas, void* dst, size_t dst_stride) {
   if (!b || !dst || canvas < 0 || canvas >= (int)b->canvases.size()) { hc::set_last_error("hc_batch_read_rgb_async: bad argument"); return HC_ERR_ARGUMENT; }
   const Canvas& c = b->canvases[canvas];

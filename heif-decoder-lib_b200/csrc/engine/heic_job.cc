@@ -23,6 +23,8 @@
 extern "C" void hc_batch_set_pack_threads(hc_batch* b, int n);   // engine.cu (internal)
 extern "C" int hc_batch_failed_pictures(const hc_batch* b, const int** pics);
 extern "C" int hc_batch_timeline_ms(hc_batch* b, float t[5]);
+extern "C" void hc_batch_mark_d2h(hc_batch* b, int which);
+extern "C" float hc_batch_async_d2h_ms(hc_batch* b);
 
 namespace {
 
@@ -764,23 +766,35 @@ int hc_heic_decode_stream_ext(hc_engine* e, int nfiles, const uint8_t* const* da
     return p;
   };
 
-  // stage 2 (this thread): submit — upload, [K0,] K1..K5 and the read-back into one of DEPTH pinned buffers are only
-  // ENQUEUED on the batch's streams; stage 3 (this thread, DEPTH-1 batches behind): deliver — wait for the stream, hand the
-  // images out, release the batch. DEPTH = 3 keeps two batches queued on the GPU behind the one that is about to be
+  // stage 2 (this thread): submit — upload, [K0,] K1..K5 and the read-back into a pinned buffer are only ENQUEUED on the
+  // batch's streams; stage 3 (this thread, depth-1 batches behind): deliver — wait for the stream, hand the images out,
+  // release the batch. Three batches in flight keep two queued on the GPU behind the one that is about to be
   // delivered: K0 is a wavefront per picture, so the head and the tail of one batch's K0 leave most of the resident chain
   // slots idle (16 files: 22 CTB slots of time for 16.6 slots of work); with the next batch's K0 already queued on its own
   // low-priority stream, its chains take those slots, and K1..K5 + D2H of the finished batch run at high priority meanwhile.
+  // The K0 kernels of the batches in flight share the GPU and finish together, so their read-backs come as a burst. When a
+  // read-back is short against the period (one GPU on its own host link: 42 of 185 ms) three in flight is the best depth
+  // (4.6 against 4.1-4.2 GP/s with four or six); when eight GPUs read back over one host link (200 ms per batch, the period
+  // itself) the GPU idles through the burst unless another group of batches is parsing meanwhile: six in flight give 28.7
+  // GP/s against 23.0 on the 8-GPU box. The depth therefore follows the measured read-back time (HEIFCUDA_STREAM_DEPTH fixes it).
   constexpr int MAX_DEPTH = 6;
-  static const int depth_env = []() { const char* m = getenv("HEIFCUDA_STREAM_DEPTH"); const int v = m ? atoi(m) : 3; return v < 2 ? 2 : (v > MAX_DEPTH ? MAX_DEPTH : v); }();
-  const int DEPTH = depth_env;
-  struct InFlight { hc_heic_job* job = nullptr; int index = 0; int slot = 0; std::vector<size_t> offs; std::vector<uint8_t*> ptrs; std::vector<size_t> strides; std::vector<int> map; clock::time_point t0; double host_s = 0, host_wait_s = 0; int share = 0; int rc = HC_OK; };
+  static const int depth_env = []() { const char* m = getenv("HEIFCUDA_STREAM_DEPTH"); const int v = m ? atoi(m) : 0; return v <= 0 ? 0 : (v < 2 ? 2 : (v > MAX_DEPTH ? MAX_DEPTH : v)); }();
+  int depth = depth_env ? depth_env : 3;
+  struct InFlight { hc_heic_job* job = nullptr; int index = 0; int slot = -1; std::vector<size_t> offs; std::vector<uint8_t*> ptrs; std::vector<size_t> strides; std::vector<int> map; clock::time_point t0; double host_s = 0, host_wait_s = 0; int share = 0; int rc = HC_OK; };
   void* pinned[MAX_DEPTH] = {};
   size_t pinned_cap[MAX_DEPTH] = {};
+  bool pinned_busy[MAX_DEPTH] = {};
+  double last_period = 0;               // seconds between completions, smoothed (below)
+  double best_d2h_ms = 0;               // shortest read-back of a batch seen so far
   double t_done[5] = {0, 0, 0, 0, 0};   // host time at which the last five batches were seen complete
   int rc = HC_OK;
   std::string err;
   auto submit = [&](hc_heic_job* j, int b, InFlight& f) -> int {
-    f.job = j; f.index = b; f.slot = b % DEPTH; f.t0 = clock::now();
+    f.job = j; f.index = b; f.t0 = clock::now();
+    f.slot = 0;
+    for (int k = 0; k < MAX_DEPTH; k++)
+      if (!pinned_busy[k]) { f.slot = k; break; }     // at most `depth` <= MAX_DEPTH batches are in flight
+    pinned_busy[f.slot] = true;
     size_t need = 0;
     f.offs.resize(j->images.size());
     f.ptrs.assign(j->images.size(), nullptr);
@@ -809,10 +823,12 @@ int hc_heic_decode_stream_ext(hc_engine* e, int nfiles, const uint8_t* const* da
     int r = (pinned[f.slot] || need == 0) ? hc_heic_job_upload(j) : HC_ERR_MEMORY;
     const double tb = now_s();
     if (r == HC_OK) r = hc_heic_job_run(j);
+    if (r == HC_OK) hc_batch_mark_d2h(j->batch, 0);
     for (size_t i = 0; r == HC_OK && i < j->images.size(); i++) {
       if (!f.ptrs[i]) f.ptrs[i] = (uint8_t*)pinned[f.slot] + f.offs[i];
       r = hc_batch_read_rgb_async(j->batch, j->images[i].canvas, f.ptrs[i], f.strides[i]);
     }
+    if (r == HC_OK) hc_batch_mark_d2h(j->batch, 1);
     if (trace_on()) fprintf(stderr, "[heifcuda] batch %d submit: pinned %.2f ms, upload %.2f ms, enqueue %.2f ms\n", b, (ta - std::chrono::duration<double>(f.t0.time_since_epoch()).count()) * 1e3, (tb - ta) * 1e3, (now_s() - tb) * 1e3);
     return r;
   };
@@ -820,6 +836,7 @@ int hc_heic_decode_stream_ext(hc_engine* e, int nfiles, const uint8_t* const* da
     hc_heic_job* j = f.job;
     const double ta = now_s();
     if (r == HC_OK) r = hc_heic_job_sync(j);
+    const double d2h_ms = r == HC_OK || r == HC_ERR_BITSTREAM ? (double)hc_batch_async_d2h_ms(j->batch) : 0.0;
     std::vector<char> bad(j->images.size(), 0);
     if (r == HC_ERR_BITSTREAM && file_status) {
       // slice data the device parser rejected: the pictures are known, the other files of the batch are intact
@@ -848,7 +865,7 @@ int hc_heic_decode_stream_ext(hc_engine* e, int nfiles, const uint8_t* const* da
         st.device_ms += gpu_ms;
         for (int q = 0; q < 4; q++) t_done[q] = t_done[q + 1];
         t_done[4] = tb;
-        if (share_opt < 0 && f.index > DEPTH && f.host_s > 0 && t_done[2] > 0) {
+        if (share_opt < 0 && f.index > 3 && f.host_s > 0 && t_done[2] > 0) {
           // Cost per coded item on either side, smoothed; the balanced share is c_dev / (c_host + c_dev). The K0 kernels of
           // consecutive batches overlap, so a batch's own event times say little; what the device costs per item is the
           // pipeline period (completion to completion, averaged over two batches because overlapping batches tend to finish
@@ -859,6 +876,7 @@ int hc_heic_decode_stream_ext(hc_engine* e, int nfiles, const uint8_t* const* da
           // overlapping batches finish in pairs (60 ms, 250 ms, 60 ms, ...): the period is taken over four completions when
           // there are that many, else over two
           const double period = t_done[0] > 0 ? (t_done[4] - t_done[0]) / 4 : (t_done[4] - t_done[2]) / 2, cd = period / n_dev;
+          last_period = period;
           // slow, outlier-resistant tracking: one noisy batch (a host thread descheduled) must not swing the share
           if (n_host < 1.0) c_hdr = 0.5 * c_hdr + 0.5 * std::min(f.host_s / n_items, 2.0 * c_hdr);
           else c_host = 0.5 * c_host + 0.5 * std::min(std::max(0.0, f.host_s - n_items * c_hdr) / n_host, 2.0 * c_host);
@@ -887,9 +905,21 @@ int hc_heic_decode_stream_ext(hc_engine* e, int nfiles, const uint8_t* const* da
     st.seconds_gpu_phase += secs(f.t0, clock::now());
     st.batches++;
     f.job = nullptr;
+    if (f.slot >= 0) pinned_busy[f.slot] = false;
+    // depth of the pipeline: follows how long a batch's read-back takes against the period (see above)
+    // (the shortest read-back seen so far counts: the others queued behind the copies of the batches that finished with them)
+    if (d2h_ms > 0 && (best_d2h_ms == 0 || d2h_ms < best_d2h_ms)) best_d2h_ms = d2h_ms;
+    if (!depth_env && best_d2h_ms > 0 && last_period > 0) {
+      const double ratio = best_d2h_ms * 1e-3 / last_period;
+      const int before = depth;
+      if (ratio > 0.6) depth = MAX_DEPTH;
+      else if (ratio < 0.4) depth = 3;
+      if (trace_on() && depth != before) fprintf(stderr, "[heifcuda] batch %d: read-back %.1f ms of a %.1f ms period: %d batches in flight from now on\n", f.index, best_d2h_ms, last_period * 1e3, depth);
+    }
+    st.depth = depth;
   };
 
-  InFlight ring[MAX_DEPTH];
+  std::deque<InFlight> flight;   // submitted, not yet delivered, in submission order
   // the host side runs up to two batches ahead of the submit stage: completions of overlapping batches come in bursts,
   // and a single batch of look-ahead left this thread waiting for the parser right after every burst
   constexpr int PARSE_AHEAD = 2;
@@ -911,20 +941,17 @@ int hc_heic_decode_stream_ext(hc_engine* e, int nfiles, const uint8_t* const* da
       continue;   // keep draining the pipeline (with error isolation: every file of the batch failed and is reported)
     }
     if (rc != HC_OK) { hc_heic_job_destroy(cur.job); continue; }
-    InFlight& f = ring[b % DEPTH];
-    if (f.job) deliver(f, f.rc);    // batch b - DEPTH (only after a skipped batch; normally delivered below)
+    while ((int)flight.size() >= depth) { deliver(flight.front(), flight.front().rc); flight.pop_front(); }   // room for this one
+    flight.emplace_back();
+    InFlight& f = flight.back();
     f.host_s = cur.seconds;
     f.map = cur.map;
     f.host_wait_s = host_wait;
     f.share = cur.share;
     f.rc = submit(cur.job, b, f);
-    InFlight& o = ring[(b + 1) % DEPTH];   // batch b - (DEPTH - 1)
-    if (o.job) deliver(o, o.rc);
+    while ((int)flight.size() > depth - 1) { deliver(flight.front(), flight.front().rc); flight.pop_front(); }   // depth - 1 stay queued
   }
-  for (int k = 1; k <= DEPTH; k++) {       // drain in submission order
-    InFlight& o = ring[(nbatches + k) % DEPTH];
-    if (o.job) deliver(o, o.rc);
-  }
+  while (!flight.empty()) { deliver(flight.front(), flight.front().rc); flight.pop_front(); }   // drain in submission order
   for (void* p : pinned)
     if (p) hc_host_free(p);
   st.seconds_total = secs(t_begin, clock::now());

@@ -64,7 +64,7 @@ class StreamStats(C.Structure):
     """hc_stream_stats"""
     _fields_ = [("seconds_total", C.c_double), ("seconds_parse", C.c_double), ("seconds_gpu_phase", C.c_double),
                 ("device_ms", C.c_double), ("bytes_h2d", C.c_uint64), ("bytes_d2h", C.c_uint64), ("pixels", C.c_int64),
-                ("batches", C.c_int32), ("launches", C.c_int32), ("files_failed", C.c_int32)]
+                ("batches", C.c_int32), ("launches", C.c_int32), ("files_failed", C.c_int32), ("depth", C.c_int32)]
 
 
 class StreamDest(C.Structure):

@@ -426,6 +426,7 @@ typedef struct hc_stream_stats {
   int64_t pixels;            /* output pixels delivered                                           */
   int32_t batches, launches;
   int32_t files_failed;      /* files reported through file_status (hc_heic_decode_stream_ext)   */
+  int32_t depth;             /* batches in flight at the end of the call (3, or 6 when read-backs are slow) */
 } hc_stream_stats;
 int hc_heic_decode_stream(hc_engine* e, int nfiles, const uint8_t* const* data, const size_t* sizes, int want_alpha,
                           int threads, int files_per_batch, hc_image_callback on_image, void* user,
