@@ -41,6 +41,8 @@ void hc_batch_set_pack_threads(hc_batch*, int) {}
 int hc_batch_failed_pictures(const hc_batch*, const int**) { return 0; }
 int hc_batch_timeline_ms(hc_batch*, float*) { return NO_ENGINE(); }
 void hc_batch_mark_d2h(hc_batch*, int) {}
+void* hc_engine_take_out_pinned(hc_engine*, size_t, size_t*) { NO_ENGINE(); return nullptr; }
+void hc_engine_give_out_pinned(hc_engine*, void*, size_t) {}
 float hc_batch_async_d2h_ms(hc_batch*) { return 0.f; }
 int hc_batch_add_overlay_canvas(hc_batch*, int, int, const uint16_t*) { return NO_ENGINE(); }
 int hc_batch_overlay_add_child(hc_batch*, int, int, int, int, const hc_csc_params*) { return NO_ENGINE(); }

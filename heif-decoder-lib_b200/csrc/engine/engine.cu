@@ -45,6 +45,7 @@ struct hc_engine {
   int device = 0;
   std::mutex mu;
   std::vector<Block> free_dev, free_pin;
+  std::vector<Block> free_out_pin;   // pinned output buffers of hc_heic_decode_stream (gigabytes each: pinning one takes a second)
   std::vector<cudaStream_t> free_streams;      // batch streams (highest priority: K1..K5, copies)
   std::vector<cudaStream_t> free_k0_streams;   // K0 streams (lowest priority), see hc_batch_reconstruct_async
   int prio_lo = 0, prio_hi = 0;
@@ -263,6 +264,7 @@ void hc_engine_destroy(hc_engine* e) {
   cudaSetDevice(e->device);
   for (auto& b : e->free_dev) cudaFree(b.p);
   for (auto& b : e->free_pin) cudaFreeHost(b.p);
+  for (auto& b : e->free_out_pin) cudaFreeHost(b.p);
   for (auto s : e->free_streams) cudaStreamDestroy(s);
   for (auto s : e->free_k0_streams) cudaStreamDestroy(s);
   for (auto ev : e->free_events) cudaEventDestroy(ev);
@@ -1249,6 +1251,19 @@ int hc_batch_copy_rgb_device(hc_batch* b, int canvas, void* dst, size_t dst_stri
   return batch_sync_checked(b, "cudaStreamSynchronize");
 }
 
+// internal (heic_job.cc): the stream API's pinned output buffers live as long as the engine — a second call, or a pipeline
+// that grows deeper, does not pin gigabytes again (1.3 s per 2.6 GB buffer measured)
+extern "C" void* hc_engine_take_out_pinned(hc_engine* e, size_t bytes, size_t* cap) {
+  if (!e || !cuda_ok(cudaSetDevice(e->device), "cudaSetDevice")) return nullptr;
+  Block b = e->take(e->free_out_pin, bytes, true);
+  if (cap) *cap = b.cap;
+  return b.p;
+}
+extern "C" void hc_engine_give_out_pinned(hc_engine* e, void* p, size_t cap) {
+  if (!e || !p) return;
+  Block b; b.p = p; b.cap = cap;
+  e->give(e->free_out_pin, b);
+}
 // internal (heic_job.cc): brackets the asynchronous read-backs of a batch with events; hc_batch_async_d2h_ms (after a sync)
 // says how long the copies took on the device's copy engine, queueing behind other batches' copies included
 extern "C" void hc_batch_mark_d2h(hc_batch* b, int which) {

@@ -25,6 +25,8 @@ extern "C" int hc_batch_failed_pictures(const hc_batch* b, const int** pics);
 extern "C" int hc_batch_timeline_ms(hc_batch* b, float t[5]);
 extern "C" void hc_batch_mark_d2h(hc_batch* b, int which);
 extern "C" float hc_batch_async_d2h_ms(hc_batch* b);
+extern "C" void* hc_engine_take_out_pinned(hc_engine* e, size_t bytes, size_t* cap);
+extern "C" void hc_engine_give_out_pinned(hc_engine* e, void* p, size_t cap);
 
 namespace {
 
@@ -815,9 +817,9 @@ int hc_heic_decode_stream_ext(hc_engine* e, int nfiles, const uint8_t* const* da
       need += (row * d.height + 255) & ~(size_t)255;
     }
     if (need > pinned_cap[f.slot]) {
-      if (pinned[f.slot]) hc_host_free(pinned[f.slot]);
-      pinned[f.slot] = hc_host_alloc(need + need / 8);
-      pinned_cap[f.slot] = pinned[f.slot] ? need + need / 8 : 0;
+      if (pinned[f.slot]) hc_engine_give_out_pinned(e, pinned[f.slot], pinned_cap[f.slot]);
+      pinned[f.slot] = hc_engine_take_out_pinned(e, need + need / 8, &pinned_cap[f.slot]);
+      if (!pinned[f.slot]) pinned_cap[f.slot] = 0;
     }
     const double ta = now_s();
     int r = (pinned[f.slot] || need == 0) ? hc_heic_job_upload(j) : HC_ERR_MEMORY;
@@ -912,9 +914,9 @@ int hc_heic_decode_stream_ext(hc_engine* e, int nfiles, const uint8_t* const* da
     if (!depth_env && best_d2h_ms > 0 && last_period > 0) {
       const double ratio = best_d2h_ms * 1e-3 / last_period;
       const int before = depth;
-      if (ratio > 0.6) depth = MAX_DEPTH;
-      else if (ratio < 0.4) depth = 3;
-      if (trace_on() && depth != before) fprintf(stderr, "[heifcuda] batch %d: read-back %.1f ms of a %.1f ms period: %d batches in flight from now on\n", f.index, best_d2h_ms, last_period * 1e3, depth);
+      if (ratio > 0.4) depth = MAX_DEPTH;
+      else if (ratio < 0.3) depth = 3;
+      if (trace_on() && (depth != before || f.index == 6)) fprintf(stderr, "[heifcuda] batch %d: read-back %.1f ms of a %.1f ms period: %d batches in flight from now on\n", f.index, best_d2h_ms, last_period * 1e3, depth);
     }
     st.depth = depth;
   };
@@ -952,8 +954,8 @@ int hc_heic_decode_stream_ext(hc_engine* e, int nfiles, const uint8_t* const* da
     while ((int)flight.size() > depth - 1) { deliver(flight.front(), flight.front().rc); flight.pop_front(); }   // depth - 1 stay queued
   }
   while (!flight.empty()) { deliver(flight.front(), flight.front().rc); flight.pop_front(); }   // drain in submission order
-  for (void* p : pinned)
-    if (p) hc_host_free(p);
+  for (int k = 0; k < MAX_DEPTH; k++)
+    if (pinned[k]) hc_engine_give_out_pinned(e, pinned[k], pinned_cap[k]);     // kept by the engine for the next call
   st.seconds_total = secs(t_begin, clock::now());
   if (stats) *stats = st;
   if (rc != HC_OK) hc::set_last_error(err);
