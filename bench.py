@@ -218,6 +218,8 @@ def plugin_arm(files, threads):
         mp = GRID_W * GRID_H / 1e6
         want = R.decode(f0, R.COLORSPACE_RGB, R.CHROMA_RGB, threads=threads, decoder_id="libde265")["interleaved"][0]
         got = R.decode(f0, R.COLORSPACE_RGB, R.CHROMA_RGB, threads=threads, decoder_id="cuda")["interleaved"][0]   # also the warm-up
+        for _ in range(3):                                                                                          # pools, clocks
+            R.decode(f0, R.COLORSPACE_RGB, R.CHROMA_RGB, threads=threads, decoder_id="cuda")
         def median_time(decoder, n=7):       # single decodes of one file vary by tens of per cent: the median of seven
             ts = []
             for _ in range(n):
@@ -644,14 +646,16 @@ def main():
 
     # ---- CPU baseline on the box's cores (rank 0, N = 1 only) ----
     cpu, plugin = None, None
+    if rank == 0 and world == 1 and not args.skip_baselines and wl == "c2":
+        # the plugin arm runs right behind the GPU measurements (after the CPU arm the GPU has idled for ten seconds and single
+        # one-tile batches do not bring its clocks back up: 55 instead of 110 MP/s measured), on an engine of its own
+        eng.close()
+        eng = None
+        plugin = plugin_arm(c2_files, cores)
     if rank == 0 and world == 1 and not args.skip_baselines and wl != "c5":
         r = reference_arm(c2_files if wl == "c2" else c4_files, 2, 1, cores, file_mp)
         cpu = {"value": r["value"] if r else None, "unit": UNIT, "cores": cores, "kind": "reference",
                "sample": r["sample"] if r else "oracle/_ref missing on this box"}
-    if rank == 0 and world == 1 and not args.skip_baselines and wl == "c2":
-        eng.close()
-        eng = None
-        plugin = plugin_arm(c2_files, cores)
     line["cpu_baseline"] = cpu
     line["plugin_dropin"] = plugin
 
