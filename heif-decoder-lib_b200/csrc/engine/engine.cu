@@ -57,6 +57,8 @@ struct hc_engine {
   int premultiply_alpha = 0;               // hc_heic_job: RGBA output multiplied by alpha in K5
   int chroma_upsampling = 0;               // HC_UPSAMPLE_*: colour conversion of hc_heic_job / hc_heic_decode_stream
   bool fused_postfilter = false;           // HEIFCUDA_POSTFILTER=fused: K3+K4 as one shared-memory tile kernel (measured slower: both forms are bound by instruction issue, not HBM — DESIGN.md)
+  int stream_depth = 0;                    // hc_heic_decode_stream: batches in flight; 0 = automatic (3 or 6 by the measured read-back time), 2..6 fixed
+  int stream_depth_learned = 0;            // what the last automatic call ended with: the next call starts there
   cudaEvent_t origin = nullptr;            // HEIFCUDA_TRACE: time zero of hc_batch_timeline_ms
   int host_share_pct = -1;                 // hc_heic_job with device_parse: percentage of the coded items the host threads parse meanwhile
 
@@ -277,6 +279,8 @@ int hc_engine_set_option(hc_engine* e, const char* name, int value) {
   if (!strcmp(name, "device_parse")) { e->device_parse = value; return HC_OK; }
   if (!strcmp(name, "k0_max_critical_ctbs")) { e->k0_max_critical = value < 1 ? 1 : value; return HC_OK; }
   if (!strcmp(name, "fused_postfilter")) { e->fused_postfilter = value != 0; return HC_OK; }
+  if (!strcmp(name, "stream_depth")) { e->stream_depth = value <= 0 ? 0 : (value < 2 ? 2 : (value > 6 ? 6 : value)); return HC_OK; }
+  if (!strcmp(name, "stream_depth_learned")) { e->stream_depth_learned = value; return HC_OK; }
   if (!strcmp(name, "host_share_pct")) { e->host_share_pct = value < 0 ? -1 : (value > 100 ? 100 : value); return HC_OK; }
   if (!strcmp(name, "premultiply_alpha")) { e->premultiply_alpha = value != 0; return HC_OK; }
   if (!strcmp(name, "chroma_upsampling")) {
@@ -291,6 +295,8 @@ int hc_engine_get_option(const hc_engine* e, const char* name) {
   if (!e || !name) return 0;
   if (!strcmp(name, "device_parse")) return e->device_parse;
   if (!strcmp(name, "fused_postfilter")) return e->fused_postfilter ? 1 : 0;
+  if (!strcmp(name, "stream_depth")) return e->stream_depth;
+  if (!strcmp(name, "stream_depth_learned")) return e->stream_depth_learned;
   if (!strcmp(name, "host_share_pct")) return e->host_share_pct;
   if (!strcmp(name, "chroma_upsampling")) return e->chroma_upsampling;
   if (!strcmp(name, "premultiply_alpha")) return e->premultiply_alpha;

@@ -780,8 +780,16 @@ int hc_heic_decode_stream_ext(hc_engine* e, int nfiles, const uint8_t* const* da
   // itself) the GPU idles through the burst unless another group of batches is parsing meanwhile: six in flight give 28.7
   // GP/s against 23.0 on the 8-GPU box. The depth therefore follows the measured read-back time (HEIFCUDA_STREAM_DEPTH fixes it).
   constexpr int MAX_DEPTH = 6;
-  static const int depth_env = []() { const char* m = getenv("HEIFCUDA_STREAM_DEPTH"); const int v = m ? atoi(m) : 0; return v <= 0 ? 0 : (v < 2 ? 2 : (v > MAX_DEPTH ? MAX_DEPTH : v)); }();
-  int depth = depth_env ? depth_env : 3;
+  // fixed by the engine option "stream_depth" or HEIFCUDA_STREAM_DEPTH; otherwise automatic, starting from what the
+  // engine's previous call ended with
+  int depth_fixed = hc_engine_get_option(e, "stream_depth");
+  if (const char* m = getenv("HEIFCUDA_STREAM_DEPTH")) {
+    const int v = atoi(m);
+    if (v > 0) depth_fixed = std::max(2, std::min(MAX_DEPTH, v));
+  }
+  const int depth_env = depth_fixed;       // 0: automatic
+  const int learned = hc_engine_get_option(e, "stream_depth_learned");
+  int depth = depth_env ? depth_env : (learned >= 2 && learned <= MAX_DEPTH ? learned : 3);
   struct InFlight { hc_heic_job* job = nullptr; int index = 0; int slot = -1; std::vector<size_t> offs; std::vector<uint8_t*> ptrs; std::vector<size_t> strides; std::vector<int> map; clock::time_point t0; double host_s = 0, host_wait_s = 0; int share = 0; int rc = HC_OK; };
   void* pinned[MAX_DEPTH] = {};
   size_t pinned_cap[MAX_DEPTH] = {};
@@ -956,6 +964,7 @@ int hc_heic_decode_stream_ext(hc_engine* e, int nfiles, const uint8_t* const* da
   while (!flight.empty()) { deliver(flight.front(), flight.front().rc); flight.pop_front(); }   // drain in submission order
   for (int k = 0; k < MAX_DEPTH; k++)
     if (pinned[k]) hc_engine_give_out_pinned(e, pinned[k], pinned_cap[k]);     // kept by the engine for the next call
+  if (!depth_env) hc_engine_set_option(e, "stream_depth_learned", depth);
   st.seconds_total = secs(t_begin, clock::now());
   if (stats) *stats = st;
   if (rc != HC_OK) hc::set_last_error(err);

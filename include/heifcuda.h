@@ -225,6 +225,9 @@ void hc_engine_destroy(hc_engine* e);
  * is parsed by the host threads instead, which run while the GPU is busy with the previous batch of
  * hc_heic_decode_stream (hybrid parse). Default -1 = automatic: none for a single hc_heic_job, and in
  * hc_heic_decode_stream a share that follows the measured host / GPU time per batch.
+ * "stream_depth" (environment HEIFCUDA_STREAM_DEPTH; default 0 = automatic): batches hc_heic_decode_stream keeps in flight,
+ * 2..6. Automatic: 3, or 6 once a batch's read-back is measured to take more than 0.4 of the period between completions
+ * (several GPUs reading back over one host link); the engine remembers the choice for its next call.
  * "chroma_upsampling" (default HC_UPSAMPLE_NEAREST): HC_UPSAMPLE_BILINEAR makes hc_heic_job / hc_heic_decode_stream convert
  * with bilinear chroma upsampling (see hc_csc_select_opt).
  * "premultiply_alpha" (default 0): 1 makes hc_heic_job / hc_heic_decode_stream multiply interleaved RGBA 8-bit output by its
