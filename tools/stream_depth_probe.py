@@ -1,7 +1,12 @@
+"""Steady state of hc_heic_decode_stream over N batches of 64 twelve-megapixel files: whole call, first-to-last delivery and
+the middle half of the run (the figure that does not depend on pipeline fill and drain). HEIFCUDA_STREAM_DEPTH=3..6 fixes
+the batches in flight.   python tools/stream_depth_probe.py 40"""
 import sys, time, os
-sys.path.insert(0, "/root/repo"); sys.path.insert(0, "/root/repo/heif-decoder-lib_b200")
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "heif-decoder-lib_b200")):
+    sys.path.insert(0, p)
 import bench, heif_b200 as hb
-files = bench.make_content(8, os.path.join("/root/repo", "gpurun_out", "bench_content"))
+files = bench.make_content(8, os.path.join(ROOT, "gpurun_out", "bench_content"))
 eng = hb.Engine(0)
 n, per = int(sys.argv[1]), 64
 lst = [files[i % 8] for i in range(per)] * n
