@@ -794,6 +794,7 @@ int hc_heic_decode_stream_ext(hc_engine* e, int nfiles, const uint8_t* const* da
   void* pinned[MAX_DEPTH] = {};
   size_t pinned_cap[MAX_DEPTH] = {};
   bool pinned_busy[MAX_DEPTH] = {};
+  bool pin_failed = false, depth_locked = false;
   double last_period = 0;               // seconds between completions, smoothed (below)
   double best_d2h_ms = 0;               // shortest read-back of a batch seen so far
   double t_done[5] = {0, 0, 0, 0, 0};   // host time at which the last five batches were seen complete
@@ -827,7 +828,14 @@ int hc_heic_decode_stream_ext(hc_engine* e, int nfiles, const uint8_t* const* da
     if (need > pinned_cap[f.slot]) {
       if (pinned[f.slot]) hc_engine_give_out_pinned(e, pinned[f.slot], pinned_cap[f.slot]);
       pinned[f.slot] = hc_engine_take_out_pinned(e, need + need / 8, &pinned_cap[f.slot]);
-      if (!pinned[f.slot]) pinned_cap[f.slot] = 0;
+      if (!pinned[f.slot]) {
+        // the host cannot pin another output buffer: the caller falls back to a shallower pipeline (below)
+        pinned_cap[f.slot] = 0;
+        pinned_busy[f.slot] = false;
+        f.slot = -1;
+        pin_failed = true;
+        return HC_ERR_MEMORY;
+      }
     }
     const double ta = now_s();
     int r = (pinned[f.slot] || need == 0) ? hc_heic_job_upload(j) : HC_ERR_MEMORY;
@@ -875,6 +883,9 @@ int hc_heic_decode_stream_ext(hc_engine* e, int nfiles, const uint8_t* const* da
         st.device_ms += gpu_ms;
         for (int q = 0; q < 4; q++) t_done[q] = t_done[q + 1];
         t_done[4] = tb;
+        // overlapping batches finish in pairs or triplets (60 ms, 250 ms, 60 ms, ...): the period between completions is taken
+        // over four of them when there are that many, else over two
+        if (t_done[2] > 0) last_period = t_done[0] > 0 ? (t_done[4] - t_done[0]) / 4 : (t_done[4] - t_done[2]) / 2;
         if (share_opt < 0 && f.index > 3 && f.host_s > 0 && t_done[2] > 0) {
           // Cost per coded item on either side, smoothed; the balanced share is c_dev / (c_host + c_dev). The K0 kernels of
           // consecutive batches overlap, so a batch's own event times say little; what the device costs per item is the
@@ -883,10 +894,7 @@ int hc_heic_decode_stream_ext(hc_engine* e, int nfiles, const uint8_t* const* da
           // host parse of the batch.
           const double n_items = (double)j->items.size();
           const double n_host = n_items * f.share / 100.0, n_dev = std::max(1.0, n_items - n_host);
-          // overlapping batches finish in pairs (60 ms, 250 ms, 60 ms, ...): the period is taken over four completions when
-          // there are that many, else over two
-          const double period = t_done[0] > 0 ? (t_done[4] - t_done[0]) / 4 : (t_done[4] - t_done[2]) / 2, cd = period / n_dev;
-          last_period = period;
+          const double period = last_period, cd = period / n_dev;
           // slow, outlier-resistant tracking: one noisy batch (a host thread descheduled) must not swing the share
           if (n_host < 1.0) c_hdr = 0.5 * c_hdr + 0.5 * std::min(f.host_s / n_items, 2.0 * c_hdr);
           else c_host = 0.5 * c_host + 0.5 * std::min(std::max(0.0, f.host_s - n_items * c_hdr) / n_host, 2.0 * c_host);
@@ -919,7 +927,7 @@ int hc_heic_decode_stream_ext(hc_engine* e, int nfiles, const uint8_t* const* da
     // depth of the pipeline: follows how long a batch's read-back takes against the period (see above)
     // (the shortest read-back seen so far counts: the others queued behind the copies of the batches that finished with them)
     if (d2h_ms > 0 && (best_d2h_ms == 0 || d2h_ms < best_d2h_ms)) best_d2h_ms = d2h_ms;
-    if (!depth_env && best_d2h_ms > 0 && last_period > 0) {
+    if (!depth_env && !depth_locked && best_d2h_ms > 0 && last_period > 0) {
       const double ratio = best_d2h_ms * 1e-3 / last_period;
       const int before = depth;
       if (ratio > 0.4) depth = MAX_DEPTH;
@@ -959,6 +967,19 @@ int hc_heic_decode_stream_ext(hc_engine* e, int nfiles, const uint8_t* const* da
     f.host_wait_s = host_wait;
     f.share = cur.share;
     f.rc = submit(cur.job, b, f);
+    while (flight.back().rc == HC_ERR_MEMORY && pin_failed && flight.size() > 1) {     // (`f` is not used below: the deque moves)
+      // no pinned memory for a buffer of its own: deliver the oldest batch, take over its buffer, and stay this shallow
+      pin_failed = false;
+      InFlight mine = std::move(flight.back());
+      flight.pop_back();
+      deliver(flight.front(), flight.front().rc);
+      flight.pop_front();
+      depth = std::max(2, (int)flight.size() + 1);
+      depth_locked = true;
+      flight.push_back(std::move(mine));
+      InFlight& again = flight.back();
+      again.rc = submit(cur.job, b, again);
+    }
     while ((int)flight.size() > depth - 1) { deliver(flight.front(), flight.front().rc); flight.pop_front(); }   // depth - 1 stay queued
   }
   while (!flight.empty()) { deliver(flight.front(), flight.front().rc); flight.pop_front(); }   // drain in submission order
