@@ -301,7 +301,7 @@ def measure_list(hb, eng, files, steps, warmup, threads, images, barrier, max_ov
 
     # an untimed call first: the engine pins its output buffers (1.3 s per 2.6 GB), fills its device pools and settles how
     # many batches it keeps in flight (3, or 6 when the read-back is slow); a service's later calls look like the timed one
-    hb.decode_stream(eng, files * (STREAM_DEPTH + 4), None, want_alpha=False, threads=threads, files_per_batch=images)
+    hb.decode_stream(eng, files * (STREAM_DEPTH + 10), None, want_alpha=False, threads=threads, files_per_batch=images)
     barrier()
     t_start = time.perf_counter()
     st = hb.decode_stream(eng, files * (2 * skip + 1 + e2e_steps), on_image, want_alpha=False, threads=threads, files_per_batch=images)

@@ -796,7 +796,9 @@ int hc_heic_decode_stream_ext(hc_engine* e, int nfiles, const uint8_t* const* da
   bool pinned_busy[MAX_DEPTH] = {};
   bool pin_failed = false, depth_locked = false;
   double last_period = 0;               // seconds between completions, smoothed (below)
-  double best_d2h_ms = 0;               // shortest read-back of a batch seen so far
+  double best_d2h_ms = 0;               // shortest read-back among the last six batches
+  double recent_d2h[6] = {0, 0, 0, 0, 0, 0};
+  int n_d2h = 0;
   double t_done[5] = {0, 0, 0, 0, 0};   // host time at which the last five batches were seen complete
   int rc = HC_OK;
   std::string err;
@@ -925,9 +927,14 @@ int hc_heic_decode_stream_ext(hc_engine* e, int nfiles, const uint8_t* const* da
     f.job = nullptr;
     if (f.slot >= 0) pinned_busy[f.slot] = false;
     // depth of the pipeline: follows how long a batch's read-back takes against the period (see above)
-    // (the shortest read-back seen so far counts: the others queued behind the copies of the batches that finished with them)
-    if (d2h_ms > 0 && (best_d2h_ms == 0 || d2h_ms < best_d2h_ms)) best_d2h_ms = d2h_ms;
-    if (!depth_env && !depth_locked && best_d2h_ms > 0 && last_period > 0) {
+    // (the shortest read-back among the last six batches counts: the others queued behind the copies of the batches that
+    // finished with them; a window, not the minimum of the whole call, so that one copy that met an idle link ages out)
+    if (d2h_ms > 0) {
+      recent_d2h[n_d2h++ % 6] = d2h_ms;
+      best_d2h_ms = recent_d2h[0];
+      for (int q = 1; q < std::min(n_d2h, 6); q++) best_d2h_ms = std::min(best_d2h_ms, recent_d2h[q]);
+    }
+    if (!depth_env && !depth_locked && n_d2h >= 3 && best_d2h_ms > 0 && last_period > 0) {
       const double ratio = best_d2h_ms * 1e-3 / last_period;
       const int before = depth;
       if (ratio > 0.4) depth = MAX_DEPTH;
